@@ -1,0 +1,166 @@
+/*
+ * sqrn.h -- C ABI of libsqrn_b200.so, the B200 (sm_100a) implementation of
+ * SQUARNA's greedy single-sequence hot path.
+ *
+ * The reference (febos/SQUARNA) is pure Python and has no FFI of its own; the
+ * seam this library replaces is
+ *
+ *   SQRNdbnseq.py:1076-1085  BPMatrix (+ alignment weighting)
+ *   SQRNdbnseq.py:1102-1199  the "G" block: pool loop over OptimalStems
+ *                            (AnnotateStems 427-495, ScoreStems 607-751,
+ *                             ChooseStems 754-789)
+ *   SQRNdbnseq.py:1201-1236  dedupe, ScoreStruct 861-899, RankStructs 902-955,
+ *                            PairsToDBN 104-163, ConsensusStemSet 845-858
+ *   SQRNdbnali.py:86-101     YieldStems (BPMatrix + AnnotateStems only)
+ *
+ * batched over sequences x parameter sets.  The Python drivers in
+ * squarna_b200/ (SQRNdbnseq / RunSQRNdbnseq / SQRNdbnali / Predict / Main) call
+ * these entry points through ctypes; INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns 0 (SQRN_OK)
+ *     or a negative error class, sqrn_last_error() gives the message;
+ *   - the caller owns every buffer; the library never keeps caller pointers
+ *     after a call returns;
+ *   - a context belongs to one GPU and one host thread at a time (one process
+ *     or thread per GPU; ctypes releases the GIL during calls);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with SQRN_E_CUDA.
+ */
+#ifndef SQRN_H
+#define SQRN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQRN_ABI_VERSION 1
+
+#define SQRN_OK             0
+#define SQRN_E_BADARG      -1
+#define SQRN_E_CAPACITY    -2   /* an output buffer is too small; needed sizes are written back */
+#define SQRN_E_CUDA        -3
+#define SQRN_E_UNSUPPORTED -4
+
+#define SQRN_MAX_BPKEYS 32
+#define SQRN_MAX_LEN    16000    /* ungapped nucleotides per sequence */
+
+typedef struct sqrn_ctx sqrn_ctx;
+
+/* One parameter set of a .conf file (SQUARNA.py:15-77 ParseConfig; fields read
+ * at SQRNdbnseq.py:1050-1062).  bpweights keeps the dict order because later
+ * keys overwrite earlier ones in either orientation (SQRNdbnseq.py:282-284). */
+typedef struct {
+    int32_t n_bp;                          /* number of bpweights entries        */
+    uint8_t bp_keys[2 * SQRN_MAX_BPKEYS];  /* two symbols per entry ("GC", ...)  */
+    double  bp_vals[SQRN_MAX_BPKEYS];
+    double  suboptmax, suboptmin, suboptsteps;
+    double  minlen, minbpscore, minfinscorefactor;
+    double  bracketweight, distcoef, orderpenalty, loopbonus, maxstemnum;
+} sqrn_paramset;
+
+/* restraint classes, one byte per position (ParseRestraints, SQRNdbnseq.py:370-376) */
+#define SQRN_RC_UNPAIRED 1   /* '_' '+' */
+#define SQRN_RC_NOLEFT   2   /* '/'  : may not be the 3' partner (j) */
+#define SQRN_RC_NORIGHT  4   /* '\\' : may not be the 5' partner (i) */
+
+/* A CSR batch of ungapped sequences (what SQRNdbnseq.py:1004-1037 produces per
+ * sequence: upper-cased, T->U, gaps removed, restraints parsed).              */
+typedef struct {
+    int64_t        n_seqs;
+    const int64_t *offsets;      /* [n_seqs+1] into symbols / react_code / restr_class / cols */
+    const uint8_t *symbols;      /* raw ASCII; case and T/U are normalised by the library       */
+    /* reactivities: NULL = all 0.5 ("default reacts", SQRNdbnseq.py:273).  Else one
+     * code per position into react_values (distinct processed reactivities, <= 256). */
+    const uint8_t *react_code;
+    const double  *react_values;
+    int32_t        n_react_values;
+    int32_t        react_sum_compensated; /* builtin sum() over exact Python floats (CPython >= 3.12) */
+    /* restraints: both NULL = none */
+    const uint8_t *restr_class;  /* SQRN_RC_* flags per position */
+    const int64_t *rbp_offsets;  /* [n_seqs+1] into rbps (pairs) */
+    const int32_t *rbps;         /* (v, w) per restraint pair, v < w, local coordinates */
+    /* alignment weighting (SQRNdbnseq.py:1031-1034, 1084-1085): score *= smat[cols[i], cols[j]] */
+    const double  *smat;         /* [smat_L x smat_L] row-major or NULL */
+    int32_t        smat_L;
+    const int32_t *cols;         /* aligned column of every ungapped position */
+    /* flags of SQRNdbnseq (SQRNdbnseq.py:973-980) */
+    int32_t interchainonly, hardrest, rankbydiff;
+    int32_t poollim, conslim, max_structs;   /* max_structs: structures returned per sequence (<=0: all) */
+    int32_t rankby[3];
+    uint64_t priority_mask;      /* bit p: parameter set p has priority (RankStructs 912-913) */
+} sqrn_batch;
+
+/* Results, caller-allocated.  Sequence b owns structures
+ * [struct_offsets[b], struct_offsets[b+1]) in final rank order; structure k owns
+ * stems [stem_offsets[k], stem_offsets[k+1]) in selection order and N_b dbn
+ * bytes at dbn + dbn_offsets[k].  On SQRN_E_CAPACITY need_* say what to allocate. */
+typedef struct {
+    int64_t  cap_structs, cap_stems, cap_dbn;
+    int64_t *struct_offsets;     /* [n_seqs+1] */
+    double  *scores;             /* [cap_structs*3] total, struct, react, each round(x,3) (ScoreStruct 899) */
+    uint8_t *struct_is_int0;     /* [cap_structs] structscore is the int 0 (prints "0") */
+    uint64_t*psmask;             /* [cap_structs] parameter sets that produced the structure */
+    int32_t *n_total;            /* [n_seqs] structures found before truncation to max_structs */
+    int64_t *stem_offsets;       /* [cap_structs+1] */
+    int32_t *stems;              /* [cap_stems*3] i, j, len (outermost pair, length) */
+    int64_t *dbn_offsets;        /* [cap_structs] */
+    int8_t  *dbn;                /* [cap_dbn] 0 '.', +L opening bracket of level L, -L closing */
+    int8_t  *cons;               /* [total symbols] consensus of the top conslim structures */
+    int64_t  need_structs, need_stems, need_dbn;
+} sqrn_result;
+
+/* stems of one AnnotateStems pass per sequence (YieldStems, SQRNdbnali.py:60-108) */
+typedef struct {
+    int64_t  cap_stems;
+    int64_t *stem_offsets;       /* [n_seqs+1] */
+    int32_t *stems;              /* [cap_stems*3] i, j, len in UNGAPPED coordinates, reference order */
+    double  *scores;             /* [cap_stems] bp score */
+    int64_t  need_stems;
+} sqrn_stems;
+
+int  sqrn_abi_version(void);
+int  sqrn_device_count(void);                 /* 0 when no CUDA device is usable */
+int  sqrn_ctx_create(int device, sqrn_ctx **out);
+void sqrn_ctx_destroy(sqrn_ctx *ctx);
+const char *sqrn_last_error(const sqrn_ctx *ctx);   /* ctx may be NULL: last create error */
+
+/* Use an externally owned CUDA stream (cudaStream_t as void*) for all work of
+ * this context, e.g. torch.cuda.current_stream().cuda_stream.                 */
+int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
+
+/* The full "G" path for a batch: replaces SQRNdbnseq.py:1048-1246 (algos == {"G"},
+ * bpp == 0).  Host buffers in, host buffers out.                              */
+int  sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps,
+                        const sqrn_batch *in, sqrn_result *out);
+
+/* Enumeration only: replaces SQRNdbnali.py:86-101 for a batch.                 */
+int  sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps,
+                            const sqrn_batch *in, sqrn_stems *out);
+
+/* ---- single-path fast lane (poollim == 1: `byseq pl=1`, SQUARNA.py:887-935) --
+ * One parameter set, default reactivities, no restraints: one structure per
+ * sequence, written as ASCII dot-bracket.  `symbols`/`offsets`/outputs are HOST
+ * pointers for sqrn_fast_predict_host and DEVICE pointers for
+ * sqrn_fast_predict_device (inputs already resident in HBM; asynchronous on the
+ * context's stream).  scores: 3 doubles per sequence, rounded as round(x,3) by
+ * the host variant and raw (thescore, reactscore, total) by the device variant. */
+int  sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps,
+                            int64_t n_seqs, const int64_t *offsets, const uint8_t *symbols,
+                            uint8_t *dbn_ascii, double *scores, int32_t *n_stems);
+int  sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps,
+                              int64_t n_seqs, int64_t total_len, int32_t max_len,
+                              const int64_t *d_offsets, const uint8_t *d_symbols,
+                              uint8_t *d_dbn_ascii, double *d_scores, int32_t *d_n_stems);
+
+/* counters of the last call: kernels launched, device milliseconds of the main kernel */
+int  sqrn_ctx_last_stats(const sqrn_ctx *ctx, int64_t *n_launches, double *kernel_ms,
+                         int64_t *n_optimal_calls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQRN_H */

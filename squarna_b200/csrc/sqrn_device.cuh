@@ -1,0 +1,958 @@
+// sqrn_device.cuh -- device side of libsqrn_b200: the greedy stem-selection
+// hot path of SQUARNA on sm_100a.
+//
+// What the reference does per OptimalStems call (SQRNdbnseq.py:792-833) with two
+// dense N x N float64 matrices, this code does from per-symbol bit masks held in
+// shared memory; no matrix is ever written to HBM:
+//
+//   pairability (BPMatrix, seq.py:258-339)   = AND of a forward mask of symbol c
+//       with the REVERSED mask of c's partners, shifted so that bit i lines up
+//       with j = s - i on anti-diagonal s = i + j;
+//   stems (AnnotateStems, seq.py:427-495)    = maximal runs of set bits, found
+//       with ctz/funnel-shift word tricks, outermost cell first;
+//   ScoreStems (seq.py:607-751)              = per-candidate scan of the region
+//       confined by the innermost pair, pow() terms from host-built tables;
+//   ChooseStems (seq.py:754-789)             = team-wide arg-max with the key
+//       (score desc, i+j asc, i asc), which is the order the reference's stable
+//       sort leaves ties in.
+//
+// A "team" is the group of threads that owns one (sequence, partial structure)
+// work item: one warp for short sequences, one CTA for long ones.
+#pragma once
+#include <stdint.h>
+#ifndef SQRN_HOST_EMU
+#include <cuda_runtime.h>
+#else
+// Single-thread "team" build used only by tests/emu (g++): the same device
+// functions with T = 1, so the bit tricks and scoring logic can be debugged
+// against the oracle on a box without a GPU.  Never part of libsqrn_b200.so.
+#include <math.h>
+#include <string.h>
+#define __CUDACC__ 1
+#define __device__
+#define __host__
+#define __forceinline__ inline
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+static inline uint32_t atomicAnd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p &= v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+#endif
+
+namespace sqrn {
+
+constexpr int MAXK  = 16;   // symbol codes
+constexpr int MAXPC = 8;    // codes that can pair (have masks)
+constexpr int CODE_A = 0, CODE_C = 1, CODE_G = 2, CODE_U = 3, CODE_SEP = 4, CODE_OTHER = 5;
+
+constexpr int RC_X = 1, RC_NOLEFT = 2, RC_NORIGHT = 4, RC_RBPOS = 8;
+
+constexpr int MODE_TAIL = 0;   // run the single-path greedy to completion
+constexpr int MODE_STEP = 1;   // one OptimalStems call, return the ChooseStems list
+constexpr int MODE_YIELD = 2;  // AnnotateStems only, stems in reference order
+
+// ---------------------------------------------------------------- parameters
+struct DevParams {
+    int      K, npc;
+    int      pc_code[MAXPC];        // symbol code of pairing slot c
+    uint32_t pairmask[MAXK];        // bit d: code pairs with code d
+    double   weight[MAXK * MAXK];
+    int      m;                     // prefilter run length = clamp(ceil(minlen), 1, 32)
+    double   minlen, minbpscore, minfinscore, loopbonus, maxstemnum, bracketweight;
+    int      bw_is_int, bw_int;
+    double   distcoef, orderpenalty;
+    const double *sdf_lut; int sdf_n;    // (1/(1+k))**distcoef      seq.py:726
+    const double *of_lut;  int of_n;     // (1/(1+o))**orderpenalty  seq.py:729
+    const double *pw17_lut; int pw17_n;  // (0.5k)**1.7              seq.py:884
+    uint8_t  code_table[256];
+};
+
+struct DevBatch {
+    int64_t        n_seqs;
+    const int64_t *off;
+    const uint8_t *sym;
+    const uint8_t *rcode;  const double *rf_pos; const double *rf_neg; const double *rvals; int R;
+    int            react_comp;
+    const uint8_t *rclass; const int64_t *rbp_off; const int32_t *rbp;
+    const double  *smat;   int L;  const int32_t *cols;
+    int            interchainonly;
+};
+
+struct DevWork {
+    int            n_items;
+    int            mode;
+    const int32_t *order;        // processing order (item ids), NULL = identity
+    const int32_t *item_seq;     // item -> sequence, NULL = identity
+    const int64_t *init_off;     // [n_items+1] CSR of initial stems, NULL = none
+    const int32_t *init_stems;   // i, j, len
+    const double  *item_subopt;  // MODE_STEP: cursubopt per item
+    int           *counter;      // global work counter (zeroed before launch)
+    // outputs
+    const int64_t *out_off;      // [n_items+1] capacity CSR for stems
+    int32_t       *out_stems;    // i, j, len
+    int32_t       *out_nstems;   // TAIL: total stems; STEP: number of chosen stems
+    double        *out_stemfin;  // optional: adjusted score per output stem
+    double        *out_raw;      // TAIL: thescore*reactscore, thescore, reactscore per item (unrounded)
+    uint8_t       *out_flags;    // bit0 struct_is_int0, bit1 level overflow, bit2 capacity overflow
+    const int64_t *dbn_off;      // [n_items] offset of the item's dbn
+    uint8_t       *out_dbn_ascii;
+    int8_t        *out_dbn_code;
+    unsigned long long *n_calls; // OptimalStems-equivalent calls performed
+};
+
+// -------------------------------------------------------------- smem layout
+struct Layout {
+    int Ncap, W, WR, Scap, RBcap, Ccap, npc;
+    int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR,
+        o_sti, o_stj, o_stl, o_stlev, o_cc, o_perm, o_grp, o_gsz, o_rbv, o_rbw,
+        o_ckey, o_clen, o_cbps, o_cfin, o_red, o_misc, total;
+};
+
+__host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline Layout make_layout(int Nmax, int RBmax, int Ccap, int npc, int tw)
+{
+    Layout L;
+    L.Ncap = align_up(Nmax > 0 ? Nmax : 1, 32);
+    L.W = L.Ncap / 32;
+    L.WR = L.W + 3;
+    L.Scap = L.Ncap / 2 + 1;
+    L.RBcap = RBmax;
+    L.Ccap = Ccap;
+    L.npc = npc;
+    int o = 0;
+    L.o_cbps = o;    o += 8 * Ccap;                       // doubles first (8-byte aligned)
+    L.o_cfin = o;    o += 8 * Ccap;
+    L.o_red = o;     o += (tw > 1) ? 32 * tw : 0;        // cross-warp reduction scratch
+    L.o_misc = o;    o += 64;
+    L.o_M = o;       o += 4 * npc * L.W;
+    L.o_PR = o;      o += 4 * npc * L.WR;
+    L.o_rowok = o;   o += 4 * L.W;
+    L.o_colokR = o;  o += 4 * L.WR;
+    L.o_cc = o;      o += 4 * L.Scap;
+    L.o_gsz = o;     o += 4 * L.Scap;
+    L.o_ckey = o;    o += 4 * Ccap;
+    L.o_partner = o; o += 2 * L.Ncap;
+    L.o_owner = o;   o += 2 * L.Ncap;
+    L.o_sepcnt = o;  o += 2 * (L.Ncap + 2);
+    L.o_sti = o;     o += 2 * L.Scap;
+    L.o_stj = o;     o += 2 * L.Scap;
+    L.o_stl = o;     o += 2 * L.Scap;
+    L.o_perm = o;    o += 2 * L.Scap;
+    L.o_grp = o;     o += 2 * L.Scap;
+    L.o_rbv = o;     o += 2 * (RBmax + 1);
+    L.o_rbw = o;     o += 2 * (RBmax + 1);
+    L.o_clen = o;    o += 2 * Ccap;
+    L.o_code = o;    o += L.Ncap;
+    L.o_rcode = o;   o += L.Ncap;
+    L.o_rcl = o;     o += L.Ncap;
+    L.o_stlev = o;   o += L.Scap;
+    L.total = align_up(o, 16);
+    return L;
+}
+
+#ifdef __CUDACC__
+
+struct Best {
+    double   fin;
+    double   bps;
+    uint32_t key;     // (i+j) << 16 | i : smaller = earlier in the reference's enumeration order
+    int      len;
+};
+
+__device__ __forceinline__ bool better(double fa, uint32_t ka, double fb, uint32_t kb)
+{
+    return fa > fb || (fa == fb && ka < kb);
+}
+
+// ------------------------------------------------------------------- team
+// TW == 1: one warp per work item, several teams per CTA.
+// TW  > 1: the whole CTA (TW warps) is one team.
+// TW == 0: a single thread (host emulation build only).
+template <int TW> struct Team {
+    static constexpr int T = TW * 32;
+#ifndef SQRN_HOST_EMU
+    __device__ static __forceinline__ int rank() { return TW == 1 ? (threadIdx.x & 31) : threadIdx.x; }
+    __device__ static __forceinline__ void sync()
+    {
+        if (TW == 1) __syncwarp(); else __syncthreads();
+    }
+#endif
+};
+#ifdef SQRN_HOST_EMU
+template <> struct Team<0> {
+    static constexpr int T = 1;
+    static inline int rank() { return 0; }
+    static inline void sync() {}
+};
+#endif
+
+struct State {
+    int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts;
+    uint8_t  *code, *rcode, *rcl, *stlev;
+    int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *perm, *grp, *rbv, *rbw;
+    uint32_t *M, *PR, *rowok, *colokR, *ckey;
+    int32_t  *cc, *gsz;
+    uint16_t *clen;
+    double   *cbps, *cfin, *red;
+    int      *misc;      // [0] candidate count  [1] next item  [2..] scratch
+    const int32_t *cols; // global, per sequence
+};
+
+__device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L)
+{
+    State s;
+    s.code = base + L.o_code;  s.rcode = base + L.o_rcode;  s.rcl = base + L.o_rcl;  s.stlev = base + L.o_stlev;
+    s.partner = (int16_t *)(base + L.o_partner);  s.owner = (int16_t *)(base + L.o_owner);
+    s.sepcnt = (int16_t *)(base + L.o_sepcnt);
+    s.sti = (int16_t *)(base + L.o_sti);  s.stj = (int16_t *)(base + L.o_stj);  s.stl = (int16_t *)(base + L.o_stl);
+    s.perm = (int16_t *)(base + L.o_perm);  s.grp = (int16_t *)(base + L.o_grp);
+    s.rbv = (int16_t *)(base + L.o_rbv);  s.rbw = (int16_t *)(base + L.o_rbw);
+    s.M = (uint32_t *)(base + L.o_M);  s.PR = (uint32_t *)(base + L.o_PR);
+    s.rowok = (uint32_t *)(base + L.o_rowok);  s.colokR = (uint32_t *)(base + L.o_colokR);
+    s.ckey = (uint32_t *)(base + L.o_ckey);
+    s.cc = (int32_t *)(base + L.o_cc);  s.gsz = (int32_t *)(base + L.o_gsz);
+    s.clen = (uint16_t *)(base + L.o_clen);
+    s.cbps = (double *)(base + L.o_cbps);
+    s.cfin = (double *)(base + L.o_cfin);
+    s.red = (double *)(base + L.o_red);
+    s.misc = (int *)(base + L.o_misc);
+    s.W = L.W; s.WR = L.WR;
+    s.N = 0; s.nst = 0; s.nrb = 0; s.has_sep = 0; s.has_react = 0; s.has_smat = 0; s.default_reacts = 1;
+    s.cols = nullptr;
+    return s;
+}
+
+// minimum hairpin rule, seq.py:293-297: j >= i + inc4(i)
+__device__ __forceinline__ int inc4_of(const State &S, int i)
+{
+    int inc = 4;
+    if (i + 1 < S.N && S.code[i + 1] == CODE_SEP) inc = 2;
+    if (i + 2 < S.N && S.code[i + 2] == CODE_SEP) inc = 3;
+    return inc;
+}
+
+// ------------------------------------------------------------- load a sequence
+template <int TW>
+__device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int seq)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const int64_t o = B.off[seq];
+    const int N = (int)(B.off[seq + 1] - o);
+    S.N = N; S.nst = 0;
+    S.has_react = B.rcode != nullptr;
+    S.has_smat = B.smat != nullptr;
+    S.cols = B.cols ? B.cols + o : nullptr;
+    const int Nw = S.W * 32;
+    for (int p = r; p < Nw; p += T) {
+        uint8_t c = CODE_OTHER, rc = 0, cl = 0;
+        if (p < N) {
+            c = P.code_table[B.sym[o + p]];
+            if (B.rcode) rc = B.rcode[o + p];
+            if (B.rclass) cl = B.rclass[o + p] & 7;
+        }
+        S.code[p] = c; S.rcode[p] = rc; S.rcl[p] = cl;
+        S.partner[p] = -1; S.owner[p] = -1;
+    }
+    Team<TW>::sync();
+    // restraint pairs (sorted by (v+w, v) by the host); mark their positions
+    int nrb_all = 0;
+    const int32_t *rb = nullptr;
+    if (B.rbp_off) { nrb_all = (int)(B.rbp_off[seq + 1] - B.rbp_off[seq]); rb = B.rbp + 2 * B.rbp_off[seq]; }
+    for (int k = r; k < nrb_all; k += T) {
+        S.rcl[rb[2 * k]] |= RC_RBPOS;       // distinct positions: no write conflicts on the same byte
+        S.rcl[rb[2 * k + 1]] |= RC_RBPOS;
+    }
+    // prefix count of separators (thread 0; N is small and this runs once per item)
+    if (r == 0) {
+        int c = 0, hs = 0;
+        for (int p = 0; p < N; p++) { S.sepcnt[p] = (int16_t)c; if (S.code[p] == CODE_SEP) { c++; hs = 1; } }
+        S.sepcnt[N] = (int16_t)c;
+        S.misc[2] = hs;
+        // statically valid restraint cells: boolmat[v,w] != 0 (seq.py:443) and on a walked diagonal
+        int n = 0;
+        for (int k = 0; k < nrb_all; k++) {
+            int v = rb[2 * k], w = rb[2 * k + 1], s = v + w;
+            if (s < 4 || s > 2 * N - 6) continue;
+            if (!(P.pairmask[S.code[v]] >> S.code[w] & 1)) continue;
+            int inc = 4;
+            if (v + 1 < N && S.code[v + 1] == CODE_SEP) inc = 2;
+            if (v + 2 < N && S.code[v + 2] == CODE_SEP) inc = 3;
+            if (w < v + inc) continue;
+            if (B.interchainonly && S.sepcnt[w] - S.sepcnt[v] <= 0) continue;
+            S.rbv[n] = (int16_t)v; S.rbw[n] = (int16_t)w; n++;
+        }
+        S.misc[3] = n;
+        // "default reacts" switch, seq.py:273: every processed reactivity == 0.5
+        int dflt = 1;
+        if (B.rcode) for (int p = 0; p < N; p++) if (B.rvals[S.rcode[p]] != 0.5) { dflt = 0; break; }
+        S.misc[4] = dflt;
+    }
+    Team<TW>::sync();
+    S.has_sep = S.misc[2]; S.nrb = S.misc[3]; S.default_reacts = S.misc[4];
+    // forward masks of each pairing symbol, reversed masks of its partners
+    for (int idx = r; idx < P.npc * S.W; idx += T) {
+        int c = idx / S.W, k = idx - c * S.W, code = P.pc_code[c];
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++) if (S.code[32 * k + b] == code && 32 * k + b < N) m |= 1u << b;
+        S.M[c * S.W + k] = m;
+    }
+    for (int idx = r; idx < P.npc * S.WR; idx += T) {
+        int c = idx / S.WR, k = idx - c * S.WR;
+        uint32_t pm = P.pairmask[P.pc_code[c]], m = 0;
+        for (int b = 0; b < 32; b++) {
+            int j = N - 1 - (32 * k + b - 32);
+            if (j >= 0 && j < N && (pm >> S.code[j] & 1)) m |= 1u << b;
+        }
+        S.PR[c * S.WR + k] = m;
+    }
+    for (int k = r; k < S.W; k += T) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++) {
+            int p = 32 * k + b;
+            if (p < N && !(S.rcl[p] & (RC_X | RC_NORIGHT | RC_RBPOS))) m |= 1u << b;
+        }
+        S.rowok[k] = m;
+    }
+    for (int k = r; k < S.WR; k += T) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++) {
+            int j = N - 1 - (32 * k + b - 32);
+            if (j >= 0 && j < N && !(S.rcl[j] & (RC_X | RC_NOLEFT | RC_RBPOS))) m |= 1u << b;
+        }
+        S.colokR[k] = m;
+    }
+    Team<TW>::sync();
+}
+
+// add a selected stem to the structure: partners, owner, row/column masks
+// (AnnotateStems zeroes the rows and columns of every selected position, seq.py:446-451)
+template <int TW>
+__device__ void team_apply_stem(State &S, int i, int j, int len)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const int idx = S.nst;
+    for (int k = r; k < len; k += T) {
+        int v = i + k, w = j - k;
+        S.partner[v] = (int16_t)w; S.partner[w] = (int16_t)v;
+        S.owner[v] = (int16_t)idx; S.owner[w] = (int16_t)idx;
+        atomicAnd(&S.rowok[v >> 5], ~(1u << (v & 31)));
+        atomicAnd(&S.rowok[w >> 5], ~(1u << (w & 31)));
+        int rv = 32 + S.N - 1 - v, rw = 32 + S.N - 1 - w;
+        atomicAnd(&S.colokR[rv >> 5], ~(1u << (rv & 31)));
+        atomicAnd(&S.colokR[rw >> 5], ~(1u << (rw & 31)));
+    }
+    if (r == 0) { S.sti[idx] = (int16_t)i; S.stj[idx] = (int16_t)j; S.stl[idx] = (int16_t)len; }
+    S.nst = idx + 1;
+    Team<TW>::sync();
+}
+
+// ------------------------------------------------ pseudoknot levels per stem
+// PairsToDBN(returnlevels=True), seq.py:119-150, restated per STEM: two
+// position-disjoint stems cross all-or-none, so the crossing test runs on the
+// outermost pairs, cross_count is the summed length of the crossing stems, the
+// first-fit order is (cross_count, outer i) and groups are ranked by their
+// number of pairs (stable).  tests/test_levels.py checks this against the
+// oracle's per-pair restatement.
+__device__ __forceinline__ bool stems_cross(int i, int j, int k, int l)
+{
+    return (i < k && k < j && j < l) || (k < i && i < l && l < j);
+}
+
+template <int TW>
+__device__ int team_levels(State &S)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const int n = S.nst;
+    if (n == 0) return 0;
+    for (int t = r; t < n; t += T) {
+        int i = S.sti[t], j = S.stj[t], c = 0;
+        for (int u = 0; u < n; u++)
+            if (u != t && stems_cross(i, j, S.sti[u], S.stj[u])) c += S.stl[u];
+        S.cc[t] = c;
+    }
+    Team<TW>::sync();
+    for (int t = r; t < n; t += T) {
+        int c = S.cc[t], i = S.sti[t], rank = 0;
+        for (int u = 0; u < n; u++) {
+            int cu = S.cc[u];
+            if (cu < c || (cu == c && S.sti[u] < i)) rank++;
+        }
+        S.perm[rank] = (int16_t)t;
+    }
+    Team<TW>::sync();
+    if (r == 0) {
+        int ng = 0;
+        for (int a = 0; a < n; a++) {
+            int t = S.perm[a], g = -1;
+            if (S.cc[t] == 0) {
+                g = 0;                                 // crosses nothing: fits the first group
+                if (ng == 0) { ng = 1; S.gsz[0] = 0; }
+            } else {
+                int i = S.sti[t], j = S.stj[t];
+                for (int h = 0; h < ng && g < 0; h++) {
+                    bool clash = false;
+                    for (int b = 0; b < a && !clash; b++) {
+                        int u = S.perm[b];
+                        if (S.grp[u] == h && stems_cross(i, j, S.sti[u], S.stj[u])) clash = true;
+                    }
+                    if (!clash) g = h;
+                }
+                if (g < 0) { g = ng++; S.gsz[g] = 0; }
+            }
+            S.grp[t] = (int16_t)g;
+            S.gsz[g] += S.stl[t];
+        }
+        // groups.sort(key=len, reverse=True) is stable: level = 1 + #groups that come first
+        for (int t = 0; t < n; t++) {
+            int g = S.grp[t], sz = S.gsz[g], lev = 1;
+            for (int h = 0; h < ng; h++)
+                if (S.gsz[h] > sz || (S.gsz[h] == sz && h < g)) lev++;
+            S.stlev[t] = (uint8_t)(lev > 255 ? 255 : lev);
+        }
+        S.misc[5] = ng;
+    }
+    Team<TW>::sync();
+    return S.misc[5];
+}
+
+// ------------------------------------------------------------ cell score
+// scoremat[i,j] of BPMatrix (seq.py:329-338), times the alignment weight
+// (seq.py:1084-1085).  Only called for cells of candidate stems.
+__device__ __forceinline__ double cell_score(const State &S, const DevParams &P, const DevBatch &B, int i, int j)
+{
+    double w = P.weight[S.code[i] * MAXK + S.code[j]];
+    if (S.has_react && !S.default_reacts) {
+        int a = S.rcode[i], b = S.rcode[j];
+        double rf = (w <= 0.0) ? __ldg(&B.rf_neg[a * B.R + b]) : __ldg(&B.rf_pos[a * B.R + b]);
+        w = __dmul_rn(w, rf);
+    }
+    if (S.has_smat) w = __dmul_rn(w, __ldg(&B.smat[(int64_t)S.cols[i] * B.L + S.cols[j]]));
+    return w;
+}
+
+// ---------------------------------------------------- one word of a diagonal
+// bit t of the result: cell (i = 32k + t, j = s - i) is a live base pair of the
+// masked bool matrix AnnotateStems walks (seq.py:431-451), restricted to the
+// walked range lo <= i <= hi of the diagonal.
+__device__ __forceinline__ uint32_t diag_word(const State &S, const DevParams &P, int s, int k, int lo, int hi)
+{
+    const int bo = 32 * k + (S.N - 1 - s) + 32;     // bit offset into the reversed arrays
+    const int wo = bo >> 5, sh = bo & 31;
+    uint32_t x = 0;
+    #pragma unroll 4
+    for (int c = 0; c < P.npc; c++) {
+        uint32_t f = S.M[c * S.W + k];
+        uint32_t g = __funnelshift_r(S.PR[c * S.WR + wo], S.PR[c * S.WR + wo + 1], sh);
+        x |= f & g;
+    }
+    x &= S.rowok[k] & __funnelshift_r(S.colokR[wo], S.colokR[wo + 1], sh);
+    // range mask
+    int b0 = lo - 32 * k, b1 = hi - 32 * k;
+    if (b0 > 0) x &= (b0 >= 32) ? 0u : (0xffffffffu << b0);
+    if (b1 < 31) x &= (b1 < 0) ? 0u : (0xffffffffu >> (31 - b1));
+    // remaining restraint pairs keep their own cell (seq.py:443) if both ends are still free
+    if (S.nrb) {
+        int a = 0, b = S.nrb;
+        while (a < b) { int mid = (a + b) >> 1; if (S.rbv[mid] + S.rbw[mid] < s) a = mid + 1; else b = mid; }
+        for (; a < S.nrb && S.rbv[a] + S.rbw[a] == s; a++) {
+            int v = S.rbv[a];
+            if ((v >> 5) == k && S.partner[v] < 0 && S.partner[S.rbw[a]] < 0) x |= 1u << (v & 31);
+        }
+    }
+    return x;
+}
+
+// walked range of diagonal s: lo..hi (inclusive) in i; false if empty
+__device__ __forceinline__ bool diag_range(const State &S, const DevBatch &B, int s, int &lo, int &hi)
+{
+    const int N = S.N;
+    lo = s - (N - 1); if (lo < 0) lo = 0;
+    hi = (s - 4) >> 1;
+    if (S.has_sep) {
+        // innermost extra cell with j - i in {2, 3} when a separator follows i (seq.py:293-297)
+        int i1 = hi + 1, d = s - 2 * i1;
+        if (i1 >= lo && d >= 2 && inc4_of(S, i1) <= d) hi = i1;
+        if (B.interchainonly) {
+            // chains differ iff a separator lies between i and j; the set of such cells is a prefix
+            if (S.sepcnt[s - lo] - S.sepcnt[lo] <= 0) return false;
+            int a = lo, b = hi;          // largest i in [lo, hi] with a separator in (i, s-i)
+            while (a < b) {
+                int mid = (a + b + 1) >> 1;
+                if (S.sepcnt[s - mid] - S.sepcnt[mid] > 0) a = mid; else b = mid - 1;
+            }
+            hi = a;
+        }
+    } else if (B.interchainonly) return false;
+    return hi >= lo;
+}
+
+// ------------------------------------------------------------- ScoreStems
+// adjusted score of candidate (outer pair (a, s-a), length len, raw score bps)
+// given the current structure; seq.py:641-745.
+__device__ double score_candidate(const State &S, const DevParams &P, int s, int a, int len, double bps)
+{
+    const int N = S.N;
+    const int oi = a, oj = s - a;
+    const int ss = a + len - 1, se = oj - len + 1;    // innermost pair, seq.py:655
+    int dots = 0, br = 0, nedges = 0, e0 = -1, e1 = -1, inblockend = -1;
+    bool between = false;
+    unsigned long long levmask = 0;
+    if (S.nst == 0) {
+        dots = se - ss - 1;
+        between = S.has_sep && (S.sepcnt[se] - S.sepcnt[ss + 1] > 0);
+    } else {
+        for (int pos = ss + 1; pos < se; pos++) {         // seq.py:665-689
+            int pr = S.partner[pos];
+            if (pr < 0) {
+                if (pos > inblockend) dots++;
+                if (S.code[pos] == CODE_SEP) between = true;
+            } else if (pr < ss || pr > se) {
+                if (pos > inblockend) {
+                    br++;
+                    int lv = S.stlev[S.owner[pos]];
+                    levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
+                }
+            } else if (pos < pr && pr > inblockend) {
+                inblockend = pr;
+                if (nedges == 0) { e0 = pos; e1 = pr; }
+                nedges++;
+            }
+        }
+    }
+    // good loops = {0..4}^2 with |x - y| <= 2 (the 19 entries of seq.py:615-622)
+    bool goodloop = false; int diff1 = 0;
+    if (nedges == 1) {
+        int x = e0 - ss - 1, y = se - e1 - 1, d = x > y ? x - y : y - x;
+        if (x <= 4 && y <= 4 && d <= 2) { goodloop = true; diff1 = d; }
+    }
+    bool goodout = false; int diff2 = 0;
+    if (S.nst) {                                           // seq.py:700-711
+        int vv = oi - 1, ww = oj + 1;
+        while (vv >= 0 && oi - vv - 1 < 5 && S.partner[vv] < 0) vv--;
+        while (ww < N && ww - oj - 1 < 5 && S.partner[ww] < 0) ww++;
+        if (vv >= 0 && ww < N && S.partner[vv] == ww) {
+            int x = oi - vv - 1, y = ww - oj - 1, d = x > y ? x - y : y - x;
+            if (x <= 4 && y <= 4 && d <= 2) { goodout = true; diff2 = d; }
+        }
+    }
+    if (!goodloop && !goodout && len < 3) return -1.0;     // seq.py:744-745
+    // loopfactor, seq.py:715 (left to right, no contraction)
+    double lf = __dadd_rn(1.0, __dmul_rn(__dmul_rn(P.loopbonus, goodloop ? 1.0 : 0.0), 2.0 - diff1 * 0.5));
+    lf = __dadd_rn(lf, __dmul_rn(__dmul_rn(P.loopbonus, goodout ? 1.0 : 0.0), 2.0 - diff2 * 0.5));
+    // tetraloop bonus, seq.py:598-604, 718
+    double tf = 1.0;
+    if (se - ss - 1 == 4 && S.code[ss + 1] == CODE_G &&
+        (S.code[ss + 3] == CODE_G || S.code[ss + 3] == CODE_A) && S.code[ss + 4] == CODE_A) tf = 1.25;
+    // stem distance factor, seq.py:721-726
+    double sdf = 1.0;
+    if (!between) {
+        int ideal = inblockend == -1 ? 4 : 2;
+        if (P.bw_is_int) {
+            int k = dots + P.bw_int * br - ideal; if (k < 0) k = -k;
+            sdf = (k < P.sdf_n) ? __ldg(&P.sdf_lut[k]) : pow(1.0 / (1.0 + (double)k), P.distcoef);
+        } else {
+            double x = fabs(__dadd_rn((double)dots, __dmul_rn(P.bracketweight, (double)br)) - (double)ideal);
+            sdf = pow(1.0 / (1.0 + x), P.distcoef);        // documented <= 1 ulp deviation
+        }
+    }
+    int order = __popcll(levmask);
+    double of = (order < P.of_n) ? __ldg(&P.of_lut[order]) : pow(1.0 / (1.0 + order), P.orderpenalty);
+    // seq.py:732
+    double fin = __dmul_rn(bps, sdf);
+    fin = __dmul_rn(fin, of);
+    fin = __dmul_rn(fin, lf);
+    fin = __dmul_rn(fin, tf);
+    return fin;
+}
+
+// ---------------------------------------------------- enumerate one diagonal
+// calls emit(a, e) for every maximal run [a, e] (in i) of at least P.m cells, in
+// increasing a: outermost stem first, the order of seq.py:486-493.
+template <class F>
+__device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, const DevBatch &B, int s, F &&emit)
+{
+    int lo, hi;
+    if (!diag_range(S, B, s, lo, hi)) return;
+    const int k0 = lo >> 5, k1 = hi >> 5;
+    const int m = P.m;
+    uint32_t x = diag_word(S, P, s, k0, lo, hi);
+    uint32_t prev_top = 0;
+    int skip_until = -1;                   // runs already emitted extend up to here
+    for (int k = k0; k <= k1; k++) {
+        uint32_t xn = (k < k1) ? diag_word(S, P, s, k + 1, lo, hi) : 0u;
+        if (x) {
+            uint32_t y = x;
+            for (int t = 1; t < m; t++) y &= __funnelshift_r(x, xn, t);
+            uint32_t starts = y & ~((x << 1) | prev_top);
+            while (starts) {
+                int b = __ffs(starts) - 1;
+                starts &= starts - 1;
+                int a = 32 * k + b;
+                if (a <= skip_until) continue;
+                // find the end of the run
+                int e;
+                uint32_t inv = ~(x >> b);            // bit 0 is 0; first set bit = run length
+                int t = inv ? __ffs(inv) - 1 : 32;
+                if (b + t < 32) e = a + t - 1;
+                else {
+                    int kk = k + 1; uint32_t w = xn;
+                    while (kk <= k1 && w == 0xffffffffu) { kk++; w = (kk <= k1) ? diag_word(S, P, s, kk, lo, hi) : 0u; }
+                    e = (kk <= k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (k1 + 1) - 1;
+                    if (e > hi) e = hi;
+                }
+                skip_until = e;
+                emit(a, e);
+            }
+        }
+        prev_top = x >> 31;
+        x = xn;
+    }
+}
+
+// -------------------------------------------- one OptimalStems pass (arg-max)
+// team-wide reductions --------------------------------------------------------
+template <int TW>
+__device__ __forceinline__ Best team_argmax(State &S, Best best)
+{
+#ifndef SQRN_HOST_EMU
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        double f = __shfl_xor_sync(0xffffffffu, best.fin, d);
+        double bp = __shfl_xor_sync(0xffffffffu, best.bps, d);
+        uint32_t k = __shfl_xor_sync(0xffffffffu, best.key, d);
+        int l = __shfl_xor_sync(0xffffffffu, best.len, d);
+        if (better(f, k, best.fin, best.key)) { best.fin = f; best.key = k; best.len = l; best.bps = bp; }
+    }
+    if (TW > 1) {
+        // cross-warp through the (now idle) scratch words of the team
+        double *sd = S.red;                              // 2 doubles + 2 words per warp
+        uint32_t *sk = (uint32_t *)(S.red + 2 * TW);
+        __syncthreads();
+        int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { sd[2 * w] = best.fin; sd[2 * w + 1] = best.bps; sk[2 * w] = best.key; sk[2 * w + 1] = (uint32_t)best.len; }
+        __syncthreads();
+        Best b2; b2.fin = -1e300; b2.key = 0xffffffffu; b2.len = 0; b2.bps = 0.0;
+        for (int q = 0; q < TW; q++) {
+            double f = sd[2 * q]; uint32_t k = sk[2 * q];
+            if (better(f, k, b2.fin, b2.key)) { b2.fin = f; b2.key = k; b2.len = (int)sk[2 * q + 1]; b2.bps = sd[2 * q + 1]; }
+        }
+        best = b2;
+        __syncthreads();
+    }
+#endif
+    return best;
+}
+
+// Enumerates every candidate stem of the current structure (AnnotateStems),
+// scores it (ScoreStems) and returns the team-wide best survivor: the head of
+// ChooseStems' stable sort.  fin = -1e300 when nothing reaches minfinscore.
+// Candidates are first pushed to a shared list so that the region scans are
+// spread over the whole team; candidates beyond the list capacity are scored by
+// the thread that found them.  On return cfin[c] holds the adjusted score of
+// list entry c (-1e300 if it failed minfinscore) and misc[0] the number of
+// candidates found (may exceed Ccap).
+template <int TW>
+__device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0; best.bps = 0.0;
+    if (r == 0) S.misc[0] = 0;
+    Team<TW>::sync();
+    const int smax = 2 * S.N - 6;
+    for (int s = 4 + r; s <= smax; s += T) {
+        enum_diag(S, P, B, s, [&](int a, int e) {
+            int len = e - a + 1;
+            if ((double)len < P.minlen) return;
+            double sc = 0.0;                      // Python sum(): left to right from 0 (seq.py:416)
+            for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
+            if (!(sc >= P.minbpscore)) return;
+            int slot = atomicAdd(&S.misc[0], 1);
+            uint32_t key = ((uint32_t)s << 16) | (uint32_t)a;
+            if (slot < L.Ccap) {
+                S.ckey[slot] = key;
+                S.clen[slot] = (uint16_t)len;
+                S.cbps[slot] = sc;
+            } else {
+                double fin = score_candidate(S, P, s, a, len, sc);
+                if (fin >= P.minfinscore && better(fin, key, best.fin, best.key)) {
+                    best.fin = fin; best.key = key; best.len = len; best.bps = sc;
+                }
+            }
+        });
+    }
+    Team<TW>::sync();
+    int nc = S.misc[0]; if (nc > L.Ccap) nc = L.Ccap;
+    for (int c = r; c < nc; c += T) {
+        uint32_t key = S.ckey[c];
+        int len = S.clen[c];
+        double sc = S.cbps[c];
+        double fin = score_candidate(S, P, key >> 16, key & 0xffff, len, sc);
+        if (!(fin >= P.minfinscore)) fin = -1e300;
+        S.cfin[c] = fin;
+        if (fin > -1e300 && better(fin, key, best.fin, best.key)) {
+            best.fin = fin; best.key = key; best.len = len; best.bps = sc;
+        }
+    }
+    Team<TW>::sync();
+    return team_argmax<TW>(S, best);
+}
+
+// two stems are "in conflict" when they share a paired position (seq.py:783-786)
+__device__ __forceinline__ bool iv_overlap(int a0, int a1, int b0, int b1) { return a0 <= b1 && b0 <= a1; }
+__device__ __forceinline__ bool stems_share(int i1, int j1, int l1, int i2, int j2, int l2)
+{
+    return iv_overlap(i1, i1 + l1 - 1, i2, i2 + l2 - 1) || iv_overlap(i1, i1 + l1 - 1, j2 - l2 + 1, j2) ||
+           iv_overlap(j1 - l1 + 1, j1, i2, i2 + l2 - 1) || iv_overlap(j1 - l1 + 1, j1, j2 - l2 + 1, j2);
+}
+
+// ChooseStems (seq.py:754-789) after a team_scan: every candidate with
+// fin >= subopt * best that conflicts with all the better chosen ones, in the
+// order of the reference's stable sort.  Writes (i, j, len) triples; returns
+// the number chosen, or -1 if the candidate list overflowed (caller retries
+// with a larger list).
+template <int TW>
+__device__ int team_choose(State &S, const Layout &L, const Best &best, double subopt,
+                           int32_t *out, double *outfin, int cap)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    if (best.fin <= -1e300) return 0;
+    int ntot = S.misc[0];
+    if (ntot > L.Ccap) return -1;
+    const double range = __dmul_rn(subopt, best.fin);
+    // rank the in-range candidates by (fin desc, enumeration order)
+    int16_t *ord = S.perm;                 // reuse: at most Scap entries are kept
+    if (r == 0) S.misc[6] = 0;
+    Team<TW>::sync();
+    for (int c = r; c < ntot; c += T) {
+        double f = S.cfin[c];
+        if (f <= -1e300 || f < range) continue;
+        uint32_t k = S.ckey[c];
+        int rank = 0;
+        for (int d = 0; d < ntot; d++) {
+            double g = S.cfin[d];
+            if (g <= -1e300 || g < range) continue;
+            if (better(g, S.ckey[d], f, k)) rank++;
+        }
+        if (rank < L.Scap) ord[rank] = (int16_t)c;
+        atomicAdd(&S.misc[6], 1);
+    }
+    Team<TW>::sync();
+    int nin = S.misc[6];
+    if (nin > L.Scap || nin > 32767) return -1;
+    if (r == 0) {
+        int n = 0;
+        for (int a = 0; a < nin; a++) {
+            int c = ord[a];
+            uint32_t k = S.ckey[c];
+            int i = k & 0xffff, j = (int)(k >> 16) - i, len = S.clen[c];
+            bool ok = true;
+            for (int q = 0; q < n && ok; q++)
+                if (!stems_share(i, j, len, out[3 * q], out[3 * q + 1], out[3 * q + 2])) ok = false;
+            if (a == 0) ok = true;
+            if (ok) {
+                if (n < cap) { out[3 * n] = i; out[3 * n + 1] = j; out[3 * n + 2] = len; if (outfin) outfin[n] = S.cfin[c]; }
+                n++;
+            }
+        }
+        S.misc[6] = n;
+    }
+    Team<TW>::sync();
+    return S.misc[6];
+}
+
+// exclusive prefix sum over the team; total returned through `total`
+template <int TW>
+__device__ __forceinline__ int team_exscan(State &S, int v, int &total)
+{
+#ifdef SQRN_HOST_EMU
+    total = v; return 0;
+#else
+    int lane = threadIdx.x & 31, x = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    int wtot = __shfl_sync(0xffffffffu, x, 31);
+    int excl = x - v;
+    if (TW == 1) { total = wtot; return excl; }
+    int *sc = (int *)S.red;
+    int w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 31) sc[w] = wtot;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int q = 0; q < TW; q++) { int t = sc[q]; if (q < w) base += t; tot += t; }
+    __syncthreads();
+    total = tot;
+    return base + excl;
+#endif
+}
+
+// AnnotateStems output in reference order (YieldStems, ali.py:86-101): stems of
+// the current structure state, written as (i, j, len) + bp score.  Returns the
+// number of stems (may exceed cap: the caller then re-allocates and re-runs).
+template <int TW>
+__device__ int team_yield(State &S, const DevParams &P, const DevBatch &B, int32_t *out, double *outsc, int64_t cap)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const int smax = 2 * S.N - 6;
+    int base = 0;
+    for (int s0 = 4; s0 <= smax; s0 += T) {
+        int s = s0 + r, cnt = 0;
+        if (s <= smax)
+            enum_diag(S, P, B, s, [&](int a, int e) {
+                int len = e - a + 1;
+                if ((double)len < P.minlen) return;
+                double sc = 0.0;
+                for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
+                if (sc >= P.minbpscore) cnt++;
+            });
+        int tot, off = team_exscan<TW>(S, cnt, tot);
+        if (cnt && s <= smax) {
+            int w = base + off;
+            enum_diag(S, P, B, s, [&](int a, int e) {
+                int len = e - a + 1;
+                if ((double)len < P.minlen) return;
+                double sc = 0.0;
+                for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
+                if (sc >= P.minbpscore) {
+                    if (w < cap) { out[3 * (int64_t)w] = a; out[3 * (int64_t)w + 1] = s - a; out[3 * (int64_t)w + 2] = len; outsc[w] = sc; }
+                    w++;
+                }
+            });
+        }
+        base += tot;
+    }
+    return base;
+}
+
+// ------------------------------------------------------------- finalisation
+// ScoreStruct (seq.py:861-899) raw values + dbn of the finished structure.
+template <int TW>
+__device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk, int item)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const int N = S.N;
+    team_levels<TW>(S);
+    int64_t doff = Wk.dbn_off ? Wk.dbn_off[item] : 0;
+    uint8_t flags = 0;
+    if (Wk.out_dbn_ascii || Wk.out_dbn_code) {
+        for (int p = r; p < N; p += T) {
+            int pr = S.partner[p];
+            int lv = pr < 0 ? 0 : S.stlev[S.owner[p]];
+            if (Wk.out_dbn_code) Wk.out_dbn_code[doff + p] = (int8_t)(pr < 0 ? 0 : (p < pr ? (lv > 127 ? 127 : lv) : -(lv > 127 ? 127 : lv)));
+            if (Wk.out_dbn_ascii) {
+                uint8_t ch = '.';
+                if (S.code[p] == CODE_SEP) ch = B.sym[B.off[Wk.item_seq ? Wk.item_seq[item] : item] + p];
+                else if (pr >= 0) {
+                    const char *op = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ", *cl = ")]}>abcdefghijklmnopqrstuvwxyz";
+                    ch = lv <= 30 ? (uint8_t)(p < pr ? op[lv - 1] : cl[lv - 1]) : (uint8_t)'?';
+                }
+                Wk.out_dbn_ascii[doff + p] = ch;
+            }
+        }
+    }
+    if (r == 0) {
+        double thescore = 0.0; bool any = false; int maxlev = 0;
+        for (int t = 0; t < S.nst; t++) {
+            int k2 = 0;                                  // bpsum in units of 0.5 (GU -0.5, AU 1.5, GC 4.0)
+            for (int q = 0; q < S.stl[t]; q++) {
+                int a = S.code[S.sti[t] + q], b = S.code[S.stj[t] - q];
+                int lo = a < b ? a : b, hi = a < b ? b : a;
+                if (lo == CODE_G && hi == CODE_U) k2 -= 1;
+                else if (lo == CODE_A && hi == CODE_U) k2 += 3;
+                else if (lo == CODE_C && hi == CODE_G) k2 += 8;
+            }
+            if (k2 > 0) {
+                double pw = (k2 < P.pw17_n) ? __ldg(&P.pw17_lut[k2]) : pow(0.5 * k2, 1.7);
+                thescore = __dadd_rn(thescore, pw); any = true;
+            }
+            if (S.stlev[t] > maxlev) maxlev = S.stlev[t];
+        }
+        double reactscore = 0.5;
+        int nsep = S.sepcnt[N];
+        if (S.has_react && !S.default_reacts) {
+            // builtin sum(): plain left-to-right for numpy floats, Neumaier for exact Python floats
+            double sum = 0.0, comp = 0.0; bool first = true;
+            for (int p = 0; p < N; p++) {
+                if (S.code[p] == CODE_SEP) continue;
+                double rv = B.rvals[S.rcode[p]];
+                double x = S.partner[p] >= 0 ? rv : __dsub_rn(1.0, rv);
+                if (first || !B.react_comp) { sum = __dadd_rn(sum, x); first = false; continue; }
+                double t = __dadd_rn(sum, x);
+                if (fabs(sum) >= fabs(x)) comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(sum, t), x));
+                else comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(x, t), sum));
+                sum = t;
+            }
+            if (B.react_comp && comp != 0.0 && isfinite(comp)) sum = __dadd_rn(sum, comp);
+            reactscore = __dsub_rn(1.0, __ddiv_rn(sum, (double)(N - nsep)));
+        }
+        if (!any) flags |= 1;
+        if (maxlev > 30) flags |= 2;
+        Wk.out_raw[3 * (int64_t)item] = __dmul_rn(thescore, reactscore);   // seq.py:899, before round()
+        Wk.out_raw[3 * (int64_t)item + 1] = thescore;
+        Wk.out_raw[3 * (int64_t)item + 2] = reactscore;
+        Wk.out_nstems[item] = S.nst;
+        if (Wk.out_flags) Wk.out_flags[item] = flags;
+    }
+    // stems in selection order
+    if (!Wk.out_off) return;
+    int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
+    for (int t = r; t < S.nst && t < cap; t += T) {
+        Wk.out_stems[3 * (so + t)] = S.sti[t];
+        Wk.out_stems[3 * (so + t) + 1] = S.stj[t];
+        Wk.out_stems[3 * (so + t) + 2] = S.stl[t];
+    }
+}
+
+// ------------------------------------------------------------ one work item
+template <int TW>
+__device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk,
+                              const Layout &L, int item)
+{
+    const int r = Team<TW>::rank();
+    const int seq = Wk.item_seq ? Wk.item_seq[item] : item;
+    team_load<TW>(S, B, P, seq);
+    if (Wk.init_off)
+        for (int64_t k = Wk.init_off[item]; k < Wk.init_off[item + 1]; k++)
+            team_apply_stem<TW>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2]);
+    unsigned long long calls = 0;
+    if (Wk.mode == MODE_TAIL) {
+        // the pool loop of seq.py:1159-1199 once it can no longer branch
+        // (cursize >= poollim => stopper = 1): take the top stem until none is left
+        while ((double)S.nst != P.maxstemnum) {
+            team_levels<TW>(S);
+            Best b = team_scan<TW>(S, P, B, L);
+            calls++;
+            if (b.fin <= -1e300) break;
+            int i = (int)(b.key & 0xffff);
+            team_apply_stem<TW>(S, i, (int)(b.key >> 16) - i, b.len);
+        }
+        team_finalize<TW>(S, P, B, Wk, item);
+    } else if (Wk.mode == MODE_STEP) {
+        int n = 0;
+        int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
+        if ((double)S.nst != P.maxstemnum) {
+            team_levels<TW>(S);
+            Best b = team_scan<TW>(S, P, B, L);
+            calls++;
+            n = team_choose<TW>(S, L, b, Wk.item_subopt[item], Wk.out_stems + 3 * so,
+                                Wk.out_stemfin ? Wk.out_stemfin + so : nullptr, (int)cap);
+        }
+        if (r == 0) Wk.out_nstems[item] = n;
+    } else {
+        int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
+        int n = team_yield<TW>(S, P, B, Wk.out_stems + 3 * so, Wk.out_stemfin + so, cap);
+        if (r == 0) Wk.out_nstems[item] = n;
+    }
+    if (r == 0 && Wk.n_calls && calls) atomicAdd(Wk.n_calls, calls);
+    Team<TW>::sync();
+}
+
+#endif  // __CUDACC__
+}  // namespace sqrn

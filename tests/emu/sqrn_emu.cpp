@@ -1,0 +1,59 @@
+// sqrn_emu.cpp -- TEST INFRASTRUCTURE: single-thread host build of the device
+// functions in squarna_b200/csrc/sqrn_device.cuh (SQRN_HOST_EMU, team size 1).
+// It lets `pytest -m "not gpu"` exercise the bit-mask enumeration, the scoring
+// and the level logic against the oracle on a box without a GPU.  It is not
+// linked into libsqrn_b200.so and nothing in squarna_b200/ loads it; the
+// parallel behaviour (ballots, shuffles, atomics, barriers) is only covered by
+// the `-m gpu` tests.
+#define SQRN_HOST_EMU 1
+#include <stdlib.h>
+#include "../../squarna_b200/csrc/sqrn_params.h"
+
+using namespace sqrn;
+
+extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *off, const uint8_t *sym,
+                       const uint8_t *rcode, const double *rvals, int R, int react_comp,
+                       const uint8_t *rclass, const int64_t *rbp_off, const int32_t *rbp,
+                       const double *smat, int L, const int32_t *cols, int interchainonly,
+                       int mode, int n_items, const int32_t *item_seq, const int64_t *init_off,
+                       const int32_t *init_stems, const double *item_subopt,
+                       const int64_t *out_off, int32_t *out_stems, int32_t *out_nstems, double *out_stemfin,
+                       double *out_raw, uint8_t *out_flags, const int64_t *dbn_off, uint8_t *dbn_ascii,
+                       int8_t *dbn_code, int ccap, unsigned long long *n_calls)
+{
+    int nmax = 1, rbmax = 0;
+    for (int64_t b = 0; b < n_seqs; b++) {
+        int n = (int)(off[b + 1] - off[b]);
+        if (n > nmax) nmax = n;
+        if (rbp_off) { int q = (int)(rbp_off[b + 1] - rbp_off[b]); if (q > rbmax) rbmax = q; }
+    }
+    HostParams H; std::string err;
+    if (!build_host_params(*ps, nmax, H, err)) return -1;
+    H.p.sdf_lut = H.lut.data() + H.sdf_off;
+    H.p.of_lut = H.lut.data() + H.of_off;
+    H.p.pw17_lut = H.lut.data() + H.pw17_off;
+    std::vector<double> rpos, rneg;
+    std::vector<int32_t> rb_sorted;
+    DevBatch B; memset(&B, 0, sizeof B);
+    B.n_seqs = n_seqs; B.off = off; B.sym = sym;
+    if (rcode) { build_react_lut(rvals, R, rpos, rneg); B.rcode = rcode; B.rf_pos = rpos.data(); B.rf_neg = rneg.data(); B.rvals = rvals; B.R = R; }
+    B.react_comp = react_comp;
+    B.rclass = rclass;
+    if (rbp_off) { sort_rbps(n_seqs, rbp_off, rbp, rb_sorted); B.rbp_off = rbp_off; B.rbp = rb_sorted.data(); }
+    B.smat = smat; B.L = L; B.cols = cols; B.interchainonly = interchainonly;
+    DevWork W; memset(&W, 0, sizeof W);
+    W.n_items = n_items; W.mode = mode; W.item_seq = item_seq; W.init_off = init_off; W.init_stems = init_stems;
+    W.item_subopt = item_subopt; W.out_off = out_off; W.out_stems = out_stems; W.out_nstems = out_nstems;
+    W.out_stemfin = out_stemfin; W.out_raw = out_raw; W.out_flags = out_flags; W.dbn_off = dbn_off;
+    W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls;
+    Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0);
+    unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
+    for (int item = 0; item < n_items; item++) {
+        State S = bind_state(smem, Lay);
+        team_run_item<0>(S, H.p, B, W, Lay, item);
+    }
+    free(smem);
+    return 0;
+}
+
+extern "C" double emu_pyround3(double x) { return pyround3(x); }
