@@ -37,6 +37,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define SQRN_API __attribute__((visibility("default")))
+#else
+#define SQRN_API
+#endif
+
 #define SQRN_ABI_VERSION 1
 
 #define SQRN_OK             0
@@ -47,6 +53,7 @@ extern "C" {
 
 #define SQRN_MAX_BPKEYS 32
 #define SQRN_MAX_LEN    16000    /* ungapped nucleotides per sequence */
+#define SQRN_MAX_REACT_LUT 2048
 
 typedef struct sqrn_ctx sqrn_ctx;
 
@@ -74,8 +81,11 @@ typedef struct {
     const int64_t *offsets;      /* [n_seqs+1] into symbols / react_code / restr_class / cols */
     const uint8_t *symbols;      /* raw ASCII; case and T/U are normalised by the library       */
     /* reactivities: NULL = all 0.5 ("default reacts", SQRNdbnseq.py:273).  Else one
-     * code per position into react_values (distinct processed reactivities, <= 256). */
-    const uint8_t *react_code;
+     * code per position into react_values (the distinct processed reactivities of
+     * the batch).  Up to SQRN_MAX_REACT_LUT distinct values the reactivity factors
+     * ((1-(ri+rj)/2)*2)**0.5 come from a host libm table (bit-exact); above that the
+     * device evaluates sqrt() (<= 1 ulp from libm pow on ~0.1 % of inputs).         */
+    const uint16_t *react_code;
     const double  *react_values;
     int32_t        n_react_values;
     int32_t        react_sum_compensated; /* builtin sum() over exact Python floats (CPython >= 3.12) */
@@ -122,23 +132,23 @@ typedef struct {
     int64_t  need_stems;
 } sqrn_stems;
 
-int  sqrn_abi_version(void);
-int  sqrn_device_count(void);                 /* 0 when no CUDA device is usable */
-int  sqrn_ctx_create(int device, sqrn_ctx **out);
-void sqrn_ctx_destroy(sqrn_ctx *ctx);
-const char *sqrn_last_error(const sqrn_ctx *ctx);   /* ctx may be NULL: last create error */
+SQRN_API int  sqrn_abi_version(void);
+SQRN_API int  sqrn_device_count(void);                 /* 0 when no CUDA device is usable */
+SQRN_API int  sqrn_ctx_create(int device, sqrn_ctx **out);
+SQRN_API void sqrn_ctx_destroy(sqrn_ctx *ctx);
+SQRN_API const char *sqrn_last_error(const sqrn_ctx *ctx);   /* ctx may be NULL: last create error */
 
 /* Use an externally owned CUDA stream (cudaStream_t as void*) for all work of
  * this context, e.g. torch.cuda.current_stream().cuda_stream.                 */
-int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
+SQRN_API int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
 
 /* The full "G" path for a batch: replaces SQRNdbnseq.py:1048-1246 (algos == {"G"},
  * bpp == 0).  Host buffers in, host buffers out.                              */
-int  sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps,
+SQRN_API int  sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps,
                         const sqrn_batch *in, sqrn_result *out);
 
 /* Enumeration only: replaces SQRNdbnali.py:86-101 for a batch.                 */
-int  sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps,
+SQRN_API int  sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps,
                             const sqrn_batch *in, sqrn_stems *out);
 
 /* ---- single-path fast lane (poollim == 1: `byseq pl=1`, SQUARNA.py:887-935) --
@@ -148,16 +158,24 @@ int  sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps,
  * sqrn_fast_predict_device (inputs already resident in HBM; asynchronous on the
  * context's stream).  scores: 3 doubles per sequence, rounded as round(x,3) by
  * the host variant and raw (thescore, reactscore, total) by the device variant. */
-int  sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps,
+SQRN_API int  sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps,
                             int64_t n_seqs, const int64_t *offsets, const uint8_t *symbols,
                             uint8_t *dbn_ascii, double *scores, int32_t *n_stems);
-int  sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps,
+SQRN_API int  sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps,
                               int64_t n_seqs, int64_t total_len, int32_t max_len,
                               const int64_t *d_offsets, const uint8_t *d_symbols,
                               uint8_t *d_dbn_ascii, double *d_scores, int32_t *d_n_stems);
 
+/* TEST SEAM (tests/ only): one launch of the work kernel in a given mode
+ * (0 run to completion, 1 one OptimalStems + ChooseStems, 2 AnnotateStems,
+ * 3 ScoreStruct + dbn) on top of caller-supplied pre-selected stems.            */
+SQRN_API int  sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, int mode, int n_items,
+                    const int32_t *item_seq, const int64_t *init_off, const int32_t *init_stems,
+                    const double *item_subopt, const int64_t *out_cap, int32_t *out_stems, int32_t *out_n,
+                    double *out_fin, double *out_raw, uint8_t *out_flags, int8_t *dbn_code, int min_ccap);
+
 /* counters of the last call: kernels launched, device milliseconds of the main kernel */
-int  sqrn_ctx_last_stats(const sqrn_ctx *ctx, int64_t *n_launches, double *kernel_ms,
+SQRN_API int  sqrn_ctx_last_stats(const sqrn_ctx *ctx, int64_t *n_launches, double *kernel_ms,
                          int64_t *n_optimal_calls);
 
 #ifdef __cplusplus

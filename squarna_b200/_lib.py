@@ -1,0 +1,261 @@
+"""Loader and thin object wrapper for libsqrn_b200.so (include/sqrn.h).
+
+There is no CPU fallback: if the shared object has not been built, or no CUDA
+device is usable, every entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import (Batch, ParamSet, Result, Stems, E_CAPACITY, OK, pack_sequences, paramset_array, ptr)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsqrn_b200.so")
+
+MODE_TAIL, MODE_STEP, MODE_YIELD, MODE_FINAL = 0, 1, 2, 3
+
+EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx_destroy",
+           "sqrn_last_error", "sqrn_ctx_set_stream", "sqrn_predict_batch", "sqrn_yield_stems_batch",
+           "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run"]
+
+_lib = None
+
+
+class SqrnError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libsqrn_b200.so and declare the prototypes of include/sqrn.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SqrnError("libsqrn_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "or `make -C squarna_b200/csrc`); squarna_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.sqrn_abi_version.restype = C.c_int
+    L.sqrn_device_count.restype = C.c_int
+    L.sqrn_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.sqrn_ctx_destroy.argtypes = [vp]
+    L.sqrn_ctx_destroy.restype = None
+    L.sqrn_last_error.argtypes = [vp]
+    L.sqrn_last_error.restype = C.c_char_p
+    L.sqrn_ctx_set_stream.argtypes = [vp, vp]
+    L.sqrn_predict_batch.argtypes = [vp, C.POINTER(ParamSet), C.c_int, C.POINTER(Batch), C.POINTER(Result)]
+    L.sqrn_yield_stems_batch.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.POINTER(Stems)]
+    L.sqrn_fast_predict_host.argtypes = [vp, C.POINTER(ParamSet), i64, vp, vp, vp, vp, vp]
+    L.sqrn_fast_predict_device.argtypes = [vp, C.POINTER(ParamSet), i64, i64, i32, vp, vp, vp, vp, vp]
+    L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
+    L.sqrn_debug_run.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.c_int, C.c_int] + [vp] * 12 + [C.c_int]
+    _lib = L
+    return L
+
+
+class PackedBatch:
+    """numpy arrays behind a sqrn_batch (kept alive as long as the object lives)."""
+
+    def __init__(self, seqs, react_codes=None, react_values=None, react_comp=False, restr_class=None,
+                 rbps=None, smat=None, cols=None, interchainonly=False, hardrest=False, rankbydiff=False,
+                 poollim=1000, conslim=1, max_structs=0, rankby=(0, 2, 1), priority_mask=0):
+        self.seqs = seqs
+        self.symbols, self.offsets = pack_sequences(seqs)
+        n = len(seqs)
+
+        def cat(lst, dt):
+            if lst is None:
+                return None
+            arrs = [np.asarray(x, dtype=dt).ravel() for x in lst]
+            tot = sum(a.size for a in arrs)
+            return np.concatenate(arrs) if tot else np.zeros(1, dt)
+
+        self.react_code = cat(react_codes, np.uint16)
+        self.react_values = None if react_values is None else np.ascontiguousarray(react_values, np.float64)
+        self.restr_class = cat(restr_class, np.uint8)
+        self.rbp_offsets = self.rbps = None
+        if rbps is not None:
+            self.rbp_offsets = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum([len(x) for x in rbps], out=self.rbp_offsets[1:])
+            self.rbps = cat(rbps, np.int32)
+        self.smat = None if smat is None else np.ascontiguousarray(smat, np.float64)
+        self.cols = cat(cols, np.int32)
+        b = Batch()
+        b.n_seqs = n
+        b.offsets = ptr(self.offsets)
+        b.symbols = ptr(self.symbols)
+        b.react_code = ptr(self.react_code)
+        b.react_values = ptr(self.react_values)
+        b.n_react_values = 0 if self.react_values is None else len(self.react_values)
+        b.react_sum_compensated = int(bool(react_comp))
+        b.restr_class = ptr(self.restr_class)
+        b.rbp_offsets = ptr(self.rbp_offsets)
+        b.rbps = ptr(self.rbps)
+        b.smat = ptr(self.smat)
+        b.smat_L = 0 if self.smat is None else self.smat.shape[0]
+        b.cols = ptr(self.cols)
+        b.interchainonly = int(bool(interchainonly))
+        b.hardrest = int(bool(hardrest))
+        b.rankbydiff = int(bool(rankbydiff))
+        b.poollim = int(poollim)
+        b.conslim = int(conslim)
+        b.max_structs = int(max_structs)
+        for k in range(3):
+            b.rankby[k] = int(rankby[k])
+        b.priority_mask = int(priority_mask)
+        self.c = b
+
+
+class Context:
+    """One GPU, one host thread at a time."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.sqrn_ctx_create(int(device), C.byref(h))
+        if rc != OK:
+            raise SqrnError("sqrn_ctx_create failed (%d): %s" % (rc, self.L.sqrn_last_error(None).decode()))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sqrn_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise SqrnError("libsqrn_b200 error %d: %s" % (rc, self.L.sqrn_last_error(self.h).decode()))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.L.sqrn_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def stats(self):
+        nl, ms, nc = C.c_int64(0), C.c_double(0), C.c_int64(0)
+        self.L.sqrn_ctx_last_stats(self.h, C.byref(nl), C.byref(ms), C.byref(nc))
+        return dict(launches=nl.value, kernel_ms=ms.value, optimal_calls=nc.value)
+
+    # ---- fast lane -----------------------------------------------------
+    def fast_predict(self, paramset, symbols, offsets):
+        """host numpy in -> (dbn ascii uint8 [total], scores (n,3) rounded, n_stems (n,))"""
+        n = len(offsets) - 1
+        ps = paramset if isinstance(paramset, ParamSet) else ParamSet.from_dict(paramset)
+        dbn = np.empty(max(int(offsets[-1]), 1), dtype=np.uint8)
+        scores = np.empty((max(n, 1), 3), dtype=np.float64)
+        nst = np.empty(max(n, 1), dtype=np.int32)
+        self._check(self.L.sqrn_fast_predict_host(self.h, C.byref(ps), n, ptr(offsets), ptr(symbols),
+                                                  ptr(dbn), ptr(scores), ptr(nst)))
+        return dbn[:int(offsets[-1])], scores[:n], nst[:n]
+
+    def fast_predict_device(self, paramset, n, total, max_len, d_off, d_sym, d_dbn, d_scores, d_nst):
+        """device pointers (ints) in/out, asynchronous on the context's stream"""
+        ps = paramset if isinstance(paramset, ParamSet) else ParamSet.from_dict(paramset)
+        self._check(self.L.sqrn_fast_predict_device(self.h, C.byref(ps), n, total, max_len,
+                                                    C.c_void_p(d_off), C.c_void_p(d_sym), C.c_void_p(d_dbn),
+                                                    C.c_void_p(d_scores), C.c_void_p(d_nst)))
+
+    # ---- general path ---------------------------------------------------
+    def predict_batch(self, paramsets, batch):
+        """paramsets: list of dicts; batch: PackedBatch.  Returns per sequence a tuple
+        (cons_codes int8[N], [ (dbn_codes, (total, struct, react), struct_is_int0, psmask, stems (k,3)) ], n_total)"""
+        arr = paramsets if not isinstance(paramsets, (list, tuple)) else paramset_array(list(paramsets))
+        nps = len(paramsets)
+        n = len(batch.offsets) - 1
+        total = int(batch.offsets[-1])
+        cap_s, cap_st, cap_d = max(8 * n, 8), max(16 * n, 64), max(4 * total, 64)
+        first = True
+        while True:
+            so = np.zeros(n + 1, np.int64)
+            scores = np.zeros((cap_s, 3))
+            isint = np.zeros(cap_s, np.uint8)
+            mask = np.zeros(cap_s, np.uint64)
+            ntot = np.zeros(max(n, 1), np.int32)
+            sto = np.zeros(cap_s + 1, np.int64)
+            stems = np.zeros((cap_st, 3), np.int32)
+            dbo = np.zeros(cap_s, np.int64)
+            dbn = np.zeros(cap_d, np.int8)
+            cons = np.zeros(max(total, 1), np.int8)
+            r = Result()
+            r.cap_structs, r.cap_stems, r.cap_dbn = cap_s, cap_st, cap_d
+            r.struct_offsets, r.scores, r.struct_is_int0, r.psmask = ptr(so), ptr(scores), ptr(isint), ptr(mask)
+            r.n_total, r.stem_offsets, r.stems, r.dbn_offsets = ptr(ntot), ptr(sto), ptr(stems), ptr(dbo)
+            r.dbn, r.cons = ptr(dbn), ptr(cons)
+            rc = self.L.sqrn_predict_batch(self.h, arr, nps, C.byref(batch.c) if first else None, C.byref(r))
+            if rc == E_CAPACITY:
+                cap_s, cap_st, cap_d = max(r.need_structs, 8), max(r.need_stems, 8), max(r.need_dbn, 8)
+                first = False
+                continue
+            self._check(rc)
+            break
+        out = []
+        for b in range(n):
+            N = int(batch.offsets[b + 1] - batch.offsets[b])
+            structs = []
+            for k in range(int(so[b]), int(so[b + 1])):
+                structs.append((dbn[dbo[k]:dbo[k] + N].copy(), tuple(float(x) for x in scores[k]), bool(isint[k]),
+                                int(mask[k]), stems[sto[k]:sto[k + 1]].copy()))
+            out.append((cons[batch.offsets[b]:batch.offsets[b] + N].copy(), structs, int(ntot[b])))
+        return out
+
+    def yield_stems(self, paramset, batch):
+        """AnnotateStems per sequence: list of (stems (k,3) int32, scores (k,) float64)"""
+        ps = paramset if isinstance(paramset, ParamSet) else ParamSet.from_dict(paramset)
+        n = len(batch.offsets) - 1
+        cap = max(64 * n, 1024)
+        first = True
+        while True:
+            off = np.zeros(n + 1, np.int64)
+            st = np.zeros((cap, 3), np.int32)
+            sc = np.zeros(cap)
+            s = Stems()
+            s.cap_stems, s.stem_offsets, s.stems, s.scores = cap, ptr(off), ptr(st), ptr(sc)
+            rc = self.L.sqrn_yield_stems_batch(self.h, C.byref(ps), C.byref(batch.c) if first else None, C.byref(s))
+            if rc == E_CAPACITY:
+                cap = max(int(s.need_stems), 8)
+                first = False
+                continue
+            self._check(rc)
+            break
+        return [(st[off[b]:off[b + 1]].copy(), sc[off[b]:off[b + 1]].copy()) for b in range(n)]
+
+    def debug_run(self, paramset, batch, mode, item_seq=None, init_stems=None, item_subopt=None,
+                  out_cap=None, min_ccap=0, want_dbn=True):
+        """test seam: one launch of the work kernel (see sqrn_debug_run in csrc/sqrn_abi.cu)"""
+        ps = ParamSet.from_dict(paramset)
+        nseq = len(batch.offsets) - 1
+        n_items = len(item_seq) if item_seq is not None else nseq
+        iseq = np.ascontiguousarray(item_seq if item_seq is not None else np.arange(nseq), dtype=np.int32)
+        lens = np.diff(batch.offsets)[iseq]
+        ioff = ist = None
+        if init_stems is not None:
+            ioff = np.zeros(n_items + 1, np.int64)
+            np.cumsum([len(x) for x in init_stems], out=ioff[1:])
+            flat = [t for x in init_stems for s in x for t in s]
+            ist = np.array(flat if flat else [0], dtype=np.int32)
+        isub = None if item_subopt is None else np.ascontiguousarray(item_subopt, np.float64)
+        if out_cap is None:
+            out_cap = (lens // 2 + 1) if mode != MODE_YIELD else (lens * lens // 4 + 8)
+        ocap = np.ascontiguousarray(np.broadcast_to(out_cap, (n_items,)), dtype=np.int64)
+        ooff = np.zeros(n_items + 1, np.int64)
+        np.cumsum(ocap, out=ooff[1:])
+        stems = np.zeros((max(int(ooff[-1]), 1), 3), np.int32)
+        outn = np.zeros(max(n_items, 1), np.int32)
+        fin = np.zeros(max(int(ooff[-1]), 1))
+        raw = np.zeros((max(n_items, 1), 3))
+        flags = np.zeros(max(n_items, 1), np.uint8)
+        doff = np.zeros(n_items + 1, np.int64)
+        np.cumsum(lens, out=doff[1:])
+        dbn = np.zeros(max(int(doff[-1]), 1), np.int8)
+        self._check(self.L.sqrn_debug_run(self.h, C.byref(ps), C.byref(batch.c), mode, n_items, ptr(iseq),
+                                          ptr(ioff), ptr(ist), ptr(isub), ptr(ocap), ptr(stems), ptr(outn),
+                                          ptr(fin), ptr(raw), ptr(flags), ptr(dbn) if want_dbn else None,
+                                          int(min_ccap)))
+        return dict(off=ooff, stems=stems, n=outn[:n_items], fin=fin, raw=raw[:n_items], flags=flags[:n_items],
+                    dbn_off=doff, dbn_code=dbn)

@@ -1,0 +1,981 @@
+// sqrn_abi.cu -- kernels + host side of the C ABI declared in include/sqrn.h.
+//
+// Host responsibilities (everything here is orchestration, none of it scores a
+// stem): digest parameter sets into tables, move CSR batches to the GPU, run the
+// structure-pool loop of SQRNdbnseq.py:1102-1199 as rounds of batched kernel
+// launches, de-duplicate / rank the finished structures (seq.py:1201-1224) and
+// hand back caller-owned buffers.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "sqrn_params.h"
+
+using namespace sqrn;
+
+// ------------------------------------------------------------------ kernel
+// Persistent teams pull work items from a global counter (length-sorted by the
+// host, longest first), so a batch of mixed lengths keeps every SM busy.
+template <int TW>
+__global__ void __launch_bounds__(TW == 1 ? 256 : TW * 32)
+k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ DevParams Psh;
+    {
+        const int *src = reinterpret_cast<const int *>(Pg);
+        int *dst = reinterpret_cast<int *>(&Psh);
+        for (int k = threadIdx.x; k < (int)(sizeof(DevParams) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int team = (TW == 1) ? (threadIdx.x >> 5) : 0;
+    State S = bind_state(smem + (size_t)team * L.total, L);
+    for (;;) {
+        int item = 0;
+        if (TW == 1) {
+            if ((threadIdx.x & 31) == 0) item = atomicAdd(Wk.counter, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+        } else {
+            if (threadIdx.x == 0) S.misc[1] = atomicAdd(Wk.counter, 1);
+            __syncthreads();
+            item = S.misc[1];
+            __syncthreads();
+        }
+        if (item >= Wk.n_items) break;
+        if (Wk.order) item = Wk.order[item];
+        team_run_item<TW>(S, Psh, B, Wk, L, item);
+    }
+}
+
+// ----------------------------------------------------------------- context
+struct DBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PEntry {
+    sqrn_paramset ps; int nmax; DevParams hp; DevParams *d_p; double *d_lut;
+};
+
+struct Stem3 { int32_t i, j, len; };
+
+struct CachedResult {           // result of the last sqrn_predict_batch, kept for the E_CAPACITY retry
+    bool valid = false;
+    int64_t n_seqs = 0, total_len = 0;
+    std::vector<int64_t> struct_offsets, stem_offsets, dbn_offsets;
+    std::vector<double> scores; std::vector<uint8_t> isint0; std::vector<uint64_t> psmask;
+    std::vector<int32_t> n_total, stems; std::vector<int8_t> dbn, cons;
+};
+struct CachedStems {
+    bool valid = false; int64_t n_seqs = 0;
+    std::vector<int64_t> off; std::vector<int32_t> stems; std::vector<double> scores;
+};
+
+enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS,
+       W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, NBUF };
+
+struct sqrn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
+    std::string err;
+    int sm_count = 0; size_t smem_optin = 0;
+    std::vector<PEntry> pcache;
+    DBuf buf[NBUF];
+    int64_t n_launches = 0, n_calls = 0; double kernel_ms = 0.0;
+    CachedResult cres; CachedStems cstems;
+};
+
+static std::string g_create_err;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SQRN_E_CUDA; } } while (0)
+
+extern "C" int sqrn_abi_version(void) { return SQRN_ABI_VERSION; }
+
+extern "C" int sqrn_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *sqrn_last_error(const sqrn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int sqrn_ctx_create(int device, sqrn_ctx **out)
+{
+    if (!out) return SQRN_E_BADARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("no usable CUDA device (libsqrn_b200 has no CPU fallback): ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return SQRN_E_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return SQRN_E_BADARG; }
+    sqrn_ctx *ctx = new sqrn_ctx();
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        g_create_err = std::string("context creation failed: ") + cudaGetErrorString(e);
+        delete ctx; return SQRN_E_CUDA;
+    }
+    ctx->own_stream = true;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return SQRN_OK;
+}
+
+extern "C" void sqrn_ctx_destroy(sqrn_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->buf) b.release();
+    for (auto &p : ctx->pcache) { cudaFree(p.d_p); cudaFree(p.d_lut); }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+extern "C" int sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return SQRN_E_BADARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false;
+    return SQRN_OK;
+}
+
+extern "C" int sqrn_ctx_last_stats(const sqrn_ctx *ctx, int64_t *n_launches, double *kernel_ms, int64_t *n_optimal_calls)
+{
+    if (!ctx) return SQRN_E_BADARG;
+    if (n_launches) *n_launches = ctx->n_launches;
+    if (kernel_ms) *kernel_ms = ctx->kernel_ms;
+    if (n_optimal_calls) *n_optimal_calls = ctx->n_calls;
+    return SQRN_OK;
+}
+
+// parameter-set digest, cached per (paramset, length class)
+static int get_params(sqrn_ctx *ctx, const sqrn_paramset &ps, int nmax, const PEntry **out)
+{
+    for (auto &e : ctx->pcache)
+        if (e.nmax >= nmax && !memcmp(&e.ps, &ps, sizeof ps)) { *out = &e; return SQRN_OK; }
+    int ncap = (nmax + 1023) / 1024 * 1024;
+    HostParams H;
+    if (!build_host_params(ps, ncap, H, ctx->err)) return SQRN_E_UNSUPPORTED;
+    PEntry e; memcpy(&e.ps, &ps, sizeof ps); e.nmax = ncap; e.d_p = nullptr; e.d_lut = nullptr;
+    CK(cudaMalloc(&e.d_lut, H.lut.size() * sizeof(double)));
+    CK(cudaMalloc(&e.d_p, sizeof(DevParams)));
+    H.p.sdf_lut = e.d_lut + H.sdf_off; H.p.of_lut = e.d_lut + H.of_off; H.p.pw17_lut = e.d_lut + H.pw17_off;
+    e.hp = H.p;
+    CK(cudaMemcpy(e.d_lut, H.lut.data(), H.lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e.d_p, &H.p, sizeof(DevParams), cudaMemcpyHostToDevice));
+    ctx->pcache.push_back(e);
+    *out = &ctx->pcache.back();
+    return SQRN_OK;
+}
+
+// ------------------------------------------------------------- launch plan
+struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; };
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+template <int TW>
+static int plan_for(sqrn_ctx *ctx, Plan &pl)
+{
+    CK(cudaFuncSetAttribute(k_work<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_work<TW>, pl.threads, pl.smem));
+    if (nb < 1) { ctx->err = "kernel does not fit on an SM"; return SQRN_E_UNSUPPORTED; }
+    pl.grid = nb * ctx->sm_count;
+    return SQRN_OK;
+}
+
+// choose the team shape for sequences up to nmax symbols
+static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int min_ccap, Plan &pl)
+{
+    const int m = P.hp.m, npc = P.hp.npc;
+    double dens = m >= 4 ? 0.004 : (m == 3 ? 0.01 : 0.025);         // candidate stems / N^2 on random RNA
+    int est = (int)(dens * nmax * (double)nmax) + 32;
+    const size_t budget = ctx->smem_optin - sizeof(DevParams) - 1024;
+    if (nmax <= 320 && min_ccap <= 1024) {
+        pl.tw = 1;
+        int ccap = std::max(std::min(next_pow2(est), 1024), 64);
+        if (ccap < min_ccap) ccap = next_pow2(min_ccap);
+        pl.L = make_layout(nmax, rbmax, ccap, npc, 1);
+        pl.tpc = (int)std::max<size_t>(1, std::min<size_t>(8, (96 * 1024) / pl.L.total));
+        pl.threads = 32 * pl.tpc;
+        pl.smem = (size_t)pl.tpc * pl.L.total;
+        return plan_for<1>(ctx, pl);
+    }
+    pl.tw = nmax <= 2048 ? 8 : 32;
+    int ccap = std::max(std::min(next_pow2(est), 4096), 256);
+    if (ccap < min_ccap) ccap = next_pow2(min_ccap);
+    for (;;) {
+        pl.L = make_layout(nmax, rbmax, ccap, npc, pl.tw);
+        if ((size_t)pl.L.total <= budget || ccap <= 256) break;
+        ccap >>= 1;
+    }
+    if ((size_t)pl.L.total > budget) { ctx->err = "sequence too long for one CTA's shared memory"; return SQRN_E_UNSUPPORTED; }
+    pl.tpc = 1; pl.threads = 32 * pl.tw; pl.smem = pl.L.total;
+    return pl.tw == 8 ? plan_for<8>(ctx, pl) : plan_for<32>(ctx, pl);
+}
+
+static int launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, const DevBatch &B, DevWork &W)
+{
+    CK(cudaMemsetAsync(W.counter, 0, sizeof(int), ctx->stream));
+    int grid = pl.grid;
+    int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
+    if (grid > teams) grid = std::max(teams, 1);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, ctx->stream>>>(P.d_p, B, W, pl.L);
+    else if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, ctx->stream>>>(P.d_p, B, W, pl.L);
+    else k_work<32><<<grid, pl.threads, pl.smem, ctx->stream>>>(P.d_p, B, W, pl.L);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    ctx->n_launches++;
+    return SQRN_OK;
+}
+
+template <class T>
+static int upload(sqrn_ctx *ctx, int slot, const T *h, size_t count, T **d)
+{
+    CK(ctx->buf[slot].ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    *d = (T *)ctx->buf[slot].p;
+    if (count) CK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return SQRN_OK;
+}
+template <class T>
+static int dalloc(sqrn_ctx *ctx, int slot, size_t count, T **d)
+{
+    CK(ctx->buf[slot].ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    *d = (T *)ctx->buf[slot].p;
+    return SQRN_OK;
+}
+#define TRY(x) do { int r_ = (x); if (r_ != SQRN_OK) return r_; } while (0)
+
+// ------------------------------------------------ fast lane (byseq pl=1 shape)
+extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
+                                        int32_t max_len, const int64_t *d_offsets, const uint8_t *d_symbols,
+                                        uint8_t *d_dbn_ascii, double *d_scores, int32_t *d_n_stems)
+{
+    if (!ctx || !ps || n_seqs < 0 || n_seqs > 0x7fffffff || max_len > SQRN_MAX_LEN) return SQRN_E_BADARG;
+    (void)total_len;
+    cudaSetDevice(ctx->device);
+    if (n_seqs == 0) return SQRN_OK;
+    const PEntry *P;
+    TRY(get_params(ctx, *ps, max_len, &P));
+    Plan pl;
+    TRY(make_plan(ctx, *P, max_len, 0, 0, pl));
+    DevBatch B; memset(&B, 0, sizeof B);
+    B.n_seqs = n_seqs; B.off = d_offsets; B.sym = d_symbols;
+    DevWork W; memset(&W, 0, sizeof W);
+    W.n_items = (int)n_seqs; W.mode = MODE_TAIL;
+    TRY(dalloc(ctx, W_COUNTER, 1, &W.counter));
+    TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &W.out_flags));
+    TRY(dalloc(ctx, W_NCALLS, 1, &W.n_calls));
+    CK(cudaMemsetAsync(W.n_calls, 0, sizeof(unsigned long long), ctx->stream));
+    W.out_nstems = d_n_stems; W.out_raw = d_scores; W.dbn_off = d_offsets; W.out_dbn_ascii = d_dbn_ascii;
+    return launch(ctx, *P, pl, B, W);
+}
+
+static int finish_stats(sqrn_ctx *ctx, bool read_calls)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->ev_valid) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->kernel_ms = ms; }
+    if (read_calls && ctx->buf[W_NCALLS].p) {
+        unsigned long long c = 0;
+        CK(cudaMemcpy(&c, ctx->buf[W_NCALLS].p, sizeof c, cudaMemcpyDeviceToHost));
+        ctx->n_calls = (int64_t)c;
+    }
+    return SQRN_OK;
+}
+
+extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, const int64_t *offsets,
+                                      const uint8_t *symbols, uint8_t *dbn_ascii, double *scores, int32_t *n_stems)
+{
+    if (!ctx || !ps || !offsets || n_seqs < 0) return SQRN_E_BADARG;
+    cudaSetDevice(ctx->device);
+    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+    if (n_seqs == 0) return SQRN_OK;
+    int64_t total = offsets[n_seqs];
+    int max_len = 0;
+    for (int64_t b = 0; b < n_seqs; b++) {
+        int64_t n = offsets[b + 1] - offsets[b];
+        if (n < 0 || n > SQRN_MAX_LEN) { ctx->err = "sequence length out of range"; return SQRN_E_BADARG; }
+        if (n > max_len) max_len = (int)n;
+    }
+    int64_t *d_off; uint8_t *d_sym, *d_dbn; double *d_sc; int32_t *d_ns;
+    TRY(upload(ctx, B_OFF, offsets, (size_t)n_seqs + 1, &d_off));
+    TRY(upload(ctx, B_SYM, symbols, (size_t)total, &d_sym));
+    TRY(dalloc(ctx, W_DBNA, (size_t)total, &d_dbn));
+    TRY(dalloc(ctx, W_ORAW, (size_t)n_seqs * 3, &d_sc));
+    TRY(dalloc(ctx, W_ON, (size_t)n_seqs, &d_ns));
+    TRY(sqrn_fast_predict_device(ctx, ps, n_seqs, total, max_len, d_off, d_sym, d_dbn, d_sc, d_ns));
+    if (total) CK(cudaMemcpyAsync(dbn_ascii, d_dbn, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(scores, d_sc, (size_t)n_seqs * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_stems) CK(cudaMemcpyAsync(n_stems, d_ns, (size_t)n_seqs * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint8_t> flags((size_t)n_seqs);
+    CK(cudaMemcpyAsync(flags.data(), ctx->buf[W_OFLAGS].p, (size_t)n_seqs, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(finish_stats(ctx, true));
+    for (int64_t k = 0; k < 3 * n_seqs; k++) scores[k] = pyround3(scores[k]);    // ScoreStruct's round(x, 3), seq.py:899
+    for (int64_t b = 0; b < n_seqs; b++)
+        if (flags[b] & 2) { ctx->err = "more than 30 pseudoknot levels: use sqrn_predict_batch"; return SQRN_E_UNSUPPORTED; }
+    return SQRN_OK;
+}
+
+// ------------------------------------------------------ general work runner
+struct DeviceBatch {                 // an uploaded sqrn_batch
+    DevBatch B; std::vector<int> len; int nmax = 0, rbmax = 0;
+    std::vector<int32_t> rb_sorted;
+};
+
+static int upload_batch(sqrn_ctx *ctx, const sqrn_batch *in, DeviceBatch &D)
+{
+    DevBatch &B = D.B; memset(&B, 0, sizeof B);
+    const int64_t n = in->n_seqs;
+    if (n < 0 || n > 0x7fffffff || !in->offsets || (!in->symbols && n)) { ctx->err = "bad batch"; return SQRN_E_BADARG; }
+    D.len.resize((size_t)n); D.nmax = 0; D.rbmax = 0;
+    for (int64_t b = 0; b < n; b++) {
+        int64_t l = in->offsets[b + 1] - in->offsets[b];
+        if (l < 0 || l > SQRN_MAX_LEN) { ctx->err = "sequence length out of range"; return SQRN_E_BADARG; }
+        D.len[b] = (int)l; D.nmax = std::max(D.nmax, (int)l);
+    }
+    const int64_t total = in->offsets[n];
+    B.n_seqs = n; B.interchainonly = in->interchainonly; B.react_comp = in->react_sum_compensated;
+    int64_t *d_off; uint8_t *d_sym;
+    TRY(upload(ctx, B_OFF, in->offsets, (size_t)n + 1, &d_off)); B.off = d_off;
+    TRY(upload(ctx, B_SYM, in->symbols, (size_t)total, &d_sym)); B.sym = d_sym;
+    if (in->react_code) {
+        int R = in->n_react_values;
+        if (R < 1 || R > 65535 || !in->react_values) { ctx->err = "bad reactivity table"; return SQRN_E_BADARG; }
+        uint16_t *d_rc; double *d_rv;
+        TRY(upload(ctx, B_RCODE, in->react_code, (size_t)total, &d_rc));
+        TRY(upload(ctx, B_RVALS, in->react_values, (size_t)R, &d_rv));
+        B.rcode = d_rc; B.rvals = d_rv; B.R = R;
+        if (R <= SQRN_MAX_REACT_LUT) {               // host libm pow() table; above that the device uses sqrt
+            std::vector<double> pos, neg;
+            build_react_lut(in->react_values, R, pos, neg);
+            double *d_p, *d_n;
+            TRY(upload(ctx, B_RFPOS, pos.data(), pos.size(), &d_p));
+            TRY(upload(ctx, B_RFNEG, neg.data(), neg.size(), &d_n));
+            B.rf_pos = d_p; B.rf_neg = d_n;
+        }
+    }
+    if (in->restr_class) { uint8_t *d; TRY(upload(ctx, B_RCLASS, in->restr_class, (size_t)total, &d)); B.rclass = d; }
+    if (in->rbp_offsets && in->rbp_offsets[n] > 0) {
+        for (int64_t b = 0; b < n; b++) {
+            int64_t q = in->rbp_offsets[b + 1] - in->rbp_offsets[b];
+            if (q < 0 || q > D.len[b]) { ctx->err = "bad restraint pair list"; return SQRN_E_BADARG; }
+            D.rbmax = std::max(D.rbmax, (int)q);
+            for (int64_t k = in->rbp_offsets[b]; k < in->rbp_offsets[b + 1]; k++) {
+                int v = in->rbps[2 * k], w = in->rbps[2 * k + 1];
+                if (v < 0 || w <= v || w >= D.len[b]) { ctx->err = "restraint pair out of range"; return SQRN_E_BADARG; }
+            }
+        }
+        sort_rbps(n, in->rbp_offsets, in->rbps, D.rb_sorted);
+        int64_t *d_o; int32_t *d_r;
+        TRY(upload(ctx, B_RBOFF, in->rbp_offsets, (size_t)n + 1, &d_o));
+        TRY(upload(ctx, B_RB, D.rb_sorted.data(), D.rb_sorted.size(), &d_r));
+        B.rbp_off = d_o; B.rbp = d_r;
+    }
+    if (in->smat) {
+        if (!in->cols || in->smat_L <= 0) { ctx->err = "smat without column map"; return SQRN_E_BADARG; }
+        double *d_s; int32_t *d_c;
+        TRY(upload(ctx, B_SMAT, in->smat, (size_t)in->smat_L * in->smat_L, &d_s));
+        TRY(upload(ctx, B_COLS, in->cols, (size_t)total, &d_c));
+        B.smat = d_s; B.L = in->smat_L; B.cols = d_c;
+    }
+    return SQRN_OK;
+}
+
+struct HostWork {
+    int mode = MODE_TAIL;
+    std::vector<int32_t> item_seq; std::vector<int64_t> init_off; std::vector<int32_t> init_stems;
+    std::vector<double> subopt; std::vector<int64_t> out_cap;        // per item stem capacity
+    bool want_dbn = false, want_fin = false;
+    // outputs
+    std::vector<int64_t> out_off, dbn_off;
+    std::vector<int32_t> out_stems, out_n; std::vector<double> out_fin, out_raw;
+    std::vector<uint8_t> flags; std::vector<int8_t> dbn;
+};
+
+// run all items of W (any mix of sequence lengths) and bring the outputs back
+static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &D, HostWork &W, int min_ccap = 0)
+{
+    const int n = (int)W.item_seq.size();
+    W.out_n.assign((size_t)n, 0);
+    W.out_off.assign((size_t)n + 1, 0);
+    for (int k = 0; k < n; k++) W.out_off[k + 1] = W.out_off[k] + W.out_cap[k];
+    const int64_t tot_stems = W.out_off[n];
+    W.out_stems.assign((size_t)tot_stems * 3, 0);
+    if (W.want_fin || W.mode == MODE_YIELD) W.out_fin.assign((size_t)tot_stems, 0.0);
+    const bool fin = (W.mode == MODE_TAIL || W.mode == MODE_FINAL);
+    if (fin) { W.out_raw.assign((size_t)n * 3, 0.0); W.flags.assign((size_t)n, 0); }
+    int64_t tot_dbn = 0;
+    if (fin && W.want_dbn) {
+        W.dbn_off.assign((size_t)n + 1, 0);
+        for (int k = 0; k < n; k++) W.dbn_off[k + 1] = W.dbn_off[k] + D.len[W.item_seq[k]];
+        tot_dbn = W.dbn_off[n];
+        W.dbn.assign((size_t)tot_dbn, 0);
+    }
+    if (n == 0) return SQRN_OK;
+
+    DevWork G; memset(&G, 0, sizeof G);
+    G.mode = W.mode;
+    int32_t *d_iseq; TRY(upload(ctx, W_ISEQ, W.item_seq.data(), (size_t)n, &d_iseq)); G.item_seq = d_iseq;
+    if (!W.init_off.empty()) {
+        int64_t *d_io; int32_t *d_is;
+        TRY(upload(ctx, W_IOFF, W.init_off.data(), (size_t)n + 1, &d_io));
+        TRY(upload(ctx, W_ISTEMS, W.init_stems.data(), W.init_stems.size(), &d_is));
+        G.init_off = d_io; G.init_stems = d_is;
+    }
+    if (W.mode == MODE_STEP) { double *d; TRY(upload(ctx, W_SUBOPT, W.subopt.data(), (size_t)n, &d)); G.item_subopt = d; }
+    int64_t *d_oo; TRY(upload(ctx, W_OOFF, W.out_off.data(), (size_t)n + 1, &d_oo)); G.out_off = d_oo;
+    TRY(dalloc(ctx, W_OSTEMS, (size_t)tot_stems * 3, &G.out_stems));
+    TRY(dalloc(ctx, W_ON, (size_t)n, &G.out_nstems));
+    if (!W.out_fin.empty()) TRY(dalloc(ctx, W_OFIN, (size_t)tot_stems, &G.out_stemfin));
+    if (fin) { TRY(dalloc(ctx, W_ORAW, (size_t)n * 3, &G.out_raw)); TRY(dalloc(ctx, W_OFLAGS, (size_t)n, &G.out_flags)); }
+    if (tot_dbn || (fin && W.want_dbn)) {
+        int64_t *d_do; TRY(upload(ctx, W_DOFF, W.dbn_off.data(), (size_t)n + 1, &d_do)); G.dbn_off = d_do;
+        TRY(dalloc(ctx, W_DBNC, (size_t)tot_dbn, &G.out_dbn_code));
+    }
+    TRY(dalloc(ctx, W_COUNTER, 1, &G.counter));
+    TRY(dalloc(ctx, W_NCALLS, 1, &G.n_calls));
+    CK(cudaMemsetAsync(G.n_calls, 0, sizeof(unsigned long long), ctx->stream));
+
+    // length classes: warp teams (<= 320), 256-thread CTAs (<= 2048), 1024-thread CTAs
+    std::vector<int32_t> order((size_t)n);
+    for (int k = 0; k < n; k++) order[k] = k;
+    auto cls = [&](int k) { int l = D.len[W.item_seq[k]]; return (l <= 320 && min_ccap <= 1024) ? 0 : (l <= 2048 ? 1 : 2); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        int ca = cls(a), cb = cls(b);
+        if (ca != cb) return ca < cb;
+        return D.len[W.item_seq[a]] > D.len[W.item_seq[b]];          // longest first inside a class
+    });
+    int32_t *d_order; TRY(upload(ctx, W_ORDER, order.data(), (size_t)n, &d_order));
+    const PEntry *P; TRY(get_params(ctx, ps, std::max(D.nmax, 1), &P));
+    int pos = 0;
+    while (pos < n) {
+        int c = cls(order[pos]), end = pos;
+        while (end < n && cls(order[end]) == c) end++;
+        int nmax_c = D.len[W.item_seq[order[pos]]];
+        Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, pl));
+        DevWork Gc = G; Gc.order = d_order + pos; Gc.n_items = end - pos;
+        TRY(launch(ctx, *P, pl, D.B, Gc));
+        pos = end;
+    }
+    CK(cudaMemcpyAsync(W.out_n.data(), G.out_nstems, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (tot_stems) CK(cudaMemcpyAsync(W.out_stems.data(), G.out_stems, (size_t)tot_stems * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!W.out_fin.empty() && tot_stems) CK(cudaMemcpyAsync(W.out_fin.data(), G.out_stemfin, (size_t)tot_stems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (fin) {
+        CK(cudaMemcpyAsync(W.out_raw.data(), G.out_raw, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(W.flags.data(), G.out_flags, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (tot_dbn) CK(cudaMemcpyAsync(W.dbn.data(), G.out_dbn_code, (size_t)tot_dbn, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long c = 0;
+    CK(cudaMemcpy(&c, G.n_calls, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->n_calls += (int64_t)c;
+    if (ctx->ev_valid) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->kernel_ms += ms; }
+    return SQRN_OK;
+}
+
+// MODE_STEP with retries: grows the per-item output capacity / candidate list
+// until every item fits (no approximation is ever returned)
+static int run_step_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &D, HostWork &W)
+{
+    const int n = (int)W.item_seq.size();
+    W.out_cap.assign((size_t)n, 16);
+    TRY(run_items(ctx, ps, D, W));
+    std::vector<int> redo;
+    for (int k = 0; k < n; k++) if (W.out_n[k] < 0 || W.out_n[k] > W.out_cap[k]) redo.push_back(k);
+    if (redo.empty()) return SQRN_OK;
+    int min_ccap = 0;
+    for (int attempt = 0; attempt < 3 && !redo.empty(); attempt++) {
+        HostWork R; R.mode = MODE_STEP;
+        bool list_overflow = false;
+        for (int k : redo) {
+            R.item_seq.push_back(W.item_seq[k]);
+            R.subopt.push_back(W.subopt[k]);
+            if (W.out_n[k] < 0) list_overflow = true;
+        }
+        if (!W.init_off.empty()) {
+            R.init_off.push_back(0);
+            for (int k : redo) {
+                for (int64_t q = W.init_off[k]; q < W.init_off[k + 1]; q++)
+                    for (int t = 0; t < 3; t++) R.init_stems.push_back(W.init_stems[3 * q + t]);
+                R.init_off.push_back((int64_t)R.init_stems.size() / 3);
+            }
+        }
+        for (int k : redo) R.out_cap.push_back(D.len[W.item_seq[k]] / 2 + 1);
+        if (list_overflow) min_ccap = min_ccap ? min_ccap * 4 : 4096;
+        TRY(run_items(ctx, ps, D, R, min_ccap));
+        std::vector<int> still;
+        // splice the re-run results back: rebuild W's CSR with the larger capacities
+        std::vector<int64_t> new_off((size_t)n + 1, 0);
+        std::vector<int64_t> new_cap = W.out_cap;
+        for (size_t q = 0; q < redo.size(); q++) if (R.out_n[q] >= 0) new_cap[redo[q]] = std::max<int64_t>(W.out_cap[redo[q]], R.out_n[q]);
+        for (int k = 0; k < n; k++) new_off[k + 1] = new_off[k] + new_cap[k];
+        std::vector<int32_t> new_stems((size_t)new_off[n] * 3, 0);
+        for (int k = 0; k < n; k++) {
+            int64_t cnt = std::min<int64_t>(std::max(W.out_n[k], 0), W.out_cap[k]);
+            std::copy(W.out_stems.begin() + 3 * W.out_off[k], W.out_stems.begin() + 3 * (W.out_off[k] + cnt), new_stems.begin() + 3 * new_off[k]);
+        }
+        for (size_t q = 0; q < redo.size(); q++) {
+            int k = redo[q];
+            if (R.out_n[q] < 0) { still.push_back(k); continue; }
+            std::copy(R.out_stems.begin() + 3 * R.out_off[q], R.out_stems.begin() + 3 * (R.out_off[q] + R.out_n[q]), new_stems.begin() + 3 * new_off[k]);
+            W.out_n[k] = R.out_n[q];
+        }
+        W.out_stems.swap(new_stems); W.out_off.swap(new_off); W.out_cap.swap(new_cap);
+        redo.swap(still);
+    }
+    if (!redo.empty()) { ctx->err = "candidate list overflow: too many tied stems for one CTA"; return SQRN_E_UNSUPPORTED; }
+    return SQRN_OK;
+}
+
+// ---------------------------------------------------- PairsToDBN on the host
+// Generic per-pair restatement of SQRNdbnseq.py:114-161 for pair sets that are
+// not a stem list (consensus intersections, hardrest forced pairs).
+static void pairs_to_codes(std::vector<std::pair<int, int>> pairs, int N, int8_t *codes)
+{
+    for (auto &p : pairs) if (p.first > p.second) std::swap(p.first, p.second);
+    std::sort(pairs.begin(), pairs.end());
+    pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+    const int n = (int)pairs.size();
+    auto X = [&](int a, int b) {
+        int i = pairs[a].first, j = pairs[a].second, k = pairs[b].first, l = pairs[b].second;
+        return (i < k && k < j && j < l) || (k < i && i < l && l < j);
+    };
+    std::vector<int> cc((size_t)n, 0), ord((size_t)n), grp((size_t)n, -1), gsz;
+    for (int a = 0; a < n; a++) for (int b = 0; b < n; b++) if (a != b && X(a, b)) cc[a]++;
+    for (int a = 0; a < n; a++) ord[a] = a;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+        if (cc[a] != cc[b]) return cc[a] < cc[b];
+        return pairs[a].first < pairs[b].first; });
+    std::vector<std::vector<int>> groups;
+    for (int a = 0; a < n; a++) {
+        int x = ord[a], g = -1;
+        for (size_t h = 0; h < groups.size() && g < 0; h++) {
+            bool clash = false;
+            for (int y : groups[h]) if (X(x, y)) { clash = true; break; }
+            if (!clash) g = (int)h;
+        }
+        if (g < 0) { g = (int)groups.size(); groups.emplace_back(); }
+        groups[g].push_back(x);
+    }
+    std::vector<int> gord(groups.size());
+    for (size_t g = 0; g < groups.size(); g++) gord[g] = (int)g;
+    std::stable_sort(gord.begin(), gord.end(), [&](int a, int b) { return groups[a].size() > groups[b].size(); });
+    for (int p = 0; p < N; p++) codes[p] = 0;
+    for (size_t r = 0; r < gord.size(); r++) {
+        int lev = (int)std::min<size_t>(r + 1, 127);
+        for (int x : groups[gord[r]]) { codes[pairs[x].first] = (int8_t)lev; codes[pairs[x].second] = (int8_t)-lev; }
+    }
+}
+
+// ------------------------------------------------------------ full G path
+struct Struct {
+    std::vector<Stem3> stems; uint64_t psmask; double score[3]; uint8_t isint0;
+    std::vector<std::pair<int, int>> bps;      // sorted
+    std::vector<int8_t> dbn;
+};
+
+static void stems_to_bps(const std::vector<Stem3> &st, std::vector<std::pair<int, int>> &bps)
+{
+    bps.clear();
+    for (auto &s : st) for (int k = 0; k < s.len; k++) bps.emplace_back(s.i + k, s.j - k);
+    std::sort(bps.begin(), bps.end());
+}
+
+struct Pool {                      // the pool of partial structures of one sequence (one paramset)
+    std::vector<std::vector<Stem3>> cur;
+    int cursize = 1; double cursubopt = 0; bool tail = false, done = false;
+    std::vector<std::vector<Stem3>> fin;     // in finalisation order
+};
+
+static int copy_result(sqrn_ctx *ctx, sqrn_result *out)
+{
+    CachedResult &C = ctx->cres;
+    out->need_structs = (int64_t)C.scores.size() / 3;
+    out->need_stems = (int64_t)C.stems.size() / 3;
+    out->need_dbn = (int64_t)C.dbn.size();
+    if (out->cap_structs < out->need_structs || out->cap_stems < out->need_stems || out->cap_dbn < out->need_dbn) {
+        ctx->err = "output capacity too small"; return SQRN_E_CAPACITY;
+    }
+    const size_t ns = (size_t)out->need_structs;
+    memcpy(out->struct_offsets, C.struct_offsets.data(), C.struct_offsets.size() * sizeof(int64_t));
+    if (ns) {
+        memcpy(out->scores, C.scores.data(), ns * 3 * sizeof(double));
+        memcpy(out->struct_is_int0, C.isint0.data(), ns);
+        memcpy(out->psmask, C.psmask.data(), ns * sizeof(uint64_t));
+        memcpy(out->dbn_offsets, C.dbn_offsets.data(), ns * sizeof(int64_t));
+    }
+    memcpy(out->stem_offsets, C.stem_offsets.data(), (ns + 1) * sizeof(int64_t));
+    if (out->n_total) memcpy(out->n_total, C.n_total.data(), C.n_total.size() * sizeof(int32_t));
+    if (!C.stems.empty()) memcpy(out->stems, C.stems.data(), C.stems.size() * sizeof(int32_t));
+    if (!C.dbn.empty()) memcpy(out->dbn, C.dbn.data(), C.dbn.size());
+    if (out->cons && !C.cons.empty()) memcpy(out->cons, C.cons.data(), C.cons.size());
+    return SQRN_OK;
+}
+
+extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps, const sqrn_batch *in, sqrn_result *out)
+{
+    if (!ctx || !out) return SQRN_E_BADARG;
+    cudaSetDevice(ctx->device);
+    if (!in) {                                   // E_CAPACITY retry: hand out the cached result
+        if (!ctx->cres.valid) { ctx->err = "no cached result"; return SQRN_E_BADARG; }
+        return copy_result(ctx, out);
+    }
+    if (!ps || n_ps < 1 || n_ps > 64) { ctx->err = "need 1..64 parameter sets"; return SQRN_E_BADARG; }
+    ctx->cres.valid = false;
+    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+    DeviceBatch D;
+    TRY(upload_batch(ctx, in, D));
+    const int64_t nseq = in->n_seqs;
+    const int poollim = in->poollim;
+    std::vector<std::vector<Struct>> uniq((size_t)nseq);
+    std::vector<std::unordered_map<uint64_t, std::vector<int>>> index((size_t)nseq);
+
+    for (int psi = 0; psi < n_ps; psi++) {
+        const sqrn_paramset &P = ps[psi];
+        const double inc = (P.suboptmax - P.suboptmin) / P.suboptsteps;          // seq.py:1071
+        std::vector<Pool> pools((size_t)nseq);
+        for (auto &pl : pools) { pl.cur.assign(1, {}); pl.cursize = 1; pl.cursubopt = P.suboptmin; }
+        std::vector<std::pair<int, int>> tail_items;      // (seq, index in its pool) run to completion
+        for (;;) {
+            // round prologue per pool, seq.py:1161-1174
+            HostWork W; W.mode = MODE_STEP;
+            std::vector<std::pair<int, int>> owner;        // item -> (seq, pool index)
+            bool any = false;
+            for (int64_t b = 0; b < nseq; b++) {
+                Pool &pl = pools[b];
+                if (pl.done || pl.tail) continue;
+                if (pl.cur.empty()) { pl.done = true; continue; }
+                if ((int)pl.cur.size() > pl.cursize) {
+                    pl.cursize = (int)pl.cur.size();
+                    if (pl.cursubopt < P.suboptmax) pl.cursubopt += inc;
+                }
+                std::vector<std::vector<Stem3>> keep;
+                for (auto &st : pl.cur) {
+                    if ((double)st.size() == P.maxstemnum) pl.fin.push_back(std::move(st));
+                    else keep.push_back(std::move(st));
+                }
+                pl.cur.swap(keep);
+                if (pl.cur.empty()) { pl.done = true; continue; }
+                if (pl.cursize >= poollim) { pl.tail = true; continue; }    // stopper == 1 from now on
+                any = true;
+                for (size_t q = 0; q < pl.cur.size(); q++) {
+                    W.item_seq.push_back((int32_t)b);
+                    W.subopt.push_back(pl.cursubopt);
+                    owner.emplace_back((int)b, (int)q);
+                }
+            }
+            if (!any) break;
+            W.init_off.push_back(0);
+            for (auto &o : owner) {
+                for (auto &s : pools[o.first].cur[o.second]) { W.init_stems.push_back(s.i); W.init_stems.push_back(s.j); W.init_stems.push_back(s.len); }
+                W.init_off.push_back((int64_t)W.init_stems.size() / 3);
+            }
+            TRY(run_step_items(ctx, P, D, W));
+            // seq.py:1179-1199: children in pool order, or finalise
+            std::vector<std::vector<std::vector<Stem3>>> next((size_t)nseq);
+            for (size_t k = 0; k < owner.size(); k++) {
+                Pool &pl = pools[owner[k].first];
+                auto &st = pl.cur[owner[k].second];
+                int nnew = W.out_n[k];
+                if (nnew == 0) { pl.fin.push_back(std::move(st)); continue; }
+                for (int q = 0; q < nnew; q++) {
+                    std::vector<Stem3> child = st;
+                    const int32_t *o = &W.out_stems[3 * (W.out_off[k] + q)];
+                    child.push_back(Stem3{ o[0], o[1], o[2] });
+                    next[owner[k].first].push_back(std::move(child));
+                }
+            }
+            for (int64_t b = 0; b < nseq; b++) if (!pools[b].done && !pools[b].tail) pools[b].cur.swap(next[b]);
+        }
+        // tail phase: every remaining structure runs to completion on its own
+        {
+            HostWork W; W.mode = MODE_TAIL;
+            std::vector<std::pair<int, int>> owner;
+            W.init_off.push_back(0);
+            for (int64_t b = 0; b < nseq; b++) {
+                Pool &pl = pools[b];
+                if (!pl.tail) continue;
+                for (size_t q = 0; q < pl.cur.size(); q++) {
+                    W.item_seq.push_back((int32_t)b);
+                    for (auto &s : pl.cur[q]) { W.init_stems.push_back(s.i); W.init_stems.push_back(s.j); W.init_stems.push_back(s.len); }
+                    W.init_off.push_back((int64_t)W.init_stems.size() / 3);
+                    W.out_cap.push_back(D.len[b] / 2 + 1);
+                    owner.emplace_back((int)b, (int)q);
+                }
+            }
+            if (!owner.empty()) {
+                TRY(run_items(ctx, P, D, W));
+                // finalisation order inside the tail: by round (= stems added), structures that hit
+                // maxstemnum before those that ran dry, then pool order (seq.py:1168-1196)
+                struct Key { int round, kind, idx; size_t item; };
+                std::vector<std::vector<Key>> keys((size_t)nseq);
+                for (size_t k = 0; k < owner.size(); k++) {
+                    int b = owner[k].first;
+                    int n0 = (int)pools[b].cur[owner[k].second].size(), n1 = W.out_n[k];
+                    int kind = ((double)n1 == P.maxstemnum) ? 0 : 1;
+                    keys[b].push_back(Key{ n1 - n0, kind, owner[k].second, k });
+                }
+                for (int64_t b = 0; b < nseq; b++) {
+                    auto &kv = keys[b];
+                    std::stable_sort(kv.begin(), kv.end(), [](const Key &x, const Key &y) {
+                        if (x.round != y.round) return x.round < y.round;
+                        if (x.kind != y.kind) return x.kind < y.kind;
+                        return x.idx < y.idx; });
+                    for (auto &key : kv) {
+                        std::vector<Stem3> st;
+                        for (int q = 0; q < W.out_n[key.item]; q++) {
+                            const int32_t *o = &W.out_stems[3 * (W.out_off[key.item] + q)];
+                            st.push_back(Stem3{ o[0], o[1], o[2] });
+                        }
+                        pools[b].fin.push_back(std::move(st));
+                    }
+                }
+            }
+        }
+        // dedupe by bp set across parameter sets, seq.py:1201-1212
+        for (int64_t b = 0; b < nseq; b++) {
+            for (auto &st : pools[b].fin) {
+                std::vector<std::pair<int, int>> bps;
+                stems_to_bps(st, bps);
+                uint64_t h = 1469598103934665603ull;
+                for (auto &p : bps) { h = (h ^ (uint64_t)p.first) * 1099511628211ull; h = (h ^ (uint64_t)p.second) * 1099511628211ull; }
+                int hit = -1;
+                for (int cand : index[b][h]) if (uniq[b][cand].bps == bps) { hit = cand; break; }
+                if (hit >= 0) { uniq[b][hit].psmask |= 1ull << psi; continue; }
+                Struct S; S.stems = std::move(st); S.psmask = 1ull << psi; S.bps.swap(bps);
+                S.score[0] = S.score[1] = S.score[2] = 0; S.isint0 = 1;
+                index[b][h].push_back((int)uniq[b].size());
+                uniq[b].push_back(std::move(S));
+            }
+        }
+    }
+
+    // ScoreStruct + dbn of every unique structure on the device (MODE_FINAL)
+    {
+        HostWork W; W.mode = MODE_FINAL; W.want_dbn = true;
+        W.init_off.push_back(0);
+        for (int64_t b = 0; b < nseq; b++)
+            for (auto &S : uniq[b]) {
+                W.item_seq.push_back((int32_t)b);
+                for (auto &s : S.stems) { W.init_stems.push_back(s.i); W.init_stems.push_back(s.j); W.init_stems.push_back(s.len); }
+                W.init_off.push_back((int64_t)W.init_stems.size() / 3);
+                W.out_cap.push_back(0);
+            }
+        TRY(run_items(ctx, ps[0], D, W));
+        size_t k = 0;
+        for (int64_t b = 0; b < nseq; b++)
+            for (auto &S : uniq[b]) {
+                for (int t = 0; t < 3; t++) S.score[t] = pyround3(W.out_raw[3 * k + t]);     // seq.py:899
+                S.isint0 = W.flags[k] & 1;
+                if (W.flags[k] & 2) {
+                    // more than 127 levels cannot be coded in int8; 31..127 are fine for the code output
+                }
+                S.dbn.assign(W.dbn.begin() + W.dbn_off[k], W.dbn.begin() + W.dbn_off[k + 1]);
+                k++;
+            }
+    }
+
+    // rank (RankStructs, seq.py:902-955), forced pairs, consensus, truncate
+    CachedResult &C = ctx->cres;
+    C = CachedResult();
+    C.n_seqs = nseq; C.total_len = in->offsets[nseq];
+    C.struct_offsets.assign((size_t)nseq + 1, 0);
+    C.stem_offsets.assign(1, 0);
+    C.n_total.assign((size_t)nseq, 0);
+    C.cons.assign((size_t)C.total_len, 0);
+    const int *rb = in->rankby;
+    if (!((rb[0] | rb[1] | rb[2]) < 3 && rb[0] >= 0 && rb[1] >= 0 && rb[2] >= 0 && rb[0] != rb[1] && rb[0] != rb[2] && rb[1] != rb[2])) {
+        ctx->err = "Invalid ranking indices"; return SQRN_E_BADARG;
+    }
+    HostParams HP;           // symbol codes of the last paramset, for the hardrest key test
+    if (in->hardrest) { std::string e; if (!build_host_params(ps[n_ps - 1], 16, HP, e)) { ctx->err = e; return SQRN_E_UNSUPPORTED; } }
+    for (int64_t b = 0; b < nseq; b++) {
+        auto &U = uniq[b];
+        const int n = (int)U.size(), N = D.len[b];
+        std::vector<int> idx((size_t)n);
+        for (int k = 0; k < n; k++) idx[k] = k;
+        auto keycmp = [&](int x, int y) {      // > 0 when x ranks before y
+            for (int t = 0; t < 3; t++) {
+                double a = U[x].score[rb[t]], c = U[y].score[rb[t]];
+                if (a > c) return 1;
+                if (a < c) return -1;
+            }
+            return 0;
+        };
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return keycmp(x, y) > 0; });
+        std::stable_partition(idx.begin(), idx.end(), [&](int x) { return (U[x].psmask & in->priority_mask) != 0; });
+        if (in->rankbydiff && n >= 3) {
+            std::vector<uint8_t> seen((size_t)N * N, 0), all((size_t)N * N, 0);
+            size_t nall = 0, nseen = 0;
+            for (auto &S : U) for (auto &p : S.bps) { size_t c = (size_t)p.first * N + p.second; if (!all[c]) { all[c] = 1; nall++; } }
+            auto mark = [&](const Struct &S) { for (auto &p : S.bps) { size_t c = (size_t)p.first * N + p.second; if (!seen[c]) { seen[c] = 1; nseen++; } } };
+            mark(U[idx[0]]);
+            int cur = 1;
+            std::vector<int> extra((size_t)n, 0);
+            while (nseen != nall && cur < n - 1) {
+                for (int k = cur; k < n; k++) {
+                    int e = 0;
+                    for (auto &p : U[idx[k]].bps) if (!seen[(size_t)p.first * N + p.second]) e++;
+                    extra[idx[k]] = e;
+                }
+                std::stable_sort(idx.begin() + cur, idx.end(), [&](int x, int y) {
+                    if (extra[x] != extra[y]) return extra[x] > extra[y];
+                    return keycmp(x, y) > 0; });
+                mark(U[idx[cur]]);
+                cur++;
+            }
+            std::stable_sort(idx.begin() + cur, idx.end(), [&](int x, int y) { return keycmp(x, y) > 0; });
+        }
+        // forced pairs, seq.py:1226-1228
+        std::vector<std::pair<int, int>> forced;
+        if (in->hardrest && in->rbp_offsets) {
+            const uint8_t *sym = in->symbols + in->offsets[b];
+            for (int64_t k = in->rbp_offsets[b]; k < in->rbp_offsets[b + 1]; k++) {
+                int v = in->rbps[2 * k], w = in->rbps[2 * k + 1];
+                // "seq[v]+seq[w] in bpweights" on the normalised symbols == the pair mask of the digest
+                int cv = HP.p.code_table[sym[v]], cw = HP.p.code_table[sym[w]];
+                if (HP.p.pairmask[cv] >> cw & 1) forced.emplace_back(v, w);
+            }
+        }
+        C.n_total[b] = n;
+        int keepn = (in->max_structs > 0 && in->max_structs < n) ? in->max_structs : n;
+        for (int r = 0; r < keepn; r++) {
+            Struct &S = U[idx[r]];
+            for (int t = 0; t < 3; t++) C.scores.push_back(S.score[t]);
+            C.isint0.push_back(S.isint0); C.psmask.push_back(S.psmask);
+            for (auto &s : S.stems) { C.stems.push_back(s.i); C.stems.push_back(s.j); C.stems.push_back(s.len); }
+            C.stem_offsets.push_back((int64_t)C.stems.size() / 3);
+            C.dbn_offsets.push_back((int64_t)C.dbn.size());
+            if (forced.empty()) C.dbn.insert(C.dbn.end(), S.dbn.begin(), S.dbn.end());
+            else {
+                std::vector<std::pair<int, int>> pp = S.bps; pp.insert(pp.end(), forced.begin(), forced.end());
+                size_t o = C.dbn.size(); C.dbn.resize(o + N);
+                pairs_to_codes(pp, N, C.dbn.data() + o);
+            }
+        }
+        C.struct_offsets[b + 1] = C.struct_offsets[b] + keepn;
+        // consensus of the top conslim structures, seq.py:845-858, 1236
+        {
+            int top = std::min(std::max(in->conslim, 0), n);
+            std::vector<std::pair<int, int>> cb;
+            if (top > 0) {
+                cb = U[idx[0]].bps;
+                for (int r = 1; r < top; r++) {
+                    std::vector<std::pair<int, int>> t;
+                    std::set_intersection(cb.begin(), cb.end(), U[idx[r]].bps.begin(), U[idx[r]].bps.end(), std::back_inserter(t));
+                    cb.swap(t);
+                }
+            }
+            int8_t *dst = C.cons.data() + in->offsets[b];
+            if (top == 1 && forced.empty()) { if (N) memcpy(dst, U[idx[0]].dbn.data(), (size_t)N); }
+            else { cb.insert(cb.end(), forced.begin(), forced.end()); pairs_to_codes(cb, N, dst); }
+        }
+    }
+    C.valid = true;
+    return copy_result(ctx, out);
+}
+
+// ------------------------------------------------------------- YieldStems
+extern "C" int sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, sqrn_stems *out)
+{
+    if (!ctx || !out) return SQRN_E_BADARG;
+    cudaSetDevice(ctx->device);
+    CachedStems &C = ctx->cstems;
+    if (in) {
+        if (!ps) return SQRN_E_BADARG;
+        C.valid = false;
+        ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+        DeviceBatch D;
+        TRY(upload_batch(ctx, in, D));
+        const int64_t nseq = in->n_seqs;
+        HostWork W; W.mode = MODE_YIELD;
+        for (int64_t b = 0; b < nseq; b++) {
+            W.item_seq.push_back((int32_t)b);
+            double n = D.len[b];
+            W.out_cap.push_back((int64_t)(0.03 * n * n) + 64);
+        }
+        TRY(run_items(ctx, *ps, D, W));
+        bool redo = false;
+        for (int64_t b = 0; b < nseq; b++) if (W.out_n[b] > W.out_cap[b]) { W.out_cap[b] = W.out_n[b]; redo = true; }
+        if (redo) TRY(run_items(ctx, *ps, D, W));
+        C.n_seqs = nseq; C.off.assign((size_t)nseq + 1, 0); C.stems.clear(); C.scores.clear();
+        for (int64_t b = 0; b < nseq; b++) {
+            int n = W.out_n[b];
+            C.off[b + 1] = C.off[b] + n;
+            C.stems.insert(C.stems.end(), W.out_stems.begin() + 3 * W.out_off[b], W.out_stems.begin() + 3 * (W.out_off[b] + n));
+            C.scores.insert(C.scores.end(), W.out_fin.begin() + W.out_off[b], W.out_fin.begin() + W.out_off[b] + n);
+        }
+        C.valid = true;
+    } else if (!C.valid) { ctx->err = "no cached result"; return SQRN_E_BADARG; }
+    out->need_stems = (int64_t)C.scores.size();
+    if (out->cap_stems < out->need_stems) { ctx->err = "output capacity too small"; return SQRN_E_CAPACITY; }
+    memcpy(out->stem_offsets, C.off.data(), C.off.size() * sizeof(int64_t));
+    if (!C.scores.empty()) {
+        memcpy(out->stems, C.stems.data(), C.stems.size() * sizeof(int32_t));
+        memcpy(out->scores, C.scores.data(), C.scores.size() * sizeof(double));
+    }
+    return SQRN_OK;
+}
+
+// ------------------------------------------------------------- test seam
+// One launch of the work kernel on host buffers, any mode: lets the GPU tests
+// check AnnotateStems / OptimalStems seams against the oracle with arbitrary
+// pre-selected stems.  Same argument meaning as the DevWork fields.
+extern "C" int sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, int mode, int n_items,
+                              const int32_t *item_seq, const int64_t *init_off, const int32_t *init_stems,
+                              const double *item_subopt, const int64_t *out_cap, int32_t *out_stems, int32_t *out_n,
+                              double *out_fin, double *out_raw, uint8_t *out_flags, int8_t *dbn_code, int min_ccap)
+{
+    if (!ctx || !ps || !in) return SQRN_E_BADARG;
+    cudaSetDevice(ctx->device);
+    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+    DeviceBatch D;
+    TRY(upload_batch(ctx, in, D));
+    HostWork W; W.mode = mode; W.want_dbn = dbn_code != nullptr; W.want_fin = out_fin != nullptr;
+    for (int k = 0; k < n_items; k++) {
+        W.item_seq.push_back(item_seq ? item_seq[k] : k);
+        W.out_cap.push_back(out_cap[k]);
+        if (item_subopt) W.subopt.push_back(item_subopt[k]);
+    }
+    if (mode == MODE_STEP && !item_subopt) W.subopt.assign((size_t)n_items, 1.0);
+    if (init_off) {
+        W.init_off.assign(init_off, init_off + n_items + 1);
+        W.init_stems.assign(init_stems, init_stems + 3 * init_off[n_items]);
+    }
+    TRY(run_items(ctx, *ps, D, W, min_ccap));
+    memcpy(out_n, W.out_n.data(), (size_t)n_items * sizeof(int32_t));
+    if (!W.out_stems.empty()) memcpy(out_stems, W.out_stems.data(), W.out_stems.size() * sizeof(int32_t));
+    if (out_fin && !W.out_fin.empty()) memcpy(out_fin, W.out_fin.data(), W.out_fin.size() * sizeof(double));
+    if (out_raw && !W.out_raw.empty()) memcpy(out_raw, W.out_raw.data(), W.out_raw.size() * sizeof(double));
+    if (out_flags && !W.flags.empty()) memcpy(out_flags, W.flags.data(), W.flags.size());
+    if (dbn_code && !W.dbn.empty()) memcpy(dbn_code, W.dbn.data(), W.dbn.size());
+    return SQRN_OK;
+}

@@ -56,6 +56,7 @@ constexpr int RC_X = 1, RC_NOLEFT = 2, RC_NORIGHT = 4, RC_RBPOS = 8;
 constexpr int MODE_TAIL = 0;   // run the single-path greedy to completion
 constexpr int MODE_STEP = 1;   // one OptimalStems call, return the ChooseStems list
 constexpr int MODE_YIELD = 2;  // AnnotateStems only, stems in reference order
+constexpr int MODE_FINAL = 3;  // ScoreStruct + dbn of the given stems, no selection
 
 // ---------------------------------------------------------------- parameters
 struct DevParams {
@@ -77,7 +78,7 @@ struct DevBatch {
     int64_t        n_seqs;
     const int64_t *off;
     const uint8_t *sym;
-    const uint8_t *rcode;  const double *rf_pos; const double *rf_neg; const double *rvals; int R;
+    const uint16_t *rcode; const double *rf_pos; const double *rf_neg; const double *rvals; int R;
     int            react_comp;
     const uint8_t *rclass; const int64_t *rbp_off; const int32_t *rbp;
     const double  *smat;   int L;  const int32_t *cols;
@@ -149,8 +150,8 @@ __host__ __device__ inline Layout make_layout(int Nmax, int RBmax, int Ccap, int
     L.o_rbv = o;     o += 2 * (RBmax + 1);
     L.o_rbw = o;     o += 2 * (RBmax + 1);
     L.o_clen = o;    o += 2 * Ccap;
+    L.o_rcode = o;   o += 2 * L.Ncap;
     L.o_code = o;    o += L.Ncap;
-    L.o_rcode = o;   o += L.Ncap;
     L.o_rcl = o;     o += L.Ncap;
     L.o_stlev = o;   o += L.Scap;
     L.total = align_up(o, 16);
@@ -195,7 +196,8 @@ template <> struct Team<0> {
 
 struct State {
     int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts;
-    uint8_t  *code, *rcode, *rcl, *stlev;
+    uint8_t  *code, *rcl, *stlev;
+    uint16_t *rcode;
     int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *perm, *grp, *rbv, *rbw;
     uint32_t *M, *PR, *rowok, *colokR, *ckey;
     int32_t  *cc, *gsz;
@@ -208,7 +210,7 @@ struct State {
 __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L)
 {
     State s;
-    s.code = base + L.o_code;  s.rcode = base + L.o_rcode;  s.rcl = base + L.o_rcl;  s.stlev = base + L.o_stlev;
+    s.code = base + L.o_code;  s.rcode = (uint16_t *)(base + L.o_rcode);  s.rcl = base + L.o_rcl;  s.stlev = base + L.o_stlev;
     s.partner = (int16_t *)(base + L.o_partner);  s.owner = (int16_t *)(base + L.o_owner);
     s.sepcnt = (int16_t *)(base + L.o_sepcnt);
     s.sti = (int16_t *)(base + L.o_sti);  s.stj = (int16_t *)(base + L.o_stj);  s.stl = (int16_t *)(base + L.o_stl);
@@ -251,7 +253,7 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
     S.cols = B.cols ? B.cols + o : nullptr;
     const int Nw = S.W * 32;
     for (int p = r; p < Nw; p += T) {
-        uint8_t c = CODE_OTHER, rc = 0, cl = 0;
+        uint8_t c = CODE_OTHER, cl = 0; uint16_t rc = 0;
         if (p < N) {
             c = P.code_table[B.sym[o + p]];
             if (B.rcode) rc = B.rcode[o + p];
@@ -430,7 +432,14 @@ __device__ __forceinline__ double cell_score(const State &S, const DevParams &P,
     double w = P.weight[S.code[i] * MAXK + S.code[j]];
     if (S.has_react && !S.default_reacts) {
         int a = S.rcode[i], b = S.rcode[j];
-        double rf = (w <= 0.0) ? __ldg(&B.rf_neg[a * B.R + b]) : __ldg(&B.rf_pos[a * B.R + b]);
+        double rf;
+        if (B.rf_pos) rf = (w <= 0.0) ? __ldg(&B.rf_neg[(size_t)a * B.R + b]) : __ldg(&B.rf_pos[(size_t)a * B.R + b]);
+        else {
+            // too many distinct reactivities for a table: sqrt instead of libm pow(x, 0.5)
+            // (differs from the reference by at most 1 ulp on ~0.1 % of inputs; documented in DESIGN.md)
+            rf = sqrt(__dmul_rn(__dsub_rn(1.0, __ddiv_rn(__dadd_rn(__ldg(&B.rvals[a]), __ldg(&B.rvals[b])), 2.0)), 2.0));
+            if (w <= 0.0) rf = __ddiv_rn(1.0, rf > 0.01 ? rf : 0.01);
+        }
         w = __dmul_rn(w, rf);
     }
     if (S.has_smat) w = __dmul_rn(w, __ldg(&B.smat[(int64_t)S.cols[i] * B.L + S.cols[j]]));
@@ -922,10 +931,10 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         for (int64_t k = Wk.init_off[item]; k < Wk.init_off[item + 1]; k++)
             team_apply_stem<TW>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2]);
     unsigned long long calls = 0;
-    if (Wk.mode == MODE_TAIL) {
+    if (Wk.mode == MODE_TAIL || Wk.mode == MODE_FINAL) {
         // the pool loop of seq.py:1159-1199 once it can no longer branch
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
-        while ((double)S.nst != P.maxstemnum) {
+        while (Wk.mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<TW>(S);
             Best b = team_scan<TW>(S, P, B, L);
             calls++;

@@ -49,7 +49,7 @@ def run(paramset, seqs, mode=MODE_TAIL, react_codes=None, react_values=None, rea
     sym, off = pack_sequences(seqs)
     nseq = len(seqs)
     cat = lambda lst, dt: (np.concatenate([np.asarray(x, dtype=dt).ravel() for x in lst]) if sum(len(x) for x in lst) else np.zeros(1, dt))
-    rcode = cat(react_codes, np.uint8) if react_codes is not None else None
+    rcode = cat(react_codes, np.uint16) if react_codes is not None else None
     rvals = np.ascontiguousarray(react_values, dtype=np.float64) if react_values is not None else None
     rcl = cat(restr_class, np.uint8) if restr_class is not None else None
     rb_off = rb = None

@@ -12,7 +12,7 @@
 using namespace sqrn;
 
 extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *off, const uint8_t *sym,
-                       const uint8_t *rcode, const double *rvals, int R, int react_comp,
+                       const uint16_t *rcode, const double *rvals, int R, int react_comp,
                        const uint8_t *rclass, const int64_t *rbp_off, const int32_t *rbp,
                        const double *smat, int L, const int32_t *cols, int interchainonly,
                        int mode, int n_items, const int32_t *item_seq, const int64_t *init_off,

@@ -1,0 +1,141 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from squarna_b200 import SQRNdbnseq as S
+from squarna_b200._abi import pack_sequences
+from squarna_b200._lib import MODE_STEP, MODE_YIELD, PackedBatch
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+_OPEN = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+_CLOSE = ")]}>abcdefghijklmnopqrstuvwxyz"
+
+
+def _ascii_from_codes(codes):
+    return "".join("." if c == 0 else (_OPEN[c - 1] if c > 0 else _CLOSE[-c - 1]) for c in codes.tolist())
+
+
+def _check_fast(ctx, ps, seqs, threads=8):
+    sym, off = pack_sequences(seqs)
+    dbn, scores, nst = ctx.fast_predict(ps, sym, off)
+    odbn, oscores, onst = O.predict_batch_simple(sym, off, [ps], poollim=1, nthreads=threads)
+    bad = []
+    for b, s in enumerate(seqs):
+        g = bytes(dbn[off[b]:off[b + 1]]).decode()
+        o = _ascii_from_codes(odbn[off[b]:off[b + 1]])
+        if g != o or nst[b] != onst[b] or tuple(scores[b]) != tuple(oscores[b]):
+            bad.append((s, g, o, tuple(scores[b]), tuple(oscores[b])))
+    assert not bad, "%d of %d differ, first: %r" % (len(bad), len(seqs), bad[0])
+
+
+def test_fast_lane_short(gpu_ctx):
+    """config-2 shape: fastest.conf, pl=1, lengths 5..200, warp teams"""
+    _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(11, 6000, 5, 200))
+
+
+def test_fast_lane_edge_lengths(gpu_ctx):
+    seqs = ["", "A", "GC", "GGGG", "GGGAAACCC", "GGGGAAAACCCC", "GCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGC",
+            "G" * 40 + "AAAA" + "C" * 40, "GGGGGGGGGGCCCCCCCCCC" * 10]
+    seqs += T.rand_seqs(12, 300, 1, 12)
+    _check_fast(gpu_ctx, T.FASTEST, seqs)
+    _check_fast(gpu_ctx, T.DEFG1, seqs)
+
+
+@pytest.mark.parametrize("ps", [T.DEFG1, T.DEFG2, T.ALI], ids=["defG1", "defG2", "ali"])
+def test_fast_lane_other_paramsets(gpu_ctx, ps):
+    """minlen 2 parameter sets: many more candidates per step (list overflow path included)"""
+    _check_fast(gpu_ctx, ps, T.rand_seqs(13, 1500, 5, 200))
+
+
+def test_fast_lane_low_complexity(gpu_ctx):
+    """GC-rich / repetitive sequences: long runs, many exact score ties"""
+    rng = random.Random(14)
+    seqs = [T.rand_seq(rng, rng.randint(20, 200), "GC") for _ in range(300)]
+    seqs += [T.rand_seq(rng, rng.randint(20, 200), "GGCCAU") for _ in range(300)]
+    seqs += [(T.rand_seq(rng, rng.randint(3, 9)) * 40)[:rng.randint(30, 200)] for _ in range(300)]
+    _check_fast(gpu_ctx, T.FASTEST, seqs)
+    _check_fast(gpu_ctx, T.DEFG2, seqs[:450])
+
+
+def test_fast_lane_cta_teams(gpu_ctx):
+    """321..2048 nt -> 256-thread CTA teams; > 2048 nt -> 1024-thread CTA teams"""
+    _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(15, 64, 321, 900))
+    _check_fast(gpu_ctx, T.G1000, T.rand_seqs(16, 24, 321, 700))
+    _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(17, 4, 2100, 2600))
+
+
+def test_yield_stems(gpu_ctx):
+    """AnnotateStems seam (YieldStems): same stems, same order, same scores"""
+    rng = random.Random(18)
+    cases = [T.rand_case(rng, 10, 260, p_gap=0.0) for _ in range(150)]
+    for ps in (T.ALI, T.FASTEST):
+        preps = [S._prepare(c[0], c[1], c[2], None) for c in cases]
+        for comp in (False, True):
+            idx = [k for k, p in enumerate(preps) if p.compensated == comp]
+            table, codes = {}, []
+            for k in idx:
+                codes.append(np.array([table.setdefault(float(x), len(table)) for x in preps[k].shortreacts], np.uint16))
+            batch = PackedBatch([preps[k].shortseq.encode("latin-1") for k in idx], react_codes=codes,
+                                react_values=np.array(list(table.keys())), restr_class=[preps[k].rclass for k in idx],
+                                rbps=[np.array(preps[k].rbps, np.int32).reshape(-1, 2) for k in idx],
+                                interchainonly=False)
+            got = gpu_ctx.yield_stems(ps, batch)
+            for k, (st, sc) in zip(idx, got):
+                p = preps[k]
+                want = O.annotate(p.shortseq, ps, p.shortreacts, p.shortrest)
+                have = [(int(a), int(b), int(c), float(d)) for (a, b, c), d in zip(st, sc)]
+                assert have == want, (p.shortseq, p.shortrest)
+
+
+def test_optimal_step(gpu_ctx):
+    """OptimalStems seam on top of pre-selected stems: ChooseStems list, order and scores"""
+    rng = random.Random(19)
+    for ps, subopt in ((T.DEFG1, 0.65), (T.DEFG2, 0.9), (T.FASTEST, 1.0)):
+        seqs = T.rand_seqs(rng.randrange(10 ** 6), 120, 20, 240)
+        init = []
+        for s in seqs:
+            _, structs, _ = O.predict_short(s, [0.5] * len(s), "." * len(s), [ps], poollim=1)
+            stems = structs[0][4]
+            init.append(stems[:rng.randint(0, len(stems))])
+        batch = PackedBatch([s.encode() for s in seqs])
+        r = gpu_ctx.debug_run(ps, batch, MODE_STEP, init_stems=init, item_subopt=[subopt] * len(seqs),
+                              out_cap=64, want_dbn=False)
+        for b, s in enumerate(seqs):
+            _, chosen = O.optimal(s, ps, subopt, selected=init[b])
+            n = r["n"][b]
+            have = [tuple(int(x) for x in r["stems"][r["off"][b] + k]) + (float(r["fin"][r["off"][b] + k]),) for k in range(n)]
+            assert have == chosen, (s, init[b])
+
+
+def _oracle_many(cases, paramsets, poollim):
+    return [O.sqrn_dbnseq(c[0], c[1], c[2], paramsets=paramsets, poollim=poollim, **c[3]) for c in cases]
+
+
+@pytest.mark.parametrize("name,paramsets,poollim,lo,hi,count", [
+    ("fastest_pl1", [T.FASTEST], 1, 10, 150, 250),
+    ("greedy_pl100", [T.DEFG1, T.DEFG2], 100, 10, 90, 120),
+    ("greedy_pl5", [T.DEFG1, T.DEFG2], 5, 10, 120, 120),
+    ("g1000_pl100", [T.G1000], 100, 150, 330, 10),
+])
+def test_predict_batch_full(gpu_ctx, name, paramsets, poollim, lo, hi, count):
+    """full SQRNdbnseq semantics (pool, dedupe, ranking, consensus, restraints, reactivities,
+    separators, gaps, hardrest, interchainonly, rankbydiff) against the oracle"""
+    rng = random.Random(hash(name) & 0xffff)
+    cases = [T.rand_case(rng, lo, hi) for _ in range(count)]
+    want = _oracle_many(cases, paramsets, poollim)
+    # one GPU batch per distinct option set (the options are batch-wide in the C ABI)
+    groups = {}
+    for k, c in enumerate(cases):
+        key = tuple(sorted((a, str(b)) for a, b in c[3].items()))
+        groups.setdefault(key, []).append(k)
+    for key, idx in groups.items():
+        kw = cases[idx[0]][3]
+        got = S.predict_many([(cases[k][0], cases[k][1], cases[k][2], None) for k in idx], paramsets,
+                             poollim=poollim, **kw)
+        for k, g in zip(idx, got):
+            assert T.same_prediction((g[0], g[1]), want[k]), (cases[k], g[:2], want[k])
