@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log

@@ -49,7 +49,7 @@ def load():
     L.sqrn_fast_predict_host.argtypes = [vp, C.POINTER(ParamSet), i64, vp, vp, vp, vp, vp]
     L.sqrn_fast_predict_device.argtypes = [vp, C.POINTER(ParamSet), i64, i64, i32, vp, vp, vp, vp, vp]
     L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
-    L.sqrn_debug_run.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.c_int, C.c_int] + [vp] * 12 + [C.c_int]
+    L.sqrn_debug_run.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.c_int, C.c_int] + [vp] * 11 + [C.c_int]
     _lib = L
     return L
 

@@ -812,7 +812,7 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
     C.n_total.assign((size_t)nseq, 0);
     C.cons.assign((size_t)C.total_len, 0);
     const int *rb = in->rankby;
-    if (!((rb[0] | rb[1] | rb[2]) < 3 && rb[0] >= 0 && rb[1] >= 0 && rb[2] >= 0 && rb[0] != rb[1] && rb[0] != rb[2] && rb[1] != rb[2])) {
+    if (!(rb[0] >= 0 && rb[0] < 3 && rb[1] >= 0 && rb[1] < 3 && rb[2] >= 0 && rb[2] < 3 && rb[0] != rb[1] && rb[0] != rb[2] && rb[1] != rb[2])) {
         ctx->err = "Invalid ranking indices"; return SQRN_E_BADARG;
     }
     HostParams HP;           // symbol codes of the last paramset, for the hardrest key test
