@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""Generates the golden vectors in this directory by IMPORTING THE REAL REFERENCE
+(/root/reference/src/SQUARNA, febos/SQUARNA) in the build container.
+
+    python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, so its outputs are committed here as
+JSON fixtures; tests/test_oracle_golden.py pins the CPU oracle (and the host-side
+Python of squarna_b200) to them.  Python 3.12.3 / numpy 2.3.5 / glibc 2.39 were
+used (float repr round-trips exactly through JSON).
+"""
+import io
+import json
+import os
+import random
+import sys
+
+REF = "/root/reference/src/SQUARNA"
+sys.path.insert(0, REF)
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import numpy as np  # noqa: E402
+import SQRNdbnseq as R  # noqa: E402
+import SQUARNA as RC  # noqa: E402
+
+from tests.common import rand_case, rand_seq  # noqa: E402
+
+CONFS = ["fastest", "greedynobpp", "nobpp", "500nobpp", "1000nobpp", "alt", "ali",
+         "def", "500", "1000", "greedy", "edmondsnobpp", "hungariannobpp", "nussinovnobpp",
+         "edmonds", "hungarian", "nussinov"]
+
+
+def dump(name, obj):
+    path = os.path.join(HERE, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, separators=(",", ":"))
+    print(name, os.path.getsize(path), "bytes")
+
+
+def jsonable_ps(ps):
+    d = dict(ps)
+    d["algorithms"] = sorted(d["algorithms"])
+    return d
+
+
+def gsets(conf):
+    names, psets = RC.ParseConfig(os.path.join(REF, conf + ".conf"))
+    return [p for p in psets if p["algorithms"] == {"G"} and p["bpp"] == 0]
+
+
+def main():
+    # --- G6: parsed configs ------------------------------------------------
+    confs = {}
+    for c in CONFS:
+        names, psets = RC.ParseConfig(os.path.join(REF, c + ".conf"))
+        confs[c] = {"names": names, "paramsets": [jsonable_ps(p) for p in psets]}
+    dump("configs.json", confs)
+
+    # --- G1: SQRNdbnseq end to end -------------------------------------------
+    rng = random.Random(20261017)
+    plan = [("fastest", 1, 8, 160, 90), ("fastest", 1000, 8, 120, 30), ("greedynobpp", 100, 8, 80, 60),
+            ("greedynobpp", 5, 8, 110, 40), ("greedynobpp", 1, 8, 140, 30), ("alt", 50, 20, 70, 25),
+            ("ali", 1000, 10, 90, 30), ("1000nobpp", 100, 100, 220, 8), ("500nobpp", 100, 60, 120, 6)]
+    cases = []
+    for conf, pl, lo, hi, count in plan:
+        psets = gsets(conf)
+        for _ in range(count):
+            seq, reacts, rest, kw = rand_case(rng, lo, hi)
+            if rng.random() < 0.25 and len(psets) > 1:
+                kw["priority"] = [rng.randrange(len(psets))]
+            smat = None
+            if rng.random() < 0.12 and len(seq) <= 60:
+                n = len(seq)
+                m = np.array([[rng.randrange(0, 21) / 4.0 for _ in range(n)] for _ in range(n)])
+                smat = ((m + m.T) / 2).tolist()
+            try:
+                out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=pl, algos={"G"},
+                                   stemmatrix=None if smat is None else np.array(smat),
+                                   **{k: (set(v) if k == "priority" else v) for k, v in kw.items()})
+            except ZeroDivisionError:
+                continue
+            cases.append({"conf": conf, "poollim": pl, "seq": seq, "reacts": reacts, "restraints": rest,
+                          "kw": kw, "smat": smat, "cons": out[0],
+                          "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+    dump("seq_api.json", cases)
+
+    # --- G2: BPMatrix + AnnotateStems ----------------------------------------
+    ann = []
+    for conf in ("fastest", "greedynobpp", "ali"):
+        for ps in gsets(conf)[:2]:
+            for _ in range(25):
+                seq, reacts, rest, kw = rand_case(rng, 8, 90, p_gap=0.0)
+                seq = seq.upper().replace("T", "U")
+                if isinstance(reacts, str):
+                    reacts = R.ProcessReacts([R.ReactDict[c] for c in reacts])
+                rbps, rxs, rl, rr = R.ParseRestraints(rest or "." * len(seq))
+                bm, sm = R.BPMatrix(seq, ps["bpweights"], rxs, rl, rr, kw["interchainonly"], reacts=reacts)
+                stems = R.AnnotateStems(bm, sm, rbps, [], ps["minlen"], ps["minbpscore"])
+                ann.append({"ps": jsonable_ps(ps), "seq": seq, "reacts": None if reacts is None else [float(x) for x in reacts],
+                            "restraints": rest, "interchainonly": kw["interchainonly"],
+                            "stems": [[s[0][0][0], s[0][0][1], s[1], float(s[2])] for s in stems]})
+    dump("annotate.json", ann)
+
+    # --- G3: PairsToDBN levels / glyphs on random (pseudoknotted) stem sets ----
+    lev = []
+    for _ in range(120):
+        n = rng.randint(20, 120)
+        used, pairs = set(), []
+        for _ in range(rng.randint(1, 10)):
+            i, j, ln = rng.randrange(n), rng.randrange(n), rng.randint(1, 6)
+            if i > j:
+                i, j = j, i
+            st = [(i + k, j - k) for k in range(ln) if i + k < j - k]
+            if st and not any(v in used or w in used for v, w in st):
+                pairs += st
+                used |= {p for bp in st for p in bp}
+        levels = R.PairsToDBN(pairs, returnlevels=True)
+        lev.append({"n": n, "pairs": pairs, "levels": [[k[0], k[1], v] for k, v in sorted(levels.items())],
+                    "dbn": R.PairsToDBN(pairs, n)})
+    dump("levels.json", lev)
+
+    # --- G4: OptimalStems on partial structures ---------------------------------
+    opt = []
+    for conf, subopt in (("fastest", 1.0), ("greedynobpp", 0.65), ("greedynobpp", 0.9), ("ali", 1.0)):
+        for ps in gsets(conf)[:2]:
+            for _ in range(20):
+                seq = rand_seq(rng, rng.randint(30, 130))
+                reacts = [0.5] * len(seq)
+                bm, sm = R.BPMatrix(seq, ps["bpweights"], set(), set(), set(), False, reacts=reacts)
+                # a partial structure: a random prefix of the single-path greedy result
+                stems, cur = [], []
+                while True:
+                    new = R.OptimalStems(seq, cur, bm, sm, reacts, set(), 1.0, ps["minlen"], ps["minbpscore"],
+                                         ps["minbpscore"] * ps["minfinscorefactor"], ps["bracketweight"],
+                                         ps["distcoef"], ps["orderpenalty"], ps["loopbonus"])
+                    if not new:
+                        break
+                    cur = cur + [new[0]]
+                sel = cur[:rng.randint(0, len(cur))]
+                allst = R.AnnotateStems(bm, sm, set(), sel, ps["minlen"], ps["minbpscore"])
+                scored = R.ScoreStems(seq, allst, sel, reacts, ps["minbpscore"] * ps["minfinscorefactor"],
+                                      ps["bracketweight"], ps["distcoef"], ps["orderpenalty"], ps["loopbonus"])
+                chosen = R.ChooseStems(scored, subopt)
+                opt.append({"ps": jsonable_ps(ps), "subopt": subopt, "seq": seq,
+                            "selected": [[s[0][0][0], s[0][0][1], s[1]] for s in sel],
+                            "scored": [[s[0][0][0], s[0][0][1], s[1], float(s[2]), float(s[3])] for s in scored],
+                            "chosen": [[s[0][0][0], s[0][0][1], s[1], float(s[3])] for s in chosen]})
+    dump("optimal.json", opt)
+
+    # --- G7: reactivity helpers -----------------------------------------------
+    rx = []
+    for _ in range(40):
+        vals = [rng.choice([rng.random() * 2 - 0.3, -999.0, float("nan"), 0.0, 1.0, 0.5]) for _ in range(rng.randint(1, 30))]
+        seq = rand_seq(rng, len(vals), "ACGU;")
+        for M, B in ((1.8, -0.6), (1.8, 1.6)):
+            pr = R.ProcessReacts(vals, M=M, B=B)
+            rx.append({"vals": [None if v != v else v for v in vals], "M": M, "B": B, "out": [float(x) for x in pr],
+                       "seq": seq, "enc": {str(f): R.EncodedReactivities(seq, pr, f) for f in (3, 10, 26)}})
+    dump("reacts.json", rx)
+
+
+if __name__ == "__main__":
+    main()

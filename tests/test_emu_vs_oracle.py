@@ -1,0 +1,125 @@
+"""The device functions of csrc/sqrn_device.cuh compiled for the host with a team of ONE
+thread (tests/emu) against the oracle: checks the bit-mask enumeration, the scoring, the
+per-stem level restatement and ChooseStems without a GPU.  The parallel behaviour of the
+same code is covered by the -m gpu tests."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from squarna_b200 import SQRNdbnseq as S
+from tests import common as T
+from tests.emu import emu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+_OPEN = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+_CLOSE = ")]}>abcdefghijklmnopqrstuvwxyz"
+
+
+def _prep_batch(cases):
+    preps = [S._prepare(c[0], c[1], c[2], None) for c in cases]
+    table, codes = {}, []
+    for p in preps:
+        codes.append(np.array([table.setdefault(float(x), len(table)) for x in p.shortreacts], np.uint16))
+    kw = dict(react_codes=codes, react_values=np.array(list(table.keys())),
+              restr_class=[p.rclass for p in preps],
+              rbps=[np.array(p.rbps, np.int32).reshape(-1, 2) for p in preps])
+    return preps, kw
+
+
+@pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
+                         ids=["fastest", "defG1", "defG2-smalllist", "ali"])
+def test_tail_plain(ps, ccap):
+    """single-path greedy (pl=1) on plain sequences: stems, dbn, raw scores"""
+    seqs = T.rand_seqs(31, 150, 5, 210)
+    r = emu.run(ps, seqs, ccap=ccap)
+    for b, s in enumerate(seqs):
+        _, structs, _ = O.predict_short(s, [0.5] * len(s), "." * len(s), [ps], poollim=1)
+        dbn, sc, isint, _, stems, _, _ = structs[0]
+        o = r["dbn_off"][b]
+        assert bytes(r["dbn_ascii"][o:o + len(s)]).decode() == dbn
+        assert [tuple(int(x) for x in r["stems"][r["off"][b] + k]) for k in range(r["n"][b])] == stems
+        assert tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][b]) == sc
+        assert bool(r["flags"][b] & 1) == isint
+
+
+@pytest.mark.parametrize("interchain", [False, True])
+def test_tail_with_restraints_and_reactivities(interchain):
+    rng = random.Random(32)
+    cases = [T.rand_case(rng, 8, 150, p_gap=0.2) for _ in range(200)]
+    preps, kw = _prep_batch(cases)
+    for comp in (False, True):
+        idx = [k for k, p in enumerate(preps) if p.compensated == comp]
+        sub = {k: [v[i] for i in idx] if isinstance(v, list) else v for k, v in kw.items()}
+        for ps in (T.DEFG1, T.FASTEST):
+            r = emu.run(ps, [preps[k].shortseq for k in idx], react_comp=comp, interchainonly=interchain, **sub)
+            for b, k in enumerate(idx):
+                p = preps[k]
+                _, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, [ps], interchainonly=interchain,
+                                                poollim=1, compensated_sum=comp)
+                dbn, sc, isint, _, stems, _, _ = structs[0]
+                got = [tuple(int(x) for x in r["stems"][r["off"][b] + q]) for q in range(r["n"][b])]
+                assert got == stems, (p.shortseq, p.shortrest)
+                assert tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][b]) == sc, (p.shortseq, cases[k][1])
+                codes = r["dbn_code"][r["dbn_off"][b]:r["dbn_off"][b] + len(p.shortseq)]
+                asc = "".join("." if c == 0 else (_OPEN[c - 1] if c > 0 else _CLOSE[-c - 1]) for c in codes.tolist())
+                assert asc == dbn
+
+
+def test_yield_matches_annotate():
+    rng = random.Random(33)
+    cases = [T.rand_case(rng, 8, 200, p_gap=0.0) for _ in range(120)]
+    preps, kw = _prep_batch(cases)
+    for ps in (T.ALI, T.FASTEST):
+        r = emu.run(ps, [p.shortseq for p in preps], mode=emu.MODE_YIELD, **kw)
+        for b, p in enumerate(preps):
+            want = O.annotate(p.shortseq, ps, p.shortreacts, p.shortrest)
+            lo = r["off"][b]
+            got = [(int(r["stems"][lo + q][0]), int(r["stems"][lo + q][1]), int(r["stems"][lo + q][2]), float(r["fin"][lo + q]))
+                   for q in range(r["n"][b])]
+            assert got == want, (p.shortseq, p.shortrest)
+
+
+def test_step_matches_golden_optimal():
+    """MODE_STEP (one OptimalStems + ChooseStems) against the REFERENCE's own outputs"""
+    with open(os.path.join(G, "optimal.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        ps = dict(c["ps"])
+        ps["algorithms"] = set(ps["algorithms"])
+        r = emu.run(ps, [c["seq"]], mode=emu.MODE_STEP, init_stems=[[tuple(s) for s in c["selected"]]],
+                    item_subopt=[c["subopt"]], ccap=4096, stem_cap=256)
+        n = r["n"][0]
+        got = [[int(r["stems"][q][0]), int(r["stems"][q][1]), int(r["stems"][q][2]), float(r["fin"][q])] for q in range(n)]
+        assert got == c["chosen"], c["seq"]
+
+
+def test_per_stem_levels_equal_per_pair_levels():
+    """SURVEY A-7: pseudoknot levels computed per stem == PairsToDBN per pair"""
+    rng = random.Random(34)
+    for _ in range(300):
+        n = rng.randint(30, 200)
+        used, stems = set(), []
+        for _ in range(rng.randint(1, 14)):
+            i, j, ln = rng.randrange(n), rng.randrange(n), rng.randint(1, 7)
+            if i > j:
+                i, j = j, i
+            if j - i < 2 * ln + 2:
+                continue
+            pos = set(range(i, i + ln)) | set(range(j - ln + 1, j + 1))
+            if pos & used:
+                continue
+            used |= pos
+            stems.append((i, j, ln))
+        if not stems:
+            continue
+        seq = "A" * n
+        r = emu.run(T.DEFG1, [seq], mode=3, init_stems=[stems])          # MODE_FINAL: levels + dbn of given stems
+        codes = r["dbn_code"][:n]
+        pairs = [(i + k, j - k) for i, j, ln in stems for k in range(ln)]
+        want = O.pair_levels(pairs)
+        for (v, w), lev in want.items():
+            assert codes[v] == lev and codes[w] == -lev, (stems, v, w)

@@ -1,0 +1,70 @@
+"""The CPU oracle (oracle/sqrn_oracle.c) against golden vectors produced by the real
+reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    with open(os.path.join(G, name)) as f:
+        return json.load(f)
+
+
+def _ps(d):
+    d = dict(d)
+    d["algorithms"] = set(d["algorithms"])
+    return d
+
+
+@pytest.fixture(scope="module")
+def configs():
+    return load("configs.json")
+
+
+def _gsets(configs, conf):
+    return [_ps(p) for p in configs[conf]["paramsets"] if p["algorithms"] == ["G"] and p["bpp"] == 0]
+
+
+def test_seq_api(configs):
+    """SQRNdbnseq end to end: consensus, every structure, its three scores (incl. the int-0
+    quirk) and its parameter-set list, in rank order"""
+    cases = load("seq_api.json")
+    assert len(cases) > 250
+    for c in cases:
+        kw = dict(c["kw"])
+        kw["rankby"] = tuple(kw["rankby"])
+        smat = None if c["smat"] is None else np.array(c["smat"])
+        cons, structs = O.sqrn_dbnseq(c["seq"], c["reacts"], c["restraints"], paramsets=_gsets(configs, c["conf"]),
+                                      poollim=c["poollim"], stemmatrix=smat, **kw)
+        assert cons == c["cons"], c["seq"]
+        assert len(structs) == len(c["structs"]), c["seq"]
+        for (d, sc, psl), (gd, gsc, gpsl) in zip(structs, c["structs"]):
+            assert d == gd and list(sc) == gsc and psl == gpsl, (c["seq"], d, gd, sc, gsc)
+            assert type(sc[1]) is type(gsc[1])
+
+
+def test_annotate_stems():
+    """BPMatrix + AnnotateStems: same stems, same order, same float64 scores"""
+    for c in load("annotate.json"):
+        got = O.annotate(c["seq"], _ps(c["ps"]), c["reacts"], c["restraints"], interchainonly=c["interchainonly"])
+        assert [list(x) for x in got] == c["stems"], c["seq"]
+
+
+def test_levels():
+    for c in load("levels.json"):
+        lev = O.pair_levels(c["pairs"])
+        assert sorted([k[0], k[1], v] for k, v in lev.items()) == c["levels"]
+
+
+def test_optimal_stems():
+    """ScoreStems survivors (order + adjusted scores) and the ChooseStems list"""
+    for c in load("optimal.json"):
+        scored, chosen = O.optimal(c["seq"], _ps(c["ps"]), c["subopt"], selected=[tuple(s) for s in c["selected"]])
+        assert [list(x) for x in scored] == c["scored"], c["seq"]
+        assert [list(x) for x in chosen] == c["chosen"], c["seq"]
