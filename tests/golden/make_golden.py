@@ -2,7 +2,8 @@
 """Generates the golden vectors in this directory by IMPORTING THE REAL REFERENCE
 (/root/reference/src/SQUARNA, febos/SQUARNA) in the build container.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # JSON vectors
+    python tests/golden/make_golden.py cli      # CLI text of the reference on tests/golden/inputs/
 
 The reference cannot travel to the GPU box, so its outputs are committed here as
 JSON fixtures; tests/test_oracle_golden.py pins the CPU oracle (and the host-side
@@ -160,5 +161,42 @@ def main():
     dump("reacts.json", rx)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "cli" not in sys.argv[1:]:
     main()
+
+
+# --- G5: CLI text of the reference on the bundled example inputs ------------------
+CLI_RUNS = {
+    "seq_greedynobpp": ["i=inputs/seq_input.fas", "c=greedynobpp", "t=4"],
+    "seq_greedynobpp_opts": ["i=inputs/seq_input.fas", "c=greedynobpp", "t=4", "pl=20", "tl=3", "ol=4", "cl=2", "rb=drs", "hr", "rf=26"],
+    "seq_fastest_byseq": ["i=inputs/seq_input.fas", "c=fastest", "byseq", "pl=1", "t=4"],
+    "seq_alt_msn": ["i=inputs/seq_input.fas", "c=alt", "t=4", "msn=3", "rb=s", "rf=10", "ico"],
+    "seq_evalonly": ["i=inputs/seq_input.fas", "c=fastest", "eo", "t=2"],
+    "shape_fastest": ["i=inputs/shape_input.fas", "c=fastest", "t=2", "pl=1"],
+    "shape_greedynobpp": ["i=inputs/shape_input.fas", "c=greedynobpp", "t=4"],
+    "inline_seq": ["s=GGGAAACCCAAAGGGUUUCCC", "c=greedynobpp", "t=2"],
+    "ali_default": ["i=inputs/ali_input.afa", "a", "t=4"],
+    "ali_verbose": ["i=inputs/ali_input.afa", "a", "v", "t=4"],
+    "ali_step3_i": ["i=inputs/ali_input.afa", "a", "s3=i", "fl=0.5", "ll=1", "t=4"],
+    "ali_step3_1": ["i=inputs/ali_input.afa", "a", "s3=1", "t=4"],
+    "ali_demo": ["i=inputs/demo.afa", "a", "t=2"],
+    "ali_as_single_fastest": ["i=inputs/ali_input.afa", "c=fastest", "pl=1", "byseq", "t=4", "if=q"],
+}
+
+
+def cli_golden():
+    import subprocess
+    man = {}
+    for name, argv in CLI_RUNS.items():
+        out = subprocess.run([sys.executable, os.path.join(REF, "SQUARNA.py")] + argv, cwd=HERE,
+                             capture_output=True, text=True)
+        assert out.returncode == 0, (name, out.stderr[-2000:])
+        with open(os.path.join(HERE, "cli", name + ".txt"), "w") as f:
+            f.write(out.stdout)
+        man[name] = argv
+        print(name, len(out.stdout), "chars")
+    dump("cli_manifest.json", man)
+
+
+if __name__ == "__main__" and "cli" in sys.argv[1:]:
+    cli_golden()
