@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--seqs", type=int, default=1_000_000, help="sequences per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,7 +235,7 @@ def main():
         achieved = abytes / (kern_ms / 1e3) / 1e9
         threads = os.cpu_count() or 1
         sample = min(n, 2500 * threads)
-        cpu_rate, cpu_nt2, cpu_dt = cpu_oracle_rate(sym, off, lens, sample, threads)
+        cpu_rate, cpu_nt2, cpu_dt = (0.0, 0.0, 0.0) if args.no_cpu else cpu_oracle_rate(sym, off, lens, sample, threads)
         h2d = int(sym.nbytes + off.nbytes)
         d2h = int(total + n * 3 * 8 + n * 4 + n)
         line = {"metric": "sequences/sec (SQRNdbnseq greedy, byseq pl=1 fastest.conf)", "value": value, "unit": "seq/s",
