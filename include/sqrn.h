@@ -142,6 +142,12 @@ SQRN_API const char *sqrn_last_error(const sqrn_ctx *ctx);   /* ctx may be NULL:
  * this context, e.g. torch.cuda.current_stream().cuda_stream.                 */
 SQRN_API int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
 
+/* Tuning / test knobs.  SQRN_TUNE_REGION selects how ScoreStems evaluates the region inside a
+ * candidate (SQRNdbnseq.py:665-689): 0 automatic, 1 the reference's position scan, 2 the walk over
+ * the selected stems.  All settings give identical results; tests force each one.             */
+#define SQRN_TUNE_REGION 1
+SQRN_API int  sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value);
+
 /* The full "G" path for a batch: replaces SQRNdbnseq.py:1048-1246 (algos == {"G"},
  * bpp == 0).  Host buffers in, host buffers out.                              */
 SQRN_API int  sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps,
@@ -156,8 +162,10 @@ SQRN_API int  sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps,
  * sequence, written as ASCII dot-bracket.  `symbols`/`offsets`/outputs are HOST
  * pointers for sqrn_fast_predict_host and DEVICE pointers for
  * sqrn_fast_predict_device (inputs already resident in HBM; asynchronous on the
- * context's stream).  scores: 3 doubles per sequence, rounded as round(x,3) by
- * the host variant and raw (thescore, reactscore, total) by the device variant. */
+ * context's stream).  scores: 3 doubles per sequence (total, structscore,
+ * reactscore; ScoreStruct, SQRNdbnseq.py:899), rounded as round(x,3) by the host
+ * variant and unrounded by the device variant.  The host variant pipelines the
+ * batch in chunks: host->device copy, kernel and device->host copy overlap.    */
 SQRN_API int  sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps,
                             int64_t n_seqs, const int64_t *offsets, const uint8_t *symbols,
                             uint8_t *dbn_ascii, double *scores, int32_t *n_stems);

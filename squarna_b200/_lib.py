@@ -17,7 +17,8 @@ MODE_TAIL, MODE_STEP, MODE_YIELD, MODE_FINAL = 0, 1, 2, 3
 
 EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx_destroy",
            "sqrn_last_error", "sqrn_ctx_set_stream", "sqrn_predict_batch", "sqrn_yield_stems_batch",
-           "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run"]
+           "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
+           "sqrn_ctx_set_tuning"]
 
 _lib = None
 
@@ -44,6 +45,7 @@ def load():
     L.sqrn_last_error.argtypes = [vp]
     L.sqrn_last_error.restype = C.c_char_p
     L.sqrn_ctx_set_stream.argtypes = [vp, vp]
+    L.sqrn_ctx_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     L.sqrn_predict_batch.argtypes = [vp, C.POINTER(ParamSet), C.c_int, C.POINTER(Batch), C.POINTER(Result)]
     L.sqrn_yield_stems_batch.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.POINTER(Stems)]
     L.sqrn_fast_predict_host.argtypes = [vp, C.POINTER(ParamSet), i64, vp, vp, vp, vp, vp]
@@ -136,6 +138,10 @@ class Context:
 
     def set_stream(self, cuda_stream):
         self._check(self.L.sqrn_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_region_mode(self, mode):
+        """0 automatic, 1 position scan, 2 stem walk (identical results; see include/sqrn.h)"""
+        self._check(self.L.sqrn_ctx_set_tuning(self.h, 1, int(mode)))
 
     def stats(self):
         nl, ms, nc = C.c_int64(0), C.c_double(0), C.c_int64(0)

@@ -18,7 +18,7 @@ using namespace sqrn;
 // Persistent teams pull work items from a global counter (length-sorted by the
 // host, longest first), so a batch of mixed lengths keeps every SM busy.
 template <int TW>
-__global__ void __launch_bounds__(TW == 1 ? 256 : TW * 32)
+__global__ void __launch_bounds__(TW == 1 ? 256 : TW * 32, TW == 1 ? 4 : 1)
 k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -43,7 +43,7 @@ k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
             __syncthreads();
         }
         if (item >= Wk.n_items) break;
-        if (Wk.order) item = Wk.order[item];
+        item = Wk.order ? Wk.order[item] : item + Wk.item_base;
         team_run_item<TW>(S, Psh, B, Wk, L, item);
     }
 }
@@ -63,6 +63,8 @@ struct DBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+
+constexpr int FAST_MAX_CHUNKS = 8;
 
 struct PEntry {
     sqrn_paramset ps; int nmax; DevParams hp; DevParams *d_p; double *d_lut;
@@ -89,12 +91,17 @@ enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB
 struct sqrn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_k2 = nullptr;       // copy-in, copy-out, second kernel stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
+    cudaEvent_t ev_start = nullptr, ev_out = nullptr, ev_k2done = nullptr;
+    cudaEvent_t ev_in[FAST_MAX_CHUNKS] = {}, ev_k0[FAST_MAX_CHUNKS] = {}, ev_k1[FAST_MAX_CHUNKS] = {};
+    uint8_t *hflags = nullptr; size_t hflags_cap = 0;                    // pinned staging for the result flags
     std::string err;
     int sm_count = 0; size_t smem_optin = 0;
     std::vector<PEntry> pcache;
     DBuf buf[NBUF];
     int64_t n_launches = 0, n_calls = 0; double kernel_ms = 0.0;
+    int region_mode = REGION_AUTO;
     CachedResult cres; CachedStems cstems;
 };
 
@@ -135,6 +142,16 @@ extern "C" int sqrn_ctx_create(int device, sqrn_ctx **out)
         delete ctx; return SQRN_E_CUDA;
     }
     ctx->own_stream = true;
+    bool ok = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_k2, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_k2done, cudaEventDisableTiming) == cudaSuccess;
+    for (int c = 0; c < FAST_MAX_CHUNKS && ok; c++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_in[c], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreate(&ctx->ev_k0[c]) == cudaSuccess && cudaEventCreate(&ctx->ev_k1[c]) == cudaSuccess;
+    if (!ok) { g_create_err = std::string("context creation failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return SQRN_E_CUDA; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
@@ -151,7 +168,11 @@ extern "C" void sqrn_ctx_destroy(sqrn_ctx *ctx)
     for (auto &b : ctx->buf) b.release();
     for (auto &p : ctx->pcache) { cudaFree(p.d_p); cudaFree(p.d_lut); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_k2);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_out); cudaEventDestroy(ctx->ev_k2done);
+    for (int c = 0; c < FAST_MAX_CHUNKS; c++) { cudaEventDestroy(ctx->ev_in[c]); cudaEventDestroy(ctx->ev_k0[c]); cudaEventDestroy(ctx->ev_k1[c]); }
+    if (ctx->hflags) cudaFreeHost(ctx->hflags);
     delete ctx;
 }
 
@@ -163,6 +184,14 @@ extern "C" int sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream)
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false;
     return SQRN_OK;
+}
+
+extern "C" int sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value)
+{
+    if (!ctx) return SQRN_E_BADARG;
+    if (what == SQRN_TUNE_REGION && value >= 0 && value <= 2) { ctx->region_mode = value; return SQRN_OK; }
+    ctx->err = "unknown tuning knob";
+    return SQRN_E_BADARG;
 }
 
 extern "C" int sqrn_ctx_last_stats(const sqrn_ctx *ctx, int64_t *n_launches, double *kernel_ms, int64_t *n_optimal_calls)
@@ -210,28 +239,33 @@ static int plan_for(sqrn_ctx *ctx, Plan &pl)
     return SQRN_OK;
 }
 
-// choose the team shape for sequences up to nmax symbols
-static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int min_ccap, Plan &pl)
+// choose the team shape for sequences up to nmax symbols.  keep_all: the mode needs every
+// survivor of a scan in the list (MODE_STEP); otherwise the lists are flushed when they fill up
+// and their sizes only set the flush granularity.
+static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int min_ccap, bool keep_all, bool extras,
+                     int max_init, Plan &pl)
 {
     const int m = P.hp.m, npc = P.hp.npc;
+    // every stem the greedy adds has >= m pairs (AnnotateStems' minlen filter, seq.py:492); max_init < 0: unknown
+    const int scap = max_init < 0 ? 0 : max_init + nmax / (2 * m) + 2;
     double dens = m >= 4 ? 0.004 : (m == 3 ? 0.01 : 0.025);         // candidate stems / N^2 on random RNA
     int est = (int)(dens * nmax * (double)nmax) + 32;
     const size_t budget = ctx->smem_optin - sizeof(DevParams) - 1024;
     if (nmax <= 320 && min_ccap <= 1024) {
         pl.tw = 1;
-        int ccap = std::max(std::min(next_pow2(est), 1024), 64);
+        int ccap = keep_all ? std::max(std::min(next_pow2(est), 1024), 64) : 128;
         if (ccap < min_ccap) ccap = next_pow2(min_ccap);
-        pl.L = make_layout(nmax, rbmax, ccap, npc, 1);
+        pl.L = make_layout(nmax, rbmax, ccap, npc, 1, 256, extras, keep_all, scap);
         pl.tpc = (int)std::max<size_t>(1, std::min<size_t>(8, (96 * 1024) / pl.L.total));
         pl.threads = 32 * pl.tpc;
         pl.smem = (size_t)pl.tpc * pl.L.total;
         return plan_for<1>(ctx, pl);
     }
     pl.tw = nmax <= 2048 ? 8 : 32;
-    int ccap = std::max(std::min(next_pow2(est), 4096), 256);
+    int ccap = keep_all ? std::max(std::min(next_pow2(est), 4096), 256) : 1024;
     if (ccap < min_ccap) ccap = next_pow2(min_ccap);
     for (;;) {
-        pl.L = make_layout(nmax, rbmax, ccap, npc, pl.tw);
+        pl.L = make_layout(nmax, rbmax, ccap, npc, pl.tw, 4096, extras, keep_all, scap);
         if ((size_t)pl.L.total <= budget || ccap <= 256) break;
         ccap >>= 1;
     }
@@ -275,6 +309,31 @@ static int dalloc(sqrn_ctx *ctx, int slot, size_t count, T **d)
 #define TRY(x) do { int r_ = (x); if (r_ != SQRN_OK) return r_; } while (0)
 
 // ------------------------------------------------ fast lane (byseq pl=1 shape)
+// one launch over items [item_base, item_base + n_items) of a resident CSR batch
+static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t st, int64_t item_base, int64_t n_items,
+                       const int64_t *d_offsets, const uint8_t *d_symbols, uint8_t *d_dbn_ascii, double *d_scores,
+                       int32_t *d_n_stems, uint8_t *d_flags, int *d_counter, unsigned long long *d_ncalls, int round3,
+                       cudaEvent_t e0, cudaEvent_t e1)
+{
+    DevBatch B; memset(&B, 0, sizeof B);
+    B.n_seqs = item_base + n_items; B.off = d_offsets; B.sym = d_symbols;
+    DevWork W; memset(&W, 0, sizeof W);
+    W.n_items = (int)n_items; W.item_base = (int)item_base; W.mode = MODE_TAIL; W.region_mode = ctx->region_mode;
+    W.round3 = round3; W.counter = d_counter; W.out_flags = d_flags; W.n_calls = d_ncalls;
+    W.out_nstems = d_n_stems; W.out_raw = d_scores; W.dbn_off = d_offsets; W.out_dbn_ascii = d_dbn_ascii;
+    int grid = pl.grid;
+    int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
+    if (grid > teams) grid = std::max(teams, 1);
+    if (e0) CK(cudaEventRecord(e0, st));
+    if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
+    else if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
+    else k_work<32><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
+    CK(cudaGetLastError());
+    if (e1) CK(cudaEventRecord(e1, st));
+    ctx->n_launches++;
+    return SQRN_OK;
+}
+
 extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
                                         int32_t max_len, const int64_t *d_offsets, const uint8_t *d_symbols,
                                         uint8_t *d_dbn_ascii, double *d_scores, int32_t *d_n_stems)
@@ -286,61 +345,108 @@ extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, 
     const PEntry *P;
     TRY(get_params(ctx, *ps, max_len, &P));
     Plan pl;
-    TRY(make_plan(ctx, *P, max_len, 0, 0, pl));
-    DevBatch B; memset(&B, 0, sizeof B);
-    B.n_seqs = n_seqs; B.off = d_offsets; B.sym = d_symbols;
-    DevWork W; memset(&W, 0, sizeof W);
-    W.n_items = (int)n_seqs; W.mode = MODE_TAIL;
-    TRY(dalloc(ctx, W_COUNTER, 1, &W.counter));
-    TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &W.out_flags));
-    TRY(dalloc(ctx, W_NCALLS, 1, &W.n_calls));
-    CK(cudaMemsetAsync(W.n_calls, 0, sizeof(unsigned long long), ctx->stream));
-    W.out_nstems = d_n_stems; W.out_raw = d_scores; W.dbn_off = d_offsets; W.out_dbn_ascii = d_dbn_ascii;
-    return launch(ctx, *P, pl, B, W);
+    TRY(make_plan(ctx, *P, max_len, 0, 0, false, false, 0, pl));
+    int *d_counter; uint8_t *d_flags; unsigned long long *d_nc;
+    TRY(dalloc(ctx, W_COUNTER, FAST_MAX_CHUNKS, &d_counter));
+    TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &d_flags));
+    TRY(dalloc(ctx, W_NCALLS, 1, &d_nc));
+    CK(cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), ctx->stream));
+    int rc = fast_launch(ctx, *P, pl, ctx->stream, 0, n_seqs, d_offsets, d_symbols, d_dbn_ascii, d_scores, d_n_stems,
+                         d_flags, d_counter, d_nc, 0, ctx->ev0, ctx->ev1);
+    if (rc == SQRN_OK) ctx->ev_valid = true;
+    return rc;
 }
 
-static int finish_stats(sqrn_ctx *ctx, bool read_calls)
-{
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->ev_valid) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->kernel_ms = ms; }
-    if (read_calls && ctx->buf[W_NCALLS].p) {
-        unsigned long long c = 0;
-        CK(cudaMemcpy(&c, ctx->buf[W_NCALLS].p, sizeof c, cudaMemcpyDeviceToHost));
-        ctx->n_calls = (int64_t)c;
-    }
-    return SQRN_OK;
-}
-
+// Host buffers in, host buffers out.  The batch is cut into chunks that flow through three
+// stages on separate streams -- host->device copy, kernel, device->host copy -- so PCIe traffic
+// in both directions overlaps the kernels of the neighbouring chunks.
 extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, const int64_t *offsets,
                                       const uint8_t *symbols, uint8_t *dbn_ascii, double *scores, int32_t *n_stems)
 {
-    if (!ctx || !ps || !offsets || n_seqs < 0) return SQRN_E_BADARG;
+    if (!ctx || !ps || !offsets || n_seqs < 0 || n_seqs > 0x7fffffff) return SQRN_E_BADARG;
     cudaSetDevice(ctx->device);
     ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
     if (n_seqs == 0) return SQRN_OK;
-    int64_t total = offsets[n_seqs];
+    const int64_t total = offsets[n_seqs];
     int max_len = 0;
     for (int64_t b = 0; b < n_seqs; b++) {
         int64_t n = offsets[b + 1] - offsets[b];
         if (n < 0 || n > SQRN_MAX_LEN) { ctx->err = "sequence length out of range"; return SQRN_E_BADARG; }
         if (n > max_len) max_len = (int)n;
     }
-    int64_t *d_off; uint8_t *d_sym, *d_dbn; double *d_sc; int32_t *d_ns;
-    TRY(upload(ctx, B_OFF, offsets, (size_t)n_seqs + 1, &d_off));
-    TRY(upload(ctx, B_SYM, symbols, (size_t)total, &d_sym));
-    TRY(dalloc(ctx, W_DBNA, (size_t)total, &d_dbn));
+    const PEntry *P;
+    TRY(get_params(ctx, *ps, max_len, &P));
+    Plan pl;
+    TRY(make_plan(ctx, *P, max_len, 0, 0, false, false, 0, pl));
+    int64_t *d_off; uint8_t *d_sym, *d_dbn, *d_flags; double *d_sc; int32_t *d_ns; int *d_counter; unsigned long long *d_nc;
+    TRY(dalloc(ctx, B_OFF, (size_t)n_seqs + 1, &d_off));
+    TRY(dalloc(ctx, B_SYM, (size_t)std::max<int64_t>(total, 1), &d_sym));
+    TRY(dalloc(ctx, W_DBNA, (size_t)std::max<int64_t>(total, 1), &d_dbn));
     TRY(dalloc(ctx, W_ORAW, (size_t)n_seqs * 3, &d_sc));
     TRY(dalloc(ctx, W_ON, (size_t)n_seqs, &d_ns));
-    TRY(sqrn_fast_predict_device(ctx, ps, n_seqs, total, max_len, d_off, d_sym, d_dbn, d_sc, d_ns));
-    if (total) CK(cudaMemcpyAsync(dbn_ascii, d_dbn, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(scores, d_sc, (size_t)n_seqs * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (n_stems) CK(cudaMemcpyAsync(n_stems, d_ns, (size_t)n_seqs * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    std::vector<uint8_t> flags((size_t)n_seqs);
-    CK(cudaMemcpyAsync(flags.data(), ctx->buf[W_OFLAGS].p, (size_t)n_seqs, cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(finish_stats(ctx, true));
-    for (int64_t k = 0; k < 3 * n_seqs; k++) scores[k] = pyround3(scores[k]);    // ScoreStruct's round(x, 3), seq.py:899
-    for (int64_t b = 0; b < n_seqs; b++)
-        if (flags[b] & 2) { ctx->err = "more than 30 pseudoknot levels: use sqrn_predict_batch"; return SQRN_E_UNSUPPORTED; }
+    TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &d_flags));
+    TRY(dalloc(ctx, W_COUNTER, FAST_MAX_CHUNKS, &d_counter));
+    TRY(dalloc(ctx, W_NCALLS, 1, &d_nc));
+    if (ctx->hflags_cap < (size_t)n_seqs) {
+        if (ctx->hflags) cudaFreeHost(ctx->hflags);
+        ctx->hflags = nullptr; ctx->hflags_cap = 0;
+        CK(cudaMallocHost(&ctx->hflags, (size_t)n_seqs + 64));
+        ctx->hflags_cap = (size_t)n_seqs + 64;
+    }
+    // chunks of at least 64 Ki sequences, at most FAST_MAX_CHUNKS
+    int nchunks = (int)std::min<int64_t>(FAST_MAX_CHUNKS, std::max<int64_t>(1, n_seqs / 65536));
+    cudaStream_t s_main = ctx->stream;
+    CK(cudaMemsetAsync(d_counter, 0, FAST_MAX_CHUNKS * sizeof(int), s_main));
+    CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), s_main));
+    CK(cudaEventRecord(ctx->ev_start, s_main));
+    CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t b0 = n_seqs * c / nchunks, b1 = n_seqs * (c + 1) / nchunks;
+        const int64_t t0 = offsets[b0], t1 = offsets[b1];
+        cudaStream_t s_k = (c & 1) ? ctx->s_k2 : s_main;
+        // stage 1: inputs of the chunk
+        CK(cudaMemcpyAsync(d_off + b0 + (c ? 1 : 0), offsets + b0 + (c ? 1 : 0), (size_t)(b1 - b0 + (c ? 0 : 1)) * sizeof(int64_t),
+                           cudaMemcpyHostToDevice, ctx->s_in));
+        if (t1 > t0) CK(cudaMemcpyAsync(d_sym + t0, symbols + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+        // stage 2: kernel
+        CK(cudaStreamWaitEvent(s_k, ctx->ev_in[c], 0));
+        if (c == 1) CK(cudaStreamWaitEvent(s_k, ctx->ev_start, 0));
+        TRY(fast_launch(ctx, *P, pl, s_k, b0, b1 - b0, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + c, d_nc, 1,
+                        ctx->ev_k0[c], ctx->ev_k1[c]));
+        // stage 3: outputs of the chunk
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k1[c], 0));
+        if (t1 > t0) CK(cudaMemcpyAsync(dbn_ascii + t0, d_dbn + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaMemcpyAsync(scores + 3 * b0, d_sc + 3 * b0, (size_t)(b1 - b0) * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (n_stems) CK(cudaMemcpyAsync(n_stems + b0, d_ns + b0, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaMemcpyAsync(ctx->hflags + b0, d_flags + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CK(cudaEventRecord(ctx->ev_out, ctx->s_out));
+    CK(cudaEventRecord(ctx->ev_k2done, ctx->s_k2));
+    CK(cudaStreamWaitEvent(s_main, ctx->ev_out, 0));          // later work on the context's stream sees the results
+    CK(cudaStreamWaitEvent(s_main, ctx->ev_k2done, 0));
+    CK(cudaStreamSynchronize(s_main));
+    for (int c = 0; c < nchunks; c++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_k0[c], ctx->ev_k1[c]) == cudaSuccess) ctx->kernel_ms += ms;
+    }
+    {
+        unsigned long long c = 0;
+        CK(cudaMemcpy(&c, d_nc, sizeof c, cudaMemcpyDeviceToHost));
+        ctx->n_calls = (int64_t)c;
+    }
+    // ScoreStruct's round(x, 3) (seq.py:899) was done on the device except next to rounding ties
+    const uint8_t *fl = ctx->hflags;
+    for (int64_t b = 0; b < n_seqs; ) {
+        if (b + 8 <= n_seqs) {
+            uint64_t w; memcpy(&w, fl + b, 8);
+            if (!(w & 0x0a0a0a0a0a0a0a0aull)) { b += 8; continue; }
+        }
+        if (fl[b] & FLAG_ROUND) for (int t = 0; t < 3; t++) scores[3 * b + t] = pyround3(scores[3 * b + t]);
+        if (fl[b] & FLAG_LEVELS) { ctx->err = "more than 30 pseudoknot levels: use sqrn_predict_batch"; return SQRN_E_UNSUPPORTED; }
+        b++;
+    }
     return SQRN_OK;
 }
 
@@ -442,7 +548,7 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
     if (n == 0) return SQRN_OK;
 
     DevWork G; memset(&G, 0, sizeof G);
-    G.mode = W.mode;
+    G.mode = W.mode; G.region_mode = ctx->region_mode;
     int32_t *d_iseq; TRY(upload(ctx, W_ISEQ, W.item_seq.data(), (size_t)n, &d_iseq)); G.item_seq = d_iseq;
     if (!W.init_off.empty()) {
         int64_t *d_io; int32_t *d_is;
@@ -475,12 +581,17 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
     });
     int32_t *d_order; TRY(upload(ctx, W_ORDER, order.data(), (size_t)n, &d_order));
     const PEntry *P; TRY(get_params(ctx, ps, std::max(D.nmax, 1), &P));
+    // most pre-selected stems of any item; MODE_FINAL gets structures of other parameter sets: no bound from m
+    int max_init = 0;
+    if (W.mode == MODE_FINAL) max_init = -1;
+    else if (!W.init_off.empty())
+        for (int k = 0; k < n; k++) max_init = std::max<int>(max_init, (int)(W.init_off[k + 1] - W.init_off[k]));
     int pos = 0;
     while (pos < n) {
         int c = cls(order[pos]), end = pos;
         while (end < n && cls(order[end]) == c) end++;
         int nmax_c = D.len[W.item_seq[order[pos]]];
-        Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, pl));
+        Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, W.mode == MODE_STEP, D.B.rcode != nullptr, max_init, pl));
         DevWork Gc = G; Gc.order = d_order + pos; Gc.n_items = end - pos;
         TRY(launch(ctx, *P, pl, D.B, Gc));
         pos = end;

@@ -10,11 +10,20 @@
 //       with j = s - i on anti-diagonal s = i + j;
 //   stems (AnnotateStems, seq.py:427-495)    = maximal runs of set bits, found
 //       with ctz/funnel-shift word tricks, outermost cell first;
-//   ScoreStems (seq.py:607-751)              = per-candidate scan of the region
-//       confined by the innermost pair, pow() terms from host-built tables;
+//   ScoreStems (seq.py:607-751)              = per-candidate evaluation of the
+//       region confined by the innermost pair -- either the reference's own
+//       position scan or an equivalent walk over the SELECTED STEMS in 5'
+//       order (a few stems instead of hundreds of positions); pow() terms come
+//       from host-built tables;
 //   ChooseStems (seq.py:754-789)             = team-wide arg-max with the key
 //       (score desc, i+j asc, i asc), which is the order the reference's stable
 //       sort leaves ties in.
+//
+// One OptimalStems pass is a three-phase pipeline so that every phase keeps the
+// lanes of a warp busy with the same kind of work:
+//   1  lane per anti-diagonal:  enumerate runs >= minlen        -> run list
+//   2a lane per run:            sum the bp scores (seq.py:416)  -> survivor list
+//   2b lane per survivor:       ScoreStems factor product       -> arg-max
 //
 // A "team" is the group of threads that owns one (sequence, partial structure)
 // work item: one warp for short sequences, one CTA for long ones.
@@ -22,6 +31,7 @@
 #include <stdint.h>
 #ifndef SQRN_HOST_EMU
 #include <cuda_runtime.h>
+#define SQRN_NOINLINE __noinline__
 #else
 // Single-thread "team" build used only by tests/emu (g++): the same device
 // functions with T = 1, so the bit tricks and scoring logic can be debugged
@@ -32,8 +42,10 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define SQRN_NOINLINE
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
@@ -57,6 +69,14 @@ constexpr int MODE_TAIL = 0;   // run the single-path greedy to completion
 constexpr int MODE_STEP = 1;   // one OptimalStems call, return the ChooseStems list
 constexpr int MODE_YIELD = 2;  // AnnotateStems only, stems in reference order
 constexpr int MODE_FINAL = 3;  // ScoreStruct + dbn of the given stems, no selection
+
+constexpr int REGION_AUTO = 0, REGION_SCAN = 1, REGION_STEMS = 2;   // ScoreStems region evaluation
+
+// result flags per item
+constexpr int FLAG_INT0 = 1;       // struct score is the int 0 (prints "0"), seq.py:871
+constexpr int FLAG_LEVELS = 2;     // more than 30 pseudoknot levels: ASCII glyphs exhausted
+constexpr int FLAG_CAPACITY = 4;
+constexpr int FLAG_ROUND = 8;      // device round(x, 3) was too close to a tie: host redoes it from out_raw2
 
 // ---------------------------------------------------------------- parameters
 struct DevParams {
@@ -88,6 +108,9 @@ struct DevBatch {
 struct DevWork {
     int            n_items;
     int            mode;
+    int            item_base;    // first item of this launch (chunked launches share one CSR)
+    int            region_mode;  // REGION_*
+    int            round3;       // TAIL/FINAL: write round(x, 3) scores (ScoreStruct, seq.py:899)
     const int32_t *order;        // processing order (item ids), NULL = identity
     const int32_t *item_seq;     // item -> sequence, NULL = identity
     const int64_t *init_off;     // [n_items+1] CSR of initial stems, NULL = none
@@ -99,8 +122,8 @@ struct DevWork {
     int32_t       *out_stems;    // i, j, len
     int32_t       *out_nstems;   // TAIL: total stems; STEP: number of chosen stems
     double        *out_stemfin;  // optional: adjusted score per output stem
-    double        *out_raw;      // TAIL: thescore*reactscore, thescore, reactscore per item (unrounded)
-    uint8_t       *out_flags;    // bit0 struct_is_int0, bit1 level overflow, bit2 capacity overflow
+    double        *out_raw;      // TAIL: thescore*reactscore, thescore, reactscore per item
+    uint8_t       *out_flags;    // FLAG_*
     const int64_t *dbn_off;      // [n_items] offset of the item's dbn
     uint8_t       *out_dbn_ascii;
     int8_t        *out_dbn_code;
@@ -109,51 +132,67 @@ struct DevWork {
 
 // -------------------------------------------------------------- smem layout
 struct Layout {
-    int Ncap, W, WR, Scap, RBcap, Ccap, npc;
-    int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR,
-        o_sti, o_stj, o_stl, o_stlev, o_cc, o_perm, o_grp, o_gsz, o_rbv, o_rbw,
-        o_ckey, o_clen, o_cbps, o_cfin, o_red, o_misc, total;
+    int Ncap, W, WR, Scap, RBcap, Rcap, Ccap, npc;
+    int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
+        o_sti, o_stj, o_stl, o_stlev, o_ssi, o_ssj, o_ssl, o_sslev, o_byi, o_cc, o_perm, o_grp, o_gsz,
+        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_misc, total;
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline Layout make_layout(int Nmax, int RBmax, int Ccap, int npc, int tw)
+// extras = the batch carries reactivities (rcode array needed); with_fin = the
+// mode keeps the adjusted score of every survivor (MODE_STEP)
+// scap = most stems one structure can hold (0: the N/2 + 1 upper bound)
+__host__ __device__ inline Layout make_layout(int Nmax, int RBmax, int Ccap, int npc, int tw, int Rcap = 0,
+                                              int extras = 1, int with_fin = 1, int scap = 0)
 {
     Layout L;
     L.Ncap = align_up(Nmax > 0 ? Nmax : 1, 32);
     L.W = L.Ncap / 32;
     L.WR = L.W + 3;
     L.Scap = L.Ncap / 2 + 1;
+    if (scap > 0 && scap < L.Scap) L.Scap = scap;
     L.RBcap = RBmax;
     L.Ccap = Ccap;
+    L.Rcap = Rcap > 0 ? Rcap : Ccap;
     L.npc = npc;
     int o = 0;
     L.o_cbps = o;    o += 8 * Ccap;                       // doubles first (8-byte aligned)
-    L.o_cfin = o;    o += 8 * Ccap;
+    L.o_cfin = o;    o += with_fin ? 8 * Ccap : 0;
     L.o_red = o;     o += (tw > 1) ? 32 * tw : 0;        // cross-warp reduction scratch
     L.o_misc = o;    o += 64;
     L.o_M = o;       o += 4 * npc * L.W;
     L.o_PR = o;      o += 4 * npc * L.WR;
     L.o_rowok = o;   o += 4 * L.W;
     L.o_colokR = o;  o += 4 * L.WR;
-    L.o_cc = o;      o += 4 * L.Scap;
-    L.o_gsz = o;     o += 4 * L.Scap;
+    L.o_Ub = o;      o += 4 * L.W;
+    L.o_Ubase = o;   o += 4 * (L.W + 1);
     L.o_ckey = o;    o += 4 * Ccap;
+    // run list; the level scratch (cc, gsz, perm, grp) is only live between two scans and shares its space
+    int lev_bytes = 4 * L.Scap + 4 * L.Scap + 2 * L.Scap + 2 * L.Scap;
+    int run_bytes = 4 * L.Rcap + 2 * L.Rcap;
+    int uni = align_up(lev_bytes > run_bytes ? lev_bytes : run_bytes, 4);
+    L.o_rkey = o;    L.o_rlen = o + 4 * L.Rcap;
+    L.o_cc = o;      L.o_gsz = o + 4 * L.Scap;  L.o_perm = o + 8 * L.Scap;  L.o_grp = o + 10 * L.Scap;
+    o += uni;
     L.o_partner = o; o += 2 * L.Ncap;
     L.o_owner = o;   o += 2 * L.Ncap;
     L.o_sepcnt = o;  o += 2 * (L.Ncap + 2);
     L.o_sti = o;     o += 2 * L.Scap;
     L.o_stj = o;     o += 2 * L.Scap;
     L.o_stl = o;     o += 2 * L.Scap;
-    L.o_perm = o;    o += 2 * L.Scap;
-    L.o_grp = o;     o += 2 * L.Scap;
+    L.o_ssi = o;     o += 2 * L.Scap;
+    L.o_ssj = o;     o += 2 * L.Scap;
+    L.o_ssl = o;     o += 2 * L.Scap;
+    L.o_byi = o;     o += 2 * L.Scap;
     L.o_rbv = o;     o += 2 * (RBmax + 1);
     L.o_rbw = o;     o += 2 * (RBmax + 1);
     L.o_clen = o;    o += 2 * Ccap;
-    L.o_rcode = o;   o += 2 * L.Ncap;
+    L.o_rcode = o;   o += extras ? 2 * L.Ncap : 0;
     L.o_code = o;    o += L.Ncap;
     L.o_rcl = o;     o += L.Ncap;
     L.o_stlev = o;   o += L.Scap;
+    L.o_sslev = o;   o += L.Scap;
     L.total = align_up(o, 16);
     return L;
 }
@@ -162,7 +201,6 @@ __host__ __device__ inline Layout make_layout(int Nmax, int RBmax, int Ccap, int
 
 struct Best {
     double   fin;
-    double   bps;
     uint32_t key;     // (i+j) << 16 | i : smaller = earlier in the reference's enumeration order
     int      len;
 };
@@ -184,6 +222,25 @@ template <int TW> struct Team {
     {
         if (TW == 1) __syncwarp(); else __syncthreads();
     }
+    // both are barriers (memory included) for the team
+    __device__ static __forceinline__ bool any(bool p)
+    {
+        if (TW == 1) { bool a = __any_sync(0xffffffffu, p); __syncwarp(); return a; }
+        return __syncthreads_or(p) != 0;
+    }
+    // Threads with p set claim consecutive slots starting at `base` (uniform); returns how many did.
+    // TW > 1 uses the team-shared `counter`, which the caller keeps equal to `base` between calls.
+    __device__ static __forceinline__ int claim(bool p, int *counter, int base, int &slot)
+    {
+        if (TW == 1) {
+            uint32_t b = __ballot_sync(0xffffffffu, p);
+            slot = base + __popc(b & ((1u << (threadIdx.x & 31)) - 1u));
+            __syncwarp();
+            return __popc(b);
+        }
+        slot = p ? atomicAdd(counter, 1) : 0;
+        return __syncthreads_count(p);
+    }
 #endif
 };
 #ifdef SQRN_HOST_EMU
@@ -191,44 +248,97 @@ template <> struct Team<0> {
     static constexpr int T = 1;
     static inline int rank() { return 0; }
     static inline void sync() {}
+    static inline bool any(bool p) { return p; }
+    static inline int claim(bool p, int *, int base, int &slot) { slot = base; return p ? 1 : 0; }
 };
 #endif
 
 struct State {
-    int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts;
-    uint8_t  *code, *rcl, *stlev;
+    int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts, region_mode;
+    uint8_t  *code, *rcl, *stlev, *sslev;
     uint16_t *rcode;
-    int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *perm, *grp, *rbv, *rbw;
-    uint32_t *M, *PR, *rowok, *colokR, *ckey;
-    int32_t  *cc, *gsz;
-    uint16_t *clen;
+    int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *ssi, *ssj, *ssl, *byi, *perm, *grp, *rbv, *rbw;
+    uint32_t *M, *PR, *rowok, *colokR, *Ub, *ckey, *rkey;
+    int32_t  *cc, *gsz, *Ubase;
+    uint16_t *clen, *rlen;
     double   *cbps, *cfin, *red;
-    int      *misc;      // [0] candidate count  [1] next item  [2..] scratch
+    int      *misc;      // [0] run count  [1] next item  [2..6] scratch  [7] survivor count
     const int32_t *cols; // global, per sequence
 };
 
 __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L)
 {
     State s;
-    s.code = base + L.o_code;  s.rcode = (uint16_t *)(base + L.o_rcode);  s.rcl = base + L.o_rcl;  s.stlev = base + L.o_stlev;
+    s.code = base + L.o_code;  s.rcode = (uint16_t *)(base + L.o_rcode);  s.rcl = base + L.o_rcl;
+    s.stlev = base + L.o_stlev;  s.sslev = base + L.o_sslev;
     s.partner = (int16_t *)(base + L.o_partner);  s.owner = (int16_t *)(base + L.o_owner);
     s.sepcnt = (int16_t *)(base + L.o_sepcnt);
     s.sti = (int16_t *)(base + L.o_sti);  s.stj = (int16_t *)(base + L.o_stj);  s.stl = (int16_t *)(base + L.o_stl);
+    s.ssi = (int16_t *)(base + L.o_ssi);  s.ssj = (int16_t *)(base + L.o_ssj);  s.ssl = (int16_t *)(base + L.o_ssl);
+    s.byi = (int16_t *)(base + L.o_byi);
     s.perm = (int16_t *)(base + L.o_perm);  s.grp = (int16_t *)(base + L.o_grp);
     s.rbv = (int16_t *)(base + L.o_rbv);  s.rbw = (int16_t *)(base + L.o_rbw);
     s.M = (uint32_t *)(base + L.o_M);  s.PR = (uint32_t *)(base + L.o_PR);
     s.rowok = (uint32_t *)(base + L.o_rowok);  s.colokR = (uint32_t *)(base + L.o_colokR);
-    s.ckey = (uint32_t *)(base + L.o_ckey);
+    s.Ub = (uint32_t *)(base + L.o_Ub);  s.Ubase = (int32_t *)(base + L.o_Ubase);
+    s.ckey = (uint32_t *)(base + L.o_ckey);  s.rkey = (uint32_t *)(base + L.o_rkey);
     s.cc = (int32_t *)(base + L.o_cc);  s.gsz = (int32_t *)(base + L.o_gsz);
-    s.clen = (uint16_t *)(base + L.o_clen);
+    s.clen = (uint16_t *)(base + L.o_clen);  s.rlen = (uint16_t *)(base + L.o_rlen);
     s.cbps = (double *)(base + L.o_cbps);
     s.cfin = (double *)(base + L.o_cfin);
     s.red = (double *)(base + L.o_red);
     s.misc = (int *)(base + L.o_misc);
     s.W = L.W; s.WR = L.WR;
     s.N = 0; s.nst = 0; s.nrb = 0; s.has_sep = 0; s.has_react = 0; s.has_smat = 0; s.default_reacts = 1;
+    s.region_mode = REGION_AUTO;
     s.cols = nullptr;
     return s;
+}
+
+// bit b of dst[k] = pred(32 k + b): one ballot per word
+template <int TW, class F>
+__device__ __forceinline__ void team_mask(uint32_t *dst, int nwords, F &&pred)
+{
+#ifdef SQRN_HOST_EMU
+    for (int k = 0; k < nwords; k++) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++) if (pred(32 * k + b)) m |= 1u << b;
+        dst[k] = m;
+    }
+#else
+    const int lane = threadIdx.x & 31;
+    const int w0 = (TW == 1) ? 0 : (int)(threadIdx.x >> 5), nw = (TW == 1) ? 1 : TW;
+    for (int k = w0; k < nwords; k += nw) {
+        uint32_t m = __ballot_sync(0xffffffffu, pred(32 * k + lane));
+        if (lane == 0) dst[k] = m;
+    }
+#endif
+}
+
+// exclusive prefix sum over the team; total returned through `total`
+template <int TW>
+__device__ __forceinline__ int team_exscan(State &S, int v, int &total)
+{
+#ifdef SQRN_HOST_EMU
+    total = v; return 0;
+#else
+    int lane = threadIdx.x & 31, x = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    int wtot = __shfl_sync(0xffffffffu, x, 31);
+    int excl = x - v;
+    if (TW == 1) { total = wtot; return excl; }
+    int *sc = (int *)S.red;
+    int w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 31) sc[w] = wtot;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int q = 0; q < TW; q++) { int t = sc[q]; if (q < w) base += t; tot += t; }
+    __syncthreads();
+    total = tot;
+    return base + excl;
+#endif
 }
 
 // minimum hairpin rule, seq.py:293-297: j >= i + inc4(i)
@@ -238,6 +348,28 @@ __device__ __forceinline__ int inc4_of(const State &S, int i)
     if (i + 1 < S.N && S.code[i + 1] == CODE_SEP) inc = 2;
     if (i + 2 < S.N && S.code[i + 2] == CODE_SEP) inc = 3;
     return inc;
+}
+
+// number of unpaired positions in [0, p)
+__device__ __forceinline__ int unpaired_before(const State &S, int p)
+{
+    return S.Ubase[p >> 5] + __popc(S.Ub[p >> 5] & ((1u << (p & 31)) - 1u));
+}
+
+// word prefix of the unpaired mask (after Ub changed)
+template <int TW>
+__device__ void team_unpaired_prefix(State &S)
+{
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    int carry = 0;
+    for (int k0 = 0; k0 < S.W; k0 += T) {
+        int k = k0 + r, v = (k < S.W) ? __popc(S.Ub[k]) : 0, tot;
+        int ex = team_exscan<TW>(S, v, tot);
+        if (k < S.W) S.Ubase[k] = carry + ex;
+        carry += tot;
+    }
+    if (r == 0) S.Ubase[S.W] = carry;
+    Team<TW>::sync();
 }
 
 // ------------------------------------------------------------- load a sequence
@@ -252,16 +384,21 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
     S.has_smat = B.smat != nullptr;
     S.cols = B.cols ? B.cols + o : nullptr;
     const int Nw = S.W * 32;
+    bool sep = false, nondef = false;
     for (int p = r; p < Nw; p += T) {
-        uint8_t c = CODE_OTHER, cl = 0; uint16_t rc = 0;
+        uint8_t c = CODE_OTHER, cl = 0;
         if (p < N) {
             c = P.code_table[B.sym[o + p]];
-            if (B.rcode) rc = B.rcode[o + p];
+            if (B.rcode) { uint16_t rc = B.rcode[o + p]; S.rcode[p] = rc; if (__ldg(&B.rvals[rc]) != 0.5) nondef = true; }
             if (B.rclass) cl = B.rclass[o + p] & 7;
-        }
-        S.code[p] = c; S.rcode[p] = rc; S.rcl[p] = cl;
+            if (c == CODE_SEP) sep = true;
+        } else if (B.rcode) S.rcode[p] = 0;
+        S.code[p] = c; S.rcl[p] = cl;
         S.partner[p] = -1; S.owner[p] = -1;
     }
+    S.has_sep = Team<TW>::any(sep);
+    // "default reacts" switch, seq.py:273: every processed reactivity == 0.5
+    S.default_reacts = !Team<TW>::any(nondef);
     Team<TW>::sync();
     // restraint pairs (sorted by (v+w, v) by the host); mark their positions
     int nrb_all = 0;
@@ -271,72 +408,54 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
         S.rcl[rb[2 * k]] |= RC_RBPOS;       // distinct positions: no write conflicts on the same byte
         S.rcl[rb[2 * k + 1]] |= RC_RBPOS;
     }
-    // prefix count of separators (thread 0; N is small and this runs once per item)
-    if (r == 0) {
-        int c = 0, hs = 0;
-        for (int p = 0; p < N; p++) { S.sepcnt[p] = (int16_t)c; if (S.code[p] == CODE_SEP) { c++; hs = 1; } }
-        S.sepcnt[N] = (int16_t)c;
-        S.misc[2] = hs;
-        // statically valid restraint cells: boolmat[v,w] != 0 (seq.py:443) and on a walked diagonal
-        int n = 0;
-        for (int k = 0; k < nrb_all; k++) {
-            int v = rb[2 * k], w = rb[2 * k + 1], s = v + w;
-            if (s < 4 || s > 2 * N - 6) continue;
-            if (!(P.pairmask[S.code[v]] >> S.code[w] & 1)) continue;
-            int inc = 4;
-            if (v + 1 < N && S.code[v + 1] == CODE_SEP) inc = 2;
-            if (v + 2 < N && S.code[v + 2] == CODE_SEP) inc = 3;
-            if (w < v + inc) continue;
-            if (B.interchainonly && S.sepcnt[w] - S.sepcnt[v] <= 0) continue;
-            S.rbv[n] = (int16_t)v; S.rbw[n] = (int16_t)w; n++;
+    S.nrb = 0;
+    if (S.has_sep || nrb_all) {
+        if (r == 0) {
+            // prefix count of separators (rare: only multi-chain inputs)
+            if (S.has_sep) {
+                int c = 0;
+                for (int p = 0; p < N; p++) { S.sepcnt[p] = (int16_t)c; if (S.code[p] == CODE_SEP) c++; }
+                S.sepcnt[N] = (int16_t)c;
+            }
+            // statically valid restraint cells: boolmat[v,w] != 0 (seq.py:443) and on a walked diagonal
+            int n = 0;
+            for (int k = 0; k < nrb_all; k++) {
+                int v = rb[2 * k], w = rb[2 * k + 1], s = v + w;
+                if (s < 4 || s > 2 * N - 6) continue;
+                if (!(P.pairmask[S.code[v]] >> S.code[w] & 1)) continue;
+                int inc = 4;
+                if (v + 1 < N && S.code[v + 1] == CODE_SEP) inc = 2;
+                if (v + 2 < N && S.code[v + 2] == CODE_SEP) inc = 3;
+                if (w < v + inc) continue;
+                if (B.interchainonly && (!S.has_sep || S.sepcnt[w] - S.sepcnt[v] <= 0)) continue;
+                S.rbv[n] = (int16_t)v; S.rbw[n] = (int16_t)w; n++;
+            }
+            S.misc[3] = n;
         }
-        S.misc[3] = n;
-        // "default reacts" switch, seq.py:273: every processed reactivity == 0.5
-        int dflt = 1;
-        if (B.rcode) for (int p = 0; p < N; p++) if (B.rvals[S.rcode[p]] != 0.5) { dflt = 0; break; }
-        S.misc[4] = dflt;
+        Team<TW>::sync();
+        S.nrb = S.misc[3];
     }
     Team<TW>::sync();
-    S.has_sep = S.misc[2]; S.nrb = S.misc[3]; S.default_reacts = S.misc[4];
-    // forward masks of each pairing symbol, reversed masks of its partners
-    for (int idx = r; idx < P.npc * S.W; idx += T) {
-        int c = idx / S.W, k = idx - c * S.W, code = P.pc_code[c];
-        uint32_t m = 0;
-        for (int b = 0; b < 32; b++) if (S.code[32 * k + b] == code && 32 * k + b < N) m |= 1u << b;
-        S.M[c * S.W + k] = m;
+    // forward masks of each pairing symbol, reversed masks of its partners (bit q of the
+    // reversed arrays is position j = N - 1 - (q - 32))
+    for (int c = 0; c < P.npc; c++) {
+        const int code = P.pc_code[c];
+        const uint32_t pm = P.pairmask[code];
+        team_mask<TW>(S.M + c * S.W, S.W, [&](int p) { return p < N && S.code[p] == code; });
+        team_mask<TW>(S.PR + c * S.WR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && (pm >> S.code[j] & 1); });
     }
-    for (int idx = r; idx < P.npc * S.WR; idx += T) {
-        int c = idx / S.WR, k = idx - c * S.WR;
-        uint32_t pm = P.pairmask[P.pc_code[c]], m = 0;
-        for (int b = 0; b < 32; b++) {
-            int j = N - 1 - (32 * k + b - 32);
-            if (j >= 0 && j < N && (pm >> S.code[j] & 1)) m |= 1u << b;
-        }
-        S.PR[c * S.WR + k] = m;
-    }
-    for (int k = r; k < S.W; k += T) {
-        uint32_t m = 0;
-        for (int b = 0; b < 32; b++) {
-            int p = 32 * k + b;
-            if (p < N && !(S.rcl[p] & (RC_X | RC_NORIGHT | RC_RBPOS))) m |= 1u << b;
-        }
-        S.rowok[k] = m;
-    }
-    for (int k = r; k < S.WR; k += T) {
-        uint32_t m = 0;
-        for (int b = 0; b < 32; b++) {
-            int j = N - 1 - (32 * k + b - 32);
-            if (j >= 0 && j < N && !(S.rcl[j] & (RC_X | RC_NOLEFT | RC_RBPOS))) m |= 1u << b;
-        }
-        S.colokR[k] = m;
-    }
+    team_mask<TW>(S.rowok, S.W, [&](int p) { return p < N && !(S.rcl[p] & (RC_X | RC_NORIGHT | RC_RBPOS)); });
+    team_mask<TW>(S.colokR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && !(S.rcl[j] & (RC_X | RC_NOLEFT | RC_RBPOS)); });
+    team_mask<TW>(S.Ub, S.W, [&](int p) { return p < N; });
+    for (int k = r; k <= S.W; k += T) S.Ubase[k] = (32 * k < N) ? 32 * k : N;
     Team<TW>::sync();
 }
 
 // add a selected stem to the structure: partners, owner, row/column masks
-// (AnnotateStems zeroes the rows and columns of every selected position, seq.py:446-451)
+// (AnnotateStems zeroes the rows and columns of every selected position, seq.py:446-451),
+// the unpaired mask and the 5'-sorted copy of the stem list
 template <int TW>
-__device__ void team_apply_stem(State &S, int i, int j, int len)
+__device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = true)
 {
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int idx = S.nst;
@@ -346,13 +465,28 @@ __device__ void team_apply_stem(State &S, int i, int j, int len)
         S.owner[v] = (int16_t)idx; S.owner[w] = (int16_t)idx;
         atomicAnd(&S.rowok[v >> 5], ~(1u << (v & 31)));
         atomicAnd(&S.rowok[w >> 5], ~(1u << (w & 31)));
+        atomicAnd(&S.Ub[v >> 5], ~(1u << (v & 31)));
+        atomicAnd(&S.Ub[w >> 5], ~(1u << (w & 31)));
         int rv = 32 + S.N - 1 - v, rw = 32 + S.N - 1 - w;
         atomicAnd(&S.colokR[rv >> 5], ~(1u << (rv & 31)));
         atomicAnd(&S.colokR[rw >> 5], ~(1u << (rw & 31)));
     }
-    if (r == 0) { S.sti[idx] = (int16_t)i; S.stj[idx] = (int16_t)j; S.stl[idx] = (int16_t)len; }
+    // insert into the 5'-sorted order: entries with a larger i move up by one
+    int pos = 0;
+    for (int q = 0; q < idx; q++) pos += (S.sti[S.byi[q]] < i);       // idx is small; every thread counts
+    Team<TW>::sync();
+    for (int q0 = 0; q0 < idx; q0 += T) {            // shift in chunks from the top so reads precede overwrites
+        int q = idx - 1 - q0 - r;
+        int16_t v = 0; bool mv = q >= pos && q >= 0;
+        if (mv) v = S.byi[q];
+        Team<TW>::sync();
+        if (mv) S.byi[q + 1] = v;
+        Team<TW>::sync();
+    }
+    if (r == 0) { S.sti[idx] = (int16_t)i; S.stj[idx] = (int16_t)j; S.stl[idx] = (int16_t)len; S.byi[pos] = (int16_t)idx; }
     S.nst = idx + 1;
     Team<TW>::sync();
+    if (refresh) team_unpaired_prefix<TW>(S);
 }
 
 // ------------------------------------------------ pseudoknot levels per stem
@@ -360,8 +494,9 @@ __device__ void team_apply_stem(State &S, int i, int j, int len)
 // position-disjoint stems cross all-or-none, so the crossing test runs on the
 // outermost pairs, cross_count is the summed length of the crossing stems, the
 // first-fit order is (cross_count, outer i) and groups are ranked by their
-// number of pairs (stable).  tests/test_levels.py checks this against the
-// oracle's per-pair restatement.
+// number of pairs (stable).  tests/test_emu_vs_oracle.py checks this against the
+// oracle's per-pair restatement.  Also refreshes the 5'-sorted stem copies
+// (ssi, ssj, ssl, sslev) the stem-walk of ScoreStems reads.
 __device__ __forceinline__ bool stems_cross(int i, int j, int k, int l)
 {
     return (i < k && k < j && j < l) || (k < i && i < l && l < j);
@@ -373,55 +508,71 @@ __device__ int team_levels(State &S)
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int n = S.nst;
     if (n == 0) return 0;
+    bool crossing = false;
     for (int t = r; t < n; t += T) {
         int i = S.sti[t], j = S.stj[t], c = 0;
         for (int u = 0; u < n; u++)
             if (u != t && stems_cross(i, j, S.sti[u], S.stj[u])) c += S.stl[u];
         S.cc[t] = c;
+        if (c) crossing = true;
     }
-    Team<TW>::sync();
-    for (int t = r; t < n; t += T) {
-        int c = S.cc[t], i = S.sti[t], rank = 0;
-        for (int u = 0; u < n; u++) {
-            int cu = S.cc[u];
-            if (cu < c || (cu == c && S.sti[u] < i)) rank++;
-        }
-        S.perm[rank] = (int16_t)t;
-    }
-    Team<TW>::sync();
-    if (r == 0) {
-        int ng = 0;
-        for (int a = 0; a < n; a++) {
-            int t = S.perm[a], g = -1;
-            if (S.cc[t] == 0) {
-                g = 0;                                 // crosses nothing: fits the first group
-                if (ng == 0) { ng = 1; S.gsz[0] = 0; }
-            } else {
-                int i = S.sti[t], j = S.stj[t];
-                for (int h = 0; h < ng && g < 0; h++) {
-                    bool clash = false;
-                    for (int b = 0; b < a && !clash; b++) {
-                        int u = S.perm[b];
-                        if (S.grp[u] == h && stems_cross(i, j, S.sti[u], S.stj[u])) clash = true;
-                    }
-                    if (!clash) g = h;
-                }
-                if (g < 0) { g = ng++; S.gsz[g] = 0; }
+    crossing = Team<TW>::any(crossing);
+    int ng = 1;
+    if (!crossing) {
+        // nothing crosses: one group, every stem on level 1
+        for (int t = r; t < n; t += T) S.stlev[t] = 1;
+        Team<TW>::sync();
+    } else {
+        Team<TW>::sync();
+        for (int t = r; t < n; t += T) {
+            int c = S.cc[t], i = S.sti[t], rank = 0;
+            for (int u = 0; u < n; u++) {
+                int cu = S.cc[u];
+                if (cu < c || (cu == c && S.sti[u] < i)) rank++;
             }
-            S.grp[t] = (int16_t)g;
-            S.gsz[g] += S.stl[t];
+            S.perm[rank] = (int16_t)t;
         }
-        // groups.sort(key=len, reverse=True) is stable: level = 1 + #groups that come first
-        for (int t = 0; t < n; t++) {
-            int g = S.grp[t], sz = S.gsz[g], lev = 1;
-            for (int h = 0; h < ng; h++)
-                if (S.gsz[h] > sz || (S.gsz[h] == sz && h < g)) lev++;
-            S.stlev[t] = (uint8_t)(lev > 255 ? 255 : lev);
+        Team<TW>::sync();
+        if (r == 0) {
+            ng = 0;
+            for (int a = 0; a < n; a++) {
+                int t = S.perm[a], g = -1;
+                if (S.cc[t] == 0) {
+                    g = 0;                                 // crosses nothing: fits the first group
+                    if (ng == 0) { ng = 1; S.gsz[0] = 0; }
+                } else {
+                    int i = S.sti[t], j = S.stj[t];
+                    for (int h = 0; h < ng && g < 0; h++) {
+                        bool clash = false;
+                        for (int b = 0; b < a && !clash; b++) {
+                            int u = S.perm[b];
+                            if (S.grp[u] == h && stems_cross(i, j, S.sti[u], S.stj[u])) clash = true;
+                        }
+                        if (!clash) g = h;
+                    }
+                    if (g < 0) { g = ng++; S.gsz[g] = 0; }
+                }
+                S.grp[t] = (int16_t)g;
+                S.gsz[g] += S.stl[t];
+            }
+            // groups.sort(key=len, reverse=True) is stable: level = 1 + #groups that come first
+            for (int t = 0; t < n; t++) {
+                int g = S.grp[t], sz = S.gsz[g], lev = 1;
+                for (int h = 0; h < ng; h++)
+                    if (S.gsz[h] > sz || (S.gsz[h] == sz && h < g)) lev++;
+                S.stlev[t] = (uint8_t)(lev > 255 ? 255 : lev);
+            }
+            S.misc[5] = ng;
         }
-        S.misc[5] = ng;
+        Team<TW>::sync();
+        ng = S.misc[5];
+    }
+    for (int q = r; q < n; q += T) {
+        int t = S.byi[q];
+        S.ssi[q] = S.sti[t]; S.ssj[q] = S.stj[t]; S.ssl[q] = S.stl[t]; S.sslev[q] = S.stlev[t];
     }
     Team<TW>::sync();
-    return S.misc[5];
+    return ng;
 }
 
 // ------------------------------------------------------------ cell score
@@ -446,35 +597,96 @@ __device__ __forceinline__ double cell_score(const State &S, const DevParams &P,
     return w;
 }
 
+// raw bp score of the run (a .. a+len-1) on diagonal s: Python sum(), left to right from 0 (seq.py:416)
+__device__ __forceinline__ double run_score(const State &S, const DevParams &P, const DevBatch &B, int s, int a, int len)
+{
+    double sc = 0.0;
+    if (!(S.has_react && !S.default_reacts) && !S.has_smat) {
+        for (int q = 0; q < len; q++) sc = __dadd_rn(sc, P.weight[S.code[a + q] * MAXK + S.code[s - a - q]]);
+    } else {
+        for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
+    }
+    return sc;
+}
+
 // ---------------------------------------------------- one word of a diagonal
+// remaining restraint pairs keep their own cell (seq.py:443) if both ends are still free
+__device__ __forceinline__ uint32_t restraint_cells(const State &S, int s, int k)
+{
+    uint32_t x = 0;
+    int a = 0, b = S.nrb;
+    while (a < b) { int mid = (a + b) >> 1; if (S.rbv[mid] + S.rbw[mid] < s) a = mid + 1; else b = mid; }
+    for (; a < S.nrb && S.rbv[a] + S.rbw[a] == s; a++) {
+        int v = S.rbv[a];
+        if ((v >> 5) == k && S.partner[v] < 0 && S.partner[S.rbw[a]] < 0) x |= 1u << (v & 31);
+    }
+    return x;
+}
+
+__device__ __forceinline__ uint32_t range_mask(int k, int lo, int hi)
+{
+    uint32_t x = 0xffffffffu;
+    int b0 = lo - 32 * k, b1 = hi - 32 * k;
+    if (b0 > 0) x &= (b0 >= 32) ? 0u : (0xffffffffu << b0);
+    if (b1 < 31) x &= (b1 < 0) ? 0u : (0xffffffffu >> (31 - b1));
+    return x;
+}
+
 // bit t of the result: cell (i = 32k + t, j = s - i) is a live base pair of the
 // masked bool matrix AnnotateStems walks (seq.py:431-451), restricted to the
-// walked range lo <= i <= hi of the diagonal.
+// walked range lo <= i <= hi of the diagonal.  Stateless form (fresh loads).
 __device__ __forceinline__ uint32_t diag_word(const State &S, const DevParams &P, int s, int k, int lo, int hi)
 {
     const int bo = 32 * k + (S.N - 1 - s) + 32;     // bit offset into the reversed arrays
     const int wo = bo >> 5, sh = bo & 31;
     uint32_t x = 0;
-    #pragma unroll 4
     for (int c = 0; c < P.npc; c++) {
         uint32_t f = S.M[c * S.W + k];
         uint32_t g = __funnelshift_r(S.PR[c * S.WR + wo], S.PR[c * S.WR + wo + 1], sh);
         x |= f & g;
     }
     x &= S.rowok[k] & __funnelshift_r(S.colokR[wo], S.colokR[wo + 1], sh);
-    // range mask
-    int b0 = lo - 32 * k, b1 = hi - 32 * k;
-    if (b0 > 0) x &= (b0 >= 32) ? 0u : (0xffffffffu << b0);
-    if (b1 < 31) x &= (b1 < 0) ? 0u : (0xffffffffu >> (31 - b1));
-    // remaining restraint pairs keep their own cell (seq.py:443) if both ends are still free
-    if (S.nrb) {
-        int a = 0, b = S.nrb;
-        while (a < b) { int mid = (a + b) >> 1; if (S.rbv[mid] + S.rbw[mid] < s) a = mid + 1; else b = mid; }
-        for (; a < S.nrb && S.rbv[a] + S.rbw[a] == s; a++) {
-            int v = S.rbv[a];
-            if ((v >> 5) == k && S.partner[v] < 0 && S.partner[S.rbw[a]] < 0) x |= 1u << (v & 31);
+    x &= range_mask(k, lo, hi);
+    if (S.nrb) x |= restraint_cells(S, s, k);
+    return x;
+}
+
+// Sliding form: walks the words k0, k0+1, ... of one diagonal and keeps the low
+// halves of the funnel shifts in registers, so each word costs npc + 1 new loads
+// of the reversed arrays instead of 2 (npc + 1).
+struct DiagWalk {
+    int k, wo, sh;
+    uint32_t plo[4], clo;
+};
+
+__device__ __forceinline__ void walk_begin(DiagWalk &it, const State &S, const DevParams &P, int s, int k0)
+{
+    const int bo = 32 * k0 + (S.N - 1 - s) + 32;
+    it.k = k0; it.wo = bo >> 5; it.sh = bo & 31;
+    #pragma unroll
+    for (int c = 0; c < 4; c++) it.plo[c] = (c < P.npc) ? S.PR[c * S.WR + it.wo] : 0u;
+    it.clo = S.colokR[it.wo];
+}
+
+__device__ __forceinline__ uint32_t walk_next(DiagWalk &it, const State &S, const DevParams &P, int s, int lo, int hi)
+{
+    const int k = it.k, wo = it.wo;
+    uint32_t x = 0;
+    #pragma unroll
+    for (int c = 0; c < 4; c++)
+        if (c < P.npc) {
+            uint32_t phi = S.PR[c * S.WR + wo + 1];
+            x |= S.M[c * S.W + k] & __funnelshift_r(it.plo[c], phi, it.sh);
+            it.plo[c] = phi;
         }
-    }
+    for (int c = 4; c < P.npc; c++)
+        x |= S.M[c * S.W + k] & __funnelshift_r(S.PR[c * S.WR + wo], S.PR[c * S.WR + wo + 1], it.sh);
+    uint32_t chi = S.colokR[wo + 1];
+    x &= S.rowok[k] & __funnelshift_r(it.clo, chi, it.sh);
+    it.clo = chi;
+    x &= range_mask(k, lo, hi);
+    if (S.nrb) x |= restraint_cells(S, s, k);
+    it.k = k + 1; it.wo = wo + 1;
     return x;
 }
 
@@ -502,85 +714,6 @@ __device__ __forceinline__ bool diag_range(const State &S, const DevBatch &B, in
     return hi >= lo;
 }
 
-// ------------------------------------------------------------- ScoreStems
-// adjusted score of candidate (outer pair (a, s-a), length len, raw score bps)
-// given the current structure; seq.py:641-745.
-__device__ double score_candidate(const State &S, const DevParams &P, int s, int a, int len, double bps)
-{
-    const int N = S.N;
-    const int oi = a, oj = s - a;
-    const int ss = a + len - 1, se = oj - len + 1;    // innermost pair, seq.py:655
-    int dots = 0, br = 0, nedges = 0, e0 = -1, e1 = -1, inblockend = -1;
-    bool between = false;
-    unsigned long long levmask = 0;
-    if (S.nst == 0) {
-        dots = se - ss - 1;
-        between = S.has_sep && (S.sepcnt[se] - S.sepcnt[ss + 1] > 0);
-    } else {
-        for (int pos = ss + 1; pos < se; pos++) {         // seq.py:665-689
-            int pr = S.partner[pos];
-            if (pr < 0) {
-                if (pos > inblockend) dots++;
-                if (S.code[pos] == CODE_SEP) between = true;
-            } else if (pr < ss || pr > se) {
-                if (pos > inblockend) {
-                    br++;
-                    int lv = S.stlev[S.owner[pos]];
-                    levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
-                }
-            } else if (pos < pr && pr > inblockend) {
-                inblockend = pr;
-                if (nedges == 0) { e0 = pos; e1 = pr; }
-                nedges++;
-            }
-        }
-    }
-    // good loops = {0..4}^2 with |x - y| <= 2 (the 19 entries of seq.py:615-622)
-    bool goodloop = false; int diff1 = 0;
-    if (nedges == 1) {
-        int x = e0 - ss - 1, y = se - e1 - 1, d = x > y ? x - y : y - x;
-        if (x <= 4 && y <= 4 && d <= 2) { goodloop = true; diff1 = d; }
-    }
-    bool goodout = false; int diff2 = 0;
-    if (S.nst) {                                           // seq.py:700-711
-        int vv = oi - 1, ww = oj + 1;
-        while (vv >= 0 && oi - vv - 1 < 5 && S.partner[vv] < 0) vv--;
-        while (ww < N && ww - oj - 1 < 5 && S.partner[ww] < 0) ww++;
-        if (vv >= 0 && ww < N && S.partner[vv] == ww) {
-            int x = oi - vv - 1, y = ww - oj - 1, d = x > y ? x - y : y - x;
-            if (x <= 4 && y <= 4 && d <= 2) { goodout = true; diff2 = d; }
-        }
-    }
-    if (!goodloop && !goodout && len < 3) return -1.0;     // seq.py:744-745
-    // loopfactor, seq.py:715 (left to right, no contraction)
-    double lf = __dadd_rn(1.0, __dmul_rn(__dmul_rn(P.loopbonus, goodloop ? 1.0 : 0.0), 2.0 - diff1 * 0.5));
-    lf = __dadd_rn(lf, __dmul_rn(__dmul_rn(P.loopbonus, goodout ? 1.0 : 0.0), 2.0 - diff2 * 0.5));
-    // tetraloop bonus, seq.py:598-604, 718
-    double tf = 1.0;
-    if (se - ss - 1 == 4 && S.code[ss + 1] == CODE_G &&
-        (S.code[ss + 3] == CODE_G || S.code[ss + 3] == CODE_A) && S.code[ss + 4] == CODE_A) tf = 1.25;
-    // stem distance factor, seq.py:721-726
-    double sdf = 1.0;
-    if (!between) {
-        int ideal = inblockend == -1 ? 4 : 2;
-        if (P.bw_is_int) {
-            int k = dots + P.bw_int * br - ideal; if (k < 0) k = -k;
-            sdf = (k < P.sdf_n) ? __ldg(&P.sdf_lut[k]) : pow(1.0 / (1.0 + (double)k), P.distcoef);
-        } else {
-            double x = fabs(__dadd_rn((double)dots, __dmul_rn(P.bracketweight, (double)br)) - (double)ideal);
-            sdf = pow(1.0 / (1.0 + x), P.distcoef);        // documented <= 1 ulp deviation
-        }
-    }
-    int order = __popcll(levmask);
-    double of = (order < P.of_n) ? __ldg(&P.of_lut[order]) : pow(1.0 / (1.0 + order), P.orderpenalty);
-    // seq.py:732
-    double fin = __dmul_rn(bps, sdf);
-    fin = __dmul_rn(fin, of);
-    fin = __dmul_rn(fin, lf);
-    fin = __dmul_rn(fin, tf);
-    return fin;
-}
-
 // ---------------------------------------------------- enumerate one diagonal
 // calls emit(a, e) for every maximal run [a, e] (in i) of at least P.m cells, in
 // increasing a: outermost stem first, the order of seq.py:486-493.
@@ -591,11 +724,13 @@ __device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, co
     if (!diag_range(S, B, s, lo, hi)) return;
     const int k0 = lo >> 5, k1 = hi >> 5;
     const int m = P.m;
-    uint32_t x = diag_word(S, P, s, k0, lo, hi);
+    DiagWalk it;
+    walk_begin(it, S, P, s, k0);
+    uint32_t x = walk_next(it, S, P, s, lo, hi);
     uint32_t prev_top = 0;
     int skip_until = -1;                   // runs already emitted extend up to here
     for (int k = k0; k <= k1; k++) {
-        uint32_t xn = (k < k1) ? diag_word(S, P, s, k + 1, lo, hi) : 0u;
+        uint32_t xn = (k < k1) ? walk_next(it, S, P, s, lo, hi) : 0u;
         if (x) {
             uint32_t y = x;
             for (int t = 1; t < m; t++) y &= __funnelshift_r(x, xn, t);
@@ -625,6 +760,167 @@ __device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, co
     }
 }
 
+// ------------------------------------------------------------- ScoreStems
+// What the scan of the region confined by the innermost pair (ss, se) yields
+// (seq.py:665-689).
+struct Region {
+    int dots, br, nedges, e0, e1, inblockend;
+    bool between;
+    unsigned long long levmask;
+};
+
+// the reference's own position-by-position scan
+__device__ __forceinline__ void region_scan(const State &S, int ss, int se, Region &R)
+{
+    int dots = 0, br = 0, nedges = 0, e0 = -1, e1 = -1, inblockend = -1;
+    bool between = false;
+    unsigned long long levmask = 0;
+    for (int pos = ss + 1; pos < se; pos++) {         // seq.py:665-689
+        int pr = S.partner[pos];
+        if (pr < 0) {
+            if (pos > inblockend) dots++;
+            if (S.code[pos] == CODE_SEP) between = true;
+        } else if (pr < ss || pr > se) {
+            if (pos > inblockend) {
+                br++;
+                int lv = S.stlev[S.owner[pos]];
+                levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
+            }
+        } else if (pos < pr && pr > inblockend) {
+            inblockend = pr;
+            if (nedges == 0) { e0 = pos; e1 = pr; }
+            nedges++;
+        }
+    }
+    R.dots = dots; R.br = br; R.nedges = nedges; R.e0 = e0; R.e1 = e1; R.inblockend = inblockend;
+    R.between = between; R.levmask = levmask;
+}
+
+// The same quantities from a walk over the selected stems in 5' order.  ss and se
+// are unpaired, so each arm of a selected stem lies entirely inside or entirely
+// outside (ss, se):
+//   both arms inside  -> its outermost pair is the only one that can raise
+//                        inblockend (the inner pairs close earlier); merged spans
+//                        of such stems are the "blocks";
+//   one arm inside    -> `len` bracket positions, counted (with the stem's level)
+//                        unless a block covers the arm;
+//   dots              =  unpaired positions of the region outside the blocks
+//                        (prefix popcounts of the unpaired mask).
+// An arm (a contiguous range of paired positions of ONE stem) cannot straddle a
+// block boundary (a paired position of ANOTHER stem), so testing its first
+// position is enough.  5' arms meet the blocks in walk order; a 3' arm whose 5'
+// arm lies left of ss is checked against the inner stems directly (these are
+// exactly the stems the candidate would cross: rare).
+__device__ __forceinline__ void region_stems(const State &S, int ss, int se, Region &R)
+{
+    const int n = S.nst;
+    int br = 0, nedges = 0, e0 = -1, e1 = -1, ibe = -1, blo = 0, covU = 0;
+    unsigned long long levmask = 0;
+    for (int q = 0; q < n; q++) {
+        const int i = S.ssi[q];
+        if (i > se) break;                              // sorted by i: nothing further can reach the region
+        const int j = S.ssj[q];
+        const bool ain = i > ss, bin = j > ss && j < se; // i < se holds here (i != se: se is unpaired)
+        if (ain && bin) {
+            if (j > ibe) {
+                if (nedges == 0) { e0 = i; e1 = j; }
+                nedges++;
+                if (i > ibe) {                          // a new block starts: close the previous one
+                    if (ibe >= 0) covU += unpaired_before(S, ibe + 1) - unpaired_before(S, blo);
+                    blo = i;
+                }
+                ibe = j;
+            }
+        } else if (ain) {                               // 5' arm inside, partner beyond se
+            if (i > ibe) {
+                br += S.ssl[q];
+                int lv = S.sslev[q];
+                levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
+            }
+        } else if (bin) {                               // 3' arm inside, 5' arm left of ss
+            const int x = j - S.ssl[q] + 1;
+            bool covered = false;
+            for (int u = q + 1; u < n && !covered; u++) {
+                int iu = S.ssi[u];
+                if (iu >= x) break;
+                if (iu > ss && S.ssj[u] < se && S.ssj[u] > x) covered = true;
+            }
+            if (!covered) {
+                br += S.ssl[q];
+                int lv = S.sslev[q];
+                levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
+            }
+        }
+    }
+    if (ibe >= 0) covU += unpaired_before(S, ibe + 1) - unpaired_before(S, blo);
+    R.dots = unpaired_before(S, se) - unpaired_before(S, ss + 1) - covU;
+    R.br = br; R.nedges = nedges; R.e0 = e0; R.e1 = e1; R.inblockend = ibe;
+    R.between = S.has_sep && (S.sepcnt[se] - S.sepcnt[ss + 1] > 0);   // separators never pair
+    R.levmask = levmask;
+}
+
+// adjusted score of candidate (outer pair (a, s-a), length len, raw score bps)
+// given the current structure; seq.py:641-745.
+__device__ __forceinline__ double score_candidate(const State &S, const DevParams &P, int s, int a, int len, double bps)
+{
+    const int N = S.N;
+    const int oi = a, oj = s - a;
+    const int ss = a + len - 1, se = oj - len + 1;    // innermost pair, seq.py:655
+    Region R;
+    if (S.nst == 0) {
+        R.dots = se - ss - 1; R.br = 0; R.nedges = 0; R.e0 = R.e1 = -1; R.inblockend = -1; R.levmask = 0;
+        R.between = S.has_sep && (S.sepcnt[se] - S.sepcnt[ss + 1] > 0);
+    } else {
+        bool by_stems = S.region_mode == REGION_STEMS ||
+                        (S.region_mode == REGION_AUTO && 5 * S.nst < 2 * (se - ss));
+        if (by_stems) region_stems(S, ss, se, R); else region_scan(S, ss, se, R);
+    }
+    // good loops = {0..4}^2 with |x - y| <= 2 (the 19 entries of seq.py:615-622)
+    bool goodloop = false; int diff1 = 0;
+    if (R.nedges == 1) {
+        int x = R.e0 - ss - 1, y = se - R.e1 - 1, d = x > y ? x - y : y - x;
+        if (x <= 4 && y <= 4 && d <= 2) { goodloop = true; diff1 = d; }
+    }
+    bool goodout = false; int diff2 = 0;
+    if (S.nst) {                                           // seq.py:700-711
+        int vv = oi - 1, ww = oj + 1;
+        while (vv >= 0 && oi - vv - 1 < 5 && S.partner[vv] < 0) vv--;
+        while (ww < N && ww - oj - 1 < 5 && S.partner[ww] < 0) ww++;
+        if (vv >= 0 && ww < N && S.partner[vv] == ww) {
+            int x = oi - vv - 1, y = ww - oj - 1, d = x > y ? x - y : y - x;
+            if (x <= 4 && y <= 4 && d <= 2) { goodout = true; diff2 = d; }
+        }
+    }
+    if (!goodloop && !goodout && len < 3) return -1.0;     // seq.py:744-745
+    // loopfactor, seq.py:715 (left to right, no contraction)
+    double lf = __dadd_rn(1.0, __dmul_rn(__dmul_rn(P.loopbonus, goodloop ? 1.0 : 0.0), 2.0 - diff1 * 0.5));
+    lf = __dadd_rn(lf, __dmul_rn(__dmul_rn(P.loopbonus, goodout ? 1.0 : 0.0), 2.0 - diff2 * 0.5));
+    // tetraloop bonus, seq.py:598-604, 718
+    double tf = 1.0;
+    if (se - ss - 1 == 4 && S.code[ss + 1] == CODE_G &&
+        (S.code[ss + 3] == CODE_G || S.code[ss + 3] == CODE_A) && S.code[ss + 4] == CODE_A) tf = 1.25;
+    // stem distance factor, seq.py:721-726
+    double sdf = 1.0;
+    if (!R.between) {
+        int ideal = R.inblockend == -1 ? 4 : 2;
+        if (P.bw_is_int) {
+            int k = R.dots + P.bw_int * R.br - ideal; if (k < 0) k = -k;
+            sdf = (k < P.sdf_n) ? __ldg(&P.sdf_lut[k]) : pow(1.0 / (1.0 + (double)k), P.distcoef);
+        } else {
+            double x = fabs(__dadd_rn((double)R.dots, __dmul_rn(P.bracketweight, (double)R.br)) - (double)ideal);
+            sdf = pow(1.0 / (1.0 + x), P.distcoef);        // documented <= 1 ulp deviation
+        }
+    }
+    int order = __popcll(R.levmask);
+    double of = (order < P.of_n) ? __ldg(&P.of_lut[order]) : pow(1.0 / (1.0 + order), P.orderpenalty);
+    // seq.py:732
+    double fin = __dmul_rn(bps, sdf);
+    fin = __dmul_rn(fin, of);
+    fin = __dmul_rn(fin, lf);
+    fin = __dmul_rn(fin, tf);
+    return fin;
+}
+
 // -------------------------------------------- one OptimalStems pass (arg-max)
 // team-wide reductions --------------------------------------------------------
 template <int TW>
@@ -634,23 +930,22 @@ __device__ __forceinline__ Best team_argmax(State &S, Best best)
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         double f = __shfl_xor_sync(0xffffffffu, best.fin, d);
-        double bp = __shfl_xor_sync(0xffffffffu, best.bps, d);
         uint32_t k = __shfl_xor_sync(0xffffffffu, best.key, d);
         int l = __shfl_xor_sync(0xffffffffu, best.len, d);
-        if (better(f, k, best.fin, best.key)) { best.fin = f; best.key = k; best.len = l; best.bps = bp; }
+        if (better(f, k, best.fin, best.key)) { best.fin = f; best.key = k; best.len = l; }
     }
     if (TW > 1) {
-        // cross-warp through the (now idle) scratch words of the team
-        double *sd = S.red;                              // 2 doubles + 2 words per warp
-        uint32_t *sk = (uint32_t *)(S.red + 2 * TW);
+        // cross-warp through the scratch words of the team
+        double *sd = S.red;                              // 1 double + 2 words per warp
+        uint32_t *sk = (uint32_t *)(S.red + TW);
         __syncthreads();
         int w = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) { sd[2 * w] = best.fin; sd[2 * w + 1] = best.bps; sk[2 * w] = best.key; sk[2 * w + 1] = (uint32_t)best.len; }
+        if ((threadIdx.x & 31) == 0) { sd[w] = best.fin; sk[2 * w] = best.key; sk[2 * w + 1] = (uint32_t)best.len; }
         __syncthreads();
-        Best b2; b2.fin = -1e300; b2.key = 0xffffffffu; b2.len = 0; b2.bps = 0.0;
+        Best b2; b2.fin = -1e300; b2.key = 0xffffffffu; b2.len = 0;
         for (int q = 0; q < TW; q++) {
-            double f = sd[2 * q]; uint32_t k = sk[2 * q];
-            if (better(f, k, b2.fin, b2.key)) { b2.fin = f; b2.key = k; b2.len = (int)sk[2 * q + 1]; b2.bps = sd[2 * q + 1]; }
+            double f = sd[q]; uint32_t k = sk[2 * q];
+            if (better(f, k, b2.fin, b2.key)) { b2.fin = f; b2.key = k; b2.len = (int)sk[2 * q + 1]; }
         }
         best = b2;
         __syncthreads();
@@ -659,56 +954,96 @@ __device__ __forceinline__ Best team_argmax(State &S, Best best)
     return best;
 }
 
+// Phase 2b for one survivor: ScoreStems' adjusted score; folds it into the
+// lane's running best.  Returns the adjusted score (-1e300 if below minfinscore).
+__device__ __forceinline__ double consider(const State &S, const DevParams &P, uint32_t key, int len, double bps, Best &best)
+{
+    double fin = score_candidate(S, P, (int)(key >> 16), (int)(key & 0xffff), len, bps);
+    if (!(fin >= P.minfinscore)) return -1e300;
+    if (better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
+    return fin;
+}
+
 // Enumerates every candidate stem of the current structure (AnnotateStems),
 // scores it (ScoreStems) and returns the team-wide best survivor: the head of
 // ChooseStems' stable sort.  fin = -1e300 when nothing reaches minfinscore.
-// Candidates are first pushed to a shared list so that the region scans are
-// spread over the whole team; candidates beyond the list capacity are scored by
-// the thread that found them.  On return cfin[c] holds the adjusted score of
-// list entry c (-1e300 if it failed minfinscore) and misc[0] the number of
-// candidates found (may exceed Ccap).
+//
+// keep_all == false (TAIL): the run and survivor lists are flushed whenever they
+// fill up, so any number of candidates is handled with small lists.
+// keep_all == true (STEP): every survivor stays in the list with its adjusted
+// score in cfin[] for team_choose; misc[7] = number of survivors found (may
+// exceed Ccap: the caller then retries with a larger list).
 template <int TW>
-__device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L)
+__device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L, const bool keep_all)
 {
     const int r = Team<TW>::rank(), T = Team<TW>::T;
-    Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0; best.bps = 0.0;
-    if (r == 0) S.misc[0] = 0;
+    Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
+    if (r == 0) { S.misc[0] = 0; S.misc[7] = 0; }
     Team<TW>::sync();
     const int smax = 2 * S.N - 6;
-    for (int s = 4 + r; s <= smax; s += T) {
-        enum_diag(S, P, B, s, [&](int a, int e) {
-            int len = e - a + 1;
-            if ((double)len < P.minlen) return;
-            double sc = 0.0;                      // Python sum(): left to right from 0 (seq.py:416)
-            for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
-            if (!(sc >= P.minbpscore)) return;
-            int slot = atomicAdd(&S.misc[0], 1);
-            uint32_t key = ((uint32_t)s << 16) | (uint32_t)a;
-            if (slot < L.Ccap) {
-                S.ckey[slot] = key;
-                S.clen[slot] = (uint16_t)len;
-                S.cbps[slot] = sc;
-            } else {
-                double fin = score_candidate(S, P, s, a, len, sc);
-                if (fin >= P.minfinscore && better(fin, key, best.fin, best.key)) {
-                    best.fin = fin; best.key = key; best.len = len; best.bps = sc;
-                }
+    const int Rcap = L.Rcap, Ccap = L.Ccap;
+    const int rflush = Rcap - (Rcap >> 2);
+    int nsurv = 0;                         // survivors in the list (uniform; mirrored in misc[7] for TW > 1)
+
+    // phase 2b over the survivor list (team-uniform call)
+    auto flush_survivors = [&]() {
+        int ns = nsurv < Ccap ? nsurv : Ccap;
+        Team<TW>::sync();                  // the survivors stored by the other threads are visible
+        for (int c = r; c < ns; c += T) {
+            double fin = consider(S, P, S.ckey[c], S.clen[c], S.cbps[c], best);
+            if (keep_all) S.cfin[c] = fin;
+        }
+        Team<TW>::sync();
+        if (!keep_all) {
+            nsurv = 0;
+            if (TW > 1) { if (r == 0) S.misc[7] = 0; Team<TW>::sync(); }
+        }
+    };
+    // phase 2a over the first nr entries of the run list (team-uniform call)
+    auto flush_runs = [&](int nr) {
+        for (int c0 = 0; c0 < nr; c0 += T) {
+            if (!keep_all && nsurv + T > Ccap) flush_survivors();
+            const int c = c0 + r;
+            bool push = false; uint32_t key = 0; int len = 0; double sc = 0.0;
+            if (c < nr) {
+                key = S.rkey[c]; len = S.rlen[c];
+                sc = run_score(S, P, B, (int)(key >> 16), (int)(key & 0xffff), len);
+                push = sc >= P.minbpscore;
             }
-        });
-    }
-    Team<TW>::sync();
-    int nc = S.misc[0]; if (nc > L.Ccap) nc = L.Ccap;
-    for (int c = r; c < nc; c += T) {
-        uint32_t key = S.ckey[c];
-        int len = S.clen[c];
-        double sc = S.cbps[c];
-        double fin = score_candidate(S, P, key >> 16, key & 0xffff, len, sc);
-        if (!(fin >= P.minfinscore)) fin = -1e300;
-        S.cfin[c] = fin;
-        if (fin > -1e300 && better(fin, key, best.fin, best.key)) {
-            best.fin = fin; best.key = key; best.len = len; best.bps = sc;
+            int slot;
+            int cnt = Team<TW>::claim(push, &S.misc[7], nsurv, slot);
+            if (push && slot < Ccap) { S.ckey[slot] = key; S.clen[slot] = (uint16_t)len; S.cbps[slot] = sc; }
+            nsurv += cnt;
+        }
+        Team<TW>::sync();
+        if (r == 0) S.misc[0] = 0;
+        Team<TW>::sync();
+    };
+
+    for (int s0 = 4; s0 <= smax; s0 += T) {
+        const int s = s0 + r;
+        const bool last = s0 + T > smax;
+        int done = -1;                     // runs of this lane's diagonal starting at a <= done are in the list
+        for (;;) {
+            bool pending = false;          // the run list filled up before this lane's diagonal was finished
+            if (s <= smax)
+                enum_diag(S, P, B, s, [&](int a, int e) {
+                    if (a <= done || pending) return;
+                    int len = e - a + 1;
+                    if ((double)len < P.minlen) return;
+                    int slot = atomicAdd(&S.misc[0], 1);
+                    if (slot < Rcap) { S.rkey[slot] = ((uint32_t)s << 16) | (uint32_t)a; S.rlen[slot] = (uint16_t)len; done = a; }
+                    else pending = true;
+                });
+            const bool anyp = Team<TW>::any(pending);
+            int nr = S.misc[0]; if (nr > Rcap) nr = Rcap;
+            Team<TW>::sync();             // every thread has read the count before anyone changes it again
+            if (nr >= rflush || last || anyp) flush_runs(nr);
+            if (!anyp) break;
         }
     }
+    flush_survivors();
+    if (r == 0) S.misc[7] = nsurv;
     Team<TW>::sync();
     return team_argmax<TW>(S, best);
 }
@@ -721,7 +1056,7 @@ __device__ __forceinline__ bool stems_share(int i1, int j1, int l1, int i2, int 
            iv_overlap(j1 - l1 + 1, j1, i2, i2 + l2 - 1) || iv_overlap(j1 - l1 + 1, j1, j2 - l2 + 1, j2);
 }
 
-// ChooseStems (seq.py:754-789) after a team_scan: every candidate with
+// ChooseStems (seq.py:754-789) after a team_scan(keep_all): every candidate with
 // fin >= subopt * best that conflicts with all the better chosen ones, in the
 // order of the reference's stable sort.  Writes (i, j, len) triples; returns
 // the number chosen, or -1 if the candidate list overflowed (caller retries
@@ -731,12 +1066,12 @@ __device__ int team_choose(State &S, const Layout &L, const Best &best, double s
                            int32_t *out, double *outfin, int cap)
 {
     const int r = Team<TW>::rank(), T = Team<TW>::T;
-    if (best.fin <= -1e300) return 0;
-    int ntot = S.misc[0];
+    int ntot = S.misc[7];
     if (ntot > L.Ccap) return -1;
+    if (best.fin <= -1e300) return 0;
     const double range = __dmul_rn(subopt, best.fin);
     // rank the in-range candidates by (fin desc, enumeration order)
-    int16_t *ord = S.perm;                 // reuse: at most Scap entries are kept
+    int16_t *ord = S.perm;                 // level scratch is free here: at most Scap entries are kept
     if (r == 0) S.misc[6] = 0;
     Team<TW>::sync();
     for (int c = r; c < ntot; c += T) {
@@ -776,32 +1111,6 @@ __device__ int team_choose(State &S, const Layout &L, const Best &best, double s
     return S.misc[6];
 }
 
-// exclusive prefix sum over the team; total returned through `total`
-template <int TW>
-__device__ __forceinline__ int team_exscan(State &S, int v, int &total)
-{
-#ifdef SQRN_HOST_EMU
-    total = v; return 0;
-#else
-    int lane = threadIdx.x & 31, x = v;
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-    int wtot = __shfl_sync(0xffffffffu, x, 31);
-    int excl = x - v;
-    if (TW == 1) { total = wtot; return excl; }
-    int *sc = (int *)S.red;
-    int w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 31) sc[w] = wtot;
-    __syncthreads();
-    int base = 0, tot = 0;
-    for (int q = 0; q < TW; q++) { int t = sc[q]; if (q < w) base += t; tot += t; }
-    __syncthreads();
-    total = tot;
-    return base + excl;
-#endif
-}
-
 // AnnotateStems output in reference order (YieldStems, ali.py:86-101): stems of
 // the current structure state, written as (i, j, len) + bp score.  Returns the
 // number of stems (may exceed cap: the caller then re-allocates and re-runs).
@@ -813,35 +1122,43 @@ __device__ int team_yield(State &S, const DevParams &P, const DevBatch &B, int32
     int base = 0;
     for (int s0 = 4; s0 <= smax; s0 += T) {
         int s = s0 + r, cnt = 0;
-        if (s <= smax)
-            enum_diag(S, P, B, s, [&](int a, int e) {
-                int len = e - a + 1;
-                if ((double)len < P.minlen) return;
-                double sc = 0.0;
-                for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
-                if (sc >= P.minbpscore) cnt++;
-            });
-        int tot, off = team_exscan<TW>(S, cnt, tot);
-        if (cnt && s <= smax) {
-            int w = base + off;
-            enum_diag(S, P, B, s, [&](int a, int e) {
-                int len = e - a + 1;
-                if ((double)len < P.minlen) return;
-                double sc = 0.0;
-                for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
-                if (sc >= P.minbpscore) {
+        // pass 0 counts the stems of this lane's diagonal, pass 1 writes them at the scanned offset
+        int w = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            if (s <= smax && (pass == 0 || cnt))
+                enum_diag(S, P, B, s, [&](int a, int e) {
+                    int len = e - a + 1;
+                    if ((double)len < P.minlen) return;
+                    double sc = run_score(S, P, B, s, a, len);
+                    if (!(sc >= P.minbpscore)) return;
+                    if (pass == 0) { cnt++; return; }
                     if (w < cap) { out[3 * (int64_t)w] = a; out[3 * (int64_t)w + 1] = s - a; out[3 * (int64_t)w + 2] = len; outsc[w] = sc; }
                     w++;
-                }
-            });
+                });
+            if (pass == 0) {
+                int tot, off = team_exscan<TW>(S, cnt, tot);
+                w = base + off;
+                base += tot;
+            }
         }
-        base += tot;
     }
     return base;
 }
 
+// round(x, 3) as CPython computes it when x * 1000 is far from a rounding tie
+// (correctly rounded decimal -> nearest double = k / 1000 with IEEE division);
+// ok = false: the caller must take the exact (host) path.  Same test as
+// pyround3() in sqrn_params.h.
+__device__ __forceinline__ double round3_fast(double x, bool &ok)
+{
+    if (!(fabs(x) < 1e9)) { ok = false; return x; }
+    double y = __dmul_rn(x, 1000.0), k = rint(y);
+    if (!(fabs(__dsub_rn(y, k)) < 0.49)) { ok = false; return x; }
+    return __ddiv_rn(k, 1000.0);
+}
+
 // ------------------------------------------------------------- finalisation
-// ScoreStruct (seq.py:861-899) raw values + dbn of the finished structure.
+// ScoreStruct (seq.py:861-899) + dbn of the finished structure.
 template <int TW>
 __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk, int item)
 {
@@ -849,15 +1166,15 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
     const int N = S.N;
     team_levels<TW>(S);
     int64_t doff = Wk.dbn_off ? Wk.dbn_off[item] : 0;
-    uint8_t flags = 0;
     if (Wk.out_dbn_ascii || Wk.out_dbn_code) {
+        const int64_t so = B.off[Wk.item_seq ? Wk.item_seq[item] : item];
         for (int p = r; p < N; p += T) {
             int pr = S.partner[p];
             int lv = pr < 0 ? 0 : S.stlev[S.owner[p]];
             if (Wk.out_dbn_code) Wk.out_dbn_code[doff + p] = (int8_t)(pr < 0 ? 0 : (p < pr ? (lv > 127 ? 127 : lv) : -(lv > 127 ? 127 : lv)));
             if (Wk.out_dbn_ascii) {
                 uint8_t ch = '.';
-                if (S.code[p] == CODE_SEP) ch = B.sym[B.off[Wk.item_seq ? Wk.item_seq[item] : item] + p];
+                if (S.code[p] == CODE_SEP) ch = B.sym[so + p];
                 else if (pr >= 0) {
                     const char *op = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ", *cl = ")]}>abcdefghijklmnopqrstuvwxyz";
                     ch = lv <= 30 ? (uint8_t)(p < pr ? op[lv - 1] : cl[lv - 1]) : (uint8_t)'?';
@@ -866,17 +1183,24 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
             }
         }
     }
+    // bpsum of every stem in units of 0.5 (GU -0.5, AU 1.5, GC 4.0), one stem per thread
+    for (int t = r; t < S.nst; t += T) {
+        int k2 = 0;
+        for (int q = 0; q < S.stl[t]; q++) {
+            int a = S.code[S.sti[t] + q], b = S.code[S.stj[t] - q];
+            int lo = a < b ? a : b, hi = a < b ? b : a;
+            if (lo == CODE_G && hi == CODE_U) k2 -= 1;
+            else if (lo == CODE_A && hi == CODE_U) k2 += 3;
+            else if (lo == CODE_C && hi == CODE_G) k2 += 8;
+        }
+        S.cc[t] = k2;
+    }
+    Team<TW>::sync();
     if (r == 0) {
+        uint8_t flags = 0;
         double thescore = 0.0; bool any = false; int maxlev = 0;
-        for (int t = 0; t < S.nst; t++) {
-            int k2 = 0;                                  // bpsum in units of 0.5 (GU -0.5, AU 1.5, GC 4.0)
-            for (int q = 0; q < S.stl[t]; q++) {
-                int a = S.code[S.sti[t] + q], b = S.code[S.stj[t] - q];
-                int lo = a < b ? a : b, hi = a < b ? b : a;
-                if (lo == CODE_G && hi == CODE_U) k2 -= 1;
-                else if (lo == CODE_A && hi == CODE_U) k2 += 3;
-                else if (lo == CODE_C && hi == CODE_G) k2 += 8;
-            }
+        for (int t = 0; t < S.nst; t++) {                // summed in selection order (seq.py:884)
+            int k2 = S.cc[t];
             if (k2 > 0) {
                 double pw = (k2 < P.pw17_n) ? __ldg(&P.pw17_lut[k2]) : pow(0.5 * k2, 1.7);
                 thescore = __dadd_rn(thescore, pw); any = true;
@@ -884,8 +1208,8 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
             if (S.stlev[t] > maxlev) maxlev = S.stlev[t];
         }
         double reactscore = 0.5;
-        int nsep = S.sepcnt[N];
         if (S.has_react && !S.default_reacts) {
+            int nsep = S.has_sep ? S.sepcnt[N] : 0;
             // builtin sum(): plain left-to-right for numpy floats, Neumaier for exact Python floats
             double sum = 0.0, comp = 0.0; bool first = true;
             for (int p = 0; p < N; p++) {
@@ -901,11 +1225,17 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
             if (B.react_comp && comp != 0.0 && isfinite(comp)) sum = __dadd_rn(sum, comp);
             reactscore = __dsub_rn(1.0, __ddiv_rn(sum, (double)(N - nsep)));
         }
-        if (!any) flags |= 1;
-        if (maxlev > 30) flags |= 2;
-        Wk.out_raw[3 * (int64_t)item] = __dmul_rn(thescore, reactscore);   // seq.py:899, before round()
-        Wk.out_raw[3 * (int64_t)item + 1] = thescore;
-        Wk.out_raw[3 * (int64_t)item + 2] = reactscore;
+        if (!any) flags |= FLAG_INT0;
+        if (maxlev > 30) flags |= FLAG_LEVELS;
+        double v0 = __dmul_rn(thescore, reactscore), v1 = thescore, v2 = reactscore;   // seq.py:899, before round()
+        if (Wk.round3) {
+            bool ok = true;
+            double q0 = round3_fast(v0, ok), q1 = round3_fast(v1, ok), q2 = round3_fast(v2, ok);
+            if (ok) { v0 = q0; v1 = q1; v2 = q2; } else flags |= FLAG_ROUND;    // raw values stay: host rounds them
+        }
+        Wk.out_raw[3 * (int64_t)item] = v0;
+        Wk.out_raw[3 * (int64_t)item + 1] = v1;
+        Wk.out_raw[3 * (int64_t)item + 2] = v2;
         Wk.out_nstems[item] = S.nst;
         if (Wk.out_flags) Wk.out_flags[item] = flags;
     }
@@ -926,17 +1256,21 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
 {
     const int r = Team<TW>::rank();
     const int seq = Wk.item_seq ? Wk.item_seq[item] : item;
+    S.region_mode = Wk.region_mode;
     team_load<TW>(S, B, P, seq);
-    if (Wk.init_off)
-        for (int64_t k = Wk.init_off[item]; k < Wk.init_off[item + 1]; k++)
-            team_apply_stem<TW>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2]);
+    if (Wk.init_off) {
+        const int64_t k0 = Wk.init_off[item], k1 = Wk.init_off[item + 1];
+        for (int64_t k = k0; k < k1; k++)
+            team_apply_stem<TW>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2], false);
+        if (k1 > k0) team_unpaired_prefix<TW>(S);
+    }
     unsigned long long calls = 0;
     if (Wk.mode == MODE_TAIL || Wk.mode == MODE_FINAL) {
         // the pool loop of seq.py:1159-1199 once it can no longer branch
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
         while (Wk.mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<TW>(S);
-            Best b = team_scan<TW>(S, P, B, L);
+            Best b = team_scan<TW>(S, P, B, L, false);
             calls++;
             if (b.fin <= -1e300) break;
             int i = (int)(b.key & 0xffff);
@@ -948,7 +1282,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
         if ((double)S.nst != P.maxstemnum) {
             team_levels<TW>(S);
-            Best b = team_scan<TW>(S, P, B, L);
+            Best b = team_scan<TW>(S, P, B, L, true);
             calls++;
             n = team_choose<TW>(S, L, b, Wk.item_subopt[item], Wk.out_stems + 3 * so,
                                 Wk.out_stemfin ? Wk.out_stemfin + so : nullptr, (int)cap);

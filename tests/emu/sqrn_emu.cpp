@@ -19,7 +19,7 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
                        const int32_t *init_stems, const double *item_subopt,
                        const int64_t *out_off, int32_t *out_stems, int32_t *out_nstems, double *out_stemfin,
                        double *out_raw, uint8_t *out_flags, const int64_t *dbn_off, uint8_t *dbn_ascii,
-                       int8_t *dbn_code, int ccap, unsigned long long *n_calls)
+                       int8_t *dbn_code, int ccap, unsigned long long *n_calls, int region_mode)
 {
     int nmax = 1, rbmax = 0;
     for (int64_t b = 0; b < n_seqs; b++) {
@@ -45,7 +45,7 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     W.n_items = n_items; W.mode = mode; W.item_seq = item_seq; W.init_off = init_off; W.init_stems = init_stems;
     W.item_subopt = item_subopt; W.out_off = out_off; W.out_stems = out_stems; W.out_nstems = out_nstems;
     W.out_stemfin = out_stemfin; W.out_raw = out_raw; W.out_flags = out_flags; W.dbn_off = dbn_off;
-    W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls;
+    W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls; W.region_mode = region_mode;
     Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0);
     unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
     for (int item = 0; item < n_items; item++) {

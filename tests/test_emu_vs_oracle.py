@@ -30,12 +30,14 @@ def _prep_batch(cases):
     return preps, kw
 
 
+@pytest.mark.parametrize("region", [0, 1, 2], ids=["auto", "scan", "stems"])
 @pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
                          ids=["fastest", "defG1", "defG2-smalllist", "ali"])
-def test_tail_plain(ps, ccap):
-    """single-path greedy (pl=1) on plain sequences: stems, dbn, raw scores"""
+def test_tail_plain(ps, ccap, region):
+    """single-path greedy (pl=1) on plain sequences: stems, dbn, raw scores; the ScoreStems region
+    evaluated by the reference's position scan, by the stem walk, and by the automatic choice"""
     seqs = T.rand_seqs(31, 150, 5, 210)
-    r = emu.run(ps, seqs, ccap=ccap)
+    r = emu.run(ps, seqs, ccap=ccap, region_mode=region)
     for b, s in enumerate(seqs):
         _, structs, _ = O.predict_short(s, [0.5] * len(s), "." * len(s), [ps], poollim=1)
         dbn, sc, isint, _, stems, _, _ = structs[0]
@@ -46,8 +48,9 @@ def test_tail_plain(ps, ccap):
         assert bool(r["flags"][b] & 1) == isint
 
 
+@pytest.mark.parametrize("region", [1, 2], ids=["scan", "stems"])
 @pytest.mark.parametrize("interchain", [False, True])
-def test_tail_with_restraints_and_reactivities(interchain):
+def test_tail_with_restraints_and_reactivities(interchain, region):
     rng = random.Random(32)
     cases = [T.rand_case(rng, 8, 150, p_gap=0.2) for _ in range(200)]
     preps, kw = _prep_batch(cases)
@@ -55,7 +58,8 @@ def test_tail_with_restraints_and_reactivities(interchain):
         idx = [k for k, p in enumerate(preps) if p.compensated == comp]
         sub = {k: [v[i] for i in idx] if isinstance(v, list) else v for k, v in kw.items()}
         for ps in (T.DEFG1, T.FASTEST):
-            r = emu.run(ps, [preps[k].shortseq for k in idx], react_comp=comp, interchainonly=interchain, **sub)
+            r = emu.run(ps, [preps[k].shortseq for k in idx], react_comp=comp, interchainonly=interchain,
+                            region_mode=region, **sub)
             for b, k in enumerate(idx):
                 p = preps[k]
                 _, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, [ps], interchainonly=interchain,
@@ -123,3 +127,32 @@ def test_per_stem_levels_equal_per_pair_levels():
         want = O.pair_levels(pairs)
         for (v, w), lev in want.items():
             assert codes[v] == lev and codes[w] == -lev, (stems, v, w)
+
+
+@pytest.mark.parametrize("region", [1, 2], ids=["scan", "stems"])
+def test_step_on_random_pseudoknotted_structures(region):
+    """ScoreStems on top of arbitrary (pseudoknotted, multi-level) partial structures: the stem walk
+    and the position scan must both reproduce the oracle's ChooseStems list and scores"""
+    rng = random.Random(35)
+    for ps, subopt in ((T.DEFG1, 0.3), (T.DEFG2, 0.5), (T.FASTEST, 0.2)):
+        for _ in range(60):
+            n = rng.randint(40, 180)
+            seq = T.rand_seq(rng, n, "ACGU" if rng.random() < 0.8 else "ACGU;")
+            used, stems = set(), []
+            for _ in range(rng.randint(1, 12)):
+                i, j, ln = rng.randrange(n), rng.randrange(n), rng.randint(1, 6)
+                if i > j:
+                    i, j = j, i
+                if j - i < 2 * ln + 2:
+                    continue
+                pos = set(range(i, i + ln)) | set(range(j - ln + 1, j + 1))
+                if pos & used or any(seq[p] == ";" for p in pos):
+                    continue
+                used |= pos
+                stems.append((i, j, ln))
+            _, chosen = O.optimal(seq, ps, subopt, selected=stems)
+            r = emu.run(ps, [seq], mode=emu.MODE_STEP, init_stems=[stems], item_subopt=[subopt], ccap=4096,
+                        stem_cap=512, region_mode=region)
+            k = r["n"][0]
+            got = [(int(r["stems"][q][0]), int(r["stems"][q][1]), int(r["stems"][q][2]), float(r["fin"][q])) for q in range(k)]
+            assert got == chosen, (seq, stems)
