@@ -146,6 +146,7 @@ SQRN_API int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
  * candidate (SQRNdbnseq.py:665-689): 0 automatic, 1 the reference's position scan, 2 the walk over
  * the selected stems.  All settings give identical results; tests force each one.             */
 #define SQRN_TUNE_REGION 1
+#define SQRN_TUNE_NO_FAST_KERNEL 2   /* 1: the fast lane uses the general kernel instead of the specialised one */
 SQRN_API int  sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value);
 
 /* The full "G" path for a batch: replaces SQRNdbnseq.py:1048-1246 (algos == {"G"},

@@ -143,6 +143,10 @@ class Context:
         """0 automatic, 1 position scan, 2 stem walk (identical results; see include/sqrn.h)"""
         self._check(self.L.sqrn_ctx_set_tuning(self.h, 1, int(mode)))
 
+    def set_no_fast_kernel(self, flag):
+        """route sqrn_fast_predict_* through the general kernel (tests compare both)"""
+        self._check(self.L.sqrn_ctx_set_tuning(self.h, 2, int(bool(flag))))
+
     def stats(self):
         nl, ms, nc = C.c_int64(0), C.c_double(0), C.c_int64(0)
         self.L.sqrn_ctx_last_stats(self.h, C.byref(nl), C.byref(ms), C.byref(nc))

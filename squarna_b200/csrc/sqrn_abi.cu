@@ -7,6 +7,7 @@
 // hand back caller-owned buffers.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -17,11 +18,11 @@ using namespace sqrn;
 // ------------------------------------------------------------------ kernel
 // Persistent teams pull work items from a global counter (length-sorted by the
 // host, longest first), so a batch of mixed lengths keeps every SM busy.
-template <int TW>
-__global__ void __launch_bounds__(TW == 1 ? 256 : TW * 32, TW == 1 ? 4 : 1)
-k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
+template <class C>
+__device__ __forceinline__ void work_loop(const DevParams *__restrict__ Pg, const DevBatch &B, const DevWork &Wk,
+                                          const Layout &L, unsigned char *smem)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int TW = C::TW;
     __shared__ DevParams Psh;
     {
         const int *src = reinterpret_cast<const int *>(Pg);
@@ -44,8 +45,31 @@ k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
         }
         if (item >= Wk.n_items) break;
         item = Wk.order ? Wk.order[item] : item + Wk.item_base;
-        team_run_item<TW>(S, Psh, B, Wk, L, item);
+        team_run_item<C>(S, Psh, B, Wk, L, item);
     }
+}
+
+// general flavour: any batch, any mode, shared-memory layout chosen per launch
+template <int TW>
+__global__ void __launch_bounds__(TW == 1 ? 256 : TW * 32, TW == 1 ? 3 : 1)
+k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    work_loop<Cfg<TW>>(Pg, B, Wk, L, smem);
+}
+
+// Fast lane (`byseq pl=1` shape): one warp per sequence, plain sequences (no reactivities,
+// restraints, alignment weights), the standard {GC, AU, GU} pairing table, single-path greedy to
+// completion.  The shared-memory layout is a compile-time constant, so every array address is
+// "team base + immediate" and the code stays small enough for the instruction cache.
+constexpr int FAST_TEAMS = 8, FAST_CCAP = 128, FAST_RCAP = 256;
+template <int NCAP>
+__global__ void __launch_bounds__(32 * FAST_TEAMS, 4)
+k_fast(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr Layout L = make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, 0, 0, NCAP / 4 + 2);
+    work_loop<Cfg<1, true, true, MODE_TAIL>>(Pg, B, Wk, L, smem);
 }
 
 // ----------------------------------------------------------------- context
@@ -64,7 +88,7 @@ struct DBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-constexpr int FAST_MAX_CHUNKS = 8;
+constexpr int FAST_MAX_CHUNKS = 16;
 
 struct PEntry {
     sqrn_paramset ps; int nmax; DevParams hp; DevParams *d_p; double *d_lut;
@@ -102,6 +126,7 @@ struct sqrn_ctx {
     DBuf buf[NBUF];
     int64_t n_launches = 0, n_calls = 0; double kernel_ms = 0.0;
     int region_mode = REGION_AUTO;
+    int no_fast_kernel = 0;      // tuning knob: route the fast lane through the general kernel
     CachedResult cres; CachedStems cstems;
 };
 
@@ -190,6 +215,7 @@ extern "C" int sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value)
 {
     if (!ctx) return SQRN_E_BADARG;
     if (what == SQRN_TUNE_REGION && value >= 0 && value <= 2) { ctx->region_mode = value; return SQRN_OK; }
+    if (what == SQRN_TUNE_NO_FAST_KERNEL) { ctx->no_fast_kernel = value != 0; return SQRN_OK; }
     ctx->err = "unknown tuning knob";
     return SQRN_E_BADARG;
 }
@@ -224,7 +250,7 @@ static int get_params(sqrn_ctx *ctx, const sqrn_paramset &ps, int nmax, const PE
 }
 
 // ------------------------------------------------------------- launch plan
-struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; };
+struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -272,6 +298,33 @@ static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int mi
     if ((size_t)pl.L.total > budget) { ctx->err = "sequence too long for one CTA's shared memory"; return SQRN_E_UNSUPPORTED; }
     pl.tpc = 1; pl.threads = 32 * pl.tw; pl.smem = pl.L.total;
     return pl.tw == 8 ? plan_for<8>(ctx, pl) : plan_for<32>(ctx, pl);
+}
+
+// the compile-time-layout fast kernel, when the parameter set and the lengths allow it
+template <int NCAP>
+static int plan_fast(sqrn_ctx *ctx, Plan &pl)
+{
+    constexpr Layout L = make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, 0, 0, NCAP / 4 + 2);
+    pl.tw = 1; pl.tpc = FAST_TEAMS; pl.threads = 32 * FAST_TEAMS; pl.L = L; pl.smem = (size_t)FAST_TEAMS * L.total;
+    pl.fast_ncap = NCAP;
+    CK(cudaFuncSetAttribute(k_fast<NCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fast<NCAP>, pl.threads, pl.smem));
+    if (nb < 1) { ctx->err = "kernel does not fit on an SM"; return SQRN_E_UNSUPPORTED; }
+    pl.grid = nb * ctx->sm_count;
+    return SQRN_OK;
+}
+
+static bool fast_eligible(const PEntry &P, int nmax) { return P.hp.std_pairs && P.hp.m >= 2 && nmax <= 320; }
+
+static int make_fast_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, Plan &pl)
+{
+    if (fast_eligible(P, nmax) && !ctx->no_fast_kernel) {
+        if (nmax <= 128) return plan_fast<128>(ctx, pl);
+        if (nmax <= 224) return plan_fast<224>(ctx, pl);
+        return plan_fast<320>(ctx, pl);
+    }
+    return make_plan(ctx, P, nmax, 0, 0, false, false, 0, pl);
 }
 
 static int launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, const DevBatch &B, DevWork &W)
@@ -325,7 +378,10 @@ static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStrea
     int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
     if (grid > teams) grid = std::max(teams, 1);
     if (e0) CK(cudaEventRecord(e0, st));
-    if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
+    if (pl.fast_ncap == 128) k_fast<128><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
+    else if (pl.fast_ncap == 224) k_fast<224><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
+    else if (pl.fast_ncap == 320) k_fast<320><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
+    else if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
     else if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
     else k_work<32><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
     CK(cudaGetLastError());
@@ -345,7 +401,7 @@ extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, 
     const PEntry *P;
     TRY(get_params(ctx, *ps, max_len, &P));
     Plan pl;
-    TRY(make_plan(ctx, *P, max_len, 0, 0, false, false, 0, pl));
+    TRY(make_fast_plan(ctx, *P, max_len, pl));
     int *d_counter; uint8_t *d_flags; unsigned long long *d_nc;
     TRY(dalloc(ctx, W_COUNTER, FAST_MAX_CHUNKS, &d_counter));
     TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &d_flags));
@@ -368,6 +424,9 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     cudaSetDevice(ctx->device);
     ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
     if (n_seqs == 0) return SQRN_OK;
+    const bool trace = getenv("SQRN_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_0 = now();
     const int64_t total = offsets[n_seqs];
     int max_len = 0;
     for (int64_t b = 0; b < n_seqs; b++) {
@@ -378,7 +437,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     const PEntry *P;
     TRY(get_params(ctx, *ps, max_len, &P));
     Plan pl;
-    TRY(make_plan(ctx, *P, max_len, 0, 0, false, false, 0, pl));
+    TRY(make_fast_plan(ctx, *P, max_len, pl));
     int64_t *d_off; uint8_t *d_sym, *d_dbn, *d_flags; double *d_sc; int32_t *d_ns; int *d_counter; unsigned long long *d_nc;
     TRY(dalloc(ctx, B_OFF, (size_t)n_seqs + 1, &d_off));
     TRY(dalloc(ctx, B_SYM, (size_t)std::max<int64_t>(total, 1), &d_sym));
@@ -394,8 +453,10 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         CK(cudaMallocHost(&ctx->hflags, (size_t)n_seqs + 64));
         ctx->hflags_cap = (size_t)n_seqs + 64;
     }
+    const double t_1 = now();
     // chunks of at least 64 Ki sequences, at most FAST_MAX_CHUNKS
     int nchunks = (int)std::min<int64_t>(FAST_MAX_CHUNKS, std::max<int64_t>(1, n_seqs / 65536));
+    if (const char *e = getenv("SQRN_FAST_CHUNKS")) nchunks = std::max(1, std::min(FAST_MAX_CHUNKS, atoi(e)));
     cudaStream_t s_main = ctx->stream;
     CK(cudaMemsetAsync(d_counter, 0, FAST_MAX_CHUNKS * sizeof(int), s_main));
     CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), s_main));
@@ -422,11 +483,13 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         if (n_stems) CK(cudaMemcpyAsync(n_stems + b0, d_ns + b0, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
         CK(cudaMemcpyAsync(ctx->hflags + b0, d_flags + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_out));
     }
+    const double t_2 = now();
     CK(cudaEventRecord(ctx->ev_out, ctx->s_out));
     CK(cudaEventRecord(ctx->ev_k2done, ctx->s_k2));
     CK(cudaStreamWaitEvent(s_main, ctx->ev_out, 0));          // later work on the context's stream sees the results
     CK(cudaStreamWaitEvent(s_main, ctx->ev_k2done, 0));
     CK(cudaStreamSynchronize(s_main));
+    const double t_3 = now();
     for (int c = 0; c < nchunks; c++) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev_k0[c], ctx->ev_k1[c]) == cudaSuccess) ctx->kernel_ms += ms;
@@ -447,6 +510,8 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         if (fl[b] & FLAG_LEVELS) { ctx->err = "more than 30 pseudoknot levels: use sqrn_predict_batch"; return SQRN_E_UNSUPPORTED; }
         b++;
     }
+    if (trace) fprintf(stderr, "[sqrn] fast_predict_host: prepare %.2f ms, enqueue %.2f ms, wait %.2f ms, finish %.2f ms\n",
+                       t_1 - t_0, t_2 - t_1, t_3 - t_2, now() - t_3);
     return SQRN_OK;
 }
 

@@ -81,6 +81,7 @@ constexpr int FLAG_ROUND = 8;      // device round(x, 3) was too close to a tie:
 // ---------------------------------------------------------------- parameters
 struct DevParams {
     int      K, npc;
+    int      std_pairs;             // the pairing table is exactly {GC, AU, GU} over ACGU
     int      pc_code[MAXPC];        // symbol code of pairing slot c
     uint32_t pairmask[MAXK];        // bit d: code pairs with code d
     double   weight[MAXK * MAXK];
@@ -132,21 +133,21 @@ struct DevWork {
 
 // -------------------------------------------------------------- smem layout
 struct Layout {
-    int Ncap, W, WR, Scap, RBcap, Rcap, Ccap, npc;
+    int Ncap, W, WR, Scap, RBcap, Rcap, Ccap, Ocap, npc;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
         o_sti, o_stj, o_stl, o_stlev, o_ssi, o_ssj, o_ssl, o_sslev, o_byi, o_cc, o_perm, o_grp, o_gsz,
         o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_misc, total;
 };
 
-__host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+__host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 // extras = the batch carries reactivities (rcode array needed); with_fin = the
 // mode keeps the adjusted score of every survivor (MODE_STEP)
 // scap = most stems one structure can hold (0: the N/2 + 1 upper bound)
-__host__ __device__ inline Layout make_layout(int Nmax, int RBmax, int Ccap, int npc, int tw, int Rcap = 0,
+__host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, int npc, int tw, int Rcap = 0,
                                               int extras = 1, int with_fin = 1, int scap = 0)
 {
-    Layout L;
+    Layout L{};
     L.Ncap = align_up(Nmax > 0 ? Nmax : 1, 32);
     L.W = L.Ncap / 32;
     L.WR = L.W + 3;
@@ -172,6 +173,7 @@ __host__ __device__ inline Layout make_layout(int Nmax, int RBmax, int Ccap, int
     int lev_bytes = 4 * L.Scap + 4 * L.Scap + 2 * L.Scap + 2 * L.Scap;
     int run_bytes = 4 * L.Rcap + 2 * L.Rcap;
     int uni = align_up(lev_bytes > run_bytes ? lev_bytes : run_bytes, 4);
+    L.Ocap = uni / 2;                                     // int16 entries team_choose can rank in this space
     L.o_rkey = o;    L.o_rlen = o + 4 * L.Rcap;
     L.o_cc = o;      L.o_gsz = o + 4 * L.Scap;  L.o_perm = o + 8 * L.Scap;  L.o_grp = o + 10 * L.Scap;
     o += uni;
@@ -253,6 +255,18 @@ template <> struct Team<0> {
 };
 #endif
 
+// Compile-time flavour of the work kernel.
+//   PLAIN: the batch has no reactivities, restraints, alignment weights or interchainonly flag
+//          (the `byseq` fast lane): all of that code is compiled out;
+//   STDP:  the pairing table is exactly {GC, AU, GU} over ACGU: pairability comes from the two
+//          bit planes of the 2-bit base codes, x = (b0 ^ r0) & (b1 | r1);
+//   MODE:  a fixed MODE_* or -1 (taken from DevWork at run time).
+template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1>
+struct Cfg {
+    static constexpr int TW = TW_, MODE = MODE_;
+    static constexpr bool PLAIN = PLAIN_, STDP = STDP_;
+};
+
 struct State {
     int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts, region_mode;
     uint8_t  *code, *rcl, *stlev, *sslev;
@@ -302,12 +316,14 @@ __device__ __forceinline__ void team_mask(uint32_t *dst, int nwords, F &&pred)
 #ifdef SQRN_HOST_EMU
     for (int k = 0; k < nwords; k++) {
         uint32_t m = 0;
+        #pragma unroll 1
         for (int b = 0; b < 32; b++) if (pred(32 * k + b)) m |= 1u << b;
         dst[k] = m;
     }
 #else
     const int lane = threadIdx.x & 31;
     const int w0 = (TW == 1) ? 0 : (int)(threadIdx.x >> 5), nw = (TW == 1) ? 1 : TW;
+    #pragma unroll 1
     for (int k = w0; k < nwords; k += nw) {
         uint32_t m = __ballot_sync(0xffffffffu, pred(32 * k + lane));
         if (lane == 0) dst[k] = m;
@@ -334,6 +350,7 @@ __device__ __forceinline__ int team_exscan(State &S, int v, int &total)
     if (lane == 31) sc[w] = wtot;
     __syncthreads();
     int base = 0, tot = 0;
+    #pragma unroll 1
     for (int q = 0; q < TW; q++) { int t = sc[q]; if (q < w) base += t; tot += t; }
     __syncthreads();
     total = tot;
@@ -357,11 +374,13 @@ __device__ __forceinline__ int unpaired_before(const State &S, int p)
 }
 
 // word prefix of the unpaired mask (after Ub changed)
-template <int TW>
+template <class C>
 __device__ void team_unpaired_prefix(State &S)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     int carry = 0;
+    #pragma unroll 1
     for (int k0 = 0; k0 < S.W; k0 += T) {
         int k = k0 + r, v = (k < S.W) ? __popc(S.Ub[k]) : 0, tot;
         int ex = team_exscan<TW>(S, v, tot);
@@ -373,52 +392,62 @@ __device__ void team_unpaired_prefix(State &S)
 }
 
 // ------------------------------------------------------------- load a sequence
-template <int TW>
+template <class C>
 __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int seq)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int64_t o = B.off[seq];
     const int N = (int)(B.off[seq + 1] - o);
     S.N = N; S.nst = 0;
-    S.has_react = B.rcode != nullptr;
-    S.has_smat = B.smat != nullptr;
-    S.cols = B.cols ? B.cols + o : nullptr;
+    S.has_react = !C::PLAIN && B.rcode != nullptr;
+    S.has_smat = !C::PLAIN && B.smat != nullptr;
+    S.cols = (!C::PLAIN && B.cols) ? B.cols + o : nullptr;
     const int Nw = S.W * 32;
     bool sep = false, nondef = false;
+    #pragma unroll 1
     for (int p = r; p < Nw; p += T) {
         uint8_t c = CODE_OTHER, cl = 0;
         if (p < N) {
             c = P.code_table[B.sym[o + p]];
-            if (B.rcode) { uint16_t rc = B.rcode[o + p]; S.rcode[p] = rc; if (__ldg(&B.rvals[rc]) != 0.5) nondef = true; }
-            if (B.rclass) cl = B.rclass[o + p] & 7;
+            if (!C::PLAIN) {
+                if (B.rcode) { uint16_t rc = B.rcode[o + p]; S.rcode[p] = rc; if (__ldg(&B.rvals[rc]) != 0.5) nondef = true; }
+                if (B.rclass) cl = B.rclass[o + p] & 7;
+            }
             if (c == CODE_SEP) sep = true;
-        } else if (B.rcode) S.rcode[p] = 0;
-        S.code[p] = c; S.rcl[p] = cl;
-        S.partner[p] = -1; S.owner[p] = -1;
+        } else if (!C::PLAIN && B.rcode) S.rcode[p] = 0;
+        S.code[p] = c;
+        if (!C::PLAIN) S.rcl[p] = cl;
+        S.partner[p] = -1;
+        if (!C::PLAIN) S.owner[p] = -1;
     }
     S.has_sep = Team<TW>::any(sep);
     // "default reacts" switch, seq.py:273: every processed reactivity == 0.5
-    S.default_reacts = !Team<TW>::any(nondef);
-    Team<TW>::sync();
-    // restraint pairs (sorted by (v+w, v) by the host); mark their positions
+    S.default_reacts = C::PLAIN ? 1 : !Team<TW>::any(nondef);
+    S.nrb = 0;
     int nrb_all = 0;
     const int32_t *rb = nullptr;
-    if (B.rbp_off) { nrb_all = (int)(B.rbp_off[seq + 1] - B.rbp_off[seq]); rb = B.rbp + 2 * B.rbp_off[seq]; }
-    for (int k = r; k < nrb_all; k += T) {
-        S.rcl[rb[2 * k]] |= RC_RBPOS;       // distinct positions: no write conflicts on the same byte
-        S.rcl[rb[2 * k + 1]] |= RC_RBPOS;
+    if (!C::PLAIN) {
+        // restraint pairs (sorted by (v+w, v) by the host); mark their positions
+        if (B.rbp_off) { nrb_all = (int)(B.rbp_off[seq + 1] - B.rbp_off[seq]); rb = B.rbp + 2 * B.rbp_off[seq]; }
+        #pragma unroll 1
+        for (int k = r; k < nrb_all; k += T) {
+            S.rcl[rb[2 * k]] |= RC_RBPOS;       // distinct positions: no write conflicts on the same byte
+            S.rcl[rb[2 * k + 1]] |= RC_RBPOS;
+        }
     }
-    S.nrb = 0;
     if (S.has_sep || nrb_all) {
         if (r == 0) {
             // prefix count of separators (rare: only multi-chain inputs)
             if (S.has_sep) {
                 int c = 0;
+                #pragma unroll 1
                 for (int p = 0; p < N; p++) { S.sepcnt[p] = (int16_t)c; if (S.code[p] == CODE_SEP) c++; }
                 S.sepcnt[N] = (int16_t)c;
             }
             // statically valid restraint cells: boolmat[v,w] != 0 (seq.py:443) and on a walked diagonal
             int n = 0;
+            #pragma unroll 1
             for (int k = 0; k < nrb_all; k++) {
                 int v = rb[2 * k], w = rb[2 * k + 1], s = v + w;
                 if (s < 4 || s > 2 * N - 6) continue;
@@ -436,17 +465,34 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
         S.nrb = S.misc[3];
     }
     Team<TW>::sync();
-    // forward masks of each pairing symbol, reversed masks of its partners (bit q of the
-    // reversed arrays is position j = N - 1 - (q - 32))
-    for (int c = 0; c < P.npc; c++) {
-        const int code = P.pc_code[c];
-        const uint32_t pm = P.pairmask[code];
-        team_mask<TW>(S.M + c * S.W, S.W, [&](int p) { return p < N && S.code[p] == code; });
-        team_mask<TW>(S.PR + c * S.WR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && (pm >> S.code[j] & 1); });
+    // bit q of the reversed arrays is position j = N - 1 - (q - 32)
+    if (C::STDP) {
+        // the two bit planes of the 2-bit base codes, forward and reversed; positions that hold
+        // no base (separators, other symbols) are excluded through rowok / colokR
+        team_mask<TW>(S.M, S.W, [&](int p) { return (S.code[p] & 1) != 0; });
+        team_mask<TW>(S.M + S.W, S.W, [&](int p) { return (S.code[p] & 2) != 0; });
+        team_mask<TW>(S.PR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && (S.code[j] & 1); });
+        team_mask<TW>(S.PR + S.WR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && (S.code[j] & 2); });
+    } else {
+        // forward masks of each pairing symbol, reversed masks of its partners
+        #pragma unroll 1
+        for (int c = 0; c < P.npc; c++) {
+            const int code = P.pc_code[c];
+            const uint32_t pm = P.pairmask[code];
+            team_mask<TW>(S.M + c * S.W, S.W, [&](int p) { return p < N && S.code[p] == code; });
+            team_mask<TW>(S.PR + c * S.WR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && (pm >> S.code[j] & 1); });
+        }
     }
-    team_mask<TW>(S.rowok, S.W, [&](int p) { return p < N && !(S.rcl[p] & (RC_X | RC_NORIGHT | RC_RBPOS)); });
-    team_mask<TW>(S.colokR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && !(S.rcl[j] & (RC_X | RC_NOLEFT | RC_RBPOS)); });
+    const int cmax = C::STDP ? 4 : MAXK;          // codes that hold a base
+    if (C::PLAIN) {
+        team_mask<TW>(S.rowok, S.W, [&](int p) { return p < N && S.code[p] < cmax; });
+        team_mask<TW>(S.colokR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && S.code[j] < cmax; });
+    } else {
+        team_mask<TW>(S.rowok, S.W, [&](int p) { return p < N && S.code[p] < cmax && !(S.rcl[p] & (RC_X | RC_NORIGHT | RC_RBPOS)); });
+        team_mask<TW>(S.colokR, S.WR, [&](int q) { int j = N - 1 - (q - 32); return j >= 0 && j < N && S.code[j] < cmax && !(S.rcl[j] & (RC_X | RC_NOLEFT | RC_RBPOS)); });
+    }
     team_mask<TW>(S.Ub, S.W, [&](int p) { return p < N; });
+    #pragma unroll 1
     for (int k = r; k <= S.W; k += T) S.Ubase[k] = (32 * k < N) ? 32 * k : N;
     Team<TW>::sync();
 }
@@ -454,11 +500,13 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
 // add a selected stem to the structure: partners, owner, row/column masks
 // (AnnotateStems zeroes the rows and columns of every selected position, seq.py:446-451),
 // the unpaired mask and the 5'-sorted copy of the stem list
-template <int TW>
+template <class C>
 __device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = true)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int idx = S.nst;
+    #pragma unroll 1
     for (int k = r; k < len; k += T) {
         int v = i + k, w = j - k;
         S.partner[v] = (int16_t)w; S.partner[w] = (int16_t)v;
@@ -473,8 +521,10 @@ __device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = 
     }
     // insert into the 5'-sorted order: entries with a larger i move up by one
     int pos = 0;
+    #pragma unroll 1
     for (int q = 0; q < idx; q++) pos += (S.sti[S.byi[q]] < i);       // idx is small; every thread counts
     Team<TW>::sync();
+    #pragma unroll 1
     for (int q0 = 0; q0 < idx; q0 += T) {            // shift in chunks from the top so reads precede overwrites
         int q = idx - 1 - q0 - r;
         int16_t v = 0; bool mv = q >= pos && q >= 0;
@@ -486,7 +536,7 @@ __device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = 
     if (r == 0) { S.sti[idx] = (int16_t)i; S.stj[idx] = (int16_t)j; S.stl[idx] = (int16_t)len; S.byi[pos] = (int16_t)idx; }
     S.nst = idx + 1;
     Team<TW>::sync();
-    if (refresh) team_unpaired_prefix<TW>(S);
+    if (refresh) team_unpaired_prefix<C>(S);
 }
 
 // ------------------------------------------------ pseudoknot levels per stem
@@ -502,15 +552,18 @@ __device__ __forceinline__ bool stems_cross(int i, int j, int k, int l)
     return (i < k && k < j && j < l) || (k < i && i < l && l < j);
 }
 
-template <int TW>
+template <class C>
 __device__ int team_levels(State &S)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int n = S.nst;
     if (n == 0) return 0;
     bool crossing = false;
+    #pragma unroll 1
     for (int t = r; t < n; t += T) {
         int i = S.sti[t], j = S.stj[t], c = 0;
+        #pragma unroll 1
         for (int u = 0; u < n; u++)
             if (u != t && stems_cross(i, j, S.sti[u], S.stj[u])) c += S.stl[u];
         S.cc[t] = c;
@@ -520,12 +573,15 @@ __device__ int team_levels(State &S)
     int ng = 1;
     if (!crossing) {
         // nothing crosses: one group, every stem on level 1
+        #pragma unroll 1
         for (int t = r; t < n; t += T) S.stlev[t] = 1;
         Team<TW>::sync();
     } else {
         Team<TW>::sync();
+        #pragma unroll 1
         for (int t = r; t < n; t += T) {
             int c = S.cc[t], i = S.sti[t], rank = 0;
+            #pragma unroll 1
             for (int u = 0; u < n; u++) {
                 int cu = S.cc[u];
                 if (cu < c || (cu == c && S.sti[u] < i)) rank++;
@@ -535,6 +591,7 @@ __device__ int team_levels(State &S)
         Team<TW>::sync();
         if (r == 0) {
             ng = 0;
+            #pragma unroll 1
             for (int a = 0; a < n; a++) {
                 int t = S.perm[a], g = -1;
                 if (S.cc[t] == 0) {
@@ -542,8 +599,10 @@ __device__ int team_levels(State &S)
                     if (ng == 0) { ng = 1; S.gsz[0] = 0; }
                 } else {
                     int i = S.sti[t], j = S.stj[t];
+                    #pragma unroll 1
                     for (int h = 0; h < ng && g < 0; h++) {
                         bool clash = false;
+                        #pragma unroll 1
                         for (int b = 0; b < a && !clash; b++) {
                             int u = S.perm[b];
                             if (S.grp[u] == h && stems_cross(i, j, S.sti[u], S.stj[u])) clash = true;
@@ -556,8 +615,10 @@ __device__ int team_levels(State &S)
                 S.gsz[g] += S.stl[t];
             }
             // groups.sort(key=len, reverse=True) is stable: level = 1 + #groups that come first
+            #pragma unroll 1
             for (int t = 0; t < n; t++) {
                 int g = S.grp[t], sz = S.gsz[g], lev = 1;
+                #pragma unroll 1
                 for (int h = 0; h < ng; h++)
                     if (S.gsz[h] > sz || (S.gsz[h] == sz && h < g)) lev++;
                 S.stlev[t] = (uint8_t)(lev > 255 ? 255 : lev);
@@ -567,6 +628,7 @@ __device__ int team_levels(State &S)
         Team<TW>::sync();
         ng = S.misc[5];
     }
+    #pragma unroll 1
     for (int q = r; q < n; q += T) {
         int t = S.byi[q];
         S.ssi[q] = S.sti[t]; S.ssj[q] = S.stj[t]; S.ssl[q] = S.stl[t]; S.sslev[q] = S.stlev[t];
@@ -598,12 +660,15 @@ __device__ __forceinline__ double cell_score(const State &S, const DevParams &P,
 }
 
 // raw bp score of the run (a .. a+len-1) on diagonal s: Python sum(), left to right from 0 (seq.py:416)
+template <class C>
 __device__ __forceinline__ double run_score(const State &S, const DevParams &P, const DevBatch &B, int s, int a, int len)
 {
     double sc = 0.0;
-    if (!(S.has_react && !S.default_reacts) && !S.has_smat) {
+    if (C::PLAIN || (!(S.has_react && !S.default_reacts) && !S.has_smat)) {
+        #pragma unroll 1
         for (int q = 0; q < len; q++) sc = __dadd_rn(sc, P.weight[S.code[a + q] * MAXK + S.code[s - a - q]]);
     } else {
+        #pragma unroll 1
         for (int q = 0; q < len; q++) sc = __dadd_rn(sc, cell_score(S, P, B, a + q, s - a - q));
     }
     return sc;
@@ -615,7 +680,9 @@ __device__ __forceinline__ uint32_t restraint_cells(const State &S, int s, int k
 {
     uint32_t x = 0;
     int a = 0, b = S.nrb;
+    #pragma unroll 1
     while (a < b) { int mid = (a + b) >> 1; if (S.rbv[mid] + S.rbw[mid] < s) a = mid + 1; else b = mid; }
+    #pragma unroll 1
     for (; a < S.nrb && S.rbv[a] + S.rbw[a] == s; a++) {
         int v = S.rbv[a];
         if ((v >> 5) == k && S.partner[v] < 0 && S.partner[S.rbw[a]] < 0) x |= 1u << (v & 31);
@@ -635,62 +702,85 @@ __device__ __forceinline__ uint32_t range_mask(int k, int lo, int hi)
 // bit t of the result: cell (i = 32k + t, j = s - i) is a live base pair of the
 // masked bool matrix AnnotateStems walks (seq.py:431-451), restricted to the
 // walked range lo <= i <= hi of the diagonal.  Stateless form (fresh loads).
+template <class C>
 __device__ __forceinline__ uint32_t diag_word(const State &S, const DevParams &P, int s, int k, int lo, int hi)
 {
     const int bo = 32 * k + (S.N - 1 - s) + 32;     // bit offset into the reversed arrays
     const int wo = bo >> 5, sh = bo & 31;
     uint32_t x = 0;
-    for (int c = 0; c < P.npc; c++) {
-        uint32_t f = S.M[c * S.W + k];
-        uint32_t g = __funnelshift_r(S.PR[c * S.WR + wo], S.PR[c * S.WR + wo + 1], sh);
-        x |= f & g;
+    if (C::STDP) {
+        uint32_t r0 = __funnelshift_r(S.PR[wo], S.PR[wo + 1], sh);
+        uint32_t r1 = __funnelshift_r(S.PR[S.WR + wo], S.PR[S.WR + wo + 1], sh);
+        x = (S.M[k] ^ r0) & (S.M[S.W + k] | r1);
+    } else {
+        #pragma unroll 1
+        for (int c = 0; c < P.npc; c++) {
+            uint32_t f = S.M[c * S.W + k];
+            uint32_t g = __funnelshift_r(S.PR[c * S.WR + wo], S.PR[c * S.WR + wo + 1], sh);
+            x |= f & g;
+        }
     }
     x &= S.rowok[k] & __funnelshift_r(S.colokR[wo], S.colokR[wo + 1], sh);
     x &= range_mask(k, lo, hi);
-    if (S.nrb) x |= restraint_cells(S, s, k);
+    if (!C::PLAIN && S.nrb) x |= restraint_cells(S, s, k);
     return x;
 }
 
 // Sliding form: walks the words k0, k0+1, ... of one diagonal and keeps the low
-// halves of the funnel shifts in registers, so each word costs npc + 1 new loads
-// of the reversed arrays instead of 2 (npc + 1).
+// halves of the funnel shifts in registers, so each word costs one new load per
+// reversed array instead of two.
 struct DiagWalk {
     int k, wo, sh;
     uint32_t plo[4], clo;
 };
 
+template <class C>
 __device__ __forceinline__ void walk_begin(DiagWalk &it, const State &S, const DevParams &P, int s, int k0)
 {
     const int bo = 32 * k0 + (S.N - 1 - s) + 32;
     it.k = k0; it.wo = bo >> 5; it.sh = bo & 31;
-    #pragma unroll
-    for (int c = 0; c < 4; c++) it.plo[c] = (c < P.npc) ? S.PR[c * S.WR + it.wo] : 0u;
+    if (C::STDP) {
+        it.plo[0] = S.PR[it.wo]; it.plo[1] = S.PR[S.WR + it.wo]; it.plo[2] = it.plo[3] = 0u;
+    } else {
+        #pragma unroll
+        for (int c = 0; c < 4; c++) it.plo[c] = (c < P.npc) ? S.PR[c * S.WR + it.wo] : 0u;
+    }
     it.clo = S.colokR[it.wo];
 }
 
+template <class C>
 __device__ __forceinline__ uint32_t walk_next(DiagWalk &it, const State &S, const DevParams &P, int s, int lo, int hi)
 {
     const int k = it.k, wo = it.wo;
     uint32_t x = 0;
-    #pragma unroll
-    for (int c = 0; c < 4; c++)
-        if (c < P.npc) {
-            uint32_t phi = S.PR[c * S.WR + wo + 1];
-            x |= S.M[c * S.W + k] & __funnelshift_r(it.plo[c], phi, it.sh);
-            it.plo[c] = phi;
-        }
-    for (int c = 4; c < P.npc; c++)
-        x |= S.M[c * S.W + k] & __funnelshift_r(S.PR[c * S.WR + wo], S.PR[c * S.WR + wo + 1], it.sh);
+    if (C::STDP) {
+        uint32_t h0 = S.PR[wo + 1], h1 = S.PR[S.WR + wo + 1];
+        uint32_t r0 = __funnelshift_r(it.plo[0], h0, it.sh), r1 = __funnelshift_r(it.plo[1], h1, it.sh);
+        x = (S.M[k] ^ r0) & (S.M[S.W + k] | r1);
+        it.plo[0] = h0; it.plo[1] = h1;
+    } else {
+        #pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (c < P.npc) {
+                uint32_t phi = S.PR[c * S.WR + wo + 1];
+                x |= S.M[c * S.W + k] & __funnelshift_r(it.plo[c], phi, it.sh);
+                it.plo[c] = phi;
+            }
+        #pragma unroll 1
+        for (int c = 4; c < P.npc; c++)
+            x |= S.M[c * S.W + k] & __funnelshift_r(S.PR[c * S.WR + wo], S.PR[c * S.WR + wo + 1], it.sh);
+    }
     uint32_t chi = S.colokR[wo + 1];
     x &= S.rowok[k] & __funnelshift_r(it.clo, chi, it.sh);
     it.clo = chi;
     x &= range_mask(k, lo, hi);
-    if (S.nrb) x |= restraint_cells(S, s, k);
+    if (!C::PLAIN && S.nrb) x |= restraint_cells(S, s, k);
     it.k = k + 1; it.wo = wo + 1;
     return x;
 }
 
 // walked range of diagonal s: lo..hi (inclusive) in i; false if empty
+template <class C>
 __device__ __forceinline__ bool diag_range(const State &S, const DevBatch &B, int s, int &lo, int &hi)
 {
     const int N = S.N;
@@ -700,41 +790,44 @@ __device__ __forceinline__ bool diag_range(const State &S, const DevBatch &B, in
         // innermost extra cell with j - i in {2, 3} when a separator follows i (seq.py:293-297)
         int i1 = hi + 1, d = s - 2 * i1;
         if (i1 >= lo && d >= 2 && inc4_of(S, i1) <= d) hi = i1;
-        if (B.interchainonly) {
+        if (!C::PLAIN && B.interchainonly) {
             // chains differ iff a separator lies between i and j; the set of such cells is a prefix
             if (S.sepcnt[s - lo] - S.sepcnt[lo] <= 0) return false;
             int a = lo, b = hi;          // largest i in [lo, hi] with a separator in (i, s-i)
+            #pragma unroll 1
             while (a < b) {
                 int mid = (a + b + 1) >> 1;
                 if (S.sepcnt[s - mid] - S.sepcnt[mid] > 0) a = mid; else b = mid - 1;
             }
             hi = a;
         }
-    } else if (B.interchainonly) return false;
+    } else if (!C::PLAIN && B.interchainonly) return false;
     return hi >= lo;
 }
 
 // ---------------------------------------------------- enumerate one diagonal
 // calls emit(a, e) for every maximal run [a, e] (in i) of at least P.m cells, in
 // increasing a: outermost stem first, the order of seq.py:486-493.
-template <class F>
+template <class C, class F>
 __device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, const DevBatch &B, int s, F &&emit)
 {
     int lo, hi;
-    if (!diag_range(S, B, s, lo, hi)) return;
+    if (!diag_range<C>(S, B, s, lo, hi)) return;
     const int k0 = lo >> 5, k1 = hi >> 5;
     const int m = P.m;
     DiagWalk it;
-    walk_begin(it, S, P, s, k0);
-    uint32_t x = walk_next(it, S, P, s, lo, hi);
+    walk_begin<C>(it, S, P, s, k0);
+    uint32_t x = walk_next<C>(it, S, P, s, lo, hi);
     uint32_t prev_top = 0;
     int skip_until = -1;                   // runs already emitted extend up to here
+    #pragma unroll 1
     for (int k = k0; k <= k1; k++) {
-        uint32_t xn = (k < k1) ? walk_next(it, S, P, s, lo, hi) : 0u;
+        uint32_t xn = (k < k1) ? walk_next<C>(it, S, P, s, lo, hi) : 0u;
         if (x) {
             uint32_t y = x;
             for (int t = 1; t < m; t++) y &= __funnelshift_r(x, xn, t);
             uint32_t starts = y & ~((x << 1) | prev_top);
+            #pragma unroll 1
             while (starts) {
                 int b = __ffs(starts) - 1;
                 starts &= starts - 1;
@@ -747,7 +840,8 @@ __device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, co
                 if (b + t < 32) e = a + t - 1;
                 else {
                     int kk = k + 1; uint32_t w = xn;
-                    while (kk <= k1 && w == 0xffffffffu) { kk++; w = (kk <= k1) ? diag_word(S, P, s, kk, lo, hi) : 0u; }
+                    #pragma unroll 1
+                    while (kk <= k1 && w == 0xffffffffu) { kk++; w = (kk <= k1) ? diag_word<C>(S, P, s, kk, lo, hi) : 0u; }
                     e = (kk <= k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (k1 + 1) - 1;
                     if (e > hi) e = hi;
                 }
@@ -775,6 +869,7 @@ __device__ __forceinline__ void region_scan(const State &S, int ss, int se, Regi
     int dots = 0, br = 0, nedges = 0, e0 = -1, e1 = -1, inblockend = -1;
     bool between = false;
     unsigned long long levmask = 0;
+    #pragma unroll 1
     for (int pos = ss + 1; pos < se; pos++) {         // seq.py:665-689
         int pr = S.partner[pos];
         if (pr < 0) {
@@ -816,6 +911,7 @@ __device__ __forceinline__ void region_stems(const State &S, int ss, int se, Reg
     const int n = S.nst;
     int br = 0, nedges = 0, e0 = -1, e1 = -1, ibe = -1, blo = 0, covU = 0;
     unsigned long long levmask = 0;
+    #pragma unroll 1
     for (int q = 0; q < n; q++) {
         const int i = S.ssi[q];
         if (i > se) break;                              // sorted by i: nothing further can reach the region
@@ -840,6 +936,7 @@ __device__ __forceinline__ void region_stems(const State &S, int ss, int se, Reg
         } else if (bin) {                               // 3' arm inside, 5' arm left of ss
             const int x = j - S.ssl[q] + 1;
             bool covered = false;
+            #pragma unroll 1
             for (int u = q + 1; u < n && !covered; u++) {
                 int iu = S.ssi[u];
                 if (iu >= x) break;
@@ -861,6 +958,10 @@ __device__ __forceinline__ void region_stems(const State &S, int ss, int se, Reg
 
 // adjusted score of candidate (outer pair (a, s-a), length len, raw score bps)
 // given the current structure; seq.py:641-745.
+// pow() outside the host-built tables (never on the shipped parameter sets): kept out of line
+__device__ SQRN_NOINLINE double slow_pow(double a, double b) { return pow(a, b); }
+
+template <class C>
 __device__ __forceinline__ double score_candidate(const State &S, const DevParams &P, int s, int a, int len, double bps)
 {
     const int N = S.N;
@@ -871,7 +972,9 @@ __device__ __forceinline__ double score_candidate(const State &S, const DevParam
         R.dots = se - ss - 1; R.br = 0; R.nedges = 0; R.e0 = R.e1 = -1; R.inblockend = -1; R.levmask = 0;
         R.between = S.has_sep && (S.sepcnt[se] - S.sepcnt[ss + 1] > 0);
     } else {
-        bool by_stems = S.region_mode == REGION_STEMS ||
+        // the fast-lane flavour carries only the stem walk (smaller code); otherwise the cheaper
+        // of the two is picked per candidate unless a test forces one
+        bool by_stems = C::PLAIN || S.region_mode == REGION_STEMS ||
                         (S.region_mode == REGION_AUTO && 5 * S.nst < 2 * (se - ss));
         if (by_stems) region_stems(S, ss, se, R); else region_scan(S, ss, se, R);
     }
@@ -884,7 +987,9 @@ __device__ __forceinline__ double score_candidate(const State &S, const DevParam
     bool goodout = false; int diff2 = 0;
     if (S.nst) {                                           // seq.py:700-711
         int vv = oi - 1, ww = oj + 1;
+        #pragma unroll 1
         while (vv >= 0 && oi - vv - 1 < 5 && S.partner[vv] < 0) vv--;
+        #pragma unroll 1
         while (ww < N && ww - oj - 1 < 5 && S.partner[ww] < 0) ww++;
         if (vv >= 0 && ww < N && S.partner[vv] == ww) {
             int x = oi - vv - 1, y = ww - oj - 1, d = x > y ? x - y : y - x;
@@ -905,14 +1010,14 @@ __device__ __forceinline__ double score_candidate(const State &S, const DevParam
         int ideal = R.inblockend == -1 ? 4 : 2;
         if (P.bw_is_int) {
             int k = R.dots + P.bw_int * R.br - ideal; if (k < 0) k = -k;
-            sdf = (k < P.sdf_n) ? __ldg(&P.sdf_lut[k]) : pow(1.0 / (1.0 + (double)k), P.distcoef);
+            sdf = (k < P.sdf_n) ? __ldg(&P.sdf_lut[k]) : slow_pow(1.0 / (1.0 + (double)k), P.distcoef);
         } else {
             double x = fabs(__dadd_rn((double)R.dots, __dmul_rn(P.bracketweight, (double)R.br)) - (double)ideal);
-            sdf = pow(1.0 / (1.0 + x), P.distcoef);        // documented <= 1 ulp deviation
+            sdf = slow_pow(1.0 / (1.0 + x), P.distcoef);   // documented <= 1 ulp deviation
         }
     }
     int order = __popcll(R.levmask);
-    double of = (order < P.of_n) ? __ldg(&P.of_lut[order]) : pow(1.0 / (1.0 + order), P.orderpenalty);
+    double of = (order < P.of_n) ? __ldg(&P.of_lut[order]) : slow_pow(1.0 / (1.0 + order), P.orderpenalty);
     // seq.py:732
     double fin = __dmul_rn(bps, sdf);
     fin = __dmul_rn(fin, of);
@@ -923,9 +1028,10 @@ __device__ __forceinline__ double score_candidate(const State &S, const DevParam
 
 // -------------------------------------------- one OptimalStems pass (arg-max)
 // team-wide reductions --------------------------------------------------------
-template <int TW>
+template <class C>
 __device__ __forceinline__ Best team_argmax(State &S, Best best)
 {
+    constexpr int TW = C::TW;
 #ifndef SQRN_HOST_EMU
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -943,6 +1049,7 @@ __device__ __forceinline__ Best team_argmax(State &S, Best best)
         if ((threadIdx.x & 31) == 0) { sd[w] = best.fin; sk[2 * w] = best.key; sk[2 * w + 1] = (uint32_t)best.len; }
         __syncthreads();
         Best b2; b2.fin = -1e300; b2.key = 0xffffffffu; b2.len = 0;
+        #pragma unroll 1
         for (int q = 0; q < TW; q++) {
             double f = sd[q]; uint32_t k = sk[2 * q];
             if (better(f, k, b2.fin, b2.key)) { b2.fin = f; b2.key = k; b2.len = (int)sk[2 * q + 1]; }
@@ -956,9 +1063,10 @@ __device__ __forceinline__ Best team_argmax(State &S, Best best)
 
 // Phase 2b for one survivor: ScoreStems' adjusted score; folds it into the
 // lane's running best.  Returns the adjusted score (-1e300 if below minfinscore).
+template <class C>
 __device__ __forceinline__ double consider(const State &S, const DevParams &P, uint32_t key, int len, double bps, Best &best)
 {
-    double fin = score_candidate(S, P, (int)(key >> 16), (int)(key & 0xffff), len, bps);
+    double fin = score_candidate<C>(S, P, (int)(key >> 16), (int)(key & 0xffff), len, bps);
     if (!(fin >= P.minfinscore)) return -1e300;
     if (better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
     return fin;
@@ -973,9 +1081,10 @@ __device__ __forceinline__ double consider(const State &S, const DevParams &P, u
 // keep_all == true (STEP): every survivor stays in the list with its adjusted
 // score in cfin[] for team_choose; misc[7] = number of survivors found (may
 // exceed Ccap: the caller then retries with a larger list).
-template <int TW>
+template <class C>
 __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L, const bool keep_all)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
     if (r == 0) { S.misc[0] = 0; S.misc[7] = 0; }
@@ -989,8 +1098,9 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
     auto flush_survivors = [&]() {
         int ns = nsurv < Ccap ? nsurv : Ccap;
         Team<TW>::sync();                  // the survivors stored by the other threads are visible
+        #pragma unroll 1
         for (int c = r; c < ns; c += T) {
-            double fin = consider(S, P, S.ckey[c], S.clen[c], S.cbps[c], best);
+            double fin = consider<C>(S, P, S.ckey[c], S.clen[c], S.cbps[c], best);
             if (keep_all) S.cfin[c] = fin;
         }
         Team<TW>::sync();
@@ -1001,13 +1111,14 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
     };
     // phase 2a over the first nr entries of the run list (team-uniform call)
     auto flush_runs = [&](int nr) {
+        #pragma unroll 1
         for (int c0 = 0; c0 < nr; c0 += T) {
             if (!keep_all && nsurv + T > Ccap) flush_survivors();
             const int c = c0 + r;
             bool push = false; uint32_t key = 0; int len = 0; double sc = 0.0;
             if (c < nr) {
                 key = S.rkey[c]; len = S.rlen[c];
-                sc = run_score(S, P, B, (int)(key >> 16), (int)(key & 0xffff), len);
+                sc = run_score<C>(S, P, B, (int)(key >> 16), (int)(key & 0xffff), len);
                 push = sc >= P.minbpscore;
             }
             int slot;
@@ -1020,6 +1131,7 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
         Team<TW>::sync();
     };
 
+    #pragma unroll 1
     for (int s0 = 4; s0 <= smax; s0 += T) {
         const int s = s0 + r;
         const bool last = s0 + T > smax;
@@ -1027,7 +1139,7 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
         for (;;) {
             bool pending = false;          // the run list filled up before this lane's diagonal was finished
             if (s <= smax)
-                enum_diag(S, P, B, s, [&](int a, int e) {
+                enum_diag<C>(S, P, B, s, [&](int a, int e) {
                     if (a <= done || pending) return;
                     int len = e - a + 1;
                     if ((double)len < P.minlen) return;
@@ -1045,7 +1157,7 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
     flush_survivors();
     if (r == 0) S.misc[7] = nsurv;
     Team<TW>::sync();
-    return team_argmax<TW>(S, best);
+    return team_argmax<C>(S, best);
 }
 
 // two stems are "in conflict" when they share a paired position (seq.py:783-786)
@@ -1061,42 +1173,47 @@ __device__ __forceinline__ bool stems_share(int i1, int j1, int l1, int i2, int 
 // order of the reference's stable sort.  Writes (i, j, len) triples; returns
 // the number chosen, or -1 if the candidate list overflowed (caller retries
 // with a larger list).
-template <int TW>
+template <class C>
 __device__ int team_choose(State &S, const Layout &L, const Best &best, double subopt,
                            int32_t *out, double *outfin, int cap)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     int ntot = S.misc[7];
     if (ntot > L.Ccap) return -1;
     if (best.fin <= -1e300) return 0;
     const double range = __dmul_rn(subopt, best.fin);
     // rank the in-range candidates by (fin desc, enumeration order)
-    int16_t *ord = S.perm;                 // level scratch is free here: at most Scap entries are kept
+    int16_t *ord = (int16_t *)S.rkey;      // the run list is dead after the scan: Ocap entries fit in its space
     if (r == 0) S.misc[6] = 0;
     Team<TW>::sync();
+    #pragma unroll 1
     for (int c = r; c < ntot; c += T) {
         double f = S.cfin[c];
         if (f <= -1e300 || f < range) continue;
         uint32_t k = S.ckey[c];
         int rank = 0;
+        #pragma unroll 1
         for (int d = 0; d < ntot; d++) {
             double g = S.cfin[d];
             if (g <= -1e300 || g < range) continue;
             if (better(g, S.ckey[d], f, k)) rank++;
         }
-        if (rank < L.Scap) ord[rank] = (int16_t)c;
+        if (rank < L.Ocap) ord[rank] = (int16_t)c;
         atomicAdd(&S.misc[6], 1);
     }
     Team<TW>::sync();
     int nin = S.misc[6];
-    if (nin > L.Scap || nin > 32767) return -1;
+    if (nin > L.Ocap || nin > 32767) return -1;
     if (r == 0) {
         int n = 0;
+        #pragma unroll 1
         for (int a = 0; a < nin; a++) {
             int c = ord[a];
             uint32_t k = S.ckey[c];
             int i = k & 0xffff, j = (int)(k >> 16) - i, len = S.clen[c];
             bool ok = true;
+            #pragma unroll 1
             for (int q = 0; q < n && ok; q++)
                 if (!stems_share(i, j, len, out[3 * q], out[3 * q + 1], out[3 * q + 2])) ok = false;
             if (a == 0) ok = true;
@@ -1114,22 +1231,25 @@ __device__ int team_choose(State &S, const Layout &L, const Best &best, double s
 // AnnotateStems output in reference order (YieldStems, ali.py:86-101): stems of
 // the current structure state, written as (i, j, len) + bp score.  Returns the
 // number of stems (may exceed cap: the caller then re-allocates and re-runs).
-template <int TW>
+template <class C>
 __device__ int team_yield(State &S, const DevParams &P, const DevBatch &B, int32_t *out, double *outsc, int64_t cap)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int smax = 2 * S.N - 6;
     int base = 0;
+    #pragma unroll 1
     for (int s0 = 4; s0 <= smax; s0 += T) {
         int s = s0 + r, cnt = 0;
         // pass 0 counts the stems of this lane's diagonal, pass 1 writes them at the scanned offset
         int w = 0;
+        #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
             if (s <= smax && (pass == 0 || cnt))
-                enum_diag(S, P, B, s, [&](int a, int e) {
+                enum_diag<C>(S, P, B, s, [&](int a, int e) {
                     int len = e - a + 1;
                     if ((double)len < P.minlen) return;
-                    double sc = run_score(S, P, B, s, a, len);
+                    double sc = run_score<C>(S, P, B, s, a, len);
                     if (!(sc >= P.minbpscore)) return;
                     if (pass == 0) { cnt++; return; }
                     if (w < cap) { out[3 * (int64_t)w] = a; out[3 * (int64_t)w + 1] = s - a; out[3 * (int64_t)w + 2] = len; outsc[w] = sc; }
@@ -1152,22 +1272,26 @@ __device__ int team_yield(State &S, const DevParams &P, const DevBatch &B, int32
 __device__ __forceinline__ double round3_fast(double x, bool &ok)
 {
     if (!(fabs(x) < 1e9)) { ok = false; return x; }
+    // y = x * 1000 carries a relative error <= 2^-53: k is the integer nearest to the exact product
+    // whenever y is further than that from the half-way point
     double y = __dmul_rn(x, 1000.0), k = rint(y);
-    if (!(fabs(__dsub_rn(y, k)) < 0.49)) { ok = false; return x; }
+    if (!(fabs(__dsub_rn(y, k)) < __dsub_rn(0.4999999, __dmul_rn(fabs(y), 1e-15)))) { ok = false; return x; }
     return __ddiv_rn(k, 1000.0);
 }
 
 // ------------------------------------------------------------- finalisation
 // ScoreStruct (seq.py:861-899) + dbn of the finished structure.
-template <int TW>
+template <class C>
 __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk, int item)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int N = S.N;
-    team_levels<TW>(S);
+    team_levels<C>(S);
     int64_t doff = Wk.dbn_off ? Wk.dbn_off[item] : 0;
     if (Wk.out_dbn_ascii || Wk.out_dbn_code) {
         const int64_t so = B.off[Wk.item_seq ? Wk.item_seq[item] : item];
+        #pragma unroll 1
         for (int p = r; p < N; p += T) {
             int pr = S.partner[p];
             int lv = pr < 0 ? 0 : S.stlev[S.owner[p]];
@@ -1184,8 +1308,10 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
         }
     }
     // bpsum of every stem in units of 0.5 (GU -0.5, AU 1.5, GC 4.0), one stem per thread
+    #pragma unroll 1
     for (int t = r; t < S.nst; t += T) {
         int k2 = 0;
+        #pragma unroll 1
         for (int q = 0; q < S.stl[t]; q++) {
             int a = S.code[S.sti[t] + q], b = S.code[S.stj[t] - q];
             int lo = a < b ? a : b, hi = a < b ? b : a;
@@ -1199,19 +1325,21 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
     if (r == 0) {
         uint8_t flags = 0;
         double thescore = 0.0; bool any = false; int maxlev = 0;
+        #pragma unroll 1
         for (int t = 0; t < S.nst; t++) {                // summed in selection order (seq.py:884)
             int k2 = S.cc[t];
             if (k2 > 0) {
-                double pw = (k2 < P.pw17_n) ? __ldg(&P.pw17_lut[k2]) : pow(0.5 * k2, 1.7);
+                double pw = (k2 < P.pw17_n) ? __ldg(&P.pw17_lut[k2]) : slow_pow(0.5 * k2, 1.7);
                 thescore = __dadd_rn(thescore, pw); any = true;
             }
             if (S.stlev[t] > maxlev) maxlev = S.stlev[t];
         }
         double reactscore = 0.5;
-        if (S.has_react && !S.default_reacts) {
+        if (!C::PLAIN && S.has_react && !S.default_reacts) {
             int nsep = S.has_sep ? S.sepcnt[N] : 0;
             // builtin sum(): plain left-to-right for numpy floats, Neumaier for exact Python floats
             double sum = 0.0, comp = 0.0; bool first = true;
+            #pragma unroll 1
             for (int p = 0; p < N; p++) {
                 if (S.code[p] == CODE_SEP) continue;
                 double rv = B.rvals[S.rcode[p]];
@@ -1242,6 +1370,7 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
     // stems in selection order
     if (!Wk.out_off) return;
     int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
+    #pragma unroll 1
     for (int t = r; t < S.nst && t < cap; t += T) {
         Wk.out_stems[3 * (so + t)] = S.sti[t];
         Wk.out_stems[3 * (so + t) + 1] = S.stj[t];
@@ -1250,47 +1379,51 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
 }
 
 // ------------------------------------------------------------ one work item
-template <int TW>
+template <class C>
 __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk,
                               const Layout &L, int item)
 {
+    constexpr int TW = C::TW;
     const int r = Team<TW>::rank();
     const int seq = Wk.item_seq ? Wk.item_seq[item] : item;
+    const int mode = C::MODE >= 0 ? C::MODE : Wk.mode;
     S.region_mode = Wk.region_mode;
-    team_load<TW>(S, B, P, seq);
+    team_load<C>(S, B, P, seq);
     if (Wk.init_off) {
         const int64_t k0 = Wk.init_off[item], k1 = Wk.init_off[item + 1];
+        #pragma unroll 1
         for (int64_t k = k0; k < k1; k++)
-            team_apply_stem<TW>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2], false);
-        if (k1 > k0) team_unpaired_prefix<TW>(S);
+            team_apply_stem<C>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2], false);
+        if (k1 > k0) team_unpaired_prefix<C>(S);
     }
     unsigned long long calls = 0;
-    if (Wk.mode == MODE_TAIL || Wk.mode == MODE_FINAL) {
+    if (mode == MODE_TAIL || mode == MODE_FINAL) {
         // the pool loop of seq.py:1159-1199 once it can no longer branch
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
-        while (Wk.mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
-            team_levels<TW>(S);
-            Best b = team_scan<TW>(S, P, B, L, false);
+        #pragma unroll 1
+        while (mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
+            team_levels<C>(S);
+            Best b = team_scan<C>(S, P, B, L, false);
             calls++;
             if (b.fin <= -1e300) break;
             int i = (int)(b.key & 0xffff);
-            team_apply_stem<TW>(S, i, (int)(b.key >> 16) - i, b.len);
+            team_apply_stem<C>(S, i, (int)(b.key >> 16) - i, b.len);
         }
-        team_finalize<TW>(S, P, B, Wk, item);
-    } else if (Wk.mode == MODE_STEP) {
+        team_finalize<C>(S, P, B, Wk, item);
+    } else if (mode == MODE_STEP) {
         int n = 0;
         int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
         if ((double)S.nst != P.maxstemnum) {
-            team_levels<TW>(S);
-            Best b = team_scan<TW>(S, P, B, L, true);
+            team_levels<C>(S);
+            Best b = team_scan<C>(S, P, B, L, true);
             calls++;
-            n = team_choose<TW>(S, L, b, Wk.item_subopt[item], Wk.out_stems + 3 * so,
+            n = team_choose<C>(S, L, b, Wk.item_subopt[item], Wk.out_stems + 3 * so,
                                 Wk.out_stemfin ? Wk.out_stemfin + so : nullptr, (int)cap);
         }
         if (r == 0) Wk.out_nstems[item] = n;
     } else {
         int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
-        int n = team_yield<TW>(S, P, B, Wk.out_stems + 3 * so, Wk.out_stemfin + so, cap);
+        int n = team_yield<C>(S, P, B, Wk.out_stems + 3 * so, Wk.out_stemfin + so, cap);
         if (r == 0) Wk.out_nstems[item] = n;
     }
     if (r == 0 && Wk.n_calls && calls) atomicAdd(Wk.n_calls, calls);

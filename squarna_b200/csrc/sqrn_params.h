@@ -69,6 +69,8 @@ inline bool build_host_params(const sqrn_paramset &ps, int nmax, HostParams &H, 
             if (P.npc >= MAXPC) { err = "too many pairing symbols in bpweights"; return false; }
             P.pc_code[P.npc++] = c;
         }
+    P.std_pairs = (K == 6 && P.npc == 4 && P.pairmask[CODE_A] == (1u << CODE_U) && P.pairmask[CODE_C] == (1u << CODE_G) &&
+                   P.pairmask[CODE_G] == ((1u << CODE_C) | (1u << CODE_U)) && P.pairmask[CODE_U] == ((1u << CODE_A) | (1u << CODE_G)));
     double m = ceil(ps.minlen);
     P.m = m < 1 ? 1 : (m > 32 ? 32 : (int)m);
     P.minlen = ps.minlen; P.minbpscore = ps.minbpscore;
@@ -100,8 +102,10 @@ inline double pyround3(double x)
         if (!isfinite(x)) return x;
         char buf[400]; snprintf(buf, sizeof buf, "%.3f", x); return strtod(buf, nullptr);
     }
+    // y carries a relative error <= 2^-53: k is the integer nearest to the exact product whenever
+    // y is further than that from the half-way point (same test as round3_fast on the device)
     double y = x * 1000.0, k = rint(y);
-    if (fabs(y - k) < 0.49) return k / 1000.0;
+    if (fabs(y - k) < 0.4999999 - fabs(y) * 1e-15) return k / 1000.0;
     char buf[64]; snprintf(buf, sizeof buf, "%.3f", x); return strtod(buf, nullptr);
 }
 

@@ -19,7 +19,7 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
                        const int32_t *init_stems, const double *item_subopt,
                        const int64_t *out_off, int32_t *out_stems, int32_t *out_nstems, double *out_stemfin,
                        double *out_raw, uint8_t *out_flags, const int64_t *dbn_off, uint8_t *dbn_ascii,
-                       int8_t *dbn_code, int ccap, unsigned long long *n_calls, int region_mode)
+                       int8_t *dbn_code, int ccap, unsigned long long *n_calls, int region_mode, int flavour)
 {
     int nmax = 1, rbmax = 0;
     for (int64_t b = 0; b < n_seqs; b++) {
@@ -50,7 +50,10 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
     for (int item = 0; item < n_items; item++) {
         State S = bind_state(smem, Lay);
-        team_run_item<0>(S, H.p, B, W, Lay, item);
+        if (flavour == 1) {            // the fast-lane flavour (plain batch, standard pairing table, MODE_TAIL)
+            if (!H.p.std_pairs || rcode || rclass || rbp_off || smat || interchainonly || mode != MODE_TAIL) { free(smem); return -2; }
+            team_run_item<Cfg<0, true, true, MODE_TAIL>>(S, H.p, B, W, Lay, item);
+        } else team_run_item<Cfg<0>>(S, H.p, B, W, Lay, item);
     }
     free(smem);
     return 0;

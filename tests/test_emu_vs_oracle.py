@@ -30,14 +30,17 @@ def _prep_batch(cases):
     return preps, kw
 
 
-@pytest.mark.parametrize("region", [0, 1, 2], ids=["auto", "scan", "stems"])
+@pytest.mark.parametrize("region", [0, 1, 2, "fast"], ids=["auto", "scan", "stems", "fastflavour"])
 @pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
                          ids=["fastest", "defG1", "defG2-smalllist", "ali"])
 def test_tail_plain(ps, ccap, region):
     """single-path greedy (pl=1) on plain sequences: stems, dbn, raw scores; the ScoreStems region
     evaluated by the reference's position scan, by the stem walk, and by the automatic choice"""
-    seqs = T.rand_seqs(31, 150, 5, 210)
-    r = emu.run(ps, seqs, ccap=ccap, region_mode=region)
+    seqs = T.rand_seqs(31, 150, 5, 210) + T.rand_seqs(36, 40, 5, 150, "ACGUN")
+    if region == "fast":       # compile-time flavour of the byseq fast lane: bit planes, stem walk only
+        r = emu.run(ps, seqs, ccap=ccap, flavour=1)
+    else:
+        r = emu.run(ps, seqs, ccap=ccap, region_mode=region)
     for b, s in enumerate(seqs):
         _, structs, _ = O.predict_short(s, [0.5] * len(s), "." * len(s), [ps], poollim=1)
         dbn, sc, isint, _, stems, _, _ = structs[0]
