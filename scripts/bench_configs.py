@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Throughput of the BASELINE.json configs other than the headline one, at reduced size
+(the headline config 2 is bench.py).  One JSON line per leg; run on the GPU box:
+
+    python scripts/bench_configs.py c5 --n 16        # rRNA-scale, 1000nobpp G set, pl=1
+    python scripts/bench_configs.py c3 --n 64        # 300..1500 nt, reactivities + restraints, G sets by length, pl=100
+    python scripts/bench_configs.py mid --n 2000     # 300..1500 nt plain, fastest.conf pl=1 (CTA teams)
+"""
+import argparse, json, os, random, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from squarna_b200 import SQRNdbnseq as S, SQUARNA as CLI, _lib           # noqa: E402
+from squarna_b200._abi import pack_sequences                              # noqa: E402
+
+CONF = os.path.join(ROOT, "squarna_b200")
+
+
+def gsets(name):
+    names, ps = CLI.ParseConfig(os.path.join(CONF, name + ".conf"))
+    return [p for p in ps if p["algorithms"] == {"G"} and not p.get("bpp", 0)]
+
+
+def rand_seqs(rng, n, lo, hi):
+    return ["".join(rng.choice("ACGU") for _ in range(rng.randint(lo, hi))) for _ in range(n)]
+
+
+def leg_tail(name, seqs, ps, oracle_n):
+    ctx = S.get_context(0)
+    sym, off = pack_sequences(seqs)
+    ctx.fast_predict(ps, sym[:int(off[2])], off[:3])            # warm-up (module load, parameter digest)
+    t0 = time.perf_counter()
+    dbn, sc, nst = ctx.fast_predict(ps, sym, off)
+    dt = time.perf_counter() - t0
+    st = ctx.stats()
+    lens = np.diff(off).astype(np.float64)
+    line = {"leg": name, "n_seqs": len(seqs), "len_min": int(lens.min()), "len_max": int(lens.max()), "seconds": dt,
+            "seq_per_s": len(seqs) / dt, "nt2_per_s": float((lens ** 2).sum()) / dt, "kernel_ms": st["kernel_ms"],
+            "optimal_calls": st["optimal_calls"], "stems_mean": float(nst.mean())}
+    if oracle_n:
+        from oracle import oracle as O
+        k = min(oracle_n, len(seqs))
+        t0 = time.perf_counter()
+        odbn, osc, onst = O.predict_batch_simple(sym[:int(off[k])], off[:k + 1], [ps], poollim=1, nthreads=os.cpu_count() or 1)
+        line["oracle_seconds_for_%d" % k] = time.perf_counter() - t0
+        line["parity"] = bool(np.array_equal(onst, nst[:k]) and np.array_equal(osc, sc[:k]))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("leg")
+    ap.add_argument("--n", type=int, default=16)
+    ap.add_argument("--oracle", type=int, default=0, help="check the first K sequences against the CPU oracle")
+    ap.add_argument("--lo", type=int, default=0)
+    ap.add_argument("--hi", type=int, default=0)
+    a = ap.parse_args()
+    rng = random.Random(20261017)
+    if a.leg == "c5":
+        leg_tail("c5 1000nobpp G pl=1", rand_seqs(rng, a.n, a.lo or 2900, a.hi or 5000), gsets("1000nobpp")[0], a.oracle)
+    elif a.leg == "mid":
+        leg_tail("mid fastest pl=1", rand_seqs(rng, a.n, a.lo or 300, a.hi or 1500), gsets("fastest")[0], a.oracle)
+    elif a.leg == "c3":
+        seqs = rand_seqs(rng, a.n, a.lo or 300, a.hi or 1500)
+        entries = []
+        for s in seqs:
+            n = len(s)
+            reacts = "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") if rng.random() > 0.03 else "?" for _ in range(n))
+            rest = ["."] * n
+            for k in range(n):
+                x = rng.random()
+                rest[k] = "_" if x < 0.05 else "/" if x < 0.06 else "\\" if x < 0.07 else "."
+            entries.append((s, reacts, "".join(rest), None))
+        groups = {"greedynobpp": [], "500nobpp": [], "1000nobpp": []}
+        for e in entries:
+            groups["greedynobpp" if len(e[0]) < 500 else "500nobpp" if len(e[0]) < 1000 else "1000nobpp"].append(e)
+        S.predict_many(entries[:1], gsets("fastest"), poollim=1)
+        for conf, es in groups.items():
+            if not es:
+                continue
+            t0 = time.perf_counter()
+            out = S.predict_many(es, gsets(conf), poollim=100)
+            dt = time.perf_counter() - t0
+            st = S.get_context(0).stats()
+            lens = np.array([len(e[0]) for e in es], dtype=np.float64)
+            print(json.dumps({"leg": "c3 " + conf + " pl=100", "n_seqs": len(es), "seconds": dt, "seq_per_s": len(es) / dt,
+                              "nt2_per_s": float((lens ** 2).sum()) / dt, "launches": st["launches"],
+                              "optimal_calls": st["optimal_calls"], "kernel_ms": st["kernel_ms"],
+                              "structs_mean": float(np.mean([len(o[1]) for o in out]))}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

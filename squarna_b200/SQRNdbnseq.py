@@ -210,17 +210,18 @@ def ReferenceScores(seq, ref, reacts):
     return ScoreStruct(seq, PairsToStems(sorted(DBNToPairs(ref))), reacts)
 
 
+# code point of every int8 level code (+L opening bracket of level L, -L closing one), indexed by
+# the code reinterpreted as uint8; levels beyond the 49 bracket pairs print as '.' (seq.py:142-143)
+_GLYPH32 = np.full(256, ord('.'), dtype=np.uint32)
+for _lev in range(1, 128):
+    if _lev <= len(_OPEN):
+        _GLYPH32[_lev] = ord(_OPEN[_lev - 1])
+        _GLYPH32[256 - _lev] = ord(_CLOSE[_lev - 1])
+
+
 def _codes_to_dbn(codes):
     """int8 level codes (+L open, -L close) -> glyph string"""
-    out = []
-    for c in codes.tolist():
-        if c == 0:
-            out.append('.')
-        elif c > 0:
-            out.append(_OPEN[c - 1] if c <= len(_OPEN) else '.')
-        else:
-            out.append(_CLOSE[-c - 1] if -c <= len(_CLOSE) else '.')
-    return ''.join(out)
+    return _GLYPH32[np.asarray(codes, dtype=np.int8).view(np.uint8)].tobytes().decode("utf-32-le")
 
 
 def _metrics(pred, known):
@@ -236,42 +237,106 @@ def _metrics(pred, known):
 # ------------------------------------------------------------ batch front-end
 class _Prepared:
     """one sequence digested the way seq.py:1004-1037 does it"""
-    __slots__ = ("seq", "shortseq", "shortrest", "shortreacts", "rbps", "rclass", "keep", "shortdbn",
+    __slots__ = ("seq", "shortseq", "shortrest", "_sr", "rbps", "rclass", "_keep", "shortdbn",
                  "dbn", "compensated")
+
+    @property
+    def shortreacts(self):
+        """processed reactivities of the ungapped sequence (all 0.5 when none were given)"""
+        return [0.5] * len(self.shortseq) if self._sr is None else self._sr
+
+    @property
+    def keep(self):
+        """ungapped position -> position in the input sequence"""
+        return np.arange(len(self.seq)) if self._keep is None else self._keep
+
+
+_REACT_LUT = {}
+
+
+def _react_lut(M=1.8, B=1.6):
+    """processed reactivity of every reactivity letter (seq.py:1019-1020 -> ProcessReacts defaults)"""
+    key = (M, B)
+    if key not in _REACT_LUT:
+        chars = sorted(ReactDict)
+        vals = ProcessReacts([ReactDict[ch] for ch in chars], M=M, B=B)
+        lut = np.full(256, np.nan)
+        for ch, v in zip(chars, vals):
+            lut[ord(ch)] = v
+        _REACT_LUT[key] = lut
+    return _REACT_LUT[key]
+
+
+_GAP_BYTES = np.zeros(256, dtype=bool)
+for _ch in GAPS:
+    _GAP_BYTES[ord(_ch)] = True
+_RC_BYTES = np.zeros(256, dtype=np.uint8)
+_RC_BYTES[ord('_')] = _RC_BYTES[ord('+')] = 1
+_RC_BYTES[ord('/')] = 2
+_RC_BYTES[ord('\\')] = 4
+_PLAIN_RESTR = np.zeros(256, dtype=bool)           # restraint symbols that are not brackets
+for _ch in "._+/\\-~":
+    _PLAIN_RESTR[ord(_ch)] = True
 
 
 def _prepare(seq, reacts, restraints, dbn):
+    """seq.py:1004-1037 for one entry.  The common shapes (no gaps, no restraints, encoded or absent
+    reactivities) take vectorised paths; everything else goes through the reference's own steps."""
     p = _Prepared()
     seq = seq.upper().replace("T", "U")                               # seq.py:1004
-    if not restraints:
-        restraints = '.' * len(seq)
-    assert len(seq) == len(restraints), "Invalid restraints given"
-    if not reacts:
-        reacts = [0.5 for _ in range(len(seq))]
-    assert len(reacts) == len(seq), "Invalid reactivities given"
-    if type(reacts) == str:
-        reacts = ProcessReacts([ReactDict[ch] for ch in reacts])      # seq.py:1019-1020 (B = 1.6 default)
+    n = len(seq)
+    if restraints:
+        assert n == len(restraints), "Invalid restraints given"
+    if reacts:
+        assert len(reacts) == n, "Invalid reactivities given"
     p.seq = seq
-    p.shortseq, p.shortrest = UnAlign(seq, restraints)
-    p.keep = [k for k, ch in enumerate(seq) if ch not in GAPS]
-    p.shortreacts = [reacts[k] for k in p.keep]
-    # builtin sum() in ScoreStruct compensates exact Python floats only (CPython >= 3.12)
-    p.compensated = all(type(x) is float for x in p.shortreacts)
+    raw = np.frombuffer(seq.encode("latin-1", "replace"), dtype=np.uint8)
+    gapmask = _GAP_BYTES[raw]
+    has_gaps = bool(gapmask.any())
+    p._keep = np.flatnonzero(~gapmask) if has_gaps else None         # None: identity
+    # --- restraints -----------------------------------------------------------
+    if not restraints:
+        p.shortseq = ''.join(seq[k] for k in p._keep) if has_gaps else seq
+        p.shortrest = '.' * len(p.shortseq)
+        p.rbps = []
+        p.rclass = np.zeros(len(p.shortseq), dtype=np.uint8)
+    else:
+        rraw = np.frombuffer(restraints.encode("latin-1", "replace"), dtype=np.uint8)
+        if not has_gaps and bool(_PLAIN_RESTR[rraw].all()):
+            p.shortseq, p.shortrest, p.rbps = seq, restraints, []    # no brackets: nothing for DBNToPairs
+            p.rclass = _RC_BYTES[rraw]
+        else:
+            p.shortseq, p.shortrest = UnAlign(seq, restraints)
+            rbps, rxs, rlefts, rrights = ParseRestraints(p.shortrest)
+            p.rbps = rbps
+            rc = np.zeros(max(len(p.shortseq), 1), dtype=np.uint8)
+            for k in rxs:
+                rc[k] |= 1
+            for k in rlefts:
+                rc[k] |= 2
+            for k in rrights:
+                rc[k] |= 4
+            p.rclass = rc[:len(p.shortseq)]
+    # --- reactivities ---------------------------------------------------------
+    if not reacts:
+        p._sr = None                                                  # all 0.5: "default reacts"
+        p.compensated = True
+    elif type(reacts) == str:
+        vals = _react_lut()[np.frombuffer(reacts.encode("latin-1", "replace"), dtype=np.uint8)]
+        if np.isnan(vals).any():
+            raise KeyError(next(ch for ch in reacts if ch not in ReactDict))
+        p._sr = vals[p._keep] if has_gaps else vals                   # numpy floats, like ProcessReacts' output
+        p.compensated = False
+    else:
+        keep = p._keep if has_gaps else range(n)
+        p._sr = [reacts[k] for k in keep]
+        # builtin sum() in ScoreStruct compensates exact Python floats only (CPython >= 3.12)
+        p.compensated = all(type(x) is float for x in p._sr)
     p.dbn = dbn
     p.shortdbn = None
     if dbn:
         assert len(seq) == len(dbn)
         p.shortdbn = UnAlign(seq, dbn)[1]
-    rbps, rxs, rlefts, rrights = ParseRestraints(p.shortrest)
-    p.rbps = rbps
-    rc = np.zeros(max(len(p.shortseq), 1), dtype=np.uint8)
-    for k in rxs:
-        rc[k] |= 1
-    for k in rlefts:
-        rc[k] |= 2
-    for k in rrights:
-        rc[k] |= 4
-    p.rclass = rc[:len(p.shortseq)]
     return p
 
 
@@ -309,28 +374,27 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
         idx = [k for k in todo if preps[k].compensated == comp]
         if not idx:
             continue
-        any_react = any(any(x != 0.5 for x in preps[k].shortreacts) for k in idx)
+        # distinct processed reactivities of the batch -> codes + value table (host pow() table in the library)
         codes = values = None
-        if any_react:
-            table = {}
-            codes = []
-            for k in idx:
-                arr = np.empty(len(preps[k].shortreacts), dtype=np.uint16)
-                for q, x in enumerate(preps[k].shortreacts):
-                    x = float(x)
-                    c = table.get(x)
-                    if c is None:
-                        c = table[x] = len(table)
-                    arr[q] = c
-                codes.append(arr)
-            if len(table) > 65535:
+        arrs = [None if preps[k]._sr is None else np.asarray(preps[k]._sr, dtype=np.float64) for k in idx]
+        if any(a is not None and bool((a != 0.5).any()) for a in arrs):
+            lens_ = [len(preps[k].shortseq) for k in idx]
+            flat = np.concatenate([np.full(n_, 0.5) if a is None else a for a, n_ in zip(arrs, lens_)]) if idx else np.zeros(0)
+            # bit patterns, not values: -0.0 / NaN payloads must stay distinct table entries
+            values_bits, inverse = np.unique(flat.view(np.uint64), return_inverse=True)
+            if len(values_bits) > 65535:
                 raise NotImplementedError("more than 65535 distinct reactivity values in one batch")
-            values = np.array(list(table.keys()), dtype=np.float64)
+            values = values_bits.view(np.float64)
+            inverse = inverse.astype(np.uint16)
+            codes, o = [], 0
+            for n_ in lens_:
+                codes.append(inverse[o:o + n_])
+                o += n_
         any_restr = any(p.rbps or p.rclass.any() for p in (preps[k] for k in idx))
         smat = cols = None
         if stemmatrix is not None:
             smat = np.asarray(stemmatrix, dtype=np.float64)
-            cols = [np.array(preps[k].keep, dtype=np.int32) for k in idx]
+            cols = [np.asarray(preps[k].keep, dtype=np.int32) for k in idx]
         pmask = 0
         for p in priority:
             if p in gsets:
@@ -350,21 +414,32 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
     for k, p in enumerate(preps):
         seq = p.seq
 
-        def expand(short):                      # ReAlign + separators, seq.py:1239-1246
-            long_ = ReAlign(short, seq)
-            return ''.join(seq[q] if seq[q] in SEPS else long_[q] for q in range(len(seq)))
+        raw = np.frombuffer(seq.encode("utf-32-le"), dtype=np.uint32)
+        seppos = np.flatnonzero((raw == ord(';')) | (raw == ord('&')))
+        keep = p._keep
+
+        def expand(codes, raw=raw, seppos=seppos, keep=keep):     # glyphs + ReAlign + separators, seq.py:1239-1246
+            g = _GLYPH32[np.asarray(codes, dtype=np.int8).view(np.uint8)]
+            if keep is not None:
+                long_ = np.full(len(raw), ord('.'), dtype=np.uint32)
+                long_[keep] = g
+                g = long_
+            if len(seppos):
+                g = g.copy() if keep is None else g
+                g[seppos] = raw[seppos]
+            return g.tobytes().decode("utf-32-le")
 
         if results[k] is None:
             cons_codes, structs = np.zeros(len(p.shortseq), np.int8), []
         else:
             cons_codes, structs = results[k]
-        cons = expand(_codes_to_dbn(cons_codes))
+        cons = expand(cons_codes)
         preds = []
         bpsets = []
         for codes, sc, isint, mask, stems in structs:
             total, struct, react = sc
             inds = [gsets[b] for b in range(len(gsets)) if mask >> b & 1]
-            preds.append((expand(_codes_to_dbn(codes)), (total, 0 if isint else struct, react), inds))
+            preds.append((expand(codes), (total, 0 if isint else struct, react), inds))
             bpsets.append(codes)
         if p.dbn:                                # seq.py:1249-1285
             known = set(DBNToPairs(p.shortdbn))

@@ -288,11 +288,12 @@ static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int mi
         return plan_for<1>(ctx, pl);
     }
     pl.tw = nmax <= 2048 ? 8 : 32;
-    int ccap = keep_all ? std::max(std::min(next_pow2(est), 4096), 256) : 1024;
+    // at least two rounds of survivors (one per thread and round) must fit between flushes
+    int ccap = keep_all ? std::max(std::min(next_pow2(est), 4096), 1024 * (pl.tw / 8)) : (pl.tw == 8 ? 2048 : 8192);
     if (ccap < min_ccap) ccap = next_pow2(min_ccap);
     for (;;) {
         pl.L = make_layout(nmax, rbmax, ccap, npc, pl.tw, 4096, extras, keep_all, scap);
-        if ((size_t)pl.L.total <= budget || ccap <= 256) break;
+        if ((size_t)pl.L.total <= budget || ccap <= 64 * pl.tw) break;
         ccap >>= 1;
     }
     if ((size_t)pl.L.total > budget) { ctx->err = "sequence too long for one CTA's shared memory"; return SQRN_E_UNSUPPORTED; }

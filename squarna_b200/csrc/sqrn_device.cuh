@@ -92,6 +92,8 @@ struct DevParams {
     const double *sdf_lut; int sdf_n;    // (1/(1+k))**distcoef      seq.py:726
     const double *of_lut;  int of_n;     // (1/(1+o))**orderpenalty  seq.py:729
     const double *pw17_lut; int pw17_n;  // (0.5k)**1.7              seq.py:884
+    int      ub_ok;                 // the factor maxima below are valid (all pow() terms come from tables)
+    double   sdf_max, of_max, lf_max;    // largest stem-distance / order / loop factor (score_bound)
     uint8_t  code_table[256];
 };
 
@@ -261,10 +263,14 @@ template <> struct Team<0> {
 //   STDP:  the pairing table is exactly {GC, AU, GU} over ACGU: pairability comes from the two
 //          bit planes of the 2-bit base codes, x = (b0 ^ r0) & (b1 | r1);
 //   MODE:  a fixed MODE_* or -1 (taken from DevWork at run time).
-template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1>
+//   RUNLIST: phase 1 collects runs in a shared list before they are scored (warp teams: keeps
+//          the lanes of phase 2a dense); off, every thread scores the runs of its own diagonal
+//          in team-wide rounds (CTA teams).  -1: on for warp teams only.
+template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1>
 struct Cfg {
     static constexpr int TW = TW_, MODE = MODE_;
     static constexpr bool PLAIN = PLAIN_, STDP = STDP_;
+    static constexpr bool RUNLIST = RUNLIST_ < 0 ? (TW_ == 1) : (RUNLIST_ != 0);
 };
 
 struct State {
@@ -806,52 +812,80 @@ __device__ __forceinline__ bool diag_range(const State &S, const DevBatch &B, in
 }
 
 // ---------------------------------------------------- enumerate one diagonal
-// calls emit(a, e) for every maximal run [a, e] (in i) of at least P.m cells, in
-// increasing a: outermost stem first, the order of seq.py:486-493.
+// Resumable walk over the maximal runs of one anti-diagonal, outermost first (the
+// order of seq.py:486-493).  runs_next() yields the next run [a, e] (in i) of at
+// least P.m cells; the caller may do other (team-uniform) work between calls.
+struct RunIter {
+    DiagWalk it;
+    int s, lo, hi, k, k1, skip_until;    // skip_until: runs already yielded extend up to here
+    uint32_t x, xn, prev_top, starts;
+    bool live;
+};
+
+__device__ __forceinline__ uint32_t run_starts(uint32_t x, uint32_t xn, uint32_t prev_top, int m)
+{
+    if (!x) return 0u;
+    uint32_t y = x;
+    for (int t = 1; t < m; t++) y &= __funnelshift_r(x, xn, t);
+    return y & ~((x << 1) | prev_top);
+}
+
+template <class C>
+__device__ __forceinline__ void runs_begin(RunIter &R, const State &S, const DevParams &P, const DevBatch &B, int s, bool on)
+{
+    R.s = s;
+    R.live = on && diag_range<C>(S, B, s, R.lo, R.hi);
+    if (!R.live) return;
+    R.k = R.lo >> 5; R.k1 = R.hi >> 5;
+    walk_begin<C>(R.it, S, P, s, R.k);
+    R.x = walk_next<C>(R.it, S, P, s, R.lo, R.hi);
+    R.xn = (R.k < R.k1) ? walk_next<C>(R.it, S, P, s, R.lo, R.hi) : 0u;
+    R.prev_top = 0; R.skip_until = -1;
+    R.starts = run_starts(R.x, R.xn, 0u, P.m);
+}
+
+template <class C>
+__device__ __forceinline__ bool runs_next(RunIter &R, const State &S, const DevParams &P, int &a, int &e)
+{
+    if (!R.live) return false;
+    #pragma unroll 1
+    for (;;) {
+        #pragma unroll 1
+        while (R.starts == 0) {
+            if (R.k >= R.k1) { R.live = false; return false; }
+            R.prev_top = R.x >> 31; R.x = R.xn; R.k++;
+            R.xn = (R.k < R.k1) ? walk_next<C>(R.it, S, P, R.s, R.lo, R.hi) : 0u;
+            R.starts = run_starts(R.x, R.xn, R.prev_top, P.m);
+        }
+        const int b = __ffs(R.starts) - 1;
+        R.starts &= R.starts - 1;
+        a = 32 * R.k + b;
+        if (a <= R.skip_until) continue;
+        // find the end of the run
+        uint32_t inv = ~(R.x >> b);              // bit 0 is 0; first set bit = run length
+        int t = inv ? __ffs(inv) - 1 : 32;
+        if (b + t < 32) e = a + t - 1;
+        else {
+            int kk = R.k + 1; uint32_t w = R.xn;
+            #pragma unroll 1
+            while (kk <= R.k1 && w == 0xffffffffu) { kk++; w = (kk <= R.k1) ? diag_word<C>(S, P, R.s, kk, R.lo, R.hi) : 0u; }
+            e = (kk <= R.k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (R.k1 + 1) - 1;
+            if (e > R.hi) e = R.hi;
+        }
+        R.skip_until = e;
+        return true;
+    }
+}
+
+// calls emit(a, e) for every maximal run of at least P.m cells of diagonal s
 template <class C, class F>
 __device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, const DevBatch &B, int s, F &&emit)
 {
-    int lo, hi;
-    if (!diag_range<C>(S, B, s, lo, hi)) return;
-    const int k0 = lo >> 5, k1 = hi >> 5;
-    const int m = P.m;
-    DiagWalk it;
-    walk_begin<C>(it, S, P, s, k0);
-    uint32_t x = walk_next<C>(it, S, P, s, lo, hi);
-    uint32_t prev_top = 0;
-    int skip_until = -1;                   // runs already emitted extend up to here
+    RunIter R;
+    runs_begin<C>(R, S, P, B, s, true);
+    int a, e;
     #pragma unroll 1
-    for (int k = k0; k <= k1; k++) {
-        uint32_t xn = (k < k1) ? walk_next<C>(it, S, P, s, lo, hi) : 0u;
-        if (x) {
-            uint32_t y = x;
-            for (int t = 1; t < m; t++) y &= __funnelshift_r(x, xn, t);
-            uint32_t starts = y & ~((x << 1) | prev_top);
-            #pragma unroll 1
-            while (starts) {
-                int b = __ffs(starts) - 1;
-                starts &= starts - 1;
-                int a = 32 * k + b;
-                if (a <= skip_until) continue;
-                // find the end of the run
-                int e;
-                uint32_t inv = ~(x >> b);            // bit 0 is 0; first set bit = run length
-                int t = inv ? __ffs(inv) - 1 : 32;
-                if (b + t < 32) e = a + t - 1;
-                else {
-                    int kk = k + 1; uint32_t w = xn;
-                    #pragma unroll 1
-                    while (kk <= k1 && w == 0xffffffffu) { kk++; w = (kk <= k1) ? diag_word<C>(S, P, s, kk, lo, hi) : 0u; }
-                    e = (kk <= k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (k1 + 1) - 1;
-                    if (e > hi) e = hi;
-                }
-                skip_until = e;
-                emit(a, e);
-            }
-        }
-        prev_top = x >> 31;
-        x = xn;
-    }
+    while (runs_next<C>(R, S, P, a, e)) emit(a, e);
 }
 
 // ------------------------------------------------------------- ScoreStems
@@ -1061,11 +1095,29 @@ __device__ __forceinline__ Best team_argmax(State &S, Best best)
     return best;
 }
 
-// Phase 2b for one survivor: ScoreStems' adjusted score; folds it into the
-// lane's running best.  Returns the adjusted score (-1e300 if below minfinscore).
-template <class C>
-__device__ __forceinline__ double consider(const State &S, const DevParams &P, uint32_t key, int len, double bps, Best &best)
+// Upper bound of the adjusted score of ANY candidate with raw score bps: every factor of
+// seq.py:732 replaced by its largest possible value, multiplied in the same order with the same
+// rounding.  Rounding is monotone, so fin <= bound holds exactly (not just approximately), which
+// makes skipping candidates whose bound is below the current best bit-exact.
+__device__ __forceinline__ double score_bound(const DevParams &P, double bps)
 {
+    if (!P.ub_ok || !(bps > 0.0)) return 1e300;
+    double u = __dmul_rn(bps, P.sdf_max);
+    u = __dmul_rn(u, P.of_max);
+    u = __dmul_rn(u, P.lf_max);
+    return __dmul_rn(u, 1.25);
+}
+
+// Phase 2b for one survivor: ScoreStems' adjusted score; folds it into the lane's running best.
+// Candidates that cannot reach `floor` (the best score so far, or the lower end of the subopt
+// range) are skipped without evaluating their region.  Returns the adjusted score (-1e300 if it
+// is below minfinscore or was skipped).
+template <class C>
+__device__ __forceinline__ double consider(const State &S, const DevParams &P, uint32_t key, int len, double bps,
+                                           double floor, Best &best)
+{
+    double ub = score_bound(P, bps);
+    if (ub < floor || ub < P.minfinscore) return -1e300;
     double fin = score_candidate<C>(S, P, (int)(key >> 16), (int)(key & 0xffff), len, bps);
     if (!(fin >= P.minfinscore)) return -1e300;
     if (better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
@@ -1076,88 +1128,160 @@ __device__ __forceinline__ double consider(const State &S, const DevParams &P, u
 // scores it (ScoreStems) and returns the team-wide best survivor: the head of
 // ChooseStems' stable sort.  fin = -1e300 when nothing reaches minfinscore.
 //
-// keep_all == false (TAIL): the run and survivor lists are flushed whenever they
-// fill up, so any number of candidates is handled with small lists.
-// keep_all == true (STEP): every survivor stays in the list with its adjusted
-// score in cfin[] for team_choose; misc[7] = number of survivors found (may
-// exceed Ccap: the caller then retries with a larger list).
+// Survivors of the bp-score filter collect in a list that is flushed whenever it
+// fills up.  A flush scores the new entries (skipping those whose upper bound
+// cannot matter), shares the team-wide best, and then
+//   subopt < 0 (TAIL): empties the list -- only the best is wanted;
+//   subopt >= 0 (STEP): keeps the entries with fin >= subopt * best so far.  The
+//     final range subopt * best can only be higher, so everything ChooseStems can
+//     return survives; misc[7] = entries kept, cfin[] their adjusted scores
+//     (misc[7] > Ccap: the in-range candidates alone overflow the list and the
+//     caller retries with a larger one).
 template <class C>
-__device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L, const bool keep_all)
+__device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L, const double subopt)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const bool keep = subopt >= 0.0;
     Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
-    if (r == 0) { S.misc[0] = 0; S.misc[7] = 0; }
+    if (r == 0) { S.misc[0] = 0; S.misc[6] = 0; S.misc[7] = 0; }
     Team<TW>::sync();
     const int smax = 2 * S.N - 6;
     const int Rcap = L.Rcap, Ccap = L.Ccap;
     const int rflush = Rcap - (Rcap >> 2);
-    int nsurv = 0;                         // survivors in the list (uniform; mirrored in misc[7] for TW > 1)
+    int nsurv = 0;                         // entries in the survivor list (uniform; mirrored in misc[7] for TW > 1)
+    int nkept = 0;                         // STEP: the first nkept entries are already scored
+    bool overflow = false;
 
     // phase 2b over the survivor list (team-uniform call)
     auto flush_survivors = [&]() {
         int ns = nsurv < Ccap ? nsurv : Ccap;
+        if (nsurv > Ccap) overflow = true;
         Team<TW>::sync();                  // the survivors stored by the other threads are visible
+        // TAIL: a candidate whose bound is below the best so far cannot win.  STEP: nor can it enter the
+        // subopt range (only used when the range lies below the best: subopt <= 1 and best > 0).
+        const double floor = !keep ? best.fin
+                           : (best.fin > 0.0 ? __dmul_rn(subopt < 1.0 ? subopt : 1.0, best.fin) : -1e300);
         #pragma unroll 1
-        for (int c = r; c < ns; c += T) {
-            double fin = consider<C>(S, P, S.ckey[c], S.clen[c], S.cbps[c], best);
-            if (keep_all) S.cfin[c] = fin;
+        for (int c = nkept + r; c < ns; c += T) {
+            double fin = consider<C>(S, P, S.ckey[c], S.clen[c], S.cbps[c], floor, best);
+            if (keep) S.cfin[c] = fin;
         }
-        Team<TW>::sync();
-        if (!keep_all) {
+        best = team_argmax<C>(S, best);    // every thread continues with the team-wide best (barrier)
+        if (!keep) {
             nsurv = 0;
             if (TW > 1) { if (r == 0) S.misc[7] = 0; Team<TW>::sync(); }
+            return;
         }
-    };
-    // phase 2a over the first nr entries of the run list (team-uniform call)
-    auto flush_runs = [&](int nr) {
+        // compact: keep what is still inside the subopt range (in place, rounds of T entries)
+        const double range = best.fin > -1e300 ? __dmul_rn(subopt, best.fin) : -1e300;
+        int nk = 0;
+        if (TW > 1) { if (r == 0) S.misc[6] = 0; Team<TW>::sync(); }
         #pragma unroll 1
-        for (int c0 = 0; c0 < nr; c0 += T) {
-            if (!keep_all && nsurv + T > Ccap) flush_survivors();
+        for (int c0 = 0; c0 < ns; c0 += T) {
             const int c = c0 + r;
-            bool push = false; uint32_t key = 0; int len = 0; double sc = 0.0;
-            if (c < nr) {
-                key = S.rkey[c]; len = S.rlen[c];
-                sc = run_score<C>(S, P, B, (int)(key >> 16), (int)(key & 0xffff), len);
-                push = sc >= P.minbpscore;
+            bool kp = false; uint32_t key = 0; uint16_t len = 0; double sc = 0.0, fin = 0.0;
+            if (c < ns) {
+                fin = S.cfin[c];
+                // the top candidate is always taken (seq.py:766), the others must be inside the range
+                kp = fin > -1e300 && (fin >= range || (fin == best.fin && S.ckey[c] == best.key));
+                if (kp) { key = S.ckey[c]; len = S.clen[c]; sc = S.cbps[c]; }
             }
             int slot;
-            int cnt = Team<TW>::claim(push, &S.misc[7], nsurv, slot);
-            if (push && slot < Ccap) { S.ckey[slot] = key; S.clen[slot] = (uint16_t)len; S.cbps[slot] = sc; }
-            nsurv += cnt;
+            int cnt = Team<TW>::claim(kp, &S.misc[6], nk, slot);     // barrier: this round's reads are done
+            if (kp) { S.ckey[slot] = key; S.clen[slot] = len; S.cbps[slot] = sc; S.cfin[slot] = fin; }
+            nk += cnt;
         }
         Team<TW>::sync();
-        if (r == 0) S.misc[0] = 0;
-        Team<TW>::sync();
+        nkept = nk; nsurv = nk;
+        if (TW > 1) { if (r == 0) S.misc[7] = nk; Team<TW>::sync(); }
+        if (nk + T > Ccap) overflow = true;        // the in-range entries alone (nearly) fill the list
+    };
+    // one survivor of phase 2a per thread (team-uniform call)
+    auto add_survivors = [&](bool push, uint32_t key, int len, double sc) {
+        int slot;
+        int cnt = Team<TW>::claim(push, &S.misc[7], nsurv, slot);
+        if (push && slot < Ccap) { S.ckey[slot] = key; S.clen[slot] = (uint16_t)len; S.cbps[slot] = sc; }
+        nsurv += cnt;
     };
 
-    #pragma unroll 1
-    for (int s0 = 4; s0 <= smax; s0 += T) {
-        const int s = s0 + r;
-        const bool last = s0 + T > smax;
-        int done = -1;                     // runs of this lane's diagonal starting at a <= done are in the list
-        for (;;) {
-            bool pending = false;          // the run list filled up before this lane's diagonal was finished
-            if (s <= smax)
-                enum_diag<C>(S, P, B, s, [&](int a, int e) {
-                    if (a <= done || pending) return;
-                    int len = e - a + 1;
-                    if ((double)len < P.minlen) return;
-                    int slot = atomicAdd(&S.misc[0], 1);
-                    if (slot < Rcap) { S.rkey[slot] = ((uint32_t)s << 16) | (uint32_t)a; S.rlen[slot] = (uint16_t)len; done = a; }
-                    else pending = true;
-                });
-            const bool anyp = Team<TW>::any(pending);
-            int nr = S.misc[0]; if (nr > Rcap) nr = Rcap;
-            Team<TW>::sync();             // every thread has read the count before anyone changes it again
-            if (nr >= rflush || last || anyp) flush_runs(nr);
-            if (!anyp) break;
+    if (!C::RUNLIST) {
+        // CTA teams (long sequences: hundreds of runs per diagonal): no run list.  Every thread
+        // walks its own diagonal and the team advances in rounds of one run per thread, so the
+        // survivor list can be flushed between rounds.
+        #pragma unroll 1
+        for (int s0 = 4; s0 <= smax; s0 += T) {
+            RunIter ri;
+            runs_begin<C>(ri, S, P, B, s0 + r, s0 + r <= smax);
+            #pragma unroll 1
+            for (;;) {
+                int a = 0, e = 0, len = 0;
+                bool has = false;
+                #pragma unroll 1
+                while (runs_next<C>(ri, S, P, a, e)) {
+                    len = e - a + 1;
+                    if ((double)len >= P.minlen) { has = true; break; }
+                }
+                bool push = false; uint32_t key = 0; double sc = 0.0;
+                if (has) {
+                    key = ((uint32_t)ri.s << 16) | (uint32_t)a;
+                    sc = run_score<C>(S, P, B, ri.s, a, len);
+                    push = sc >= P.minbpscore;
+                }
+                add_survivors(push, key, len, sc);
+                const bool more = Team<TW>::any(has);
+                if (nsurv + T > Ccap && !overflow) flush_survivors();
+                if (!more) break;
+            }
+        }
+    } else {
+        // warp teams: phase 1 fills a run list, phase 2a scores it with dense lanes
+        auto flush_runs = [&](int nr) {
+            #pragma unroll 1
+            for (int c0 = 0; c0 < nr; c0 += T) {
+                if (nsurv + T > Ccap && !overflow) flush_survivors();
+                const int c = c0 + r;
+                bool push = false; uint32_t key = 0; int len = 0; double sc = 0.0;
+                if (c < nr) {
+                    key = S.rkey[c]; len = S.rlen[c];
+                    sc = run_score<C>(S, P, B, (int)(key >> 16), (int)(key & 0xffff), len);
+                    push = sc >= P.minbpscore;
+                }
+                add_survivors(push, key, len, sc);
+            }
+            Team<TW>::sync();
+            if (r == 0) S.misc[0] = 0;
+            Team<TW>::sync();
+        };
+        #pragma unroll 1
+        for (int s0 = 4; s0 <= smax; s0 += T) {
+            const int s = s0 + r;
+            const bool last = s0 + T > smax;
+            int done = -1;                     // runs of this lane's diagonal starting at a <= done are in the list
+            #pragma unroll 1
+            for (;;) {
+                bool pending = false;          // the run list filled up before this lane's diagonal was finished
+                if (s <= smax)
+                    enum_diag<C>(S, P, B, s, [&](int a, int e) {
+                        if (a <= done || pending) return;
+                        int len = e - a + 1;
+                        if ((double)len < P.minlen) return;
+                        int slot = atomicAdd(&S.misc[0], 1);
+                        if (slot < Rcap) { S.rkey[slot] = ((uint32_t)s << 16) | (uint32_t)a; S.rlen[slot] = (uint16_t)len; done = a; }
+                        else pending = true;
+                    });
+                const bool anyp = Team<TW>::any(pending);
+                int nr = S.misc[0]; if (nr > Rcap) nr = Rcap;
+                Team<TW>::sync();             // every thread has read the count before anyone changes it again
+                if (nr >= rflush || last || anyp) flush_runs(nr);
+                if (!anyp) break;
+            }
         }
     }
-    flush_survivors();
-    if (r == 0) S.misc[7] = nsurv;
+    if (!overflow) flush_survivors();
+    if (r == 0) S.misc[7] = overflow ? 0x7fffffff : nsurv;
     Team<TW>::sync();
-    return team_argmax<C>(S, best);
+    return best;
 }
 
 // two stems are "in conflict" when they share a paired position (seq.py:783-786)
@@ -1190,13 +1314,13 @@ __device__ int team_choose(State &S, const Layout &L, const Best &best, double s
     #pragma unroll 1
     for (int c = r; c < ntot; c += T) {
         double f = S.cfin[c];
-        if (f <= -1e300 || f < range) continue;
         uint32_t k = S.ckey[c];
+        if (f <= -1e300 || (f < range && !(f == best.fin && k == best.key))) continue;
         int rank = 0;
         #pragma unroll 1
         for (int d = 0; d < ntot; d++) {
             double g = S.cfin[d];
-            if (g <= -1e300 || g < range) continue;
+            if (g <= -1e300 || (g < range && !(g == best.fin && S.ckey[d] == best.key))) continue;
             if (better(g, S.ckey[d], f, k)) rank++;
         }
         if (rank < L.Ocap) ord[rank] = (int16_t)c;
@@ -1403,7 +1527,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         #pragma unroll 1
         while (mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
-            Best b = team_scan<C>(S, P, B, L, false);
+            Best b = team_scan<C>(S, P, B, L, -1.0);
             calls++;
             if (b.fin <= -1e300) break;
             int i = (int)(b.key & 0xffff);
@@ -1415,7 +1539,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
         if ((double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
-            Best b = team_scan<C>(S, P, B, L, true);
+            Best b = team_scan<C>(S, P, B, L, Wk.item_subopt[item]);
             calls++;
             n = team_choose<C>(S, L, b, Wk.item_subopt[item], Wk.out_stems + 3 * so,
                                 Wk.out_stemfin ? Wk.out_stemfin + so : nullptr, (int)cap);

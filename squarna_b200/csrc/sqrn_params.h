@@ -90,6 +90,26 @@ inline bool build_host_params(const sqrn_paramset &ps, int nmax, HostParams &H, 
     for (int o = 0; o < P.of_n; o++) H.lut.push_back(pow(1.0 / (double)(1 + o), ps.orderpenalty));
     H.pw17_off = H.lut.size();
     for (int k = 0; k < P.pw17_n; k++) H.lut.push_back(pow(0.5 * k, 1.7));
+    // factor maxima for score_bound(): valid when every factor comes from the tables above
+    P.ub_ok = P.bw_is_int ? 1 : 0;
+    P.sdf_max = 1.0;                                   // "between chains" gives exactly 1 (SQRNdbnseq.py:723)
+    for (int k = 0; k < P.sdf_n; k++) if (H.lut[H.sdf_off + k] > P.sdf_max) P.sdf_max = H.lut[H.sdf_off + k];
+    P.of_max = 0.0;
+    for (int o = 0; o < P.of_n; o++) if (H.lut[H.of_off + o] > P.of_max) P.of_max = H.lut[H.of_off + o];
+    if (!(P.sdf_max < 1e300) || !(P.of_max < 1e300) || !(P.of_max > 0.0)) P.ub_ok = 0;
+    // loopfactor = 1 + lb*g1*(2 - d1/2) + lb*g2*(2 - d2/2), g in {0,1}, (2 - d/2) in {2, 1.5, 1} (SQRNdbnseq.py:715)
+    {
+        double lb = ps.loopbonus, best = 1.0;
+        const double cs[4] = { 0.0, 2.0, 1.5, 1.0 };   // 0.0 = no good loop
+        for (int x = 0; x < 4; x++)
+            for (int y = 0; y < 4; y++) {
+                double lf = 1.0 + (lb * (x ? 1.0 : 0.0)) * (x ? cs[x] : 2.0);
+                lf = lf + (lb * (y ? 1.0 : 0.0)) * (y ? cs[y] : 2.0);
+                if (lf > best) best = lf;
+            }
+        P.lf_max = best;
+        if (!(best < 1e300)) P.ub_ok = 0;
+    }
     return true;
 }
 

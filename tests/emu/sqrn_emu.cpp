@@ -52,8 +52,9 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
         State S = bind_state(smem, Lay);
         if (flavour == 1) {            // the fast-lane flavour (plain batch, standard pairing table, MODE_TAIL)
             if (!H.p.std_pairs || rcode || rclass || rbp_off || smat || interchainonly || mode != MODE_TAIL) { free(smem); return -2; }
-            team_run_item<Cfg<0, true, true, MODE_TAIL>>(S, H.p, B, W, Lay, item);
-        } else team_run_item<Cfg<0>>(S, H.p, B, W, Lay, item);
+            team_run_item<Cfg<0, true, true, MODE_TAIL, 1>>(S, H.p, B, W, Lay, item);
+        } else if (flavour == 2) team_run_item<Cfg<0, false, false, -1, 1>>(S, H.p, B, W, Lay, item);   // run-list scan
+        else team_run_item<Cfg<0>>(S, H.p, B, W, Lay, item);                                              // per-thread rounds
     }
     free(smem);
     return 0;

@@ -30,7 +30,7 @@ def _prep_batch(cases):
     return preps, kw
 
 
-@pytest.mark.parametrize("region", [0, 1, 2, "fast"], ids=["auto", "scan", "stems", "fastflavour"])
+@pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist"], ids=["auto", "scan", "stems", "fastflavour", "runlist"])
 @pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
                          ids=["fastest", "defG1", "defG2-smalllist", "ali"])
 def test_tail_plain(ps, ccap, region):
@@ -39,6 +39,8 @@ def test_tail_plain(ps, ccap, region):
     seqs = T.rand_seqs(31, 150, 5, 210) + T.rand_seqs(36, 40, 5, 150, "ACGUN")
     if region == "fast":       # compile-time flavour of the byseq fast lane: bit planes, stem walk only
         r = emu.run(ps, seqs, ccap=ccap, flavour=1)
+    elif region == "runlist":  # the warp-team scan (shared run list) of the general flavour
+        r = emu.run(ps, seqs, ccap=ccap, flavour=2)
     else:
         r = emu.run(ps, seqs, ccap=ccap, region_mode=region)
     for b, s in enumerate(seqs):
@@ -51,9 +53,9 @@ def test_tail_plain(ps, ccap, region):
         assert bool(r["flags"][b] & 1) == isint
 
 
-@pytest.mark.parametrize("region", [1, 2], ids=["scan", "stems"])
+@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2)], ids=["scan", "stems", "runlist"])
 @pytest.mark.parametrize("interchain", [False, True])
-def test_tail_with_restraints_and_reactivities(interchain, region):
+def test_tail_with_restraints_and_reactivities(interchain, region, flavour):
     rng = random.Random(32)
     cases = [T.rand_case(rng, 8, 150, p_gap=0.2) for _ in range(200)]
     preps, kw = _prep_batch(cases)
@@ -62,7 +64,7 @@ def test_tail_with_restraints_and_reactivities(interchain, region):
         sub = {k: [v[i] for i in idx] if isinstance(v, list) else v for k, v in kw.items()}
         for ps in (T.DEFG1, T.FASTEST):
             r = emu.run(ps, [preps[k].shortseq for k in idx], react_comp=comp, interchainonly=interchain,
-                            region_mode=region, **sub)
+                            region_mode=region, flavour=flavour, **sub)
             for b, k in enumerate(idx):
                 p = preps[k]
                 _, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, [ps], interchainonly=interchain,
