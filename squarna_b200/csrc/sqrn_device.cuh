@@ -137,7 +137,7 @@ struct DevWork {
 struct Layout {
     int Ncap, W, WR, Scap, RBcap, Rcap, Ccap, Ocap, npc;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
-        o_sti, o_stj, o_stl, o_stlev, o_ssi, o_ssj, o_ssl, o_sslev, o_byi, o_cc, o_perm, o_grp, o_gsz,
+        o_sti, o_stj, o_stl, o_stlev, o_evpos, o_evid, o_cc, o_perm, o_grp, o_gsz,
         o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_misc, total;
 };
 
@@ -185,10 +185,8 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_sti = o;     o += 2 * L.Scap;
     L.o_stj = o;     o += 2 * L.Scap;
     L.o_stl = o;     o += 2 * L.Scap;
-    L.o_ssi = o;     o += 2 * L.Scap;
-    L.o_ssj = o;     o += 2 * L.Scap;
-    L.o_ssl = o;     o += 2 * L.Scap;
-    L.o_byi = o;     o += 2 * L.Scap;
+    L.o_evpos = o;   o += 4 * L.Scap;                     // two arm events per stem
+    L.o_evid = o;    o += 4 * L.Scap;
     L.o_rbv = o;     o += 2 * (RBmax + 1);
     L.o_rbw = o;     o += 2 * (RBmax + 1);
     L.o_clen = o;    o += 2 * Ccap;
@@ -196,7 +194,6 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_code = o;    o += L.Ncap;
     L.o_rcl = o;     o += L.Ncap;
     L.o_stlev = o;   o += L.Scap;
-    L.o_sslev = o;   o += L.Scap;
     L.total = align_up(o, 16);
     return L;
 }
@@ -232,6 +229,12 @@ template <int TW> struct Team {
         if (TW == 1) { bool a = __any_sync(0xffffffffu, p); __syncwarp(); return a; }
         return __syncthreads_or(p) != 0;
     }
+    // number of threads with p set (barrier)
+    __device__ static __forceinline__ int count(bool p)
+    {
+        if (TW == 1) { int c = __popc(__ballot_sync(0xffffffffu, p)); __syncwarp(); return c; }
+        return __syncthreads_count(p);
+    }
     // Threads with p set claim consecutive slots starting at `base` (uniform); returns how many did.
     // TW > 1 uses the team-shared `counter`, which the caller keeps equal to `base` between calls.
     __device__ static __forceinline__ int claim(bool p, int *counter, int base, int &slot)
@@ -253,6 +256,7 @@ template <> struct Team<0> {
     static inline int rank() { return 0; }
     static inline void sync() {}
     static inline bool any(bool p) { return p; }
+    static inline int count(bool p) { return p ? 1 : 0; }
     static inline int claim(bool p, int *, int base, int &slot) { slot = base; return p ? 1 : 0; }
 };
 #endif
@@ -275,9 +279,9 @@ struct Cfg {
 
 struct State {
     int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts, region_mode;
-    uint8_t  *code, *rcl, *stlev, *sslev;
+    uint8_t  *code, *rcl, *stlev;
     uint16_t *rcode;
-    int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *ssi, *ssj, *ssl, *byi, *perm, *grp, *rbv, *rbw;
+    int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *evpos, *evid, *perm, *grp, *rbv, *rbw;
     uint32_t *M, *PR, *rowok, *colokR, *Ub, *ckey, *rkey;
     int32_t  *cc, *gsz, *Ubase;
     uint16_t *clen, *rlen;
@@ -290,12 +294,11 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
 {
     State s;
     s.code = base + L.o_code;  s.rcode = (uint16_t *)(base + L.o_rcode);  s.rcl = base + L.o_rcl;
-    s.stlev = base + L.o_stlev;  s.sslev = base + L.o_sslev;
+    s.stlev = base + L.o_stlev;
     s.partner = (int16_t *)(base + L.o_partner);  s.owner = (int16_t *)(base + L.o_owner);
     s.sepcnt = (int16_t *)(base + L.o_sepcnt);
     s.sti = (int16_t *)(base + L.o_sti);  s.stj = (int16_t *)(base + L.o_stj);  s.stl = (int16_t *)(base + L.o_stl);
-    s.ssi = (int16_t *)(base + L.o_ssi);  s.ssj = (int16_t *)(base + L.o_ssj);  s.ssl = (int16_t *)(base + L.o_ssl);
-    s.byi = (int16_t *)(base + L.o_byi);
+    s.evpos = (int16_t *)(base + L.o_evpos);  s.evid = (int16_t *)(base + L.o_evid);
     s.perm = (int16_t *)(base + L.o_perm);  s.grp = (int16_t *)(base + L.o_grp);
     s.rbv = (int16_t *)(base + L.o_rbv);  s.rbw = (int16_t *)(base + L.o_rbw);
     s.M = (uint32_t *)(base + L.o_M);  s.PR = (uint32_t *)(base + L.o_PR);
@@ -525,21 +528,34 @@ __device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = 
         atomicAnd(&S.colokR[rv >> 5], ~(1u << (rv & 31)));
         atomicAnd(&S.colokR[rw >> 5], ~(1u << (rw & 31)));
     }
-    // insert into the 5'-sorted order: entries with a larger i move up by one
-    int pos = 0;
-    #pragma unroll 1
-    for (int q = 0; q < idx; q++) pos += (S.sti[S.byi[q]] < i);       // idx is small; every thread counts
+    // two arm events (first position of the 5' arm and of the 3' arm) go into the position-sorted
+    // event list that ScoreStems walks: entries behind them move up by one or two
+    const int ne = 2 * idx, p1 = i, p2 = j - len + 1;
+    int r1, r2;
+    {
+        int lo_ = 0, hi_ = ne;
+        #pragma unroll 1
+        while (lo_ < hi_) { int mid = (lo_ + hi_) >> 1; if (S.evpos[mid] < p1) lo_ = mid + 1; else hi_ = mid; }
+        r1 = lo_; hi_ = ne;
+        #pragma unroll 1
+        while (lo_ < hi_) { int mid = (lo_ + hi_) >> 1; if (S.evpos[mid] < p2) lo_ = mid + 1; else hi_ = mid; }
+        r2 = lo_;
+    }
     Team<TW>::sync();
     #pragma unroll 1
-    for (int q0 = 0; q0 < idx; q0 += T) {            // shift in chunks from the top so reads precede overwrites
-        int q = idx - 1 - q0 - r;
-        int16_t v = 0; bool mv = q >= pos && q >= 0;
-        if (mv) v = S.byi[q];
+    for (int q0 = 0; q0 < ne; q0 += T) {             // from the top, so reads precede overwrites
+        const int q = ne - 1 - q0 - r;
+        int16_t vp = 0, vi = 0; const bool mv = q >= r1;
+        if (mv) { vp = S.evpos[q]; vi = S.evid[q]; }
         Team<TW>::sync();
-        if (mv) S.byi[q + 1] = v;
+        if (mv) { int d = q >= r2 ? 2 : 1; S.evpos[q + d] = vp; S.evid[q + d] = vi; }
         Team<TW>::sync();
     }
-    if (r == 0) { S.sti[idx] = (int16_t)i; S.stj[idx] = (int16_t)j; S.stl[idx] = (int16_t)len; S.byi[pos] = (int16_t)idx; }
+    if (r == 0) {
+        S.sti[idx] = (int16_t)i; S.stj[idx] = (int16_t)j; S.stl[idx] = (int16_t)len;
+        S.evpos[r1] = (int16_t)p1; S.evid[r1] = (int16_t)(2 * idx);
+        S.evpos[r2 + 1] = (int16_t)p2; S.evid[r2 + 1] = (int16_t)(2 * idx + 1);
+    }
     S.nst = idx + 1;
     Team<TW>::sync();
     if (refresh) team_unpaired_prefix<C>(S);
@@ -551,8 +567,7 @@ __device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = 
 // outermost pairs, cross_count is the summed length of the crossing stems, the
 // first-fit order is (cross_count, outer i) and groups are ranked by their
 // number of pairs (stable).  tests/test_emu_vs_oracle.py checks this against the
-// oracle's per-pair restatement.  Also refreshes the 5'-sorted stem copies
-// (ssi, ssj, ssl, sslev) the stem-walk of ScoreStems reads.
+// oracle's per-pair restatement.
 __device__ __forceinline__ bool stems_cross(int i, int j, int k, int l)
 {
     return (i < k && k < j && j < l) || (k < i && i < l && l < j);
@@ -634,12 +649,6 @@ __device__ int team_levels(State &S)
         Team<TW>::sync();
         ng = S.misc[5];
     }
-    #pragma unroll 1
-    for (int q = r; q < n; q += T) {
-        int t = S.byi[q];
-        S.ssi[q] = S.sti[t]; S.ssj[q] = S.stj[t]; S.ssl[q] = S.stl[t]; S.sslev[q] = S.stlev[t];
-    }
-    Team<TW>::sync();
     return ng;
 }
 
@@ -925,62 +934,56 @@ __device__ __forceinline__ void region_scan(const State &S, int ss, int se, Regi
     R.between = between; R.levmask = levmask;
 }
 
-// The same quantities from a walk over the selected stems in 5' order.  ss and se
-// are unpaired, so each arm of a selected stem lies entirely inside or entirely
-// outside (ss, se):
-//   both arms inside  -> its outermost pair is the only one that can raise
-//                        inblockend (the inner pairs close earlier); merged spans
-//                        of such stems are the "blocks";
-//   one arm inside    -> `len` bracket positions, counted (with the stem's level)
-//                        unless a block covers the arm;
-//   dots              =  unpaired positions of the region outside the blocks
-//                        (prefix popcounts of the unpaired mask).
-// An arm (a contiguous range of paired positions of ONE stem) cannot straddle a
-// block boundary (a paired position of ANOTHER stem), so testing its first
-// position is enough.  5' arms meet the blocks in walk order; a 3' arm whose 5'
-// arm lies left of ss is checked against the inner stems directly (these are
-// exactly the stems the candidate would cross: rare).
+// The same quantities from a walk over the ARMS of the selected stems that lie inside the
+// region, in position order (binary search to the first one).  ss and se are unpaired, so each
+// arm of a selected stem lies entirely inside or entirely outside (ss, se):
+//   5' arm inside, 3' arm inside  -> an "inner" stem: its outermost pair is the only one that can
+//                        raise inblockend (its inner pairs close earlier); the merged spans of
+//                        inner stems are the "blocks";
+//   exactly one arm inside        -> `len` bracket positions, counted (with the stem's level)
+//                        unless a block covers the arm: inblockend at the arm's first position
+//                        is the largest 3' end among the inner stems opened before it -- all of
+//                        them have been met by then, because events come in position order;
+//   dots              =  unpaired positions of the region outside the blocks (prefix popcounts of
+//                        the unpaired mask).
+// An arm (a contiguous range of paired positions of ONE stem) cannot straddle a block boundary (a
+// paired position of ANOTHER stem), so testing its first position is enough.
 __device__ __forceinline__ void region_stems(const State &S, int ss, int se, Region &R)
 {
-    const int n = S.nst;
+    const int ne = 2 * S.nst;
     int br = 0, nedges = 0, e0 = -1, e1 = -1, ibe = -1, blo = 0, covU = 0;
     unsigned long long levmask = 0;
+    int q = 0;
+    {
+        int hi_ = ne;
+        #pragma unroll 1
+        while (q < hi_) { int mid = (q + hi_) >> 1; if (S.evpos[mid] <= ss) q = mid + 1; else hi_ = mid; }
+    }
     #pragma unroll 1
-    for (int q = 0; q < n; q++) {
-        const int i = S.ssi[q];
-        if (i > se) break;                              // sorted by i: nothing further can reach the region
-        const int j = S.ssj[q];
-        const bool ain = i > ss, bin = j > ss && j < se; // i < se holds here (i != se: se is unpaired)
-        if (ain && bin) {
-            if (j > ibe) {
-                if (nedges == 0) { e0 = i; e1 = j; }
-                nedges++;
-                if (i > ibe) {                          // a new block starts: close the previous one
-                    if (ibe >= 0) covU += unpaired_before(S, ibe + 1) - unpaired_before(S, blo);
-                    blo = i;
+    for (; q < ne; q++) {
+        const int x = S.evpos[q];
+        if (x > se) break;
+        const int id = S.evid[q], t = id >> 1;
+        const int i = S.sti[t], j = S.stj[t];
+        if (!(id & 1)) {                                // 5' arm, x == i
+            if (j < se) {                               // inner stem
+                if (j > ibe) {
+                    if (nedges == 0) { e0 = i; e1 = j; }
+                    nedges++;
+                    if (i > ibe) {                      // a new block starts: close the previous one
+                        if (ibe >= 0) covU += unpaired_before(S, ibe + 1) - unpaired_before(S, blo);
+                        blo = i;
+                    }
+                    ibe = j;
                 }
-                ibe = j;
+                continue;
             }
-        } else if (ain) {                               // 5' arm inside, partner beyond se
-            if (i > ibe) {
-                br += S.ssl[q];
-                int lv = S.sslev[q];
-                levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
-            }
-        } else if (bin) {                               // 3' arm inside, 5' arm left of ss
-            const int x = j - S.ssl[q] + 1;
-            bool covered = false;
-            #pragma unroll 1
-            for (int u = q + 1; u < n && !covered; u++) {
-                int iu = S.ssi[u];
-                if (iu >= x) break;
-                if (iu > ss && S.ssj[u] < se && S.ssj[u] > x) covered = true;
-            }
-            if (!covered) {
-                br += S.ssl[q];
-                int lv = S.sslev[q];
-                levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
-            }
+        } else if (i > ss) continue;                    // 3' arm of an inner stem
+        // one-armed: 5' arm with the partner beyond se, or 3' arm with the partner left of ss
+        if (x > ibe) {
+            br += S.stl[t];
+            int lv = S.stlev[t];
+            levmask |= 1ull << (lv > 63 ? 63 : lv - 1);
         }
     }
     if (ibe >= 0) covU += unpaired_before(S, ibe + 1) - unpaired_before(S, blo);
@@ -990,8 +993,6 @@ __device__ __forceinline__ void region_stems(const State &S, int ss, int se, Reg
     R.levmask = levmask;
 }
 
-// adjusted score of candidate (outer pair (a, s-a), length len, raw score bps)
-// given the current structure; seq.py:641-745.
 // pow() outside the host-built tables (never on the shipped parameter sets): kept out of line
 __device__ SQRN_NOINLINE double slow_pow(double a, double b) { return pow(a, b); }
 
@@ -1008,8 +1009,7 @@ __device__ __forceinline__ double score_candidate(const State &S, const DevParam
     } else {
         // the fast-lane flavour carries only the stem walk (smaller code); otherwise the cheaper
         // of the two is picked per candidate unless a test forces one
-        bool by_stems = C::PLAIN || S.region_mode == REGION_STEMS ||
-                        (S.region_mode == REGION_AUTO && 5 * S.nst < 2 * (se - ss));
+        bool by_stems = C::PLAIN || S.region_mode != REGION_SCAN;
         if (by_stems) region_stems(S, ss, se, R); else region_scan(S, ss, se, R);
     }
     // good loops = {0..4}^2 with |x - y| <= 2 (the 19 entries of seq.py:615-622)
@@ -1155,9 +1155,10 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
 
     // phase 2b over the survivor list (team-uniform call)
     auto flush_survivors = [&]() {
+        Team<TW>::sync();                  // the survivors stored by the other threads are visible
+        if (!C::RUNLIST) nsurv = S.misc[7];            // exact count (the rounds only track an upper bound)
         int ns = nsurv < Ccap ? nsurv : Ccap;
         if (nsurv > Ccap) overflow = true;
-        Team<TW>::sync();                  // the survivors stored by the other threads are visible
         // TAIL: a candidate whose bound is below the best so far cannot win.  STEP: nor can it enter the
         // subopt range (only used when the range lies below the best: subopt <= 1 and best > 0).
         const double floor = !keep ? best.fin
@@ -1170,7 +1171,7 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
         best = team_argmax<C>(S, best);    // every thread continues with the team-wide best (barrier)
         if (!keep) {
             nsurv = 0;
-            if (TW > 1) { if (r == 0) S.misc[7] = 0; Team<TW>::sync(); }
+            if (TW > 1 || !C::RUNLIST) { Team<TW>::sync(); if (r == 0) S.misc[7] = 0; Team<TW>::sync(); }
             return;
         }
         // compact: keep what is still inside the subopt range (in place, rounds of T entries)
@@ -1194,7 +1195,7 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
         }
         Team<TW>::sync();
         nkept = nk; nsurv = nk;
-        if (TW > 1) { if (r == 0) S.misc[7] = nk; Team<TW>::sync(); }
+        if (TW > 1 || !C::RUNLIST) { if (r == 0) S.misc[7] = nk; Team<TW>::sync(); }
         if (nk + T > Ccap) overflow = true;        // the in-range entries alone (nearly) fill the list
     };
     // one survivor of phase 2a per thread (team-uniform call)
@@ -1228,10 +1229,15 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
                     sc = run_score<C>(S, P, B, ri.s, a, len);
                     push = sc >= P.minbpscore;
                 }
-                add_survivors(push, key, len, sc);
-                const bool more = Team<TW>::any(has);
+                if (push) {
+                    int slot = atomicAdd(&S.misc[7], 1);
+                    if (slot < Ccap) { S.ckey[slot] = key; S.clen[slot] = (uint16_t)len; S.cbps[slot] = sc; }
+                }
+                // one barrier per round: the number of threads that had a run bounds the new survivors
+                const int nh = Team<TW>::count(has);
+                nsurv += nh;
                 if (nsurv + T > Ccap && !overflow) flush_survivors();
-                if (!more) break;
+                if (nh == 0) break;
             }
         }
     } else {
