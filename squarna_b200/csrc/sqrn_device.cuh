@@ -886,15 +886,49 @@ __device__ __forceinline__ bool runs_next(RunIter &R, const State &S, const DevP
     }
 }
 
-// calls emit(a, e) for every maximal run of at least P.m cells of diagonal s
+// Non-resumable form of the same walk: calls emit(a, e) for every maximal run of at least P.m
+// cells of diagonal s.  Kept separate from RunIter because its word loop is uniform across the
+// lanes of a warp (every lane steps its diagonal one word at a time), which the warp-team scan
+// relies on for lane utilisation.
 template <class C, class F>
 __device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, const DevBatch &B, int s, F &&emit)
 {
-    RunIter R;
-    runs_begin<C>(R, S, P, B, s, true);
-    int a, e;
+    int lo, hi;
+    if (!diag_range<C>(S, B, s, lo, hi)) return;
+    const int k0 = lo >> 5, k1 = hi >> 5;
+    DiagWalk it;
+    walk_begin<C>(it, S, P, s, k0);
+    uint32_t x = walk_next<C>(it, S, P, s, lo, hi);
+    uint32_t prev_top = 0;
+    int skip_until = -1;                   // runs already emitted extend up to here
     #pragma unroll 1
-    while (runs_next<C>(R, S, P, a, e)) emit(a, e);
+    for (int k = k0; k <= k1; k++) {
+        uint32_t xn = (k < k1) ? walk_next<C>(it, S, P, s, lo, hi) : 0u;
+        uint32_t starts = run_starts(x, xn, prev_top, P.m);
+        #pragma unroll 1
+        while (starts) {
+            int b = __ffs(starts) - 1;
+            starts &= starts - 1;
+            int a = 32 * k + b;
+            if (a <= skip_until) continue;
+            // find the end of the run
+            int e;
+            uint32_t inv = ~(x >> b);            // bit 0 is 0; first set bit = run length
+            int t = inv ? __ffs(inv) - 1 : 32;
+            if (b + t < 32) e = a + t - 1;
+            else {
+                int kk = k + 1; uint32_t w = xn;
+                #pragma unroll 1
+                while (kk <= k1 && w == 0xffffffffu) { kk++; w = (kk <= k1) ? diag_word<C>(S, P, s, kk, lo, hi) : 0u; }
+                e = (kk <= k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (k1 + 1) - 1;
+                if (e > hi) e = hi;
+            }
+            skip_until = e;
+            emit(a, e);
+        }
+        prev_top = x >> 31;
+        x = xn;
+    }
 }
 
 // ------------------------------------------------------------- ScoreStems
@@ -1156,16 +1190,41 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
     // phase 2b over the survivor list (team-uniform call)
     auto flush_survivors = [&]() {
         Team<TW>::sync();                  // the survivors stored by the other threads are visible
-        if (!C::RUNLIST) nsurv = S.misc[7];            // exact count (the rounds only track an upper bound)
+        if (!C::RUNLIST) {
+            // the shared counter also counts threads that found the list full and parked with their run
+            nsurv = S.misc[7];
+            if (nsurv > Ccap && !overflow) nsurv = Ccap;
+        }
         int ns = nsurv < Ccap ? nsurv : Ccap;
         if (nsurv > Ccap) overflow = true;
         // TAIL: a candidate whose bound is below the best so far cannot win.  STEP: nor can it enter the
         // subopt range (only used when the range lies below the best: subopt <= 1 and best > 0).
-        const double floor = !keep ? best.fin
-                           : (best.fin > 0.0 ? __dmul_rn(subopt < 1.0 ? subopt : 1.0, best.fin) : -1e300);
+        auto floor_of = [&](const Best &b) {
+            return !keep ? b.fin : (b.fin > 0.0 ? __dmul_rn(subopt < 1.0 ? subopt : 1.0, b.fin) : -1e300);
+        };
+        double first = -1e300;             // entries with at least this raw score are scored in a first pass
+        if (!C::RUNLIST && best.fin <= -1e300 && ns - nkept > T) {
+            // nothing to bound against yet: score the entries with the highest raw scores first, so that
+            // the bound can dismiss most of the others (each entry is still scored at most once)
+            Best q; q.fin = -1e300; q.key = 0; q.len = 0;
+            #pragma unroll 1
+            for (int c = nkept + r; c < ns; c += T) { double b = S.cbps[c]; if (b > q.fin) q.fin = b; }
+            q = team_argmax<C>(S, q);
+            first = q.fin > 0.0 ? __dmul_rn(q.fin, 0.7) : -1e300;
+            #pragma unroll 1
+            for (int c = nkept + r; c < ns; c += T) {
+                double b = S.cbps[c];
+                if (!(b >= first)) continue;
+                double fin = consider<C>(S, P, S.ckey[c], S.clen[c], b, floor_of(best), best);
+                if (keep) S.cfin[c] = fin;
+            }
+            best = team_argmax<C>(S, best);
+        }
         #pragma unroll 1
         for (int c = nkept + r; c < ns; c += T) {
-            double fin = consider<C>(S, P, S.ckey[c], S.clen[c], S.cbps[c], floor, best);
+            double b = S.cbps[c];
+            if (first > -1e300 && b >= first) continue;          // done in the first pass
+            double fin = consider<C>(S, P, S.ckey[c], S.clen[c], b, floor_of(best), best);
             if (keep) S.cfin[c] = fin;
         }
         best = team_argmax<C>(S, best);    // every thread continues with the team-wide best (barrier)
@@ -1207,37 +1266,39 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
     };
 
     if (!C::RUNLIST) {
-        // CTA teams (long sequences: hundreds of runs per diagonal): no run list.  Every thread
-        // walks its own diagonal and the team advances in rounds of one run per thread, so the
-        // survivor list can be flushed between rounds.
+        // CTA teams (long sequences: hundreds of runs per diagonal): no run list.  Every thread walks
+        // its own diagonal at its own pace and appends the runs that pass the bp-score filter to the
+        // survivor list; when the list is full the thread parks (keeping the run it could not store).
+        // The team meets at a barrier only when every thread is parked or done, flushes the list
+        // and resumes: barriers per scan = list fills + diagonals / T.
         #pragma unroll 1
         for (int s0 = 4; s0 <= smax; s0 += T) {
             RunIter ri;
             runs_begin<C>(ri, S, P, B, s0 + r, s0 + r <= smax);
+            bool done = !ri.live, carry = false;
+            uint32_t ckey_ = 0; int clen_ = 0; double csc_ = 0.0;
             #pragma unroll 1
             for (;;) {
-                int a = 0, e = 0, len = 0;
-                bool has = false;
                 #pragma unroll 1
-                while (runs_next<C>(ri, S, P, a, e)) {
-                    len = e - a + 1;
-                    if ((double)len >= P.minlen) { has = true; break; }
-                }
-                bool push = false; uint32_t key = 0; double sc = 0.0;
-                if (has) {
-                    key = ((uint32_t)ri.s << 16) | (uint32_t)a;
-                    sc = run_score<C>(S, P, B, ri.s, a, len);
-                    push = sc >= P.minbpscore;
-                }
-                if (push) {
+                while (!done || carry) {
+                    if (!carry) {
+                        if (*(volatile int *)&S.misc[7] >= Ccap && !overflow) break;       // list full: park
+                        int a, e;
+                        if (!runs_next<C>(ri, S, P, a, e)) { done = true; break; }
+                        int len = e - a + 1;
+                        if ((double)len < P.minlen) continue;
+                        double sc = run_score<C>(S, P, B, ri.s, a, len);
+                        if (!(sc >= P.minbpscore)) continue;
+                        ckey_ = ((uint32_t)ri.s << 16) | (uint32_t)a; clen_ = len; csc_ = sc;
+                    }
                     int slot = atomicAdd(&S.misc[7], 1);
-                    if (slot < Ccap) { S.ckey[slot] = key; S.clen[slot] = (uint16_t)len; S.cbps[slot] = sc; }
+                    if (slot < Ccap) { S.ckey[slot] = ckey_; S.clen[slot] = (uint16_t)clen_; S.cbps[slot] = csc_; carry = false; }
+                    else if (overflow) carry = false;          // STEP list overflow: the result is discarded anyway
+                    else { carry = true; break; }              // lost the race for the last slots: park with the run
                 }
-                // one barrier per round: the number of threads that had a run bounds the new survivors
-                const int nh = Team<TW>::count(has);
-                nsurv += nh;
-                if (nsurv + T > Ccap && !overflow) flush_survivors();
-                if (nh == 0) break;
+                const int nd = Team<TW>::count(done && !carry);          // barrier
+                flush_survivors();
+                if (nd == T) break;
             }
         }
     } else {
