@@ -147,6 +147,9 @@ SQRN_API int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
  * the selected stems.  All settings give identical results; tests force each one.             */
 #define SQRN_TUNE_REGION 1
 #define SQRN_TUNE_NO_FAST_KERNEL 2   /* 1: the fast lane uses the general kernel instead of the specialised one */
+#define SQRN_TUNE_CLUSTER 3          /* long sequences (> 2048 nt, run to completion): 0 automatic (a thread-block
+                                        cluster per sequence when there are too few to fill the SMs one CTA each),
+                                        1 never, 2/4/8/16 always with this cluster size */
 SQRN_API int  sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value);
 
 /* The full "G" path for a batch: replaces SQRNdbnseq.py:1048-1246 (algos == {"G"},

@@ -60,6 +60,8 @@ def main():
         leg_tail("c5 1000nobpp G pl=1", rand_seqs(rng, a.n, a.lo or 2900, a.hi or 5000), gsets("1000nobpp")[0], a.oracle)
     elif a.leg == "mid":
         leg_tail("mid fastest pl=1", rand_seqs(rng, a.n, a.lo or 300, a.hi or 1500), gsets("fastest")[0], a.oracle)
+    elif a.leg == "c4":
+        leg_alignment(a.n, a.lo or 300, a.hi or 400)
     elif a.leg == "c3":
         seqs = rand_seqs(rng, a.n, a.lo or 300, a.hi or 1500)
         entries = []
@@ -87,6 +89,61 @@ def main():
                               "nt2_per_s": float((lens ** 2).sum()) / dt, "launches": st["launches"],
                               "optimal_calls": st["optimal_calls"], "kernel_ms": st["kernel_ms"],
                               "structs_mean": float(np.mean([len(o[1]) for o in out]))}), flush=True)
+
+
+def make_alignment(rng, n_seqs, anc_len, n_cols):
+    """ancestor with a planted nested structure; descendants with 10 % substitutions (compensatory in
+    stems) and gap columns up to n_cols"""
+    comp = {"A": "U", "U": "A", "G": "C", "C": "G"}
+    anc = [rng.choice("ACGU") for _ in range(anc_len)]
+    pairs = []
+    pos = 5
+    while pos + 40 < anc_len:                       # hairpins of 6-9 bp with 5-nt loops
+        ln = rng.randint(6, 9)
+        i, j = pos, pos + 2 * ln + 4
+        for k in range(ln):
+            anc[j - k] = comp[anc[i + k]]
+            pairs.append((i + k, j - k))
+        pos = j + rng.randint(4, 10)
+    gapcols = sorted(rng.sample(range(n_cols), n_cols - anc_len))
+    colmap = [c for c in range(n_cols) if c not in set(gapcols)]
+    ref = ["."] * n_cols
+    for v, w in pairs:
+        ref[colmap[v]], ref[colmap[w]] = "(", ")"
+    rows = []
+    partner = dict(pairs); partner.update({w: v for v, w in pairs})
+    for _ in range(n_seqs):
+        seq = list(anc)
+        for p in range(anc_len):
+            if rng.random() < 0.10:
+                seq[p] = rng.choice("ACGU")
+                if p in partner:
+                    seq[partner[p]] = comp[seq[p]]
+        row = ["-"] * n_cols
+        for p, c in enumerate(colmap):
+            row[c] = seq[p] if rng.random() > 0.02 else "-"
+        rows.append("".join(row))
+    return rows, "".join(ref)
+
+
+def leg_alignment(n_seqs, anc_len, n_cols):
+    import io, tempfile
+    rng = random.Random(20261017)
+    rows, ref = make_alignment(rng, n_seqs, anc_len, n_cols)
+    with tempfile.NamedTemporaryFile("w", suffix=".afa", delete=False) as f:
+        f.write("?" * n_cols + "\n" + "." * n_cols + "\n" + ref + "\n")
+        for k, r in enumerate(rows):
+            f.write(">seq%d\n%s\n" % (k, r))
+        path = f.name
+    S.get_context(0)
+    sink = io.StringIO()
+    t0 = time.perf_counter()
+    CLI.Predict(inputfile=path, alignment=True, write_to=sink)
+    dt = time.perf_counter() - t0
+    text = sink.getvalue().split("\n")
+    tail = [ln for ln in text if ln.strip()][-6:]
+    print(json.dumps({"leg": "c4 alignment ali.conf", "n_seqs": n_seqs, "columns": n_cols, "seconds": dt,
+                      "seq_per_s": n_seqs / dt, "output_tail": tail}), flush=True)
 
 
 if __name__ == "__main__":

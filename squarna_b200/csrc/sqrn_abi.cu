@@ -49,6 +49,43 @@ __device__ __forceinline__ void work_loop(const DevParams *__restrict__ Pg, cons
     }
 }
 
+// Cluster flavour for a FEW LONG sequences (rRNA scale): one thread-block cluster per sequence.
+// Each CTA (1024 threads) holds a full replica of the sequence state -- bit masks, partners, stems:
+// tens of KB, the N x N matrices never exist -- and scans every CS-th anti-diagonal; the per-CTA
+// winners are exchanged through distributed shared memory (cluster_best) and every replica applies
+// the same stem.  Rank 0 fetches the work items and writes the results.
+template <bool PLAIN, bool STDP>
+__global__ void __launch_bounds__(1024, 1)
+k_cluster(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
+{
+    namespace cg = cooperative_groups;
+    using C = Cfg<32, PLAIN, STDP, MODE_TAIL, -1, true>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ DevParams Psh;
+    {
+        const int *src = reinterpret_cast<const int *>(Pg);
+        int *dst = reinterpret_cast<int *>(&Psh);
+        for (int k = threadIdx.x; k < (int)(sizeof(DevParams) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned cr = cl.block_rank(), cs = cl.num_blocks();
+    State S = bind_state(smem, L);
+    S.dstride = (int)cs; S.doffset = (int)cr;
+    for (;;) {
+        if (cr == 0 && threadIdx.x == 0) {
+            int it = atomicAdd(Wk.counter, 1);
+            for (unsigned q = 0; q < cs; q++) *cl.map_shared_rank(&S.misc[1], q) = it;      // DSMEM broadcast
+        }
+        cl.sync();
+        int item = S.misc[1];
+        cl.sync();                          // everyone has read it before rank 0 may overwrite it
+        if (item >= Wk.n_items) break;
+        item = Wk.order ? Wk.order[item] : item + Wk.item_base;
+        team_run_item<C>(S, Psh, B, Wk, L, item);
+    }
+}
+
 // general flavour: any batch, any mode, shared-memory layout chosen per launch
 template <int TW>
 __global__ void __launch_bounds__(TW == 1 ? 256 : TW * 32, TW == 1 ? 3 : 1)
@@ -127,11 +164,14 @@ struct sqrn_ctx {
     int64_t n_launches = 0, n_calls = 0; double kernel_ms = 0.0;
     int region_mode = REGION_AUTO;
     int no_fast_kernel = 0;      // tuning knob: route the fast lane through the general kernel
+    int no_cluster = 0, force_cluster = 0;   // tuning knobs: never / always (with this size) use k_cluster for long sequences
+    int64_t n_cluster_launches = 0;
     CachedResult cres; CachedStems cstems;
 };
 
 static std::string g_create_err;
 
+#define TRY(x) do { int r_ = (x); if (r_ != SQRN_OK) return r_; } while (0)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SQRN_E_CUDA; } } while (0)
 
@@ -216,6 +256,9 @@ extern "C" int sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value)
     if (!ctx) return SQRN_E_BADARG;
     if (what == SQRN_TUNE_REGION && value >= 0 && value <= 2) { ctx->region_mode = value; return SQRN_OK; }
     if (what == SQRN_TUNE_NO_FAST_KERNEL) { ctx->no_fast_kernel = value != 0; return SQRN_OK; }
+    if (what == SQRN_TUNE_CLUSTER && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) {
+        ctx->no_cluster = value == 1; ctx->force_cluster = value > 1 ? value : 0; return SQRN_OK;   // 0 automatic, 1 never, 2..16 always
+    }
     ctx->err = "unknown tuning knob";
     return SQRN_E_BADARG;
 }
@@ -250,7 +293,7 @@ static int get_params(sqrn_ctx *ctx, const sqrn_paramset &ps, int nmax, const PE
 }
 
 // ------------------------------------------------------------- launch plan
-struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; };
+struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; int cluster = 0; bool cl_plain = false; };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -316,29 +359,92 @@ static int plan_fast(sqrn_ctx *ctx, Plan &pl)
     return SQRN_OK;
 }
 
+static void maybe_cluster(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int n_items, bool plain, bool tail_mode);
+
 static bool fast_eligible(const PEntry &P, int nmax) { return P.hp.std_pairs && P.hp.m >= 2 && nmax <= 320; }
 
-static int make_fast_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, Plan &pl)
+static int make_fast_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int n_items, Plan &pl)
 {
     if (fast_eligible(P, nmax) && !ctx->no_fast_kernel) {
         if (nmax <= 128) return plan_fast<128>(ctx, pl);
         if (nmax <= 224) return plan_fast<224>(ctx, pl);
         return plan_fast<320>(ctx, pl);
     }
-    return make_plan(ctx, P, nmax, 0, 0, false, false, 0, pl);
+    TRY(make_plan(ctx, P, nmax, 0, 0, false, false, 0, pl));
+    maybe_cluster(ctx, P, pl, n_items, true, true);
+    return SQRN_OK;
+}
+
+// Few long sequences: give each one a thread-block cluster instead of a single CTA (k_cluster).
+// n_items = work items of the launch; plain = no reactivities / restraints / smat / interchainonly.
+template <bool PLAIN, bool STDP>
+static int plan_cluster_t(sqrn_ctx *ctx, Plan &pl, int cs)
+{
+    auto kern = k_cluster<PLAIN, STDP>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = pl.smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+    if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); return SQRN_E_UNSUPPORTED; }
+    pl.cluster = cs; pl.grid = ncl;          // grid counts clusters here
+    return SQRN_OK;
+}
+
+static void maybe_cluster(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int n_items, bool plain, bool tail_mode)
+{
+    if (pl.tw != 32 || !tail_mode || ctx->no_cluster || n_items < 1) return;
+    int want = ctx->force_cluster;
+    if (!want) {
+        if (2 * n_items > ctx->sm_count) return;             // enough sequences to fill the SMs one CTA each
+        want = 8;
+        while (want > 2 && want * n_items > ctx->sm_count) want >>= 1;
+    }
+    pl.cl_plain = plain && P.hp.std_pairs;
+    for (int cs = want; cs >= 2; cs >>= 1) {
+        int rc = pl.cl_plain ? plan_cluster_t<true, true>(ctx, pl, cs) : plan_cluster_t<false, false>(ctx, pl, cs);
+        if (rc == SQRN_OK) return;
+    }
+    pl.cluster = 0;
+}
+
+// one launch of the work kernel the plan names
+static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t st, const DevBatch &B, const DevWork &W)
+{
+    if (pl.cluster) {
+        int ncl = std::min(pl.grid, std::max(W.n_items, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ncl * pl.cluster)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)pl.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const DevParams *dp = P.d_p;
+        if (pl.cl_plain) CK(cudaLaunchKernelEx(&cfg, k_cluster<true, true>, dp, B, W, pl.L));
+        else CK(cudaLaunchKernelEx(&cfg, k_cluster<false, false>, dp, B, W, pl.L));
+        ctx->n_cluster_launches++;
+        return SQRN_OK;
+    }
+    int grid = pl.grid;
+    int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
+    if (grid > teams) grid = std::max(teams, 1);
+    if (pl.fast_ncap == 128) k_fast<128><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
+    else if (pl.fast_ncap == 224) k_fast<224><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
+    else if (pl.fast_ncap == 320) k_fast<320><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
+    else if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
+    else if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
+    else k_work<32><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
+    CK(cudaGetLastError());
+    return SQRN_OK;
 }
 
 static int launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, const DevBatch &B, DevWork &W)
 {
     CK(cudaMemsetAsync(W.counter, 0, sizeof(int), ctx->stream));
-    int grid = pl.grid;
-    int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
-    if (grid > teams) grid = std::max(teams, 1);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, ctx->stream>>>(P.d_p, B, W, pl.L);
-    else if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, ctx->stream>>>(P.d_p, B, W, pl.L);
-    else k_work<32><<<grid, pl.threads, pl.smem, ctx->stream>>>(P.d_p, B, W, pl.L);
-    CK(cudaGetLastError());
+    TRY(dispatch(ctx, P, pl, ctx->stream, B, W));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
     ctx->n_launches++;
@@ -360,7 +466,6 @@ static int dalloc(sqrn_ctx *ctx, int slot, size_t count, T **d)
     *d = (T *)ctx->buf[slot].p;
     return SQRN_OK;
 }
-#define TRY(x) do { int r_ = (x); if (r_ != SQRN_OK) return r_; } while (0)
 
 // ------------------------------------------------ fast lane (byseq pl=1 shape)
 // one launch over items [item_base, item_base + n_items) of a resident CSR batch
@@ -375,17 +480,8 @@ static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStrea
     W.n_items = (int)n_items; W.item_base = (int)item_base; W.mode = MODE_TAIL; W.region_mode = ctx->region_mode;
     W.round3 = round3; W.counter = d_counter; W.out_flags = d_flags; W.n_calls = d_ncalls;
     W.out_nstems = d_n_stems; W.out_raw = d_scores; W.dbn_off = d_offsets; W.out_dbn_ascii = d_dbn_ascii;
-    int grid = pl.grid;
-    int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
-    if (grid > teams) grid = std::max(teams, 1);
     if (e0) CK(cudaEventRecord(e0, st));
-    if (pl.fast_ncap == 128) k_fast<128><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
-    else if (pl.fast_ncap == 224) k_fast<224><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
-    else if (pl.fast_ncap == 320) k_fast<320><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
-    else if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
-    else if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
-    else k_work<32><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
-    CK(cudaGetLastError());
+    TRY(dispatch(ctx, P, pl, st, B, W));
     if (e1) CK(cudaEventRecord(e1, st));
     ctx->n_launches++;
     return SQRN_OK;
@@ -402,7 +498,7 @@ extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, 
     const PEntry *P;
     TRY(get_params(ctx, *ps, max_len, &P));
     Plan pl;
-    TRY(make_fast_plan(ctx, *P, max_len, pl));
+    TRY(make_fast_plan(ctx, *P, max_len, (int)n_seqs, pl));
     int *d_counter; uint8_t *d_flags; unsigned long long *d_nc;
     TRY(dalloc(ctx, W_COUNTER, FAST_MAX_CHUNKS, &d_counter));
     TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &d_flags));
@@ -423,7 +519,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
 {
     if (!ctx || !ps || !offsets || n_seqs < 0 || n_seqs > 0x7fffffff) return SQRN_E_BADARG;
     cudaSetDevice(ctx->device);
-    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
     if (n_seqs == 0) return SQRN_OK;
     const bool trace = getenv("SQRN_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -438,7 +534,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     const PEntry *P;
     TRY(get_params(ctx, *ps, max_len, &P));
     Plan pl;
-    TRY(make_fast_plan(ctx, *P, max_len, pl));
+    TRY(make_fast_plan(ctx, *P, max_len, (int)n_seqs, pl));
     int64_t *d_off; uint8_t *d_sym, *d_dbn, *d_flags; double *d_sc; int32_t *d_ns; int *d_counter; unsigned long long *d_nc;
     TRY(dalloc(ctx, B_OFF, (size_t)n_seqs + 1, &d_off));
     TRY(dalloc(ctx, B_SYM, (size_t)std::max<int64_t>(total, 1), &d_sym));
@@ -658,6 +754,10 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
         while (end < n && cls(order[end]) == c) end++;
         int nmax_c = D.len[W.item_seq[order[pos]]];
         Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, W.mode == MODE_STEP, D.B.rcode != nullptr, max_init, pl));
+        {
+            const bool plain = !D.B.rcode && !D.B.rclass && !D.B.rbp_off && !D.B.smat && !D.B.interchainonly;
+            maybe_cluster(ctx, *P, pl, end - pos, plain, W.mode == MODE_TAIL);
+        }
         DevWork Gc = G; Gc.order = d_order + pos; Gc.n_items = end - pos;
         TRY(launch(ctx, *P, pl, D.B, Gc));
         pos = end;
@@ -827,7 +927,7 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
     }
     if (!ps || n_ps < 1 || n_ps > 64) { ctx->err = "need 1..64 parameter sets"; return SQRN_E_BADARG; }
     ctx->cres.valid = false;
-    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
     DeviceBatch D;
     TRY(upload_batch(ctx, in, D));
     const int64_t nseq = in->n_seqs;
@@ -1089,7 +1189,7 @@ extern "C" int sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, co
     if (in) {
         if (!ps) return SQRN_E_BADARG;
         C.valid = false;
-        ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+        ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
         DeviceBatch D;
         TRY(upload_batch(ctx, in, D));
         const int64_t nseq = in->n_seqs;
@@ -1133,7 +1233,7 @@ extern "C" int sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn
 {
     if (!ctx || !ps || !in) return SQRN_E_BADARG;
     cudaSetDevice(ctx->device);
-    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0;
+    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
     DeviceBatch D;
     TRY(upload_batch(ctx, in, D));
     HostWork W; W.mode = mode; W.want_dbn = dbn_code != nullptr; W.want_fin = out_fin != nullptr;

@@ -31,6 +31,7 @@
 #include <stdint.h>
 #ifndef SQRN_HOST_EMU
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #define SQRN_NOINLINE __noinline__
 #else
 // Single-thread "team" build used only by tests/emu (g++): the same device
@@ -138,7 +139,7 @@ struct Layout {
     int Ncap, W, WR, Scap, RBcap, Rcap, Ccap, Ocap, npc;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
         o_sti, o_stj, o_stl, o_stlev, o_evpos, o_evid, o_cc, o_perm, o_grp, o_gsz,
-        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_misc, total;
+        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, total;
 };
 
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -163,6 +164,7 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_cbps = o;    o += 8 * Ccap;                       // doubles first (8-byte aligned)
     L.o_cfin = o;    o += with_fin ? 8 * Ccap : 0;
     L.o_red = o;     o += (tw > 1) ? 32 * tw : 0;        // cross-warp reduction scratch
+    L.o_xchg = o;    o += (tw > 1) ? 2 * 16 * 16 : 0;     // cluster exchange: 2 parities x 16 ranks x (fin, key, len)
     L.o_misc = o;    o += 64;
     L.o_M = o;       o += 4 * npc * L.W;
     L.o_PR = o;      o += 4 * npc * L.WR;
@@ -270,15 +272,19 @@ template <> struct Team<0> {
 //   RUNLIST: phase 1 collects runs in a shared list before they are scored (warp teams: keeps
 //          the lanes of phase 2a dense); off, every thread scores the runs of its own diagonal
 //          in team-wide rounds (CTA teams).  -1: on for warp teams only.
-template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1>
+//   CLUSTER: the team is a thread-block CLUSTER: every CTA keeps a full replica of the (small)
+//          sequence state in its own shared memory and scans every CS-th anti-diagonal; the
+//          CTA-local winners meet in rank 0's shared memory through DSMEM once per greedy step.
+template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1, bool CLUSTER_ = false>
 struct Cfg {
     static constexpr int TW = TW_, MODE = MODE_;
-    static constexpr bool PLAIN = PLAIN_, STDP = STDP_;
+    static constexpr bool PLAIN = PLAIN_, STDP = STDP_, CLUSTER = CLUSTER_;
     static constexpr bool RUNLIST = RUNLIST_ < 0 ? (TW_ == 1) : (RUNLIST_ != 0);
 };
 
 struct State {
     int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts, region_mode;
+    int dstride, doffset;            // this team scans the anti-diagonals 4 + doffset + dstride * q (cluster: rank, size)
     uint8_t  *code, *rcl, *stlev;
     uint16_t *rcode;
     int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *evpos, *evid, *perm, *grp, *rbv, *rbw;
@@ -286,6 +292,7 @@ struct State {
     int32_t  *cc, *gsz, *Ubase;
     uint16_t *clen, *rlen;
     double   *cbps, *cfin, *red;
+    unsigned char *xchg;
     int      *misc;      // [0] run count  [1] next item  [2..6] scratch  [7] survivor count
     const int32_t *cols; // global, per sequence
 };
@@ -310,10 +317,12 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
     s.cbps = (double *)(base + L.o_cbps);
     s.cfin = (double *)(base + L.o_cfin);
     s.red = (double *)(base + L.o_red);
+    s.xchg = base + L.o_xchg;
     s.misc = (int *)(base + L.o_misc);
     s.W = L.W; s.WR = L.WR;
     s.N = 0; s.nst = 0; s.nrb = 0; s.has_sep = 0; s.has_react = 0; s.has_smat = 0; s.default_reacts = 1;
     s.region_mode = REGION_AUTO;
+    s.dstride = 1; s.doffset = 0;
     s.cols = nullptr;
     return s;
 }
@@ -1272,9 +1281,10 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
         // The team meets at a barrier only when every thread is parked or done, flushes the list
         // and resumes: barriers per scan = list fills + diagonals / T.
         #pragma unroll 1
-        for (int s0 = 4; s0 <= smax; s0 += T) {
+        for (int q0 = 0; 4 + S.doffset + S.dstride * q0 <= smax; q0 += T) {
             RunIter ri;
-            runs_begin<C>(ri, S, P, B, s0 + r, s0 + r <= smax);
+            const int s_mine = 4 + S.doffset + S.dstride * (q0 + r);
+            runs_begin<C>(ri, S, P, B, s_mine, s_mine <= smax);
             bool done = !ri.live, carry = false;
             uint32_t ckey_ = 0; int clen_ = 0; double csc_ = 0.0;
             #pragma unroll 1
@@ -1321,9 +1331,9 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
             Team<TW>::sync();
         };
         #pragma unroll 1
-        for (int s0 = 4; s0 <= smax; s0 += T) {
-            const int s = s0 + r;
-            const bool last = s0 + T > smax;
+        for (int q0 = 0; 4 + S.doffset + S.dstride * q0 <= smax; q0 += T) {
+            const int s = 4 + S.doffset + S.dstride * (q0 + r);
+            const bool last = 4 + S.doffset + S.dstride * (q0 + T) > smax;
             int done = -1;                     // runs of this lane's diagonal starting at a <= done are in the list
             #pragma unroll 1
             for (;;) {
@@ -1569,6 +1579,40 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
     }
 }
 
+// ------------------------------------------------ cluster-wide arg-max (DSMEM)
+// Every CTA of the cluster publishes the winner of its share of the anti-diagonals in rank 0's
+// shared memory (a remote store through distributed shared memory), the cluster synchronises, and
+// every CTA reads the CS entries back and picks the same overall winner with the same tie rule.
+// Two parity buffers make one cluster barrier per greedy step enough.
+struct XchgEntry { double fin; uint32_t key; int len; };
+
+template <class C>
+__device__ __forceinline__ Best cluster_best(State &S, Best b, int step)
+{
+#ifndef SQRN_HOST_EMU
+    if (C::CLUSTER) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cl = cg::this_cluster();
+        const unsigned cr = cl.block_rank(), cs = cl.num_blocks();
+        XchgEntry *x0 = (XchgEntry *)cl.map_shared_rank(S.xchg, 0) + (step & 1) * 16;
+        if (threadIdx.x == 0) { XchgEntry e; e.fin = b.fin; e.key = b.key; e.len = b.len; x0[cr] = e; }
+        cl.sync();
+        if (threadIdx.x == 0) {
+            Best g; g.fin = -1e300; g.key = 0xffffffffu; g.len = 0;
+            for (unsigned q = 0; q < cs; q++) {
+                XchgEntry e = x0[q];
+                if (better(e.fin, e.key, g.fin, g.key)) { g.fin = e.fin; g.key = e.key; g.len = e.len; }
+            }
+            S.red[0] = g.fin; ((uint32_t *)(S.red + 1))[0] = g.key; ((uint32_t *)(S.red + 1))[1] = (uint32_t)g.len;
+        }
+        __syncthreads();
+        b.fin = S.red[0]; b.key = ((uint32_t *)(S.red + 1))[0]; b.len = (int)((uint32_t *)(S.red + 1))[1];
+        __syncthreads();
+    }
+#endif
+    return b;
+}
+
 // ------------------------------------------------------------ one work item
 template <class C>
 __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk,
@@ -1595,12 +1639,14 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         while (mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
             Best b = team_scan<C>(S, P, B, L, -1.0);
+            b = cluster_best<C>(S, b, (int)calls);
             calls++;
             if (b.fin <= -1e300) break;
             int i = (int)(b.key & 0xffff);
             team_apply_stem<C>(S, i, (int)(b.key >> 16) - i, b.len);
         }
-        team_finalize<C>(S, P, B, Wk, item);
+        if (C::CLUSTER && S.doffset != 0) calls = 0;          // replicas: rank 0 reports
+        else team_finalize<C>(S, P, B, Wk, item);
     } else if (mode == MODE_STEP) {
         int n = 0;
         int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;

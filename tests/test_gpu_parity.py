@@ -69,6 +69,39 @@ def test_fast_lane_cta_teams(gpu_ctx):
     _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(17, 4, 2100, 2600))
 
 
+@pytest.mark.parametrize("cs", [1, 2, 4, 8], ids=["one-cta", "cluster2", "cluster4", "cluster8"])
+def test_long_sequences_cluster_sizes(gpu_ctx, cs):
+    """> 2048 nt run to completion: one CTA per sequence and thread-block clusters of 2/4/8 CTAs
+    (replicated state, every CS-th anti-diagonal per CTA, DSMEM arg-max exchange) give the oracle's result"""
+    seqs = T.rand_seqs(21, 3, 2060, 2400) + [T.rand_seq(random.Random(22), 2100, "GC")]
+    try:
+        gpu_ctx.set_cluster(cs)
+        _check_fast(gpu_ctx, T.G1000, seqs[:3])
+        _check_fast(gpu_ctx, T.FASTEST, seqs)
+    finally:
+        gpu_ctx.set_cluster(0)
+
+
+def test_fast_kernel_equals_general_kernel(gpu_ctx):
+    """the specialised fast-lane kernel (static layout, bit planes) and the general kernel agree bit for bit"""
+    seqs = T.rand_seqs(23, 4000, 1, 320) + T.rand_seqs(24, 200, 5, 200, "ACGUN;&acgut")
+    sym, off = pack_sequences(seqs)
+    a = gpu_ctx.fast_predict(T.FASTEST, sym, off)
+    try:
+        gpu_ctx.set_no_fast_kernel(True)
+        b = gpu_ctx.fast_predict(T.FASTEST, sym, off)
+        for mode in (1, 2):
+            gpu_ctx.set_region_mode(mode)
+            c = gpu_ctx.fast_predict(T.FASTEST, sym, off)
+            for x, y in zip(b, c):
+                assert np.array_equal(x, y)
+    finally:
+        gpu_ctx.set_no_fast_kernel(False)
+        gpu_ctx.set_region_mode(0)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
 def test_yield_stems(gpu_ctx):
     """AnnotateStems seam (YieldStems): same stems, same order, same scores"""
     rng = random.Random(18)
