@@ -830,16 +830,7 @@ __device__ __forceinline__ bool diag_range(const State &S, const DevBatch &B, in
 }
 
 // ---------------------------------------------------- enumerate one diagonal
-// Resumable walk over the maximal runs of one anti-diagonal, outermost first (the
-// order of seq.py:486-493).  runs_next() yields the next run [a, e] (in i) of at
-// least P.m cells; the caller may do other (team-uniform) work between calls.
-struct RunIter {
-    DiagWalk it;
-    int s, lo, hi, k, k1, skip_until;    // skip_until: runs already yielded extend up to here
-    uint32_t x, xn, prev_top, starts;
-    bool live;
-};
-
+// bits of x where a maximal run of at least m cells starts (xn = next word, prev_top = top bit of the previous one)
 __device__ __forceinline__ uint32_t run_starts(uint32_t x, uint32_t xn, uint32_t prev_top, int m)
 {
     if (!x) return 0u;
@@ -848,57 +839,10 @@ __device__ __forceinline__ uint32_t run_starts(uint32_t x, uint32_t xn, uint32_t
     return y & ~((x << 1) | prev_top);
 }
 
-template <class C>
-__device__ __forceinline__ void runs_begin(RunIter &R, const State &S, const DevParams &P, const DevBatch &B, int s, bool on)
-{
-    R.s = s;
-    R.live = on && diag_range<C>(S, B, s, R.lo, R.hi);
-    if (!R.live) return;
-    R.k = R.lo >> 5; R.k1 = R.hi >> 5;
-    walk_begin<C>(R.it, S, P, s, R.k);
-    R.x = walk_next<C>(R.it, S, P, s, R.lo, R.hi);
-    R.xn = (R.k < R.k1) ? walk_next<C>(R.it, S, P, s, R.lo, R.hi) : 0u;
-    R.prev_top = 0; R.skip_until = -1;
-    R.starts = run_starts(R.x, R.xn, 0u, P.m);
-}
-
-template <class C>
-__device__ __forceinline__ bool runs_next(RunIter &R, const State &S, const DevParams &P, int &a, int &e)
-{
-    if (!R.live) return false;
-    #pragma unroll 1
-    for (;;) {
-        #pragma unroll 1
-        while (R.starts == 0) {
-            if (R.k >= R.k1) { R.live = false; return false; }
-            R.prev_top = R.x >> 31; R.x = R.xn; R.k++;
-            R.xn = (R.k < R.k1) ? walk_next<C>(R.it, S, P, R.s, R.lo, R.hi) : 0u;
-            R.starts = run_starts(R.x, R.xn, R.prev_top, P.m);
-        }
-        const int b = __ffs(R.starts) - 1;
-        R.starts &= R.starts - 1;
-        a = 32 * R.k + b;
-        if (a <= R.skip_until) continue;
-        // find the end of the run
-        uint32_t inv = ~(R.x >> b);              // bit 0 is 0; first set bit = run length
-        int t = inv ? __ffs(inv) - 1 : 32;
-        if (b + t < 32) e = a + t - 1;
-        else {
-            int kk = R.k + 1; uint32_t w = R.xn;
-            #pragma unroll 1
-            while (kk <= R.k1 && w == 0xffffffffu) { kk++; w = (kk <= R.k1) ? diag_word<C>(S, P, R.s, kk, R.lo, R.hi) : 0u; }
-            e = (kk <= R.k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (R.k1 + 1) - 1;
-            if (e > R.hi) e = R.hi;
-        }
-        R.skip_until = e;
-        return true;
-    }
-}
-
-// Non-resumable form of the same walk: calls emit(a, e) for every maximal run of at least P.m
-// cells of diagonal s.  Kept separate from RunIter because its word loop is uniform across the
-// lanes of a warp (every lane steps its diagonal one word at a time), which the warp-team scan
-// relies on for lane utilisation.
+// Lane-per-diagonal walk (warp teams, YieldStems): calls emit(a, e) for every maximal run [a, e]
+// (in i) of at least P.m cells of diagonal s, outermost first -- the order of seq.py:486-493.
+// The word loop is uniform across the lanes of a warp (every lane steps its own diagonal one word
+// at a time).
 template <class C, class F>
 __device__ __forceinline__ void enum_diag(const State &S, const DevParams &P, const DevBatch &B, int s, F &&emit)
 {
@@ -1275,41 +1219,120 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
     };
 
     if (!C::RUNLIST) {
-        // CTA teams (long sequences: hundreds of runs per diagonal): no run list.  Every thread walks
-        // its own diagonal at its own pace and appends the runs that pass the bp-score filter to the
-        // survivor list; when the list is full the thread parks (keeping the run it could not store).
-        // The team meets at a barrier only when every thread is parked or done, flushes the list
-        // and resumes: barriers per scan = list fills + diagonals / T.
-        #pragma unroll 1
-        for (int q0 = 0; 4 + S.doffset + S.dstride * q0 <= smax; q0 += T) {
-            RunIter ri;
-            const int s_mine = 4 + S.doffset + S.dstride * (q0 + r);
-            runs_begin<C>(ri, S, P, B, s_mine, s_mine <= smax);
-            bool done = !ri.live, carry = false;
-            uint32_t ckey_ = 0; int clen_ = 0; double csc_ = 0.0;
+        // CTA teams (long sequences: hundreds of runs per diagonal): a WARP walks one anti-diagonal,
+        // 32 words (1024 cells) per step, one word per lane, so the lanes do the same work at the same
+        // time: build the word, find the run starts in it, score those runs, append the ones that pass
+        // the bp-score filter to the survivor list.  When the list is full a lane parks (keeping the run
+        // it could not store); the team meets at a barrier only when every warp is parked or done,
+        // flushes the list and resumes where it stopped.
+#ifdef SQRN_HOST_EMU
+        constexpr int WL = 1;
+        const int G = 1, lane = 0;
+#else
+        constexpr int WL = 32;
+        // short diagonals: a sub-group of G = 4..32 lanes per diagonal (G >= words of the longest one,
+        // when that is <= 32), so a warp walks 32 / G diagonals at once
+        int G = 32;
+        { const int wd = (S.N / 2 + 31) / 32 + 1; while (G > 4 && (G >> 1) >= wd) G >>= 1; }
+        const int lane = (threadIdx.x & 31) & (G - 1);         // lane within the group
+#endif
+        const int gid = r / G, ng = T / G;             // this group, groups in the team
+        int q = gid;                                   // index of this group's diagonal within the team's share
+        int sd = 0, lo = 0, hi = 0, k1 = -1, kb = 0;   // group-uniform: diagonal, walked range, last word, chunk base
+        bool have_diag = false, warp_done = false, need_chunk = true;
+        uint32_t x = 0, xn = 0, starts = 0, carry_top = 0;
+        int k = 0;
+        bool carry = false;
+        uint32_t ckey_ = 0; int clen_ = 0; double csc_ = 0.0;
+
+        // next chunk of the current diagonal, or the first chunk of the group's next diagonal
+        // (uniform within a group; the groups of a warp run it in lockstep).  false: nothing left.
+        auto advance = [&]() -> bool {
+            bool live = true;
             #pragma unroll 1
             for (;;) {
-                #pragma unroll 1
-                while (!done || carry) {
-                    if (!carry) {
-                        if (*(volatile int *)&S.misc[7] >= Ccap && !overflow) break;       // list full: park
-                        int a, e;
-                        if (!runs_next<C>(ri, S, P, a, e)) { done = true; break; }
-                        int len = e - a + 1;
-                        if ((double)len < P.minlen) continue;
-                        double sc = run_score<C>(S, P, B, ri.s, a, len);
-                        if (!(sc >= P.minbpscore)) continue;
-                        ckey_ = ((uint32_t)ri.s << 16) | (uint32_t)a; clen_ = len; csc_ = sc;
-                    }
-                    int slot = atomicAdd(&S.misc[7], 1);
-                    if (slot < Ccap) { S.ckey[slot] = ckey_; S.clen[slot] = (uint16_t)clen_; S.cbps[slot] = csc_; carry = false; }
-                    else if (overflow) carry = false;          // STEP list overflow: the result is discarded anyway
-                    else { carry = true; break; }              // lost the race for the last slots: park with the run
+                if (have_diag) {
+                    kb += G;
+                    if (kb <= k1) break;
+                    have_diag = false; q += ng;
                 }
-                const int nd = Team<TW>::count(done && !carry);          // barrier
-                flush_survivors();
-                if (nd == T) break;
+                sd = 4 + S.doffset + S.dstride * q;
+                if (sd > smax) { live = false; break; }
+                if (!diag_range<C>(S, B, sd, lo, hi)) { q += ng; continue; }
+                have_diag = true; kb = lo >> 5; k1 = hi >> 5; carry_top = 0;
+                break;
             }
+            k = kb + lane;
+            x = (live && k <= k1) ? diag_word<C>(S, P, sd, k, lo, hi) : 0u;
+#ifdef SQRN_HOST_EMU
+            xn = (live && kb + G <= k1) ? diag_word<C>(S, P, sd, kb + G, lo, hi) : 0u;
+            uint32_t pt = carry_top;
+            carry_top = x >> 31;
+#else
+            xn = __shfl_down_sync(0xffffffffu, x, 1, G);
+            if (lane == G - 1) xn = (live && kb + G <= k1) ? diag_word<C>(S, P, sd, kb + G, lo, hi) : 0u;
+            uint32_t xp = __shfl_up_sync(0xffffffffu, x, 1, G);
+            uint32_t pt = lane == 0 ? carry_top : (xp >> 31);
+            carry_top = __shfl_sync(0xffffffffu, x, G - 1, G) >> 31;
+#endif
+            starts = live ? run_starts(x, xn, pt, P.m) : 0u;
+            return live;
+        };
+
+        #pragma unroll 1
+        for (;;) {
+            if (!warp_done) {
+                #pragma unroll 1
+                for (;;) {
+                    if (need_chunk) {
+                        // a group without diagonals left idles (no starts) until the whole warp is done
+                        bool live = advance();
+#ifndef SQRN_HOST_EMU
+                        live = __any_sync(0xffffffffu, live);
+#endif
+                        if (!live) { warp_done = true; break; }
+                        need_chunk = false;
+                    }
+                    bool parked = false;
+                    #pragma unroll 1
+                    while (starts || carry) {
+                        if (!carry) {
+                            if (*(volatile int *)&S.misc[7] >= Ccap && !overflow) { parked = true; break; }   // list full
+                            const int b = __ffs(starts) - 1;
+                            starts &= starts - 1;
+                            const int a = 32 * k + b;
+                            int e;
+                            uint32_t inv = ~(x >> b);            // bit 0 is 0; first set bit = run length
+                            int t = inv ? __ffs(inv) - 1 : 32;
+                            if (b + t < 32) e = a + t - 1;
+                            else {
+                                int kk = k + 1; uint32_t w = xn;
+                                #pragma unroll 1
+                                while (kk <= k1 && w == 0xffffffffu) { kk++; w = (kk <= k1) ? diag_word<C>(S, P, sd, kk, lo, hi) : 0u; }
+                                e = (kk <= k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (k1 + 1) - 1;
+                                if (e > hi) e = hi;
+                            }
+                            const int len = e - a + 1;
+                            if ((double)len < P.minlen) continue;
+                            const double sc = run_score<C>(S, P, B, sd, a, len);
+                            if (!(sc >= P.minbpscore)) continue;
+                            ckey_ = ((uint32_t)sd << 16) | (uint32_t)a; clen_ = len; csc_ = sc;
+                        }
+                        int slot = atomicAdd(&S.misc[7], 1);
+                        if (slot < Ccap) { S.ckey[slot] = ckey_; S.clen[slot] = (uint16_t)clen_; S.cbps[slot] = csc_; carry = false; }
+                        else if (overflow) carry = false;      // STEP list overflow: the result is discarded anyway
+                        else { carry = true; parked = true; break; }   // lost the race for the last slots: park with the run
+                    }
+#ifndef SQRN_HOST_EMU
+                    parked = __any_sync(0xffffffffu, parked);
+#endif
+                    if (parked) break;
+                    need_chunk = true;
+                }
+            }
+            const int nd = Team<TW>::count(warp_done);           // barrier
+            flush_survivors();
+            if (nd == T) break;
         }
     } else {
         // warp teams: phase 1 fills a run list, phase 2a scores it with dense lanes
