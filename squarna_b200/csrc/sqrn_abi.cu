@@ -100,13 +100,19 @@ k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
 // completion.  The shared-memory layout is a compile-time constant, so every array address is
 // "team base + immediate" and the code stays small enough for the instruction cache.
 constexpr int FAST_TEAMS = 8, FAST_CCAP = 128, FAST_RCAP = 256;
+// persistent run list: ~0.003 N^2 entries on random RNA with minlen 4 (measured)
+__host__ __device__ constexpr int fast_pcap(int ncap) { return ncap <= 128 ? 128 : ncap <= 224 ? 272 : 448; }
+template <int NCAP> __host__ __device__ constexpr Layout fast_layout()
+{
+    return make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, -1, 0, NCAP / 4 + 2, fast_pcap(NCAP), 2);
+}
 template <int NCAP>
 __global__ void __launch_bounds__(32 * FAST_TEAMS, 4)
 k_fast(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr Layout L = make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, 0, 0, NCAP / 4 + 2);
-    work_loop<Cfg<1, true, true, MODE_TAIL>>(Pg, B, Wk, L, smem);
+    constexpr Layout L = fast_layout<NCAP>();
+    work_loop<Cfg<1, true, true, MODE_TAIL, -1, false, true>>(Pg, B, Wk, L, smem);
 }
 
 // ----------------------------------------------------------------- context
@@ -348,7 +354,7 @@ static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int mi
 template <int NCAP>
 static int plan_fast(sqrn_ctx *ctx, Plan &pl)
 {
-    constexpr Layout L = make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, 0, 0, NCAP / 4 + 2);
+    constexpr Layout L = fast_layout<NCAP>();
     pl.tw = 1; pl.tpc = FAST_TEAMS; pl.threads = 32 * FAST_TEAMS; pl.L = L; pl.smem = (size_t)FAST_TEAMS * L.total;
     pl.fast_ncap = NCAP;
     CK(cudaFuncSetAttribute(k_fast<NCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));

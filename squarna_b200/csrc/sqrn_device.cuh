@@ -136,7 +136,8 @@ struct DevWork {
 
 // -------------------------------------------------------------- smem layout
 struct Layout {
-    int Ncap, W, WR, Scap, RBcap, Rcap, Ccap, Ocap, npc;
+    int Ncap, W, WR, Scap, RBcap, Rcap, Ccap, Ocap, npc, Pcap;
+    int o_pbps, o_pkey;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
         o_sti, o_stj, o_stl, o_stlev, o_evpos, o_evid, o_cc, o_perm, o_grp, o_gsz,
         o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, total;
@@ -144,11 +145,17 @@ struct Layout {
 
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-// extras = the batch carries reactivities (rcode array needed); with_fin = the
+// extras = 1: the batch carries reactivities (rcode array needed), 0: it does not, -1: plain batch
+// (no restraint classes either); with_fin = the
 // mode keeps the adjusted score of every survivor (MODE_STEP)
 // scap = most stems one structure can hold (0: the N/2 + 1 upper bound)
+// pcap = entries of the PERSISTENT run list (Cfg::PERSIST; 0: none).  That list replaces the run
+//        and survivor lists of the rescanning path and shares their space -- a sequence uses one
+//        path or the other -- but it is live between scans, so the level scratch gets its own room.
+// planes = bit-mask planes per direction (0: npc; the 2-bit-plane flavour needs 2)
 __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, int npc, int tw, int Rcap = 0,
-                                              int extras = 1, int with_fin = 1, int scap = 0)
+                                              int extras = 1, int with_fin = 1, int scap = 0, int pcap = 0,
+                                              int planes = 0)
 {
     Layout L{};
     L.Ncap = align_up(Nmax > 0 ? Nmax : 1, 32);
@@ -159,28 +166,41 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.RBcap = RBmax;
     L.Ccap = Ccap;
     L.Rcap = Rcap > 0 ? Rcap : Ccap;
+    L.Pcap = pcap;
     L.npc = npc;
+    if (planes <= 0) planes = npc;
     int o = 0;
-    L.o_cbps = o;    o += 8 * Ccap;                       // doubles first (8-byte aligned)
-    L.o_cfin = o;    o += with_fin ? 8 * Ccap : 0;
-    L.o_red = o;     o += (tw > 1) ? 32 * tw : 0;        // cross-warp reduction scratch
-    L.o_xchg = o;    o += (tw > 1) ? 2 * 16 * 16 : 0;     // cluster exchange: 2 parities x 16 ranks x (fin, key, len)
-    L.o_misc = o;    o += 64;
-    L.o_M = o;       o += 4 * npc * L.W;
-    L.o_PR = o;      o += 4 * npc * L.WR;
-    L.o_rowok = o;   o += 4 * L.W;
-    L.o_colokR = o;  o += 4 * L.WR;
-    L.o_Ub = o;      o += 4 * L.W;
-    L.o_Ubase = o;   o += 4 * (L.W + 1);
+    // ---- the lists (doubles first: 8-byte aligned)
+    L.o_cbps = o;    o += 8 * Ccap;
     L.o_ckey = o;    o += 4 * Ccap;
-    // run list; the level scratch (cc, gsz, perm, grp) is only live between two scans and shares its space
+    // run list; without a persistent list the level scratch (cc, gsz, perm, grp) is only live between
+    // two scans and shares its space
     int lev_bytes = 4 * L.Scap + 4 * L.Scap + 2 * L.Scap + 2 * L.Scap;
     int run_bytes = 4 * L.Rcap + 2 * L.Rcap;
-    int uni = align_up(lev_bytes > run_bytes ? lev_bytes : run_bytes, 4);
+    int uni = align_up((lev_bytes > run_bytes && pcap <= 0) ? lev_bytes : run_bytes, 4);
     L.Ocap = uni / 2;                                     // int16 entries team_choose can rank in this space
     L.o_rkey = o;    L.o_rlen = o + 4 * L.Rcap;
     L.o_cc = o;      L.o_gsz = o + 4 * L.Scap;  L.o_perm = o + 8 * L.Scap;  L.o_grp = o + 10 * L.Scap;
     o += uni;
+    L.o_clen = o;    o += 2 * Ccap;
+    L.o_pbps = 0;    L.o_pkey = 8 * pcap;
+    if (pcap > 0) {
+        if (o < 12 * pcap) o = 12 * pcap;
+        o = align_up(o, 4);
+        L.o_cc = o;  L.o_gsz = o + 4 * L.Scap;  L.o_perm = o + 8 * L.Scap;  L.o_grp = o + 10 * L.Scap;
+        o += align_up(lev_bytes, 4);
+    }
+    o = align_up(o, 8);
+    L.o_cfin = o;    o += with_fin ? 8 * Ccap : 0;
+    L.o_red = o;     o += (tw > 1) ? 32 * tw : 0;        // cross-warp reduction scratch
+    L.o_xchg = o;    o += (tw > 1) ? 2 * 16 * 16 : 0;     // cluster exchange: 2 parities x 16 ranks x (fin, key, len)
+    L.o_misc = o;    o += 64;
+    L.o_M = o;       o += 4 * planes * L.W;
+    L.o_PR = o;      o += 4 * planes * L.WR;
+    L.o_rowok = o;   o += 4 * L.W;
+    L.o_colokR = o;  o += 4 * L.WR;
+    L.o_Ub = o;      o += 4 * L.W;
+    L.o_Ubase = o;   o += 4 * (L.W + 1);
     L.o_partner = o; o += 2 * L.Ncap;
     L.o_owner = o;   o += 2 * L.Ncap;
     L.o_sepcnt = o;  o += 2 * (L.Ncap + 2);
@@ -191,10 +211,9 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_evid = o;    o += 4 * L.Scap;
     L.o_rbv = o;     o += 2 * (RBmax + 1);
     L.o_rbw = o;     o += 2 * (RBmax + 1);
-    L.o_clen = o;    o += 2 * Ccap;
-    L.o_rcode = o;   o += extras ? 2 * L.Ncap : 0;
+    L.o_rcode = o;   o += extras > 0 ? 2 * L.Ncap : 0;
     L.o_code = o;    o += L.Ncap;
-    L.o_rcl = o;     o += L.Ncap;
+    L.o_rcl = o;     o += extras >= 0 ? L.Ncap : 0;
     L.o_stlev = o;   o += L.Scap;
     L.total = align_up(o, 16);
     return L;
@@ -275,10 +294,14 @@ template <> struct Team<0> {
 //   CLUSTER: the team is a thread-block CLUSTER: every CTA keeps a full replica of the (small)
 //          sequence state in its own shared memory and scans every CS-th anti-diagonal; the
 //          CTA-local winners meet in rank 0's shared memory through DSMEM once per greedy step.
-template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1, bool CLUSTER_ = false>
+//   PERSIST: MODE_TAIL keeps the list of maximal runs ACROSS greedy steps (persist_build /
+//          persist_step): the anti-diagonals are enumerated once, afterwards only the runs that
+//          touch the stem just selected are cut into their surviving pieces.  Needs Layout::Pcap.
+template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1, bool CLUSTER_ = false,
+          bool PERSIST_ = false>
 struct Cfg {
     static constexpr int TW = TW_, MODE = MODE_;
-    static constexpr bool PLAIN = PLAIN_, STDP = STDP_, CLUSTER = CLUSTER_;
+    static constexpr bool PLAIN = PLAIN_, STDP = STDP_, CLUSTER = CLUSTER_, PERSIST = PERSIST_;
     static constexpr bool RUNLIST = RUNLIST_ < 0 ? (TW_ == 1) : (RUNLIST_ != 0);
 };
 
@@ -288,12 +311,12 @@ struct State {
     uint8_t  *code, *rcl, *stlev;
     uint16_t *rcode;
     int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *evpos, *evid, *perm, *grp, *rbv, *rbw;
-    uint32_t *M, *PR, *rowok, *colokR, *Ub, *ckey, *rkey;
+    uint32_t *M, *PR, *rowok, *colokR, *Ub, *ckey, *rkey, *pkey;
     int32_t  *cc, *gsz, *Ubase;
     uint16_t *clen, *rlen;
-    double   *cbps, *cfin, *red;
+    double   *cbps, *cfin, *red, *pbps;
     unsigned char *xchg;
-    int      *misc;      // [0] run count  [1] next item  [2..6] scratch  [7] survivor count
+    int      *misc;      // [0] run count  [1] next item  [2..6] scratch  [7] survivor count  [8] persistent entries
     const int32_t *cols; // global, per sequence
 };
 
@@ -315,6 +338,7 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
     s.cc = (int32_t *)(base + L.o_cc);  s.gsz = (int32_t *)(base + L.o_gsz);
     s.clen = (uint16_t *)(base + L.o_clen);  s.rlen = (uint16_t *)(base + L.o_rlen);
     s.cbps = (double *)(base + L.o_cbps);
+    s.pbps = (double *)(base + L.o_pbps);  s.pkey = (uint32_t *)(base + L.o_pkey);
     s.cfin = (double *)(base + L.o_cfin);
     s.red = (double *)(base + L.o_red);
     s.xchg = base + L.o_xchg;
@@ -1384,6 +1408,189 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
     return best;
 }
 
+// ------------------------------------------ persistent run list (MODE_TAIL)
+// AnnotateStems (seq.py:427-495) is a function of the masked bool matrix, and between two greedy
+// steps that matrix only LOSES cells: the rows and columns of the positions of the stem just
+// selected (seq.py:446-451; restraint cells die the same way, seq.py:438-443).  So every maximal
+// run of the next step is a piece of a maximal run of this one.  The list below holds the maximal
+// runs of at least minlen cells; a step cuts the runs that touch the new stem into their surviving
+// pieces, re-sums those (outer -> inner from 0.0, seq.py:416) and leaves the rest alone -- the
+// anti-diagonals are enumerated once per sequence instead of once per step.
+//
+// A run whose POSITIVE cell scores sum to less than minbpscore is dropped for good: the score of
+// any piece of it is <= that sum (also in floating point: rounding is monotone and every partial
+// sum of the positive terms dominates the matching partial sum of the piece), so no piece can pass
+// the bp-score filter of seq.py:492.
+//
+// entry = cand << 31 | s << 17 | a << 8 | len (s = i + j, a = outermost i), 0 = dead; cand: the run
+// passes minbpscore as it stands; pbps = its bp score.
+constexpr uint32_t PK_CAND = 0x80000000u;
+#ifdef SQRN_HOST_EMU
+static long g_emu_persist_steps = 0;      // tests assert that the persistent path really ran
+#endif
+__device__ __forceinline__ uint32_t pk_pack(int s, int a, int len) { return ((uint32_t)s << 17) | ((uint32_t)a << 8) | (uint32_t)len; }
+__device__ __forceinline__ int pk_len(uint32_t e) { return (int)(e & 255u); }
+__device__ __forceinline__ int pk_a(uint32_t e) { return (int)((e >> 8) & 511u); }
+__device__ __forceinline__ int pk_s(uint32_t e) { return (int)((e >> 17) & 0x3fffu); }
+__device__ __forceinline__ uint32_t pk_key(uint32_t e) { return ((uint32_t)pk_s(e) << 16) | (uint32_t)pk_a(e); }
+
+// bp score of a run and the sum of its positive cells
+template <class C>
+__device__ __forceinline__ double run_score_pos(const State &S, const DevParams &P, const DevBatch &B, int s, int a, int len,
+                                                double &pos)
+{
+    double sc = 0.0, ps = 0.0;
+    const bool simple = C::PLAIN || (!(S.has_react && !S.default_reacts) && !S.has_smat);
+    #pragma unroll 1
+    for (int q = 0; q < len; q++) {
+        double w = simple ? P.weight[S.code[a + q] * MAXK + S.code[s - a - q]] : cell_score(S, P, B, a + q, s - a - q);
+        sc = __dadd_rn(sc, w);
+        if (w > 0.0) ps = __dadd_rn(ps, w);
+    }
+    pos = ps;
+    return sc;
+}
+
+// worth trying: the expected number of runs fits the list (the list falls back when it overflows)
+__device__ __forceinline__ bool persist_wanted(const State &S, const DevParams &P, const Layout &L)
+{
+    if (L.Pcap <= 0 || S.N > 511) return false;
+    const double dens = P.m >= 4 ? 0.003 : (P.m == 3 ? 0.008 : 0.02);
+    return dens * S.N * (double)S.N <= 0.75 * L.Pcap;
+}
+
+// Enumerates the maximal runs of the current structure state into the persistent list.
+// false: the list overflowed (the caller rescans every step, as before).
+template <class C>
+__device__ bool persist_build(State &S, const DevParams &P, const DevBatch &B, const Layout &L)
+{
+    constexpr int TW = C::TW;
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const int Pcap = L.Pcap;
+    const int smax = 2 * S.N - 6;
+    if (r == 0) S.misc[8] = 0;
+    Team<TW>::sync();
+    int n = 0;                                   // entries [0, n) are scored and filtered
+    #pragma unroll 1
+    for (int s0 = 4; s0 <= smax; s0 += T) {
+        const int s = s0 + r;
+        if (s <= smax)
+            enum_diag<C>(S, P, B, s, [&](int a, int e) {
+                const int len = e - a + 1;
+                if ((double)len < P.minlen) return;
+                if (len > 255) { atomicAdd(&S.misc[8], 1 << 20); return; }
+                const int slot = atomicAdd(&S.misc[8], 1);
+                if (slot < Pcap) S.pkey[slot] = pk_pack(s, a, len);
+            });
+        Team<TW>::sync();
+        const int nr = S.misc[8];
+        if (nr > Pcap) return false;             // uniform
+        const bool last = s0 + T > smax;
+        if (nr - n < T && !last && nr + 2 * T <= Pcap) continue;
+        // score the new runs with dense lanes; keep those whose positive part can reach minbpscore
+        int nk = n;
+        #pragma unroll 1
+        for (int c0 = n; c0 < nr; c0 += T) {
+            const int c = c0 + r;
+            bool keep = false; uint32_t e = 0; double sc = 0.0;
+            if (c < nr) {
+                e = S.pkey[c];
+                double pos;
+                sc = run_score_pos<C>(S, P, B, pk_s(e), pk_a(e), pk_len(e), pos);
+                keep = pos >= P.minbpscore;
+                if (sc >= P.minbpscore) e |= PK_CAND;
+            }
+            int slot;
+            const int cnt = Team<TW>::claim(keep, &S.misc[6], nk, slot);      // barrier: this round's reads are done
+            if (keep) { S.pkey[slot] = e; S.pbps[slot] = sc; }
+            nk += cnt;
+        }
+        n = nk;
+        Team<TW>::sync();
+        if (r == 0) S.misc[8] = n;
+        Team<TW>::sync();
+    }
+    return true;
+}
+
+// One OptimalStems pass over the persistent list.  (ui, uj, ul) = the stem applied since the last
+// pass (ul = 0: none): runs touching it are cut first.  ok = false: the list overflowed while
+// pieces were appended (it is abandoned; the caller rescans).
+template <class C>
+__device__ Best persist_step(State &S, const DevParams &P, const DevBatch &B, const Layout &L, int ui, int uj, int ul, bool &ok)
+{
+    constexpr int TW = C::TW;
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    const int Pcap = L.Pcap;
+    int n = S.misc[8];
+    ok = true;
+#ifdef SQRN_HOST_EMU
+    g_emu_persist_steps++;
+#endif
+    if (ul > 0) {
+        const int u1 = ui + ul - 1, v0 = uj - ul + 1;      // dead positions: [ui, u1] and [v0, uj]
+        #pragma unroll 1
+        for (int c = r; c < n; c += T) {
+            const uint32_t e = S.pkey[c];
+            if (!e) continue;
+            const int len = pk_len(e), a = pk_a(e), s = pk_s(e), t = s - a;
+            // cell q of the run is (a + q, t - q): the q-ranges whose row or column died
+            const int A0 = ui - a, A1 = u1 - a, B0 = v0 - a, B1 = uj - a;
+            const int C0 = t - u1, C1 = t - ui, D0 = t - uj, D1 = t - v0;
+            const int top = len - 1;
+            const bool hit = (A0 <= top && A1 >= 0) || (B0 <= top && B1 >= 0) || (C0 <= top && C1 >= 0) || (D0 <= top && D1 >= 0);
+            if (!hit) continue;
+            auto dead = [&](int q) { return (q >= A0 && q <= A1) || (q >= B0 && q <= B1) || (q >= C0 && q <= C1) || (q >= D0 && q <= D1); };
+            bool first = true;
+            int q = 0;
+            #pragma unroll 1
+            while (q < len) {
+                #pragma unroll 1
+                while (q < len && dead(q)) q++;
+                const int st = q;
+                #pragma unroll 1
+                while (q < len && !dead(q)) q++;
+                const int pl = q - st;
+                if (pl <= 0 || (double)pl < P.minlen) continue;
+                double pos;
+                const double sc = run_score_pos<C>(S, P, B, s, a + st, pl, pos);
+                if (!(pos >= P.minbpscore)) continue;
+                const uint32_t ne = pk_pack(s, a + st, pl) | (sc >= P.minbpscore ? PK_CAND : 0u);
+                const int slot = first ? c : atomicAdd(&S.misc[8], 1);
+                if (slot < Pcap) { S.pkey[slot] = ne; S.pbps[slot] = sc; }
+                first = false;
+            }
+            if (first) S.pkey[c] = 0u;
+        }
+        Team<TW>::sync();
+        n = S.misc[8];
+        if (n > Pcap) { ok = false; n = Pcap; }
+        Team<TW>::sync();
+        if (!ok) return Best{-1e300, 0xffffffffu, 0};
+    }
+    Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
+    double floor = -1e300;
+    #pragma unroll 1
+    for (int c0 = 0; c0 < n; c0 += T) {
+        const int c = c0 + r;
+        if (c < n) {
+            const uint32_t e = S.pkey[c];
+            if (e & PK_CAND)
+                consider<C>(S, P, pk_key(e), pk_len(e), S.pbps[c], best.fin > floor ? best.fin : floor, best);
+        }
+#ifndef SQRN_HOST_EMU
+        if (TW == 1 && c0 + T < n) {
+            // share a lower bound of the best score so far (its high word): what cannot reach it is skipped
+            unsigned hi = best.fin > 0.0 ? (unsigned)__double2hiint(best.fin) : 0u;
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            const double f = __hiloint2double((int)hi, 0);
+            if (hi && f > floor) floor = f;
+        }
+#endif
+    }
+    return team_argmax<C>(S, best);
+}
+
 // two stems are "in conflict" when they share a paired position (seq.py:783-786)
 __device__ __forceinline__ bool iv_overlap(int a0, int a1, int b0, int b1) { return a0 <= b1 && b0 <= a1; }
 __device__ __forceinline__ bool stems_share(int i1, int j1, int l1, int i2, int j2, int l2)
@@ -1658,15 +1865,24 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
     if (mode == MODE_TAIL || mode == MODE_FINAL) {
         // the pool loop of seq.py:1159-1199 once it can no longer branch
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
+        bool persist = false;
+        int ui = 0, uj = 0, ul = 0;                 // the stem applied since the last pass over the list
+        if (C::PERSIST && !C::CLUSTER && mode == MODE_TAIL && (double)S.nst != P.maxstemnum && persist_wanted(S, P, L))
+            persist = persist_build<C>(S, P, B, L);
         #pragma unroll 1
         while (mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
-            Best b = team_scan<C>(S, P, B, L, -1.0);
+            Best b;
+            if (C::PERSIST && persist) {
+                b = persist_step<C>(S, P, B, L, ui, uj, ul, persist);
+                if (!persist) b = team_scan<C>(S, P, B, L, -1.0);
+            } else b = team_scan<C>(S, P, B, L, -1.0);
             b = cluster_best<C>(S, b, (int)calls);
             calls++;
             if (b.fin <= -1e300) break;
             int i = (int)(b.key & 0xffff);
-            team_apply_stem<C>(S, i, (int)(b.key >> 16) - i, b.len);
+            ui = i; uj = (int)(b.key >> 16) - i; ul = b.len;
+            team_apply_stem<C>(S, ui, uj, ul);
         }
         if (C::CLUSTER && S.doffset != 0) calls = 0;          // replicas: rank 0 reports
         else team_finalize<C>(S, P, B, Wk, item);

@@ -33,15 +33,17 @@ def lib():
         _lib = C.CDLL(build())
         _lib.emu_run.argtypes = [C.POINTER(ParamSet), C.c_int64] + [C.c_void_p] * 4 + [C.c_int, C.c_int] + \
             [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 13 + \
-            [C.c_int, C.c_void_p, C.c_int, C.c_int]
+            [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.emu_pyround3.restype = C.c_double
+        _lib.emu_persist_steps.restype = C.c_long
         _lib.emu_pyround3.argtypes = [C.c_double]
     return _lib
 
 
 def run(paramset, seqs, mode=MODE_TAIL, react_codes=None, react_values=None, react_comp=False,
         restr_class=None, rbps=None, smat=None, cols=None, interchainonly=False,
-        item_seq=None, init_stems=None, item_subopt=None, ccap=128, stem_cap=None, region_mode=0, flavour=0):
+        item_seq=None, init_stems=None, item_subopt=None, ccap=128, stem_cap=None, region_mode=0, flavour=0,
+        pcap=0):
     """seqs: list of normalised ungapped strings.  react_codes/restr_class: list of per-sequence uint8
     arrays; rbps: list of per-sequence (n,2) arrays; init_stems: list per item of (i,j,len) lists.
     Returns dict of numpy outputs."""
@@ -89,7 +91,7 @@ def run(paramset, seqs, mode=MODE_TAIL, react_codes=None, react_values=None, rea
                    ptr(sm), 0 if sm is None else sm.shape[0], ptr(cl), int(interchainonly),
                    mode, n_items, ptr(iseq), ptr(ioff), ptr(ist), ptr(isub),
                    ptr(out_off), ptr(out_stems), ptr(out_n), ptr(out_fin), ptr(out_raw), ptr(out_flags),
-                   ptr(dbn_off), ptr(dbn_a), ptr(dbn_c), int(ccap), C.byref(ncalls), int(region_mode), int(flavour))
+                   ptr(dbn_off), ptr(dbn_a), ptr(dbn_c), int(ccap), C.byref(ncalls), int(region_mode), int(flavour), int(pcap))
     assert rc == 0
     return dict(off=out_off, stems=out_stems, n=out_n[:n_items], fin=out_fin, raw=out_raw[:n_items],
                 flags=out_flags[:n_items], dbn_off=dbn_off, dbn_ascii=dbn_a, dbn_code=dbn_c,

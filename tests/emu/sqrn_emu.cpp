@@ -19,7 +19,7 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
                        const int32_t *init_stems, const double *item_subopt,
                        const int64_t *out_off, int32_t *out_stems, int32_t *out_nstems, double *out_stemfin,
                        double *out_raw, uint8_t *out_flags, const int64_t *dbn_off, uint8_t *dbn_ascii,
-                       int8_t *dbn_code, int ccap, unsigned long long *n_calls, int region_mode, int flavour)
+                       int8_t *dbn_code, int ccap, unsigned long long *n_calls, int region_mode, int flavour, int pcap)
 {
     int nmax = 1, rbmax = 0;
     for (int64_t b = 0; b < n_seqs; b++) {
@@ -46,18 +46,24 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     W.item_subopt = item_subopt; W.out_off = out_off; W.out_stems = out_stems; W.out_nstems = out_nstems;
     W.out_stemfin = out_stemfin; W.out_raw = out_raw; W.out_flags = out_flags; W.dbn_off = dbn_off;
     W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls; W.region_mode = region_mode;
-    Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0);
+    Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, (flavour == 3 || flavour == 4) ? pcap : 0);
     unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
     for (int item = 0; item < n_items; item++) {
         State S = bind_state(smem, Lay);
         if (flavour == 1) {            // the fast-lane flavour (plain batch, standard pairing table, MODE_TAIL)
             if (!H.p.std_pairs || rcode || rclass || rbp_off || smat || interchainonly || mode != MODE_TAIL) { free(smem); return -2; }
             team_run_item<Cfg<0, true, true, MODE_TAIL, 1>>(S, H.p, B, W, Lay, item);
-        } else if (flavour == 2) team_run_item<Cfg<0, false, false, -1, 1>>(S, H.p, B, W, Lay, item);   // run-list scan
+        } else if (flavour == 3) {     // the fast-lane flavour with the persistent run list (what k_fast runs)
+            if (!H.p.std_pairs || rcode || rclass || rbp_off || smat || interchainonly || mode != MODE_TAIL) { free(smem); return -2; }
+            team_run_item<Cfg<0, true, true, MODE_TAIL, 1, false, true>>(S, H.p, B, W, Lay, item);
+        } else if (flavour == 4) team_run_item<Cfg<0, false, false, -1, 1, false, true>>(S, H.p, B, W, Lay, item);   // general flavour, persistent list
+        else if (flavour == 2) team_run_item<Cfg<0, false, false, -1, 1>>(S, H.p, B, W, Lay, item);   // run-list scan
         else team_run_item<Cfg<0>>(S, H.p, B, W, Lay, item);                                              // per-thread rounds
     }
     free(smem);
     return 0;
 }
+
+extern "C" long emu_persist_steps(void) { return sqrn::g_emu_persist_steps; }
 
 extern "C" double emu_pyround3(double x) { return pyround3(x); }

@@ -30,7 +30,8 @@ def _prep_batch(cases):
     return preps, kw
 
 
-@pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist"], ids=["auto", "scan", "stems", "fastflavour", "runlist"])
+@pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist", "persist", "persist-small", "persist-general"],
+                         ids=["auto", "scan", "stems", "fastflavour", "runlist", "persist", "persist-smalllist", "persist-general"])
 @pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
                          ids=["fastest", "defG1", "defG2-smalllist", "ali"])
 def test_tail_plain(ps, ccap, region):
@@ -41,6 +42,14 @@ def test_tail_plain(ps, ccap, region):
         r = emu.run(ps, seqs, ccap=ccap, flavour=1)
     elif region == "runlist":  # the warp-team scan (shared run list) of the general flavour
         r = emu.run(ps, seqs, ccap=ccap, flavour=2)
+    elif region == "persist":  # what k_fast runs: the run list persists across greedy steps
+        before = emu.lib().emu_persist_steps()
+        r = emu.run(ps, seqs, ccap=ccap, flavour=3, pcap=4096)
+        assert emu.lib().emu_persist_steps() - before == r["ncalls"]        # every OptimalStems pass used the list
+    elif region == "persist-small":   # a list that overflows on the longer sequences (at build time or while
+        r = emu.run(ps, seqs, ccap=ccap, flavour=3, pcap=96)      # pieces are appended): falls back to rescanning
+    elif region == "persist-general":
+        r = emu.run(ps, seqs, ccap=ccap, flavour=4, pcap=4096)
     else:
         r = emu.run(ps, seqs, ccap=ccap, region_mode=region)
     for b, s in enumerate(seqs):
@@ -53,7 +62,7 @@ def test_tail_plain(ps, ccap, region):
         assert bool(r["flags"][b] & 1) == isint
 
 
-@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2)], ids=["scan", "stems", "runlist"])
+@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2), (0, 4)], ids=["scan", "stems", "runlist", "persist"])
 @pytest.mark.parametrize("interchain", [False, True])
 def test_tail_with_restraints_and_reactivities(interchain, region, flavour):
     rng = random.Random(32)
@@ -64,7 +73,7 @@ def test_tail_with_restraints_and_reactivities(interchain, region, flavour):
         sub = {k: [v[i] for i in idx] if isinstance(v, list) else v for k, v in kw.items()}
         for ps in (T.DEFG1, T.FASTEST):
             r = emu.run(ps, [preps[k].shortseq for k in idx], react_comp=comp, interchainonly=interchain,
-                            region_mode=region, flavour=flavour, **sub)
+                            region_mode=region, flavour=flavour, pcap=4096, **sub)
             for b, k in enumerate(idx):
                 p = preps[k]
                 _, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, [ps], interchainonly=interchain,
