@@ -47,6 +47,8 @@
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static inline uint32_t __brev(uint32_t x) { uint32_t y = 0; for (int b = 0; b < 32; b++) if (x >> b & 1) y |= 1u << (31 - b); return y; }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
@@ -415,6 +417,14 @@ __device__ __forceinline__ int unpaired_before(const State &S, int p)
     return S.Ubase[p >> 5] + __popc(S.Ub[p >> 5] & ((1u << (p & 31)) - 1u));
 }
 
+// bits p0 .. p0 + 4 of the unpaired mask (positions outside the sequence read as 0)
+__device__ __forceinline__ uint32_t unpaired_bits5(const State &S, int p0)
+{
+    const int w = p0 >> 5, sh = p0 & 31;
+    const uint32_t lo = (w >= 0 && w < S.W) ? S.Ub[w] : 0u, hi = (w + 1 >= 0 && w + 1 < S.W) ? S.Ub[w + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh) & 31u;
+}
+
 // word prefix of the unpaired mask (after Ub changed)
 template <class C>
 __device__ void team_unpaired_prefix(State &S)
@@ -442,6 +452,51 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
     const int64_t o = B.off[seq];
     const int N = (int)(B.off[seq + 1] - o);
     S.N = N; S.nst = 0;
+#ifndef SQRN_HOST_EMU
+    if (C::PLAIN && C::STDP && TW == 1) {
+        // fast lane: the forward masks come from ballots over the symbols as they are read (one
+        // coalesced pass), the reversed ones from the forward words by a funnel shift and a bit reversal
+        S.has_react = 0; S.has_smat = 0; S.cols = nullptr; S.default_reacts = 1; S.nrb = 0;
+        bool sep = false;
+        #pragma unroll 1
+        for (int k = 0; k < S.W; k++) {
+            const int p = 32 * k + r;
+            uint8_t c = CODE_OTHER;
+            if (p < N) c = P.code_table[B.sym[o + p]];
+            S.code[p] = c;
+            S.partner[p] = -1;
+            sep |= c == CODE_SEP;
+            const uint32_t in = __ballot_sync(0xffffffffu, p < N);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, p < N && (c & 1));
+            const uint32_t b1 = __ballot_sync(0xffffffffu, p < N && (c & 2));
+            const uint32_t okb = __ballot_sync(0xffffffffu, p < N && c < 4);
+            if (r == 0) {
+                S.M[k] = b0; S.M[S.W + k] = b1; S.rowok[k] = okb; S.Ub[k] = in;
+                S.Ubase[k] = (32 * k < N) ? 32 * k : N;
+            }
+        }
+        if (r == 0) S.Ubase[S.W] = N;
+        S.has_sep = __any_sync(0xffffffffu, sep);
+        __syncwarp();
+        // bit b of reversed word q is position N + 31 - 32 q - b: the forward window starting at N - 32 q, reversed
+        #pragma unroll 1
+        for (int q = r; q < S.WR; q += 32) {
+            const int p0 = N - 32 * q, w = p0 >> 5, sh = p0 & 31;
+            const bool lo_ok = w >= 0 && w < S.W, hi_ok = w + 1 >= 0 && w + 1 < S.W;
+            S.PR[q] = __brev(__funnelshift_r(lo_ok ? S.M[w] : 0u, hi_ok ? S.M[w + 1] : 0u, sh));
+            S.PR[S.WR + q] = __brev(__funnelshift_r(lo_ok ? S.M[S.W + w] : 0u, hi_ok ? S.M[S.W + w + 1] : 0u, sh));
+            S.colokR[q] = __brev(__funnelshift_r(lo_ok ? S.rowok[w] : 0u, hi_ok ? S.rowok[w + 1] : 0u, sh));
+        }
+        if (S.has_sep && r == 0) {
+            int c = 0;
+            #pragma unroll 1
+            for (int p = 0; p < N; p++) { S.sepcnt[p] = (int16_t)c; if (S.code[p] == CODE_SEP) c++; }
+            S.sepcnt[N] = (int16_t)c;
+        }
+        __syncwarp();
+        return;
+    }
+#endif
     S.has_react = !C::PLAIN && B.rcode != nullptr;
     S.has_smat = !C::PLAIN && B.smat != nullptr;
     S.cols = (!C::PLAIN && B.cols) ? B.cols + o : nullptr;
@@ -858,8 +913,15 @@ __device__ __forceinline__ bool diag_range(const State &S, const DevBatch &B, in
 __device__ __forceinline__ uint32_t run_starts(uint32_t x, uint32_t xn, uint32_t prev_top, int m)
 {
     if (!x) return 0u;
-    uint32_t y = x;
-    for (int t = 1; t < m; t++) y &= __funnelshift_r(x, xn, t);
+    // bit b of y: cells b .. b + have - 1 of the (x, xn) pair are all set; `have` doubles per step
+    uint32_t y = x, yn = xn;
+    #pragma unroll 1
+    for (int have = 1; have < m;) {
+        const int step = have < m - have ? have : m - have;
+        y &= __funnelshift_r(y, yn, step);
+        yn &= yn >> step;
+        have += step;
+    }
     return y & ~((x << 1) | prev_top);
 }
 
@@ -1031,14 +1093,17 @@ __device__ __forceinline__ double score_candidate(const State &S, const DevParam
     }
     bool goodout = false; int diff2 = 0;
     if (S.nst) {                                           // seq.py:700-711
-        int vv = oi - 1, ww = oj + 1;
-        #pragma unroll 1
-        while (vv >= 0 && oi - vv - 1 < 5 && S.partner[vv] < 0) vv--;
-        #pragma unroll 1
-        while (ww < N && ww - oj - 1 < 5 && S.partner[ww] < 0) ww++;
-        if (vv >= 0 && ww < N && S.partner[vv] == ww) {
-            int x = oi - vv - 1, y = ww - oj - 1, d = x > y ? x - y : y - x;
-            if (x <= 4 && y <= 4 && d <= 2) { goodout = true; diff2 = d; }
+        // the nearest paired position within five on either side, from the unpaired mask: the
+        // reference walks outwards over at most five unpaired positions (a sixth one, or the end of
+        // the sequence, cannot close a good loop: x, y <= 4)
+        const uint32_t pl = ~unpaired_bits5(S, oi - 5) & 31u;      // bit t: position oi - 5 + t is paired (or < 0)
+        const uint32_t pr = ~unpaired_bits5(S, oj + 1) & 31u;      // bit t: position oj + 1 + t is paired (or >= N)
+        if (pl && pr) {
+            const int vv = oi - 5 + (31 - __clz(pl)), ww = oj + 1 + (__ffs(pr) - 1);
+            if (vv >= 0 && ww < N && S.partner[vv] == ww) {
+                int x = oi - vv - 1, y = ww - oj - 1, d = x > y ? x - y : y - x;
+                if (d <= 2) { goodout = true; diff2 = d; }
+            }
         }
     }
     if (!goodloop && !goodout && len < 3) return -1.0;     // seq.py:744-745
@@ -1434,6 +1499,14 @@ __device__ __forceinline__ int pk_a(uint32_t e) { return (int)((e >> 8) & 511u);
 __device__ __forceinline__ int pk_s(uint32_t e) { return (int)((e >> 17) & 0x3fffu); }
 __device__ __forceinline__ uint32_t pk_key(uint32_t e) { return ((uint32_t)pk_s(e) << 16) | (uint32_t)pk_a(e); }
 
+// bits lo .. hi (clipped to 0 .. 31) set
+__device__ __forceinline__ uint32_t bits_between(int lo, int hi)
+{
+    if (lo < 0) lo = 0;
+    if (hi > 31) hi = 31;
+    return lo <= hi ? (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo) : 0u;
+}
+
 // bp score of a run and the sum of its positive cells
 template <class C>
 __device__ __forceinline__ double run_score_pos(const State &S, const DevParams &P, const DevBatch &B, int s, int a, int len,
@@ -1540,18 +1613,32 @@ __device__ Best persist_step(State &S, const DevParams &P, const DevBatch &B, co
             const int top = len - 1;
             const bool hit = (A0 <= top && A1 >= 0) || (B0 <= top && B1 >= 0) || (C0 <= top && C1 >= 0) || (D0 <= top && D1 >= 0);
             if (!hit) continue;
+            // the surviving pieces = runs of live cells: from a bit mask (the usual case, len <= 32) or a walk
+            uint32_t live = len <= 32 ? (0xffffffffu >> (32 - len)) & ~(bits_between(A0, A1) | bits_between(B0, B1) |
+                                                                        bits_between(C0, C1) | bits_between(D0, D1)) : 0u;
             auto dead = [&](int q) { return (q >= A0 && q <= A1) || (q >= B0 && q <= B1) || (q >= C0 && q <= C1) || (q >= D0 && q <= D1); };
             bool first = true;
             int q = 0;
             #pragma unroll 1
-            while (q < len) {
-                #pragma unroll 1
-                while (q < len && dead(q)) q++;
-                const int st = q;
-                #pragma unroll 1
-                while (q < len && !dead(q)) q++;
-                const int pl = q - st;
-                if (pl <= 0 || (double)pl < P.minlen) continue;
+            for (;;) {
+                int st, pl;
+                if (len <= 32) {
+                    if (!live) break;
+                    st = __ffs(live) - 1;
+                    const uint32_t inv = ~(live >> st);
+                    pl = inv ? __ffs(inv) - 1 : 32;
+                    live = (st + pl >= 32) ? 0u : (live >> (st + pl)) << (st + pl);
+                } else {
+                    #pragma unroll 1
+                    while (q < len && dead(q)) q++;
+                    if (q >= len) break;
+                    st = q;
+                    #pragma unroll 1
+                    while (q < len && !dead(q)) q++;
+                    pl = q - st;
+                }
+                if ((double)pl < P.minlen) continue;
+                // re-summed from the piece's own outermost cell (seq.py:416)
                 double pos;
                 const double sc = run_score_pos<C>(S, P, B, s, a + st, pl, pos);
                 if (!(pos >= P.minbpscore)) continue;

@@ -19,6 +19,13 @@ _OPEN = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ"
 _CLOSE = ")]}>abcdefghijklmnopqrstuvwxyz"
 
 
+# competing helices with runs of more than 32 cells (the persistent list cuts those by a cell walk,
+# not by the 32-bit mask) and low-complexity repeats (many long overlapping runs)
+LONG_RUNS = ["G" * 40 + "AAAA" + "C" * 40 + "AAAA" + "G" * 40,
+             "G" * 36 + "U" + "C" * 45 + "GAAA" + "G" * 38 + "A" + "C" * 20,
+             "GC" * 50, "GGGCCC" * 20, "A" * 35 + "GAAA" + "U" * 50 + "GCGC" + "A" * 40]
+
+
 def _prep_batch(cases):
     preps = [S._prepare(c[0], c[1], c[2], None) for c in cases]
     table, codes = {}, []
@@ -37,7 +44,7 @@ def _prep_batch(cases):
 def test_tail_plain(ps, ccap, region):
     """single-path greedy (pl=1) on plain sequences: stems, dbn, raw scores; the ScoreStems region
     evaluated by the reference's position scan, by the stem walk, and by the automatic choice"""
-    seqs = T.rand_seqs(31, 150, 5, 210) + T.rand_seqs(36, 40, 5, 150, "ACGUN")
+    seqs = T.rand_seqs(31, 150, 5, 210) + T.rand_seqs(36, 40, 5, 150, "ACGUN") + LONG_RUNS
     if region == "fast":       # compile-time flavour of the byseq fast lane: bit planes, stem walk only
         r = emu.run(ps, seqs, ccap=ccap, flavour=1)
     elif region == "runlist":  # the warp-team scan (shared run list) of the general flavour

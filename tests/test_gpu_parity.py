@@ -42,6 +42,9 @@ def test_fast_lane_edge_lengths(gpu_ctx):
     seqs = ["A", "GC", "GGGG", "GGGAAACCC", "GGGGAAAACCCC", "GCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGC",
             "G" * 40 + "AAAA" + "C" * 40, "GGGGGGGGGGCCCCCCCCCC" * 10]
     seqs += T.rand_seqs(12, 300, 1, 12)
+    # competing helices with runs of more than 32 cells (persistent run list: cut by a cell walk)
+    seqs += ["G" * 40 + "AAAA" + "C" * 40 + "AAAA" + "G" * 40, "G" * 36 + "U" + "C" * 45 + "GAAA" + "G" * 38 + "A" + "C" * 20,
+             "GC" * 50, "GGGCCC" * 20, "A" * 35 + "GAAA" + "U" * 50 + "GCGC" + "A" * 40, "GC" * 110, "GGGGCCCC" * 27]
     _check_fast(gpu_ctx, T.FASTEST, seqs)
     _check_fast(gpu_ctx, T.DEFG1, seqs)
 
