@@ -27,6 +27,7 @@ __device__ __forceinline__ void work_loop(const DevParams *__restrict__ Pg, cons
     {
         const int *src = reinterpret_cast<const int *>(Pg);
         int *dst = reinterpret_cast<int *>(&Psh);
+        #pragma unroll 1
         for (int k = threadIdx.x; k < (int)(sizeof(DevParams) / 4); k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();

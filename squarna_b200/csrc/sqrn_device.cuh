@@ -1143,6 +1143,24 @@ __device__ __forceinline__ Best team_argmax(State &S, Best best)
 {
     constexpr int TW = C::TW;
 #ifndef SQRN_HOST_EMU
+    if (TW == 1) {
+        // three warp reductions on an order-preserving integer image of the score (high word, low word)
+        // and the enumeration key, instead of five shuffle rounds of (double, key, len)
+        unsigned long long u = (unsigned long long)__double_as_longlong(__dadd_rn(best.fin, 0.0));      // -0.0 -> +0.0
+        u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+        const uint32_t hi = (uint32_t)(u >> 32), lo = (uint32_t)u;
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+        bool in = hi == mh;
+        const uint32_t ml = __reduce_max_sync(0xffffffffu, in ? lo : 0u);
+        in = in && lo == ml;
+        const uint32_t mk = __reduce_min_sync(0xffffffffu, in ? best.key : 0xffffffffu);
+        in = in && best.key == mk;
+        const int src = __ffs(__ballot_sync(0xffffffffu, in)) - 1;
+        best.fin = __shfl_sync(0xffffffffu, best.fin, src);
+        best.len = __shfl_sync(0xffffffffu, best.len, src);
+        best.key = mk;
+        return best;
+    }
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         double f = __shfl_xor_sync(0xffffffffu, best.fin, d);
@@ -1800,12 +1818,13 @@ __device__ __forceinline__ double round3_fast(double x, bool &ok)
 // ------------------------------------------------------------- finalisation
 // ScoreStruct (seq.py:861-899) + dbn of the finished structure.
 template <class C>
-__device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk, int item)
+__device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, const DevWork &Wk, int item,
+                              bool levels_valid = false)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int N = S.N;
-    team_levels<C>(S);
+    if (!levels_valid) team_levels<C>(S);         // stlev[] of the final structure
     int64_t doff = Wk.dbn_off ? Wk.dbn_off[item] : 0;
     if (Wk.out_dbn_ascii || Wk.out_dbn_code) {
         const int64_t so = B.off[Wk.item_seq ? Wk.item_seq[item] : item];
@@ -1956,9 +1975,11 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         int ui = 0, uj = 0, ul = 0;                 // the stem applied since the last pass over the list
         if (C::PERSIST && !C::CLUSTER && mode == MODE_TAIL && (double)S.nst != P.maxstemnum && persist_wanted(S, P, L))
             persist = persist_build<C>(S, P, B, L);
+        bool lev_ok = false;                        // stlev[] matches the current stem set
         #pragma unroll 1
         while (mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
+            lev_ok = true;
             Best b;
             if (C::PERSIST && persist) {
                 b = persist_step<C>(S, P, B, L, ui, uj, ul, persist);
@@ -1970,9 +1991,10 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
             int i = (int)(b.key & 0xffff);
             ui = i; uj = (int)(b.key >> 16) - i; ul = b.len;
             team_apply_stem<C>(S, ui, uj, ul);
+            lev_ok = false;
         }
         if (C::CLUSTER && S.doffset != 0) calls = 0;          // replicas: rank 0 reports
-        else team_finalize<C>(S, P, B, Wk, item);
+        else team_finalize<C>(S, P, B, Wk, item, lev_ok);
     } else if (mode == MODE_STEP) {
         int n = 0;
         int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
