@@ -33,6 +33,7 @@ __device__ __forceinline__ void work_loop(const DevParams *__restrict__ Pg, cons
     __syncthreads();
     const int team = (TW == 1) ? (threadIdx.x >> 5) : 0;
     State S = bind_state(smem + (size_t)team * L.total, L);
+    const int n_items = Wk.n_items_dev ? *Wk.n_items_dev : Wk.n_items;
     for (;;) {
         int item = 0;
         if (TW == 1) {
@@ -44,7 +45,7 @@ __device__ __forceinline__ void work_loop(const DevParams *__restrict__ Pg, cons
             item = S.misc[1];
             __syncthreads();
         }
-        if (item >= Wk.n_items) break;
+        if (item >= n_items) break;
         item = Wk.order ? Wk.order[item] : item + Wk.item_base;
         team_run_item<C>(S, Psh, B, Wk, L, item);
     }
@@ -107,6 +108,10 @@ template <int NCAP> __host__ __device__ constexpr Layout fast_layout()
 {
     return make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, -1, 0, NCAP / 4 + 2, fast_pcap(NCAP), 2);
 }
+template <int NCAP> __host__ __device__ constexpr Layout rescan_layout()
+{
+    return make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, -1, 0, NCAP / 4 + 2, 0, 2);
+}
 template <int NCAP>
 __global__ void __launch_bounds__(32 * FAST_TEAMS, 4)
 k_fast(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk)
@@ -114,6 +119,16 @@ k_fast(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk)
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr Layout L = fast_layout<NCAP>();
     work_loop<Cfg<1, true, true, MODE_TAIL, -1, false, true>>(Pg, B, Wk, L, smem);
+}
+// The same lane without the persistent run list: every greedy step re-enumerates the anti-diagonals.
+// Runs behind k_fast on the items whose list overflowed (DevWork::ovf_list), normally none.
+template <int NCAP>
+__global__ void __launch_bounds__(32 * FAST_TEAMS, 4)
+k_fast_rescan(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr Layout L = rescan_layout<NCAP>();
+    work_loop<Cfg<1, true, true, MODE_TAIL>>(Pg, B, Wk, L, smem);
 }
 
 // ----------------------------------------------------------------- context
@@ -154,7 +169,7 @@ struct CachedStems {
 
 enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -300,7 +315,8 @@ static int get_params(sqrn_ctx *ctx, const sqrn_paramset &ps, int nmax, const PE
 }
 
 // ------------------------------------------------------------- launch plan
-struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; int cluster = 0; bool cl_plain = false; };
+struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; int cluster = 0; bool cl_plain = false;
+              size_t smem_rescan = 0; int grid_rescan = 0; };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -363,6 +379,12 @@ static int plan_fast(sqrn_ctx *ctx, Plan &pl)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fast<NCAP>, pl.threads, pl.smem));
     if (nb < 1) { ctx->err = "kernel does not fit on an SM"; return SQRN_E_UNSUPPORTED; }
     pl.grid = nb * ctx->sm_count;
+    constexpr Layout L2 = rescan_layout<NCAP>();
+    pl.smem_rescan = (size_t)FAST_TEAMS * L2.total;
+    CK(cudaFuncSetAttribute(k_fast_rescan<NCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rescan));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fast_rescan<NCAP>, pl.threads, pl.smem_rescan));
+    if (nb < 1) { ctx->err = "kernel does not fit on an SM"; return SQRN_E_UNSUPPORTED; }
+    pl.grid_rescan = nb * ctx->sm_count;
     return SQRN_OK;
 }
 
@@ -437,9 +459,21 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
     int grid = pl.grid;
     int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
     if (grid > teams) grid = std::max(teams, 1);
-    if (pl.fast_ncap == 128) k_fast<128><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
-    else if (pl.fast_ncap == 224) k_fast<224><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
-    else if (pl.fast_ncap == 320) k_fast<320><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W);
+    if (pl.fast_ncap) {
+        if (!W.ovf_list || !W.ovf_count || !W.n_items_dev) { ctx->err = "fast lane launched without an overflow list"; return SQRN_E_BADARG; }
+        DevWork W1 = W; W1.n_items_dev = nullptr;
+        if (pl.fast_ncap == 128) k_fast<128><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
+        else if (pl.fast_ncap == 224) k_fast<224><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
+        else k_fast<320><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
+        CK(cudaGetLastError());
+        // the items whose run list overflowed (usually none: the CTAs then leave at once)
+        DevWork W2 = W; W2.order = W.ovf_list; W2.counter = W.ovf_count + 1; W2.ovf_list = nullptr; W2.ovf_count = nullptr;
+        const int g2 = std::min(grid, pl.grid_rescan);
+        if (pl.fast_ncap == 128) k_fast_rescan<128><<<g2, pl.threads, pl.smem_rescan, st>>>(P.d_p, B, W2);
+        else if (pl.fast_ncap == 224) k_fast_rescan<224><<<g2, pl.threads, pl.smem_rescan, st>>>(P.d_p, B, W2);
+        else k_fast_rescan<320><<<g2, pl.threads, pl.smem_rescan, st>>>(P.d_p, B, W2);
+        ctx->n_launches++;
+    }
     else if (pl.tw == 1) k_work<1><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
     else if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
     else k_work<32><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W, pl.L);
@@ -478,7 +512,7 @@ static int dalloc(sqrn_ctx *ctx, int slot, size_t count, T **d)
 // one launch over items [item_base, item_base + n_items) of a resident CSR batch
 static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t st, int64_t item_base, int64_t n_items,
                        const int64_t *d_offsets, const uint8_t *d_symbols, uint8_t *d_dbn_ascii, double *d_scores,
-                       int32_t *d_n_stems, uint8_t *d_flags, int *d_counter, unsigned long long *d_ncalls, int round3,
+                       int32_t *d_n_stems, uint8_t *d_flags, int *d_counter, int32_t *d_ovf, unsigned long long *d_ncalls, int round3,
                        cudaEvent_t e0, cudaEvent_t e1)
 {
     DevBatch B; memset(&B, 0, sizeof B);
@@ -486,6 +520,9 @@ static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStrea
     DevWork W; memset(&W, 0, sizeof W);
     W.n_items = (int)n_items; W.item_base = (int)item_base; W.mode = MODE_TAIL; W.region_mode = ctx->region_mode;
     W.round3 = round3; W.counter = d_counter; W.out_flags = d_flags; W.n_calls = d_ncalls;
+    if (pl.fast_ncap) {          // [counter, overflow count, counter of the rescanning kernel]; list slots of this item range
+        W.ovf_count = d_counter + 1; W.n_items_dev = d_counter + 1; W.ovf_list = d_ovf + item_base;
+    }
     W.out_nstems = d_n_stems; W.out_raw = d_scores; W.dbn_off = d_offsets; W.out_dbn_ascii = d_dbn_ascii;
     if (e0) CK(cudaEventRecord(e0, st));
     TRY(dispatch(ctx, P, pl, st, B, W));
@@ -507,13 +544,15 @@ extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, 
     Plan pl;
     TRY(make_fast_plan(ctx, *P, max_len, (int)n_seqs, pl));
     int *d_counter; uint8_t *d_flags; unsigned long long *d_nc;
-    TRY(dalloc(ctx, W_COUNTER, FAST_MAX_CHUNKS, &d_counter));
+    int32_t *d_ovf;
+    TRY(dalloc(ctx, W_COUNTER, 4 * FAST_MAX_CHUNKS, &d_counter));
+    TRY(dalloc(ctx, W_OVF, (size_t)n_seqs, &d_ovf));
     TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &d_flags));
     TRY(dalloc(ctx, W_NCALLS, 1, &d_nc));
-    CK(cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d_counter, 0, 4 * sizeof(int), ctx->stream));
     CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), ctx->stream));
     int rc = fast_launch(ctx, *P, pl, ctx->stream, 0, n_seqs, d_offsets, d_symbols, d_dbn_ascii, d_scores, d_n_stems,
-                         d_flags, d_counter, d_nc, 0, ctx->ev0, ctx->ev1);
+                         d_flags, d_counter, d_ovf, d_nc, 0, ctx->ev0, ctx->ev1);
     if (rc == SQRN_OK) ctx->ev_valid = true;
     return rc;
 }
@@ -549,7 +588,9 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     TRY(dalloc(ctx, W_ORAW, (size_t)n_seqs * 3, &d_sc));
     TRY(dalloc(ctx, W_ON, (size_t)n_seqs, &d_ns));
     TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &d_flags));
-    TRY(dalloc(ctx, W_COUNTER, FAST_MAX_CHUNKS, &d_counter));
+    int32_t *d_ovf;
+    TRY(dalloc(ctx, W_COUNTER, 4 * FAST_MAX_CHUNKS, &d_counter));
+    TRY(dalloc(ctx, W_OVF, (size_t)n_seqs, &d_ovf));
     TRY(dalloc(ctx, W_NCALLS, 1, &d_nc));
     if (ctx->hflags_cap < (size_t)n_seqs) {
         if (ctx->hflags) cudaFreeHost(ctx->hflags);
@@ -562,7 +603,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     int nchunks = (int)std::min<int64_t>(FAST_MAX_CHUNKS, std::max<int64_t>(1, n_seqs / 65536));
     if (const char *e = getenv("SQRN_FAST_CHUNKS")) nchunks = std::max(1, std::min(FAST_MAX_CHUNKS, atoi(e)));
     cudaStream_t s_main = ctx->stream;
-    CK(cudaMemsetAsync(d_counter, 0, FAST_MAX_CHUNKS * sizeof(int), s_main));
+    CK(cudaMemsetAsync(d_counter, 0, 4 * FAST_MAX_CHUNKS * sizeof(int), s_main));
     CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), s_main));
     CK(cudaEventRecord(ctx->ev_start, s_main));
     CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
@@ -578,7 +619,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         // stage 2: kernel
         CK(cudaStreamWaitEvent(s_k, ctx->ev_in[c], 0));
         if (c == 1) CK(cudaStreamWaitEvent(s_k, ctx->ev_start, 0));
-        TRY(fast_launch(ctx, *P, pl, s_k, b0, b1 - b0, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + c, d_nc, 1,
+        TRY(fast_launch(ctx, *P, pl, s_k, b0, b1 - b0, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + 4 * c, d_ovf, d_nc, 1,
                         ctx->ev_k0[c], ctx->ev_k1[c]));
         // stage 3: outputs of the chunk
         CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k1[c], 0));

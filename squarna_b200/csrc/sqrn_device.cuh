@@ -123,6 +123,9 @@ struct DevWork {
     const int32_t *init_stems;   // i, j, len
     const double  *item_subopt;  // MODE_STEP: cursubopt per item
     int           *counter;      // global work counter (zeroed before launch)
+    const int     *n_items_dev;  // if set, the item count is read from here (a list an earlier kernel of the stream filled)
+    int           *ovf_count;    // Cfg::PERSIST kernels: items whose run list overflowed are appended here and
+    int32_t       *ovf_list;     //   left to a rescanning kernel launched behind them (order = ovf_list)
     // outputs
     const int64_t *out_off;      // [n_items+1] capacity CSR for stems
     int32_t       *out_stems;    // i, j, len
@@ -299,6 +302,9 @@ template <> struct Team<0> {
 //   PERSIST: MODE_TAIL keeps the list of maximal runs ACROSS greedy steps (persist_build /
 //          persist_step): the anti-diagonals are enumerated once, afterwards only the runs that
 //          touch the stem just selected are cut into their surviving pieces.  Needs Layout::Pcap.
+//          A PERSIST kernel carries no rescanning code at all (its hot instruction range has to
+//          fit the SM's instruction cache): an item whose list overflows is appended to
+//          DevWork::ovf_list and redone from scratch by a non-PERSIST kernel.
 template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1, bool CLUSTER_ = false,
           bool PERSIST_ = false>
 struct Cfg {
@@ -1543,11 +1549,11 @@ __device__ __forceinline__ double run_score_pos(const State &S, const DevParams 
 }
 
 // worth trying: the expected number of runs fits the list (the list falls back when it overflows)
-__device__ __forceinline__ bool persist_wanted(const State &S, const DevParams &P, const Layout &L)
+__device__ __forceinline__ bool persist_wanted(int N, const DevParams &P, const Layout &L)
 {
-    if (L.Pcap <= 0 || S.N > 511) return false;
+    if (L.Pcap <= 0 || N > 511) return false;
     const double dens = P.m >= 4 ? 0.003 : (P.m == 3 ? 0.008 : 0.02);
-    return dens * S.N * (double)S.N <= 0.75 * L.Pcap;
+    return dens * N * (double)N <= 0.75 * L.Pcap;
 }
 
 // Enumerates the maximal runs of the current structure state into the persistent list.
@@ -1959,6 +1965,14 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
     const int seq = Wk.item_seq ? Wk.item_seq[item] : item;
     const int mode = C::MODE >= 0 ? C::MODE : Wk.mode;
     S.region_mode = Wk.region_mode;
+    if (C::PERSIST) {
+        // hopeless for the list (too long for this parameter set): straight to the rescanning kernel
+        const int N = (int)(B.off[seq + 1] - B.off[seq]);
+        if (!persist_wanted(N, P, L)) {
+            if (r == 0) { const int slot = atomicAdd(Wk.ovf_count, 1); Wk.ovf_list[slot] = item; }
+            return;
+        }
+    }
     team_load<C>(S, B, P, seq);
     if (Wk.init_off) {
         const int64_t k0 = Wk.init_off[item], k1 = Wk.init_off[item + 1];
@@ -1971,19 +1985,18 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
     if (mode == MODE_TAIL || mode == MODE_FINAL) {
         // the pool loop of seq.py:1159-1199 once it can no longer branch
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
-        bool persist = false;
+        bool ok = true;                             // PERSIST: the run list has not overflowed
         int ui = 0, uj = 0, ul = 0;                 // the stem applied since the last pass over the list
-        if (C::PERSIST && !C::CLUSTER && mode == MODE_TAIL && (double)S.nst != P.maxstemnum && persist_wanted(S, P, L))
-            persist = persist_build<C>(S, P, B, L);
+        if (C::PERSIST && mode == MODE_TAIL && (double)S.nst != P.maxstemnum) ok = persist_build<C>(S, P, B, L);
         bool lev_ok = false;                        // stlev[] matches the current stem set
         #pragma unroll 1
-        while (mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
+        while (ok && mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
             lev_ok = true;
             Best b;
-            if (C::PERSIST && persist) {
-                b = persist_step<C>(S, P, B, L, ui, uj, ul, persist);
-                if (!persist) b = team_scan<C>(S, P, B, L, -1.0);
+            if (C::PERSIST) {
+                b = persist_step<C>(S, P, B, L, ui, uj, ul, ok);
+                if (!ok) break;
             } else b = team_scan<C>(S, P, B, L, -1.0);
             b = cluster_best<C>(S, b, (int)calls);
             calls++;
@@ -1992,6 +2005,11 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
             ui = i; uj = (int)(b.key >> 16) - i; ul = b.len;
             team_apply_stem<C>(S, ui, uj, ul);
             lev_ok = false;
+        }
+        if (C::PERSIST && !ok) {
+            if (r == 0) { const int slot = atomicAdd(Wk.ovf_count, 1); Wk.ovf_list[slot] = item; }
+            Team<TW>::sync();
+            return;
         }
         if (C::CLUSTER && S.doffset != 0) calls = 0;          // replicas: rank 0 reports
         else team_finalize<C>(S, P, B, Wk, item, lev_ok);

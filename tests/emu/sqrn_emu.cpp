@@ -48,7 +48,14 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls; W.region_mode = region_mode;
     Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, (flavour == 3 || flavour == 4) ? pcap : 0);
     unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
-    for (int item = 0; item < n_items; item++) {
+    // PERSIST flavours park the items whose run list overflowed; they are redone by the rescanning flavour
+    std::vector<int32_t> ovf((size_t)n_items + 1); int n_ovf = 0;
+    W.ovf_list = ovf.data(); W.ovf_count = &n_ovf;
+    for (int pass = 0; pass < 2; pass++) {
+    const int todo = pass == 0 ? n_items : n_ovf;
+    if (pass == 1) { if (flavour == 3) flavour = 1; else if (flavour == 4) flavour = 2; }
+    for (int q = 0; q < todo; q++) {
+        const int item = pass == 0 ? q : ovf[q];
         State S = bind_state(smem, Lay);
         if (flavour == 1) {            // the fast-lane flavour (plain batch, standard pairing table, MODE_TAIL)
             if (!H.p.std_pairs || rcode || rclass || rbp_off || smat || interchainonly || mode != MODE_TAIL) { free(smem); return -2; }
@@ -59,6 +66,8 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
         } else if (flavour == 4) team_run_item<Cfg<0, false, false, -1, 1, false, true>>(S, H.p, B, W, Lay, item);   // general flavour, persistent list
         else if (flavour == 2) team_run_item<Cfg<0, false, false, -1, 1>>(S, H.p, B, W, Lay, item);   // run-list scan
         else team_run_item<Cfg<0>>(S, H.p, B, W, Lay, item);                                              // per-thread rounds
+    }
+    if (flavour != 3 && flavour != 4) break;
     }
     free(smem);
     return 0;
