@@ -147,7 +147,7 @@ struct DBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-constexpr int FAST_MAX_CHUNKS = 16;
+constexpr int FAST_MAX_CHUNKS = 20;
 
 struct PEntry {
     sqrn_paramset ps; int nmax; DevParams hp; DevParams *d_p; double *d_lut;
@@ -177,7 +177,7 @@ struct sqrn_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr, s_k2 = nullptr;       // copy-in, copy-out, second kernel stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
     cudaEvent_t ev_start = nullptr, ev_out = nullptr, ev_k2done = nullptr;
-    cudaEvent_t ev_in[FAST_MAX_CHUNKS] = {}, ev_k0[FAST_MAX_CHUNKS] = {}, ev_k1[FAST_MAX_CHUNKS] = {};
+    cudaEvent_t ev_in[FAST_MAX_CHUNKS] = {}, ev_k0[FAST_MAX_CHUNKS] = {}, ev_k1[FAST_MAX_CHUNKS] = {}, ev_o[FAST_MAX_CHUNKS] = {};
     uint8_t *hflags = nullptr; size_t hflags_cap = 0;                    // pinned staging for the result flags
     std::string err;
     int sm_count = 0; size_t smem_optin = 0;
@@ -237,7 +237,8 @@ extern "C" int sqrn_ctx_create(int device, sqrn_ctx **out)
               cudaEventCreateWithFlags(&ctx->ev_k2done, cudaEventDisableTiming) == cudaSuccess;
     for (int c = 0; c < FAST_MAX_CHUNKS && ok; c++)
         ok = cudaEventCreateWithFlags(&ctx->ev_in[c], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreate(&ctx->ev_k0[c]) == cudaSuccess && cudaEventCreate(&ctx->ev_k1[c]) == cudaSuccess;
+             cudaEventCreate(&ctx->ev_k0[c]) == cudaSuccess && cudaEventCreate(&ctx->ev_k1[c]) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_o[c], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { g_create_err = std::string("context creation failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return SQRN_E_CUDA; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
@@ -258,7 +259,7 @@ extern "C" void sqrn_ctx_destroy(sqrn_ctx *ctx)
     cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_k2);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_out); cudaEventDestroy(ctx->ev_k2done);
-    for (int c = 0; c < FAST_MAX_CHUNKS; c++) { cudaEventDestroy(ctx->ev_in[c]); cudaEventDestroy(ctx->ev_k0[c]); cudaEventDestroy(ctx->ev_k1[c]); }
+    for (int c = 0; c < FAST_MAX_CHUNKS; c++) { cudaEventDestroy(ctx->ev_in[c]); cudaEventDestroy(ctx->ev_k0[c]); cudaEventDestroy(ctx->ev_k1[c]); cudaEventDestroy(ctx->ev_o[c]); }
     if (ctx->hflags) cudaFreeHost(ctx->hflags);
     delete ctx;
 }
@@ -571,16 +572,6 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_0 = now();
     const int64_t total = offsets[n_seqs];
-    int max_len = 0;
-    for (int64_t b = 0; b < n_seqs; b++) {
-        int64_t n = offsets[b + 1] - offsets[b];
-        if (n < 0 || n > SQRN_MAX_LEN) { ctx->err = "sequence length out of range"; return SQRN_E_BADARG; }
-        if (n > max_len) max_len = (int)n;
-    }
-    const PEntry *P;
-    TRY(get_params(ctx, *ps, max_len, &P));
-    Plan pl;
-    TRY(make_fast_plan(ctx, *P, max_len, (int)n_seqs, pl));
     int64_t *d_off; uint8_t *d_sym, *d_dbn, *d_flags; double *d_sc; int32_t *d_ns; int *d_counter; unsigned long long *d_nc;
     TRY(dalloc(ctx, B_OFF, (size_t)n_seqs + 1, &d_off));
     TRY(dalloc(ctx, B_SYM, (size_t)std::max<int64_t>(total, 1), &d_sym));
@@ -599,18 +590,41 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         ctx->hflags_cap = (size_t)n_seqs + 64;
     }
     const double t_1 = now();
-    // chunks of at least 64 Ki sequences, at most FAST_MAX_CHUNKS
-    int nchunks = (int)std::min<int64_t>(FAST_MAX_CHUNKS, std::max<int64_t>(1, n_seqs / 65536));
-    if (const char *e = getenv("SQRN_FAST_CHUNKS")) nchunks = std::max(1, std::min(FAST_MAX_CHUNKS, atoi(e)));
+    // chunks of at least 64 Ki sequences; the first and the last one are cut again (1/4 + 3/4, 2/3 + 1/3) so that
+    // the pipeline fills and drains on small pieces
+    int nbase = (int)std::min<int64_t>(FAST_MAX_CHUNKS - 2, std::max<int64_t>(1, n_seqs / 65536));
+    if (const char *e = getenv("SQRN_FAST_CHUNKS")) nbase = std::max(1, std::min(FAST_MAX_CHUNKS - 2, atoi(e)));
+    int64_t bounds[FAST_MAX_CHUNKS + 1];
+    int nchunks = 0;
+    bounds[0] = 0;
+    for (int c = 0; c < nbase; c++) {
+        const int64_t lo = n_seqs * c / nbase, hi = n_seqs * (c + 1) / nbase;
+        if (nbase >= 4 && c == 0) bounds[++nchunks] = lo + (hi - lo) / 4;
+        if (nbase >= 4 && c == nbase - 1) bounds[++nchunks] = lo + (hi - lo) * 2 / 3;
+        bounds[++nchunks] = hi;
+    }
     cudaStream_t s_main = ctx->stream;
     CK(cudaMemsetAsync(d_counter, 0, 4 * FAST_MAX_CHUNKS * sizeof(int), s_main));
     CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), s_main));
     CK(cudaEventRecord(ctx->ev_start, s_main));
     CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    Plan plans[4]; bool have_plan[4] = {false, false, false, false};
     for (int c = 0; c < nchunks; c++) {
-        const int64_t b0 = n_seqs * c / nchunks, b1 = n_seqs * (c + 1) / nchunks;
+        const int64_t b0 = bounds[c], b1 = bounds[c + 1];
         const int64_t t0 = offsets[b0], t1 = offsets[b1];
         cudaStream_t s_k = (c & 1) ? ctx->s_k2 : s_main;
+        // the chunk's longest sequence picks its kernel (scanned while the earlier chunks are in flight)
+        int max_len = 0;
+        for (int64_t b = b0; b < b1; b++) {
+            int64_t n = offsets[b + 1] - offsets[b];
+            if (n < 0 || n > SQRN_MAX_LEN) { ctx->err = "sequence length out of range"; cudaDeviceSynchronize(); return SQRN_E_BADARG; }
+            if (n > max_len) max_len = (int)n;
+        }
+        const PEntry *P;
+        TRY(get_params(ctx, *ps, max_len, &P));
+        const int cls = max_len <= 128 ? 0 : max_len <= 224 ? 1 : max_len <= 320 ? 2 : 3;
+        if (cls == 3 || !have_plan[cls]) { TRY(make_fast_plan(ctx, *P, max_len, (int)(b1 - b0), plans[cls])); have_plan[cls] = true; }
+        const Plan &pl = plans[cls];
         // stage 1: inputs of the chunk
         CK(cudaMemcpyAsync(d_off + b0 + (c ? 1 : 0), offsets + b0 + (c ? 1 : 0), (size_t)(b1 - b0 + (c ? 0 : 1)) * sizeof(int64_t),
                            cudaMemcpyHostToDevice, ctx->s_in));
@@ -627,12 +641,29 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         CK(cudaMemcpyAsync(scores + 3 * b0, d_sc + 3 * b0, (size_t)(b1 - b0) * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
         if (n_stems) CK(cudaMemcpyAsync(n_stems + b0, d_ns + b0, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
         CK(cudaMemcpyAsync(ctx->hflags + b0, d_flags + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaEventRecord(ctx->ev_o[c], ctx->s_out));
     }
     const double t_2 = now();
     CK(cudaEventRecord(ctx->ev_out, ctx->s_out));
     CK(cudaEventRecord(ctx->ev_k2done, ctx->s_k2));
     CK(cudaStreamWaitEvent(s_main, ctx->ev_out, 0));          // later work on the context's stream sees the results
     CK(cudaStreamWaitEvent(s_main, ctx->ev_k2done, 0));
+    // ScoreStruct's round(x, 3) (seq.py:899) was done on the device except next to rounding ties: the flags of
+    // each chunk are checked as soon as its results are back, while the later chunks are still in flight
+    bool too_many_levels = false;
+    for (int c = 0; c < nchunks; c++) {
+        CK(cudaEventSynchronize(ctx->ev_o[c]));
+        const uint8_t *fl = ctx->hflags;
+        for (int64_t b = bounds[c]; b < bounds[c + 1]; ) {
+            if (b + 8 <= bounds[c + 1]) {
+                uint64_t w; memcpy(&w, fl + b, 8);
+                if (!(w & 0x0a0a0a0a0a0a0a0aull)) { b += 8; continue; }
+            }
+            if (fl[b] & FLAG_ROUND) for (int t = 0; t < 3; t++) scores[3 * b + t] = pyround3(scores[3 * b + t]);
+            if (fl[b] & FLAG_LEVELS) too_many_levels = true;
+            b++;
+        }
+    }
     CK(cudaStreamSynchronize(s_main));
     const double t_3 = now();
     for (int c = 0; c < nchunks; c++) {
@@ -644,19 +675,16 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         CK(cudaMemcpy(&c, d_nc, sizeof c, cudaMemcpyDeviceToHost));
         ctx->n_calls = (int64_t)c;
     }
-    // ScoreStruct's round(x, 3) (seq.py:899) was done on the device except next to rounding ties
-    const uint8_t *fl = ctx->hflags;
-    for (int64_t b = 0; b < n_seqs; ) {
-        if (b + 8 <= n_seqs) {
-            uint64_t w; memcpy(&w, fl + b, 8);
-            if (!(w & 0x0a0a0a0a0a0a0a0aull)) { b += 8; continue; }
+    if (too_many_levels) { ctx->err = "more than 30 pseudoknot levels: use sqrn_predict_batch"; return SQRN_E_UNSUPPORTED; }
+    if (trace) {
+        fprintf(stderr, "[sqrn] fast_predict_host: prepare %.2f ms, enqueue %.2f ms, wait %.2f ms, finish %.2f ms\n",
+                t_1 - t_0, t_2 - t_1, t_3 - t_2, now() - t_3);
+        for (int c = 0; c < nchunks; c++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ctx->ev_k0[0], ctx->ev_k0[c]); cudaEventElapsedTime(&b, ctx->ev_k0[0], ctx->ev_k1[c]);
+            fprintf(stderr, "[sqrn]   chunk %2d kernel %.3f .. %.3f ms\n", c, a, b);
         }
-        if (fl[b] & FLAG_ROUND) for (int t = 0; t < 3; t++) scores[3 * b + t] = pyround3(scores[3 * b + t]);
-        if (fl[b] & FLAG_LEVELS) { ctx->err = "more than 30 pseudoknot levels: use sqrn_predict_batch"; return SQRN_E_UNSUPPORTED; }
-        b++;
     }
-    if (trace) fprintf(stderr, "[sqrn] fast_predict_host: prepare %.2f ms, enqueue %.2f ms, wait %.2f ms, finish %.2f ms\n",
-                       t_1 - t_0, t_2 - t_1, t_3 - t_2, now() - t_3);
     return SQRN_OK;
 }
 
