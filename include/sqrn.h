@@ -150,6 +150,8 @@ SQRN_API int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
 #define SQRN_TUNE_CLUSTER 3          /* long sequences (> 2048 nt, run to completion): 0 automatic (a thread-block
                                         cluster per sequence when there are too few to fill the SMs one CTA each),
                                         1 never, 2/4/8/16 always with this cluster size */
+#define SQRN_TUNE_NO_GLIST 4         /* 1: CTA teams (> 320 nt) rescan the anti-diagonals every greedy step instead of keeping
+                                        the persistent candidate list in global memory (k_long) */
 SQRN_API int  sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value);
 
 /* The full "G" path for a batch: replaces SQRNdbnseq.py:1048-1246 (algos == {"G"},

@@ -151,6 +151,10 @@ class Context:
         """long sequences: 0 automatic, 1 one CTA per sequence, 2/4/8/16 a cluster of that many CTAs per sequence"""
         self._check(self.L.sqrn_ctx_set_tuning(self.h, 3, int(mode)))
 
+    def set_no_glist(self, flag):
+        """CTA teams rescan every greedy step instead of keeping the global persistent list (tests compare both)"""
+        self._check(self.L.sqrn_ctx_set_tuning(self.h, 4, int(bool(flag))))
+
     def stats(self):
         nl, ms, nc = C.c_int64(0), C.c_double(0), C.c_int64(0)
         self.L.sqrn_ctx_last_stats(self.h, C.byref(nl), C.byref(ms), C.byref(nc))

@@ -97,6 +97,17 @@ k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
     work_loop<Cfg<TW>>(Pg, B, Wk, L, smem);
 }
 
+// Long sequences, run to completion (MODE_TAIL): CTA teams over the persistent candidate list in
+// global memory (gl_build / gl_step): one enumeration per sequence, cached adjusted scores.  Items
+// whose list overflows its slot go to DevWork::ovf_list and are redone by k_work<TW> behind it.
+template <int TW>
+__global__ void __launch_bounds__(TW * 32, 1)
+k_long(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    work_loop<Cfg<TW, false, false, MODE_TAIL, -1, false, true>>(Pg, B, Wk, L, smem);
+}
+
 // Fast lane (`byseq pl=1` shape): one warp per sequence, plain sequences (no reactivities,
 // restraints, alignment weights), the standard {GC, AU, GU} pairing table, single-path greedy to
 // completion.  The shared-memory layout is a compile-time constant, so every array address is
@@ -169,7 +180,7 @@ struct CachedStems {
 
 enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GCNT, W_GSTAT, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -187,7 +198,8 @@ struct sqrn_ctx {
     int region_mode = REGION_AUTO;
     int no_fast_kernel = 0;      // tuning knob: route the fast lane through the general kernel
     int no_cluster = 0, force_cluster = 0;   // tuning knobs: never / always (with this size) use k_cluster for long sequences
-    int64_t n_cluster_launches = 0;
+    int64_t n_cluster_launches = 0, n_glist_launches = 0;
+    int no_glist = 0;            // tuning knob: CTA teams rescan every step (no global persistent list)
     CachedResult cres; CachedStems cstems;
 };
 
@@ -279,6 +291,7 @@ extern "C" int sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value)
     if (!ctx) return SQRN_E_BADARG;
     if (what == SQRN_TUNE_REGION && value >= 0 && value <= 2) { ctx->region_mode = value; return SQRN_OK; }
     if (what == SQRN_TUNE_NO_FAST_KERNEL) { ctx->no_fast_kernel = value != 0; return SQRN_OK; }
+    if (what == SQRN_TUNE_NO_GLIST) { ctx->no_glist = value != 0; return SQRN_OK; }
     if (what == SQRN_TUNE_CLUSTER && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) {
         ctx->no_cluster = value == 1; ctx->force_cluster = value > 1 ? value : 0; return SQRN_OK;   // 0 automatic, 1 never, 2..16 always
     }
@@ -317,7 +330,8 @@ static int get_params(sqrn_ctx *ctx, const sqrn_paramset &ps, int nmax, const PE
 
 // ------------------------------------------------------------- launch plan
 struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; int cluster = 0; bool cl_plain = false;
-              size_t smem_rescan = 0; int grid_rescan = 0; };
+              size_t smem_rescan = 0; int grid_rescan = 0;
+              bool glist = false; Layout Lg; size_t smem_g = 0; int grid_g = 0; long long gcap = 0; };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -368,6 +382,36 @@ static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int mi
     return pl.tw == 8 ? plan_for<8>(ctx, pl) : plan_for<32>(ctx, pl);
 }
 
+// CTA teams in MODE_TAIL: plan the global-list kernel next to the rescanning one (which stays as its fallback)
+template <int TW>
+static int plan_glist_t(sqrn_ctx *ctx, Plan &pl)
+{
+    CK(cudaFuncSetAttribute(k_long<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_g));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_long<TW>, TW * 32, pl.smem_g));
+    if (nb < 1) return SQRN_E_UNSUPPORTED;
+    pl.grid_g = nb * ctx->sm_count;
+    return SQRN_OK;
+}
+
+static void maybe_glist(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int nmax, int rbmax, bool extras, int max_init, bool tail_mode)
+{
+    if (pl.tw == 1 || !tail_mode || ctx->no_glist || !P.hp.ub_ok || !(P.hp.loopbonus >= 0.0) || nmax > 32767) return;
+    const int m = P.hp.m;
+    const int scap = max_init < 0 ? 0 : max_init + nmax / (2 * m) + 2;
+    pl.Lg = make_layout(nmax, rbmax, 64 * pl.tw, P.hp.npc, pl.tw, 64, extras, 0, scap, -1);    // Ccap: 64 list slots per warp
+    pl.smem_g = pl.Lg.total;
+    if (pl.smem_g + sizeof(DevParams) + 1024 > ctx->smem_optin) return;
+    if ((pl.tw == 8 ? plan_glist_t<8>(ctx, pl) : plan_glist_t<32>(ctx, pl)) != SQRN_OK) { cudaGetLastError(); return; }
+    // entries per slot: runs whose positive part reaches minbpscore, ~0.02 N^2 for minlen 2 on random RNA
+    const double dens = m >= 4 ? 0.003 : (m == 3 ? 0.008 : 0.02);
+    pl.gcap = (long long)(1.5 * dens * nmax * (double)nmax) + 4096;
+    // at most ~6 GB of list space: fewer resident CTAs rather than smaller slots
+    const long long budget = 6ll << 30;
+    if (pl.gcap * 24 * pl.grid_g > budget) pl.grid_g = (int)std::max<long long>(1, budget / (pl.gcap * 24));
+    pl.glist = true;
+}
+
 // the compile-time-layout fast kernel, when the parameter set and the lengths allow it
 template <int NCAP>
 static int plan_fast(sqrn_ctx *ctx, Plan &pl)
@@ -401,6 +445,7 @@ static int make_fast_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int n_items,
         return plan_fast<320>(ctx, pl);
     }
     TRY(make_plan(ctx, P, nmax, 0, 0, false, false, 0, pl));
+    maybe_glist(ctx, P, pl, nmax, 0, false, 0, true);
     maybe_cluster(ctx, P, pl, n_items, true, true);
     return SQRN_OK;
 }
@@ -428,6 +473,7 @@ static void maybe_cluster(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int n_items,
 {
     if (pl.tw != 32 || !tail_mode || ctx->no_cluster || n_items < 1) return;
     int want = ctx->force_cluster;
+    if (!want && pl.glist) return;                           // the global-list kernel beats rescanning clusters
     if (!want) {
         if (2 * n_items > ctx->sm_count) return;             // enough sequences to fill the SMs one CTA each
         want = 8;
@@ -439,6 +485,22 @@ static void maybe_cluster(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int n_items,
         if (rc == SQRN_OK) return;
     }
     pl.cluster = 0;
+}
+
+template <class T>
+static int upload(sqrn_ctx *ctx, int slot, const T *h, size_t count, T **d)
+{
+    CK(ctx->buf[slot].ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    *d = (T *)ctx->buf[slot].p;
+    if (count) CK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return SQRN_OK;
+}
+template <class T>
+static int dalloc(sqrn_ctx *ctx, int slot, size_t count, T **d)
+{
+    CK(ctx->buf[slot].ensure(std::max<size_t>(count, 1) * sizeof(T)));
+    *d = (T *)ctx->buf[slot].p;
+    return SQRN_OK;
 }
 
 // one launch of the work kernel the plan names
@@ -460,6 +522,38 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
     int grid = pl.grid;
     int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
     if (grid > teams) grid = std::max(teams, 1);
+    if (pl.glist && W.mode == MODE_TAIL && !W.init_off) {       // items with pre-selected stems (pool tails) have few steps left: rescan
+        const int gg = std::max(1, std::min(pl.grid_g, W.n_items));
+        GEnt *ge; double *gb; int32_t *ovf; int *cnt;
+        TRY(dalloc(ctx, W_GENT, (size_t)gg * pl.gcap, &ge));
+        TRY(dalloc(ctx, W_GBPS, (size_t)gg * pl.gcap, &gb));
+        TRY(dalloc(ctx, W_OVF, (size_t)W.n_items, &ovf));
+        TRY(dalloc(ctx, W_GCNT, 4, &cnt));
+        CK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
+        DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_cap = pl.gcap;
+        const bool trace = getenv("SQRN_TRACE") != nullptr;
+        unsigned long long *d_stat = nullptr;
+        if (trace) { TRY(dalloc(ctx, W_GSTAT, 8, &d_stat)); CK(cudaMemsetAsync(d_stat, 0, 8 * sizeof(unsigned long long), st)); W1.g_stat = d_stat; }
+        W1.ovf_count = cnt; W1.ovf_list = ovf;
+        if (pl.tw == 8) k_long<8><<<gg, 256, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
+        else k_long<32><<<gg, 1024, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
+        CK(cudaGetLastError());
+        DevWork W2 = W; W2.order = ovf; W2.n_items_dev = cnt; W2.counter = cnt + 1;
+        if (pl.tw == 8) k_work<8><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W2, pl.L);
+        else k_work<32><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W2, pl.L);
+        CK(cudaGetLastError());
+        ctx->n_launches++; ctx->n_glist_launches++;
+        if (trace) {
+            unsigned long long h[8]; int hc[4];
+            CK(cudaStreamSynchronize(st));
+            CK(cudaMemcpy(h, d_stat, sizeof h, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(hc, cnt, sizeof hc, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[sqrn] k_long<%d>: %d items (%d overflowed), %d CTAs x %lld entries; steps %llu (level changes %llu), "
+                    "entries swept %llu, evaluations %llu, cache resets %llu, cuts %llu\n", pl.tw, W.n_items, hc[0], gg, pl.gcap,
+                    h[3], h[4], h[0], h[1], h[2], h[5]);
+        }
+        return SQRN_OK;
+    }
     if (pl.fast_ncap) {
         if (!W.ovf_list || !W.ovf_count || !W.n_items_dev) { ctx->err = "fast lane launched without an overflow list"; return SQRN_E_BADARG; }
         DevWork W1 = W; W1.n_items_dev = nullptr;
@@ -490,22 +584,6 @@ static int launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, const DevBatch
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
     ctx->n_launches++;
-    return SQRN_OK;
-}
-
-template <class T>
-static int upload(sqrn_ctx *ctx, int slot, const T *h, size_t count, T **d)
-{
-    CK(ctx->buf[slot].ensure(std::max<size_t>(count, 1) * sizeof(T)));
-    *d = (T *)ctx->buf[slot].p;
-    if (count) CK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    return SQRN_OK;
-}
-template <class T>
-static int dalloc(sqrn_ctx *ctx, int slot, size_t count, T **d)
-{
-    CK(ctx->buf[slot].ensure(std::max<size_t>(count, 1) * sizeof(T)));
-    *d = (T *)ctx->buf[slot].p;
     return SQRN_OK;
 }
 
@@ -832,6 +910,7 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
         Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, W.mode == MODE_STEP, D.B.rcode != nullptr, max_init, pl));
         {
             const bool plain = !D.B.rcode && !D.B.rclass && !D.B.rbp_off && !D.B.smat && !D.B.interchainonly;
+            maybe_glist(ctx, *P, pl, std::max(nmax_c, 1), D.rbmax, D.B.rcode != nullptr, max_init, W.mode == MODE_TAIL);
             maybe_cluster(ctx, *P, pl, end - pos, plain, W.mode == MODE_TAIL);
         }
         DevWork Gc = G; Gc.order = d_order + pos; Gc.n_items = end - pos;

@@ -55,6 +55,10 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline int __double2loint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(uint32_t)u; }
+static inline int __double2hiint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32); }
+static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x; }
+static inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 static inline uint32_t atomicAnd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p &= v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
@@ -124,6 +128,11 @@ struct DevWork {
     const double  *item_subopt;  // MODE_STEP: cursubopt per item
     int           *counter;      // global work counter (zeroed before launch)
     const int     *n_items_dev;  // if set, the item count is read from here (a list an earlier kernel of the stream filled)
+    void          *g_ent;        // Cfg::GLIST: persistent candidate lists (16-byte GEnt records), slot b = [b * g_cap, (b + 1) * g_cap)
+    double        *g_bps;
+    long long      g_cap;
+    unsigned long long *g_stat;      // optional counters: [0] entries swept, [1] ScoreStems evaluations, [2] cache resets,
+                                     // [3] steps, [4] steps with a level change, [5] cuts
     int           *ovf_count;    // Cfg::PERSIST kernels: items whose run list overflowed are appended here and
     int32_t       *ovf_list;     //   left to a rescanning kernel launched behind them (order = ovf_list)
     // outputs
@@ -145,7 +154,7 @@ struct Layout {
     int o_pbps, o_pkey;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
         o_sti, o_stj, o_stl, o_stlev, o_evpos, o_evid, o_cc, o_perm, o_grp, o_gsz,
-        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, total;
+        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, o_stlev2, total;
 };
 
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -188,7 +197,7 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_cc = o;      L.o_gsz = o + 4 * L.Scap;  L.o_perm = o + 8 * L.Scap;  L.o_grp = o + 10 * L.Scap;
     o += uni;
     L.o_clen = o;    o += 2 * Ccap;
-    L.o_pbps = 0;    L.o_pkey = 8 * pcap;
+    L.o_pbps = 0;    L.o_pkey = pcap > 0 ? 8 * pcap : 0;
     if (pcap > 0) {
         if (o < 12 * pcap) o = 12 * pcap;
         o = align_up(o, 4);
@@ -220,6 +229,7 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_code = o;    o += L.Ncap;
     L.o_rcl = o;     o += extras >= 0 ? L.Ncap : 0;
     L.o_stlev = o;   o += L.Scap;
+    L.o_stlev2 = o;  o += pcap < 0 ? L.Scap : 0;      // pcap < 0: global persistent list (levels of the previous step)
     L.total = align_up(o, 16);
     return L;
 }
@@ -305,18 +315,22 @@ template <> struct Team<0> {
 //          A PERSIST kernel carries no rescanning code at all (its hot instruction range has to
 //          fit the SM's instruction cache): an item whose list overflows is appended to
 //          DevWork::ovf_list and redone from scratch by a non-PERSIST kernel.
+//   GLIST: the persistent list lives in GLOBAL memory (DevWork::g_*; one slot per resident CTA) and
+//          caches the adjusted score of every candidate between steps (gl_build / gl_step): for CTA
+//          teams (long sequences, 10^5 .. 10^6 runs).  -1: on for CTA teams.
 template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1, bool CLUSTER_ = false,
-          bool PERSIST_ = false>
+          bool PERSIST_ = false, int GLIST_ = -1>
 struct Cfg {
     static constexpr int TW = TW_, MODE = MODE_;
     static constexpr bool PLAIN = PLAIN_, STDP = STDP_, CLUSTER = CLUSTER_, PERSIST = PERSIST_;
+    static constexpr bool GLIST = PERSIST_ && (GLIST_ < 0 ? (TW_ > 1) : (GLIST_ != 0));
     static constexpr bool RUNLIST = RUNLIST_ < 0 ? (TW_ == 1) : (RUNLIST_ != 0);
 };
 
 struct State {
     int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts, region_mode;
     int dstride, doffset;            // this team scans the anti-diagonals 4 + doffset + dstride * q (cluster: rank, size)
-    uint8_t  *code, *rcl, *stlev;
+    uint8_t  *code, *rcl, *stlev, *stlev2;
     uint16_t *rcode;
     int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *evpos, *evid, *perm, *grp, *rbv, *rbw;
     uint32_t *M, *PR, *rowok, *colokR, *Ub, *ckey, *rkey, *pkey;
@@ -332,7 +346,7 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
 {
     State s;
     s.code = base + L.o_code;  s.rcode = (uint16_t *)(base + L.o_rcode);  s.rcl = base + L.o_rcl;
-    s.stlev = base + L.o_stlev;
+    s.stlev = base + L.o_stlev;  s.stlev2 = base + L.o_stlev2;
     s.partner = (int16_t *)(base + L.o_partner);  s.owner = (int16_t *)(base + L.o_owner);
     s.sepcnt = (int16_t *)(base + L.o_sepcnt);
     s.sti = (int16_t *)(base + L.o_sti);  s.stj = (int16_t *)(base + L.o_stj);  s.stl = (int16_t *)(base + L.o_stl);
@@ -1218,6 +1232,29 @@ __device__ __forceinline__ double consider(const State &S, const DevParams &P, u
 {
     double ub = score_bound(P, bps);
     if (ub < floor || ub < P.minfinscore) return -1e300;
+    if (!C::PERSIST && P.ub_ok && bps > 0.0 && P.loopbonus >= 0.0) {
+        // second, tighter bound for the candidates the first one lets through (teams that scan many
+        // candidates per step): the tetraloop factor is cheap to get exactly, and a good loop needs a
+        // paired position within five of the stem's inner / outer ends -- read from the unpaired mask.
+        // Same multiplication order and rounding as seq.py:732 with factors >= the true ones.
+        const int a = (int)(key & 0xffff), oj = (int)(key >> 16) - a;
+        const int ss = a + len - 1, se = oj - len + 1;
+        double tf = 1.0;
+        if (se - ss - 1 == 4 && S.code[ss + 1] == CODE_G &&
+            (S.code[ss + 3] == CODE_G || S.code[ss + 3] == CODE_A) && S.code[ss + 4] == CODE_A) tf = 1.25;
+        bool in_ok = false, out_ok = false;
+        if (S.nst) {
+            in_ok = (~unpaired_bits5(S, ss + 1) & 31u) && (~unpaired_bits5(S, se - 5) & 31u);
+            out_ok = (~unpaired_bits5(S, a - 5) & 31u) && (~unpaired_bits5(S, oj + 1) & 31u);
+        }
+        double lf = __dadd_rn(1.0, __dmul_rn(__dmul_rn(P.loopbonus, in_ok ? 1.0 : 0.0), 2.0));
+        lf = __dadd_rn(lf, __dmul_rn(__dmul_rn(P.loopbonus, out_ok ? 1.0 : 0.0), 2.0));
+        double u = __dmul_rn(bps, P.sdf_max);
+        u = __dmul_rn(u, P.of_max);
+        u = __dmul_rn(u, lf);
+        u = __dmul_rn(u, tf);
+        if (u < floor || u < P.minfinscore) return -1e300;
+    }
     double fin = score_candidate<C>(S, P, (int)(key >> 16), (int)(key & 0xffff), len, bps);
     if (!(fin >= P.minfinscore)) return -1e300;
     if (better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
@@ -1702,6 +1739,336 @@ __device__ Best persist_step(State &S, const DevParams &P, const DevBatch &B, co
     return team_argmax<C>(S, best);
 }
 
+// ------------------------- persistent candidate list in global memory (CTA teams)
+// Long sequences have 10^5 .. 10^6 maximal runs and hundreds of greedy steps; rescanning them
+// costs O(N^2) cell visits plus a ScoreStems region walk per surviving candidate per step.  Here
+// the runs are enumerated ONCE into a per-CTA list in global memory (key, length, bp score) and
+// every entry CACHES what the last evaluation found:
+//   FRESH   nothing known;
+//   EVAL    g_fin = the adjusted score (ScoreStems) under the structure it was evaluated with;
+//   PRUNED  g_fin = an upper bound of the adjusted score (score_bound / tight_bound) that was
+//           below the best score of the step that looked at it;
+//   BELOW   the run's bp score is under minbpscore: no candidate as it stands, kept because a piece of
+//           it may be one after a cut.
+// A step (gl_step) makes two coalesced sweeps over the list:
+//   1. cut the runs that touch the stem T just selected (as persist_step does), put the entries
+//      whose cached value may have changed back to FRESH, and take the arg-max of the cached
+//      scores that are still valid -> the floor;
+//   2. look at FRESH entries and at PRUNED entries whose bound reaches the floor: bounds first,
+//      ScoreStems only for what passes.
+// When does the adjusted score of a candidate c = (oi, oj, len), innermost pair (ss, se), change?
+// ScoreStems reads (seq.py:607-751) the partners of the positions in (ss, se) and within five of
+// the outermost pair, and the levels of the selected stems with a wing inside (ss, se).  So T can
+// only matter if one of its arms meets [oi - 5, oj + 5] -- and not even then if T lies inside a
+// selected stem B that itself lies inside (ss, se): positions under B are behind `inblockend`
+// (seq.py:672-689) both before and after.  The host of T ("encloser": the selected stem with the
+// largest i that encloses T) is found once per step.  Levels: if the level of any OLD stem
+// changed when T was added, every EVAL entry goes back to FRESH.
+constexpr uint32_t GK_DEAD = 0xffffffffu;
+constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u;
+
+// one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16, v = the cached score / bound
+struct alignas(16) GEnt { uint32_t key, meta; double v; };
+struct GList { GEnt *ent; double *bps; int cap; unsigned long long *stat; };
+constexpr int GL_BATCH = 4;       // records a thread loads back to back before it looks at any (memory-level parallelism)
+
+__device__ __forceinline__ GEnt gl_load(const GEnt *p)
+{
+#ifdef SQRN_HOST_EMU
+    return *p;
+#else
+    const uint4 q = *reinterpret_cast<const uint4 *>(p);
+    GEnt e; e.key = q.x; e.meta = q.y; e.v = __hiloint2double((int)q.w, (int)q.z);
+    return e;
+#endif
+}
+__device__ __forceinline__ void gl_store(GEnt *p, uint32_t key, uint32_t meta, double v)
+{
+#ifdef SQRN_HOST_EMU
+    p->key = key; p->meta = meta; p->v = v;
+#else
+    uint4 q; q.x = key; q.y = meta; q.z = (uint32_t)__double2loint(v); q.w = (uint32_t)__double2hiint(v);
+    *reinterpret_cast<uint4 *>(p) = q;
+#endif
+}
+
+// the second, tighter bound of consider() as a function: exact tetraloop factor, loop bonuses only
+// where a paired position within five makes a good loop possible
+__device__ __forceinline__ double tight_bound(const State &S, const DevParams &P, uint32_t key, int len, double bps)
+{
+    const int a = (int)(key & 0xffff), oj = (int)(key >> 16) - a;
+    const int ss = a + len - 1, se = oj - len + 1;
+    double tf = 1.0;
+    if (se - ss - 1 == 4 && S.code[ss + 1] == CODE_G &&
+        (S.code[ss + 3] == CODE_G || S.code[ss + 3] == CODE_A) && S.code[ss + 4] == CODE_A) tf = 1.25;
+    bool in_ok = false, out_ok = false;
+    if (S.nst) {
+        in_ok = (~unpaired_bits5(S, ss + 1) & 31u) && (~unpaired_bits5(S, se - 5) & 31u);
+        out_ok = (~unpaired_bits5(S, a - 5) & 31u) && (~unpaired_bits5(S, oj + 1) & 31u);
+    }
+    double lf = __dadd_rn(1.0, __dmul_rn(__dmul_rn(P.loopbonus, in_ok ? 1.0 : 0.0), 2.0));
+    lf = __dadd_rn(lf, __dmul_rn(__dmul_rn(P.loopbonus, out_ok ? 1.0 : 0.0), 2.0));
+    double u = __dmul_rn(bps, P.sdf_max);
+    u = __dmul_rn(u, P.of_max);
+    u = __dmul_rn(u, lf);
+    return __dmul_rn(u, tf);
+}
+
+__device__ __forceinline__ bool gl_wanted(int N, const DevParams &P, long long cap)
+{
+    if (cap <= 0 || N > 32767 || !P.ub_ok || !(P.loopbonus >= 0.0)) return false;
+    const double dens = P.m >= 4 ? 0.003 : (P.m == 3 ? 0.008 : 0.02);
+    return dens * N * (double)N <= 0.8 * (double)cap;
+}
+
+// Enumerates the maximal runs of the current structure state into the global list (a warp per
+// anti-diagonal, a word per lane).  false: overflow.
+template <class C>
+__device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const GList &g)
+{
+    constexpr int TW = C::TW;
+    const int r = Team<TW>::rank();
+#ifdef SQRN_HOST_EMU
+    constexpr int WL = 1;
+    const int lane = 0, wid = 0, nw = 1;
+#else
+    constexpr int WL = 32;
+    const int lane = threadIdx.x & 31, wid = r >> 5, nw = TW;
+#endif
+    const int smax = 2 * S.N - 6;
+    if (r == 0) S.misc[8] = 0;
+    Team<TW>::sync();
+    #pragma unroll 1
+    for (int s = 4 + wid; s <= smax; s += nw) {
+        int lo, hi;
+        if (!diag_range<C>(S, B, s, lo, hi)) continue;
+        const int k1 = hi >> 5;
+        uint32_t carry_top = 0;
+        #pragma unroll 1
+        for (int kb = lo >> 5; kb <= k1; kb += WL) {
+            const int k = kb + lane;
+            const uint32_t x = k <= k1 ? diag_word<C>(S, P, s, k, lo, hi) : 0u;
+#ifdef SQRN_HOST_EMU
+            const uint32_t xn = k + 1 <= k1 ? diag_word<C>(S, P, s, k + 1, lo, hi) : 0u;
+            const uint32_t pt = carry_top;
+            carry_top = x >> 31;
+#else
+            uint32_t xn = __shfl_down_sync(0xffffffffu, x, 1);
+            if (lane == 31) xn = kb + 32 <= k1 ? diag_word<C>(S, P, s, kb + 32, lo, hi) : 0u;
+            const uint32_t xp = __shfl_up_sync(0xffffffffu, x, 1);
+            const uint32_t pt = lane == 0 ? carry_top : (xp >> 31);
+            carry_top = __shfl_sync(0xffffffffu, x, 31) >> 31;
+#endif
+            uint32_t starts = run_starts(x, xn, pt, P.m);
+            #pragma unroll 1
+            while (starts) {
+                const int b = __ffs(starts) - 1;
+                starts &= starts - 1;
+                const int a = 32 * k + b;
+                int e;
+                const uint32_t inv = ~(x >> b);
+                const int t = inv ? __ffs(inv) - 1 : 32;
+                if (b + t < 32) e = a + t - 1;
+                else {
+                    int kk = k + 1; uint32_t w = xn;
+                    #pragma unroll 1
+                    while (kk <= k1 && w == 0xffffffffu) { kk++; w = (kk <= k1) ? diag_word<C>(S, P, s, kk, lo, hi) : 0u; }
+                    e = (kk <= k1) ? 32 * kk + (__ffs(~w) - 1) - 1 : 32 * (k1 + 1) - 1;
+                    if (e > hi) e = hi;
+                }
+                const int len = e - a + 1;
+                if ((double)len < P.minlen) continue;
+                double pos;
+                const double sc = run_score_pos<C>(S, P, B, s, a, len, pos);
+                if (!(pos >= P.minbpscore)) continue;
+                const int slot = atomicAdd(&S.misc[8], 1);
+                if (slot < g.cap) {
+                    gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)a, (uint32_t)len | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
+                    g.bps[slot] = sc;
+                }
+            }
+        }
+    }
+    Team<TW>::sync();
+    return S.misc[8] <= g.cap;
+}
+
+// One OptimalStems pass over the global list.  (ui, uj, ul): the stem T applied since the last pass
+// (ul = 0: none); (ei, ej): the selected stem enclosing T with the largest i (ei < 0: none);
+// relevel: the level of some older stem changed when T was added.  ok = false: overflow.
+template <class C>
+__device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const GList &g, int ui, int uj, int ul,
+                        int ei, int ej, bool relevel, bool &ok)
+{
+    constexpr int TW = C::TW;
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    ok = true;
+    int n = S.misc[8];
+    Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
+    const int u1 = ui + ul - 1, v0 = uj - ul + 1;          // the arms of T: [ui, u1] and [v0, uj]
+    unsigned n_eval = 0, n_reset = 0, n_cut = 0;
+    GEnt buf[GL_BATCH];
+    // ---- sweep 1: cut, invalidate, arg-max of the cached scores that still hold
+    #pragma unroll 1
+    for (int c0 = r; c0 < n; c0 += GL_BATCH * T) {
+        #pragma unroll
+        for (int u = 0; u < GL_BATCH; u++) {
+            const int c = c0 + u * T;
+            if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
+        }
+        #pragma unroll 1
+        for (int u = 0; u < GL_BATCH; u++) {
+            const int c = c0 + u * T;
+            const uint32_t key = buf[u].key;
+            if (key == GK_DEAD) continue;
+            const uint32_t meta = buf[u].meta;
+            const int len = (int)(meta & 0xffffu), a = (int)(key & 0xffffu), s = (int)(key >> 16), t = s - a;
+            uint32_t st = meta >> 16;
+            if (ul > 0) {
+                const int A0 = ui - a, A1 = u1 - a, B0 = v0 - a, B1 = uj - a;
+                const int C0 = t - u1, C1 = t - ui, D0 = t - uj, D1 = t - v0;
+                const int top = len - 1;
+                if ((A0 <= top && A1 >= 0) || (B0 <= top && B1 >= 0) || (C0 <= top && C1 >= 0) || (D0 <= top && D1 >= 0)) {
+                    uint32_t live = len <= 32 ? (0xffffffffu >> (32 - len)) & ~(bits_between(A0, A1) | bits_between(B0, B1) |
+                                                                                bits_between(C0, C1) | bits_between(D0, D1)) : 0u;
+                    auto dead = [&](int q) { return (q >= A0 && q <= A1) || (q >= B0 && q <= B1) || (q >= C0 && q <= C1) || (q >= D0 && q <= D1); };
+                    bool first = true;
+                    int q = 0;
+                    #pragma unroll 1
+                    for (;;) {
+                        int p0, pl;
+                        if (len <= 32) {
+                            if (!live) break;
+                            p0 = __ffs(live) - 1;
+                            const uint32_t inv = ~(live >> p0);
+                            pl = inv ? __ffs(inv) - 1 : 32;
+                            live = (p0 + pl >= 32) ? 0u : (live >> (p0 + pl)) << (p0 + pl);
+                        } else {
+                            #pragma unroll 1
+                            while (q < len && dead(q)) q++;
+                            if (q >= len) break;
+                            p0 = q;
+                            #pragma unroll 1
+                            while (q < len && !dead(q)) q++;
+                            pl = q - p0;
+                        }
+                        if ((double)pl < P.minlen) continue;
+                        double pos;
+                        const double sc = run_score_pos<C>(S, P, B, s, a + p0, pl, pos);
+                        if (!(pos >= P.minbpscore)) continue;
+                        const int slot = first ? c : atomicAdd(&S.misc[8], 1);
+                        if (slot < g.cap) {
+                            gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)(a + p0),
+                                     (uint32_t)pl | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
+                            g.bps[slot] = sc;
+                        }
+                        first = false;
+                    }
+                    if (first) g.ent[c].key = GK_DEAD;
+                    n_cut++;
+                    continue;
+                }
+                if (st == GS_EVAL || st == GS_PRUNED) {
+                    // does T meet the window the cached value was computed from?
+                    const int w0 = a - 5, w1 = t + 5, ss = a + len - 1, se = t - len + 1;
+                    const bool touches = (ui <= w1 && u1 >= w0) || (v0 <= w1 && uj >= w0);
+                    const bool shielded = ei >= 0 && ss < ei && ej < se;
+                    if ((touches && !shielded) || (relevel && st == GS_EVAL)) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
+                }
+            }
+            if (st == GS_EVAL) {
+                const double fin = buf[u].v;
+                if (fin >= P.minfinscore && better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
+            }
+        }
+    }
+    best = team_argmax<C>(S, best);               // barrier: the appended pieces are visible
+    n = S.misc[8];
+    if (n > g.cap) { ok = false; return best; }
+    // ---- sweep 2: FRESH entries, and PRUNED ones whose bound reaches the floor.  The bounds are checked
+    // entry by entry; what passes is collected in a per-warp list and evaluated 32 at a time, so that the
+    // ScoreStems region walks (hundreds of instructions each) run with full warps.
+    unsigned *fl_hi = (unsigned *)&S.misc[9];     // high word of the best score found so far in this sweep (a lower bound of it)
+    if (r == 0) *fl_hi = best.fin > 0.0 ? (unsigned)__double2hiint(best.fin) : 0u;
+    Team<TW>::sync();
+    double floor = best.fin;
+    auto refresh_floor = [&]() {
+        const unsigned h = *(volatile unsigned *)fl_hi;
+        const double f = __hiloint2double((int)h, 0);
+        if (h && f > floor) floor = f;
+    };
+    auto evaluate = [&](int c) {
+        const GEnt e = gl_load(&g.ent[c]);
+        const int len = (int)(e.meta & 0xffffu);
+        const double bps = g.bps[c];
+        const double fin = score_candidate<C>(S, P, (int)(e.key >> 16), (int)(e.key & 0xffffu), len, bps);
+        gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_EVAL << 16), fin);
+        n_eval++;
+#ifdef SQRN_EMU_DEBUG
+        printf("  eval nst=%d (%d,%d,%d) bps=%g fin=%.17g\n", S.nst, (int)(e.key & 0xffff), (int)(e.key >> 16) - (int)(e.key & 0xffff), len, bps, fin);
+#endif
+        if (fin >= P.minfinscore && better(fin, e.key, best.fin, best.key)) {
+            best.fin = fin; best.key = e.key; best.len = len;
+            if (fin > floor) { floor = fin; if (fin > 0.0) atomicMax(fl_hi, (unsigned)__double2hiint(fin)); }
+        }
+    };
+    // true: entry c has to be evaluated (its bounds reach the floor)
+    auto screen = [&](int c, const GEnt &e) -> bool {
+        if (e.key == GK_DEAD) return false;
+        const uint32_t st = e.meta >> 16;
+        if (st == GS_EVAL || st == GS_BELOW) return false;
+        if (st == GS_PRUNED && e.v < floor) return false;
+        const int len = (int)(e.meta & 0xffffu);
+        const double bps = g.bps[c];
+        double ub = score_bound(P, bps);
+        if (!(ub < floor || ub < P.minfinscore)) ub = tight_bound(S, P, e.key, len, bps);
+        if (ub < floor || ub < P.minfinscore) { gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16), ub); return false; }
+        return true;
+    };
+#ifdef SQRN_HOST_EMU
+    #pragma unroll 1
+    for (int c = 0; c < n; c++) { refresh_floor(); buf[0] = gl_load(&g.ent[c]); if (screen(c, buf[0])) evaluate(c); }
+#else
+    {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int *wl = (int *)S.ckey + 64 * wid;       // this warp's list of entries to evaluate (Layout::Ccap = 64 per warp)
+        int wn = 0;
+        #pragma unroll 1
+        for (int c0 = 32 * wid; c0 < n; c0 += GL_BATCH * T) {
+            #pragma unroll
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int c = c0 + u * T + lane;
+                if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
+            }
+            #pragma unroll 1
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int c = c0 + u * T + lane;
+                refresh_floor();
+                const bool need = screen(c, buf[u]);
+                const uint32_t bal = __ballot_sync(0xffffffffu, need);
+                if (need) wl[wn + __popc(bal & ((1u << lane) - 1u))] = c;
+                wn += __popc(bal);
+                __syncwarp();
+                if (wn >= 32) {
+                    wn -= 32;
+                    evaluate(wl[wn + lane]);
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane < wn) evaluate(wl[lane]);
+        __syncwarp();
+    }
+#endif
+    if (g.stat) {
+        if (n_eval) atomicAdd(&g.stat[1], (unsigned long long)n_eval);
+        if (n_reset) atomicAdd(&g.stat[2], (unsigned long long)n_reset);
+        if (n_cut) atomicAdd(&g.stat[5], (unsigned long long)n_cut);
+        if (r == 0) { atomicAdd(&g.stat[0], (unsigned long long)n); atomicAdd(&g.stat[3], 1ull); if (relevel) atomicAdd(&g.stat[4], 1ull); }
+    }
+    return team_argmax<C>(S, best);
+}
+
 // two stems are "in conflict" when they share a paired position (seq.py:783-786)
 __device__ __forceinline__ bool iv_overlap(int a0, int a1, int b0, int b1) { return a0 <= b1 && b0 <= a1; }
 __device__ __forceinline__ bool stems_share(int i1, int j1, int l1, int i2, int j2, int l2)
@@ -1965,10 +2332,20 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
     const int seq = Wk.item_seq ? Wk.item_seq[item] : item;
     const int mode = C::MODE >= 0 ? C::MODE : Wk.mode;
     S.region_mode = Wk.region_mode;
+    GList g{};
+    if (C::GLIST) {
+#ifdef SQRN_HOST_EMU
+        const long long slot = 0;
+#else
+        const long long slot = blockIdx.x;
+#endif
+        g.ent = (GEnt *)Wk.g_ent + slot * Wk.g_cap; g.bps = Wk.g_bps + slot * Wk.g_cap;
+        g.cap = (int)Wk.g_cap; g.stat = Wk.g_stat;
+    }
     if (C::PERSIST) {
         // hopeless for the list (too long for this parameter set): straight to the rescanning kernel
         const int N = (int)(B.off[seq + 1] - B.off[seq]);
-        if (!persist_wanted(N, P, L)) {
+        if (!(C::GLIST ? gl_wanted(N, P, Wk.g_cap) : persist_wanted(N, P, L))) {
             if (r == 0) { const int slot = atomicAdd(Wk.ovf_count, 1); Wk.ovf_list[slot] = item; }
             return;
         }
@@ -1987,14 +2364,43 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
         bool ok = true;                             // PERSIST: the run list has not overflowed
         int ui = 0, uj = 0, ul = 0;                 // the stem applied since the last pass over the list
-        if (C::PERSIST && mode == MODE_TAIL && (double)S.nst != P.maxstemnum) ok = persist_build<C>(S, P, B, L);
+        if (C::PERSIST && mode == MODE_TAIL && (double)S.nst != P.maxstemnum)
+            ok = C::GLIST ? gl_build<C>(S, P, B, g) : persist_build<C>(S, P, B, L);
         bool lev_ok = false;                        // stlev[] matches the current stem set
         #pragma unroll 1
         while (ok && mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
             lev_ok = true;
             Best b;
-            if (C::PERSIST) {
+            if (C::GLIST) {
+                constexpr int T = Team<TW>::T;
+                bool relevel = false;
+                int ei = -1, ej = -1;
+                if (ul > 0) {
+                    // did the new stem (index nst - 1) move an older stem to another level?
+                    bool ch = false;
+                    #pragma unroll 1
+                    for (int t = r; t < S.nst - 1; t += T) if (S.stlev[t] != S.stlev2[t]) ch = true;
+                    relevel = Team<TW>::any(ch);
+                    // its encloser: the older stem with the largest i whose arms lie outside both arms of it
+                    if (r == 0) {
+                        int bi = -1, bj = -1;
+                        #pragma unroll 1
+                        for (int t = 0; t < S.nst - 1; t++) {
+                            const int i = S.sti[t], j = S.stj[t], l = S.stl[t];
+                            if (i + l - 1 < ui && j - l + 1 > uj && i > bi) { bi = i; bj = j; }
+                        }
+                        S.misc[10] = bi; S.misc[11] = bj;
+                    }
+                    Team<TW>::sync();
+                    ei = S.misc[10]; ej = S.misc[11];
+                }
+                #pragma unroll 1
+                for (int t = r; t < S.nst; t += T) S.stlev2[t] = S.stlev[t];
+                Team<TW>::sync();
+                b = gl_step<C>(S, P, B, g, ui, uj, ul, ei, ej, relevel, ok);
+                if (!ok) break;
+            } else if (C::PERSIST) {
                 b = persist_step<C>(S, P, B, L, ui, uj, ul, ok);
                 if (!ok) break;
             } else b = team_scan<C>(S, P, B, L, -1.0);

@@ -46,14 +46,19 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     W.item_subopt = item_subopt; W.out_off = out_off; W.out_stems = out_stems; W.out_nstems = out_nstems;
     W.out_stemfin = out_stemfin; W.out_raw = out_raw; W.out_flags = out_flags; W.dbn_off = dbn_off;
     W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls; W.region_mode = region_mode;
-    Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, (flavour == 3 || flavour == 4) ? pcap : 0);
+    Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, (flavour == 3 || flavour == 4) ? pcap : (flavour == 5 ? -1 : 0));
+    std::vector<GEnt> ge; std::vector<double> gb;
+    if (flavour == 5) {            // global persistent list with cached scores (what CTA teams run), capacity pcap
+        ge.resize((size_t)pcap + 1); gb.resize((size_t)pcap + 1);
+        W.g_ent = ge.data(); W.g_bps = gb.data(); W.g_cap = pcap;
+    }
     unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
     // PERSIST flavours park the items whose run list overflowed; they are redone by the rescanning flavour
     std::vector<int32_t> ovf((size_t)n_items + 1); int n_ovf = 0;
     W.ovf_list = ovf.data(); W.ovf_count = &n_ovf;
     for (int pass = 0; pass < 2; pass++) {
     const int todo = pass == 0 ? n_items : n_ovf;
-    if (pass == 1) { if (flavour == 3) flavour = 1; else if (flavour == 4) flavour = 2; }
+    if (pass == 1) { if (flavour == 3) flavour = 1; else if (flavour == 4 || flavour == 5) flavour = 2; }
     for (int q = 0; q < todo; q++) {
         const int item = pass == 0 ? q : ovf[q];
         State S = bind_state(smem, Lay);
@@ -64,10 +69,11 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
             if (!H.p.std_pairs || rcode || rclass || rbp_off || smat || interchainonly || mode != MODE_TAIL) { free(smem); return -2; }
             team_run_item<Cfg<0, true, true, MODE_TAIL, 1, false, true>>(S, H.p, B, W, Lay, item);
         } else if (flavour == 4) team_run_item<Cfg<0, false, false, -1, 1, false, true>>(S, H.p, B, W, Lay, item);   // general flavour, persistent list
+        else if (flavour == 5) team_run_item<Cfg<0, false, false, -1, 0, false, true, 1>>(S, H.p, B, W, Lay, item);   // global list
         else if (flavour == 2) team_run_item<Cfg<0, false, false, -1, 1>>(S, H.p, B, W, Lay, item);   // run-list scan
         else team_run_item<Cfg<0>>(S, H.p, B, W, Lay, item);                                              // per-thread rounds
     }
-    if (flavour != 3 && flavour != 4) break;
+    if (flavour != 3 && flavour != 4 && flavour != 5) break;
     }
     free(smem);
     return 0;

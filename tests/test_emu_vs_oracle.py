@@ -37,8 +37,9 @@ def _prep_batch(cases):
     return preps, kw
 
 
-@pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist", "persist", "persist-small", "persist-general"],
-                         ids=["auto", "scan", "stems", "fastflavour", "runlist", "persist", "persist-smalllist", "persist-general"])
+@pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist", "persist", "persist-small", "persist-general", "glist", "glist-small"],
+                         ids=["auto", "scan", "stems", "fastflavour", "runlist", "persist", "persist-smalllist", "persist-general",
+                              "glist", "glist-smalllist"])
 @pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
                          ids=["fastest", "defG1", "defG2-smalllist", "ali"])
 def test_tail_plain(ps, ccap, region):
@@ -57,6 +58,10 @@ def test_tail_plain(ps, ccap, region):
         r = emu.run(ps, seqs, ccap=ccap, flavour=3, pcap=96)      # pieces are appended): falls back to rescanning
     elif region == "persist-general":
         r = emu.run(ps, seqs, ccap=ccap, flavour=4, pcap=4096)
+    elif region == "glist":    # what CTA teams run: the list in global memory, adjusted scores cached between steps
+        r = emu.run(ps, seqs, ccap=ccap, flavour=5, pcap=1 << 16)
+    elif region == "glist-small":
+        r = emu.run(ps, seqs, ccap=ccap, flavour=5, pcap=600)
     else:
         r = emu.run(ps, seqs, ccap=ccap, region_mode=region)
     for b, s in enumerate(seqs):
@@ -69,7 +74,7 @@ def test_tail_plain(ps, ccap, region):
         assert bool(r["flags"][b] & 1) == isint
 
 
-@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2), (0, 4)], ids=["scan", "stems", "runlist", "persist"])
+@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2), (0, 4), (0, 5)], ids=["scan", "stems", "runlist", "persist", "glist"])
 @pytest.mark.parametrize("interchain", [False, True])
 def test_tail_with_restraints_and_reactivities(interchain, region, flavour):
     rng = random.Random(32)
@@ -177,3 +182,24 @@ def test_step_on_random_pseudoknotted_structures(region):
             k = r["n"][0]
             got = [(int(r["stems"][q][0]), int(r["stems"][q][1]), int(r["stems"][q][2]), float(r["fin"][q])) for q in range(k)]
             assert got == chosen, (seq, stems)
+
+
+def test_glist_cached_scores_under_pseudoknots():
+    """The global persistent list (CTA teams) keeps the adjusted score of a candidate between greedy steps
+    unless the new stem meets the window ScoreStems read, or an older stem changed its pseudoknot level.
+    Parameter sets that accept many pseudoknots (up to ~10 levels) against the rescanning flavour and,
+    for a sample, the oracle."""
+    pk = dict(T.ALI); pk["orderpenalty"] = 0.1; pk["minfinscorefactor"] = 0.8
+    for ps in (T.ALI, T.DEFG2, T.G1000, pk):
+        seqs = T.rand_seqs(101, 40, 150, 450) + T.rand_seqs(102, 10, 300, 500, "GC") + T.rand_seqs(103, 10, 200, 400, "GGCCAU")
+        a = emu.run(ps, seqs, ccap=256, flavour=5, pcap=1 << 20)
+        b = emu.run(ps, seqs, ccap=256, flavour=2)
+        for k in range(len(seqs)):
+            sa = [tuple(int(x) for x in a["stems"][a["off"][k] + q]) for q in range(a["n"][k])]
+            sb = [tuple(int(x) for x in b["stems"][b["off"][k] + q]) for q in range(b["n"][k])]
+            assert sa == sb and (a["raw"][k] == b["raw"][k]).all(), seqs[k]
+            assert bytes(a["dbn_ascii"][a["dbn_off"][k]:a["dbn_off"][k + 1]]) == bytes(b["dbn_ascii"][b["dbn_off"][k]:b["dbn_off"][k + 1]])
+        for k in range(0, len(seqs), 12):
+            _, structs, _ = O.predict_short(seqs[k], [0.5] * len(seqs[k]), "." * len(seqs[k]), [ps], poollim=1)
+            sa = [tuple(int(x) for x in a["stems"][a["off"][k] + q]) for q in range(a["n"][k])]
+            assert sa == structs[0][4]

@@ -72,6 +72,24 @@ def test_fast_lane_cta_teams(gpu_ctx):
     _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(17, 4, 2100, 2600))
 
 
+@pytest.mark.parametrize("ps", [T.FASTEST, T.G1000, T.ALI], ids=["fastest", "1000G", "ali"])
+def test_cta_teams_global_list_vs_rescan(gpu_ctx, ps):
+    """CTA teams keep a persistent candidate list with cached adjusted scores in global memory (k_long);
+    the rescanning kernel (k_work) must give the same structures, stems and scores; a sample against the oracle"""
+    seqs = T.rand_seqs(41, 96, 321, 1400) + T.rand_seqs(42, 6, 2100, 3000) + T.rand_seqs(43, 6, 400, 900, "GC") + \
+        T.rand_seqs(44, 6, 400, 900, "GGCCAU")
+    sym, off = pack_sequences(seqs)
+    a = gpu_ctx.fast_predict(ps, sym, off)
+    try:
+        gpu_ctx.set_no_glist(True)
+        b = gpu_ctx.fast_predict(ps, sym, off)
+    finally:
+        gpu_ctx.set_no_glist(False)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    _check_fast(gpu_ctx, ps, seqs[:12] + seqs[100:103])
+
+
 @pytest.mark.parametrize("cs", [1, 2, 4, 8], ids=["one-cta", "cluster2", "cluster4", "cluster8"])
 def test_long_sequences_cluster_sizes(gpu_ctx, cs):
     """> 2048 nt run to completion: one CTA per sequence and thread-block clusters of 2/4/8 CTAs
