@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_work -c 1 -f -o gpurun_out/prof_long \
-    python scripts/bench_configs.py c5 --n 148 --lo 2900 --hi 3100 > gpurun_out/ncu_long.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_long -s 1 -c 1 -f -o gpurun_out/prof_long \
+    python scripts/bench_configs.py c5 --n 148 > gpurun_out/ncu_long.log 2>&1
 tail -3 gpurun_out/ncu_long.log

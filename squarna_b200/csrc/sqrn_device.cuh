@@ -59,6 +59,7 @@ static inline int __double2loint(double x) { uint64_t u; memcpy(&u, &x, 8); retu
 static inline int __double2hiint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32); }
 static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x; }
 static inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 static inline uint32_t atomicAnd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p &= v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
@@ -1770,7 +1771,7 @@ constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u;
 // one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16, v = the cached score / bound
 struct alignas(16) GEnt { uint32_t key, meta; double v; };
 struct GList { GEnt *ent; double *bps; int cap; unsigned long long *stat; };
-constexpr int GL_BATCH = 4;       // records a thread loads back to back before it looks at any (memory-level parallelism)
+constexpr int GL_BATCH = 8;       // records a thread loads back to back before it looks at any (memory-level parallelism)
 
 __device__ __forceinline__ GEnt gl_load(const GEnt *p)
 {
@@ -1908,17 +1909,36 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     const int u1 = ui + ul - 1, v0 = uj - ul + 1;          // the arms of T: [ui, u1] and [v0, uj]
     unsigned n_eval = 0, n_reset = 0, n_cut = 0;
     GEnt buf[GL_BATCH];
+    double bpsbuf[GL_BATCH];
+    // Warps take chunks of 32 * GL_BATCH consecutive records from a shared counter (cuts and evaluations
+    // are unevenly spread over the list; fixed strides would leave most warps waiting at the barriers).
+#ifdef SQRN_HOST_EMU
+    const int lane = 0;
+    constexpr int WL = 1;
+    int next_chunk = 0;
+    auto grab = [&]() { const int c0 = next_chunk; next_chunk += WL * GL_BATCH; return c0; };
+#else
+    const int lane = threadIdx.x & 31;
+    constexpr int WL = 32;
+    auto grab = [&]() {
+        int c0 = 0;
+        if (lane == 0) c0 = atomicAdd(&S.misc[12], WL * GL_BATCH);
+        return __shfl_sync(0xffffffffu, c0, 0);
+    };
+#endif
+    if (r == 0) S.misc[12] = 0;
+    Team<TW>::sync();
     // ---- sweep 1: cut, invalidate, arg-max of the cached scores that still hold
     #pragma unroll 1
-    for (int c0 = r; c0 < n; c0 += GL_BATCH * T) {
+    for (int c0 = grab(); c0 < n; c0 = grab()) {
         #pragma unroll
         for (int u = 0; u < GL_BATCH; u++) {
-            const int c = c0 + u * T;
+            const int c = c0 + u * WL + lane;
             if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
         }
         #pragma unroll 1
         for (int u = 0; u < GL_BATCH; u++) {
-            const int c = c0 + u * T;
+            const int c = c0 + u * WL + lane;
             const uint32_t key = buf[u].key;
             if (key == GK_DEAD) continue;
             const uint32_t meta = buf[u].meta;
@@ -1989,7 +2009,10 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     // entry by entry; what passes is collected in a per-warp list and evaluated 32 at a time, so that the
     // ScoreStems region walks (hundreds of instructions each) run with full warps.
     unsigned *fl_hi = (unsigned *)&S.misc[9];     // high word of the best score found so far in this sweep (a lower bound of it)
-    if (r == 0) *fl_hi = best.fin > 0.0 ? (unsigned)__double2hiint(best.fin) : 0u;
+    if (r == 0) { *fl_hi = best.fin > 0.0 ? (unsigned)__double2hiint(best.fin) : 0u; S.misc[12] = 0; }
+#ifdef SQRN_HOST_EMU
+    next_chunk = 0;
+#endif
     Team<TW>::sync();
     double floor = best.fin;
     auto refresh_floor = [&]() {
@@ -2013,13 +2036,12 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         }
     };
     // true: entry c has to be evaluated (its bounds reach the floor)
-    auto screen = [&](int c, const GEnt &e) -> bool {
+    auto screen = [&](int c, const GEnt &e, double bps) -> bool {
         if (e.key == GK_DEAD) return false;
         const uint32_t st = e.meta >> 16;
         if (st == GS_EVAL || st == GS_BELOW) return false;
         if (st == GS_PRUNED && e.v < floor) return false;
         const int len = (int)(e.meta & 0xffffu);
-        const double bps = g.bps[c];
         double ub = score_bound(P, bps);
         if (!(ub < floor || ub < P.minfinscore)) ub = tight_bound(S, P, e.key, len, bps);
         if (ub < floor || ub < P.minfinscore) { gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16), ub); return false; }
@@ -2027,24 +2049,32 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     };
 #ifdef SQRN_HOST_EMU
     #pragma unroll 1
-    for (int c = 0; c < n; c++) { refresh_floor(); buf[0] = gl_load(&g.ent[c]); if (screen(c, buf[0])) evaluate(c); }
+    for (int c = 0; c < n; c++) { refresh_floor(); buf[0] = gl_load(&g.ent[c]); if (screen(c, buf[0], g.bps[c])) evaluate(c); }
 #else
     {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int wid = threadIdx.x >> 5;
         int *wl = (int *)S.ckey + 64 * wid;       // this warp's list of entries to evaluate (Layout::Ccap = 64 per warp)
         int wn = 0;
         #pragma unroll 1
-        for (int c0 = 32 * wid; c0 < n; c0 += GL_BATCH * T) {
+        for (int c0 = grab(); c0 < n; c0 = grab()) {
             #pragma unroll
             for (int u = 0; u < GL_BATCH; u++) {
-                const int c = c0 + u * T + lane;
+                const int c = c0 + u * 32 + lane;
                 if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
+            }
+            refresh_floor();
+            // the bp scores of the records that will be screened, all loads in flight together
+            #pragma unroll
+            for (int u = 0; u < GL_BATCH; u++) {
+                const uint32_t st = buf[u].meta >> 16;
+                const bool want = buf[u].key != GK_DEAD && (st == GS_FRESH || (st == GS_PRUNED && !(buf[u].v < floor)));
+                bpsbuf[u] = want ? g.bps[c0 + u * 32 + lane] : 0.0;
             }
             #pragma unroll 1
             for (int u = 0; u < GL_BATCH; u++) {
-                const int c = c0 + u * T + lane;
+                const int c = c0 + u * 32 + lane;
                 refresh_floor();
-                const bool need = screen(c, buf[u]);
+                const bool need = screen(c, buf[u], bpsbuf[u]);
                 const uint32_t bal = __ballot_sync(0xffffffffu, need);
                 if (need) wl[wn + __popc(bal & ((1u << lane) - 1u))] = c;
                 wn += __popc(bal);
@@ -2383,17 +2413,15 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
                     for (int t = r; t < S.nst - 1; t += T) if (S.stlev[t] != S.stlev2[t]) ch = true;
                     relevel = Team<TW>::any(ch);
                     // its encloser: the older stem with the largest i whose arms lie outside both arms of it
-                    if (r == 0) {
-                        int bi = -1, bj = -1;
-                        #pragma unroll 1
-                        for (int t = 0; t < S.nst - 1; t++) {
-                            const int i = S.sti[t], j = S.stj[t], l = S.stl[t];
-                            if (i + l - 1 < ui && j - l + 1 > uj && i > bi) { bi = i; bj = j; }
-                        }
-                        S.misc[10] = bi; S.misc[11] = bj;
+                    if (r == 0) S.misc[10] = -1;
+                    Team<TW>::sync();
+                    #pragma unroll 1
+                    for (int t = r; t < S.nst - 1; t += T) {
+                        const int i = S.sti[t], j = S.stj[t], l = S.stl[t];
+                        if (i + l - 1 < ui && j - l + 1 > uj) atomicMax(&S.misc[10], (i << 16) | j);      // largest i wins
                     }
                     Team<TW>::sync();
-                    ei = S.misc[10]; ej = S.misc[11];
+                    if (S.misc[10] >= 0) { ei = S.misc[10] >> 16; ej = S.misc[10] & 0xffff; }
                 }
                 #pragma unroll 1
                 for (int t = r; t < S.nst; t += T) S.stlev2[t] = S.stlev[t];
