@@ -533,7 +533,7 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
         DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_cap = pl.gcap;
         const bool trace = getenv("SQRN_TRACE") != nullptr;
         unsigned long long *d_stat = nullptr;
-        if (trace) { TRY(dalloc(ctx, W_GSTAT, 8, &d_stat)); CK(cudaMemsetAsync(d_stat, 0, 8 * sizeof(unsigned long long), st)); W1.g_stat = d_stat; }
+        if (trace) { TRY(dalloc(ctx, W_GSTAT, 16, &d_stat)); CK(cudaMemsetAsync(d_stat, 0, 16 * sizeof(unsigned long long), st)); W1.g_stat = d_stat; }
         W1.ovf_count = cnt; W1.ovf_list = ovf;
         if (pl.tw == 8) k_long<8><<<gg, 256, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
         else k_long<32><<<gg, 1024, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
@@ -544,13 +544,15 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
         CK(cudaGetLastError());
         ctx->n_launches++; ctx->n_glist_launches++;
         if (trace) {
-            unsigned long long h[8]; int hc[4];
+            unsigned long long h[16]; int hc[4];
             CK(cudaStreamSynchronize(st));
             CK(cudaMemcpy(h, d_stat, sizeof h, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(hc, cnt, sizeof hc, cudaMemcpyDeviceToHost));
             fprintf(stderr, "[sqrn] k_long<%d>: %d items (%d overflowed), %d CTAs x %lld entries; steps %llu (level changes %llu), "
                     "entries swept %llu, evaluations %llu, cache resets %llu, cuts %llu\n", pl.tw, W.n_items, hc[0], gg, pl.gcap,
                     h[3], h[4], h[0], h[1], h[2], h[5]);
+            fprintf(stderr, "[sqrn]   cycles (thread 0, summed over CTAs, M): build %.1f, loop %.1f = levels %.1f + sweep1 %.1f + sweep2 %.1f + apply %.1f + rest\n",
+                    h[9] / 1e6, h[8] / 1e6, h[10] / 1e6, h[6] / 1e6, h[7] / 1e6, h[11] / 1e6);
         }
         return SQRN_OK;
     }

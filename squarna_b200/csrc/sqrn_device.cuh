@@ -682,13 +682,29 @@ __device__ __forceinline__ bool stems_cross(int i, int j, int k, int l)
     return (i < k && k < j && j < l) || (k < i && i < l && l < j);
 }
 
+// added >= 0: stlev[] is current except for the stem with this index, which was just appended.  A stem
+// that crosses nothing joins the first-created group whatever the others do (its cross_count is 0 and
+// it cannot clash with anyone), the cross_counts and the first-fit of the others do not change, and the
+// first group only grows -- so if that group already ranks first (misc[13]), every level stays and
+// the new stem is on level 1.  Anything else is recomputed in full.
 template <class C>
-__device__ int team_levels(State &S)
+__device__ int team_levels(State &S, int added = -1)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     const int n = S.nst;
-    if (n == 0) return 0;
+    if (n == 0) { if (r == 0) S.misc[13] = 1; Team<TW>::sync(); return 0; }
+    if (added >= 0 && S.misc[13] == 1) {
+        const int i = S.sti[added], j = S.stj[added];
+        bool x = false;
+        #pragma unroll 1
+        for (int u = r; u < n; u += T) if (u != added && stems_cross(i, j, S.sti[u], S.stj[u])) x = true;
+        if (!Team<TW>::any(x)) {
+            if (r == 0) S.stlev[added] = 1;
+            Team<TW>::sync();
+            return 1;
+        }
+    }
     bool crossing = false;
     #pragma unroll 1
     for (int t = r; t < n; t += T) {
@@ -705,6 +721,7 @@ __device__ int team_levels(State &S)
         // nothing crosses: one group, every stem on level 1
         #pragma unroll 1
         for (int t = r; t < n; t += T) S.stlev[t] = 1;
+        if (r == 0) S.misc[13] = 1;
         Team<TW>::sync();
     } else {
         Team<TW>::sync();
@@ -754,6 +771,11 @@ __device__ int team_levels(State &S)
                 S.stlev[t] = (uint8_t)(lev > 255 ? 255 : lev);
             }
             S.misc[5] = ng;
+            // does the first-created group (home of every stem that crosses nothing) rank first?
+            int first = 1;
+            #pragma unroll 1
+            for (int h = 1; h < ng; h++) if (S.gsz[h] > S.gsz[0]) first = 0;
+            S.misc[13] = first;
         }
         Team<TW>::sync();
         ng = S.misc[5];
@@ -1747,8 +1769,9 @@ __device__ Best persist_step(State &S, const DevParams &P, const DevBatch &B, co
 // every entry CACHES what the last evaluation found:
 //   FRESH   nothing known;
 //   EVAL    g_fin = the adjusted score (ScoreStems) under the structure it was evaluated with;
-//   PRUNED  g_fin = an upper bound of the adjusted score (score_bound / tight_bound) that was
-//           below the best score of the step that looked at it;
+//   PRUNED  g_fin = an upper bound of the adjusted score (tight_bound) that was below the best score of
+//           the step that looked at it;  PRUNED1: the same with score_bound, which does not depend on
+//           the structure and therefore never goes stale;
 //   BELOW   the run's bp score is under minbpscore: no candidate as it stands, kept because a piece of
 //           it may be one after a cut.
 // A step (gl_step) makes two coalesced sweeps over the list:
@@ -1765,8 +1788,13 @@ __device__ Best persist_step(State &S, const DevParams &P, const DevBatch &B, co
 // (seq.py:672-689) both before and after.  The host of T ("encloser": the selected stem with the
 // largest i that encloses T) is found once per step.  Levels: if the level of any OLD stem
 // changed when T was added, every EVAL entry goes back to FRESH.
+#ifdef SQRN_HOST_EMU
+static inline long long gl_clock() { return 0; }
+#else
+__device__ __forceinline__ long long gl_clock() { return clock64(); }
+#endif
 constexpr uint32_t GK_DEAD = 0xffffffffu;
-constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u;
+constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u, GS_PRUNED1 = 4u;
 
 // one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16, v = the cached score / bound
 struct alignas(16) GEnt { uint32_t key, meta; double v; };
@@ -1928,6 +1956,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
 #endif
     if (r == 0) S.misc[12] = 0;
     Team<TW>::sync();
+    const long long t_a = g.stat ? gl_clock() : 0;
     // ---- sweep 1: cut, invalidate, arg-max of the cached scores that still hold
     #pragma unroll 1
     for (int c0 = grab(); c0 < n; c0 = grab()) {
@@ -1944,7 +1973,9 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
             const uint32_t meta = buf[u].meta;
             const int len = (int)(meta & 0xffffu), a = (int)(key & 0xffffu), s = (int)(key >> 16), t = s - a;
             uint32_t st = meta >> 16;
-            if (ul > 0) {
+            // T can cut the run or change its cached score only if one of its arms meets [a - 5, t + 5]
+            // (the run's rows and columns all lie in [a, t]); most records fail this test and are done
+            if (ul > 0 && !((u1 < a - 5 || ui > t + 5) && (uj < a - 5 || v0 > t + 5))) {
                 const int A0 = ui - a, A1 = u1 - a, B0 = v0 - a, B1 = uj - a;
                 const int C0 = t - u1, C1 = t - ui, D0 = t - uj, D1 = t - v0;
                 const int top = len - 1;
@@ -1989,13 +2020,13 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
                     continue;
                 }
                 if (st == GS_EVAL || st == GS_PRUNED) {
-                    // does T meet the window the cached value was computed from?
-                    const int w0 = a - 5, w1 = t + 5, ss = a + len - 1, se = t - len + 1;
-                    const bool touches = (ui <= w1 && u1 >= w0) || (v0 <= w1 && uj >= w0);
+                    // T meets the window the cached value was computed from: stale unless T is shielded
+                    const int ss = a + len - 1, se = t - len + 1;
                     const bool shielded = ei >= 0 && ss < ei && ej < se;
-                    if ((touches && !shielded) || (relevel && st == GS_EVAL)) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
+                    if (!shielded) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
                 }
             }
+            if (relevel && st == GS_EVAL) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
             if (st == GS_EVAL) {
                 const double fin = buf[u].v;
                 if (fin >= P.minfinscore && better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
@@ -2003,6 +2034,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         }
     }
     best = team_argmax<C>(S, best);               // barrier: the appended pieces are visible
+    const long long t_b = g.stat ? gl_clock() : 0;
     n = S.misc[8];
     if (n > g.cap) { ok = false; return best; }
     // ---- sweep 2: FRESH entries, and PRUNED ones whose bound reaches the floor.  The bounds are checked
@@ -2040,10 +2072,11 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         if (e.key == GK_DEAD) return false;
         const uint32_t st = e.meta >> 16;
         if (st == GS_EVAL || st == GS_BELOW) return false;
-        if (st == GS_PRUNED && e.v < floor) return false;
+        if ((st == GS_PRUNED || st == GS_PRUNED1) && e.v < floor) return false;
         const int len = (int)(e.meta & 0xffffu);
         double ub = score_bound(P, bps);
-        if (!(ub < floor || ub < P.minfinscore)) ub = tight_bound(S, P, e.key, len, bps);
+        if (ub < floor || ub < P.minfinscore) { if (st != GS_PRUNED1) gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED1 << 16), ub); return false; }
+        ub = tight_bound(S, P, e.key, len, bps);
         if (ub < floor || ub < P.minfinscore) { gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16), ub); return false; }
         return true;
     };
@@ -2067,7 +2100,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
             #pragma unroll
             for (int u = 0; u < GL_BATCH; u++) {
                 const uint32_t st = buf[u].meta >> 16;
-                const bool want = buf[u].key != GK_DEAD && (st == GS_FRESH || (st == GS_PRUNED && !(buf[u].v < floor)));
+                const bool want = buf[u].key != GK_DEAD && (st == GS_FRESH || ((st == GS_PRUNED || st == GS_PRUNED1) && !(buf[u].v < floor)));
                 bpsbuf[u] = want ? g.bps[c0 + u * 32 + lane] : 0.0;
             }
             #pragma unroll 1
@@ -2091,6 +2124,8 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     }
 #endif
     if (g.stat) {
+        Team<TW>::sync();
+        if (r == 0) { const long long t_c = gl_clock(); atomicAdd(&g.stat[6], (unsigned long long)(t_b - t_a)); atomicAdd(&g.stat[7], (unsigned long long)(t_c - t_b)); }
         if (n_eval) atomicAdd(&g.stat[1], (unsigned long long)n_eval);
         if (n_reset) atomicAdd(&g.stat[2], (unsigned long long)n_reset);
         if (n_cut) atomicAdd(&g.stat[5], (unsigned long long)n_cut);
@@ -2395,11 +2430,17 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         bool ok = true;                             // PERSIST: the run list has not overflowed
         int ui = 0, uj = 0, ul = 0;                 // the stem applied since the last pass over the list
         if (C::PERSIST && mode == MODE_TAIL && (double)S.nst != P.maxstemnum)
+        {
+            const long long t0 = (C::GLIST && g.stat) ? gl_clock() : 0;
             ok = C::GLIST ? gl_build<C>(S, P, B, g) : persist_build<C>(S, P, B, L);
+            if (C::GLIST && g.stat && r == 0) atomicAdd(&g.stat[9], (unsigned long long)(gl_clock() - t0));
+        }
         bool lev_ok = false;                        // stlev[] matches the current stem set
         #pragma unroll 1
         while (ok && mode == MODE_TAIL && (double)S.nst != P.maxstemnum) {
-            team_levels<C>(S);
+            const long long t_it = (C::GLIST && g.stat) ? gl_clock() : 0;
+            team_levels<C>(S, ul > 0 ? S.nst - 1 : -1);
+            if (C::GLIST && g.stat && r == 0) atomicAdd(&g.stat[10], (unsigned long long)(gl_clock() - t_it));
             lev_ok = true;
             Best b;
             if (C::GLIST) {
@@ -2437,7 +2478,9 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
             if (b.fin <= -1e300) break;
             int i = (int)(b.key & 0xffff);
             ui = i; uj = (int)(b.key >> 16) - i; ul = b.len;
+            const long long t_ap = (C::GLIST && g.stat) ? gl_clock() : 0;
             team_apply_stem<C>(S, ui, uj, ul);
+            if (C::GLIST && g.stat && r == 0) { atomicAdd(&g.stat[11], (unsigned long long)(gl_clock() - t_ap)); atomicAdd(&g.stat[8], (unsigned long long)(gl_clock() - t_it)); }
             lev_ok = false;
         }
         if (C::PERSIST && !ok) {
