@@ -189,6 +189,21 @@ SQRN_API int  sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_
                     double *out_fin, double *out_raw, uint8_t *out_flags, int8_t *dbn_code, int min_ccap);
 
 /* counters of the last call: kernels launched, device milliseconds of the main kernel */
+/* Bulk text lane of the CLI's single-sequence mode (host only): what SQUARNA.py:80-256 (input) and
+ * SQRNdbnseq.py:1301-1406 (the printed block) do, for the plain shape of an input -- name line + sequence,
+ * nothing else -- on whole buffers.  SQRN_E_UNSUPPORTED: the text has another shape (default lines, per-entry
+ * reactivities / restraints / reference, non-ASCII, ...): use the per-entry path.  multiline: plain FASTA.
+ * sqrn_text_parse writes the counts always and fills the arrays when the capacities suffice (else
+ * SQRN_E_CAPACITY).  sqrn_text_format writes the blocks of entries [first, first + count); *written = bytes
+ * needed / written. */
+SQRN_API int  sqrn_text_parse(const char *text, int64_t len, int multiline, int64_t *n_entries, int64_t *total_seq,
+                        int64_t cap_entries, int64_t cap_seq, int64_t *name_begin, int32_t *name_len,
+                        int64_t *seq_offsets, uint8_t *seq);
+SQRN_API int  sqrn_text_format(int64_t first, int64_t count, const char *text, const int64_t *name_begin,
+                        const int32_t *name_len, const int64_t *seq_offsets, const uint8_t *seq,
+                        const int64_t *sym_offsets, const uint8_t *dbn, const double *scores, int conslim,
+                        const char *psname, char *out, int64_t cap, int64_t *written);
+
 SQRN_API int  sqrn_ctx_last_stats(const sqrn_ctx *ctx, int64_t *n_launches, double *kernel_ms,
                          int64_t *n_optimal_calls);
 

@@ -465,6 +465,18 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
     inputs, fmt, _single = ParseInput(inputseq, inputfile, inputformat, fmt=fileformat, ignore=ignorewarn,
                                       inputrestr=inputrestr, M=M, B=B)
 
+    # Bulk lane: one greedy parameter set, pl=1, an input made of name + sequence lines only.  The whole file is
+    # parsed, predicted and turned into text on buffers (csrc/sqrn_textio.cpp + the fast lane); any other shape
+    # takes the per-entry path below, which prints the same text.
+    algos_ = {a for a in algos} if algos else None
+    if (inputfile and not inputseq and fmt in ("default", "fasta") and auto is None and not evalonly
+            and len(paramsets) == 1 and (algos_ or set(paramsets[0]["algorithms"])) == {"G"}
+            and not paramsets[0].get("bpp", 0) and poollim == 1 and not interchainonly
+            and min(toplim, outplim, conslim) >= 1 and (fmt == "fasta" or inputformat.startswith("q"))
+            and os.environ.get("SQRN_NO_BULK") is None):
+        if _bulk_lane(inputfile, fmt == "fasta", paramsetnames[0], paramsets[0], conslim, write_to):
+            return
+
     def config_for(sequence):               # autoconfig by RAW (gapped) length, cli.py:870-878
         if auto is None or len(sequence) < 500:
             return 0
@@ -490,6 +502,46 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
             flush()
         pending.append((which, entry))
     flush()
+
+
+_GAP_TABLE = None
+
+
+def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=0, slice_entries=131072):
+    """SQUARNA.py:845-935 for the plain shape of an input.  False: not that shape (nothing was written)."""
+    global _GAP_TABLE
+    import numpy as np
+    from . import _lib
+    from .SQRNdbnseq import get_context
+    with open(path, "rb") as fh:
+        text = fh.read()
+    parsed = _lib.text_parse(text, multiline)
+    if parsed is None:
+        return False
+    if _GAP_TABLE is None:
+        _GAP_TABLE = np.zeros(256, dtype=bool)
+        _GAP_TABLE[[ord(ch) for ch in GAPS]] = True
+    keep = ~_GAP_TABLE[parsed.seq]                                    # UnAlign (seq.py:236-255) on the whole buffer
+    sym = np.ascontiguousarray(parsed.seq[keep])
+    csum = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
+    sym_off = np.ascontiguousarray(csum[parsed.seq_offsets])
+    if int(np.diff(sym_off).max(initial=0)) > 16000:
+        return False
+    ctx = get_context(device)
+    try:
+        dbn, scores, _nst = ctx.fast_predict(paramset, sym, sym_off)
+    except _lib.SqrnError:
+        return False                                                 # e.g. more than 30 pseudoknot levels: general path
+    binary = getattr(sink, "buffer", None)
+    for first in range(0, parsed.n, slice_entries):
+        count = min(slice_entries, parsed.n - first)
+        block = _lib.text_format(parsed, first, count, sym_off, dbn, scores, conslim, psname)
+        if binary is not None:
+            sink.flush()
+            binary.write(block)
+        else:
+            sink.write(block.decode("ascii"))
+    return True
 
 
 # --------------------------------------------------------------------- Main

@@ -18,7 +18,7 @@ MODE_TAIL, MODE_STEP, MODE_YIELD, MODE_FINAL = 0, 1, 2, 3
 EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx_destroy",
            "sqrn_last_error", "sqrn_ctx_set_stream", "sqrn_predict_batch", "sqrn_yield_stems_batch",
            "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
-           "sqrn_ctx_set_tuning"]
+           "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_format"]
 
 _lib = None
 
@@ -52,8 +52,52 @@ def load():
     L.sqrn_fast_predict_device.argtypes = [vp, C.POINTER(ParamSet), i64, i64, i32, vp, vp, vp, vp, vp]
     L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
     L.sqrn_debug_run.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.c_int, C.c_int] + [vp] * 11 + [C.c_int]
+    L.sqrn_text_parse.argtypes = [vp, i64, C.c_int, C.POINTER(i64), C.POINTER(i64), i64, i64, vp, vp, vp, vp]
+    L.sqrn_text_format.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_char_p, vp, i64, C.POINTER(i64)]
     _lib = L
     return L
+
+
+# ---- bulk text lane (host only; include/sqrn.h) -----------------------------
+class ParsedText:
+    """what sqrn_text_parse found: the text itself, name spans, and the sequence tokens as a CSR"""
+    __slots__ = ("text", "n", "name_begin", "name_len", "seq_offsets", "seq")
+
+
+def text_parse(text, multiline):
+    """text: bytes of an input file.  Returns ParsedText, or None when the text is not of the plain shape
+    (the caller then takes the per-entry path)."""
+    L = load()
+    n, tot = C.c_int64(0), C.c_int64(0)
+    cap_e, cap_s = text.count(b">") + 1, len(text) + 1
+    name_begin = np.empty(cap_e, np.int64)
+    name_len = np.empty(cap_e, np.int32)
+    seq_off = np.empty(cap_e + 1, np.int64)
+    seq = np.empty(cap_s, np.uint8)
+    rc = L.sqrn_text_parse(text, len(text), int(bool(multiline)), C.byref(n), C.byref(tot), cap_e, cap_s,
+                           ptr(name_begin), ptr(name_len), ptr(seq_off), ptr(seq))
+    if rc != OK:
+        return None
+    out = ParsedText()
+    out.text, out.n = text, n.value
+    out.name_begin, out.name_len = name_begin[:n.value], name_len[:n.value]
+    out.seq_offsets, out.seq = seq_off[:n.value + 1], seq[:tot.value]
+    return out
+
+
+def text_format(parsed, first, count, sym_offsets, dbn, scores, conslim, psname):
+    """bytes of the RunSQRNdbnseq text blocks of entries [first, first + count)"""
+    L = load()
+    need = C.c_int64(0)
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    args = (first, count, parsed.text, ptr(parsed.name_begin), ptr(parsed.name_len), ptr(parsed.seq_offsets),
+            ptr(parsed.seq), ptr(sym_offsets), ptr(dbn), ptr(scores), int(conslim), psname.encode("ascii"))
+    L.sqrn_text_format(*args, None, 0, C.byref(need))
+    buf = np.empty(max(need.value, 1), np.uint8)
+    rc = L.sqrn_text_format(*args, ptr(buf), len(buf), C.byref(need))
+    if rc != OK:
+        raise SqrnError("sqrn_text_format failed (%d)" % rc)
+    return buf[:need.value].tobytes()
 
 
 class PackedBatch:

@@ -1,0 +1,149 @@
+// sqrn_textio.cpp -- bulk text lane of the CLI's single-sequence mode (host only, no CUDA).
+//
+// At >= 10^7 sequences/s on the device, reading the input and writing SQUARNA's text block per
+// sequence in Python is the end-to-end limiter.  These two functions do what
+// SQUARNA.py:80-256 (ParseDefaultInput / ParseFasta) and SQRNdbnseq.py:1301-1406 (the text of
+// RunSQRNdbnseq) do for the PLAIN shape of an input -- name line + sequence, no reactivities,
+// restraints or reference, one predicted structure per sequence -- on whole buffers.  Anything
+// else is reported as SQRN_E_UNSUPPORTED and the caller takes the general (per-entry) path, so
+// the text produced is the same either way (tests/test_host_python.py compares both).
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/sqrn.h"
+
+namespace {
+
+// str.strip() / str.split() whitespace, ASCII part
+inline bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
+inline bool is_gap(unsigned char c) { return c == '-' || c == '.' || c == '~'; }      // seq.py:12
+
+// repr(round(x, 3)) for the magnitudes scores have: the decimal with at most three fraction digits,
+// trailing zeros dropped but one kept ("12.0", "0.5", "187.935", "-0.0")
+inline int fmt3(char *dst, double x)
+{
+    int n = snprintf(dst, 48, "%.3f", x);
+    while (n > 0 && dst[n - 1] == '0' && n > 1 && dst[n - 2] != '.') n--;
+    return n;
+}
+
+}  // namespace
+
+// One pass over the text.  multiline != 0: plain FASTA (a sequence may span lines, whole stripped
+// lines are joined, SQUARNA.py:239-256); 0: SQUARNA's default format with the sequence on the
+// first line after the name and nothing but blank lines after it (SQUARNA.py:80-203 with
+// inputformat "q..."), the sequence being the first whitespace-separated token.
+// Writes the counts always; fills the arrays when the capacities suffice, else SQRN_E_CAPACITY.
+// name_begin/name_len: the stripped '>' line; seq_offsets[n+1] + seq: the sequence tokens.
+extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int64_t *n_entries, int64_t *total_seq,
+                               int64_t cap_entries, int64_t cap_seq, int64_t *name_begin, int32_t *name_len,
+                               int64_t *seq_offsets, uint8_t *seq)
+{
+    if (!text || len < 0 || !n_entries || !total_seq) return SQRN_E_BADARG;
+    const bool fill = name_begin && name_len && seq_offsets && seq;
+    int64_t n = 0, tot = 0;
+    bool overflow = false;
+    int data_lines = 0;              // non-blank data lines of the current entry
+    int raw_lines = 0;               // all its data lines, blank ones included
+    bool in_entry = false;
+    int64_t p = 0;
+    while (p < len) {
+        // one line [p, e), newline at e (or end of text)
+        const char *nl = (const char *)memchr(text + p, '\n', (size_t)(len - p));
+        const int64_t e = nl ? (int64_t)(nl - text) : len;
+        int64_t a = p, b = e;
+        for (int64_t q = p; q < e; q++) {
+            const unsigned char c = (unsigned char)text[q];
+            if (c >= 0x80) return SQRN_E_UNSUPPORTED;                 // not ASCII: characters != bytes
+            if (c == '\r' && q + 1 != e) return SQRN_E_UNSUPPORTED;   // a lone CR is a line break for Python
+        }
+        while (a < b && is_ws((unsigned char)text[a])) a++;
+        while (b > a && is_ws((unsigned char)text[b - 1])) b--;
+        if (p < e && text[p] == '>') {                                // startswith('>') on the raw line
+            if (in_entry && !multiline && data_lines != 1) return SQRN_E_UNSUPPORTED;
+            if (n < cap_entries && fill) { name_begin[n] = a; name_len[n] = (int32_t)(b - a); seq_offsets[n] = tot; }
+            else overflow = true;
+            n++;
+            in_entry = true; data_lines = 0; raw_lines = 0;
+        } else if (a < b) {                                           // a non-blank data line
+            if (!in_entry) {
+                if (multiline) { p = e + 1; continue; }               // FASTA: text before the first '>' is dropped
+                return SQRN_E_UNSUPPORTED;                            // default reactivities / restraints / reference lines
+            }
+            int64_t tb = b;
+            if (!multiline) {
+                // the sequence is the FIRST line after the name (a blank one there is an error in the reference);
+                // later non-blank lines are reactivities / restraints / reference
+                if (raw_lines >= 1) return SQRN_E_UNSUPPORTED;
+                tb = a;
+                while (tb < b && !is_ws((unsigned char)text[tb])) tb++;   // first token; the rest is a comment
+            }
+            if (tot + (tb - a) <= cap_seq && fill && !overflow) memcpy(seq + tot, text + a, (size_t)(tb - a));
+            else overflow = true;
+            tot += tb - a;
+            data_lines++; raw_lines++;
+        } else if (in_entry) raw_lines++;
+        p = e + 1;
+    }
+    if (in_entry && !multiline && data_lines != 1) return SQRN_E_UNSUPPORTED;
+    if (n == 0) return SQRN_E_UNSUPPORTED;
+    *n_entries = n; *total_seq = tot;
+    if (!fill || overflow || n > cap_entries) return SQRN_E_CAPACITY;
+    seq_offsets[n] = tot;
+    return SQRN_OK;
+}
+
+// The text block of RunSQRNdbnseq (SQRNdbnseq.py:1301-1406) for entries [first, first + count) of a
+// parsed input whose prediction has ONE structure per sequence:
+//   name / sequence / '_' * L / dbn \t top-<conslim>_consensus / '=' * L / dbn \t #1 \t total \t struct \t react \t <psname>
+// seq_offsets + seq: the sequence tokens as parsed (gaps included); sym_offsets + dbn: the ungapped
+// CSR the prediction ran on and its dot-bracket bytes (gap columns print '.', ReAlign, seq.py:210-233;
+// separators were already put back by the kernel).  scores: 3 per sequence, already round(x, 3);
+// a structure score of exactly 0 prints as the int 0 (seq.py:871).
+extern "C" int sqrn_text_format(int64_t first, int64_t count, const char *text, const int64_t *name_begin,
+                                const int32_t *name_len, const int64_t *seq_offsets, const uint8_t *seq,
+                                const int64_t *sym_offsets, const uint8_t *dbn, const double *scores, int conslim,
+                                const char *psname, char *out, int64_t cap, int64_t *written)
+{
+    if (!text || !name_begin || !name_len || !seq_offsets || !seq || !sym_offsets || !dbn || !scores || !psname || !written)
+        return SQRN_E_BADARG;
+    const size_t pl = strlen(psname);
+    char cons[48];
+    const int cl = snprintf(cons, sizeof cons, "\ttop-%d_consensus\n", conslim);
+    int64_t w = 0;
+    // needed size first (cheap): per entry name + 5 L + fixed
+    int64_t need = 0;
+    for (int64_t k = first; k < first + count; k++)
+        need += name_len[k] + 5 * (seq_offsets[k + 1] - seq_offsets[k]) + 6 + cl + 4 + 3 * 32 + 5 + (int64_t)pl;
+    *written = need;
+    if (!out || cap < need) return SQRN_E_CAPACITY;
+    for (int64_t k = first; k < first + count; k++) {
+        const int64_t L = seq_offsets[k + 1] - seq_offsets[k];
+        const uint8_t *s = seq + seq_offsets[k];
+        const uint8_t *d = dbn + sym_offsets[k];
+        const int64_t nd = sym_offsets[k + 1] - sym_offsets[k];
+        memcpy(out + w, text + name_begin[k], (size_t)name_len[k]); w += name_len[k]; out[w++] = '\n';
+        memcpy(out + w, s, (size_t)L); w += L; out[w++] = '\n';
+        memset(out + w, '_', (size_t)L); w += L; out[w++] = '\n';
+        char *line = out + w;                       // the re-gapped dot-bracket line, written once and copied
+        int64_t q = 0;
+        for (int64_t c = 0; c < L; c++) {
+            if (is_gap(s[c])) line[c] = '.';
+            else { if (q >= nd) return SQRN_E_BADARG; line[c] = (char)d[q++]; }
+        }
+        if (q != nd) return SQRN_E_BADARG;
+        w += L;
+        memcpy(out + w, cons, (size_t)cl); w += cl;
+        memset(out + w, '=', (size_t)L); w += L; out[w++] = '\n';
+        memcpy(out + w, line, (size_t)L); w += L;
+        memcpy(out + w, "\t#1\t", 4); w += 4;
+        const double total = scores[3 * k], st = scores[3 * k + 1], re = scores[3 * k + 2];
+        w += fmt3(out + w, total); out[w++] = '\t';
+        if (st == 0.0) out[w++] = '0'; else w += fmt3(out + w, st);
+        out[w++] = '\t';
+        w += fmt3(out + w, re); out[w++] = '\t';
+        memcpy(out + w, psname, pl); w += (int64_t)pl; out[w++] = '\n';
+    }
+    *written = w;
+    return SQRN_OK;
+}

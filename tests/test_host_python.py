@@ -135,3 +135,89 @@ def test_evalonly_cli_text_matches_reference():
         os.chdir(cwd)
     with open(os.path.join(G, "cli", "seq_evalonly.txt")) as f:
         assert buf.getvalue() == f.read()
+
+
+# ---- bulk text lane (csrc/sqrn_textio.cpp): the same entries and the same text as the per-entry Python path
+def _rand_text(rng, n, fasta, gaps=True):
+    lines = []
+    for k in range(n):
+        name = ">seq%d" % k + rng.choice(["", " some description", "\tx=1  "])
+        alphabet = "ACGUTacgun" + ("-.~" if gaps else "")
+        seq = "".join(rng.choice(alphabet) for _ in range(rng.randint(1, 90)))
+        if seq[0] in "-.~":
+            seq = "A" + seq[1:]
+        lines.append(name)
+        if fasta:
+            while seq:
+                cut = rng.randint(1, 60)
+                lines.append(rng.choice(["", " "]) + seq[:cut])
+                seq = seq[cut:]
+                if rng.random() < 0.1:
+                    lines.append("")
+        else:
+            lines.append(seq + rng.choice(["", " a comment", "\t# x"]))
+            if rng.random() < 0.2:
+                lines.append("")
+    return "\n".join(lines) + rng.choice(["", "\n", "\r\n"])
+
+
+@pytest.mark.parametrize("fasta", [False, True], ids=["default", "fasta"])
+def test_bulk_text_parse_matches_the_entry_parsers(tmp_path, fasta):
+    import random
+    from squarna_b200 import _lib
+    rng = random.Random(5)
+    for trial in range(20):
+        text = _rand_text(rng, rng.randint(1, 40), fasta)
+        if trial % 4 == 3:
+            text = text.replace("\r\n", "\n").replace("\n", "\r\n")
+        path = tmp_path / ("t%d.fa" % trial)
+        path.write_bytes(text.encode())
+        want = list(CLI.ParseFasta(str(path)) if fasta else CLI.ParseDefaultInput(str(path), "qtrf"))
+        got = _lib.text_parse(text.encode(), fasta)
+        assert got is not None and got.n == len(want)
+        for k, (name, seq, reacts, rests, ref) in enumerate(want):
+            assert reacts is None and rests is None and ref is None
+            b = int(got.name_begin[k])
+            assert text.encode()[b:b + int(got.name_len[k])].decode() == name
+            assert bytes(got.seq[got.seq_offsets[k]:got.seq_offsets[k + 1]]).decode() == seq
+
+
+def test_bulk_text_parse_declines_other_shapes():
+    from squarna_b200 import _lib
+    for text in (b"....\n>s\nACGU\n",                       # default restraints line
+                 b">s\nACGU\n0.1 0.2 0.3 0.4\n",            # reactivities of the entry
+                 b">s\nACGU\n\n((.))\n",                   # restraints after a blank reactivity line
+                 b">s\n\nACGU\n",                           # blank sequence line (an error in the reference)
+                 b">s\n", b"", b"ACGU\n",                    # no sequence / no entry
+                 b">s\nAC\xc3\xa9GU\n", b">s\nAC\rGU\n"):   # not ASCII / lone CR
+        assert _lib.text_parse(text, False) is None, text
+    assert _lib.text_parse(b"junk\n>s\nAC\nGU\n", True).n == 1          # FASTA drops text before the first '>'
+
+
+def test_bulk_text_format_matches_the_entry_printer():
+    import random
+    import numpy as np
+    from squarna_b200 import _lib
+    rng = random.Random(6)
+    text = _rand_text(rng, 60, False).encode()
+    parsed = _lib.text_parse(text, False)
+    seqs = [bytes(parsed.seq[parsed.seq_offsets[k]:parsed.seq_offsets[k + 1]]).decode() for k in range(parsed.n)]
+    short = ["".join(ch for ch in s if ch not in S.GAPS) for s in seqs]
+    dbns = ["".join(rng.choice("..(([)]).") for _ in s) for s in short]
+    sym_off = np.zeros(parsed.n + 1, np.int64)
+    np.cumsum([len(s) for s in short], out=sym_off[1:])
+    dbn = np.frombuffer("".join(dbns).encode(), np.uint8)
+    vals = [0.0, 0.5, 12.0, 187.935, 3.1, 1234567.891, 0.001, 45.67, 100.0, 0.125]
+    scores = np.array([[rng.choice(vals), rng.choice(vals), rng.choice(vals)] for _ in seqs])
+    got = _lib.text_format(parsed, 0, parsed.n, sym_off, dbn, scores, 2, "fastestG").decode()
+    want = io.StringIO()
+    for k, s in enumerate(seqs):
+        name = text[int(parsed.name_begin[k]):int(parsed.name_begin[k]) + int(parsed.name_len[k])].decode()
+        long_dbn = S.ReAlign(dbns[k], s)
+        total, struct, react = (float(x) for x in scores[k])
+        pred = (long_dbn, [(long_dbn, (total, 0 if struct == 0 else struct, react), [0])], [math.nan] * 6, [math.nan] * 7)
+        S._print_entry(name, s, None, None, None, 3, want)
+        S._print_prediction(pred, s, None, None, ["fastestG"], 2, 1, want)
+    assert got == want.getvalue()
+    part = _lib.text_format(parsed, 7, 5, sym_off, dbn, scores, 2, "fastestG").decode()
+    assert part in got and part.startswith(">seq7")
