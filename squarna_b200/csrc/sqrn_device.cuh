@@ -155,7 +155,7 @@ struct Layout {
     int o_pbps, o_pkey;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
         o_sti, o_stj, o_stl, o_stlev, o_evpos, o_evid, o_cc, o_perm, o_grp, o_gsz,
-        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, o_stlev2, total;
+        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, o_stlev2, o_evjump, total;
 };
 
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -231,6 +231,9 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_rcl = o;     o += extras >= 0 ? L.Ncap : 0;
     L.o_stlev = o;   o += L.Scap;
     L.o_stlev2 = o;  o += pcap < 0 ? L.Scap : 0;      // pcap < 0: global persistent list (levels of the previous step)
+    o = align_up(o, 2);
+    L.o_evjump = tw != 1 ? o : -1;                    // CTA teams (and the host emulation, tw = 0): where the arm walk of
+    o += tw != 1 ? 4 * L.Scap : 0;                    // ScoreStems may jump to (team_apply_stem)
     L.total = align_up(o, 16);
     return L;
 }
@@ -333,7 +336,7 @@ struct State {
     int dstride, doffset;            // this team scans the anti-diagonals 4 + doffset + dstride * q (cluster: rank, size)
     uint8_t  *code, *rcl, *stlev, *stlev2;
     uint16_t *rcode;
-    int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *evpos, *evid, *perm, *grp, *rbv, *rbw;
+    int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *evpos, *evid, *evjump, *perm, *grp, *rbv, *rbw;
     uint32_t *M, *PR, *rowok, *colokR, *Ub, *ckey, *rkey, *pkey;
     int32_t  *cc, *gsz, *Ubase;
     uint16_t *clen, *rlen;
@@ -352,6 +355,7 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
     s.sepcnt = (int16_t *)(base + L.o_sepcnt);
     s.sti = (int16_t *)(base + L.o_sti);  s.stj = (int16_t *)(base + L.o_stj);  s.stl = (int16_t *)(base + L.o_stl);
     s.evpos = (int16_t *)(base + L.o_evpos);  s.evid = (int16_t *)(base + L.o_evid);
+    s.evjump = L.o_evjump >= 0 ? (int16_t *)(base + L.o_evjump) : nullptr;
     s.perm = (int16_t *)(base + L.o_perm);  s.grp = (int16_t *)(base + L.o_grp);
     s.rbv = (int16_t *)(base + L.o_rbv);  s.rbw = (int16_t *)(base + L.o_rbw);
     s.M = (uint32_t *)(base + L.o_M);  s.PR = (uint32_t *)(base + L.o_PR);
@@ -667,6 +671,32 @@ __device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = 
     }
     S.nst = idx + 1;
     Team<TW>::sync();
+    if (TW != 1 && S.evjump) {
+        // A selected stem t = (i, j) is CLOSED when no selected stem starts inside (i, j) and ends beyond j.
+        // The arm walk of ScoreStems (region_stems) that meets the 5' arm of a closed stem lying inside the
+        // candidate's region may jump to the first arm behind j: everything in between is under the block
+        // the stem opens (`inblockend` >= j, seq.py:672-689) and can neither count nor extend it.
+        const int ne2 = 2 * S.nst;
+        #pragma unroll 1
+        for (int q = r; q < ne2; q += T) {
+            const int id = S.evid[q];
+            int jmp = q + 1;
+            if (!(id & 1)) {
+                const int t = id >> 1, ti = S.sti[t], tj = S.stj[t];
+                bool closed = true;
+                #pragma unroll 1
+                for (int u = 0; u < S.nst && closed; u++) { const int ui_ = S.sti[u]; if (ui_ > ti && ui_ < tj && S.stj[u] > tj) closed = false; }
+                if (closed) {
+                    int lo_ = q + 1, hi_ = ne2;
+                    #pragma unroll 1
+                    while (lo_ < hi_) { int mid = (lo_ + hi_) >> 1; if (S.evpos[mid] <= tj) lo_ = mid + 1; else hi_ = mid; }
+                    jmp = lo_;
+                }
+            }
+            S.evjump[q] = (int16_t)jmp;
+        }
+        Team<TW>::sync();
+    }
     if (refresh) team_unpaired_prefix<C>(S);
 }
 
@@ -1092,6 +1122,7 @@ __device__ __forceinline__ void region_stems(const State &S, int ss, int se, Reg
                     }
                     ibe = j;
                 }
+                if (S.evjump) q = S.evjump[q] - 1;      // a closed stem: on to the first arm behind it
                 continue;
             }
         } else if (i > ss) continue;                    // 3' arm of an inner stem
