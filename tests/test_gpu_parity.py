@@ -123,6 +123,37 @@ def test_fast_kernel_equals_general_kernel(gpu_ctx):
         assert np.array_equal(x, y)
 
 
+def test_config2_full_size(gpu_ctx):
+    """BASELINE config 2 at full size (1 M sequences, 60..200 nt, fastest.conf, pl=1), the bench workload itself:
+    the persistent-list fast lane against the rescanning general kernel (two different algorithms for the same
+    steps) on every sequence, the oracle on a 30 k prefix, and structural properties of all 1 M results."""
+    import bench
+    sym, off, lens = bench.make_batch(1_000_000, bench.SEED)
+    dbn, scores, nst = gpu_ctx.fast_predict(T.FASTEST, sym, off)
+    try:
+        gpu_ctx.set_no_fast_kernel(True)
+        dbn2, scores2, nst2 = gpu_ctx.fast_predict(T.FASTEST, sym, off)
+    finally:
+        gpu_ctx.set_no_fast_kernel(False)
+    assert np.array_equal(dbn, dbn2) and np.array_equal(scores, scores2) and np.array_equal(nst, nst2)
+    k = 30_000
+    odbn, oscores, onst = O.predict_batch_simple(sym[:int(off[k])], off[:k + 1], [T.FASTEST], poollim=1, nthreads=16)
+    glyph = np.zeros(256, np.int8)
+    for lv, (o, c) in enumerate(zip(_OPEN, _CLOSE), 1):
+        glyph[ord(o)], glyph[ord(c)] = lv, -lv
+    assert np.array_equal(glyph[dbn[:int(off[k])]], odbn)
+    assert np.array_equal(scores[:k], oscores) and np.array_equal(nst[:k], onst)
+    # every structure is balanced on every level, every stem has >= minlen = 4 pairs, scores are 3-decimal values
+    lev = glyph[dbn].astype(np.int64)
+    for L in range(1, int(np.abs(lev).max()) + 1):
+        bal = np.add.reduceat((lev == L).astype(np.int64) - (lev == -L), off[:-1])
+        assert not bal.any()
+    pairs = np.add.reduceat((lev > 0).astype(np.int64), off[:-1])
+    assert (pairs >= 4 * nst).all() and ((nst == 0) == (pairs == 0)).all()
+    assert np.array_equal(np.round(scores, 3), scores)
+    assert (scores[:, 2] == 0.5).all() and (scores[nst == 0, 1] == 0).all()
+
+
 def test_yield_stems(gpu_ctx):
     """AnnotateStems seam (YieldStems): same stems, same order, same scores"""
     rng = random.Random(18)
