@@ -522,7 +522,8 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
     int grid = pl.grid;
     int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
     if (grid > teams) grid = std::max(teams, 1);
-    if (pl.glist && W.mode == MODE_TAIL && !W.init_off) {       // items with pre-selected stems (pool tails) have few steps left: rescan
+    static const bool glist_init = getenv("SQRN_GLIST_INIT") != nullptr;       // experiment: the list also for pool tails
+    if (pl.glist && W.mode == MODE_TAIL && (!W.init_off || glist_init)) {       // items with pre-selected stems (pool tails) have few steps left: rescan
         const int gg = std::max(1, std::min(pl.grid_g, W.n_items));
         GEnt *ge; double *gb; int32_t *ovf; int *cnt;
         TRY(dalloc(ctx, W_GENT, (size_t)gg * pl.gcap, &ge));
@@ -759,6 +760,13 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     if (trace) {
         fprintf(stderr, "[sqrn] fast_predict_host: prepare %.2f ms, enqueue %.2f ms, wait %.2f ms, finish %.2f ms\n",
                 t_1 - t_0, t_2 - t_1, t_3 - t_2, now() - t_3);
+        {
+            std::vector<int> hc(4 * FAST_MAX_CHUNKS);
+            cudaMemcpy(hc.data(), d_counter, hc.size() * sizeof(int), cudaMemcpyDeviceToHost);
+            long long ovf = 0;
+            for (int c = 0; c < nchunks; c++) ovf += hc[4 * c + 1];
+            fprintf(stderr, "[sqrn]   items sent to the rescanning kernel (run-list overflow): %lld of %lld\n", ovf, (long long)n_seqs);
+        }
         for (int c = 0; c < nchunks; c++) {
             float a = 0, b = 0;
             cudaEventElapsedTime(&a, ctx->ev_k0[0], ctx->ev_k0[c]); cudaEventElapsedTime(&b, ctx->ev_k0[0], ctx->ev_k1[c]);
@@ -868,7 +876,7 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
     DevWork G; memset(&G, 0, sizeof G);
     G.mode = W.mode; G.region_mode = ctx->region_mode;
     int32_t *d_iseq; TRY(upload(ctx, W_ISEQ, W.item_seq.data(), (size_t)n, &d_iseq)); G.item_seq = d_iseq;
-    if (!W.init_off.empty()) {
+    if (!W.init_off.empty() && !W.init_stems.empty()) {
         int64_t *d_io; int32_t *d_is;
         TRY(upload(ctx, W_IOFF, W.init_off.data(), (size_t)n + 1, &d_io));
         TRY(upload(ctx, W_ISTEMS, W.init_stems.data(), W.init_stems.size(), &d_is));

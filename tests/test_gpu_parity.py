@@ -215,6 +215,8 @@ def _oracle_many(cases, paramsets, poollim):
     ("greedy_pl100", [T.DEFG1, T.DEFG2], 100, 10, 90, 120),
     ("greedy_pl5", [T.DEFG1, T.DEFG2], 5, 10, 120, 120),
     ("g1000_pl100", [T.G1000], 100, 150, 330, 10),
+    ("fastest_pl1_long", [T.FASTEST], 1, 330, 800, 20),       # CTA teams with the global candidate list, non-plain batches
+    ("g1000_pl1_long", [T.G1000], 1, 330, 600, 10),
 ])
 def test_predict_batch_full(gpu_ctx, name, paramsets, poollim, lo, hi, count):
     """full SQRNdbnseq semantics (pool, dedupe, ranking, consensus, restraints, reactivities,
