@@ -74,6 +74,7 @@ k_cluster(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
     const unsigned cr = cl.block_rank(), cs = cl.num_blocks();
     State S = bind_state(smem, L);
     S.dstride = (int)cs; S.doffset = (int)cr;
+    cl.sync();                              // every CTA of the cluster is resident before anyone writes into its shared memory
     for (;;) {
         if (cr == 0 && threadIdx.x == 0) {
             int it = atomicAdd(Wk.counter, 1);

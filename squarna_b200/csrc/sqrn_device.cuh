@@ -2209,6 +2209,7 @@ __device__ int team_choose(State &S, const Layout &L, const Best &best, double s
     }
     Team<TW>::sync();
     int nin = S.misc[6];
+    Team<TW>::sync();                      // everyone has read the count before thread 0 reuses the word below
     if (nin > L.Ocap || nin > 32767) return -1;
     if (r == 0) {
         int n = 0;
