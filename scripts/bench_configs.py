@@ -27,6 +27,9 @@ def rand_seqs(rng, n, lo, hi):
 
 def leg_tail(name, seqs, ps, oracle_n):
     ctx = S.get_context(0)
+    if os.environ.get("SQRN_CLUSTER"):            # 1: never a cluster, 2/4/8/16: always that size (default: automatic)
+        ctx.set_cluster(int(os.environ["SQRN_CLUSTER"]))
+        name += " cluster=" + os.environ["SQRN_CLUSTER"]
     sym, off = pack_sequences(seqs)
     k = int(np.argmax(np.diff(off)))                            # warm-up on the longest sequence: module load, parameter
     ctx.fast_predict(ps, sym[int(off[k]):int(off[k + 1])], np.array([0, off[k + 1] - off[k]], dtype=np.int64))   # digest, scratch

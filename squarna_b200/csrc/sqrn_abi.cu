@@ -56,12 +56,14 @@ __device__ __forceinline__ void work_loop(const DevParams *__restrict__ Pg, cons
 // tens of KB, the N x N matrices never exist -- and scans every CS-th anti-diagonal; the per-CTA
 // winners are exchanged through distributed shared memory (cluster_best) and every replica applies
 // the same stem.  Rank 0 fetches the work items and writes the results.
-template <bool PLAIN, bool STDP>
+// GL: the cluster shares ONE global candidate list (gl_build / gl_step): its CTAs take anti-diagonals (build) and
+// record chunks (sweeps) from counters in global memory and meet through the same DSMEM exchange twice per step.
+template <bool PLAIN, bool STDP, bool GL = false>
 __global__ void __launch_bounds__(1024, 1)
 k_cluster(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
 {
     namespace cg = cooperative_groups;
-    using C = Cfg<32, PLAIN, STDP, MODE_TAIL, -1, true>;
+    using C = Cfg<32, PLAIN, STDP, MODE_TAIL, -1, true, GL>;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ DevParams Psh;
     {
@@ -181,7 +183,7 @@ struct CachedStems {
 
 enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GCNT, W_GSTAT, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GCNT, W_GCNT2, W_GSTAT, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -332,7 +334,7 @@ static int get_params(sqrn_ctx *ctx, const sqrn_paramset &ps, int nmax, const PE
 // ------------------------------------------------------------- launch plan
 struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; int cluster = 0; bool cl_plain = false;
               size_t smem_rescan = 0; int grid_rescan = 0;
-              bool glist = false; Layout Lg; size_t smem_g = 0; int grid_g = 0; long long gcap = 0; };
+              bool glist = false; Layout Lg; size_t smem_g = 0; int grid_g = 0; long long gcap = 0; int grid_classic = 0; };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -453,13 +455,14 @@ static int make_fast_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int n_items,
 
 // Few long sequences: give each one a thread-block cluster instead of a single CTA (k_cluster).
 // n_items = work items of the launch; plain = no reactivities / restraints / smat / interchainonly.
-template <bool PLAIN, bool STDP>
+template <bool PLAIN, bool STDP, bool GL = false>
 static int plan_cluster_t(sqrn_ctx *ctx, Plan &pl, int cs)
 {
-    auto kern = k_cluster<PLAIN, STDP>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    auto kern = k_cluster<PLAIN, STDP, GL>;
+    const size_t smem = GL ? pl.smem_g : pl.smem;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = pl.smem;
+    cfg.gridDim = dim3((unsigned)(cs * ctx->sm_count)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
@@ -474,15 +477,17 @@ static void maybe_cluster(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int n_items,
 {
     if (pl.tw != 32 || !tail_mode || ctx->no_cluster || n_items < 1) return;
     int want = ctx->force_cluster;
-    if (!want && pl.glist) return;                           // the global-list kernel beats rescanning clusters
     if (!want) {
         if (2 * n_items > ctx->sm_count) return;             // enough sequences to fill the SMs one CTA each
         want = 8;
         while (want > 2 && want * n_items > ctx->sm_count) want >>= 1;
     }
     pl.cl_plain = plain && P.hp.std_pairs;
+    pl.grid_classic = pl.grid;
     for (int cs = want; cs >= 2; cs >>= 1) {
-        int rc = pl.cl_plain ? plan_cluster_t<true, true>(ctx, pl, cs) : plan_cluster_t<false, false>(ctx, pl, cs);
+        // with a global candidate list planned (k_long), the cluster shares one list; else it rescans
+        int rc = pl.glist && pl.tw == 32 ? plan_cluster_t<false, false, true>(ctx, pl, cs)
+               : pl.cl_plain ? plan_cluster_t<true, true>(ctx, pl, cs) : plan_cluster_t<false, false>(ctx, pl, cs);
         if (rc == SQRN_OK) return;
     }
     pl.cluster = 0;
@@ -507,6 +512,35 @@ static int dalloc(sqrn_ctx *ctx, int slot, size_t count, T **d)
 // one launch of the work kernel the plan names
 static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t st, const DevBatch &B, const DevWork &W)
 {
+    static const bool glist_init = getenv("SQRN_GLIST_INIT") != nullptr;       // experiment: the list also for pool tails
+    const bool use_glist = pl.glist && W.mode == MODE_TAIL && (!W.init_off || glist_init);
+    if (pl.cluster && use_glist && pl.tw == 32) {
+        // a thread-block cluster per sequence over ONE shared candidate list; overflowed items go to k_work<32> behind it
+        const int ncl = std::min(pl.grid, std::max(W.n_items, 1));
+        GEnt *ge; double *gb; int32_t *ovf; int *cnt, *gcnt;
+        TRY(dalloc(ctx, W_GENT, (size_t)ncl * pl.gcap, &ge));
+        TRY(dalloc(ctx, W_GBPS, (size_t)ncl * pl.gcap, &gb));
+        TRY(dalloc(ctx, W_OVF, (size_t)W.n_items, &ovf));
+        TRY(dalloc(ctx, W_GCNT, 4, &cnt));
+        TRY(dalloc(ctx, W_GCNT2, (size_t)4 * ncl, &gcnt));
+        CK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
+        CK(cudaMemsetAsync(gcnt, 0, (size_t)4 * ncl * sizeof(int), st));
+        DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_cap = pl.gcap; W1.g_cnt = gcnt;
+        W1.ovf_count = cnt; W1.ovf_list = ovf;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ncl * pl.cluster)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = pl.smem_g; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)pl.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const DevParams *dp = P.d_p;
+        CK(cudaLaunchKernelEx(&cfg, k_cluster<false, false, true>, dp, B, W1, pl.Lg));
+        DevWork W2 = W; W2.order = ovf; W2.n_items_dev = cnt; W2.counter = cnt + 1;
+        int g2 = pl.grid_classic > 0 ? pl.grid_classic : ctx->sm_count;
+        k_work<32><<<g2, pl.threads, pl.smem, st>>>(P.d_p, B, W2, pl.L);
+        CK(cudaGetLastError());
+        ctx->n_launches++; ctx->n_cluster_launches++; ctx->n_glist_launches++;
+        return SQRN_OK;
+    }
     if (pl.cluster) {
         int ncl = std::min(pl.grid, std::max(W.n_items, 1));
         cudaLaunchConfig_t cfg = {};
@@ -523,8 +557,7 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
     int grid = pl.grid;
     int teams = (W.n_items + pl.tpc - 1) / pl.tpc;
     if (grid > teams) grid = std::max(teams, 1);
-    static const bool glist_init = getenv("SQRN_GLIST_INIT") != nullptr;       // experiment: the list also for pool tails
-    if (pl.glist && W.mode == MODE_TAIL && (!W.init_off || glist_init)) {       // items with pre-selected stems (pool tails) have few steps left: rescan
+    if (use_glist) {       // items with pre-selected stems (pool tails) have few steps left: they rescan
         const int gg = std::max(1, std::min(pl.grid_g, W.n_items));
         GEnt *ge; double *gb; int32_t *ovf; int *cnt;
         TRY(dalloc(ctx, W_GENT, (size_t)gg * pl.gcap, &ge));

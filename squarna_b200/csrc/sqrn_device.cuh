@@ -132,6 +132,7 @@ struct DevWork {
     void          *g_ent;        // Cfg::GLIST: persistent candidate lists (16-byte GEnt records), slot b = [b * g_cap, (b + 1) * g_cap)
     double        *g_bps;
     long long      g_cap;
+    int           *g_cnt;        // cluster flavour: 4 ints per slot -- [0] records in the list, [1] chunk counter of the sweeps
     unsigned long long *g_stat;      // optional counters: [0] entries swept, [1] ScoreStems evaluations, [2] cache resets,
                                      // [3] steps, [4] steps with a level change, [5] cuts
     int           *ovf_count;    // Cfg::PERSIST kernels: items whose run list overflowed are appended here and
@@ -1829,7 +1830,7 @@ constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u, G
 
 // one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16, v = the cached score / bound
 struct alignas(16) GEnt { uint32_t key, meta; double v; };
-struct GList { GEnt *ent; double *bps; int cap; unsigned long long *stat; };
+struct GList { GEnt *ent; double *bps; int cap; unsigned long long *stat; int *cnt; };
 constexpr int GL_BATCH = 8;       // records a thread loads back to back before it looks at any (memory-level parallelism)
 
 __device__ __forceinline__ GEnt gl_load(const GEnt *p)
@@ -1881,6 +1882,21 @@ __device__ __forceinline__ bool gl_wanted(int N, const DevParams &P, long long c
     return dens * N * (double)N <= 0.8 * (double)cap;
 }
 
+template <class C> __device__ __forceinline__ Best cluster_best(State &S, Best b, int step);
+
+// barrier of everything that works on the item: the CTA, or the thread-block cluster (whose CTAs share
+// one list; its counters then live in global memory, DevWork::g_cnt)
+template <class C>
+__device__ __forceinline__ void gl_sync()
+{
+#ifndef SQRN_HOST_EMU
+    if (C::CLUSTER) { cooperative_groups::this_cluster().sync(); return; }
+#endif
+    Team<C::TW>::sync();
+}
+template <class C>
+__device__ __forceinline__ bool gl_leader(const State &S) { return Team<C::TW>::rank() == 0 && (!C::CLUSTER || S.doffset == 0); }
+
 // Enumerates the maximal runs of the current structure state into the global list (a warp per
 // anti-diagonal, a word per lane).  false: overflow.
 template <class C>
@@ -1896,10 +1912,12 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
     const int lane = threadIdx.x & 31, wid = r >> 5, nw = TW;
 #endif
     const int smax = 2 * S.N - 6;
-    if (r == 0) S.misc[8] = 0;
-    Team<TW>::sync();
+    int *np = C::CLUSTER ? &g.cnt[0] : &S.misc[8];        // records in the list
+    if (gl_leader<C>(S)) *np = 0;
+    gl_sync<C>();
+    const int gw = C::CLUSTER ? S.doffset * nw + wid : wid, gnw = C::CLUSTER ? S.dstride * nw : nw;
     #pragma unroll 1
-    for (int s = 4 + wid; s <= smax; s += nw) {
+    for (int s = 4 + gw; s <= smax; s += gnw) {
         int lo, hi;
         if (!diag_range<C>(S, B, s, lo, hi)) continue;
         const int k1 = hi >> 5;
@@ -1941,7 +1959,7 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
                 double pos;
                 const double sc = run_score_pos<C>(S, P, B, s, a, len, pos);
                 if (!(pos >= P.minbpscore)) continue;
-                const int slot = atomicAdd(&S.misc[8], 1);
+                const int slot = atomicAdd(np, 1);
                 if (slot < g.cap) {
                     gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)a, (uint32_t)len | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
                     g.bps[slot] = sc;
@@ -1949,8 +1967,8 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
             }
         }
     }
-    Team<TW>::sync();
-    return S.misc[8] <= g.cap;
+    gl_sync<C>();
+    return *(volatile int *)np <= g.cap;
 }
 
 // One OptimalStems pass over the global list.  (ui, uj, ul): the stem T applied since the last pass
@@ -1958,12 +1976,14 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
 // relevel: the level of some older stem changed when T was added.  ok = false: overflow.
 template <class C>
 __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const GList &g, int ui, int uj, int ul,
-                        int ei, int ej, bool relevel, bool &ok)
+                        int ei, int ej, bool relevel, bool &ok, int &xc)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     ok = true;
-    int n = S.misc[8];
+    int *np = C::CLUSTER ? &g.cnt[0] : &S.misc[8];        // records in the list
+    int *cc = C::CLUSTER ? &g.cnt[1] : &S.misc[12];       // next chunk of the sweep
+    int n = *(volatile int *)np;
     Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
     const int u1 = ui + ul - 1, v0 = uj - ul + 1;          // the arms of T: [ui, u1] and [v0, uj]
     unsigned n_eval = 0, n_reset = 0, n_cut = 0;
@@ -1981,12 +2001,12 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     constexpr int WL = 32;
     auto grab = [&]() {
         int c0 = 0;
-        if (lane == 0) c0 = atomicAdd(&S.misc[12], WL * GL_BATCH);
+        if (lane == 0) c0 = atomicAdd(cc, WL * GL_BATCH);
         return __shfl_sync(0xffffffffu, c0, 0);
     };
 #endif
-    if (r == 0) S.misc[12] = 0;
-    Team<TW>::sync();
+    if (gl_leader<C>(S)) *cc = 0;
+    gl_sync<C>();
     const long long t_a = g.stat ? gl_clock() : 0;
     // ---- sweep 1: cut, invalidate, arg-max of the cached scores that still hold
     #pragma unroll 1
@@ -2038,7 +2058,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
                         double pos;
                         const double sc = run_score_pos<C>(S, P, B, s, a + p0, pl, pos);
                         if (!(pos >= P.minbpscore)) continue;
-                        const int slot = first ? c : atomicAdd(&S.misc[8], 1);
+                        const int slot = first ? c : atomicAdd(np, 1);
                         if (slot < g.cap) {
                             gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)(a + p0),
                                      (uint32_t)pl | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
@@ -2065,18 +2085,20 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         }
     }
     best = team_argmax<C>(S, best);               // barrier: the appended pieces are visible
+    if (C::CLUSTER) best = cluster_best<C>(S, best, xc++);       // (cluster barrier inside)
     const long long t_b = g.stat ? gl_clock() : 0;
-    n = S.misc[8];
+    n = *(volatile int *)np;
     if (n > g.cap) { ok = false; return best; }
     // ---- sweep 2: FRESH entries, and PRUNED ones whose bound reaches the floor.  The bounds are checked
     // entry by entry; what passes is collected in a per-warp list and evaluated 32 at a time, so that the
     // ScoreStems region walks (hundreds of instructions each) run with full warps.
     unsigned *fl_hi = (unsigned *)&S.misc[9];     // high word of the best score found so far in this sweep (a lower bound of it)
-    if (r == 0) { *fl_hi = best.fin > 0.0 ? (unsigned)__double2hiint(best.fin) : 0u; S.misc[12] = 0; }
+    if (r == 0) *fl_hi = best.fin > 0.0 ? (unsigned)__double2hiint(best.fin) : 0u;
+    if (gl_leader<C>(S)) *cc = 0;
 #ifdef SQRN_HOST_EMU
     next_chunk = 0;
 #endif
-    Team<TW>::sync();
+    gl_sync<C>();
     double floor = best.fin;
     auto refresh_floor = [&]() {
         const unsigned h = *(volatile unsigned *)fl_hi;
@@ -2160,9 +2182,11 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         if (n_eval) atomicAdd(&g.stat[1], (unsigned long long)n_eval);
         if (n_reset) atomicAdd(&g.stat[2], (unsigned long long)n_reset);
         if (n_cut) atomicAdd(&g.stat[5], (unsigned long long)n_cut);
-        if (r == 0) { atomicAdd(&g.stat[0], (unsigned long long)n); atomicAdd(&g.stat[3], 1ull); if (relevel) atomicAdd(&g.stat[4], 1ull); }
+        if (gl_leader<C>(S)) { atomicAdd(&g.stat[0], (unsigned long long)n); atomicAdd(&g.stat[3], 1ull); if (relevel) atomicAdd(&g.stat[4], 1ull); }
     }
-    return team_argmax<C>(S, best);
+    best = team_argmax<C>(S, best);
+    if (C::CLUSTER) best = cluster_best<C>(S, best, xc++);
+    return best;
 }
 
 // two stems are "in conflict" when they share a paired position (seq.py:783-786)
@@ -2434,16 +2458,17 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
 #ifdef SQRN_HOST_EMU
         const long long slot = 0;
 #else
-        const long long slot = blockIdx.x;
+        const long long slot = C::CLUSTER ? blockIdx.x / (unsigned)S.dstride : blockIdx.x;      // one list per cluster
 #endif
         g.ent = (GEnt *)Wk.g_ent + slot * Wk.g_cap; g.bps = Wk.g_bps + slot * Wk.g_cap;
         g.cap = (int)Wk.g_cap; g.stat = Wk.g_stat;
+        g.cnt = Wk.g_cnt ? Wk.g_cnt + 4 * slot : nullptr;
     }
     if (C::PERSIST) {
         // hopeless for the list (too long for this parameter set): straight to the rescanning kernel
         const int N = (int)(B.off[seq + 1] - B.off[seq]);
         if (!(C::GLIST ? gl_wanted(N, P, Wk.g_cap) : persist_wanted(N, P, L))) {
-            if (r == 0) { const int slot = atomicAdd(Wk.ovf_count, 1); Wk.ovf_list[slot] = item; }
+            if (r == 0 && (!C::CLUSTER || S.doffset == 0)) { const int slot = atomicAdd(Wk.ovf_count, 1); Wk.ovf_list[slot] = item; }
             return;
         }
     }
@@ -2460,6 +2485,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         // the pool loop of seq.py:1159-1199 once it can no longer branch
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
         bool ok = true;                             // PERSIST: the run list has not overflowed
+        int xc = 0;                                 // cluster flavour of the global list: exchanges done (buffer parity)
         int ui = 0, uj = 0, ul = 0;                 // the stem applied since the last pass over the list
         if (C::PERSIST && mode == MODE_TAIL && (double)S.nst != P.maxstemnum)
         {
@@ -2499,13 +2525,13 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
                 #pragma unroll 1
                 for (int t = r; t < S.nst; t += T) S.stlev2[t] = S.stlev[t];
                 Team<TW>::sync();
-                b = gl_step<C>(S, P, B, g, ui, uj, ul, ei, ej, relevel, ok);
+                b = gl_step<C>(S, P, B, g, ui, uj, ul, ei, ej, relevel, ok, xc);
                 if (!ok) break;
             } else if (C::PERSIST) {
                 b = persist_step<C>(S, P, B, L, ui, uj, ul, ok);
                 if (!ok) break;
             } else b = team_scan<C>(S, P, B, L, -1.0);
-            b = cluster_best<C>(S, b, (int)calls);
+            if (!C::GLIST) b = cluster_best<C>(S, b, (int)calls);
             calls++;
             if (b.fin <= -1e300) break;
             int i = (int)(b.key & 0xffff);
@@ -2516,7 +2542,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
             lev_ok = false;
         }
         if (C::PERSIST && !ok) {
-            if (r == 0) { const int slot = atomicAdd(Wk.ovf_count, 1); Wk.ovf_list[slot] = item; }
+            if (r == 0 && (!C::CLUSTER || S.doffset == 0)) { const int slot = atomicAdd(Wk.ovf_count, 1); Wk.ovf_list[slot] = item; }
             Team<TW>::sync();
             return;
         }

@@ -91,16 +91,36 @@ def test_cta_teams_global_list_vs_rescan(gpu_ctx, ps):
 
 
 @pytest.mark.parametrize("cs", [1, 2, 4, 8], ids=["one-cta", "cluster2", "cluster4", "cluster8"])
-def test_long_sequences_cluster_sizes(gpu_ctx, cs):
-    """> 2048 nt run to completion: one CTA per sequence and thread-block clusters of 2/4/8 CTAs
-    (replicated state, every CS-th anti-diagonal per CTA, DSMEM arg-max exchange) give the oracle's result"""
+@pytest.mark.parametrize("glist", [True, False], ids=["shared-list", "rescan"])
+def test_long_sequences_cluster_sizes(gpu_ctx, cs, glist):
+    """> 2048 nt run to completion: one CTA per sequence and thread-block clusters of 2/4/8 CTAs (replicated state,
+    DSMEM arg-max exchange) give the oracle's result -- both with the cluster sharing one global candidate list
+    (anti-diagonals and record chunks dealt from counters in global memory) and with every CTA rescanning every
+    CS-th anti-diagonal"""
     seqs = T.rand_seqs(21, 3, 2060, 2400) + [T.rand_seq(random.Random(22), 2100, "GC")]
     try:
         gpu_ctx.set_cluster(cs)
+        gpu_ctx.set_no_glist(not glist)
         _check_fast(gpu_ctx, T.G1000, seqs[:3])
         _check_fast(gpu_ctx, T.FASTEST, seqs)
     finally:
         gpu_ctx.set_cluster(0)
+        gpu_ctx.set_no_glist(False)
+
+
+def test_few_long_sequences_take_clusters_automatically(gpu_ctx):
+    """fewer long sequences than half the SMs: a cluster per sequence sharing one candidate list, same results as
+    one CTA per sequence"""
+    seqs = T.rand_seqs(25, 5, 2100, 3200)
+    sym, off = pack_sequences(seqs)
+    a = gpu_ctx.fast_predict(T.G1000, sym, off)
+    try:
+        gpu_ctx.set_cluster(1)
+        b = gpu_ctx.fast_predict(T.G1000, sym, off)
+    finally:
+        gpu_ctx.set_cluster(0)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
 
 
 def test_fast_kernel_equals_general_kernel(gpu_ctx):
