@@ -1145,7 +1145,8 @@ __device__ __forceinline__ void region_stems(const State &S, int ss, int se, Reg
 __device__ SQRN_NOINLINE double slow_pow(double a, double b) { return pow(a, b); }
 
 template <class C>
-__device__ __forceinline__ double score_candidate(const State &S, const DevParams &P, int s, int a, int len, double bps)
+__device__ __forceinline__ double score_candidate(const State &S, const DevParams &P, int s, int a, int len, double bps,
+                                                  int *order_out = nullptr)
 {
     const int N = S.N;
     const int oi = a, oj = s - a;
@@ -1202,6 +1203,7 @@ __device__ __forceinline__ double score_candidate(const State &S, const DevParam
         }
     }
     int order = __popcll(R.levmask);
+    if (order_out) *order_out = order;          // 0: no wing of a selected stem counts, the levels do not enter the score
     double of = (order < P.of_n) ? __ldg(&P.of_lut[order]) : slow_pow(1.0 / (1.0 + order), P.orderpenalty);
     // seq.py:732
     double fin = __dmul_rn(bps, sdf);
@@ -1827,6 +1829,7 @@ __device__ __forceinline__ long long gl_clock() { return clock64(); }
 #endif
 constexpr uint32_t GK_DEAD = 0xffffffffu;
 constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u, GS_PRUNED1 = 4u;
+constexpr uint32_t GS_MASK = 7u, GS_LEVELS = 8u;      // GS_LEVELS (with EVAL): the score involves pseudoknot levels
 
 // one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16, v = the cached score / bound
 struct alignas(16) GEnt { uint32_t key, meta; double v; };
@@ -2023,7 +2026,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
             if (key == GK_DEAD) continue;
             const uint32_t meta = buf[u].meta;
             const int len = (int)(meta & 0xffffu), a = (int)(key & 0xffffu), s = (int)(key >> 16), t = s - a;
-            uint32_t st = meta >> 16;
+            uint32_t st = (meta >> 16) & GS_MASK;
             // T can cut the run or change its cached score only if one of its arms meets [a - 5, t + 5]
             // (the run's rows and columns all lie in [a, t]); most records fail this test and are done
             if (ul > 0 && !((u1 < a - 5 || ui > t + 5) && (uj < a - 5 || v0 > t + 5))) {
@@ -2077,7 +2080,8 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
                     if (!shielded) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
                 }
             }
-            if (relevel && st == GS_EVAL) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
+            // a level change only matters to scores that counted the wing of a selected stem
+            if (relevel && st == GS_EVAL && (meta >> 16 & GS_LEVELS)) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
             if (st == GS_EVAL) {
                 const double fin = buf[u].v;
                 if (fin >= P.minfinscore && better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
@@ -2109,8 +2113,9 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         const GEnt e = gl_load(&g.ent[c]);
         const int len = (int)(e.meta & 0xffffu);
         const double bps = g.bps[c];
-        const double fin = score_candidate<C>(S, P, (int)(e.key >> 16), (int)(e.key & 0xffffu), len, bps);
-        gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_EVAL << 16), fin);
+        int order = 0;
+        const double fin = score_candidate<C>(S, P, (int)(e.key >> 16), (int)(e.key & 0xffffu), len, bps, &order);
+        gl_store(&g.ent[c], e.key, (uint32_t)len | ((GS_EVAL | (order ? GS_LEVELS : 0u)) << 16), fin);
         n_eval++;
 #ifdef SQRN_EMU_DEBUG
         printf("  eval nst=%d (%d,%d,%d) bps=%g fin=%.17g\n", S.nst, (int)(e.key & 0xffff), (int)(e.key >> 16) - (int)(e.key & 0xffff), len, bps, fin);
@@ -2123,7 +2128,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     // true: entry c has to be evaluated (its bounds reach the floor)
     auto screen = [&](int c, const GEnt &e, double bps) -> bool {
         if (e.key == GK_DEAD) return false;
-        const uint32_t st = e.meta >> 16;
+        const uint32_t st = (e.meta >> 16) & GS_MASK;
         if (st == GS_EVAL || st == GS_BELOW) return false;
         if ((st == GS_PRUNED || st == GS_PRUNED1) && e.v < floor) return false;
         const int len = (int)(e.meta & 0xffffu);
@@ -2152,7 +2157,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
             // the bp scores of the records that will be screened, all loads in flight together
             #pragma unroll
             for (int u = 0; u < GL_BATCH; u++) {
-                const uint32_t st = buf[u].meta >> 16;
+                const uint32_t st = (buf[u].meta >> 16) & GS_MASK;
                 const bool want = buf[u].key != GK_DEAD && (st == GS_FRESH || ((st == GS_PRUNED || st == GS_PRUNED1) && !(buf[u].v < floor)));
                 bpsbuf[u] = want ? g.bps[c0 + u * 32 + lane] : 0.0;
             }
