@@ -10,6 +10,6 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --seqs 100000 --no-cpu > gpurun_out/ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_fast$ -s 3 -c 1 -f -o gpurun_out/prof \
-    python bench.py --steps 1 --warmup 3 --seqs 200000 --no-cpu > gpurun_out/ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out
