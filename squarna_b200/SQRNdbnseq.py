@@ -345,9 +345,209 @@ def _encode_symbols(shortseq):
     return shortseq.encode("latin-1", "replace")
 
 
+def _make_batch(preps, idx, comp, stemmatrix, interchainonly, **opts):
+    """PackedBatch of the prepared entries idx (all with the same reactivity-sum mode `comp`)"""
+    # distinct processed reactivities of the batch -> codes + value table (host pow() table in the library)
+    codes = values = None
+    arrs = [None if preps[k]._sr is None else np.asarray(preps[k]._sr, dtype=np.float64) for k in idx]
+    if any(a is not None and bool((a != 0.5).any()) for a in arrs):
+        lens_ = [len(preps[k].shortseq) for k in idx]
+        flat = np.concatenate([np.full(n_, 0.5) if a is None else a for a, n_ in zip(arrs, lens_)]) if idx else np.zeros(0)
+        # bit patterns, not values: -0.0 / NaN payloads must stay distinct table entries
+        values_bits, inverse = np.unique(flat.view(np.uint64), return_inverse=True)
+        if len(values_bits) > 65535:
+            raise NotImplementedError("more than 65535 distinct reactivity values in one batch")
+        values = values_bits.view(np.float64)
+        inverse = inverse.astype(np.uint16)
+        codes, o = [], 0
+        for n_ in lens_:
+            codes.append(inverse[o:o + n_])
+            o += n_
+    any_restr = any(p.rbps or p.rclass.any() for p in (preps[k] for k in idx))
+    smat = cols = None
+    if stemmatrix is not None:
+        smat = np.asarray(stemmatrix, dtype=np.float64)
+        cols = [np.asarray(preps[k].keep, dtype=np.int32) for k in idx]
+    return PackedBatch([_encode_symbols(preps[k].shortseq) for k in idx],
+                       react_codes=codes, react_values=values, react_comp=comp,
+                       restr_class=[preps[k].rclass for k in idx] if any_restr else None,
+                       rbps=[np.array(preps[k].rbps, dtype=np.int32).reshape(-1, 2) for k in idx] if any_restr else None,
+                       smat=smat, cols=cols, interchainonly=interchainonly, max_structs=0, **opts)
+
+
+# ---------------------------------------------------------------- non-greedy algorithms (host)
+def ConsensusStemSet(stemsets):
+    """base pairs present in every stem list (seq.py:845-858)"""
+    common = None
+    for stemset in stemsets:
+        bps = {bp for stem in stemset for bp in stem[0]}
+        common = bps if common is None else common & bps
+    return common or set()
+
+
+def RankStructs(stemsets, rankbydiff=False, rankby=(0, 2, 1), priority=set()):
+    """order of the predicted structures (seq.py:902-955): stable descending sort by the rankby score tuple,
+    structures of priority parameter sets first, then -- with rankbydiff -- repeatedly the structure that adds
+    most base pairs not seen so far.  stemsets: [stems, scores, paramset indices]"""
+    def score_key(x):
+        return [x[1][rb] for rb in rankby]
+
+    ranked = sorted(stemsets, key=score_key, reverse=True)
+    ranked = [x for x in ranked if priority & set(x[2])] + [x for x in ranked if not (priority & set(x[2]))]
+    if not rankbydiff or len(ranked) < 3:
+        return ranked
+    bpsets = {id(x): {bp for stem in x[0] for bp in stem[0]} for x in ranked}
+    everything = set().union(*bpsets.values())
+    seen = set(bpsets[id(ranked[0])])
+    cur = 1
+    while seen != everything and cur < len(ranked) - 1:
+        tail = sorted(ranked[cur:], key=lambda x: (len(bpsets[id(x)] - seen), score_key(x)), reverse=True)
+        ranked = ranked[:cur] + tail
+        seen |= bpsets[id(ranked[cur])]
+        cur += 1
+    return ranked[:cur] + sorted(ranked[cur:], key=score_key, reverse=True)
+
+
+def _cell_scorer(p, paramset, smat):
+    """scoremat[v, w] of BPMatrix for one prepared entry (seq.py:258-339, times the alignment weight 1084-1085)"""
+    weights = {}
+    for bp, w in paramset["bpweights"].items():
+        weights[bp] = w
+        weights[bp[1] + bp[0]] = w
+    seq, reacts = p.shortseq, p.shortreacts
+    default = p._sr is None or set(reacts) == {0.5}
+    keep = p.keep
+
+    def score(v, w):
+        base = weights.get(seq[v] + seq[w], 0)
+        rf = 1 if default else ((1 - (reacts[v] + reacts[w]) / 2) * 2) ** 0.5
+        if base <= 0:
+            rf = 1 / max(rf, 0.01)
+        val = base * 1.0 * rf                        # bps * boolmat * reactfactor: the cell is a live pair here
+        if smat is not None:
+            val = val * smat[keep[v], keep[w]]
+        return val
+    return score
+
+
+def RunAlgo(seq, stems, cell_score, minlen, minscore, algo="E", levellimit=3):
+    """one non-greedy prediction (seq.py:548-595).  stems: AnnotateStems output [[pairs, len, score], ...];
+    cell_score(v, w) = bpscorematrix[v, w]."""
+    from . import SQRNalgos
+    N = len(seq)
+    if algo == "E":
+        pairs = SQRNalgos.Edmonds(stems)
+    elif algo == "N":
+        pairs = SQRNalgos.Nussinov(seq, stems, N, SEPS)
+    elif algo == "H":
+        pairs = SQRNalgos.Hungarian(seq, stems, N, SEPS)
+    else:
+        pairs = []
+
+    def passing(pairlist):                           # partial stems below the thresholds go
+        out = []
+        for stem in PairsToStems(sorted((min(v, w), max(v, w)) for v, w in pairlist)):
+            score = sum(cell_score(v, w) for v, w in stem[0])
+            if score >= minscore and stem[1] >= minlen:
+                out.append((stem, score))
+        return out
+
+    kept = [bp for stem, _ in passing(pairs) for bp in stem[0]]
+    kept = DBNToPairs(PairsToDBN(kept, N, levellimit=levellimit))      # pseudoknots beyond the level limit go
+    levels = PairsToDBN(kept, N, returnlevels=True)
+    stemset = []
+    for stem, score in passing(kept):
+        if levels[stem[0][0]] > 1 and stem[1] < 4:                      # short pseudoknotted stems go
+            continue
+        stemset.append(stem + [score, score, ''])
+    return stemset
+
+
+def _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydiff, rankby, interchainonly,
+                        stemmatrix, poollim, priority, algos, device, levellimit):
+    """SQRNdbnseq (seq.py:1039-1286) for parameter sets that name Nussinov / Hungarian / Edmonds: per parameter
+    set the greedy structures come from sqrn_predict_batch and the stems for the other builders from
+    sqrn_yield_stems_batch; de-duplication, ScoreStruct of the host-built structures, ranking and consensus
+    follow the reference on the host."""
+    preps = [_prepare(*e) for e in entries]
+    ctx = get_context(device)
+    n = len(entries)
+    per_ps = [[None] * len(paramsets) for _ in range(n)]       # [entry][paramset] -> list of (stems, scores) in order
+    for psi, ps in enumerate(paramsets):
+        use = set(algos) if algos else set(ps["algorithms"])
+        for k in range(n):
+            per_ps[k][psi] = []
+        for comp in (False, True):
+            idx = [k for k in range(n) if preps[k].compensated == comp]
+            if not idx:
+                continue
+            others = [a for a in use if a != "G"]             # set order, as in the reference's `for algo in algos`
+            if others:
+                batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly)
+                for k, (st, sc) in zip(idx, ctx.yield_stems(ps, batch)):
+                    p = preps[k]
+                    stems = [[[(i + q, j - q) for q in range(ln)], ln, float(s_)] for (i, j, ln), s_ in zip(st.tolist(), sc.tolist())]
+                    cell = _cell_scorer(p, ps, None if stemmatrix is None else np.asarray(stemmatrix, dtype=np.float64))
+                    ll = levellimit if levellimit is not None else 3 - int(len(p.shortseq) > 500)
+                    for algo in others:
+                        stemset = RunAlgo(p.shortseq, stems, cell, ps["minlen"], ps["minbpscore"], algo, ll)
+                        per_ps[k][psi].append((stemset, ScoreStruct(p.shortseq, stemset, p.shortreacts)))
+            if "G" in use:
+                batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly, hardrest=False, rankbydiff=False,
+                                    poollim=poollim, conslim=1, rankby=rankby, priority_mask=0)
+                for k, (_cons, structs, _nt) in zip(idx, ctx.predict_batch([ps], batch)):
+                    for codes, sc, isint, _mask, stems in structs:
+                        stemset = [[[(i + q, j - q) for q in range(ln)], ln] for i, j, ln in np.asarray(stems).tolist()]
+                        total, struct, react = sc
+                        per_ps[k][psi].append((stemset, (total, 0 if isint else struct, react)))
+    final = []
+    for k, p in enumerate(preps):
+        fin, seen = [], {}
+        for psi in range(len(paramsets)):
+            for stemset, scores in per_ps[k][psi]:
+                key = tuple(sorted(bp for stem in stemset for bp in stem[0]))
+                if key not in seen:
+                    fin.append([stemset, scores, psi])
+                    seen[key] = {psi}
+                else:
+                    seen[key].add(psi)
+        for item in fin:
+            item[2] = sorted(seen[tuple(sorted(bp for stem in item[0] for bp in stem[0]))])
+        ranked = RankStructs(fin, rankbydiff, rankby, priority=set(priority))
+        sseq = p.shortseq
+        bpw = paramsets[-1]["bpweights"]                               # the loop variable the reference leaves behind
+        forced = {(v, w) for v, w in p.rbps if sseq[v] + sseq[w] in bpw or sseq[w] + sseq[v] in bpw} if hardrest else set()
+        n_short = len(sseq)
+
+        def expand(pairs, p=p, n_short=n_short):
+            dbn = ReAlign(PairsToDBN(pairs, n_short), p.seq)
+            return ''.join(p.seq[q] if p.seq[q] in SEPS else dbn[q] for q in range(len(p.seq)))
+
+        dbns = [expand({bp for stem in x[0] for bp in stem[0]} | forced) for x in ranked]
+        consbps = ConsensusStemSet([x[0] for x in ranked[:conslim]]) | forced
+        cons = expand(consbps)
+        preds = [(dbn, x[1], x[2]) for dbn, x in zip(dbns, ranked)]
+        if p.dbn:
+            known = set(DBNToPairs(p.shortdbn))
+            consresult = list(_metrics(set(consbps), known))
+            best, result = -1, []
+            for rank, x in enumerate(ranked):
+                bps = {bp for stem in x[0] for bp in stem[0]} | forced
+                tp, fp, fn, fsc, prc, rcl = _metrics(bps, known)
+                if fsc > best:
+                    best = fsc
+                    result = [tp, fp, fn, fsc, prc, rcl, rank + 1]
+                if rank + 1 >= toplim:
+                    break
+            final.append((cons, preds, consresult, result))
+        else:
+            final.append((cons, preds, [np.nan] * 6, [np.nan] * 7))
+    return final
+
+
 def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankbydiff=False,
                  rankby=(0, 2, 1), interchainonly=False, stemmatrix=None, poollim=1000,
-                 priority=frozenset(), algos=frozenset(), device=0):
+                 priority=frozenset(), algos=frozenset(), device=0, levellimit=None):
     """Batched SQRNdbnseq: entries = [(seq, reacts, restraints, dbn)], one GPU
     call for all of them.  Returns the reference's 4-tuple per entry."""
     assert set(rankby) == {0, 1, 2} and len(rankby) == 3, "Invalid ranking indices"
@@ -359,8 +559,9 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
             raise NotImplementedError("parameter set #{} has bpp != 0: ViennaRNA base-pair probabilities are "
                                       "outside the GPU hot path (use the *nobpp configs)".format(psi))
         if use - {"G"}:
-            raise NotImplementedError("algorithms {} are outside the GPU hot path (greedy 'G' only)"
-                                      .format(sorted(use - {"G"})))
+            # Nussinov / Hungarian / Edmonds sets: stems from the GPU, the builders on the host
+            return _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydiff, rankby,
+                                       interchainonly, stemmatrix, poollim, priority, algos, device, levellimit)
         if "G" in use:
             gsets.append(psi)
     preps = [_prepare(*e) for e in entries]
@@ -374,38 +575,9 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
         idx = [k for k in todo if preps[k].compensated == comp]
         if not idx:
             continue
-        # distinct processed reactivities of the batch -> codes + value table (host pow() table in the library)
-        codes = values = None
-        arrs = [None if preps[k]._sr is None else np.asarray(preps[k]._sr, dtype=np.float64) for k in idx]
-        if any(a is not None and bool((a != 0.5).any()) for a in arrs):
-            lens_ = [len(preps[k].shortseq) for k in idx]
-            flat = np.concatenate([np.full(n_, 0.5) if a is None else a for a, n_ in zip(arrs, lens_)]) if idx else np.zeros(0)
-            # bit patterns, not values: -0.0 / NaN payloads must stay distinct table entries
-            values_bits, inverse = np.unique(flat.view(np.uint64), return_inverse=True)
-            if len(values_bits) > 65535:
-                raise NotImplementedError("more than 65535 distinct reactivity values in one batch")
-            values = values_bits.view(np.float64)
-            inverse = inverse.astype(np.uint16)
-            codes, o = [], 0
-            for n_ in lens_:
-                codes.append(inverse[o:o + n_])
-                o += n_
-        any_restr = any(p.rbps or p.rclass.any() for p in (preps[k] for k in idx))
-        smat = cols = None
-        if stemmatrix is not None:
-            smat = np.asarray(stemmatrix, dtype=np.float64)
-            cols = [np.asarray(preps[k].keep, dtype=np.int32) for k in idx]
-        pmask = 0
-        for p in priority:
-            if p in gsets:
-                pmask |= 1 << gsets.index(p)
-        batch = PackedBatch([_encode_symbols(preps[k].shortseq) for k in idx],
-                            react_codes=codes, react_values=values, react_comp=comp,
-                            restr_class=[preps[k].rclass for k in idx] if any_restr else None,
-                            rbps=[np.array(preps[k].rbps, dtype=np.int32).reshape(-1, 2) for k in idx] if any_restr else None,
-                            smat=smat, cols=cols, interchainonly=interchainonly, hardrest=hardrest,
-                            rankbydiff=rankbydiff, poollim=poollim, conslim=conslim, max_structs=0,
-                            rankby=rankby, priority_mask=pmask)
+        batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly, hardrest=hardrest, rankbydiff=rankbydiff,
+                            poollim=poollim, conslim=conslim, rankby=rankby,
+                            priority_mask=sum(1 << gsets.index(p) for p in priority if p in gsets))
         out = get_context(device).predict_batch([paramsets[g] for g in gsets], batch)
         for k, (cons, structs, _ntot) in zip(idx, out):
             results[k] = (cons, structs)
@@ -472,13 +644,14 @@ def SQRNdbnseq(seq, reacts=None, restraints=None, dbn=None,
      consensus_metrics[6], topN_metrics[7]).
 
     threads / mp only choose a multiprocessing layout in the reference and never
-    change results; here the work is one batched GPU call.  `entropy` and the
-    non-greedy algorithms are outside the GPU hot path (NotImplementedError)."""
+    change results; here the work is one batched GPU call.  Parameter sets that name Nussinov / Hungarian /
+    Edmonds get their stems from the GPU and run those builders on the host (SQRNalgos.py); `entropy` is
+    outside the path (NotImplementedError)."""
     if entropy:
         raise NotImplementedError("entropy mode is outside the GPU hot path")
     return predict_many([(seq, reacts, restraints, dbn)], paramsets, conslim, toplim, hardrest,
                         rankbydiff, rankby, interchainonly, stemmatrix, poollim,
-                        frozenset(priority), frozenset(algos))[0]
+                        frozenset(priority), frozenset(algos), levellimit=levellimit)[0]
 
 
 def _print_entry(name, sequence, reactivities, restraints, reference, reactformat, sink, rfam=None):
@@ -556,7 +729,7 @@ def RunSQRNdbnseq(name, sequence, reactivities, restraints,
 
 def RunSQRNdbnseqBatch(entries, paramsetnames, paramsets, rankbydiff, rankby, hardrest, interchainonly,
                        toplim, outplim, conslim, reactformat, evalonly, poollim=1000, sink=sys.stdout,
-                       stemmatrix=None, algos={'G', }, priority=None, rfam=None):
+                       stemmatrix=None, algos={'G', }, priority=None, rfam=None, levellimit=None):
     """RunSQRNdbnseq for many entries [(name, seq, reacts, restraints, reference)]
     with ONE batched GPU call; text is written in input order (what the
     reference's ordered imap gives, SQUARNA.py:929-935)."""
@@ -565,7 +738,7 @@ def RunSQRNdbnseqBatch(entries, paramsetnames, paramsets, rankbydiff, rankby, ha
     if not evalonly:
         preds = predict_many([(e[1], e[2], e[3], e[4]) for e in entries], paramsets, conslim, toplim,
                              hardrest, rankbydiff, rankby, interchainonly, stemmatrix, poollim,
-                             frozenset(priority), frozenset(algos))
+                             frozenset(priority), frozenset(algos), levellimit=levellimit)
     out = []
     for (name, seq, reacts, rests, ref), pred in zip(entries, preds):
         _print_entry(name, seq, reacts, rests, ref, reactformat, sink, rfam)

@@ -493,7 +493,7 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
         names_, sets_ = tables[pending[0][0]]
         RunSQRNdbnseqBatch([e[1] for e in pending], names_, sets_, rankbydiff, rankby, hardrest, interchainonly,
                            toplim, outplim, conslim, reactformat, evalonly, poollim, sink=write_to,
-                           algos=algos, priority=priority, rfam=None)
+                           algos=algos, priority=priority, rfam=None, levellimit=levellimit)
         del pending[:]
 
     for entry in inputs:

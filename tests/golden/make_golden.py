@@ -4,6 +4,7 @@
 
     python tests/golden/make_golden.py          # JSON vectors
     python tests/golden/make_golden.py cli      # CLI text of the reference on tests/golden/inputs/
+    python tests/golden/make_golden.py algos    # SQRNdbnseq with the Nussinov / Hungarian / Edmonds parameter sets
 
 The reference cannot travel to the GPU box, so its outputs are committed here as
 JSON fixtures; tests/test_oracle_golden.py pins the CPU oracle (and the host-side
@@ -160,6 +161,39 @@ def main():
                        "seq": seq, "enc": {str(f): R.EncodedReactivities(seq, pr, f) for f in (3, 10, 26)}})
     dump("reacts.json", rx)
 
+
+def algos_golden():
+    """SQRNdbnseq with parameter sets that name Nussinov / Hungarian / Edmonds (bpp 0): nobpp.conf (defG1, defG2,
+    defN, defE, defH) and the single-algorithm configs.  Every set names ONE algorithm, so the reference's
+    iteration over the `algos` set is deterministic."""
+    rng = random.Random(20261018)
+    cases = []
+    plan = [("nobpp", 100, 8, 90, 40), ("nobpp", 1, 20, 140, 15), ("nussinovnobpp", 100, 8, 120, 25),
+            ("edmondsnobpp", 100, 8, 120, 25), ("hungariannobpp", 100, 8, 120, 25)]
+    for conf, pl, lo, hi, count in plan:
+        names, psets = RC.ParseConfig(os.path.join(REF, conf + ".conf"))
+        assert all(p["bpp"] == 0 and len(p["algorithms"]) == 1 for p in psets), conf
+        for _ in range(count):
+            seq, reacts, rest, kw = rand_case(rng, lo, hi)
+            if rng.random() < 0.3:
+                kw["priority"] = [rng.randrange(len(psets))]
+            if rng.random() < 0.3:
+                kw["conslim"] = rng.choice([1, 2, 3])
+            if rng.random() < 0.2:
+                kw["levellimit"] = rng.choice([1, 2])
+            try:
+                out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=pl,
+                                   **{k: (set(v) if k == "priority" else v) for k, v in kw.items()})
+            except ZeroDivisionError:
+                continue
+            cases.append({"conf": conf, "poollim": pl, "seq": seq, "reacts": reacts, "restraints": rest, "kw": kw,
+                          "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+    dump("algos.json", cases)
+
+
+if __name__ == "__main__" and "algos" in sys.argv[1:]:
+    algos_golden()
+    sys.exit(0)
 
 if __name__ == "__main__" and "cli" not in sys.argv[1:]:
     main()

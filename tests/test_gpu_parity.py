@@ -255,3 +255,30 @@ def test_predict_batch_full(gpu_ctx, name, paramsets, poollim, lo, hi, count):
                              poollim=poollim, **kw)
         for k, g in zip(idx, got):
             assert T.same_prediction((g[0], g[1]), want[k]), (cases[k], g[:2], want[k])
+
+
+def test_non_greedy_algorithms_match_the_reference(gpu_ctx):
+    """parameter sets that name Nussinov / Hungarian / Edmonds (nobpp.conf and the single-algorithm configs):
+    stems from sqrn_yield_stems_batch, the builders on the host (squarna_b200/SQRNalgos.py), de-duplication /
+    ranking / consensus as in the reference -- against tests/golden/algos.json, made by the real reference"""
+    import json
+    import os
+    from squarna_b200 import SQUARNA as CLI
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+    with open(os.path.join(here, "golden", "algos.json")) as f:
+        cases = json.load(f)
+    confs = {}
+    bad = []
+    for c in cases:
+        if c["conf"] not in confs:
+            confs[c["conf"]] = CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1]
+        kw = dict(c["kw"])
+        if "priority" in kw:
+            kw["priority"] = set(kw["priority"])
+        kw["rankby"] = tuple(kw["rankby"])
+        got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, confs[c["conf"]], poollim=c["poollim"], **kw)
+        want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+        if not T.same_prediction((got[0], got[1]), want):
+            bad.append((c["conf"], c["seq"], c["kw"], got[:2], want))
+    assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
