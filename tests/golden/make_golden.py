@@ -215,6 +215,10 @@ CLI_RUNS = {
     "ali_step3_1": ["i=inputs/ali_input.afa", "a", "s3=1", "t=4"],
     "ali_demo": ["i=inputs/demo.afa", "a", "t=2"],
     "ali_as_single_fastest": ["i=inputs/ali_input.afa", "c=fastest", "pl=1", "byseq", "t=4", "if=q"],
+    "seq_nobpp": ["i=inputs/seq_input.fas", "c=nobpp", "t=4"],                     # G + Nussinov + Edmonds + Hungarian sets
+    "shape_nobpp_opts": ["i=inputs/shape_input.fas", "c=nobpp", "t=4", "pl=50", "tl=4", "ol=6", "cl=2", "rb=dr", "ll=1"],
+    "seq_edmondsnobpp": ["i=inputs/seq_input.fas", "c=edmondsnobpp", "t=2"],
+    "ali_nobpp": ["i=inputs/ali_input.afa", "a", "c=nobpp", "t=4"],                # alignment mode, step 2 with all five sets
 }
 
 
