@@ -645,13 +645,36 @@ def SQRNdbnseq(seq, reacts=None, restraints=None, dbn=None,
 
     threads / mp only choose a multiprocessing layout in the reference and never
     change results; here the work is one batched GPU call.  Parameter sets that name Nussinov / Hungarian /
-    Edmonds get their stems from the GPU and run those builders on the host (SQRNalgos.py); `entropy` is
-    outside the path (NotImplementedError)."""
+    Edmonds get their stems from the GPU and run those builders on the host (SQRNalgos.py); `entropy=True`
+    returns the stem-matrix entropy string of the first parameter set."""
     if entropy:
-        raise NotImplementedError("entropy mode is outside the GPU hot path")
+        return Entropy(seq, reacts, restraints, paramsets[0], interchainonly, stemmatrix)
     return predict_many([(seq, reacts, restraints, dbn)], paramsets, conslim, toplim, hardrest,
                         rankbydiff, rankby, interchainonly, stemmatrix, poollim,
                         frozenset(priority), frozenset(algos), levellimit=levellimit)[0]
+
+
+def Entropy(seq, reacts, restraints, paramset, interchainonly=False, stemmatrix=None, device=0):
+    """mean row entropy of the stem-score matrix of the first parameter set, as the string the reference returns
+    (seq.py:520-545, reached through SQRNdbnseq(entropy=True), seq.py:1087-1089): every stem AnnotateStems finds
+    writes its score into the cells of its pairs (both triangles); a row's entropy is that of its non-zero cells
+    normalised to 1.  The stems come from sqrn_yield_stems_batch."""
+    p = _prepare(seq, reacts, restraints, None)
+    batch = _make_batch([p], [0], p.compensated, stemmatrix, interchainonly)
+    (st, sc), = get_context(device).yield_stems(paramset, batch)
+    n = len(p.shortseq)
+    mat = np.zeros((n, n))
+    for (i, j, ln), score in zip(st.tolist(), sc.tolist()):
+        for q in range(ln):
+            mat[i + q, j - q] = score
+            mat[j - q, i + q] = score
+    ent = 0
+    for row in mat:
+        tot = row.sum()
+        if tot:
+            probs = [x for x in row / tot if x]
+            ent += sum(-(probs * np.log2(probs)))
+    return str(round(ent / n, 3))
 
 
 def _print_entry(name, sequence, reactivities, restraints, reference, reactformat, sink, rfam=None):
@@ -712,8 +735,7 @@ def RunSQRNdbnseq(name, sequence, reactivities, restraints,
                   priority=None, rfam=None, M=1.8, B=-0.6):
     """Print the reference's text block for one entry and return the prediction
     4-tuple (seq.py:1289-1408)."""
-    if entropy:
-        raise NotImplementedError("entropy mode is outside the GPU hot path")
+    # `entropy` is accepted and, as in the reference (seq.py:1349-1353 does not hand it on), has no effect here
     priority = _resolve_priority(priority, paramsetnames, rfam)
     _print_entry(name, sequence, reactivities, restraints, reference, reactformat, sink, rfam)
     if evalonly:

@@ -9,8 +9,9 @@ Behavioural differences from the reference, all outside the hot path:
   * `threads` / `byseq` only chose a multiprocessing layout in the reference and
     never changed the output; here every mode batches entries into GPU calls and
     prints in input order.
-  * parameter sets with `bpp != 0` (ViennaRNA), the N/H/E algorithms, entropy
-    mode and the rfam/g4/rbp restraint discovery raise NotImplementedError.
+  * parameter sets with `bpp != 0` (ViennaRNA, not installed: parity unpinned) and the
+    rfam/g4/rbp restraint discovery (external binaries / network) raise NotImplementedError.
+    Nussinov / Hungarian / Edmonds parameter sets run on the host from GPU-enumerated stems.
 """
 import os
 import sys
@@ -414,8 +415,8 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
     elif "s" in rankby:
         rankby = (1, 2, 0)
 
-    if entropy:
-        raise NotImplementedError("entropy mode is outside the GPU hot path")
+    # `ent` / entropy: parsed and handed to the runners, which (like the reference's RunSQRNdbnseq,
+    # SQRNdbnseq.py:1349-1353) do not use it; SQRNdbnseq(entropy=True) is the API that returns the entropy
     if rfam or g4 or rbp:
         raise NotImplementedError("rfam / g4 / rbp restraint discovery is outside the GPU hot path")
 

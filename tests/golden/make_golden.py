@@ -189,6 +189,16 @@ def algos_golden():
             cases.append({"conf": conf, "poollim": pl, "seq": seq, "reacts": reacts, "restraints": rest, "kw": kw,
                           "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
     dump("algos.json", cases)
+    # SQRNdbnseq(entropy=True): the stem-matrix entropy string of the first parameter set
+    ent = []
+    for conf in ("greedynobpp", "fastest", "ali"):
+        names, psets = RC.ParseConfig(os.path.join(REF, conf + ".conf"))
+        for _ in range(12):
+            seq, reacts, rest, kw = rand_case(rng, 8, 120)
+            out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, entropy=True, interchainonly=kw["interchainonly"])
+            ent.append({"conf": conf, "seq": seq, "reacts": reacts, "restraints": rest,
+                        "interchainonly": kw["interchainonly"], "entropy": out})
+    dump("entropy.json", ent)
 
 
 if __name__ == "__main__" and "algos" in sys.argv[1:]:

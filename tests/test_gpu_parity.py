@@ -282,3 +282,19 @@ def test_non_greedy_algorithms_match_the_reference(gpu_ctx):
         if not T.same_prediction((got[0], got[1]), want):
             bad.append((c["conf"], c["seq"], c["kw"], got[:2], want))
     assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+
+
+def test_entropy_mode_matches_the_reference(gpu_ctx):
+    """SQRNdbnseq(entropy=True) (seq.py:520-545): stems from the GPU, the row entropies on the host"""
+    import json
+    import os
+    from squarna_b200 import SQUARNA as CLI
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+    with open(os.path.join(here, "golden", "entropy.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        psets = CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1]
+        got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, psets, entropy=True,
+                           interchainonly=c["interchainonly"])
+        assert got == c["entropy"], (c["seq"], got, c["entropy"])

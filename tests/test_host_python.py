@@ -118,8 +118,8 @@ def test_predict_argument_errors():
         CLI.Predict(inputseq="ACGU", configfile="fastest", rankby="q")
     with pytest.raises(ValueError, match="Inappropriate algorithm"):
         CLI.Predict(inputseq="ACGU", configfile="fastest", algorithms="x")
-    with pytest.raises(NotImplementedError):
-        CLI.Predict(inputseq="ACGU", configfile="fastest", entropy=True)
+    with pytest.raises(NotImplementedError):          # rfam / g4 / rbp restraint discovery: external binaries + network
+        CLI.Predict(inputseq="ACGU", configfile="fastest", rfam=True)
 
 
 def test_evalonly_cli_text_matches_reference():
