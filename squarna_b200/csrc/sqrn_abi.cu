@@ -402,7 +402,7 @@ static void maybe_glist(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int nmax, int 
     if (pl.tw == 1 || !tail_mode || ctx->no_glist || !P.hp.ub_ok || !(P.hp.loopbonus >= 0.0) || nmax > 32767) return;
     const int m = P.hp.m;
     const int scap = max_init < 0 ? 0 : max_init + nmax / (2 * m) + 2;
-    pl.Lg = make_layout(nmax, rbmax, 64 * pl.tw, P.hp.npc, pl.tw, 64, extras, 0, scap, -1);    // Ccap: 64 list slots per warp
+    pl.Lg = make_layout(nmax, rbmax, 128 * pl.tw, P.hp.npc, pl.tw, 64, extras, 0, scap, -1);   // Ccap: 2 x 64 list slots per warp
     pl.smem_g = pl.Lg.total;
     if (pl.smem_g + sizeof(DevParams) + 1024 > ctx->smem_optin) return;
     if ((pl.tw == 8 ? plan_glist_t<8>(ctx, pl) : plan_glist_t<32>(ctx, pl)) != SQRN_OK) { cudaGetLastError(); return; }

@@ -1991,7 +1991,6 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     const int u1 = ui + ul - 1, v0 = uj - ul + 1;          // the arms of T: [ui, u1] and [v0, uj]
     unsigned n_eval = 0, n_reset = 0, n_cut = 0;
     GEnt buf[GL_BATCH];
-    double bpsbuf[GL_BATCH];
     // Warps take chunks of 32 * GL_BATCH consecutive records from a shared counter (cuts and evaluations
     // are unevenly spread over the list; fixed strides would leave most warps waiting at the barriers).
 #ifdef SQRN_HOST_EMU
@@ -2126,12 +2125,14 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         }
     };
     // true: entry c has to be evaluated (its bounds reach the floor)
-    auto screen = [&](int c, const GEnt &e, double bps) -> bool {
+    auto screen = [&](int c) -> bool {
+        const GEnt e = gl_load(&g.ent[c]);
         if (e.key == GK_DEAD) return false;
         const uint32_t st = (e.meta >> 16) & GS_MASK;
         if (st == GS_EVAL || st == GS_BELOW) return false;
         if ((st == GS_PRUNED || st == GS_PRUNED1) && e.v < floor) return false;
         const int len = (int)(e.meta & 0xffffu);
+        const double bps = g.bps[c];
         double ub = score_bound(P, bps);
         if (ub < floor || ub < P.minfinscore) { if (st != GS_PRUNED1) gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED1 << 16), ub); return false; }
         ub = tight_bound(S, P, e.key, len, bps);
@@ -2140,12 +2141,35 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     };
 #ifdef SQRN_HOST_EMU
     #pragma unroll 1
-    for (int c = 0; c < n; c++) { refresh_floor(); buf[0] = gl_load(&g.ent[c]); if (screen(c, buf[0], g.bps[c])) evaluate(c); }
+    for (int c = 0; c < n; c++) { refresh_floor(); if (screen(c)) evaluate(c); }
 #else
     {
+        // Two per-warp lists keep both stages dense: records whose state asks for a look (FRESH, or PRUNED with a
+        // bound that reaches the floor) are collected and SCREENED 32 at a time (their bp scores and records are
+        // re-read with 32 loads in flight), and what passes the bounds is collected and EVALUATED 32 at a time.
         const int wid = threadIdx.x >> 5;
-        int *wl = (int *)S.ckey + 64 * wid;       // this warp's list of entries to evaluate (Layout::Ccap = 64 per warp)
-        int wn = 0;
+        int *wa = (int *)S.ckey + 128 * wid, *wb = wa + 64;      // Layout::Ccap = 128 per warp
+        int na = 0, nb = 0;
+        auto push = [&](int *list, int &cnt, bool p, int c) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, p);
+            if (p) list[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
+            cnt += __popc(bal);
+            __syncwarp();
+        };
+        auto drain = [&](bool all) {
+            #pragma unroll 1
+            while (na >= 32 || (all && na > 0)) {
+                const int take = na >= 32 ? 32 : na;
+                na -= take;
+                refresh_floor();
+                const bool need = lane < take && screen(wa[na + lane]);
+                const int c = lane < take ? wa[na + lane] : 0;
+                __syncwarp();
+                push(wb, nb, need, c);
+                if (nb >= 32) { nb -= 32; evaluate(wb[nb + lane]); __syncwarp(); }
+            }
+            if (all && nb > 0) { if (lane < nb) evaluate(wb[lane]); nb = 0; __syncwarp(); }
+        };
         #pragma unroll 1
         for (int c0 = grab(); c0 < n; c0 = grab()) {
             #pragma unroll
@@ -2154,31 +2178,15 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
                 if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
             }
             refresh_floor();
-            // the bp scores of the records that will be screened, all loads in flight together
-            #pragma unroll
+            #pragma unroll 1
             for (int u = 0; u < GL_BATCH; u++) {
                 const uint32_t st = (buf[u].meta >> 16) & GS_MASK;
                 const bool want = buf[u].key != GK_DEAD && (st == GS_FRESH || ((st == GS_PRUNED || st == GS_PRUNED1) && !(buf[u].v < floor)));
-                bpsbuf[u] = want ? g.bps[c0 + u * 32 + lane] : 0.0;
-            }
-            #pragma unroll 1
-            for (int u = 0; u < GL_BATCH; u++) {
-                const int c = c0 + u * 32 + lane;
-                refresh_floor();
-                const bool need = screen(c, buf[u], bpsbuf[u]);
-                const uint32_t bal = __ballot_sync(0xffffffffu, need);
-                if (need) wl[wn + __popc(bal & ((1u << lane) - 1u))] = c;
-                wn += __popc(bal);
-                __syncwarp();
-                if (wn >= 32) {
-                    wn -= 32;
-                    evaluate(wl[wn + lane]);
-                    __syncwarp();
-                }
+                push(wa, na, want, c0 + u * 32 + lane);
+                if (na >= 32) drain(false);
             }
         }
-        if (lane < wn) evaluate(wl[lane]);
-        __syncwarp();
+        drain(true);
     }
 #endif
     if (g.stat) {
