@@ -183,7 +183,7 @@ struct CachedStems {
 
 enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GCNT, W_GCNT2, W_GSTAT, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -520,7 +520,7 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
         GEnt *ge; double *gb; int32_t *ovf; int *cnt, *gcnt;
         TRY(dalloc(ctx, W_GENT, (size_t)ncl * pl.gcap, &ge));
         TRY(dalloc(ctx, W_GBPS, (size_t)ncl * pl.gcap, &gb));
-        TRY(dalloc(ctx, W_OVF, (size_t)W.n_items, &ovf));
+        TRY(dalloc(ctx, W_OVF2, (size_t)W.n_items, &ovf));      // not W_OVF: fast-lane chunks on the other stream use that one
         TRY(dalloc(ctx, W_GCNT, 4, &cnt));
         TRY(dalloc(ctx, W_GCNT2, (size_t)4 * ncl, &gcnt));
         CK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
@@ -562,7 +562,7 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
         GEnt *ge; double *gb; int32_t *ovf; int *cnt;
         TRY(dalloc(ctx, W_GENT, (size_t)gg * pl.gcap, &ge));
         TRY(dalloc(ctx, W_GBPS, (size_t)gg * pl.gcap, &gb));
-        TRY(dalloc(ctx, W_OVF, (size_t)W.n_items, &ovf));
+        TRY(dalloc(ctx, W_OVF2, (size_t)W.n_items, &ovf));      // not W_OVF: fast-lane chunks on the other stream use that one
         TRY(dalloc(ctx, W_GCNT, 4, &cnt));
         CK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
         DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_cap = pl.gcap;
@@ -629,7 +629,7 @@ static int launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, const DevBatch
 static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t st, int64_t item_base, int64_t n_items,
                        const int64_t *d_offsets, const uint8_t *d_symbols, uint8_t *d_dbn_ascii, double *d_scores,
                        int32_t *d_n_stems, uint8_t *d_flags, int *d_counter, int32_t *d_ovf, unsigned long long *d_ncalls, int round3,
-                       cudaEvent_t e0, cudaEvent_t e1)
+                       cudaEvent_t e0, cudaEvent_t e1, const int32_t *d_order = nullptr)
 {
     DevBatch B; memset(&B, 0, sizeof B);
     B.n_seqs = item_base + n_items; B.off = d_offsets; B.sym = d_symbols;
@@ -640,6 +640,7 @@ static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStrea
         W.ovf_count = d_counter + 1; W.n_items_dev = d_counter + 1; W.ovf_list = d_ovf + item_base;
     }
     W.out_nstems = d_n_stems; W.out_raw = d_scores; W.dbn_off = d_offsets; W.out_dbn_ascii = d_dbn_ascii;
+    W.order = d_order;             // absolute item ids, or NULL: items item_base .. item_base + n_items - 1 in order
     if (e0) CK(cudaEventRecord(e0, st));
     TRY(dispatch(ctx, P, pl, st, B, W));
     if (e1) CK(cudaEventRecord(e1, st));
@@ -740,6 +741,21 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         const int cls = max_len <= 128 ? 0 : max_len <= 224 ? 1 : max_len <= 320 ? 2 : 3;
         if (cls == 3 || !have_plan[cls]) { TRY(make_fast_plan(ctx, *P, max_len, (int)(b1 - b0), plans[cls])); have_plan[cls] = true; }
         const Plan &pl = plans[cls];
+        // CTA-team plans share per-context scratch (candidate lists, counters): their chunks all go to one stream
+        if (pl.tw > 1) s_k = s_main;
+        // long sequences: longest first, so that the last CTAs to finish are not the longest items
+        const int32_t *d_order = nullptr;
+        if (pl.tw > 1 && b1 - b0 > 1) {
+            std::vector<int32_t> ord((size_t)(b1 - b0));
+            for (int64_t k = 0; k < b1 - b0; k++) ord[(size_t)k] = (int32_t)(b0 + k);
+            std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+                return offsets[x + 1] - offsets[x] > offsets[y + 1] - offsets[y]; });
+            int32_t *d_o;
+            TRY(dalloc(ctx, W_ORDER, (size_t)n_seqs, &d_o));
+            CK(cudaMemcpyAsync(d_o + b0, ord.data(), ord.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
+            CK(cudaStreamSynchronize(ctx->s_in));          // `ord` is a local: the staged copy must be done with it
+            d_order = d_o + b0;
+        }
         // stage 1: inputs of the chunk
         CK(cudaMemcpyAsync(d_off + b0 + (c ? 1 : 0), offsets + b0 + (c ? 1 : 0), (size_t)(b1 - b0 + (c ? 0 : 1)) * sizeof(int64_t),
                            cudaMemcpyHostToDevice, ctx->s_in));
@@ -749,7 +765,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         CK(cudaStreamWaitEvent(s_k, ctx->ev_in[c], 0));
         if (c == 1) CK(cudaStreamWaitEvent(s_k, ctx->ev_start, 0));
         TRY(fast_launch(ctx, *P, pl, s_k, b0, b1 - b0, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + 4 * c, d_ovf, d_nc, 1,
-                        ctx->ev_k0[c], ctx->ev_k1[c]));
+                        ctx->ev_k0[c], ctx->ev_k1[c], d_order));
         // stage 3: outputs of the chunk
         CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k1[c], 0));
         if (t1 > t0) CK(cudaMemcpyAsync(dbn_ascii + t0, d_dbn + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ctx->s_out));
