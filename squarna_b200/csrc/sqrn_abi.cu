@@ -104,7 +104,7 @@ k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
 // global memory (gl_build / gl_step): one enumeration per sequence, cached adjusted scores.  Items
 // whose list overflows its slot go to DevWork::ovf_list and are redone by k_work<TW> behind it.
 template <int TW>
-__global__ void __launch_bounds__(TW * 32, 1)
+__global__ void __launch_bounds__(TW * 32, TW == 8 ? 4 : 1)
 k_long(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
 {
     extern __shared__ __align__(16) unsigned char smem[];
