@@ -193,6 +193,7 @@ struct sqrn_ctx {
     cudaEvent_t ev_start = nullptr, ev_out = nullptr, ev_k2done = nullptr;
     cudaEvent_t ev_in[FAST_MAX_CHUNKS] = {}, ev_k0[FAST_MAX_CHUNKS] = {}, ev_k1[FAST_MAX_CHUNKS] = {}, ev_o[FAST_MAX_CHUNKS] = {};
     uint8_t *hflags = nullptr; size_t hflags_cap = 0;                    // pinned staging for the result flags
+    int32_t *horder = nullptr; size_t horder_cap = 0;                   // pinned: processing order of the fast-lane chunks
     std::string err;
     int sm_count = 0; size_t smem_optin = 0;
     std::vector<PEntry> pcache;
@@ -276,6 +277,7 @@ extern "C" void sqrn_ctx_destroy(sqrn_ctx *ctx)
     cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_out); cudaEventDestroy(ctx->ev_k2done);
     for (int c = 0; c < FAST_MAX_CHUNKS; c++) { cudaEventDestroy(ctx->ev_in[c]); cudaEventDestroy(ctx->ev_k0[c]); cudaEventDestroy(ctx->ev_k1[c]); cudaEventDestroy(ctx->ev_o[c]); }
     if (ctx->hflags) cudaFreeHost(ctx->hflags);
+    if (ctx->horder) cudaFreeHost(ctx->horder);
     delete ctx;
 }
 
@@ -725,6 +727,14 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     CK(cudaEventRecord(ctx->ev_start, s_main));
     CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
     Plan plans[4]; bool have_plan[4] = {false, false, false, false};
+    if (ctx->horder_cap < (size_t)n_seqs) {
+        if (ctx->horder) cudaFreeHost(ctx->horder);
+        ctx->horder = nullptr; ctx->horder_cap = 0;
+        CK(cudaMallocHost(&ctx->horder, ((size_t)n_seqs + 64) * sizeof(int32_t)));
+        ctx->horder_cap = (size_t)n_seqs + 64;
+    }
+    std::vector<int64_t> len_count;
+    const bool no_order = getenv("SQRN_FAST_NO_ORDER") != nullptr;
     for (int c = 0; c < nchunks; c++) {
         const int64_t b0 = bounds[c], b1 = bounds[c + 1];
         const int64_t t0 = offsets[b0], t1 = offsets[b1];
@@ -744,16 +754,19 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         // CTA-team plans share per-context scratch (candidate lists, counters): their chunks all go to one stream
         if (pl.tw > 1) s_k = s_main;
         // long sequences: longest first, so that the last CTAs to finish are not the longest items
+        // Longest first within the chunk (a counting sort by length, done while the earlier chunks run): the
+        // persistent CTAs of a chunk then finish on short items, so the SM slots the next chunk's kernel is
+        // waiting for free up together instead of trailing behind one long sequence each.
         const int32_t *d_order = nullptr;
-        if (pl.tw > 1 && b1 - b0 > 1) {
-            std::vector<int32_t> ord((size_t)(b1 - b0));
-            for (int64_t k = 0; k < b1 - b0; k++) ord[(size_t)k] = (int32_t)(b0 + k);
-            std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
-                return offsets[x + 1] - offsets[x] > offsets[y + 1] - offsets[y]; });
+        if (b1 - b0 > 1 && (pl.tw > 1 || b1 - b0 >= 4096) && !no_order) {
+            int32_t *ord = ctx->horder + b0;      // pinned, one region per chunk: the copy below is truly asynchronous
+            len_count.assign((size_t)max_len + 2, 0);
+            for (int64_t b = b0; b < b1; b++) len_count[(size_t)(max_len - (offsets[b + 1] - offsets[b])) + 1]++;
+            for (int l = 0; l <= max_len; l++) len_count[(size_t)l + 1] += len_count[(size_t)l];
+            for (int64_t b = b0; b < b1; b++) ord[len_count[(size_t)(max_len - (offsets[b + 1] - offsets[b]))]++] = (int32_t)b;
             int32_t *d_o;
             TRY(dalloc(ctx, W_ORDER, (size_t)n_seqs, &d_o));
-            CK(cudaMemcpyAsync(d_o + b0, ord.data(), ord.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
-            CK(cudaStreamSynchronize(ctx->s_in));          // `ord` is a local: the staged copy must be done with it
+            CK(cudaMemcpyAsync(d_o + b0, ord, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
             d_order = d_o + b0;
         }
         // stage 1: inputs of the chunk
