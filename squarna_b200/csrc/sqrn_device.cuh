@@ -1970,29 +1970,39 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
             }
         }
     }
+    ((int *)S.cbps)[r] = -1;                          // gl_step: no remembered best yet
     gl_sync<C>();
     return *(volatile int *)np <= g.cap;
 }
 
-// One OptimalStems pass over the global list.  (ui, uj, ul): the stem T applied since the last pass
-// (ul = 0: none); (ei, ej): the selected stem enclosing T with the largest i (ei < 0: none);
-// relevel: the level of some older stem changed when T was added.  ok = false: overflow.
+// One OptimalStems pass over the global list: ONE coalesced sweep.  (ui, uj, ul): the stem T applied since
+// the last pass (ul = 0: none); (ei, ej): the selected stem enclosing T with the largest i (ei < 0: none);
+// relevel: the level of some older stem changed when T was added; step: number of this pass (stamps the
+// records it has brought up to date, so that nothing is revised twice).  ok = false: overflow.
+//
+//   prologue  every thread re-checks the record that was ITS best in the previous pass; what is still a valid
+//             cached score gives the floor before the sweep starts (usually last pass's runner-up);
+//   sweep     per record: cut / invalidate against T (`revise`), arg-max of the cached scores that hold, and
+//             FRESH records or PRUNED ones whose bound reaches the floor go to a per-warp list that is
+//             SCREENED 32 at a time (bounds); what passes goes to a second list EVALUATED 32 at a time;
+//   epilogue  the pieces appended by the cuts of this pass (behind the old end of the list) are screened too.
 template <class C>
 __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const GList &g, int ui, int uj, int ul,
-                        int ei, int ej, bool relevel, bool &ok, int &xc)
+                        int ei, int ej, bool relevel, bool &ok, int &xc, int step)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     ok = true;
     int *np = C::CLUSTER ? &g.cnt[0] : &S.misc[8];        // records in the list
     int *cc = C::CLUSTER ? &g.cnt[1] : &S.misc[12];       // next chunk of the sweep
-    int n = *(volatile int *)np;
+    int *top = (int *)S.cbps;                             // per thread: the record that was its best in the last pass
+    const int n = *(volatile int *)np;
+    const uint32_t stamp = (uint32_t)(step % 4095 + 1) << 20;       // never 0 (= not stamped); the caller stops at 4094 passes
     Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
+    int best_idx = -1;
     const int u1 = ui + ul - 1, v0 = uj - ul + 1;          // the arms of T: [ui, u1] and [v0, uj]
     unsigned n_eval = 0, n_reset = 0, n_cut = 0;
     GEnt buf[GL_BATCH];
-    // Warps take chunks of 32 * GL_BATCH consecutive records from a shared counter (cuts and evaluations
-    // are unevenly spread over the list; fixed strides would leave most warps waiting at the barriers).
 #ifdef SQRN_HOST_EMU
     const int lane = 0;
     constexpr int WL = 1;
@@ -2001,112 +2011,93 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
 #else
     const int lane = threadIdx.x & 31;
     constexpr int WL = 32;
+    // warps take chunks of 32 * GL_BATCH consecutive records from a shared counter (cuts and evaluations are
+    // unevenly spread over the list; fixed strides would leave most warps waiting at the barriers)
     auto grab = [&]() {
         int c0 = 0;
         if (lane == 0) c0 = atomicAdd(cc, WL * GL_BATCH);
         return __shfl_sync(0xffffffffu, c0, 0);
     };
 #endif
-    if (gl_leader<C>(S)) *cc = 0;
-    gl_sync<C>();
-    const long long t_a = g.stat ? gl_clock() : 0;
-    // ---- sweep 1: cut, invalidate, arg-max of the cached scores that still hold
-    #pragma unroll 1
-    for (int c0 = grab(); c0 < n; c0 = grab()) {
-        #pragma unroll
-        for (int u = 0; u < GL_BATCH; u++) {
-            const int c = c0 + u * WL + lane;
-            if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
-        }
-        #pragma unroll 1
-        for (int u = 0; u < GL_BATCH; u++) {
-            const int c = c0 + u * WL + lane;
-            const uint32_t key = buf[u].key;
-            if (key == GK_DEAD) continue;
-            const uint32_t meta = buf[u].meta;
-            const int len = (int)(meta & 0xffffu), a = (int)(key & 0xffffu), s = (int)(key >> 16), t = s - a;
-            uint32_t st = (meta >> 16) & GS_MASK;
-            // T can cut the run or change its cached score only if one of its arms meets [a - 5, t + 5]
-            // (the run's rows and columns all lie in [a, t]); most records fail this test and are done
-            if (ul > 0 && !((u1 < a - 5 || ui > t + 5) && (uj < a - 5 || v0 > t + 5))) {
-                const int A0 = ui - a, A1 = u1 - a, B0 = v0 - a, B1 = uj - a;
-                const int C0 = t - u1, C1 = t - ui, D0 = t - uj, D1 = t - v0;
-                const int top = len - 1;
-                if ((A0 <= top && A1 >= 0) || (B0 <= top && B1 >= 0) || (C0 <= top && C1 >= 0) || (D0 <= top && D1 >= 0)) {
-                    uint32_t live = len <= 32 ? (0xffffffffu >> (32 - len)) & ~(bits_between(A0, A1) | bits_between(B0, B1) |
-                                                                                bits_between(C0, C1) | bits_between(D0, D1)) : 0u;
-                    auto dead = [&](int q) { return (q >= A0 && q <= A1) || (q >= B0 && q <= B1) || (q >= C0 && q <= C1) || (q >= D0 && q <= D1); };
-                    bool first = true;
-                    int q = 0;
-                    #pragma unroll 1
-                    for (;;) {
-                        int p0, pl;
-                        if (len <= 32) {
-                            if (!live) break;
-                            p0 = __ffs(live) - 1;
-                            const uint32_t inv = ~(live >> p0);
-                            pl = inv ? __ffs(inv) - 1 : 32;
-                            live = (p0 + pl >= 32) ? 0u : (live >> (p0 + pl)) << (p0 + pl);
-                        } else {
-                            #pragma unroll 1
-                            while (q < len && dead(q)) q++;
-                            if (q >= len) break;
-                            p0 = q;
-                            #pragma unroll 1
-                            while (q < len && !dead(q)) q++;
-                            pl = q - p0;
-                        }
-                        if ((double)pl < P.minlen) continue;
-                        double pos;
-                        const double sc = run_score_pos<C>(S, P, B, s, a + p0, pl, pos);
-                        if (!(pos >= P.minbpscore)) continue;
-                        const int slot = first ? c : atomicAdd(np, 1);
-                        if (slot < g.cap) {
-                            gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)(a + p0),
-                                     (uint32_t)pl | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
-                            g.bps[slot] = sc;
-                        }
-                        first = false;
-                    }
-                    if (first) g.ent[c].key = GK_DEAD;
-                    n_cut++;
-                    continue;
-                }
-                if (st == GS_EVAL || st == GS_PRUNED) {
-                    // T meets the window the cached value was computed from: stale unless T is shielded
-                    const int ss = a + len - 1, se = t - len + 1;
-                    const bool shielded = ei >= 0 && ss < ei && ej < se;
-                    if (!shielded) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
-                }
-            }
-            // a level change only matters to scores that counted the wing of a selected stem
-            if (relevel && st == GS_EVAL && (meta >> 16 & GS_LEVELS)) { st = GS_FRESH; g.ent[c].meta = (uint32_t)len; n_reset++; }
-            if (st == GS_EVAL) {
-                const double fin = buf[u].v;
-                if (fin >= P.minfinscore && better(fin, key, best.fin, best.key)) { best.fin = fin; best.key = key; best.len = len; }
-            }
-        }
-    }
-    best = team_argmax<C>(S, best);               // barrier: the appended pieces are visible
-    if (C::CLUSTER) best = cluster_best<C>(S, best, xc++);       // (cluster barrier inside)
-    const long long t_b = g.stat ? gl_clock() : 0;
-    n = *(volatile int *)np;
-    if (n > g.cap) { ok = false; return best; }
-    // ---- sweep 2: FRESH entries, and PRUNED ones whose bound reaches the floor.  The bounds are checked
-    // entry by entry; what passes is collected in a per-warp list and evaluated 32 at a time, so that the
-    // ScoreStems region walks (hundreds of instructions each) run with full warps.
-    unsigned *fl_hi = (unsigned *)&S.misc[9];     // high word of the best score found so far in this sweep (a lower bound of it)
-    if (r == 0) *fl_hi = best.fin > 0.0 ? (unsigned)__double2hiint(best.fin) : 0u;
-    if (gl_leader<C>(S)) *cc = 0;
-#ifdef SQRN_HOST_EMU
-    next_chunk = 0;
-#endif
-    gl_sync<C>();
-    double floor = best.fin;
+    unsigned *fl_hi = (unsigned *)&S.misc[9];     // high word of the best score found so far (a lower bound of it)
+    double floor = -1e300;
     auto refresh_floor = [&]() {
         const unsigned h = *(volatile unsigned *)fl_hi;
         const double f = __hiloint2double((int)h, 0);
         if (h && f > floor) floor = f;
+    };
+    auto offer = [&](double fin, uint32_t key, int len, int c) {          // a valid adjusted score
+        if (fin >= P.minfinscore && better(fin, key, best.fin, best.key)) {
+            best.fin = fin; best.key = key; best.len = len; best_idx = c;
+            if (fin > floor) { floor = fin; if (fin > 0.0) atomicMax(fl_hi, (unsigned)__double2hiint(fin)); }
+        }
+    };
+    // Brings record c (loaded into e) up to date with T: cuts it, or puts its cached value back to FRESH when T
+    // may have changed it.  Returns the state it is in now (GK_DEAD records and cut ones report GS_BELOW: nothing
+    // more to do with them in this pass -- the pieces of a cut are FRESH records of their own).
+    auto revise = [&](int c, GEnt &e) -> uint32_t {
+        if (e.key == GK_DEAD) return GS_BELOW;
+        const uint32_t meta = e.meta;
+        uint32_t st = (meta >> 16) & GS_MASK;
+        if (ul <= 0 || (meta & 0xfff00000u) == stamp) return st;          // no new stem, or already revised in this pass
+        const int len = (int)(meta & 0xffffu), a = (int)(e.key & 0xffffu), s = (int)(e.key >> 16), t = s - a;
+        // T can cut the run or change its cached score only if one of its arms meets [a - 5, t + 5]
+        // (the run's rows and columns all lie in [a, t]); most records fail this test and are done
+        if (!((u1 < a - 5 || ui > t + 5) && (uj < a - 5 || v0 > t + 5))) {
+            const int A0 = ui - a, A1 = u1 - a, B0 = v0 - a, B1 = uj - a;
+            const int C0 = t - u1, C1 = t - ui, D0 = t - uj, D1 = t - v0;
+            const int topq = len - 1;
+            if ((A0 <= topq && A1 >= 0) || (B0 <= topq && B1 >= 0) || (C0 <= topq && C1 >= 0) || (D0 <= topq && D1 >= 0)) {
+                uint32_t live = len <= 32 ? (0xffffffffu >> (32 - len)) & ~(bits_between(A0, A1) | bits_between(B0, B1) |
+                                                                            bits_between(C0, C1) | bits_between(D0, D1)) : 0u;
+                auto dead = [&](int q) { return (q >= A0 && q <= A1) || (q >= B0 && q <= B1) || (q >= C0 && q <= C1) || (q >= D0 && q <= D1); };
+                bool first = true;
+                int q = 0;
+                #pragma unroll 1
+                for (;;) {
+                    int p0, pl;
+                    if (len <= 32) {
+                        if (!live) break;
+                        p0 = __ffs(live) - 1;
+                        const uint32_t inv = ~(live >> p0);
+                        pl = inv ? __ffs(inv) - 1 : 32;
+                        live = (p0 + pl >= 32) ? 0u : (live >> (p0 + pl)) << (p0 + pl);
+                    } else {
+                        #pragma unroll 1
+                        while (q < len && dead(q)) q++;
+                        if (q >= len) break;
+                        p0 = q;
+                        #pragma unroll 1
+                        while (q < len && !dead(q)) q++;
+                        pl = q - p0;
+                    }
+                    if ((double)pl < P.minlen) continue;
+                    double pos;
+                    const double sc = run_score_pos<C>(S, P, B, s, a + p0, pl, pos);
+                    if (!(pos >= P.minbpscore)) continue;
+                    const int slot = first ? c : atomicAdd(np, 1);
+                    const uint32_t nm = (uint32_t)pl | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16) | stamp;
+                    if (slot < g.cap) {
+                        gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)(a + p0), nm, 0.0);
+                        g.bps[slot] = sc;
+                    }
+                    if (first) { e.key = ((uint32_t)s << 16) | (uint32_t)(a + p0); e.meta = nm; }
+                    first = false;
+                }
+                n_cut++;
+                if (first) { g.ent[c].key = GK_DEAD; e.key = GK_DEAD; return GS_BELOW; }
+                return (e.meta >> 16) & GS_MASK;          // the piece that stayed in this slot
+            }
+            if (st == GS_EVAL || st == GS_PRUNED) {
+                // T meets the window the cached value was computed from: stale unless T is shielded
+                const int ss = a + len - 1, se = t - len + 1;
+                const bool shielded = ei >= 0 && ss < ei && ej < se;
+                if (!shielded) { st = GS_FRESH; e.meta = (uint32_t)len | stamp; g.ent[c].meta = e.meta; n_reset++; return st; }
+            }
+        }
+        // a level change only matters to scores that counted the wing of a selected stem
+        if (relevel && st == GS_EVAL && (meta >> 16 & GS_LEVELS)) { st = GS_FRESH; e.meta = (uint32_t)len | stamp; g.ent[c].meta = e.meta; n_reset++; }
+        return st;
     };
     auto evaluate = [&](int c) {
         const GEnt e = gl_load(&g.ent[c]);
@@ -2114,17 +2105,14 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         const double bps = g.bps[c];
         int order = 0;
         const double fin = score_candidate<C>(S, P, (int)(e.key >> 16), (int)(e.key & 0xffffu), len, bps, &order);
-        gl_store(&g.ent[c], e.key, (uint32_t)len | ((GS_EVAL | (order ? GS_LEVELS : 0u)) << 16), fin);
+        gl_store(&g.ent[c], e.key, (uint32_t)len | ((GS_EVAL | (order ? GS_LEVELS : 0u)) << 16) | stamp, fin);
         n_eval++;
 #ifdef SQRN_EMU_DEBUG
         printf("  eval nst=%d (%d,%d,%d) bps=%g fin=%.17g\n", S.nst, (int)(e.key & 0xffff), (int)(e.key >> 16) - (int)(e.key & 0xffff), len, bps, fin);
 #endif
-        if (fin >= P.minfinscore && better(fin, e.key, best.fin, best.key)) {
-            best.fin = fin; best.key = e.key; best.len = len;
-            if (fin > floor) { floor = fin; if (fin > 0.0) atomicMax(fl_hi, (unsigned)__double2hiint(fin)); }
-        }
+        offer(fin, e.key, len, c);
     };
-    // true: entry c has to be evaluated (its bounds reach the floor)
+    // true: record c (already revised) has to be evaluated: its bounds reach the floor
     auto screen = [&](int c) -> bool {
         const GEnt e = gl_load(&g.ent[c]);
         if (e.key == GK_DEAD) return false;
@@ -2134,61 +2122,106 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         const int len = (int)(e.meta & 0xffffu);
         const double bps = g.bps[c];
         double ub = score_bound(P, bps);
-        if (ub < floor || ub < P.minfinscore) { if (st != GS_PRUNED1) gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED1 << 16), ub); return false; }
+        if (ub < floor || ub < P.minfinscore) { if (st != GS_PRUNED1) gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED1 << 16) | stamp, ub); return false; }
         ub = tight_bound(S, P, e.key, len, bps);
-        if (ub < floor || ub < P.minfinscore) { gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16), ub); return false; }
+        if (ub < floor || ub < P.minfinscore) { gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16) | stamp, ub); return false; }
         return true;
     };
-#ifdef SQRN_HOST_EMU
-    #pragma unroll 1
-    for (int c = 0; c < n; c++) { refresh_floor(); if (screen(c)) evaluate(c); }
-#else
-    {
-        // Two per-warp lists keep both stages dense: records whose state asks for a look (FRESH, or PRUNED with a
-        // bound that reaches the floor) are collected and SCREENED 32 at a time (their bp scores and records are
-        // re-read with 32 loads in flight), and what passes the bounds is collected and EVALUATED 32 at a time.
-        const int wid = threadIdx.x >> 5;
-        int *wa = (int *)S.ckey + 128 * wid, *wb = wa + 64;      // Layout::Ccap = 128 per warp
-        int na = 0, nb = 0;
-        auto push = [&](int *list, int &cnt, bool p, int c) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, p);
-            if (p) list[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
-            cnt += __popc(bal);
-            __syncwarp();
-        };
-        auto drain = [&](bool all) {
-            #pragma unroll 1
-            while (na >= 32 || (all && na > 0)) {
-                const int take = na >= 32 ? 32 : na;
-                na -= take;
-                refresh_floor();
-                const bool need = lane < take && screen(wa[na + lane]);
-                const int c = lane < take ? wa[na + lane] : 0;
-                __syncwarp();
-                push(wb, nb, need, c);
-                if (nb >= 32) { nb -= 32; evaluate(wb[nb + lane]); __syncwarp(); }
-            }
-            if (all && nb > 0) { if (lane < nb) evaluate(wb[lane]); nb = 0; __syncwarp(); }
-        };
-        #pragma unroll 1
-        for (int c0 = grab(); c0 < n; c0 = grab()) {
-            #pragma unroll
-            for (int u = 0; u < GL_BATCH; u++) {
-                const int c = c0 + u * 32 + lane;
-                if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
-            }
-            refresh_floor();
-            #pragma unroll 1
-            for (int u = 0; u < GL_BATCH; u++) {
-                const uint32_t st = (buf[u].meta >> 16) & GS_MASK;
-                const bool want = buf[u].key != GK_DEAD && (st == GS_FRESH || ((st == GS_PRUNED || st == GS_PRUNED1) && !(buf[u].v < floor)));
-                push(wa, na, want, c0 + u * 32 + lane);
-                if (na >= 32) drain(false);
-            }
+    auto wants_look = [&](uint32_t st, const GEnt &e) {
+        return st == GS_FRESH || ((st == GS_PRUNED || st == GS_PRUNED1) && !(e.v < floor));
+    };
+
+    // ---- prologue: the floor from the records that were the threads' bests in the last pass
+    if (r == 0) *fl_hi = 0u;
+    if (gl_leader<C>(S)) *cc = 0;
+    gl_sync<C>();
+    const long long t_a = g.stat ? gl_clock() : 0;
+    if (n >= 8 * T || C::CLUSTER) {                // (short lists: a sweep is a few records per thread, a floor buys nothing)
+        const int c = top[r];
+        if (c >= 0 && c < n) {
+            GEnt e = gl_load(&g.ent[c]);
+            if (revise(c, e) == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
         }
-        drain(true);
+        Best f = team_argmax<C>(S, best);
+        if (C::CLUSTER) f = cluster_best<C>(S, f, xc++);
+        if (f.fin > floor) floor = f.fin;          // every thread starts from the team-wide (cluster-wide) floor
     }
+    // ---- the sweep
+#ifdef SQRN_HOST_EMU
+    auto look = [&](int c) { refresh_floor(); if (screen(c)) evaluate(c); };
+    #pragma unroll 1
+    for (int c = 0; c < n; c++) {
+        GEnt e = gl_load(&g.ent[c]);
+        const uint32_t st = revise(c, e);
+        if (st == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
+        else if (wants_look(st, e)) look(c);
+    }
+    const int n2 = *(volatile int *)np;
+    if (n2 > g.cap) { ok = false; return best; }
+    #pragma unroll 1
+    for (int c = n; c < n2; c++) look(c);           // the pieces appended by this pass
+    const long long t_b = t_a;
+#else
+    const int wid = threadIdx.x >> 5;
+    int *wa = (int *)S.ckey + 128 * wid, *wb = wa + 64;      // Layout::Ccap = 128 per warp
+    int na = 0, nb = 0;
+    auto push = [&](int *list, int &cnt, bool p, int c) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, p);
+        if (p) list[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
+        cnt += __popc(bal);
+        __syncwarp();
+    };
+    auto drain = [&](bool all) {
+        #pragma unroll 1
+        while (na >= 32 || (all && na > 0)) {
+            const int take = na >= 32 ? 32 : na;
+            na -= take;
+            refresh_floor();
+            const int c = lane < take ? wa[na + lane] : 0;
+            const bool need = lane < take && screen(c);
+            __syncwarp();
+            push(wb, nb, need, c);
+            if (nb >= 32) { nb -= 32; evaluate(wb[nb + lane]); __syncwarp(); }
+        }
+        if (all && nb > 0) { if (lane < nb) evaluate(wb[lane]); nb = 0; __syncwarp(); }
+    };
+    #pragma unroll 1
+    for (int c0 = grab(); c0 < n; c0 = grab()) {
+        #pragma unroll
+        for (int u = 0; u < GL_BATCH; u++) {
+            const int c = c0 + u * 32 + lane;
+            if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
+        }
+        refresh_floor();
+        #pragma unroll 1
+        for (int u = 0; u < GL_BATCH; u++) {
+            const int c = c0 + u * 32 + lane;
+            GEnt e = buf[u];
+            const uint32_t st = revise(c, e);
+            if (st == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
+            push(wa, na, wants_look(st, e), c);
+            if (na >= 32) drain(false);
+        }
+    }
+    drain(true);
+    // ---- epilogue: the pieces this pass appended
+    if (gl_leader<C>(S)) *cc = n;
+    gl_sync<C>();
+    const long long t_b = g.stat ? gl_clock() : 0;
+    const int n2 = *(volatile int *)np;
+    if (n2 > g.cap) { ok = false; return best; }
+    #pragma unroll 1
+    for (int c0 = grab(); c0 < n2; c0 = grab()) {
+        #pragma unroll 1
+        for (int u = 0; u < GL_BATCH; u++) {
+            const int c = c0 + u * 32 + lane;
+            push(wa, na, c < n2, c);
+            if (na >= 32) drain(false);
+        }
+    }
+    drain(true);
 #endif
+    top[r] = best_idx;
     if (g.stat) {
         Team<TW>::sync();
         if (r == 0) { const long long t_c = gl_clock(); atomicAdd(&g.stat[6], (unsigned long long)(t_b - t_a)); atomicAdd(&g.stat[7], (unsigned long long)(t_c - t_b)); }
@@ -2538,7 +2571,8 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
                 #pragma unroll 1
                 for (int t = r; t < S.nst; t += T) S.stlev2[t] = S.stlev[t];
                 Team<TW>::sync();
-                b = gl_step<C>(S, P, B, g, ui, uj, ul, ei, ej, relevel, ok, xc);
+                if (calls >= 4094) { ok = false; break; }        // the pass stamp of the records has 12 bits: let the rescanning kernel do it
+                b = gl_step<C>(S, P, B, g, ui, uj, ul, ei, ej, relevel, ok, xc, (int)calls);
                 if (!ok) break;
             } else if (C::PERSIST) {
                 b = persist_step<C>(S, P, B, L, ui, uj, ul, ok);
