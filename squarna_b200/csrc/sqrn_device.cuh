@@ -19,11 +19,16 @@
 //       (score desc, i+j asc, i asc), which is the order the reference's stable
 //       sort leaves ties in.
 //
-// One OptimalStems pass is a three-phase pipeline so that every phase keeps the
-// lanes of a warp busy with the same kind of work:
+// One RESCANNING OptimalStems pass (team_scan) is a three-phase pipeline so that every
+// phase keeps the lanes of a warp busy with the same kind of work:
 //   1  lane per anti-diagonal:  enumerate runs >= minlen        -> run list
 //   2a lane per run:            sum the bp scores (seq.py:416)  -> survivor list
 //   2b lane per survivor:       ScoreStems factor product       -> arg-max
+// Sequences that run to completion (MODE_TAIL) do not rescan: between two greedy steps the
+// masked matrix only loses cells, so the list of maximal runs is built once and then only
+// cut where the selected stem touches it -- in shared memory for warp teams (persist_build /
+// persist_step), in global memory with cached adjusted scores for CTA teams and thread-block
+// clusters (gl_build / gl_step).  DESIGN.md 3.1-3.2.
 //
 // A "team" is the group of threads that owns one (sequence, partial structure)
 // work item: one warp for short sequences, one CTA for long ones.
