@@ -199,6 +199,8 @@ SQRN_API int  sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_
 SQRN_API int  sqrn_text_parse(const char *text, int64_t len, int multiline, int64_t *n_entries, int64_t *total_seq,
                         int64_t cap_entries, int64_t cap_seq, int64_t *name_begin, int32_t *name_len,
                         int64_t *seq_offsets, uint8_t *seq);
+SQRN_API int  sqrn_text_ungap(int64_t n, const int64_t *seq_offsets, const uint8_t *seq,      /* UnAlign, seq.py:236-255 */
+                        int64_t *sym_offsets, uint8_t *sym);
 SQRN_API int  sqrn_text_format(int64_t first, int64_t count, const char *text, const int64_t *name_begin,
                         const int32_t *name_len, const int64_t *seq_offsets, const uint8_t *seq,
                         const int64_t *sym_offsets, const uint8_t *dbn, const double *scores, int conslim,

@@ -505,12 +505,8 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
     flush()
 
 
-_GAP_TABLE = None
-
-
 def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=0, slice_entries=131072):
     """SQUARNA.py:845-935 for the plain shape of an input.  False: not that shape (nothing was written)."""
-    global _GAP_TABLE
     import numpy as np
     from . import _lib
     from .SQRNdbnseq import get_context
@@ -519,13 +515,7 @@ def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=0, slice
     parsed = _lib.text_parse(text, multiline)
     if parsed is None:
         return False
-    if _GAP_TABLE is None:
-        _GAP_TABLE = np.zeros(256, dtype=bool)
-        _GAP_TABLE[[ord(ch) for ch in GAPS]] = True
-    keep = ~_GAP_TABLE[parsed.seq]                                    # UnAlign (seq.py:236-255) on the whole buffer
-    sym = np.ascontiguousarray(parsed.seq[keep])
-    csum = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
-    sym_off = np.ascontiguousarray(csum[parsed.seq_offsets])
+    sym, sym_off = _lib.text_ungap(parsed)                           # UnAlign (seq.py:236-255) on the whole buffer
     if int(np.diff(sym_off).max(initial=0)) > 16000:
         return False
     ctx = get_context(device)

@@ -18,7 +18,7 @@ MODE_TAIL, MODE_STEP, MODE_YIELD, MODE_FINAL = 0, 1, 2, 3
 EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx_destroy",
            "sqrn_last_error", "sqrn_ctx_set_stream", "sqrn_predict_batch", "sqrn_yield_stems_batch",
            "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
-           "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_format"]
+           "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_ungap", "sqrn_text_format"]
 
 _lib = None
 
@@ -53,6 +53,7 @@ def load():
     L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
     L.sqrn_debug_run.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.c_int, C.c_int] + [vp] * 11 + [C.c_int]
     L.sqrn_text_parse.argtypes = [vp, i64, C.c_int, C.POINTER(i64), C.POINTER(i64), i64, i64, vp, vp, vp, vp]
+    L.sqrn_text_ungap.argtypes = [i64, vp, vp, vp, vp]
     L.sqrn_text_format.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_char_p, vp, i64, C.POINTER(i64)]
     _lib = L
     return L
@@ -83,6 +84,17 @@ def text_parse(text, multiline):
     out.name_begin, out.name_len = name_begin[:n.value], name_len[:n.value]
     out.seq_offsets, out.seq = seq_off[:n.value + 1], seq[:tot.value]
     return out
+
+
+def text_ungap(parsed):
+    """(symbols without gap characters, their CSR offsets) of a ParsedText: UnAlign on the whole buffer"""
+    L = load()
+    sym = np.empty(max(len(parsed.seq), 1), np.uint8)
+    off = np.empty(parsed.n + 1, np.int64)
+    rc = L.sqrn_text_ungap(parsed.n, ptr(parsed.seq_offsets), ptr(parsed.seq), ptr(off), ptr(sym))
+    if rc != OK:
+        raise SqrnError("sqrn_text_ungap failed (%d)" % rc)
+    return sym[:int(off[-1])], off
 
 
 def text_format(parsed, first, count, sym_offsets, dbn, scores, conslim, psname):

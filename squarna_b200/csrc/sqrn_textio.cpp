@@ -19,11 +19,27 @@ inline bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (
 inline bool is_gap(unsigned char c) { return c == '-' || c == '.' || c == '~'; }      // seq.py:12
 
 // repr(round(x, 3)) for the magnitudes scores have: the decimal with at most three fraction digits,
-// trailing zeros dropped but one kept ("12.0", "0.5", "187.935", "-0.0")
+// trailing zeros dropped but one kept ("12.0", "0.5", "187.935", "-0.0").  x is already a rounded value
+// k / 1000, so k = llround(1000 x) is exact below 2^52 / 1000 and the digits come from integer arithmetic;
+// anything else (huge, nan, inf) takes printf.
 inline int fmt3(char *dst, double x)
 {
-    int n = snprintf(dst, 48, "%.3f", x);
-    while (n > 0 && dst[n - 1] == '0' && n > 1 && dst[n - 2] != '.') n--;
+    if (!(x > -4.0e12 && x < 4.0e12)) {
+        int n = snprintf(dst, 48, "%.3f", x);
+        while (n > 1 && dst[n - 1] == '0' && dst[n - 2] != '.') n--;
+        return n;
+    }
+    int n = 0;
+    if (x < 0.0 || (x == 0.0 && 1.0 / x < 0.0)) { dst[n++] = '-'; x = -x; }
+    const long long k = (long long)(x * 1000.0 + 0.5);
+    long long ip = k / 1000;
+    const int fp = (int)(k % 1000);
+    char tmp[24]; int t = 0;
+    do { tmp[t++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+    while (t) dst[n++] = tmp[--t];
+    dst[n++] = '.';
+    dst[n++] = (char)('0' + fp / 100);
+    if (fp % 100) { dst[n++] = (char)('0' + fp / 10 % 10); if (fp % 10) dst[n++] = (char)('0' + fp % 10); }
     return n;
 }
 
@@ -90,6 +106,21 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
     *n_entries = n; *total_seq = tot;
     if (!fill || overflow || n > cap_entries) return SQRN_E_CAPACITY;
     seq_offsets[n] = tot;
+    return SQRN_OK;
+}
+
+// UnAlign (seq.py:236-255) of every parsed sequence in one pass: the symbols without the gap characters
+// "-.~" and their CSR offsets (what the prediction runs on).  sym must hold seq_offsets[n] bytes.
+extern "C" int sqrn_text_ungap(int64_t n, const int64_t *seq_offsets, const uint8_t *seq, int64_t *sym_offsets, uint8_t *sym)
+{
+    if (n < 0 || !seq_offsets || !seq || !sym_offsets || !sym) return SQRN_E_BADARG;
+    int64_t w = 0;
+    sym_offsets[0] = 0;
+    for (int64_t k = 0; k < n; k++) {
+        for (int64_t c = seq_offsets[k]; c < seq_offsets[k + 1]; c++)
+            if (!is_gap(seq[c])) sym[w++] = seq[c];
+        sym_offsets[k + 1] = w;
+    }
     return SQRN_OK;
 }
 

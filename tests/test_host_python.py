@@ -221,3 +221,42 @@ def test_bulk_text_format_matches_the_entry_printer():
     assert got == want.getvalue()
     part = _lib.text_format(parsed, 7, 5, sym_off, dbn, scores, 2, "fastestG").decode()
     assert part in got and part.startswith(">seq7")
+
+
+def test_bulk_text_numbers_print_like_python():
+    """scores are round(x, 3) values; the bulk formatter must print them as Python's print() does
+    (shortest repr): integer-arithmetic digits in csrc/sqrn_textio.cpp against repr() on many magnitudes"""
+    import random
+    import numpy as np
+    from squarna_b200 import _lib
+    rng = random.Random(7)
+    vals = [0.0, -0.0, 0.001, -0.001, 0.5, 1.0, 12.0, 100.0, 187.935, 999.999, 1000.0, 123456.789, 1e9 + 0.125, 4.0e12 - 1, 5e12,
+            0.1, 0.01, 0.07, 2.675, 1.005, 99999999.999]
+    for _ in range(30000):
+        mag = rng.choice([1, 10, 1000, 1e5, 1e8])
+        vals.append(round(rng.uniform(-mag, mag), 3))
+    vals = [round(v, 3) for v in vals]
+    n = len(vals)
+    text = ("".join(">s\nA\n" for _ in range(n))).encode()
+    parsed = _lib.text_parse(text, False)
+    sym, sym_off = _lib.text_ungap(parsed)
+    assert bytes(sym) == b"A" * n and sym_off[-1] == n
+    scores = np.zeros((n, 3))
+    scores[:, 0] = vals
+    scores[:, 1] = 1.0
+    scores[:, 2] = vals[::-1]
+    out = _lib.text_format(parsed, 0, n, sym_off, np.full(n, ord("."), np.uint8), scores, 1, "x").decode().split("\n")
+    lines = [ln for ln in out if "\t#1\t" in ln]
+    assert len(lines) == n
+    for k, ln in enumerate(lines):
+        f = ln.split("\t")
+        assert f[2] == repr(float(vals[k])) and f[4] == repr(float(vals[n - 1 - k])), (vals[k], f)
+
+
+def test_bulk_text_ungap_matches_unalign():
+    from squarna_b200 import _lib
+    text = b">a\nAC-G.U~A\n>b\n---\n>c\nacgu\n"
+    parsed = _lib.text_parse(text, False)
+    sym, off = _lib.text_ungap(parsed)
+    want = [S.UnAlign(s, "." * len(s))[0] for s in ("AC-G.U~A", "---", "acgu")]
+    assert [bytes(sym[off[k]:off[k + 1]]).decode() for k in range(3)] == want
