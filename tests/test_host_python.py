@@ -260,3 +260,36 @@ def test_bulk_text_ungap_matches_unalign():
     sym, off = _lib.text_ungap(parsed)
     want = [S.UnAlign(s, "." * len(s))[0] for s in ("AC-G.U~A", "---", "acgu")]
     assert [bytes(sym[off[k]:off[k + 1]]).decode() for k in range(3)] == want
+
+
+def test_bulk_lane_glue_without_a_gpu(tmp_path, monkeypatch):
+    """the Python glue of the CLI bulk lane (parse -> ungap -> predict -> format) with the GPU call stubbed out:
+    the text must be what the per-entry printer writes for the same (stub) prediction"""
+    import numpy as np
+
+    class Stub:
+        def fast_predict(self, ps, sym, off):
+            n = len(off) - 1
+            dbn = np.full(len(sym), ord("."), np.uint8)
+            for k in range(n):                       # a hairpin where there is room, so that gaps get re-inserted into brackets
+                if off[k + 1] - off[k] >= 8:
+                    dbn[off[k]] = ord("(")
+                    dbn[off[k + 1] - 1] = ord(")")
+            return dbn, np.tile([1.5, 3.0, 0.5], (n, 1)), np.ones(n, np.int32)
+
+    monkeypatch.setattr(S, "get_context", lambda device=0: Stub())
+    path = tmp_path / "in.fa"
+    path.write_text(">a x\nACG-UACGU.A\n>b\nGGGG comment\n>c\nacgu~acguacgu\n")
+    buf = io.StringIO()
+    assert CLI._bulk_lane(str(path), False, "fastestG", {"dummy": 1}, 1, buf)
+    want = io.StringIO()
+    for name, seq in ((">a x", "ACG-UACGU.A"), (">b", "GGGG"), (">c", "acgu~acguacgu")):
+        short = "".join(ch for ch in seq if ch not in S.GAPS)
+        d = "." * len(short) if len(short) < 8 else "(" + "." * (len(short) - 2) + ")"
+        long_dbn = S.ReAlign(d, seq)
+        S._print_entry(name, seq, None, None, None, 3, want)
+        S._print_prediction((long_dbn, [(long_dbn, (1.5, 3.0, 0.5), [0])], [math.nan] * 6, [math.nan] * 7),
+                            seq, None, None, ["fastestG"], 1, 1, want)
+    assert buf.getvalue() == want.getvalue()
+    (tmp_path / "other.fa").write_text(">a\nACGU\n((..))\n")
+    assert CLI._bulk_lane(str(tmp_path / "other.fa"), False, "fastestG", {"dummy": 1}, 1, io.StringIO()) is False
