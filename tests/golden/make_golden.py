@@ -199,6 +199,21 @@ def algos_golden():
             ent.append({"conf": conf, "seq": seq, "reacts": reacts, "restraints": rest,
                         "interchainonly": kw["interchainonly"], "entropy": out})
     dump("entropy.json", ent)
+    # the same with an alignment-derived stem matrix (step 2 of the alignment mode, seq.py:1031-1034, 1084-1085)
+    smat_cases = []
+    names, psets = RC.ParseConfig(os.path.join(REF, "nobpp.conf"))
+    for _ in range(30):
+        seq, reacts, rest, kw = rand_case(rng, 8, 60)
+        n = len(seq)
+        m = np.array([[rng.randrange(0, 21) / 4.0 for _ in range(n)] for _ in range(n)])
+        smat = ((m + m.T) / 2).tolist()
+        try:
+            out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=100, stemmatrix=np.array(smat), **kw)
+        except ZeroDivisionError:
+            continue
+        smat_cases.append({"conf": "nobpp", "poollim": 100, "seq": seq, "reacts": reacts, "restraints": rest, "kw": kw,
+                           "smat": smat, "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+    dump("algos_smat.json", smat_cases)
 
 
 if __name__ == "__main__" and "algos" in sys.argv[1:]:

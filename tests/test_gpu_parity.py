@@ -266,8 +266,10 @@ def test_non_greedy_algorithms_match_the_reference(gpu_ctx):
     from squarna_b200 import SQUARNA as CLI
     here = os.path.dirname(os.path.abspath(__file__))
     pkg = os.path.dirname(os.path.abspath(CLI.__file__))
-    with open(os.path.join(here, "golden", "algos.json")) as f:
-        cases = json.load(f)
+    cases = []
+    for name in ("algos.json", "algos_smat.json"):              # the second file: with an alignment-derived stem matrix
+        with open(os.path.join(here, "golden", name)) as f:
+            cases += json.load(f)
     confs = {}
     bad = []
     for c in cases:
@@ -277,6 +279,8 @@ def test_non_greedy_algorithms_match_the_reference(gpu_ctx):
         if "priority" in kw:
             kw["priority"] = set(kw["priority"])
         kw["rankby"] = tuple(kw["rankby"])
+        if c.get("smat") is not None:
+            kw["stemmatrix"] = np.array(c["smat"])
         got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, confs[c["conf"]], poollim=c["poollim"], **kw)
         want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
         if not T.same_prediction((got[0], got[1]), want):

@@ -293,3 +293,67 @@ def test_bulk_lane_glue_without_a_gpu(tmp_path, monkeypatch):
     assert buf.getvalue() == want.getvalue()
     (tmp_path / "other.fa").write_text(">a\nACGU\n((..))\n")
     assert CLI._bulk_lane(str(tmp_path / "other.fa"), False, "fastestG", {"dummy": 1}, 1, io.StringIO()) is False
+
+
+class _OracleContext:
+    """stands in for the GPU context in CPU tests of the host logic: AnnotateStems and the greedy structures come
+    from the oracle (which the -m gpu tests prove bit-identical to the kernels)"""
+
+    def yield_stems(self, ps, b):
+        import numpy as np
+        from oracle import oracle as O
+        out = []
+        for k in b["idx"]:
+            p = b["preps"][k]
+            smat = None
+            if b["stemmatrix"] is not None:
+                keep = p.keep
+                smat = np.asarray(b["stemmatrix"], dtype=np.float64)[np.ix_(keep, keep)]
+            st = O.annotate(p.shortseq, ps, p.shortreacts, p.shortrest, (), b["interchainonly"], smat)
+            out.append((np.array([s[:3] for s in st], dtype=np.int32).reshape(-1, 3), np.array([s[3] for s in st])))
+        return out
+
+    def predict_batch(self, paramsets, b):
+        import numpy as np
+        from oracle import oracle as O
+        out = []
+        for k in b["idx"]:
+            p = b["preps"][k]
+            smat = None
+            if b["stemmatrix"] is not None:
+                keep = p.keep
+                smat = np.asarray(b["stemmatrix"], dtype=np.float64)[np.ix_(keep, keep)]
+            o = b["opts"]
+            cons, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, list(paramsets), b["interchainonly"],
+                                               o.get("poollim", 1000), smat, o.get("rankby", (0, 2, 1)), (), False, 1, False,
+                                               b["comp"])
+            out.append((None, [(None, sc, isint, 1, np.array(stems, dtype=np.int32).reshape(-1, 3))
+                               for _d, sc, isint, _psl, stems, *_ in structs], len(structs)))
+        return out
+
+
+def test_non_greedy_parameter_sets_on_the_host(monkeypatch):
+    """_predict_many_mixed (Nussinov / Hungarian / Edmonds builders, RunAlgo, de-duplication across parameter sets,
+    RankStructs, consensus, hardrest, level limit, alignment weighting) against the 160 cases of tests/golden/algos.json
+    and algos_smat.json made by the real reference, with the oracle supplying what the GPU supplies in the -m gpu version of this test"""
+    monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
+    monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
+                        dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
+    from tests import common as T
+    import numpy as np
+    confs, bad = {}, []
+    cases = load("algos.json") + load("algos_smat.json")        # the second file: with an alignment-derived stem matrix
+    for c in cases:
+        if c["conf"] not in confs:
+            confs[c["conf"]] = CLI.ParseConfig(os.path.join(PKG, c["conf"] + ".conf"))[1]
+        kw = dict(c["kw"])
+        if "priority" in kw:
+            kw["priority"] = set(kw["priority"])
+        kw["rankby"] = tuple(kw["rankby"])
+        if c.get("smat") is not None:
+            kw["stemmatrix"] = np.array(c["smat"])
+        got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, confs[c["conf"]], poollim=c["poollim"], **kw)
+        want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+        if not T.same_prediction((got[0], got[1]), want):
+            bad.append((c["conf"], c["seq"], c["kw"]))
+    assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
