@@ -240,7 +240,7 @@ def main():
     dev_ms, _ = timed(step_device, args.steps)
     # per-launch kernel time: one launch per step on this path
     kern_ms = dev_ms / args.steps
-    launches = args.steps * 1
+    launches = args.steps * 2          # per step of the timed (device-resident) leg: k_fast<224> + k_fast_rescan<224> behind it
     for _ in range(2):
         step_host()
     _, e2e_wall_ms = timed(step_host, args.steps)
