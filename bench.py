@@ -238,7 +238,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     dev_ms, _ = timed(step_device, args.steps)
-    # per-launch kernel time: one launch per step on this path
+    # kernel time per step: one k_fast launch (the k_fast_rescan launch behind it finds an empty overflow list)
     kern_ms = dev_ms / args.steps
     launches = args.steps * 2          # per step of the timed (device-resident) leg: k_fast<224> + k_fast_rescan<224> behind it
     for _ in range(2):

@@ -357,3 +357,17 @@ def test_non_greedy_parameter_sets_on_the_host(monkeypatch):
         if not T.same_prediction((got[0], got[1]), want):
             bad.append((c["conf"], c["seq"], c["kw"]))
     assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+
+
+def test_bench_helpers_without_a_gpu(monkeypatch):
+    """bench.py pieces that do not need a device: workload generator, algorithmic bytes, and the
+    best-effort CPU binding of multi-GPU ranks, which must leave the affinity alone when NVML is not usable"""
+    import bench
+    sym, off, lens = bench.make_batch(1000, bench.SEED)
+    assert off[0] == 0 and off[-1] == len(sym) == lens.sum() and lens.min() >= 60 and lens.max() <= 200
+    assert set(bytes(sym[:200])) <= set(b"ACGU")
+    assert bench.algorithmic_bytes(lens) == int(sum((n + 3) // 4 + 8 + (n + 32) + n for n in lens.tolist()))
+    before = os.sched_getaffinity(0)
+    assert bench.bind_near_gpu(0) is None or os.sched_getaffinity(0) <= before
+    monkeypatch.setenv("SQRN_BENCH_NO_BIND", "1")
+    assert bench.bind_near_gpu(0) is None
