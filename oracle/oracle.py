@@ -175,9 +175,10 @@ def _ptr(a):
 
 def predict_short(shortseq, shortreacts, shortrest, paramsets, interchainonly=False, poollim=1000,
                   smat=None, rankby=(0, 2, 1), priority=(), rankbydiff=False, conslim=1,
-                  hardrest=False, compensated_sum=False):
+                  hardrest=False, compensated_sum=False, raw_codes=False):
     """Greedy prediction on an ungapped, normalised sequence.  Returns
-    (cons_dbn, [ (dbn, scores3, struct_is_int0, [paramset idx], stems[(i,j,len)], bpscores, finscores) ], ncalls)."""
+    (cons_dbn, [ (dbn, scores3, struct_is_int0, [paramset idx], stems[(i,j,len)], bpscores, finscores) ], ncalls).
+    raw_codes: the dbns as signed pseudoknot-level codes (+L opening, -L closing, 0 unpaired) instead of strings."""
     L = lib()
     N = len(shortseq)
     ps = _PS(paramsets)
@@ -204,13 +205,13 @@ def predict_short(shortseq, shortreacts, shortrest, paramsets, interchainonly=Fa
             dbn = np.zeros(max(N, 1), dtype=np.int32)
             L.orc_result_get(R, k, _ptr(stems), _ptr(bpsc), _ptr(finsc), _ptr(sc), C.byref(isint),
                              C.byref(mask), _ptr(dbn))
-            out.append((codes_to_dbn(dbn[:N]), tuple(float(x) for x in sc), bool(isint.value),
+            out.append((dbn[:N].astype(np.int8) if raw_codes else codes_to_dbn(dbn[:N]), tuple(float(x) for x in sc), bool(isint.value),
                         [p for p in range(64) if mask.value >> p & 1],
                         [tuple(int(x) for x in row) for row in stems[:ns]],
                         bpsc[:ns].tolist(), finsc[:ns].tolist()))
         cons = np.zeros(max(N, 1), dtype=np.int32)
         L.orc_result_cons(R, _ptr(cons))
-        return codes_to_dbn(cons[:N]), out, L.orc_result_ncalls(R)
+        return (cons[:N].astype(np.int8) if raw_codes else codes_to_dbn(cons[:N])), out, L.orc_result_ncalls(R)
     finally:
         L.orc_result_free(R)
 

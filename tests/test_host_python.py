@@ -324,11 +324,13 @@ class _OracleContext:
                 keep = p.keep
                 smat = np.asarray(b["stemmatrix"], dtype=np.float64)[np.ix_(keep, keep)]
             o = b["opts"]
+            prio = [q for q in range(len(paramsets)) if o.get("priority_mask", 0) >> q & 1]
             cons, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, list(paramsets), b["interchainonly"],
-                                               o.get("poollim", 1000), smat, o.get("rankby", (0, 2, 1)), (), False, 1, False,
-                                               b["comp"])
-            out.append((None, [(None, sc, isint, 1, np.array(stems, dtype=np.int32).reshape(-1, 3))
-                               for _d, sc, isint, _psl, stems, *_ in structs], len(structs)))
+                                               o.get("poollim", 1000), smat, o.get("rankby", (0, 2, 1)), prio,
+                                               o.get("rankbydiff", False), o.get("conslim", 1), o.get("hardrest", False),
+                                               b["comp"], raw_codes=True)
+            out.append((cons, [(codes, sc, isint, sum(1 << q for q in psl), np.array(stems, dtype=np.int32).reshape(-1, 3))
+                               for codes, sc, isint, psl, stems, *_ in structs], len(structs)))
         return out
 
 
@@ -371,3 +373,32 @@ def test_bench_helpers_without_a_gpu(monkeypatch):
     assert bench.bind_near_gpu(0) is None or os.sched_getaffinity(0) <= before
     monkeypatch.setenv("SQRN_BENCH_NO_BIND", "1")
     assert bench.bind_near_gpu(0) is None
+
+
+def test_sqrndbnseq_host_python_on_the_reference_cases(monkeypatch):
+    """squarna_b200.SQRNdbnseq.SQRNdbnseq -- _prepare (gaps, separators, restraints, reactivity decoding), the result
+    assembly (level codes -> glyphs, ReAlign, separators, paramset lists, int-0 score) -- on the end-to-end cases of
+    tests/golden/seq_api.json made by the real reference, with the oracle standing in for the GPU call"""
+    import numpy as np
+    from tests import common as T
+    monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
+    monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
+                        dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
+    confs, bad = {}, []
+    cases = load("seq_api.json")
+    for c in cases:
+        if c["conf"] not in confs:
+            psets = CLI.ParseConfig(os.path.join(PKG, c["conf"] + ".conf"))[1]
+            confs[c["conf"]] = [p for p in psets if p["algorithms"] == {"G"} and not p["bpp"]]
+        kw = dict(c["kw"])
+        if "priority" in kw:
+            kw["priority"] = set(kw["priority"])
+        kw["rankby"] = tuple(kw["rankby"])
+        if c.get("smat") is not None:
+            kw["stemmatrix"] = np.array(c["smat"])
+        got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, confs[c["conf"]], poollim=c["poollim"],
+                           algos={"G"}, **kw)
+        want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+        if not T.same_prediction((got[0], got[1]), want):
+            bad.append((c["conf"], c["seq"], c["kw"]))
+    assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
