@@ -402,3 +402,67 @@ def test_sqrndbnseq_host_python_on_the_reference_cases(monkeypatch):
         if not T.same_prediction((got[0], got[1]), want):
             bad.append((c["conf"], c["seq"], c["kw"]))
     assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+
+
+def _oracle_yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=0):
+    """SQRNdbnali._yield_many with the oracle's AnnotateStems in place of the GPU call"""
+    import numpy as np
+    from oracle import oracle as O
+    out = []
+    ps = dict(bpweights=bpweights, minlen=minlen, minbpscore=minbpscore)
+    for seq, reacts, rests in entries:
+        seq = seq.upper().replace("T", "U")
+        shortseq, shortrest = S.UnAlign(seq, rests if rests else "." * len(seq))
+        keep = [k for k, ch in enumerate(seq) if ch not in S.GAPS]
+        shortreacts = [reacts[k] for k in keep] if reacts else None
+        st = O.annotate(shortseq, ps, shortreacts, shortrest, (), interchainonly, None)
+        out.append((np.array(keep, dtype=np.int32), np.array([s[:3] for s in st], dtype=np.int32).reshape(-1, 3),
+                    np.array([s[3] for s in st], dtype=np.float64)))
+    return out
+
+
+def _oracle_fast_predict(self, paramset, symbols, offsets):
+    import numpy as np
+    from oracle import oracle as O
+    codes, scores, nst = O.predict_batch_simple(symbols, offsets, [paramset], poollim=1, nthreads=4)
+    glyph_o, glyph_c = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ", ")]}>abcdefghijklmnopqrstuvwxyz"
+    lut = {0: ord(".")}
+    for lv in range(1, 31):
+        lut[lv], lut[-lv] = ord(glyph_o[lv - 1]), ord(glyph_c[lv - 1])
+    dbn = np.array([lut[int(c)] for c in codes.tolist()], dtype=np.uint8)
+    seps = (symbols == ord(";")) | (symbols == ord("&"))          # the kernel puts separators back itself
+    dbn[seps] = symbols[seps]
+    return dbn, scores.reshape(-1, 3), nst
+
+
+with open(os.path.join(G, "cli_manifest.json")) as _f:
+    _CLI_RUNS = json.load(_f)
+
+
+@pytest.mark.parametrize("name", sorted(_CLI_RUNS))
+def test_cli_text_with_the_oracle_standing_in_for_the_gpu(name, monkeypatch):
+    """the whole host side of the CLI (option handling, parsers, batching, bulk lane, alignment mode, Nussinov /
+    Hungarian / Edmonds sets, printing) against the reference's own text (tests/golden/cli/*.txt); the -m gpu
+    version of this test (tests/test_gpu_cli.py) runs the same commands on the kernels"""
+    from squarna_b200 import SQRNdbnali as A
+    _OracleContext.fast_predict = _oracle_fast_predict
+    monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
+    monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
+                        dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
+    monkeypatch.setattr(A, "_yield_many", _oracle_yield_many)
+    buf = io.StringIO()
+    cwd = os.getcwd()
+    os.chdir(G)
+    try:
+        with contextlib.redirect_stdout(buf):
+            CLI.Main(_CLI_RUNS[name])
+    finally:
+        os.chdir(cwd)
+    with open(os.path.join(G, "cli", name + ".txt")) as f:
+        want = f.read()
+    got = buf.getvalue()
+    if got != want:
+        gl, wl = got.split("\n"), want.split("\n")
+        for k, (a, b) in enumerate(zip(gl, wl)):
+            assert a == b, "first difference at line %d of %s" % (k + 1, name)
+        assert len(gl) == len(wl)
