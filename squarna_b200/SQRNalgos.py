@@ -82,36 +82,44 @@ def Nussinov(seq, stems, N, seps, minloop=3, matrix=None):
     return BackTrack(0, N - 1, K, minloop, seq, seps)
 
 
+def _weighted_pairs(stems, power, matrix):
+    """(v, w, weight) of every candidate pair, weight = score ** power: the pairs of the stems in stem order, or the
+    positive upper-triangle cells of a score matrix in row-major order"""
+    if matrix is not None:
+        vs, ws = np.nonzero(np.triu(np.asarray(matrix) > 0, 1))
+        return [(int(v), int(w), matrix[v, w] ** power) for v, w in zip(vs.tolist(), ws.tolist())]
+    return [(v, w, sc ** power) for (v, w), sc in _pair_scores(stems).items()]
+
+
 def Edmonds(stems, power=1.7, matrix=None):
     """maximum-weight matching of the graph whose edges are the stem pairs, weight = (stem score) ** 1.7
     (SQRNalgos.py:96-110); edges enter the graph in stem order, which is what ties are broken by"""
-    import networkx as nx
-    if matrix is None:
-        edges = [(v, w, sc ** power) for (v, w), sc in _pair_scores(stems).items()]
-    else:
-        n = matrix.shape[0]
-        edges = [(v, w, matrix[v, w] ** power) for v in range(n - 1) for w in range(v + 1, n) if matrix[v, w] > 0]
-    graph = nx.Graph()
-    graph.add_weighted_edges_from(edges)
-    return sorted(nx.max_weight_matching(graph))
+    from networkx import Graph, max_weight_matching
+    graph = Graph()
+    graph.add_weighted_edges_from(_weighted_pairs(stems, power, matrix))
+    return sorted(max_weight_matching(graph))
 
 
 def Hungarian(seq, stems, N, seps, minloop=3, power=1.7, matrix=None):
     """assignment problem on the symmetric N x N matrix of -(stem score) ** 1.7; a pair (k, l) is kept when the
     assignment is mutual, the cell is non-zero and the hairpin rule holds (SQRNalgos.py:113-136)"""
     from scipy.optimize import linear_sum_assignment
-    if matrix is None:
-        cost = np.zeros((N, N))
-        for (v, w), sc in _pair_scores(stems).items():
-            cost[v, w] = cost[w, v] = -(sc ** power)
-    else:
+    if matrix is not None:
         cost = -(matrix ** power)
+    else:
+        cost = np.zeros((N, N))
+        trip = _weighted_pairs(stems, power, None)
+        if trip:
+            vs, ws, wt = (np.array(x) for x in zip(*trip))
+            cost[vs, ws] = -wt
+            cost[ws, vs] = -wt
     rows, cols = linear_sum_assignment(cost)
-    mate = dict(zip(rows.tolist(), cols.tolist()))
-    pairs = []
-    for k, l in mate.items():
-        if not (k < l - minloop or (k < l and _has_sep(seq, k + 1, l, seps))):
-            continue
-        if mate.get(l) == k and cost[k, l] != 0:
-            pairs.append((k, l))
-    return pairs
+    partner = np.full(N, -1, dtype=np.int64)
+    partner[rows] = cols
+    out = []
+    for k in rows.tolist():                              # row order, as the reference's dict of the assignment
+        l = int(partner[k])
+        far_enough = k < l - minloop or (k < l and _has_sep(seq, k + 1, l, seps))
+        if far_enough and partner[l] == k and cost[k, l] != 0:
+            out.append((k, l))
+    return out
