@@ -5,6 +5,7 @@
     python tests/golden/make_golden.py          # JSON vectors
     python tests/golden/make_golden.py cli      # CLI text of the reference on tests/golden/inputs/
     python tests/golden/make_golden.py algos    # SQRNdbnseq with the Nussinov / Hungarian / Edmonds parameter sets
+    python tests/golden/make_golden.py long     # SQRNdbnseq on 321 .. 1200 nt sequences (minutes)
 
 The reference cannot travel to the GPU box, so its outputs are committed here as
 JSON fixtures; tests/test_oracle_golden.py pins the CPU oracle (and the host-side
@@ -215,6 +216,31 @@ def algos_golden():
                            "smat": smat, "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
     dump("algos_smat.json", smat_cases)
 
+
+def long_golden():
+    """SQRNdbnseq end to end on sequences of 321 .. 1200 nt (the lengths the CTA-team kernels serve): pins the
+    oracle, and through it the kernels, where the reference needs seconds to minutes per case"""
+    import time
+    rng = random.Random(20261020)
+    plan = [("fastest", 1, 330, 520, 6), ("1000nobpp", 1, 330, 420, 3), ("greedynobpp", 3, 321, 360, 2),
+            ("fastest", 1, 600, 1200, 5), ("1000nobpp", 1, 500, 900, 4), ("500nobpp", 3, 500, 620, 2),
+            ("greedynobpp", 5, 330, 420, 2)]
+    cases = []
+    for conf, pl, lo, hi, count in plan:
+        psets = gsets(conf)
+        for _ in range(count):
+            seq, reacts, rest, kw = rand_case(rng, lo, hi)
+            t0 = time.time()
+            out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=pl, algos={"G"}, **kw)
+            print(conf, len(seq), "%.1f s" % (time.time() - t0), flush=True)
+            cases.append({"conf": conf, "poollim": pl, "seq": seq, "reacts": reacts, "restraints": rest, "kw": kw,
+                          "smat": None, "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+    dump("seq_api_long.json", cases)
+
+
+if __name__ == "__main__" and "long" in sys.argv[1:]:
+    long_golden()
+    sys.exit(0)
 
 if __name__ == "__main__" and "algos" in sys.argv[1:]:
     algos_golden()

@@ -31,11 +31,13 @@ def _gsets(configs, conf):
     return [_ps(p) for p in configs[conf]["paramsets"] if p["algorithms"] == ["G"] and p["bpp"] == 0]
 
 
-def test_seq_api(configs):
+@pytest.mark.parametrize("fname,least", [("seq_api.json", 250), ("seq_api_long.json", 20)], ids=["short", "321-1200nt"])
+def test_seq_api(configs, fname, least):
     """SQRNdbnseq end to end: consensus, every structure, its three scores (incl. the int-0
-    quirk) and its parameter-set list, in rank order"""
-    cases = load("seq_api.json")
-    assert len(cases) > 250
+    quirk) and its parameter-set list, in rank order.  The second file holds sequences of 321 .. 1137 nt,
+    the lengths the CTA-team kernels serve."""
+    cases = load(fname)
+    assert len(cases) > least
     for c in cases:
         kw = dict(c["kw"])
         kw["rankby"] = tuple(kw["rankby"])
