@@ -6,6 +6,7 @@
     python tests/golden/make_golden.py cli      # CLI text of the reference on tests/golden/inputs/
     python tests/golden/make_golden.py algos    # SQRNdbnseq with the Nussinov / Hungarian / Edmonds parameter sets
     python tests/golden/make_golden.py long     # SQRNdbnseq on 321 .. 1200 nt sequences (minutes)
+    python tests/golden/make_golden.py xlong    # three sequences of 2050 .. 2500 nt (tens of minutes)
 
 The reference cannot travel to the GPU box, so its outputs are committed here as
 JSON fixtures; tests/test_oracle_golden.py pins the CPU oracle (and the host-side
@@ -237,6 +238,27 @@ def long_golden():
                           "smat": None, "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
     dump("seq_api_long.json", cases)
 
+
+def xlong_golden():
+    """three plain sequences of 2050 .. 2500 nt (the 1024-thread CTA / cluster kernels): tens of minutes in the reference"""
+    import time
+    rng = random.Random(20261021)
+    cases = []
+    for conf, n in (("fastest", 2100), ("fastest", 2500), ("1000nobpp", 2050)):
+        psets = gsets(conf)
+        seq = rand_seq(rng, n)
+        t0 = time.time()
+        out = R.SQRNdbnseq(seq, None, None, None, psets, mp=False, poollim=1, algos={"G"})
+        print(conf, n, "%.0f s" % (time.time() - t0), flush=True)
+        cases.append({"conf": conf, "poollim": 1, "seq": seq, "reacts": None, "restraints": None,
+                      "kw": {"rankby": [0, 2, 1]}, "smat": None, "cons": out[0],
+                      "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+        dump("seq_api_xlong.json", cases)
+
+
+if __name__ == "__main__" and "xlong" in sys.argv[1:]:
+    xlong_golden()
+    sys.exit(0)
 
 if __name__ == "__main__" and "long" in sys.argv[1:]:
     long_golden()

@@ -203,3 +203,22 @@ def test_glist_cached_scores_under_pseudoknots():
             _, structs, _ = O.predict_short(seqs[k], [0.5] * len(seqs[k]), "." * len(seqs[k]), [ps], poollim=1)
             sa = [tuple(int(x) for x in a["stems"][a["off"][k] + q]) for q in range(a["n"][k])]
             assert sa == structs[0][4]
+
+
+@pytest.mark.parametrize("flavour", [5, 2], ids=["global-list", "rescan"])
+def test_device_code_on_rrna_scale_reference_cases(flavour):
+    """the device functions (host emulation) on the reference's OWN results for plain sequences of 2050 .. 2500 nt
+    (tests/golden/seq_api_xlong.json): the global candidate list with cached scores, and the rescanning pass"""
+    from squarna_b200 import SQUARNA as CLI
+    pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+    with open(os.path.join(G, "seq_api_xlong.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        if flavour == 2 and c["conf"] != "fastest":
+            continue                                  # minlen 2 at 2050 nt: minutes in the single-thread rescanning build
+        ps = [p for p in CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1] if p["algorithms"] == {"G"} and not p["bpp"]][0]
+        r = emu.run(ps, [c["seq"]], ccap=4096, flavour=flavour, pcap=1 << 21)
+        dbn, sc, _psl = c["structs"][0]
+        assert bytes(r["dbn_ascii"][:len(c["seq"])]).decode() == dbn == c["cons"]
+        got = tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][0])
+        assert got == tuple(float(x) for x in sc)
