@@ -333,3 +333,28 @@ def test_long_reference_cases(gpu_ctx):
         if not T.same_prediction((got[0], got[1]), want):
             bad.append((c["conf"], len(c["seq"]), c["kw"]))
     assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+
+
+@pytest.mark.parametrize("cluster", [0, 1], ids=["clusters", "one-cta-each"])
+def test_rrna_scale_reference_cases(gpu_ctx, cluster):
+    """plain sequences of 2050 .. 2500 nt against the real reference's own output (tests/golden/seq_api_xlong.json,
+    minutes each in the reference): thread-block clusters sharing one candidate list, and one 1024-thread CTA each"""
+    import json
+    import os
+    from squarna_b200 import SQUARNA as CLI
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+    with open(os.path.join(here, "golden", "seq_api_xlong.json")) as f:
+        cases = json.load(f)
+    try:
+        gpu_ctx.set_cluster(cluster)
+        for c in cases:
+            ps = [p for p in CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1]
+                  if p["algorithms"] == {"G"} and not p["bpp"]][0]
+            sym, off = pack_sequences([c["seq"]])
+            dbn, scores, _nst = gpu_ctx.fast_predict(ps, sym, off)
+            want_dbn, want_sc, _ = c["structs"][0]
+            assert bytes(dbn).decode() == want_dbn == c["cons"]
+            assert tuple(float(x) for x in scores[0]) == tuple(float(x) for x in want_sc)
+    finally:
+        gpu_ctx.set_cluster(0)
