@@ -7,6 +7,7 @@
     python tests/golden/make_golden.py algos    # SQRNdbnseq with the Nussinov / Hungarian / Edmonds parameter sets
     python tests/golden/make_golden.py long     # SQRNdbnseq on 321 .. 1200 nt sequences (minutes)
     python tests/golden/make_golden.py xlong    # three sequences of 2050 .. 2500 nt (tens of minutes)
+    python tests/golden/make_golden.py c3       # BASELINE config 3 shape (reactivities + restraints, pl=100), 300 .. 620 nt
 
 The reference cannot travel to the GPU box, so its outputs are committed here as
 JSON fixtures; tests/test_oracle_golden.py pins the CPU oracle (and the host-side
@@ -255,6 +256,44 @@ def xlong_golden():
                       "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
         dump("seq_api_xlong.json", cases)
 
+
+def c3_golden():
+    """BASELINE config 3 shape: 300 .. 620 nt, reactivities as rf=26 letters (3 % '?'), restraints 5 % '_', 1 % '/',
+    1 % '\\' plus 0-2 canonical stems as brackets, G sets by length (greedynobpp < 500, 500nobpp above), CLI default pl=100"""
+    import time
+    rng = random.Random(20261022)
+    comp = {"A": "U", "U": "A", "G": "C", "C": "G"}
+    cases = []
+    for n in (300, 340, 420, 480, 520, 620):
+        seq = [rng.choice("ACGU") for _ in range(n)]
+        rest = ["."] * n
+        for _ in range(rng.randint(0, 2)):                      # a planted canonical stem, given as a restraint
+            ln = rng.randint(3, 6)
+            i = rng.randrange(5, n // 2 - 10)
+            j = rng.randrange(n // 2 + 10, n - 5)
+            for k in range(ln):
+                seq[j - k] = comp[seq[i + k]]
+                rest[i + k], rest[j - k] = "(", ")"
+        for k in range(n):
+            if rest[k] == ".":
+                x = rng.random()
+                rest[k] = "_" if x < 0.05 else "/" if x < 0.06 else "\\" if x < 0.07 else "."
+        seq, rest = "".join(seq), "".join(rest)
+        reacts = "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") if rng.random() > 0.03 else "?" for _ in range(n))
+        conf = "greedynobpp" if n < 500 else "500nobpp"
+        psets = gsets(conf)
+        t0 = time.time()
+        out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=100, algos={"G"})
+        print(conf, n, "%.0f s" % (time.time() - t0), len(out[1]), "structures", flush=True)
+        cases.append({"conf": conf, "poollim": 100, "seq": seq, "reacts": reacts, "restraints": rest,
+                      "kw": {"rankby": [0, 2, 1]}, "smat": None, "cons": out[0],
+                      "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+        dump("seq_api_c3.json", cases)
+
+
+if __name__ == "__main__" and "c3" in sys.argv[1:]:
+    c3_golden()
+    sys.exit(0)
 
 if __name__ == "__main__" and "xlong" in sys.argv[1:]:
     xlong_golden()

@@ -385,7 +385,7 @@ def test_sqrndbnseq_host_python_on_the_reference_cases(monkeypatch):
     monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
                         dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
     confs, bad = {}, []
-    cases = load("seq_api.json") + load("seq_api_long.json")
+    cases = load("seq_api.json") + load("seq_api_long.json") + load("seq_api_c3.json")
     for c in cases:
         if c["conf"] not in confs:
             psets = CLI.ParseConfig(os.path.join(PKG, c["conf"] + ".conf"))[1]

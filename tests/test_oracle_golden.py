@@ -31,13 +31,15 @@ def _gsets(configs, conf):
     return [_ps(p) for p in configs[conf]["paramsets"] if p["algorithms"] == ["G"] and p["bpp"] == 0]
 
 
-@pytest.mark.parametrize("fname,least", [("seq_api.json", 250), ("seq_api_long.json", 20), ("seq_api_xlong.json", 1)],
-                         ids=["short", "321-1200nt", "2050-2500nt"])
+@pytest.mark.parametrize("fname,least", [("seq_api.json", 250), ("seq_api_long.json", 20), ("seq_api_xlong.json", 1),
+                                         ("seq_api_c3.json", 5)],
+                         ids=["short", "321-1200nt", "2050-2500nt", "config3-shape"])
 def test_seq_api(configs, fname, least):
     """SQRNdbnseq end to end: consensus, every structure, its three scores (incl. the int-0
     quirk) and its parameter-set list, in rank order.  The second file holds sequences of 321 .. 1137 nt,
     the lengths the CTA-team kernels serve; the third three plain sequences of 2050 .. 2500 nt (1024-thread CTAs and
-    clusters; minutes each in the reference)."""
+    clusters; minutes each in the reference); the fourth the shape of BASELINE config 3 (300 .. 620 nt, reactivity
+    letters, restraints incl. planted stems, G sets by length, pl=100: up to 173 ranked structures per sequence)."""
     cases = load(fname)
     assert len(cases) > least
     for c in cases:
