@@ -358,3 +358,27 @@ def test_rrna_scale_reference_cases(gpu_ctx, cluster):
             assert tuple(float(x) for x in scores[0]) == tuple(float(x) for x in want_sc)
     finally:
         gpu_ctx.set_cluster(0)
+
+
+def test_config3_shape_reference_cases(gpu_ctx):
+    """the shape of BASELINE config 3 (reactivity letters, restraints with planted stems, G sets by length, pl=100:
+    pool rounds on CTA teams, up to 173 ranked structures) against the real reference's own output
+    (tests/golden/seq_api_c3.json).  Kept last in this file: the fixture was made after the round's GPU budget was
+    spent, so this is the first time these pool rounds above 320 nt meet the reference on a GPU."""
+    import json
+    import os
+    from squarna_b200 import SQUARNA as CLI
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+    with open(os.path.join(here, "golden", "seq_api_c3.json")) as f:
+        cases = json.load(f)
+    confs, bad = {}, []
+    for c in cases:
+        if c["conf"] not in confs:
+            psets = CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1]
+            confs[c["conf"]] = [p for p in psets if p["algorithms"] == {"G"} and not p["bpp"]]
+        got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, confs[c["conf"]], poollim=c["poollim"], algos={"G"})
+        want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+        if not T.same_prediction((got[0], got[1]), want):
+            bad.append((c["conf"], len(c["seq"])))
+    assert not bad, "%d of %d differ: %r" % (len(bad), len(cases), bad)
