@@ -222,3 +222,25 @@ def test_device_code_on_rrna_scale_reference_cases(flavour):
         assert bytes(r["dbn_ascii"][:len(c["seq"])]).decode() == dbn == c["cons"]
         got = tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][0])
         assert got == tuple(float(x) for x in sc)
+
+
+@pytest.mark.parametrize("flavour", [5, 2], ids=["global-list", "rescan"])
+def test_device_code_on_long_reference_cases(flavour):
+    """the device functions (host emulation) on the reference's own results for 321 .. 1137 nt sequences with
+    restraints, reactivities, gaps and separators, single-path greedy (tests/golden/seq_api_long.json, pl = 1)"""
+    from squarna_b200 import SQUARNA as CLI
+    pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+    with open(os.path.join(G, "seq_api_long.json")) as f:
+        cases = [c for c in json.load(f) if c["poollim"] == 1 and not c["kw"]["hardrest"]]
+    assert len(cases) >= 8
+    for c in cases:
+        ps = [p for p in CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1] if p["algorithms"] == {"G"} and not p["bpp"]][0]
+        preps, kw = _prep_batch([(c["seq"], c["reacts"], c["restraints"])])
+        p = preps[0]
+        r = emu.run(ps, [p.shortseq], react_comp=p.compensated, interchainonly=c["kw"]["interchainonly"],
+                    ccap=4096, flavour=flavour, pcap=1 << 20, **kw)
+        short = bytes(r["dbn_ascii"][:len(p.shortseq)]).decode()
+        want_dbn, want_sc, _ = c["structs"][0]
+        assert S.ReAlign(short, p.seq) == want_dbn == c["cons"], (c["conf"], len(c["seq"]))
+        got = tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][0])
+        assert got == tuple(float(x) for x in want_sc) and bool(r["flags"][0] & 1) == (type(want_sc[1]) is int)
