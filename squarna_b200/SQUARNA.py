@@ -524,14 +524,15 @@ def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=0, slice
     except _lib.SqrnError:
         return False                                                 # e.g. more than 30 pseudoknot levels: general path
     binary = getattr(sink, "buffer", None)
+    scratch = []                                                     # one text buffer, reused by every slice
     for first in range(0, parsed.n, slice_entries):
         count = min(slice_entries, parsed.n - first)
-        block = _lib.text_format(parsed, first, count, sym_off, dbn, scores, conslim, psname)
+        block = _lib.text_format(parsed, first, count, sym_off, dbn, scores, conslim, psname, scratch)
         if binary is not None:
             sink.flush()
-            binary.write(block)
+            binary.write(memoryview(block))
         else:
-            sink.write(block.decode("ascii"))
+            sink.write(block.tobytes().decode("ascii"))
     return True
 
 

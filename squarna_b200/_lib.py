@@ -97,19 +97,32 @@ def text_ungap(parsed):
     return sym[:int(off[-1])], off
 
 
-def text_format(parsed, first, count, sym_offsets, dbn, scores, conslim, psname):
-    """bytes of the RunSQRNdbnseq text blocks of entries [first, first + count)"""
+def text_format(parsed, first, count, sym_offsets, dbn, scores, conslim, psname, scratch=None):
+    """the RunSQRNdbnseq text blocks of entries [first, first + count) as bytes; with `scratch` (a list holding a
+    reusable uint8 array, or empty) a view into that array is returned instead (no copy, no fresh pages per call)"""
     L = load()
     need = C.c_int64(0)
     scores = np.ascontiguousarray(scores, dtype=np.float64)
     args = (first, count, parsed.text, ptr(parsed.name_begin), ptr(parsed.name_len), ptr(parsed.seq_offsets),
             ptr(parsed.seq), ptr(sym_offsets), ptr(dbn), ptr(scores), int(conslim), psname.encode("ascii"))
-    L.sqrn_text_format(*args, None, 0, C.byref(need))
-    buf = np.empty(max(need.value, 1), np.uint8)
+    # an upper bound of the text size (three numbers of at most 24 characters per entry), so that one call does it
+    bound = int(parsed.name_len[first:first + count].sum()) + \
+        5 * int(parsed.seq_offsets[first + count] - parsed.seq_offsets[first]) + count * (len(psname) + 128)
+    if scratch is not None and scratch and len(scratch[0]) >= bound:
+        buf = scratch[0]
+    else:
+        buf = np.empty(max(bound, 1), np.uint8)
+        if scratch is not None:
+            scratch[:] = [buf]
     rc = L.sqrn_text_format(*args, ptr(buf), len(buf), C.byref(need))
+    if rc == E_CAPACITY:
+        buf = np.empty(max(need.value, 1), np.uint8)
+        if scratch is not None:
+            scratch[:] = [buf]
+        rc = L.sqrn_text_format(*args, ptr(buf), len(buf), C.byref(need))
     if rc != OK:
         raise SqrnError("sqrn_text_format failed (%d)" % rc)
-    return buf[:need.value].tobytes()
+    return buf[:need.value] if scratch is not None else buf[:need.value].tobytes()
 
 
 class PackedBatch:

@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 #include "../../include/sqrn.h"
 
 namespace {
@@ -124,57 +126,102 @@ extern "C" int sqrn_text_ungap(int64_t n, const int64_t *seq_offsets, const uint
     return SQRN_OK;
 }
 
+namespace {
+
+struct FormatJob {
+    const char *text; const int64_t *name_begin; const int32_t *name_len; const int64_t *seq_offsets; const uint8_t *seq;
+    const int64_t *sym_offsets; const uint8_t *dbn; const double *scores; const char *psname; size_t pl;
+    const char *cons; int cl;
+};
+
+// exact size of one entry's block
+inline int64_t block_size(const FormatJob &J, int64_t k)
+{
+    char tmp[48];
+    const int64_t L = J.seq_offsets[k + 1] - J.seq_offsets[k];
+    const double st = J.scores[3 * k + 1];
+    // name \n seq \n ____ \n dbn <cons> ==== \n dbn \t#1\t total \t struct \t react \t psname \n
+    return J.name_len[k] + 1 + 5 * L + 3 + J.cl + 4 + fmt3(tmp, J.scores[3 * k]) + 1 +
+           (st == 0.0 ? 1 : fmt3(tmp, st)) + 1 + fmt3(tmp, J.scores[3 * k + 2]) + 1 + (int64_t)J.pl + 1;
+}
+
+// writes the block of entry k at out; returns its size, or -1 if the dot-bracket string does not fit the sequence
+inline int64_t write_block(const FormatJob &J, int64_t k, char *out)
+{
+    const int64_t L = J.seq_offsets[k + 1] - J.seq_offsets[k];
+    const uint8_t *s = J.seq + J.seq_offsets[k];
+    const uint8_t *d = J.dbn + J.sym_offsets[k];
+    const int64_t nd = J.sym_offsets[k + 1] - J.sym_offsets[k];
+    int64_t w = 0;
+    memcpy(out + w, J.text + J.name_begin[k], (size_t)J.name_len[k]); w += J.name_len[k]; out[w++] = '\n';
+    memcpy(out + w, s, (size_t)L); w += L; out[w++] = '\n';
+    memset(out + w, '_', (size_t)L); w += L; out[w++] = '\n';
+    char *line = out + w;                       // the re-gapped dot-bracket line, written once and copied
+    int64_t q = 0;
+    for (int64_t c = 0; c < L; c++) {
+        if (is_gap(s[c])) line[c] = '.';
+        else { if (q >= nd) return -1; line[c] = (char)d[q++]; }
+    }
+    if (q != nd) return -1;
+    w += L;
+    memcpy(out + w, J.cons, (size_t)J.cl); w += J.cl;
+    memset(out + w, '=', (size_t)L); w += L; out[w++] = '\n';
+    memcpy(out + w, line, (size_t)L); w += L;
+    memcpy(out + w, "\t#1\t", 4); w += 4;
+    const double total = J.scores[3 * k], st = J.scores[3 * k + 1], re = J.scores[3 * k + 2];
+    w += fmt3(out + w, total); out[w++] = '\t';
+    if (st == 0.0) out[w++] = '0'; else w += fmt3(out + w, st);
+    out[w++] = '\t';
+    w += fmt3(out + w, re); out[w++] = '\t';
+    memcpy(out + w, J.psname, J.pl); w += (int64_t)J.pl; out[w++] = '\n';
+    return w;
+}
+
+}  // namespace
+
 // The text block of RunSQRNdbnseq (SQRNdbnseq.py:1301-1406) for entries [first, first + count) of a
 // parsed input whose prediction has ONE structure per sequence:
 //   name / sequence / '_' * L / dbn \t top-<conslim>_consensus / '=' * L / dbn \t #1 \t total \t struct \t react \t <psname>
 // seq_offsets + seq: the sequence tokens as parsed (gaps included); sym_offsets + dbn: the ungapped
 // CSR the prediction ran on and its dot-bracket bytes (gap columns print '.', ReAlign, seq.py:210-233;
 // separators were already put back by the kernel).  scores: 3 per sequence, already round(x, 3);
-// a structure score of exactly 0 prints as the int 0 (seq.py:871).
+// a structure score of exactly 0 prints as the int 0 (seq.py:871).  Two passes (exact block sizes, then the
+// text), each spread over a few host threads when there are many entries.
 extern "C" int sqrn_text_format(int64_t first, int64_t count, const char *text, const int64_t *name_begin,
                                 const int32_t *name_len, const int64_t *seq_offsets, const uint8_t *seq,
                                 const int64_t *sym_offsets, const uint8_t *dbn, const double *scores, int conslim,
                                 const char *psname, char *out, int64_t cap, int64_t *written)
 {
-    if (!text || !name_begin || !name_len || !seq_offsets || !seq || !sym_offsets || !dbn || !scores || !psname || !written)
+    if (!text || !name_begin || !name_len || !seq_offsets || !seq || !sym_offsets || !dbn || !scores || !psname || !written ||
+        count < 0)
         return SQRN_E_BADARG;
-    const size_t pl = strlen(psname);
     char cons[48];
-    const int cl = snprintf(cons, sizeof cons, "\ttop-%d_consensus\n", conslim);
-    int64_t w = 0;
-    // needed size first (cheap): per entry name + 5 L + fixed
-    int64_t need = 0;
-    for (int64_t k = first; k < first + count; k++)
-        need += name_len[k] + 5 * (seq_offsets[k + 1] - seq_offsets[k]) + 6 + cl + 4 + 3 * 32 + 5 + (int64_t)pl;
-    *written = need;
-    if (!out || cap < need) return SQRN_E_CAPACITY;
-    for (int64_t k = first; k < first + count; k++) {
-        const int64_t L = seq_offsets[k + 1] - seq_offsets[k];
-        const uint8_t *s = seq + seq_offsets[k];
-        const uint8_t *d = dbn + sym_offsets[k];
-        const int64_t nd = sym_offsets[k + 1] - sym_offsets[k];
-        memcpy(out + w, text + name_begin[k], (size_t)name_len[k]); w += name_len[k]; out[w++] = '\n';
-        memcpy(out + w, s, (size_t)L); w += L; out[w++] = '\n';
-        memset(out + w, '_', (size_t)L); w += L; out[w++] = '\n';
-        char *line = out + w;                       // the re-gapped dot-bracket line, written once and copied
-        int64_t q = 0;
-        for (int64_t c = 0; c < L; c++) {
-            if (is_gap(s[c])) line[c] = '.';
-            else { if (q >= nd) return SQRN_E_BADARG; line[c] = (char)d[q++]; }
-        }
-        if (q != nd) return SQRN_E_BADARG;
-        w += L;
-        memcpy(out + w, cons, (size_t)cl); w += cl;
-        memset(out + w, '=', (size_t)L); w += L; out[w++] = '\n';
-        memcpy(out + w, line, (size_t)L); w += L;
-        memcpy(out + w, "\t#1\t", 4); w += 4;
-        const double total = scores[3 * k], st = scores[3 * k + 1], re = scores[3 * k + 2];
-        w += fmt3(out + w, total); out[w++] = '\t';
-        if (st == 0.0) out[w++] = '0'; else w += fmt3(out + w, st);
-        out[w++] = '\t';
-        w += fmt3(out + w, re); out[w++] = '\t';
-        memcpy(out + w, psname, pl); w += (int64_t)pl; out[w++] = '\n';
+    FormatJob J{text, name_begin, name_len, seq_offsets, seq, sym_offsets, dbn, scores, psname, strlen(psname), cons,
+                snprintf(cons, sizeof cons, "\ttop-%d_consensus\n", conslim)};
+    int nthreads = 1;
+    if (count >= 8192) {
+        nthreads = (int)std::thread::hardware_concurrency();
+        nthreads = nthreads < 1 ? 1 : (nthreads > 8 ? 8 : nthreads);
     }
-    *written = w;
+    auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = first + count * t / nthreads; hi = first + count * (t + 1) / nthreads; };
+    std::vector<int64_t> start((size_t)count + 1);
+    auto run = [&](auto &&fn) {
+        if (nthreads == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    run([&](int t) { int64_t lo, hi; range(t, lo, hi); for (int64_t k = lo; k < hi; k++) start[(size_t)(k - first) + 1] = block_size(J, k); });
+    start[0] = 0;
+    for (int64_t k = 0; k < count; k++) start[(size_t)k + 1] += start[(size_t)k];
+    *written = start[(size_t)count];
+    if (!out || cap < start[(size_t)count]) return SQRN_E_CAPACITY;
+    std::vector<int> bad((size_t)nthreads, 0);
+    run([&](int t) {
+        int64_t lo, hi; range(t, lo, hi);
+        for (int64_t k = lo; k < hi; k++)
+            if (write_block(J, k, out + start[(size_t)(k - first)]) != start[(size_t)(k - first) + 1] - start[(size_t)(k - first)]) { bad[(size_t)t] = 1; return; }
+    });
+    for (int b : bad) if (b) return SQRN_E_BADARG;
     return SQRN_OK;
 }
