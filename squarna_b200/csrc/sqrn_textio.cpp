@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <thread>
 #include <vector>
 #include "../../include/sqrn.h"
@@ -53,9 +54,9 @@ inline int fmt3(char *dst, double x)
 // inputformat "q..."), the sequence being the first whitespace-separated token.
 // Writes the counts always; fills the arrays when the capacities suffice, else SQRN_E_CAPACITY.
 // name_begin/name_len: the stripped '>' line; seq_offsets[n+1] + seq: the sequence tokens.
-extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int64_t *n_entries, int64_t *total_seq,
-                               int64_t cap_entries, int64_t cap_seq, int64_t *name_begin, int32_t *name_len,
-                               int64_t *seq_offsets, uint8_t *seq)
+static int parse_segment(const char *text, int64_t len, int multiline, int64_t *n_entries, int64_t *total_seq,
+                         int64_t cap_entries, int64_t cap_seq, int64_t *name_begin, int32_t *name_len,
+                         int64_t *seq_offsets, uint8_t *seq)
 {
     if (!text || len < 0 || !n_entries || !total_seq) return SQRN_E_BADARG;
     const bool fill = name_begin && name_len && seq_offsets && seq;
@@ -104,10 +105,74 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
         p = e + 1;
     }
     if (in_entry && !multiline && data_lines != 1) return SQRN_E_UNSUPPORTED;
-    if (n == 0) return SQRN_E_UNSUPPORTED;
     *n_entries = n; *total_seq = tot;
     if (!fill || overflow || n > cap_entries) return SQRN_E_CAPACITY;
     seq_offsets[n] = tot;
+    return SQRN_OK;
+}
+
+
+// The public entry: long texts are cut at entry boundaries ("\n>") into a few segments that are counted, then
+// filled, by one host thread each.
+extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int64_t *n_entries, int64_t *total_seq,
+                               int64_t cap_entries, int64_t cap_seq, int64_t *name_begin, int32_t *name_len,
+                               int64_t *seq_offsets, uint8_t *seq)
+{
+    if (!text || len < 0 || !n_entries || !total_seq) return SQRN_E_BADARG;
+    int nt = 1;
+    if (len >= (4ll << 20)) {
+        nt = (int)std::thread::hardware_concurrency();
+        nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+    }
+    std::vector<int64_t> cut((size_t)nt + 1, len);
+    cut[0] = 0;
+    for (int t = 1; t < nt; t++) {
+        int64_t p = std::max(len * t / nt, cut[(size_t)t - 1]);
+        const char *q = p < len ? (const char *)memchr(text + p, '\n', (size_t)(len - p)) : nullptr;
+        while (q && q + 1 < text + len && q[1] != '>') q = (const char *)memchr(q + 1, '\n', (size_t)(text + len - (q + 1)));
+        cut[(size_t)t] = (q && q + 1 < text + len) ? (int64_t)(q + 1 - text) : len;
+    }
+    std::vector<int64_t> cnt((size_t)nt, 0), tot((size_t)nt, 0);
+    std::vector<int> rc((size_t)nt, SQRN_OK);
+    auto run = [&](auto &&fn) {
+        if (nt == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    // pass 1: counts (and the shape check) per segment
+    run([&](int t) {
+        const int r = parse_segment(text + cut[(size_t)t], cut[(size_t)t + 1] - cut[(size_t)t], multiline, &cnt[(size_t)t], &tot[(size_t)t],
+                                    0, 0, nullptr, nullptr, nullptr, nullptr);
+        rc[(size_t)t] = (r == SQRN_E_CAPACITY) ? SQRN_OK : r;
+    });
+    int64_t n = 0, total = 0;
+    std::vector<int64_t> n0((size_t)nt + 1, 0), s0((size_t)nt + 1, 0);
+    for (int t = 0; t < nt; t++) {
+        if (rc[(size_t)t] != SQRN_OK) return rc[(size_t)t];
+        n += cnt[(size_t)t]; total += tot[(size_t)t];
+        n0[(size_t)t + 1] = n; s0[(size_t)t + 1] = total;
+    }
+    if (n == 0) return SQRN_E_UNSUPPORTED;
+    *n_entries = n; *total_seq = total;
+    if (!(name_begin && name_len && seq_offsets && seq) || n > cap_entries || total > cap_seq) return SQRN_E_CAPACITY;
+    // pass 2: fill, every segment into its own slice of the arrays
+    run([&](int t) {
+        if (!cnt[(size_t)t]) return;
+        int64_t c = 0, s_ = 0;
+        int64_t *so = seq_offsets + n0[(size_t)t];
+        const int64_t last = so[cnt[(size_t)t]];         // the next segment's first offset lives there: keep it
+        (void)last;
+        std::vector<int64_t> local((size_t)cnt[(size_t)t] + 1);
+        rc[(size_t)t] = parse_segment(text + cut[(size_t)t], cut[(size_t)t + 1] - cut[(size_t)t], multiline, &c, &s_, cnt[(size_t)t], tot[(size_t)t],
+                                      name_begin + n0[(size_t)t], name_len + n0[(size_t)t], local.data(), seq + s0[(size_t)t]);
+        for (int64_t k = 0; k < cnt[(size_t)t]; k++) {
+            name_begin[n0[(size_t)t] + k] += cut[(size_t)t];
+            so[k] = local[(size_t)k] + s0[(size_t)t];
+        }
+    });
+    for (int t = 0; t < nt; t++) if (rc[(size_t)t] != SQRN_OK) return rc[(size_t)t];
+    seq_offsets[n] = total;
     return SQRN_OK;
 }
 

@@ -466,3 +466,30 @@ def test_cli_text_with_the_oracle_standing_in_for_the_gpu(name, monkeypatch):
         for k, (a, b) in enumerate(zip(gl, wl)):
             assert a == b, "first difference at line %d of %s" % (k + 1, name)
         assert len(gl) == len(wl)
+
+
+@pytest.mark.parametrize("fasta", [False, True], ids=["default", "fasta"])
+def test_bulk_text_parse_of_a_long_text_in_segments(tmp_path, fasta):
+    """texts above 4 MB are parsed in segments cut at entry boundaries, one host thread each: same entries as the
+    entry parsers; a foreign shape anywhere in the text is still declined"""
+    import random
+    from squarna_b200 import _lib
+    rng = random.Random(11)
+    text = _rand_text(rng, 80000, fasta)
+    assert len(text) > (4 << 20)
+    path = tmp_path / "big.fa"
+    path.write_bytes(text.encode())
+    want = list(CLI.ParseFasta(str(path)) if fasta else CLI.ParseDefaultInput(str(path), "qtrf"))
+    got = _lib.text_parse(text.encode(), fasta)
+    assert got is not None and got.n == len(want)
+    raw = text.encode()
+    for k in range(0, got.n, 7):
+        name, seq = want[k][0], want[k][1]
+        b = int(got.name_begin[k])
+        assert raw[b:b + int(got.name_len[k])].decode() == name
+        assert bytes(got.seq[got.seq_offsets[k]:got.seq_offsets[k + 1]]).decode() == seq
+    assert int(got.seq_offsets[-1]) == len(got.seq) == sum(len(w[1]) for w in want)
+    if not fasta:
+        cut = text.rfind("\n>", 0, len(text) * 3 // 4)
+        broken = text[:cut] + "\n>x\nACGU\n0.1 0.2 0.3 0.4" + text[cut:]          # an entry with a reactivity line, far from the start
+        assert _lib.text_parse(broken.encode(), False) is None
