@@ -43,13 +43,14 @@ extern "C" {
 #define SQRN_API
 #endif
 
-#define SQRN_ABI_VERSION 1
+#define SQRN_ABI_VERSION 2
 
 #define SQRN_OK             0
 #define SQRN_E_BADARG      -1
 #define SQRN_E_CAPACITY    -2   /* an output buffer is too small; needed sizes are written back */
 #define SQRN_E_CUDA        -3
 #define SQRN_E_UNSUPPORTED -4
+#define SQRN_E_NOMEM       -5   /* host allocation failed */
 
 #define SQRN_MAX_BPKEYS 32
 #define SQRN_MAX_LEN    16000    /* ungapped nucleotides per sequence */
@@ -102,6 +103,15 @@ typedef struct {
     int32_t poollim, conslim, max_structs;   /* max_structs: structures returned per sequence (<=0: all) */
     int32_t rankby[3];
     uint64_t priority_mask;      /* bit p: parameter set p has priority (RankStructs 912-913) */
+    /* base-pair-probability weighting of the score matrix (BPMatrix, SQRNdbnseq.py:341-365), ABI >= 2.  The host
+     * evaluates the probabilities (ViennaRNA in the reference) and hands over, per sequence b, one row-major
+     * N_b x N_b float64 matrix term[i * N_b + j] = (bpp[i, j] / max bpp) ** |power| at element offset
+     * bpp_offsets[b].  bpp_mode 1: scoremat += term (the reference's negative powers), 2: scoremat *= term
+     * (positive powers), 0: no weighting.  The term belongs to ONE parameter set: sqrn_predict_batch accepts it
+     * only with n_ps == 1 (parameter sets with different powers are separate calls). */
+    const double  *bpp_term;
+    const int64_t *bpp_offsets;  /* [n_seqs+1] */
+    int32_t        bpp_mode;
 } sqrn_batch;
 
 /* Results, caller-allocated.  Sequence b owns structures

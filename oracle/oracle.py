@@ -62,6 +62,8 @@ def lib():
         L.orc_predict.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.POINTER(_ParamSet), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_predict_bpp.restype = C.c_void_p
+        L.orc_predict_bpp.argtypes = L.orc_predict.argtypes + [C.c_void_p, C.c_int]
         L.orc_result_count.argtypes = [C.c_void_p]
         L.orc_result_ncalls.argtypes = [C.c_void_p]
         L.orc_result_ncalls.restype = C.c_long
@@ -72,6 +74,7 @@ def lib():
         L.orc_annotate.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                    C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_annotate_bpp.argtypes = L.orc_annotate.argtypes + [C.c_void_p, C.c_int]
         L.orc_optimal.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.POINTER(_ParamSet), C.c_int, C.c_double, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -175,10 +178,12 @@ def _ptr(a):
 
 def predict_short(shortseq, shortreacts, shortrest, paramsets, interchainonly=False, poollim=1000,
                   smat=None, rankby=(0, 2, 1), priority=(), rankbydiff=False, conslim=1,
-                  hardrest=False, compensated_sum=False, raw_codes=False):
+                  hardrest=False, compensated_sum=False, raw_codes=False, bpp_term=None, bpp_mode=0):
     """Greedy prediction on an ungapped, normalised sequence.  Returns
     (cons_dbn, [ (dbn, scores3, struct_is_int0, [paramset idx], stems[(i,j,len)], bpscores, finscores) ], ncalls).
-    raw_codes: the dbns as signed pseudoknot-level codes (+L opening, -L closing, 0 unpaired) instead of strings."""
+    raw_codes: the dbns as signed pseudoknot-level codes (+L opening, -L closing, 0 unpaired) instead of strings.
+    bpp_term / bpp_mode: the N x N base-pair-probability term of seq.py:341-365 (1: added, 2: multiplied), applied
+    for every parameter set of the call."""
     L = lib()
     N = len(shortseq)
     ps = _PS(paramsets)
@@ -189,9 +194,12 @@ def predict_short(shortseq, shortreacts, shortrest, paramsets, interchainonly=Fa
     for p in priority:
         pmask |= 1 << p
     sm = None if smat is None else np.ascontiguousarray(smat, dtype=np.float64)
-    R = L.orc_predict(shortseq.encode("latin-1"), N, _ptr(reacts), _ptr(rclass), _ptr(rbps), len(rbps),
-                      ps.arr, ps.n, int(interchainonly), int(poollim), _ptr(sm), _ptr(rk),
-                      pmask, int(rankbydiff), int(conslim), int(hardrest), int(compensated_sum))
+    bt = None if bpp_term is None else np.ascontiguousarray(bpp_term, dtype=np.float64)
+    assert bt is None or bt.shape == (N, N)
+    R = L.orc_predict_bpp(shortseq.encode("latin-1"), N, _ptr(reacts), _ptr(rclass), _ptr(rbps), len(rbps),
+                          ps.arr, ps.n, int(interchainonly), int(poollim), _ptr(sm), _ptr(rk),
+                          pmask, int(rankbydiff), int(conslim), int(hardrest), int(compensated_sum),
+                          _ptr(bt), int(bpp_mode) if bt is not None else 0)
     try:
         out = []
         for k in range(L.orc_result_count(R)):
@@ -261,7 +269,7 @@ def sqrn_dbnseq(seq, reacts=None, restraints=None, dbn=None, paramsets=(), consl
 
 
 def annotate(shortseq, paramset, shortreacts=None, shortrest=None, selected=(), interchainonly=False,
-             smat=None):
+             smat=None, bpp_term=None, bpp_mode=0):
     """AnnotateStems seam (seq.py:427-495 after BPMatrix): list of (i, j, len, score)."""
     L = lib()
     N = len(shortseq)
@@ -274,9 +282,12 @@ def annotate(shortseq, paramset, shortreacts=None, shortrest=None, selected=(), 
     cap = N * N // 2 + 16
     st = np.zeros((cap, 3), dtype=np.int32)
     sc = np.zeros(cap)
-    n = L.orc_annotate(shortseq.encode("latin-1"), N, _ptr(reacts), _ptr(rclass), _ptr(rbps), len(rbps),
-                       len(vals), keys, _ptr(vals), int(interchainonly), float(paramset["minlen"]),
-                       float(paramset["minbpscore"]), _ptr(sel), len(sel), _ptr(sm), cap, _ptr(st), _ptr(sc))
+    bt = None if bpp_term is None else np.ascontiguousarray(bpp_term, dtype=np.float64)
+    assert bt is None or bt.shape == (N, N)
+    n = L.orc_annotate_bpp(shortseq.encode("latin-1"), N, _ptr(reacts), _ptr(rclass), _ptr(rbps), len(rbps),
+                           len(vals), keys, _ptr(vals), int(interchainonly), float(paramset["minlen"]),
+                           float(paramset["minbpscore"]), _ptr(sel), len(sel), _ptr(sm), cap, _ptr(st), _ptr(sc),
+                           _ptr(bt), int(bpp_mode) if bt is not None else 0)
     return [(int(st[k, 0]), int(st[k, 1]), int(st[k, 2]), float(sc[k])) for k in range(n)]
 
 

@@ -209,7 +209,8 @@ def RunSQRNdbnali(objs, defreacts, defrests, defref,
         buf = io.StringIO()
         results = _seq.RunSQRNdbnseqBatch([tuple(obj) for obj in objs], paramsetnames, paramsets, rankbydiff,
                                           rankby, hardrest, interchainonly, toplim, outplim, conslim, reactformat,
-                                          False, poollim, sink=buf, stemmatrix=smat, algos=algos)
+                                          False, poollim, sink=buf, stemmatrix=smat, algos=algos, entropy=entropy,
+                                          M=M, B=B)
         if verbose:
             print(buf.getvalue(), end='', file=sink)
         structs = [r[0] for r in results]

@@ -12,7 +12,9 @@ ChooseStems, the structure pool, ScoreStruct and the ranking are behind
 Reference lines cited as seq.py:N are /root/reference/src/SQUARNA/SQRNdbnseq.py.
 """
 import math
+import os
 import sys
+import threading
 
 import numpy as np
 
@@ -36,13 +38,120 @@ _OPEN_IDX = {c: k for k, c in enumerate(_OPEN)}
 _CLOSE_IDX = {c: k for k, c in enumerate(_CLOSE)}
 
 _ctx = {}
+_ctx_lock = threading.Lock()
 
 
 def get_context(device=0):
-    """Process-wide GPU context (one per device)."""
-    if device not in _ctx:
-        _ctx[device] = _lib.Context(device)
-    return _ctx[device]
+    """Process-wide GPU context (one per device; one host thread drives a context at a time)."""
+    with _ctx_lock:
+        if device not in _ctx:
+            _ctx[device] = _lib.Context(device)
+        return _ctx[device]
+
+
+def visible_devices():
+    """indices of the usable CUDA devices of this process (CUDA_VISIBLE_DEVICES applies)"""
+    return list(range(_lib.load().sqrn_device_count()))
+
+
+def _resolve_devices(devices, device=0):
+    """devices=None: every visible GPU (the reference's Pool(threads) over sequences, SQUARNA.py:889, becomes one
+    host thread per GPU); an int or a list picks them explicitly"""
+    if devices is None:
+        env = os.environ.get("SQRN_DEVICES")               # e.g. "0,2": the only knob the unchanged Predict() surface has
+        devs = [int(x) for x in env.split(",") if x.strip()] if env else (visible_devices() or [device])
+    elif isinstance(devices, int):
+        devs = [devices]
+    else:
+        devs = list(devices)
+    return devs or [device]
+
+
+def run_sharded(fn, items, lengths, devices, exponent=3.0):
+    """fn(sub_items, device) -> list, for the items dealt to each device by cost (length ** exponent), one host
+    thread per GPU (ctypes releases the GIL during the library calls); results come back in input order.  No
+    collective: sequences are independent."""
+    from .sharding import shard_plan
+    plan = shard_plan(lengths, len(devices), exponent)
+    out = [None] * len(items)
+    errors = []
+
+    def work(dev, idx):
+        try:
+            if len(idx):
+                res = fn([items[k] for k in idx.tolist()], dev)
+                for k, r in zip(idx.tolist(), res):
+                    out[k] = r
+        except BaseException as e:                     # surfaced in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d, idx)) for d, idx in zip(devices, plan)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out
+
+
+# ---- base-pair probabilities (bpp != 0 parameter sets, seq.py:341-365) --------------------------------
+_RNA = None
+
+
+def set_rna_module(module):
+    """Use `module` in place of ViennaRNA's `RNA` for base-pair probabilities (anything with the same
+    fold_compound / sc_add_SHAPE_deigan / pf / bpp / mfe / exp_params_rescale surface); None: import RNA."""
+    global _RNA
+    _RNA = module
+
+
+def _rna():
+    if _RNA is not None:
+        return _RNA
+    import RNA                                         # ViennaRNA, as in the reference (seq.py:342)
+    return RNA
+
+
+def BPPMatrix(shortseq, shortreacts, M=1.8, B=-0.6):
+    """the base-pair probability matrix BPMatrix asks ViennaRNA for (seq.py:341-365): partition function with the
+    SHAPE pseudo-energies when reactivities are given, redone with rescaled Boltzmann factors when every
+    probability underflowed.  Returns the N x N float64 array (all zero if both attempts gave nothing)."""
+    RNA = _rna()
+    default = shortreacts is None or set(shortreacts) == {0.5, }
+    fc = RNA.fold_compound(''.join(ch if ch not in SEPS and ord(ch) <= 127 else 'N' for ch in shortseq))
+    if not default:
+        fc.sc_add_SHAPE_deigan(ProcessReacts(shortreacts, reverse=True, M=M, B=B), m=M, b=B)
+    fc.pf()
+    bppm = np.array(fc.bpp())[1:, 1:]
+    if np.max(bppm) > 0:
+        return bppm
+    (_ss, mfe) = fc.mfe()
+    fc.exp_params_rescale(mfe)
+    fc.pf()
+    return np.array(fc.bpp())[1:, 1:]
+
+
+def _bpp_terms(preps, idx, paramset, M, B):
+    """None when the parameter set has bpp == 0; else (mode, [N x N term per entry of idx]) with
+    term = (bppm / max bppm) ** |bpp|: mode 1 is added to the score matrix (bpp < 0), mode 2 multiplies it
+    (bpp > 0) -- seq.py:350-364.  No probabilities at all: the neutral term (the reference leaves the matrix alone)."""
+    power = paramset.get("bpp", 0)
+    if not power:
+        return None
+    mode = 1 if power < 0 else 2
+    terms = []
+    for k in idx:
+        p = preps[k]
+        if p.bppm is None or p.bppm_key != (M, B):
+            p.bppm = BPPMatrix(p.shortseq, p._sr if p._sr is None else list(p._sr), M, B)
+            p.bppm_key = (M, B)
+        mx = np.max(p.bppm) if p.bppm.size else 0
+        if mx > 0:
+            terms.append(np.ascontiguousarray((p.bppm / mx) ** abs(power), dtype=np.float64))
+        else:
+            terms.append(np.zeros_like(p.bppm) if mode == 1 else np.ones_like(p.bppm))
+    return mode, terms
 
 
 # --------------------------------------------------------------------- helpers
@@ -238,7 +347,7 @@ def _metrics(pred, known):
 class _Prepared:
     """one sequence digested the way seq.py:1004-1037 does it"""
     __slots__ = ("seq", "shortseq", "shortrest", "_sr", "rbps", "rclass", "_keep", "shortdbn",
-                 "dbn", "compensated")
+                 "dbn", "compensated", "bppm", "bppm_key")
 
     @property
     def shortreacts(self):
@@ -283,6 +392,7 @@ def _prepare(seq, reacts, restraints, dbn):
     """seq.py:1004-1037 for one entry.  The common shapes (no gaps, no restraints, encoded or absent
     reactivities) take vectorised paths; everything else goes through the reference's own steps."""
     p = _Prepared()
+    p.bppm = p.bppm_key = None
     seq = seq.upper().replace("T", "U")                               # seq.py:1004
     n = len(seq)
     if restraints:
@@ -345,7 +455,7 @@ def _encode_symbols(shortseq):
     return shortseq.encode("latin-1", "replace")
 
 
-def _make_batch(preps, idx, comp, stemmatrix, interchainonly, **opts):
+def _make_batch(preps, idx, comp, stemmatrix, interchainonly, bpp=None, **opts):
     """PackedBatch of the prepared entries idx (all with the same reactivity-sum mode `comp`)"""
     # distinct processed reactivities of the batch -> codes + value table (host pow() table in the library)
     codes = values = None
@@ -372,7 +482,8 @@ def _make_batch(preps, idx, comp, stemmatrix, interchainonly, **opts):
                        react_codes=codes, react_values=values, react_comp=comp,
                        restr_class=[preps[k].rclass for k in idx] if any_restr else None,
                        rbps=[np.array(preps[k].rbps, dtype=np.int32).reshape(-1, 2) for k in idx] if any_restr else None,
-                       smat=smat, cols=cols, interchainonly=interchainonly, max_structs=0, **opts)
+                       smat=smat, cols=cols, interchainonly=interchainonly, max_structs=0,
+                       bpp_mode=bpp[0] if bpp else 0, bpp_terms=bpp[1] if bpp else None, **opts)
 
 
 # ---------------------------------------------------------------- non-greedy algorithms (host)
@@ -408,8 +519,9 @@ def RankStructs(stemsets, rankbydiff=False, rankby=(0, 2, 1), priority=set()):
     return ranked[:cur] + sorted(ranked[cur:], key=score_key, reverse=True)
 
 
-def _cell_scorer(p, paramset, smat):
-    """scoremat[v, w] of BPMatrix for one prepared entry (seq.py:258-339, times the alignment weight 1084-1085)"""
+def _cell_scorer(p, paramset, smat, bpp_mode=0, bpp_term=None):
+    """scoremat[v, w] of BPMatrix for one prepared entry (seq.py:258-339 and the bpp term 350-364, times the
+    alignment weight 1084-1085)"""
     weights = {}
     for bp, w in paramset["bpweights"].items():
         weights[bp] = w
@@ -424,6 +536,10 @@ def _cell_scorer(p, paramset, smat):
         if base <= 0:
             rf = 1 / max(rf, 0.01)
         val = base * 1.0 * rf                        # bps * boolmat * reactfactor: the cell is a live pair here
+        if bpp_mode == 1:
+            val = val + bpp_term[v, w]
+        elif bpp_mode == 2:
+            val = val * bpp_term[v, w]
         if smat is not None:
             val = val * smat[keep[v], keep[w]]
         return val
@@ -464,14 +580,16 @@ def RunAlgo(seq, stems, cell_score, minlen, minscore, algo="E", levellimit=3):
 
 
 def _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydiff, rankby, interchainonly,
-                        stemmatrix, poollim, priority, algos, device, levellimit):
-    """SQRNdbnseq (seq.py:1039-1286) for parameter sets that name Nussinov / Hungarian / Edmonds: per parameter
-    set the greedy structures come from sqrn_predict_batch and the stems for the other builders from
-    sqrn_yield_stems_batch; de-duplication, ScoreStruct of the host-built structures, ranking and consensus
-    follow the reference on the host."""
+                        stemmatrix, poollim, priority, algos, device, levellimit, M=1.8, B=-0.6):
+    """SQRNdbnseq (seq.py:1039-1286) for parameter sets that name Nussinov / Hungarian / Edmonds or weight the
+    score matrix with base-pair probabilities (bpp != 0): per parameter set the greedy structures come from
+    sqrn_predict_batch and the stems for the other builders from sqrn_yield_stems_batch (both with that set's bpp
+    term); de-duplication, ScoreStruct of the host-built structures, ranking and consensus follow the reference on
+    the host."""
     preps = [_prepare(*e) for e in entries]
     ctx = get_context(device)
     n = len(entries)
+    smat_np = None if stemmatrix is None else np.asarray(stemmatrix, dtype=np.float64)
     per_ps = [[None] * len(paramsets) for _ in range(n)]       # [entry][paramset] -> list of (stems, scores) in order
     for psi, ps in enumerate(paramsets):
         use = set(algos) if algos else set(ps["algorithms"])
@@ -481,20 +599,21 @@ def _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydif
             idx = [k for k in range(n) if preps[k].compensated == comp]
             if not idx:
                 continue
+            bpp = _bpp_terms(preps, idx, ps, M, B)
             others = [a for a in use if a != "G"]             # set order, as in the reference's `for algo in algos`
             if others:
-                batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly)
-                for k, (st, sc) in zip(idx, ctx.yield_stems(ps, batch)):
+                batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly, bpp=bpp)
+                for q, (k, (st, sc)) in enumerate(zip(idx, ctx.yield_stems(ps, batch))):
                     p = preps[k]
-                    stems = [[[(i + q, j - q) for q in range(ln)], ln, float(s_)] for (i, j, ln), s_ in zip(st.tolist(), sc.tolist())]
-                    cell = _cell_scorer(p, ps, None if stemmatrix is None else np.asarray(stemmatrix, dtype=np.float64))
+                    stems = [[[(i + t, j - t) for t in range(ln)], ln, float(s_)] for (i, j, ln), s_ in zip(st.tolist(), sc.tolist())]
+                    cell = _cell_scorer(p, ps, smat_np, bpp[0] if bpp else 0, bpp[1][q] if bpp else None)
                     ll = levellimit if levellimit is not None else 3 - int(len(p.shortseq) > 500)
                     for algo in others:
                         stemset = RunAlgo(p.shortseq, stems, cell, ps["minlen"], ps["minbpscore"], algo, ll)
                         per_ps[k][psi].append((stemset, ScoreStruct(p.shortseq, stemset, p.shortreacts)))
             if "G" in use:
-                batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly, hardrest=False, rankbydiff=False,
-                                    poollim=poollim, conslim=1, rankby=rankby, priority_mask=0)
+                batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly, bpp=bpp, hardrest=False,
+                                    rankbydiff=False, poollim=poollim, conslim=1, rankby=rankby, priority_mask=0)
                 for k, (_cons, structs, _nt) in zip(idx, ctx.predict_batch([ps], batch)):
                     for codes, sc, isint, _mask, stems in structs:
                         stemset = [[[(i + q, j - q) for q in range(ln)], ln] for i, j, ln in np.asarray(stems).tolist()]
@@ -547,23 +666,50 @@ def _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydif
 
 def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankbydiff=False,
                  rankby=(0, 2, 1), interchainonly=False, stemmatrix=None, poollim=1000,
-                 priority=frozenset(), algos=frozenset(), device=0, levellimit=None):
-    """Batched SQRNdbnseq: entries = [(seq, reacts, restraints, dbn)], one GPU
-    call for all of them.  Returns the reference's 4-tuple per entry."""
+                 priority=frozenset(), algos=frozenset(), device=None, levellimit=None, M=1.8, B=-0.6, devices=None):
+    """Batched SQRNdbnseq: entries = [(seq, reacts, restraints, dbn)], one GPU call for all of them per GPU.
+    devices=None: every visible GPU -- the entries are dealt by length to one host thread per GPU (the
+    reference's Pool(threads) over sequences, SQUARNA.py:889) and come back in input order; `device` (an int) or
+    a list in `devices` names the GPUs explicitly.  Returns the reference's 4-tuple per entry."""
     assert set(rankby) == {0, 1, 2} and len(rankby) == 3, "Invalid ranking indices"
+    devs = [device] if device is not None else _resolve_devices(devices)
+    if len(devs) > 1 and len(entries) >= 2 * len(devs):
+        return run_sharded(lambda sub, dev: predict_many(sub, paramsets, conslim, toplim, hardrest, rankbydiff,
+                                                         rankby, interchainonly, stemmatrix, poollim, priority,
+                                                         algos, dev, levellimit, M, B),
+                           entries, [len(e[0]) for e in entries], devs)
+    device = devs[0]
     # which parameter sets run the greedy algorithm (seq.py:1046-1102)
     gsets = []
+    mixed = False
     for psi, ps in enumerate(paramsets):
         use = set(algos) if algos else set(ps["algorithms"])
-        if ps.get("bpp", 0):
-            raise NotImplementedError("parameter set #{} has bpp != 0: ViennaRNA base-pair probabilities are "
-                                      "outside the GPU hot path (use the *nobpp configs)".format(psi))
-        if use - {"G"}:
-            # Nussinov / Hungarian / Edmonds sets: stems from the GPU, the builders on the host (SURVEY 8f-2)
-            return _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydiff, rankby,
-                                       interchainonly, stemmatrix, poollim, priority, algos, device, levellimit)
+        if use - {"G"} or ps.get("bpp", 0):
+            # Nussinov / Hungarian / Edmonds sets: stems from the GPU, the builders on the host (SURVEY 8f-2);
+            # bpp sets: the probabilities come from the host (ViennaRNA or set_rna_module) as one term per
+            # parameter set (SURVEY 8f-4), so the sets run one call each
+            mixed = True
         if "G" in use:
             gsets.append(psi)
+    if mixed:
+        if any(ps.get("bpp", 0) for ps in paramsets):
+            _rna()                                  # ModuleNotFoundError now, as the reference's `import RNA`, not after GPU work
+            # N x N float64 per entry and bpp set on the device: bound the cells per call
+            out, chunk, cells = [], [], 0
+            for e in entries:
+                c = len(e[0]) ** 2
+                if chunk and cells + c > (1 << 25):
+                    out += _predict_many_mixed(chunk, paramsets, conslim, toplim, hardrest, rankbydiff, rankby,
+                                               interchainonly, stemmatrix, poollim, priority, algos, device, levellimit, M, B)
+                    chunk, cells = [], 0
+                chunk.append(e)
+                cells += c
+            if chunk:
+                out += _predict_many_mixed(chunk, paramsets, conslim, toplim, hardrest, rankbydiff, rankby,
+                                           interchainonly, stemmatrix, poollim, priority, algos, device, levellimit, M, B)
+            return out
+        return _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydiff, rankby,
+                                   interchainonly, stemmatrix, poollim, priority, algos, device, levellimit, M, B)
     preps = [_prepare(*e) for e in entries]
     results = [None] * len(entries)
     if not gsets:
@@ -648,23 +794,16 @@ def SQRNdbnseq(seq, reacts=None, restraints=None, dbn=None,
     Edmonds get their stems from the GPU and run those builders on the host (SQRNalgos.py); `entropy=True`
     returns the stem-matrix entropy string of the first parameter set."""
     if entropy:
-        return Entropy(seq, reacts, restraints, paramsets[0], interchainonly, stemmatrix)
+        return Entropy(seq, reacts, restraints, paramsets[0], interchainonly, stemmatrix, M=M, B=B)
     return predict_many([(seq, reacts, restraints, dbn)], paramsets, conslim, toplim, hardrest,
                         rankbydiff, rankby, interchainonly, stemmatrix, poollim,
-                        frozenset(priority), frozenset(algos), levellimit=levellimit)[0]
+                        frozenset(priority), frozenset(algos), levellimit=levellimit, M=M, B=B)[0]
 
 
-def Entropy(seq, reacts, restraints, paramset, interchainonly=False, stemmatrix=None, device=0):
-    """mean row entropy of the stem-score matrix of the first parameter set, as the string the reference returns
-    (seq.py:520-545, reached through SQRNdbnseq(entropy=True), seq.py:1087-1089): every stem AnnotateStems finds
-    writes its score into the cells of its pairs (both triangles); a row's entropy is that of its non-zero cells
-    normalised to 1.  The stems come from sqrn_yield_stems_batch."""
-    p = _prepare(seq, reacts, restraints, None)
-    batch = _make_batch([p], [0], p.compensated, stemmatrix, interchainonly)
-    (st, sc), = get_context(device).yield_stems(paramset, batch)
-    n = len(p.shortseq)
+def _stem_matrix_entropy(n, stems, scores):
+    """seq.py:520-545 from the (i, j, len) stems of one AnnotateStems pass and their scores"""
     mat = np.zeros((n, n))
-    for (i, j, ln), score in zip(st.tolist(), sc.tolist()):
+    for (i, j, ln), score in zip(stems.tolist(), scores.tolist()):
         for q in range(ln):
             mat[i + q, j - q] = score
             mat[j - q, i + q] = score
@@ -677,10 +816,39 @@ def Entropy(seq, reacts, restraints, paramset, interchainonly=False, stemmatrix=
     return str(round(ent / n, 3))
 
 
-def _print_entry(name, sequence, reactivities, restraints, reference, reactformat, sink, rfam=None):
-    """header block of RunSQRNdbnseq (seq.py:1301-1345)"""
+def entropy_many(entries, paramset, interchainonly=False, stemmatrix=None, device=0, M=1.8, B=-0.6):
+    """Entropy for many entries [(seq, reacts, restraints)] with one sqrn_yield_stems_batch call per
+    reactivity-sum mode; returns the strings in input order"""
+    preps = [_prepare(seq, reacts, restraints, None) for seq, reacts, restraints in entries]
+    out = [None] * len(preps)
+    ctx = get_context(device)
+    for comp in (False, True):
+        idx = [k for k, p in enumerate(preps) if p.compensated == comp]
+        if not idx:
+            continue
+        batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly,
+                            bpp=_bpp_terms(preps, idx, paramset, M, B))
+        for k, (st, sc) in zip(idx, ctx.yield_stems(paramset, batch)):
+            out[k] = _stem_matrix_entropy(len(preps[k].shortseq), st, sc)
+    return out
+
+
+def Entropy(seq, reacts, restraints, paramset, interchainonly=False, stemmatrix=None, device=0, M=1.8, B=-0.6):
+    """mean row entropy of the stem-score matrix of the first parameter set, as the string the reference returns
+    (seq.py:520-545, reached through SQRNdbnseq(entropy=True), seq.py:1087-1089): every stem AnnotateStems finds
+    writes its score into the cells of its pairs (both triangles); a row's entropy is that of its non-zero cells
+    normalised to 1.  The stems come from sqrn_yield_stems_batch."""
+    return entropy_many([(seq, reacts, restraints)], paramset, interchainonly, stemmatrix, device, M, B)[0]
+
+
+def _print_entry(name, sequence, reactivities, restraints, reference, reactformat, sink, rfam=None, entropy_val=None):
+    """header block of RunSQRNdbnseq (seq.py:1301-1345); entropy_val: the string SQRNdbnseq(entropy=True) returned
+    (seq.py:1313-1318 prints it next to the sequence)"""
     print(name, file=sink)
-    print(sequence, file=sink)
+    if entropy_val is not None:
+        print('\t'.join([sequence, "entropy:", entropy_val]), file=sink)
+    else:
+        print(sequence, file=sink)
     if reactivities:
         print(EncodedReactivities(sequence, reactivities, reactformat), "reactivities", sep='\t', file=sink)
     if restraints:
@@ -735,9 +903,13 @@ def RunSQRNdbnseq(name, sequence, reactivities, restraints,
                   priority=None, rfam=None, M=1.8, B=-0.6):
     """Print the reference's text block for one entry and return the prediction
     4-tuple (seq.py:1289-1408)."""
-    # `entropy` is accepted and, as in the reference (seq.py:1349-1353 does not hand it on), has no effect here
     priority = _resolve_priority(priority, paramsetnames, rfam)
-    _print_entry(name, sequence, reactivities, restraints, reference, reactformat, sink, rfam)
+    entropy_val = None
+    if entropy:                                                  # seq.py:1313-1318
+        entropy_val = SQRNdbnseq(sequence, reactivities, restraints, reference, paramsets, conslim, toplim, hardrest,
+                                 rankbydiff, rankby, interchainonly, threads, mp, stemmatrix, poollim,
+                                 entropy=True, algos=algos, M=M, B=B)
+    _print_entry(name, sequence, reactivities, restraints, reference, reactformat, sink, rfam, entropy_val)
     if evalonly:
         return None, None, None, None
     prediction = SQRNdbnseq(sequence, reactivities, restraints, reference,
@@ -751,19 +923,23 @@ def RunSQRNdbnseq(name, sequence, reactivities, restraints,
 
 def RunSQRNdbnseqBatch(entries, paramsetnames, paramsets, rankbydiff, rankby, hardrest, interchainonly,
                        toplim, outplim, conslim, reactformat, evalonly, poollim=1000, sink=sys.stdout,
-                       stemmatrix=None, algos={'G', }, priority=None, rfam=None, levellimit=None):
+                       stemmatrix=None, algos={'G', }, priority=None, rfam=None, levellimit=None,
+                       entropy=False, M=1.8, B=-0.6, devices=None):
     """RunSQRNdbnseq for many entries [(name, seq, reacts, restraints, reference)]
     with ONE batched GPU call; text is written in input order (what the
     reference's ordered imap gives, SQUARNA.py:929-935)."""
     priority = _resolve_priority(priority, paramsetnames, rfam)
     preds = [None] * len(entries)
+    ents = [None] * len(entries)
+    if entropy:                                                  # seq.py:1313-1318, before evalonly returns
+        ents = entropy_many([(e[1], e[2], e[3]) for e in entries], paramsets[0], interchainonly, stemmatrix, M=M, B=B)
     if not evalonly:
         preds = predict_many([(e[1], e[2], e[3], e[4]) for e in entries], paramsets, conslim, toplim,
                              hardrest, rankbydiff, rankby, interchainonly, stemmatrix, poollim,
-                             frozenset(priority), frozenset(algos), levellimit=levellimit)
+                             frozenset(priority), frozenset(algos), levellimit=levellimit, M=M, B=B, devices=devices)
     out = []
-    for (name, seq, reacts, rests, ref), pred in zip(entries, preds):
-        _print_entry(name, seq, reacts, rests, ref, reactformat, sink, rfam)
+    for (name, seq, reacts, rests, ref), pred, ent in zip(entries, preds, ents):
+        _print_entry(name, seq, reacts, rests, ref, reactformat, sink, rfam, ent)
         if evalonly:
             out.append((None, None, None, None))
         else:

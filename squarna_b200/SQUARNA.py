@@ -415,8 +415,8 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
     elif "s" in rankby:
         rankby = (1, 2, 0)
 
-    # `ent` / entropy: parsed and handed to the runners, which (like the reference's RunSQRNdbnseq,
-    # SQRNdbnseq.py:1349-1353) do not use it; SQRNdbnseq(entropy=True) is the API that returns the entropy
+    # `ent` / entropy: the runners print "sequence<TAB>entropy:<TAB>value" in place of the sequence line
+    # (SQRNdbnseq.py:1313-1318; Predict hands it on at SQUARNA.py:883, 926 and 990)
     if rfam or g4 or rbp:
         raise NotImplementedError("rfam / g4 / rbp restraint discovery is outside the GPU hot path")
 
@@ -474,7 +474,7 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
             and len(paramsets) == 1 and (algos_ or set(paramsets[0]["algorithms"])) == {"G"}
             and not paramsets[0].get("bpp", 0) and poollim == 1 and not interchainonly
             and min(toplim, outplim, conslim) >= 1 and (fmt == "fasta" or inputformat.startswith("q"))
-            and os.environ.get("SQRN_NO_BULK") is None):
+            and not entropy and os.environ.get("SQRN_NO_BULK") is None):
         if _bulk_lane(inputfile, fmt == "fasta", paramsetnames[0], paramsets[0], conslim, write_to):
             return
 
@@ -494,7 +494,7 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
         names_, sets_ = tables[pending[0][0]]
         RunSQRNdbnseqBatch([e[1] for e in pending], names_, sets_, rankbydiff, rankby, hardrest, interchainonly,
                            toplim, outplim, conslim, reactformat, evalonly, poollim, sink=write_to,
-                           algos=algos, priority=priority, rfam=None, levellimit=levellimit)
+                           algos=algos, priority=priority, rfam=None, levellimit=levellimit, entropy=entropy, M=M, B=B)
         del pending[:]
 
     for entry in inputs:

@@ -6,7 +6,7 @@ import numpy as np
 MAX_BPKEYS = 32
 MAX_LEN = 16000
 
-OK, E_BADARG, E_CAPACITY, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4
+OK, E_BADARG, E_CAPACITY, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4, -5
 RC_UNPAIRED, RC_NOLEFT, RC_NORIGHT = 1, 2, 4
 
 
@@ -57,7 +57,8 @@ class Batch(C.Structure):
                 ("smat", C.c_void_p), ("smat_L", C.c_int32), ("cols", C.c_void_p),
                 ("interchainonly", C.c_int32), ("hardrest", C.c_int32), ("rankbydiff", C.c_int32),
                 ("poollim", C.c_int32), ("conslim", C.c_int32), ("max_structs", C.c_int32),
-                ("rankby", C.c_int32 * 3), ("priority_mask", C.c_uint64)]
+                ("rankby", C.c_int32 * 3), ("priority_mask", C.c_uint64),
+                ("bpp_term", C.c_void_p), ("bpp_offsets", C.c_void_p), ("bpp_mode", C.c_int32)]
 
 
 class Result(C.Structure):

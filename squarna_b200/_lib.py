@@ -130,7 +130,8 @@ class PackedBatch:
 
     def __init__(self, seqs, react_codes=None, react_values=None, react_comp=False, restr_class=None,
                  rbps=None, smat=None, cols=None, interchainonly=False, hardrest=False, rankbydiff=False,
-                 poollim=1000, conslim=1, max_structs=0, rankby=(0, 2, 1), priority_mask=0):
+                 poollim=1000, conslim=1, max_structs=0, rankby=(0, 2, 1), priority_mask=0,
+                 bpp_terms=None, bpp_mode=0):
         self.seqs = seqs
         self.symbols, self.offsets = pack_sequences(seqs)
         n = len(seqs)
@@ -175,6 +176,15 @@ class PackedBatch:
         for k in range(3):
             b.rankby[k] = int(rankby[k])
         b.priority_mask = int(priority_mask)
+        # base-pair-probability terms: one N x N float64 matrix per sequence (include/sqrn.h)
+        self.bpp_term = self.bpp_offsets = None
+        if bpp_terms is not None and bpp_mode:
+            self.bpp_offsets = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum([int(t.size) for t in bpp_terms], out=self.bpp_offsets[1:])
+            self.bpp_term = cat([np.ascontiguousarray(t, dtype=np.float64) for t in bpp_terms], np.float64)
+            b.bpp_term = ptr(self.bpp_term)
+            b.bpp_offsets = ptr(self.bpp_offsets)
+            b.bpp_mode = int(bpp_mode)
         self.c = b
 
 

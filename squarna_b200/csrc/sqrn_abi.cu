@@ -181,7 +181,7 @@ struct CachedStems {
     std::vector<int64_t> off; std::vector<int32_t> stems; std::vector<double> scores;
 };
 
-enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS,
+enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS, B_BPP, B_BPPOFF,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
        W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, NBUF };
 
@@ -901,6 +901,15 @@ static int upload_batch(sqrn_ctx *ctx, const sqrn_batch *in, DeviceBatch &D)
         TRY(upload(ctx, B_COLS, in->cols, (size_t)total, &d_c));
         B.smat = d_s; B.L = in->smat_L; B.cols = d_c;
     }
+    if (in->bpp_mode) {
+        if ((in->bpp_mode != 1 && in->bpp_mode != 2) || !in->bpp_term || !in->bpp_offsets) { ctx->err = "bad bpp term"; return SQRN_E_BADARG; }
+        for (int64_t b = 0; b < n; b++)
+            if (in->bpp_offsets[b + 1] - in->bpp_offsets[b] != (int64_t)D.len[b] * D.len[b]) { ctx->err = "bpp term: need one N x N matrix per sequence"; return SQRN_E_BADARG; }
+        double *d_t; int64_t *d_o;
+        TRY(upload(ctx, B_BPP, in->bpp_term, (size_t)in->bpp_offsets[n], &d_t));
+        TRY(upload(ctx, B_BPPOFF, in->bpp_offsets, (size_t)n + 1, &d_o));
+        B.bpp = d_t; B.bpp_off = d_o; B.bpp_mode = in->bpp_mode;
+    }
     return SQRN_OK;
 }
 
@@ -982,7 +991,7 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
         int nmax_c = D.len[W.item_seq[order[pos]]];
         Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, W.mode == MODE_STEP, D.B.rcode != nullptr, max_init, pl));
         {
-            const bool plain = !D.B.rcode && !D.B.rclass && !D.B.rbp_off && !D.B.smat && !D.B.interchainonly;
+            const bool plain = !D.B.rcode && !D.B.rclass && !D.B.rbp_off && !D.B.smat && !D.B.interchainonly && !D.B.bpp;
             maybe_glist(ctx, *P, pl, std::max(nmax_c, 1), D.rbmax, D.B.rcode != nullptr, max_init, W.mode == MODE_TAIL);
             maybe_cluster(ctx, *P, pl, end - pos, plain, W.mode == MODE_TAIL);
         }
@@ -1017,7 +1026,12 @@ static int run_step_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBa
     for (int k = 0; k < n; k++) if (W.out_n[k] < 0 || W.out_n[k] > W.out_cap[k]) redo.push_back(k);
     if (redo.empty()) return SQRN_OK;
     int min_ccap = 0;
-    for (int attempt = 0; attempt < 3 && !redo.empty(); attempt++) {
+    // ChooseStems returns a set of pairwise-conflicting alternatives (seq.py:783-787): it is bounded by the number of
+    // candidates, not by N / 2.  team_choose reports the true count even when it could only write `cap` triples, so an
+    // item is done only when its count fits the capacity it ran with; otherwise it runs again with exactly that count.
+    std::vector<int64_t> want((size_t)n, 0);
+    for (int k : redo) want[k] = std::max<int64_t>(D.len[W.item_seq[k]] / 2 + 1, W.out_n[k]);
+    for (int attempt = 0; attempt < 5 && !redo.empty(); attempt++) {
         HostWork R; R.mode = MODE_STEP;
         bool list_overflow = false;
         for (int k : redo) {
@@ -1033,14 +1047,15 @@ static int run_step_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBa
                 R.init_off.push_back((int64_t)R.init_stems.size() / 3);
             }
         }
-        for (int k : redo) R.out_cap.push_back(D.len[W.item_seq[k]] / 2 + 1);
+        for (int k : redo) R.out_cap.push_back(want[k]);
         if (list_overflow) min_ccap = min_ccap ? min_ccap * 4 : 4096;
         TRY(run_items(ctx, ps, D, R, min_ccap));
         std::vector<int> still;
         // splice the re-run results back: rebuild W's CSR with the larger capacities
         std::vector<int64_t> new_off((size_t)n + 1, 0);
         std::vector<int64_t> new_cap = W.out_cap;
-        for (size_t q = 0; q < redo.size(); q++) if (R.out_n[q] >= 0) new_cap[redo[q]] = std::max<int64_t>(W.out_cap[redo[q]], R.out_n[q]);
+        auto fits = [&](size_t q) { return R.out_n[q] >= 0 && R.out_n[q] <= R.out_cap[q]; };
+        for (size_t q = 0; q < redo.size(); q++) if (fits(q)) new_cap[redo[q]] = std::max<int64_t>(W.out_cap[redo[q]], R.out_n[q]);
         for (int k = 0; k < n; k++) new_off[k + 1] = new_off[k] + new_cap[k];
         std::vector<int32_t> new_stems((size_t)new_off[n] * 3, 0);
         for (int k = 0; k < n; k++) {
@@ -1049,7 +1064,12 @@ static int run_step_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBa
         }
         for (size_t q = 0; q < redo.size(); q++) {
             int k = redo[q];
-            if (R.out_n[q] < 0) { still.push_back(k); continue; }
+            if (!fits(q)) {
+                W.out_n[k] = R.out_n[q];                                // < 0: list overflow again; > cap: the count to run with
+                if (R.out_n[q] > 0) want[k] = R.out_n[q];
+                still.push_back(k);
+                continue;
+            }
             std::copy(R.out_stems.begin() + 3 * R.out_off[q], R.out_stems.begin() + 3 * (R.out_off[q] + R.out_n[q]), new_stems.begin() + 3 * new_off[k]);
             W.out_n[k] = R.out_n[q];
         }
@@ -1154,6 +1174,7 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
         return copy_result(ctx, out);
     }
     if (!ps || n_ps < 1 || n_ps > 64) { ctx->err = "need 1..64 parameter sets"; return SQRN_E_BADARG; }
+    if (in->bpp_mode && n_ps != 1) { ctx->err = "a bpp term belongs to one parameter set: call with n_ps == 1"; return SQRN_E_BADARG; }
     ctx->cres.valid = false;
     ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
     DeviceBatch D;

@@ -119,6 +119,7 @@ struct DevBatch {
     const uint8_t *rclass; const int64_t *rbp_off; const int32_t *rbp;
     const double  *smat;   int L;  const int32_t *cols;
     int            interchainonly;
+    const double  *bpp; const int64_t *bpp_off; int bpp_mode;      // per-sequence N x N term, 1 additive / 2 multiplicative
 };
 
 struct DevWork {
@@ -339,6 +340,7 @@ struct Cfg {
 
 struct State {
     int N, W, WR, nst, nrb, has_sep, has_react, has_smat, default_reacts, region_mode;
+    int bpp_mode; const double *bpp;   // base-pair-probability term of this sequence (seq.py:341-365), 0 / NULL: none
     int dstride, doffset;            // this team scans the anti-diagonals 4 + doffset + dstride * q (cluster: rank, size)
     uint8_t  *code, *rcl, *stlev, *stlev2;
     uint16_t *rcode;
@@ -379,6 +381,7 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
     s.W = L.W; s.WR = L.WR;
     s.N = 0; s.nst = 0; s.nrb = 0; s.has_sep = 0; s.has_react = 0; s.has_smat = 0; s.default_reacts = 1;
     s.region_mode = REGION_AUTO;
+    s.bpp_mode = 0; s.bpp = nullptr;
     s.dstride = 1; s.doffset = 0;
     s.cols = nullptr;
     return s;
@@ -488,6 +491,7 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
         // fast lane: the forward masks come from ballots over the symbols as they are read (one
         // coalesced pass), the reversed ones from the forward words by a funnel shift and a bit reversal
         S.has_react = 0; S.has_smat = 0; S.cols = nullptr; S.default_reacts = 1; S.nrb = 0;
+        S.bpp_mode = 0; S.bpp = nullptr;
         bool sep = false;
         #pragma unroll 1
         for (int k = 0; k < S.W; k++) {
@@ -531,6 +535,8 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
     S.has_react = !C::PLAIN && B.rcode != nullptr;
     S.has_smat = !C::PLAIN && B.smat != nullptr;
     S.cols = (!C::PLAIN && B.cols) ? B.cols + o : nullptr;
+    S.bpp_mode = (!C::PLAIN && B.bpp) ? B.bpp_mode : 0;
+    S.bpp = S.bpp_mode ? B.bpp + B.bpp_off[seq] : nullptr;
     const int Nw = S.W * 32;
     bool sep = false, nondef = false;
     #pragma unroll 1
@@ -837,6 +843,10 @@ __device__ __forceinline__ double cell_score(const State &S, const DevParams &P,
         }
         w = __dmul_rn(w, rf);
     }
+    if (S.bpp_mode) {                                   // seq.py:353-356: scoremat += term, or scoremat *= term
+        const double t = __ldg(&S.bpp[(int64_t)i * S.N + j]);
+        w = S.bpp_mode == 1 ? __dadd_rn(w, t) : __dmul_rn(w, t);
+    }
     if (S.has_smat) w = __dmul_rn(w, __ldg(&B.smat[(int64_t)S.cols[i] * B.L + S.cols[j]]));
     return w;
 }
@@ -846,7 +856,7 @@ template <class C>
 __device__ __forceinline__ double run_score(const State &S, const DevParams &P, const DevBatch &B, int s, int a, int len)
 {
     double sc = 0.0;
-    if (C::PLAIN || (!(S.has_react && !S.default_reacts) && !S.has_smat)) {
+    if (C::PLAIN || (!(S.has_react && !S.default_reacts) && !S.has_smat && !S.bpp_mode)) {
         #pragma unroll 1
         for (int q = 0; q < len; q++) sc = __dadd_rn(sc, P.weight[S.code[a + q] * MAXK + S.code[s - a - q]]);
     } else {
@@ -1636,7 +1646,7 @@ __device__ __forceinline__ double run_score_pos(const State &S, const DevParams 
                                                 double &pos)
 {
     double sc = 0.0, ps = 0.0;
-    const bool simple = C::PLAIN || (!(S.has_react && !S.default_reacts) && !S.has_smat);
+    const bool simple = C::PLAIN || (!(S.has_react && !S.default_reacts) && !S.has_smat && !S.bpp_mode);
     #pragma unroll 1
     for (int q = 0; q < len; q++) {
         double w = simple ? P.weight[S.code[a + q] * MAXK + S.code[s - a - q]] : cell_score(S, P, B, a + q, s - a - q);

@@ -11,9 +11,29 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <new>
+#include <system_error>
 #include <thread>
 #include <vector>
 #include "../../include/sqrn.h"
+
+// fn(0) .. fn(nt - 1), one host thread each.  A thread that cannot be started (std::system_error) does not
+// abort the call: its share, and every later one, runs on the calling thread instead.
+template <class F>
+static void run_threads(int nt, F &fn)
+{
+    if (nt <= 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    int started = 0;
+    try {
+        th.reserve((size_t)nt);
+        for (; started < nt; started++) th.emplace_back([&fn, started] { fn(started); });
+    } catch (const std::system_error &) {
+    } catch (const std::bad_alloc &) {
+    }
+    for (int t = started; t < nt; t++) fn(t);
+    for (auto &x : th) x.join();
+}
 
 namespace {
 
@@ -119,6 +139,7 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
                                int64_t *seq_offsets, uint8_t *seq)
 {
     if (!text || len < 0 || !n_entries || !total_seq) return SQRN_E_BADARG;
+    try {
     int nt = 1;
     if (len >= (4ll << 20)) {
         nt = (int)std::thread::hardware_concurrency();
@@ -134,12 +155,7 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
     }
     std::vector<int64_t> cnt((size_t)nt, 0), tot((size_t)nt, 0);
     std::vector<int> rc((size_t)nt, SQRN_OK);
-    auto run = [&](auto &&fn) {
-        if (nt == 1) { fn(0); return; }
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++) th.emplace_back(fn, t);
-        for (auto &x : th) x.join();
-    };
+    auto run = [&](auto &&fn) { run_threads(nt, fn); };
     // pass 1: counts (and the shape check) per segment
     run([&](int t) {
         const int r = parse_segment(text + cut[(size_t)t], cut[(size_t)t + 1] - cut[(size_t)t], multiline, &cnt[(size_t)t], &tot[(size_t)t],
@@ -161,8 +177,6 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
         if (!cnt[(size_t)t]) return;
         int64_t c = 0, s_ = 0;
         int64_t *so = seq_offsets + n0[(size_t)t];
-        const int64_t last = so[cnt[(size_t)t]];         // the next segment's first offset lives there: keep it
-        (void)last;
         std::vector<int64_t> local((size_t)cnt[(size_t)t] + 1);
         rc[(size_t)t] = parse_segment(text + cut[(size_t)t], cut[(size_t)t + 1] - cut[(size_t)t], multiline, &c, &s_, cnt[(size_t)t], tot[(size_t)t],
                                       name_begin + n0[(size_t)t], name_len + n0[(size_t)t], local.data(), seq + s0[(size_t)t]);
@@ -174,6 +188,7 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
     for (int t = 0; t < nt; t++) if (rc[(size_t)t] != SQRN_OK) return rc[(size_t)t];
     seq_offsets[n] = total;
     return SQRN_OK;
+    } catch (...) { return SQRN_E_NOMEM; }      // out of host memory: nothing crosses the C boundary
 }
 
 // UnAlign (seq.py:236-255) of every parsed sequence in one pass: the symbols without the gap characters
@@ -260,6 +275,7 @@ extern "C" int sqrn_text_format(int64_t first, int64_t count, const char *text, 
     if (!text || !name_begin || !name_len || !seq_offsets || !seq || !sym_offsets || !dbn || !scores || !psname || !written ||
         count < 0)
         return SQRN_E_BADARG;
+    try {
     char cons[48];
     FormatJob J{text, name_begin, name_len, seq_offsets, seq, sym_offsets, dbn, scores, psname, strlen(psname), cons,
                 snprintf(cons, sizeof cons, "\ttop-%d_consensus\n", conslim)};
@@ -270,12 +286,7 @@ extern "C" int sqrn_text_format(int64_t first, int64_t count, const char *text, 
     }
     auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = first + count * t / nthreads; hi = first + count * (t + 1) / nthreads; };
     std::vector<int64_t> start((size_t)count + 1);
-    auto run = [&](auto &&fn) {
-        if (nthreads == 1) { fn(0); return; }
-        std::vector<std::thread> th;
-        for (int t = 0; t < nthreads; t++) th.emplace_back(fn, t);
-        for (auto &x : th) x.join();
-    };
+    auto run = [&](auto &&fn) { run_threads(nthreads, fn); };
     run([&](int t) { int64_t lo, hi; range(t, lo, hi); for (int64_t k = lo; k < hi; k++) start[(size_t)(k - first) + 1] = block_size(J, k); });
     start[0] = 0;
     for (int64_t k = 0; k < count; k++) start[(size_t)k + 1] += start[(size_t)k];
@@ -289,4 +300,5 @@ extern "C" int sqrn_text_format(int64_t first, int64_t count, const char *text, 
     });
     for (int b : bad) if (b) return SQRN_E_BADARG;
     return SQRN_OK;
+    } catch (...) { return SQRN_E_NOMEM; }
 }

@@ -18,16 +18,31 @@ import numpy as np
 
 
 def shard_plan(lengths, world, exponent=2.0):
-    """Deal sequences to `world` queues: longest first, in snake order (0..w-1, w-1..0, ...), so
-    every queue gets the same number of sequences (+-1) and nearly the same sum of N**exponent.
-    Returns a list of int64 index arrays; inside a queue the order is longest first, which is
-    also the order the persistent kernels want (long items first, short ones fill the tail)."""
-    lengths = np.asarray(lengths)
+    """Deal sequences to `world` queues so that the queues carry nearly the same sum of N**exponent
+    (the cost of a sequence: ~N^2 for short ones, ~N^3 above a few hundred nt): longest first, each
+    to the queue with the smallest load so far (LPT).  Sequences of equal length are dealt in blocks
+    -- with a million short sequences the loop runs over the distinct lengths, not over the
+    sequences -- and the queues end up with the same count (+-1) per length.
+    Returns a list of int64 index arrays; inside a queue the order is longest first, which is also
+    the order the persistent kernels want (long items first, short ones fill the tail)."""
+    lengths = np.asarray(lengths).astype(np.int64)
     n = len(lengths)
-    order = np.argsort(-lengths.astype(np.int64), kind="stable")
-    pos = np.arange(n)
-    lap, k = pos // world, pos % world
-    queue = np.where(lap % 2 == 0, k, world - 1 - k)
+    order = np.argsort(-lengths, kind="stable")
+    if world <= 1 or n == 0:
+        return [order] + [np.zeros(0, dtype=np.int64) for _ in range(max(world, 1) - 1)]
+    sl = lengths[order]
+    starts = np.flatnonzero(np.r_[True, sl[1:] != sl[:-1]])           # one block per distinct length
+    ends = np.r_[starts[1:], n]
+    load = np.zeros(world)
+    queue = np.empty(n, dtype=np.int64)
+    for a, b in zip(starts.tolist(), ends.tolist()):
+        cost = float(sl[a]) ** exponent
+        by_load = np.argsort(load, kind="stable")                     # lightest queue first
+        cnt = b - a
+        share = np.full(world, cnt // world, dtype=np.int64)
+        share[:cnt % world] += 1                                      # the extra ones go to the lightest queues
+        queue[a:b] = np.repeat(by_load, share)
+        load[by_load] += share * cost
     return [order[queue == q] for q in range(world)]
 
 

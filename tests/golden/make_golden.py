@@ -8,6 +8,9 @@
     python tests/golden/make_golden.py long     # SQRNdbnseq on 321 .. 1200 nt sequences (minutes)
     python tests/golden/make_golden.py xlong    # three sequences of 2050 .. 2500 nt (tens of minutes)
     python tests/golden/make_golden.py c3       # BASELINE config 3 shape (reactivities + restraints, pl=100), 300 .. 620 nt
+    python tests/golden/make_golden.py c3b N    # one config-3 case of N nt from workloads.config3 (700 / 1100 / 1500: tens of minutes each)
+    python tests/golden/make_golden.py xlong3k  # one plain 3000-nt sequence, 1000nobpp G, pl=1 (config 5 lengths)
+    python tests/golden/make_golden.py c4       # config 4 shape: the reference CLI on a synthetic 64 x 400 alignment
 
 The reference cannot travel to the GPU box, so its outputs are committed here as
 JSON fixtures; tests/test_oracle_golden.py pins the CPU oracle (and the host-side
@@ -291,6 +294,120 @@ def c3_golden():
         dump("seq_api_c3.json", cases)
 
 
+
+def xlong3k_golden():
+    """one plain 3000-nt sequence (config 5 lengths), 1000nobpp G set, pl=1: the reference takes tens of minutes"""
+    import time
+    import workloads
+    sym, off, lens = workloads.config5(1, seed=20261023, lo=3000, hi=3000)
+    seq = sym.tobytes().decode()
+    psets = gsets("1000nobpp")
+    t0 = time.time()
+    out = R.SQRNdbnseq(seq, None, None, None, psets, mp=False, poollim=1, algos={"G"})
+    print("1000nobpp", len(seq), "%.0f s" % (time.time() - t0), flush=True)
+    dump("seq_api_xlong3k.json", [{"conf": "1000nobpp", "poollim": 1, "seq": seq, "reacts": None, "restraints": None,
+                                   "kw": {"rankby": [0, 2, 1]}, "smat": None, "cons": out[0],
+                                   "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]}])
+
+
+def c3b_golden(n):
+    """BASELINE config 3 above 620 nt: ONE case of n nt made by workloads.config3 (reactivity letters, restraints,
+    planted stems), G sets by length (500nobpp's two G sets for 500-999 nt, 1000nobpp above), CLI default pl=100"""
+    import time
+    import workloads
+    (seq, reacts, rest), = workloads.config3(1, seed=20261024 + n, lo=n, hi=n)
+    conf = workloads.config3_conf(n)
+    psets = gsets(conf)
+    t0 = time.time()
+    out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=100, algos={"G"})
+    print(conf, n, "%.0f s" % (time.time() - t0), len(out[1]), "structures", flush=True)
+    # (the per-length files are merged into seq_api_c3b.json afterwards)
+    dump("seq_api_c3b_%d.json" % n, [{"conf": conf, "poollim": 100, "seq": seq, "reacts": reacts, "restraints": rest,
+                                      "kw": {"rankby": [0, 2, 1]}, "smat": None, "cons": out[0],
+                                      "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]}])
+
+
+def c4_golden(n_seqs=64, anc_len=300, n_cols=400, verbose=False):
+    """BASELINE config 4 shape (n_seqs x 400): the reference CLI in alignment mode on workloads.config4"""
+    import subprocess
+    import time
+    import workloads
+    rows, ref = workloads.config4(n_seqs, anc_len, n_cols)
+    name = "ali_c4_%dx%d" % (n_seqs, n_cols)
+    with open(os.path.join(HERE, "inputs", name + ".afa"), "w") as f:
+        f.write(workloads.config4_text(rows, ref))
+    t0 = time.time()
+    argv = ["i=inputs/%s.afa" % name, "a"] + (["v"] if verbose else []) + ["t=3"]
+    out = subprocess.run([sys.executable, os.path.join(REF, "SQUARNA.py")] + argv, cwd=HERE, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    print(name, "%.0f s" % (time.time() - t0), len(out.stdout), "chars", flush=True)
+    with open(os.path.join(HERE, "cli", name + ("_verbose" if verbose else "") + ".txt"), "w") as f:
+        f.write(out.stdout)
+
+
+def bpp_golden():
+    """SQRNdbnseq with the bpp != 0 parameter sets (def.conf, greedy.conf, edmonds / hungarian / nussinov.conf): the REAL
+    reference with tests/fake_rna.py in place of ViennaRNA's RNA module (not installed here) -- pins the additive /
+    multiplicative weighting of the score matrix, the rescale fall-back, the SHAPE hand-over and everything downstream"""
+    from tests import fake_rna
+    sys.modules["RNA"] = fake_rna
+    rng = random.Random(20261025)
+    cases = []
+    plan = [("def", 100, 8, 70, 30), ("greedy", 100, 8, 90, 25), ("greedy", 1, 30, 160, 10), ("edmonds", 100, 8, 90, 8),
+            ("hungarian", 100, 8, 90, 8), ("nussinov", 100, 8, 90, 8), ("def", 5, 20, 100, 8)]
+    for conf, pl, lo, hi, count in plan:
+        names, psets = RC.ParseConfig(os.path.join(REF, conf + ".conf"))
+        assert all(len(p["algorithms"]) == 1 for p in psets), conf
+        for _ in range(count):
+            seq, reacts, rest, kw = rand_case(rng, lo, hi)
+            if conf == "def" and rng.random() < 0.6:
+                kw["priority"] = [k for k, nm in enumerate(names) if nm in ("bppN", "bppH1", "bppH2")]     # the CLI's default
+            if rng.random() < 0.3:
+                kw["conslim"] = rng.choice([1, 2, 3])
+            M, B = rng.choice([(1.8, -0.6), (1.8, -0.6), (2.6, -0.8)])
+            try:
+                out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=pl, M=M, B=B,
+                                   **{k: (set(v) if k == "priority" else v) for k, v in kw.items()})
+            except ZeroDivisionError:
+                continue
+            cases.append({"conf": conf, "poollim": pl, "seq": seq, "reacts": reacts, "restraints": rest, "kw": kw, "M": M, "B": B,
+                          "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+    # one case above 500 nt with 500.conf's sets (autoconfig length class)
+    names, psets = RC.ParseConfig(os.path.join(REF, "500.conf"))
+    seq, reacts, rest, kw = rand_case(rng, 505, 520)
+    out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=3, **kw)
+    cases.append({"conf": "500", "poollim": 3, "seq": seq, "reacts": reacts, "restraints": rest, "kw": kw, "M": 1.8, "B": -0.6,
+                  "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]})
+    dump("seq_api_bpp.json", cases)
+    # entropy of a first parameter set with bpp (greedy.conf: bppG1)
+    ent = []
+    names, psets = RC.ParseConfig(os.path.join(REF, "greedy.conf"))
+    for _ in range(10):
+        seq, reacts, rest, kw = rand_case(rng, 8, 100)
+        out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, entropy=True, interchainonly=kw["interchainonly"])
+        ent.append({"conf": "greedy", "seq": seq, "reacts": reacts, "restraints": rest,
+                    "interchainonly": kw["interchainonly"], "entropy": out})
+    dump("entropy_bpp.json", ent)
+
+
+if __name__ == "__main__" and "bpp" in sys.argv[1:]:
+    bpp_golden()
+    sys.exit(0)
+
+if __name__ == "__main__" and "xlong3k" in sys.argv[1:]:
+    xlong3k_golden()
+    sys.exit(0)
+
+if __name__ == "__main__" and "c3b" in sys.argv[1:]:
+    c3b_golden(int(sys.argv[sys.argv.index("c3b") + 1]))
+    sys.exit(0)
+
+if __name__ == "__main__" and "c4" in sys.argv[1:]:
+    c4_golden(16, verbose=True)
+    c4_golden(64)
+    c4_golden(256)
+    sys.exit(0)
+
 if __name__ == "__main__" and "c3" in sys.argv[1:]:
     c3_golden()
     sys.exit(0)
@@ -331,15 +448,32 @@ CLI_RUNS = {
     "shape_nobpp_opts": ["i=inputs/shape_input.fas", "c=nobpp", "t=4", "pl=50", "tl=4", "ol=6", "cl=2", "rb=dr", "ll=1"],
     "seq_edmondsnobpp": ["i=inputs/seq_input.fas", "c=edmondsnobpp", "t=2"],
     "ali_nobpp": ["i=inputs/ali_input.afa", "a", "c=nobpp", "t=4"],                # alignment mode, step 2 with all five sets
+    "seq_greedynobpp_ent": ["i=inputs/seq_input.fas", "c=greedynobpp", "ent", "t=4"],          # the entropy line
+    "seq_fastest_byseq_ent": ["i=inputs/shape_input.fas", "c=fastest", "byseq", "pl=1", "ent", "t=2"],
+    "ali_demo_ent_verbose": ["i=inputs/demo.afa", "a", "v", "ent", "t=2"],
+    # the CLI's DEFAULT configs (def.conf: 12 sets, 7 of them with bpp) -- with tests/fake_rna.py as the RNA module
+    "seq_default_fakerna": ["i=inputs/seq_input.fas", "t=4"],
+    "inline_default_fakerna": ["s=GGGAAACCCAAAGGGUUUCCCAAAGGCGAAAGCC", "t=2"],
+    "shape_greedy_fakerna": ["i=inputs/shape_input.fas", "c=greedy", "t=2", "pl=20"],
+    # BASELINE config 4 shape: synthetic alignments from workloads.config4 (inputs written by `make_golden.py c4`)
+    "ali_c4_64x400": ["i=inputs/ali_c4_64x400.afa", "a", "t=3"],
+    "ali_c4_256x400": ["i=inputs/ali_c4_256x400.afa", "a", "t=3"],
 }
 
 
 def cli_golden():
     import subprocess
     man = {}
+    only = set(sys.argv[sys.argv.index("cli") + 1:])          # `cli name ...`: regenerate just these texts
     for name, argv in CLI_RUNS.items():
+        env = dict(os.environ)
+        if name.endswith("_fakerna"):
+            env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "_fake_site"), os.path.dirname(os.path.dirname(HERE))])
+        if only and name not in only:
+            man[name] = argv
+            continue
         out = subprocess.run([sys.executable, os.path.join(REF, "SQUARNA.py")] + argv, cwd=HERE,
-                             capture_output=True, text=True)
+                             capture_output=True, text=True, env=env)
         assert out.returncode == 0, (name, out.stderr[-2000:])
         with open(os.path.join(HERE, "cli", name + ".txt"), "w") as f:
             f.write(out.stdout)

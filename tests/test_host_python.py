@@ -299,17 +299,26 @@ class _OracleContext:
     """stands in for the GPU context in CPU tests of the host logic: AnnotateStems and the greedy structures come
     from the oracle (which the -m gpu tests prove bit-identical to the kernels)"""
 
+    @staticmethod
+    def _extras(b, q, k):
+        """(alignment weights, bpp term, bpp mode) of entry k = the q-th of the batch"""
+        import numpy as np
+        p = b["preps"][k]
+        smat = None
+        if b["stemmatrix"] is not None:
+            keep = p.keep
+            smat = np.asarray(b["stemmatrix"], dtype=np.float64)[np.ix_(keep, keep)]
+        bpp = b["opts"].get("bpp")
+        return smat, (bpp[1][q] if bpp else None), (bpp[0] if bpp else 0)
+
     def yield_stems(self, ps, b):
         import numpy as np
         from oracle import oracle as O
         out = []
-        for k in b["idx"]:
+        for q, k in enumerate(b["idx"]):
             p = b["preps"][k]
-            smat = None
-            if b["stemmatrix"] is not None:
-                keep = p.keep
-                smat = np.asarray(b["stemmatrix"], dtype=np.float64)[np.ix_(keep, keep)]
-            st = O.annotate(p.shortseq, ps, p.shortreacts, p.shortrest, (), b["interchainonly"], smat)
+            smat, term, mode = self._extras(b, q, k)
+            st = O.annotate(p.shortseq, ps, p.shortreacts, p.shortrest, (), b["interchainonly"], smat, term, mode)
             out.append((np.array([s[:3] for s in st], dtype=np.int32).reshape(-1, 3), np.array([s[3] for s in st])))
         return out
 
@@ -317,30 +326,70 @@ class _OracleContext:
         import numpy as np
         from oracle import oracle as O
         out = []
-        for k in b["idx"]:
+        for q, k in enumerate(b["idx"]):
             p = b["preps"][k]
-            smat = None
-            if b["stemmatrix"] is not None:
-                keep = p.keep
-                smat = np.asarray(b["stemmatrix"], dtype=np.float64)[np.ix_(keep, keep)]
+            smat, term, mode = self._extras(b, q, k)
             o = b["opts"]
-            prio = [q for q in range(len(paramsets)) if o.get("priority_mask", 0) >> q & 1]
+            prio = [q_ for q_ in range(len(paramsets)) if o.get("priority_mask", 0) >> q_ & 1]
             cons, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, list(paramsets), b["interchainonly"],
                                                o.get("poollim", 1000), smat, o.get("rankby", (0, 2, 1)), prio,
                                                o.get("rankbydiff", False), o.get("conslim", 1), o.get("hardrest", False),
-                                               b["comp"], raw_codes=True)
-            out.append((cons, [(codes, sc, isint, sum(1 << q for q in psl), np.array(stems, dtype=np.int32).reshape(-1, 3))
+                                               b["comp"], raw_codes=True, bpp_term=term, bpp_mode=mode)
+            out.append((cons, [(codes, sc, isint, sum(1 << q_ for q_ in psl), np.array(stems, dtype=np.int32).reshape(-1, 3))
                                for codes, sc, isint, psl, stems, *_ in structs], len(structs)))
         return out
+
+
+def _stand_in(monkeypatch):
+    monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
+    monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
+                        dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
+
+
+def test_bpp_parameter_sets_on_the_host(monkeypatch):
+    """def.conf / greedy.conf / 500.conf / edmonds / hungarian / nussinov.conf -- the configs with bpp != 0 sets, which
+    the CLI uses by default -- against the REAL reference driven by tests/fake_rna.py in place of ViennaRNA
+    (tests/golden/seq_api_bpp.json, entropy_bpp.json): BPPMatrix's calls, the additive / multiplicative terms, one
+    device call per parameter set, host de-duplication and ranking.  Without an RNA module the call raises what the
+    reference raises."""
+    from tests import common as T, fake_rna
+    _stand_in(monkeypatch)
+    S.set_rna_module(None)
+    psets = CLI.ParseConfig(os.path.join(PKG, "def.conf"))[1]
+    for conf in ("def", "500", "1000", "greedy"):                # every default config asks for ViennaRNA
+        with pytest.raises(ModuleNotFoundError):
+            S.SQRNdbnseq("GGGGAAAACCCC", paramsets=CLI.ParseConfig(os.path.join(PKG, conf + ".conf"))[1])
+    S.set_rna_module(fake_rna)
+    try:
+        confs, bad = {}, []
+        cases = load("seq_api_bpp.json")
+        for c in cases:
+            if c["conf"] not in confs:
+                confs[c["conf"]] = CLI.ParseConfig(os.path.join(PKG, c["conf"] + ".conf"))[1]
+            kw = dict(c["kw"])
+            if "priority" in kw:
+                kw["priority"] = set(kw["priority"])
+            kw["rankby"] = tuple(kw["rankby"])
+            got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, confs[c["conf"]], poollim=c["poollim"],
+                               M=c["M"], B=c["B"], **kw)
+            want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+            if not T.same_prediction((got[0], got[1]), want):
+                bad.append((c["conf"], c["seq"], c["kw"]))
+        assert len(cases) >= 90 and not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+        for c in load("entropy_bpp.json"):
+            psets = CLI.ParseConfig(os.path.join(PKG, c["conf"] + ".conf"))[1]
+            got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, psets, entropy=True,
+                               interchainonly=c["interchainonly"])
+            assert got == c["entropy"], (c["seq"], got, c["entropy"])
+    finally:
+        S.set_rna_module(None)
 
 
 def test_non_greedy_parameter_sets_on_the_host(monkeypatch):
     """_predict_many_mixed (Nussinov / Hungarian / Edmonds builders, RunAlgo, de-duplication across parameter sets,
     RankStructs, consensus, hardrest, level limit, alignment weighting) against the 160 cases of tests/golden/algos.json
     and algos_smat.json made by the real reference, with the oracle supplying what the GPU supplies in the -m gpu version of this test"""
-    monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
-    monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
-                        dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
+    _stand_in(monkeypatch)
     from tests import common as T
     import numpy as np
     confs, bad = {}, []
@@ -381,11 +430,9 @@ def test_sqrndbnseq_host_python_on_the_reference_cases(monkeypatch):
     tests/golden/seq_api.json made by the real reference, with the oracle standing in for the GPU call"""
     import numpy as np
     from tests import common as T
-    monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
-    monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
-                        dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
+    _stand_in(monkeypatch)
     confs, bad = {}, []
-    cases = load("seq_api.json") + load("seq_api_long.json") + load("seq_api_c3.json")
+    cases = load("seq_api.json") + load("seq_api_long.json") + load("seq_api_c3.json") + load("seq_api_c3b.json")
     for c in cases:
         if c["conf"] not in confs:
             psets = CLI.ParseConfig(os.path.join(PKG, c["conf"] + ".conf"))[1]
@@ -445,11 +492,11 @@ def test_cli_text_with_the_oracle_standing_in_for_the_gpu(name, monkeypatch):
     Hungarian / Edmonds sets, printing) against the reference's own text (tests/golden/cli/*.txt); the -m gpu
     version of this test (tests/test_gpu_cli.py) runs the same commands on the kernels"""
     from squarna_b200 import SQRNdbnali as A
+    from tests import fake_rna
     _OracleContext.fast_predict = _oracle_fast_predict
-    monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
-    monkeypatch.setattr(S, "_make_batch", lambda preps, idx, comp, stemmatrix, interchainonly, **opts:
-                        dict(preps=preps, idx=idx, comp=comp, stemmatrix=stemmatrix, interchainonly=interchainonly, opts=opts))
+    _stand_in(monkeypatch)
     monkeypatch.setattr(A, "_yield_many", _oracle_yield_many)
+    S.set_rna_module(fake_rna if name.endswith("_fakerna") else None)     # the default configs ask ViennaRNA for bpp
     buf = io.StringIO()
     cwd = os.getcwd()
     os.chdir(G)
@@ -458,6 +505,7 @@ def test_cli_text_with_the_oracle_standing_in_for_the_gpu(name, monkeypatch):
             CLI.Main(_CLI_RUNS[name])
     finally:
         os.chdir(cwd)
+        S.set_rna_module(None)
     with open(os.path.join(G, "cli", name + ".txt")) as f:
         want = f.read()
     got = buf.getvalue()

@@ -32,14 +32,15 @@ def _gsets(configs, conf):
 
 
 @pytest.mark.parametrize("fname,least", [("seq_api.json", 250), ("seq_api_long.json", 20), ("seq_api_xlong.json", 1),
-                                         ("seq_api_c3.json", 5)],
-                         ids=["short", "321-1200nt", "2050-2500nt", "config3-shape"])
+                                         ("seq_api_c3.json", 5), ("seq_api_c3b.json", 7)],
+                         ids=["short", "321-1200nt", "2050-2500nt", "config3-shape", "config3-550-1500nt"])
 def test_seq_api(configs, fname, least):
     """SQRNdbnseq end to end: consensus, every structure, its three scores (incl. the int-0
     quirk) and its parameter-set list, in rank order.  The second file holds sequences of 321 .. 1137 nt,
     the lengths the CTA-team kernels serve; the third three plain sequences of 2050 .. 2500 nt (1024-thread CTAs and
     clusters; minutes each in the reference); the fourth the shape of BASELINE config 3 (300 .. 620 nt, reactivity
-    letters, restraints incl. planted stems, G sets by length, pl=100: up to 173 ranked structures per sequence)."""
+    letters, restraints incl. planted stems, G sets by length, pl=100: up to 173 ranked structures per sequence); the
+    fifth eight config-3 inputs from workloads.config3 at 550 .. 1500 nt (500nobpp's two G sets below 1000 nt, 1000nobpp above)."""
     cases = load(fname)
     assert len(cases) > least
     for c in cases:
