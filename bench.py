@@ -1,28 +1,38 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the greedy hot path on BASELINE.json's config 2:
-synthetic random RNAs, length U{60..200}, `byseq pl=1 c=fastest.conf`.
+"""bench.py -- throughput of the greedy hot path on BASELINE.json's configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--seqs S] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|5] [--seqs S] [--impl ours|reference]
 
-A "step" is one pass of the hot path over one batch of S sequences per GPU
-(default 1 000 000, the configuration the metric is quoted on).  For N > 1 the
-driver launches one process per GPU with torchrun; sequences are independent, so
-ranks shard them with no data-path collective (weak scaling: S per GPU).
+--config 2 (default, the configuration the metric is quoted on): 1 M synthetic random RNAs U{60..200} per GPU,
+            `byseq pl=1 c=fastest.conf`; weak scaling (S per GPU, ranks take disjoint batches).
+--config 5: 10 k sequences U{2900..5000}, 1000nobpp.conf G set, pl=1; STRONG scaling: one global batch, dealt
+            to the ranks by length ** 3 (squarna_b200/sharding.py), results gathered on rank 0 in input order.
+--config 3: 100 k sequences U{300..1500} with reactivity letters and restraints, G sets by length, pl=100
+            (pool rounds); strong scaling; a cap on the number of sequences is named in config.workload.
+
+A "step" is one pass of the hot path over the batch.  For N > 1 the driver launches one process per GPU with
+torchrun; sequences are independent, so there is no data-path collective (NCCL carries only the timing barrier,
+the max over ranks and the gather of finished results).
 
 Printed by rank 0 as ONE JSON line:
-  value    sequences/s with inputs resident in HBM (device-pointer C-ABI call)
-  e2e      same through the host-buffer C-ABI call: pinned host -> device copies
-           and device -> host reads inside the timed region
-  roofline algorithmic bytes per launch / measured kernel time vs measured HBM peak
-  cpu_baseline  the oracle port (oracle/sqrn_oracle.c) on the box's host cores,
-           bounded sample of the same workload
-`--impl reference` times only the CPU oracle port (rank 0; other ranks exit).
+  value    sequences/s with inputs resident in HBM (device-pointer C-ABI call; config 3: the C-ABI batch call
+           on prepared host batches -- its general entry has no device-pointer form)
+  e2e      the same through the host-buffer C-ABI call (config 3: through predict_many from Python strings):
+           host -> device copies and device -> host reads inside the timed region
+  e2e_cli  (config 2, N = 1) the CLI surface: Predict(inputfile=<1 M-sequence FASTA>, c=fastest, byseq, pl=1),
+           text file in, text out
+  roofline algorithmic bytes per launch / measured kernel time vs the measured HBM peak
+  cpu_baseline  the UNMODIFIED Python reference (baseline/_ref/SQUARNA, `byseq t=<cores>`) on a bounded sample of
+           the same workload, and the plain-C oracle port beside it
+`--impl reference` times only the CPU side: the Python reference through its own Predict() (rank 0; other ranks exit).
 """
 import argparse
+import io
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -31,26 +41,54 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SEED = 20261017
+import workloads  # noqa: E402
+
+SEED = workloads.SEED
 FASTEST = dict(algorithms={"G"}, bpp=0.0, bpweights={"GC": 3.25, "AU": 1.25, "GU": -1.25},
                suboptmax=1.0, suboptmin=1.0, suboptsteps=1.0, minlen=4.0, minbpscore=7.0,
                minfinscorefactor=1.25, distcoef=0.09, bracketweight=-2.0, orderpenalty=1.0,
                loopbonus=0.125, maxstemnum=1e6)          # the reference's fastest.conf
 WORKLOAD = "config2: synthetic random RNA, len U{60..200}, byseq pl=1 c=fastest.conf"
+METRIC = {2: "sequences/sec (SQRNdbnseq greedy, byseq pl=1 fastest.conf)",
+          5: "sequences/sec (SQRNdbnseq greedy, 2900-5000 nt, 1000nobpp.conf G set, pl=1)",
+          3: "sequences/sec (SQRNdbnseq greedy, 300-1500 nt, reactivities + restraints, G sets by length, pl=100)"}
+REF_DIR = os.path.join(ROOT, "baseline", "_ref", "SQUARNA")
 
 
 def make_batch(n, seed):
-    rng = np.random.default_rng(seed)
-    lens = rng.integers(60, 201, size=n, dtype=np.int64)
-    off = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(lens, out=off[1:])
-    sym = np.frombuffer(b"ACGU", dtype=np.uint8)[rng.integers(0, 4, size=int(off[-1]), dtype=np.uint8)]
-    return np.ascontiguousarray(sym), off, lens
+    """config 2's batch (kept under this name for the tests)"""
+    return workloads.config2(n, seed)
 
 
 def algorithmic_bytes(lens):
     """ceil(N/4) + 8 + S*(N + 32) + N per sequence, S = 1 structure"""
-    return int(((lens + 3) // 4 + 8 + (lens + 32) + lens).sum())
+    return workloads.algorithmic_bytes(lens)
+
+
+def conf_gsets(name):
+    """bpp-free greedy parameter sets of a shipped .conf (the sets the GPU path serves without ViennaRNA)"""
+    from squarna_b200 import SQUARNA as CLI
+    psets = CLI.ParseConfig(os.path.join(ROOT, "squarna_b200", name + ".conf"))[1]
+    return [p for p in psets if p["algorithms"] == {"G"} and not p.get("bpp", 0)]
+
+
+def host_cores():
+    """cores this process may run on (the box's count when no affinity mask is set)"""
+    try:
+        return len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 class ClockSampler(threading.Thread):
@@ -84,48 +122,128 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_oracle_rate(sym, off, lens, sample, threads):
+# ------------------------------------------------------------------ CPU side: the reference and the port
+def write_fasta(path, sym, off, count, reacts=None, rests=None):
+    with open(path, "w") as f:
+        for b in range(count):
+            f.write(">s%d\n" % b)
+            f.write(sym[int(off[b]):int(off[b + 1])].tobytes().decode())
+            f.write("\n")
+            if reacts is not None:
+                f.write(reacts[b] + "\n" + rests[b] + "\n")
+
+
+def run_python_reference(inp, kwargs, timeout=3600):
+    """the UNMODIFIED reference through its own Predict() in a child process (scripts/ref_runner.py).
+    Returns (seconds inside Predict, output text path) or (None, reason)."""
+    if not os.path.isdir(REF_DIR):
+        return None, "baseline/_ref/SQUARNA is missing (scripts/install_reference.py copies it from /root/reference)"
+    outp = inp + ".out"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ref_runner.py"), inp, outp, json.dumps(kwargs)],
+                         capture_output=True, text=True, timeout=timeout)
+    if res.returncode != 0:
+        return None, "reference failed: " + res.stderr.strip().split("\n")[-1][:200]
+    return json.loads(res.stdout.strip().split("\n")[-1])["seconds"], outp
+
+
+def reference_rate_config2(sym, off, lens, sample, threads, tmpdir):
+    """seq/s of the Python reference on the first `sample` sequences: `byseq pl=1 c=fastest.conf t=threads`
+    (README usage example 9; SQUARNA.py:887-935)"""
+    inp = os.path.join(tmpdir, "ref_c2_%d.fa" % sample)
+    write_fasta(inp, sym, off, sample)
+    secs, outp = run_python_reference(inp, dict(configfile="fastest", byseq=True, poollim=1, threads=threads))
+    if secs is None:
+        return None, outp, None
+    return sample / secs, secs, outp
+
+
+def cpu_oracle_rate(sym, off, lens, sample, threads, ps=None):
     """oracle port on `threads` host threads over the first `sample` sequences"""
     from oracle import oracle as O
     O.lib()
     s_off = off[:sample + 1]
     s_sym = sym[:int(s_off[-1])]
     t0 = time.perf_counter()
-    O.predict_batch_simple(s_sym, s_off, [FASTEST], poollim=1, nthreads=threads)
+    O.predict_batch_simple(s_sym, s_off, [ps or FASTEST], poollim=1, nthreads=threads)
     dt = time.perf_counter() - t0
     return sample / dt, float((lens[:sample].astype(np.float64) ** 2).sum()) / dt, dt
 
 
+def cpu_baseline_config2(sym, off, lens, threads, budget_s=20.0):
+    """both CPU rates on a bounded prefix: the Python reference (kind "reference") and the C port beside it"""
+    with tempfile.TemporaryDirectory() as tmp:
+        cal = min(len(lens), max(threads * 10, 64))                   # one Pool batch per worker (SQUARNA.py:888)
+        rate, secs, _ = reference_rate_config2(sym, off, lens, cal, threads, tmp)
+        ref = None
+        if rate is not None:
+            sample = int(min(len(lens), 20000, max(cal, rate * budget_s)))
+            rate, secs, _ = reference_rate_config2(sym, off, lens, sample, threads, tmp)
+            if rate is not None:
+                ref = {"value": rate, "unit": "seq/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model(),
+                       "nt2_per_s": float((lens[:sample].astype(np.float64) ** 2).sum()) / secs,
+                       "sample": "first %d sequences of the workload, %.1f s inside the reference's own Predict(byseq=True, "
+                                 "poollim=1, configfile='fastest', threads=%d) -- baseline/_ref/SQUARNA, unmodified"
+                                 % (sample, secs, threads)}
+        psample = int(min(len(lens), 50000 * threads))
+        prate, pnt2, pdt = cpu_oracle_rate(sym, off, lens, psample, threads)
+        port = {"value": prate, "unit": "seq/s", "cores": threads, "kind": "port", "nt2_per_s": pnt2,
+                "sample": "first %d sequences, %.1f s, oracle/sqrn_oracle.c (plain-C restatement) on %d threads"
+                          % (psample, pdt, threads)}
+        if ref is None:
+            port["note"] = "Python reference unavailable: " + str(secs)
+            return port
+        ref["port"] = port
+        return ref
+
+
 def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores"""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample = max(1000, min(args.seqs, 3000 * threads))
-    sym, off, lens = make_batch(sample, SEED)
-    for _ in range(min(args.warmup, 1)):
-        cpu_oracle_rate(sym, off, lens, min(sample, 200 * threads), threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_oracle_rate(sym, off, lens, sample, threads)
-    dt = (time.perf_counter() - t0) / args.steps
+    threads = host_cores()
+    if args.config != 2:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the headline config 2; "
+                          "configs 3 and 5 report their CPU baseline inside their own line"}), flush=True)
+        return
+    sym, off, lens = make_batch(min(args.seqs, 40000), SEED)
+    with tempfile.TemporaryDirectory() as tmp:
+        cal = max(threads * 10, 64)
+        rate, secs, _ = reference_rate_config2(sym, off, lens, cal, threads, tmp)
+        if rate is None:                                              # no Python reference on this box: the port
+            sample = max(1000, min(len(lens), 3000 * threads))
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                cpu_oracle_rate(sym, off, lens, sample, threads)
+            dt = (time.perf_counter() - t0) / args.steps
+            kind, how = "port", "oracle/sqrn_oracle.c on %d threads (%s)" % (threads, secs)
+        else:
+            # every step = Predict() on a prefix sized so that steps + warm-ups end within ~3 minutes
+            budget = 200.0 / max(args.steps + min(args.warmup, 1), 1)
+            sample = int(min(len(lens), max(cal, rate * budget)))
+            for _ in range(min(args.warmup, 1)):
+                reference_rate_config2(sym, off, lens, cal, threads, tmp)
+            tot = 0.0
+            for _ in range(args.steps):
+                tot += reference_rate_config2(sym, off, lens, sample, threads, tmp)[1]
+            dt = tot / args.steps
+            kind, how = "reference", ("the reference's own Predict(byseq=True, poollim=1, configfile='fastest', threads=%d), "
+                                      "baseline/_ref/SQUARNA unmodified" % threads)
     val = sample / dt
-    line = {"impl": "reference", "metric": "sequences/sec (SQRNdbnseq greedy, byseq pl=1 fastest.conf)",
-            "value": val, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "nt2_per_s": float((lens.astype(np.float64) ** 2).sum()) / dt,
+    line = {"impl": "reference", "metric": METRIC[2], "value": val, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "nt2_per_s": float((lens[:sample].astype(np.float64) ** 2).sum()) / dt,
             "config": {"workload": WORKLOAD, "seqs_per_step": sample},
-            "cpu_baseline": {"value": val, "unit": "seq/s", "cores": threads, "kind": "port",
-                             "sample": "first %d sequences of the workload per step, oracle/sqrn_oracle.c "
-                                       "(plain-C restatement of the Python reference), %d threads" % (sample, threads)},
+            "cpu_baseline": {"value": val, "unit": "seq/s", "cores": threads, "kind": kind, "cpu_model": cpu_model(),
+                             "sample": "first %d sequences of the workload per step; %s" % (sample, how)},
             "e2e": {"value": val, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def bind_near_gpu(index):
-    """Multi-GPU runs: keep this rank's host threads (and, by first touch, its pinned buffers) on the CPUs NVML
-    names as local to its GPU, so that the H2D / D2H traffic of the end-to-end leg does not cross sockets.
-    Best effort: any failure leaves the affinity alone.  SQRN_BENCH_NO_BIND=1 switches it off."""
+    """Multi-GPU runs: keep this rank's host threads (and, by first touch, its pinned buffers) on the CPUs local to
+    its GPU -- sysfs local_cpulist of the PCI device when it names a proper subset, else NVML's affinity mask --
+    so that the H2D / D2H traffic of the end-to-end leg does not cross sockets.  Best effort: any failure leaves
+    the affinity alone.  SQRN_BENCH_NO_BIND=1 switches it off."""
     if os.environ.get("SQRN_BENCH_NO_BIND"):
         return None
     try:
@@ -138,12 +256,26 @@ def bind_near_gpu(index):
                 return None
             index = int(ids[index])
         handle = pynvml.nvmlDeviceGetHandleByIndex(index)
-        ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
         allowed = os.sched_getaffinity(0)
-        cpus = sorted(c for c in (64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1)
-                      if c in allowed)
-        if len(cpus) >= 4 and len(cpus) < len(allowed):
+        cpus = []
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]
+            with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus += list(range(int(lo), int(hi or lo) + 1))
+            cpus = sorted(c for c in cpus if c in allowed)
+        except Exception:
+            cpus = []
+        if not (4 <= len(cpus) < len(allowed)):
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+            cpus = sorted(c for c in (64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1)
+                          if c in allowed)
+        if 4 <= len(cpus) < len(allowed):
             os.sched_setaffinity(0, cpus)
             return len(cpus)
     except Exception:
@@ -151,29 +283,37 @@ def bind_near_gpu(index):
     return None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--seqs", type=int, default=1_000_000, help="sequences per GPU per step")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
+
+def load_traffic(kernel):
+    """DRAM bytes and issue metrics of one launch of `kernel` from the committed ncu capture (profiles/traffic_latest.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_latest.json")) as f:
+            tr = json.load(f)
+        for rec in (tr if isinstance(tr, list) else [tr]):
+            if rec.get("kernel") == kernel:
+                return rec
+    except Exception:
+        pass
+    return None
+
+
+# ------------------------------------------------------------------------------ configs 2 and 5: the fast lane
+def bench_fast(args, rank, world, local):
     import torch
     import torch.distributed as dist
     from squarna_b200 import _lib
     from squarna_b200._abi import ParamSet
+    from squarna_b200.sharding import shard_plan, take_csr, plan_imbalance
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    cfg = args.config
+    strong = cfg == 5
     torch.cuda.set_device(local)
     bound = bind_near_gpu(local) if world > 1 else None
     if world > 1:
@@ -181,13 +321,26 @@ def main():
     ctx = _lib.Context(local)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    ps = ParamSet.from_dict(FASTEST)
-
-    n = args.seqs
-    sym, off, lens = make_batch(n, SEED + rank)
+    if cfg == 2:
+        psd = FASTEST
+        n_global = args.seqs * world
+        sym, off, lens = make_batch(args.seqs, SEED + rank)                 # weak: every rank its own batch
+        workload = WORKLOAD
+        imbalance = None
+    else:
+        psd = conf_gsets("1000nobpp")[0]
+        n_global = args.seqs
+        gsym, goff, glens = workloads.config5(n_global, SEED)
+        plan = shard_plan(glens, world, 3.0)
+        idx = plan[rank]
+        sym, off = take_csr(gsym, goff, idx)                                 # strong: this rank's queue, longest first
+        lens = np.diff(off)
+        imbalance = plan_imbalance(glens, plan, 3.0)
+        workload = "config5: %d synthetic random RNAs, len U{2900..5000}, 1000nobpp.conf G set, pl=1" % n_global
+    ps = ParamSet.from_dict(psd)
+    n = len(lens)
     total, max_len = int(off[-1]), int(lens.max())
-    # pinned host buffers (e2e leg) and resident device buffers (value leg)
-    h_sym = torch.from_numpy(sym).pin_memory()
+    h_sym = torch.from_numpy(np.ascontiguousarray(sym)).pin_memory()
     h_off = torch.from_numpy(off).pin_memory()
     h_dbn = torch.empty(total, dtype=torch.uint8).pin_memory()
     h_sc = torch.empty(n * 3, dtype=torch.float64).pin_memory()
@@ -232,86 +385,333 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
     stream.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
     dev_ms, _ = timed(step_device, args.steps)
-    # kernel time per step: one k_fast launch (the k_fast_rescan launch behind it finds an empty overflow list)
+    dev_stats = ctx.stats()
     kern_ms = dev_ms / args.steps
-    launches = args.steps * 2          # per step of the timed (device-resident) leg: k_fast<224> + k_fast_rescan<224> behind it
-    for _ in range(2):
+    for _ in range(2 if cfg == 2 else 1):
         step_host()
     _, e2e_wall_ms = timed(step_host, args.steps)
     e2e_stats = ctx.stats()
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # sanity: the e2e leg and the device leg produced the same structures
-    assert np.array_equal(h_dbn.numpy(), d_dbn.cpu().numpy()), "device and host legs disagree"
+    # the two legs produced the same structures, stem counts and (after round(x, 3)) scores
+    assert np.array_equal(h_dbn.numpy(), d_dbn.cpu().numpy()), "device and host legs disagree (dot-brackets)"
+    assert np.array_equal(h_ns.numpy(), d_ns.cpu().numpy()), "device and host legs disagree (stem counts)"
+    dsc, hsc = d_sc.cpu().numpy(), h_sc.numpy()
+    near = np.round(dsc, 3)
+    for k in np.flatnonzero(near != hsc).tolist():                       # rounding ties: Python's round() decides
+        assert round(float(dsc[k]), 3) == float(hsc[k]), "device and host legs disagree (scores)"
 
-    seqs_all = n * world
-    value = seqs_all / (dev_ms / args.steps / 1e3)
-    nt2 = float((lens.astype(np.float64) ** 2).sum()) * world / (dev_ms / args.steps / 1e3)
-    e2e = seqs_all / (e2e_wall_ms / args.steps / 1e3)
+    # strong scaling: finished results gathered on rank 0 in input order (host-side, after the timed region)
+    gathered = None
+    if strong and world > 1:
+        from squarna_b200.sharding import gather_to_root
+        per_seq, per_pos = gather_to_root(idx, {"scores": hsc.reshape(-1, 3), "n_stems": h_ns.numpy()},
+                                          {"dbn": h_dbn.numpy()}, off, goff, rank, world, dist)
+        if rank == 0:
+            gathered = int(per_seq["n_stems"].shape[0]) == n_global and int(per_pos["dbn"].shape[0]) == int(goff[-1])
+
+    value = n_global / (dev_ms / args.steps / 1e3)
+    e2e = n_global / (e2e_wall_ms / args.steps / 1e3)
+    nt2_sum = float((lens.astype(np.float64) ** 2).sum())
+    if world > 1:
+        t = torch.tensor([nt2_sum], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        nt2_sum = float(t[0])
+    nt2 = nt2_sum / (dev_ms / args.steps / 1e3)
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         abytes = algorithmic_bytes(lens)
-        # DRAM traffic of one launch from the committed ncu capture of this same configuration
+        kernel = "k_fast<224>" if cfg == 2 else "k_long<32>"
+        tr = load_traffic(kernel)
         traffic, ncu_note = None, {}
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-            if tr.get("seqs"):
-                # per launch of THIS run: the capture's bytes scaled by the sequence count when the sizes differ
-                traffic = int((tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n / float(tr["seqs"])))
-                ncu_note = {"issue_slots_busy_pct": tr.get("issue_slots_busy_pct"), "ipc_active": tr.get("ipc_active"),
-                            "icc_hit_rate_pct": tr.get("icc_hit_rate_pct"),
-                            "warp_instructions_per_sequence": tr.get("warp_instructions_per_sequence"),
-                            "traffic_source": tr.get("source"), "traffic_capture_seqs": tr["seqs"]}
-        except Exception:
-            pass
+        if tr and tr.get("seqs"):
+            traffic = int((tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n / float(tr["seqs"])))
+            ncu_note = {k: tr.get(k) for k in ("issue_slots_busy_pct", "ipc_active", "icc_hit_rate_pct",
+                                               "warp_instructions_per_sequence", "active_threads_per_warp_instruction")}
+            ncu_note.update({"traffic_source": tr.get("source"), "traffic_capture_seqs": tr["seqs"]})
         achieved = abytes / (kern_ms / 1e3) / 1e9
-        threads = os.cpu_count() or 1
-        sample = min(n, 50000 * threads)          # ~10 s of host work at ~4 k seq/s per core
-        # the host-core baseline is a rank-0, N = 1 leg (the reference arm reports it at every N)
+        threads = host_cores()
         skip_cpu = args.no_cpu or world > 1
-        cpu_rate, cpu_nt2, cpu_dt = (0.0, 0.0, 0.0) if skip_cpu else cpu_oracle_rate(sym, off, lens, sample, threads)
+        if skip_cpu:
+            cpu = {"value": 0.0, "unit": "seq/s", "cores": threads, "kind": "reference",
+                   "sample": "not run (N > 1 or --no-cpu): see the N = 1 line and the reference arm"}
+        elif cfg == 2:
+            cpu = cpu_baseline_config2(sym, off, lens, threads)
+        else:
+            cpu = cpu_baseline_config5(threads, psd, dev_stats, n)
         h2d = int(sym.nbytes + off.nbytes)
         d2h = int(total + n * 3 * 8 + n * 4 + n)
-        line = {"metric": "sequences/sec (SQRNdbnseq greedy, byseq pl=1 fastest.conf)", "value": value, "unit": "seq/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "nt2_per_s": nt2,
-                "config": {"workload": WORKLOAD, "seqs_per_gpu_per_step": n, "total_nt_per_gpu": total,
-                           "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no flush" % ((h2d + d2h) / 1e6),
-                           "sharding": "independent sequences per rank, no collective",
+        line = {"metric": METRIC[cfg], "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "nt2_per_s": nt2,
+                "config": {"workload": workload, "seqs_per_gpu_per_step": n, "total_nt_per_gpu": total,
+                           "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no flush" % ((h2d + d2h) / 1e6)
+                           if cfg == 2 else "every step streams the sequences' candidate lists (GBs) through L2; no flush",
+                           "sharding": ("one global batch dealt by length^3, imbalance %.4f, results gathered on rank 0: %s"
+                                        % (imbalance, gathered)) if strong else "independent sequences per rank, no collective",
                            "host_cpus_bound_to_gpu_locality": bound},
                 "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_wall_ms / args.steps,
                         "kernel_ms_in_step": e2e_stats["kernel_ms"], "launches_per_step": e2e_stats["launches"],
                         "pipeline": "chunked: H2D, kernel and D2H of neighbouring chunks overlap on 4 streams"},
-                "gpu_launches": launches,
+                "gpu_launches": args.steps * (2 if cfg == 2 else max(int(dev_stats["launches"]), 1) * 2),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                             "kernel": "k_fast<224>", "algorithmic_bytes_per_launch": abytes, "kernel_ms": kern_ms,
-                             "note": "issue-bound integer path, not HBM-bound: the kernel keeps ~%s %% of the issue slots busy "
-                                     "(profiles/), its DRAM traffic is about the algorithmic bytes"
-                                     % ncu_note.get("issue_slots_busy_pct", "80"), **ncu_note},
-                "cpu_baseline": {"value": cpu_rate, "unit": "seq/s", "cores": threads, "kind": "port",
-                                 "nt2_per_s": cpu_nt2,
-                                 "sample": ("not run at N > 1 (see the N = 1 line and the reference arm)" if world > 1 else
-                                            "first %d sequences of rank 0's batch, %.1f s, oracle/sqrn_oracle.c on %d threads"
-                                            % (sample, cpu_dt, threads))},
+                             "kernel": kernel, "algorithmic_bytes_per_launch": abytes, "kernel_ms": kern_ms,
+                             "optimal_calls_per_step": dev_stats["optimal_calls"],
+                             "note": "issue / latency-bound integer path, not HBM-bound: see the ncu figures (profiles/)",
+                             **ncu_note},
+                "cpu_baseline": cpu,
                 "clocks": sampler.summary()}
+        if cfg == 2 and world == 1 and not args.no_cli:
+            line["e2e_cli"] = cli_leg(sym, off, lens, h_dbn.numpy())
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cli_leg(sym, off, lens, want_dbn):
+    """the CLI surface on the whole batch: Predict(inputfile=<FASTA>, c=fastest, byseq, pl=1) -- text file in, text out
+    (the bulk text lane: csrc/sqrn_textio.cpp + the fast lane), checked against the C-ABI leg's dot-brackets"""
+    from squarna_b200 import SQUARNA as CLI
+    n = len(lens)
+    with tempfile.TemporaryDirectory() as tmp:
+        inp, outp = os.path.join(tmp, "c2.fa"), os.path.join(tmp, "c2.out")
+        # the FASTA text: ">s<k>\n<sequence>\n", built vectorised (1 M entries)
+        names = np.char.add(np.char.add(">s", np.arange(n).astype(str)), "\n").astype("S")
+        with open(inp, "wb") as f:
+            parts = []
+            for b in range(n):
+                parts.append(names[b])
+                parts.append(sym[int(off[b]):int(off[b + 1])].tobytes())
+                parts.append(b"\n")
+            f.write(b"".join(parts))
+        best = None
+        for _ in range(2):                                   # the second run has the page cache and the contexts warm
+            with open(outp, "w") as sink:
+                t0 = time.perf_counter()
+                CLI.Predict(inputfile=inp, configfile="fastest", byseq=True, poollim=1, write_to=sink)
+                sink.flush()
+                dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        # parity of the text with the C-ABI leg: line 4 of every 6-line block is the consensus dot-bracket
+        ok = True
+        with open(outp, "rb") as f:
+            for b, block in zip(range(2000), iter(lambda: [f.readline() for _ in range(6)], None)):
+                cons = block[3].split(b"\t")[0]
+                if cons != want_dbn[int(off[b]):int(off[b + 1])].tobytes():
+                    ok = False
+        return {"value": n / best, "unit": "seq/s", "seconds": best, "input_bytes": os.path.getsize(inp),
+                "output_bytes": os.path.getsize(outp), "matches_c_abi_leg_first_2000": ok,
+                "call": "Predict(inputfile=<FASTA of %d sequences>, configfile='fastest', byseq=True, poollim=1, write_to=<file>)" % n}
+
+
+def cpu_baseline_config5(threads, psd, dev_stats, n):
+    """The reference needs about an hour per sequence at these lengths (O(N^3); BASELINE.md: 293 s at 1000 nt), so
+    what is timed is bounded and labelled: the C port on `threads` sequences of 2900 nt (the CHEAPEST length of the
+    workload: an upper bound of the CPU rate), and the Python reference on the same number of 2900-nt sequences with
+    maxstemnum=1 (ONE greedy step), extrapolated by the steps per sequence the GPU run counted."""
+    k = max(1, min(threads, 32))
+    sym, off, lens = workloads.config5(k, SEED + 1, lo=2900, hi=2900)
+    rate, nt2, dt = cpu_oracle_rate(sym, off, lens, k, threads, psd)
+    out = {"value": rate, "unit": "seq/s", "cores": threads, "kind": "port", "nt2_per_s": nt2, "cpu_model": cpu_model(),
+           "sample": "%d sequences of 2900 nt (the shortest of the workload: an UPPER bound of the CPU rate), %.1f s, "
+                     "oracle/sqrn_oracle.c on %d threads" % (k, dt, threads)}
+    steps_per_seq = dev_stats["optimal_calls"] / max(n, 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        inp = os.path.join(tmp, "ref_c5.fa")
+        write_fasta(inp, sym, off, k)
+        secs, _ = run_python_reference(inp, dict(configfile="1000nobpp", byseq=True, poollim=1, threads=threads,
+                                                 algorithms="G", maxstemnum=1), timeout=1200)
+    if secs is not None:
+        per_step = secs / (k / min(k, threads))
+        out["reference"] = {"kind": "reference", "seconds_for_one_greedy_step": per_step, "cores": threads,
+                            "extrapolated_seq_per_s": min(k, threads) / (per_step * max(steps_per_seq, 1.0)),
+                            "sample": "the reference's own Predict(byseq, pl=1, c=1000nobpp, algo=G, msn=1) on %d sequences of 2900 nt: "
+                                      "%.1f s = BPMatrix + ONE greedy step each; a full prediction takes ~%.0f steps (counted by "
+                                      "the GPU run), so the rate is EXTRAPOLATED, not measured" % (k, secs, steps_per_seq)}
+    return out
+
+
+# ------------------------------------------------------------------------------ config 3: pool rounds
+def bench_config3(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from squarna_b200 import SQRNdbnseq as S
+    from squarna_b200.sharding import shard_plan, plan_imbalance
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_global = args.seqs
+    entries = workloads.config3(n_global, SEED)
+    glens = np.array([len(e[0]) for e in entries])
+    plan = shard_plan(glens, world, 3.0)
+    idx = plan[rank]
+    mine = [entries[k] for k in idx.tolist()]
+    lens = glens[idx]
+    groups = {}
+    for e in mine:
+        groups.setdefault(workloads.config3_conf(len(e[0])), []).append((e[0], e[1], e[2], None))
+    psets = {c: conf_gsets(c) for c in groups}
+    ctx = S.get_context(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: three passes over a small prefix of every group (module load, parameter digests, scratch buffers)
+    for _ in range(max(args.warmup, 3)):
+        for c, es in groups.items():
+            S.predict_many(es[:8], psets[c], poollim=100, device=local)
+    sampler = ClockSampler(local)
+    sampler.start()
+    # e2e leg: predict_many from Python strings (prepare, pack, C-ABI call with host buffers, result assembly)
+    barrier()
+    t0 = time.perf_counter()
+    kern_ms, launches, calls, structs = 0.0, 0, 0, 0
+    results = {}
+    for _ in range(args.steps):
+        for c, es in groups.items():
+            results[c] = S.predict_many(es, psets[c], poollim=100, device=local)
+            st = ctx.stats()
+            kern_ms += st["kernel_ms"]; launches += st["launches"]; calls += st["optimal_calls"]
+            structs += sum(len(r[1]) for r in results[c])
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    # value leg: the C-ABI batch call alone on prepared batches (no Python preparation / result assembly)
+    batches = []
+    for c, es in groups.items():
+        preps = [S._prepare(*e) for e in es]
+        for comp in (False, True):
+            ii = [k for k, p in enumerate(preps) if p.compensated == comp]
+            if ii:
+                batches.append((c, S._make_batch(preps, ii, comp, None, False, hardrest=False, rankbydiff=False, poollim=100,
+                                                 conslim=1, rankby=(0, 2, 1), priority_mask=0)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for c, b in batches:
+            ctx.predict_batch(psets[c], b)
+    barrier()
+    abi_s = (time.perf_counter() - t0) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([e2e_s, abi_s, kern_ms / args.steps], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(launches), float(calls), float(structs), float((lens.astype(np.float64) ** 2).sum())],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    e2e_s, abi_s, kms = (float(x) for x in t)
+    if rank == 0:
+        peaks = load_peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        s_mean = float(tot[2]) / args.steps / max(n_global, 1)
+        abytes = workloads.algorithmic_bytes(glens, n_structs=min(5.0, s_mean), reacts=True, restraints=True)
+        achieved = abytes / max(kms / 1e3, 1e-9) / 1e9
+        threads = host_cores()
+        cpu = {"value": 0.0, "unit": "seq/s", "cores": threads, "kind": "reference", "sample": "not run (N > 1 or --no-cpu)"}
+        if not (args.no_cpu or world > 1):
+            cpu = cpu_baseline_config3(entries, threads)
+        cap = "" if n_global >= 100000 else " (CAPPED at %d of the 100 000 sequences)" % n_global
+        line = {"metric": METRIC[3], "value": n_global / abi_s, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": abi_s * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "nt2_per_s": float(tot[3]) / abi_s,
+                "config": {"workload": "config3: %d synthetic RNAs%s, len U{300..1500}, rf=26 reactivity letters (3%% '?'), restraints "
+                                       "(5%% '_', 1%% '/', 1%% '\\', 0-2 planted stems), G sets by length (greedynobpp / 500nobpp / "
+                                       "1000nobpp), pl=100" % (n_global, cap),
+                           "warmup_note": "warm-up passes run on an 8-sequence prefix of every length class",
+                           "sharding": "one global batch dealt by length^3, imbalance %.4f" % plan_imbalance(glens, plan, 3.0),
+                           "l2_policy": "inputs larger than L2 per pass; no flush"},
+                "e2e": {"value": n_global / e2e_s, "unit": "seq/s", "ms_per_step": e2e_s * 1e3,
+                        "h2d_bytes_per_step": int(sum(len(e[0]) * 4 + 8 for e in mine)),
+                        "d2h_bytes_per_step": int(float(tot[2]) / args.steps / world * (float(lens.mean()) + 40)),
+                        "call": "squarna_b200.SQRNdbnseq.predict_many(entries, paramsets, poollim=100) per length class"},
+                "gpu_launches": int(float(tot[0])),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                             "kernel": "k_work<8> (MODE_STEP pool rounds)", "algorithmic_bytes_per_launch": abytes,
+                             "kernel_ms": kms, "optimal_calls_per_step": float(tot[1]) / args.steps,
+                             "structures_per_sequence": s_mean},
+                "cpu_baseline": cpu, "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_config3(entries, threads):
+    """the Python reference on a stratified sample (one sequence near 300 / 500 / 800 / 1100 / 1500 nt per worker, at most
+    64 in all): Predict(byseq, algo=G, pl=100) with the reference's own autoconfig replaced by the bpp-free G sets"""
+    targets = [300, 500, 800, 1100, 1500]
+    per = max(1, min(threads, 64) // len(targets))
+    lens = np.array([len(e[0]) for e in entries])
+    pick = []
+    for tlen in targets:
+        order = np.argsort(np.abs(lens - tlen), kind="stable")
+        pick += order[:per].tolist()
+    out = {"unit": "seq/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model()}
+    total_s, per_len = 0.0, {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for conf in ("greedynobpp", "500nobpp", "1000nobpp"):
+            ks = [k for k in pick if workloads.config3_conf(int(lens[k])) == conf]
+            if not ks:
+                continue
+            inp = os.path.join(tmp, "ref_c3_%s.fa" % conf)
+            with open(inp, "w") as f:
+                for k in ks:
+                    f.write(">s%d\n%s\n%s\n%s\n" % (k, entries[k][0], entries[k][1], entries[k][2]))
+            secs, _ = run_python_reference(inp, dict(configfile=conf, byseq=True, poollim=100, threads=threads, algorithms="G",
+                                                     inputformat="qtr", reactformat=26), timeout=3000)
+            if secs is None:
+                out.update({"value": 0.0, "sample": "Python reference unavailable"})
+                return out
+            total_s += secs
+            per_len[conf] = {"sequences": len(ks), "seconds": secs}
+    out.update({"value": len(pick) / total_s, "sample": "stratified sample of %d sequences nearest to 300/500/800/1100/1500 nt, "
+                "the reference's own Predict(byseq, algo=G, pl=100) per length class: %s" % (len(pick), json.dumps(per_len))})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5])
+    ap.add_argument("--seqs", type=int, default=None,
+                    help="config 2: sequences per GPU per step (default 1 000 000); configs 3 / 5: sequences of the global batch")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-cli", action="store_true", help="skip the CLI-level end-to-end leg of config 2")
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {2: 20, 5: 3, 3: 1}[args.config]
+    if args.seqs is None:
+        args.seqs = {2: 1_000_000, 5: 10_000, 3: 100_000 if args.gpus >= 8 else 20_000}[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if args.config == 3:
+        bench_config3(args, rank, world, local)
+    else:
+        bench_fast(args, rank, world, local)
 
 
 if __name__ == "__main__":

@@ -25,9 +25,17 @@ def ReAlignDict(shortseq, longseq):
     return {k: cols[k] for k in range(len(shortseq))}
 
 
-def _yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=0):
-    """entries: [(seq, reacts or None, restraints or None)] (aligned).  One GPU call.
+def _yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=None):
+    """entries: [(seq, reacts or None, restraints or None)] (aligned).  One GPU call per GPU: with several visible
+    devices (device=None) the rows are dealt to one host thread per GPU (the reference's Pool.imap over sequences,
+    ali.py:222-233) and come back in input order.
     Returns per entry (cols int32[n_ungapped], stems int32[k,3] ungapped, scores float64[k])."""
+    if device is None:
+        devs = _seq._resolve_devices(None)
+        if len(devs) > 1 and len(entries) >= 8 * len(devs):
+            return _seq.run_sharded(lambda sub, dev: _yield_many(sub, bpweights, interchainonly, minlen, minbpscore, dev),
+                                    entries, [len(e[0]) for e in entries], devs, exponent=2.0)
+        device = devs[0]
     preps = []
     for seq, reacts, rests in entries:
         seq = seq.upper().replace("T", "U")                           # ali.py:65

@@ -505,7 +505,7 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
     flush()
 
 
-def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=0, slice_entries=131072):
+def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, slice_entries=131072):
     """SQUARNA.py:845-935 for the plain shape of an input.  False: not that shape (nothing was written)."""
     import numpy as np
     from . import _lib
@@ -518,7 +518,14 @@ def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=0, slice
     sym, sym_off = _lib.text_ungap(parsed)                           # UnAlign (seq.py:236-255) on the whole buffer
     if int(np.diff(sym_off).max(initial=0)) > 16000:
         return False
-    ctx = get_context(device)
+    from .SQRNdbnseq import _resolve_devices
+    devs = [device] if device is not None else _resolve_devices(None)
+    if len(devs) > 1 and parsed.n >= 4096 * len(devs):
+        # every visible GPU, one host thread each (the reference's Pool(threads) over sequences, SQUARNA.py:889)
+        from .sharding import MultiGPU
+        ctx = MultiGPU(contexts=[get_context(d) for d in devs])
+    else:
+        ctx = get_context(devs[0])
     try:
         dbn, scores, _nst = ctx.fast_predict(paramset, sym, sym_off)
     except _lib.SqrnError:

@@ -77,11 +77,29 @@ def put_csr(dst_values, dst_offsets, idx, sub_values, sub_offsets):
         dst_values[dst] = sub_values[:total]
 
 
-class MultiGPU:
-    """The fast lane (`byseq pl=1` shape) over several GPUs of one box from one process."""
+def contiguous_plan(lengths, world, exponent=2.0):
+    """Cut the batch into `world` CONTIGUOUS ranges of nearly equal cost (sum of N**exponent): for batches of
+    many short sequences, where any range is a fair sample of the lengths -- the ranges are views of the CSR
+    arrays, nothing is gathered.  Returns world + 1 boundaries."""
+    cost = np.cumsum(np.asarray(lengths, dtype=np.float64) ** exponent)
+    n = len(cost)
+    if n == 0:
+        return np.zeros(world + 1, dtype=np.int64)
+    cuts = np.searchsorted(cost, cost[-1] * np.arange(1, world) / world, side="right")
+    return np.concatenate(([0], np.minimum(cuts, n), [n])).astype(np.int64)
 
-    def __init__(self, devices=None):
+
+class MultiGPU:
+    """The fast lane (`byseq pl=1` shape) over several GPUs of one box from one process: one host thread per
+    GPU (ctypes releases the GIL during the library calls), results in input order."""
+
+    def __init__(self, devices=None, contexts=None):
         from . import _lib
+        self.own = contexts is None
+        if contexts is not None:
+            self.ctx = list(contexts)
+            self.devices = [c.device for c in self.ctx]
+            return
         n = _lib.load().sqrn_device_count()
         if n < 1:
             raise _lib.SqrnError("no usable CUDA device (squarna_b200 has no CPU fallback)")
@@ -89,22 +107,42 @@ class MultiGPU:
         self.ctx = [_lib.Context(d) for d in self.devices]
 
     def close(self):
-        for c in self.ctx:
-            c.close()
+        if self.own:
+            for c in self.ctx:
+                c.close()
 
     def fast_predict(self, paramset, symbols, offsets):
-        """same contract as Context.fast_predict, sequences sharded by length over the GPUs"""
+        """same contract as Context.fast_predict.  Short sequences (all <= 320 nt: warp teams) are cut into
+        contiguous ranges of equal cost; anything longer is dealt by length ** 3 (shard_plan)."""
         offsets = np.asarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
         lens = np.diff(offsets)
-        plan = shard_plan(lens, len(self.ctx))
+        world = len(self.ctx)
         dbn = np.empty(max(int(offsets[-1]), 1), dtype=np.uint8)
         scores = np.empty((max(n, 1), 3), dtype=np.float64)
         nst = np.empty(max(n, 1), dtype=np.int32)
         errors = []
+        contiguous = n > 0 and int(lens.max()) <= 320
+        if contiguous:
+            cuts = contiguous_plan(lens, world)
+            jobs = [(int(cuts[q]), int(cuts[q + 1])) for q in range(world)]
+        else:
+            jobs = shard_plan(lens, world, 3.0)
 
-        def work(ctx, idx):
+        def work(ctx, job):
             try:
+                if contiguous:
+                    lo, hi = job
+                    if hi <= lo:
+                        return
+                    t0, t1 = int(offsets[lo]), int(offsets[hi])
+                    sub_sym = symbols[t0:t1] if t1 > t0 else np.zeros(1, np.uint8)
+                    d, sc, ns = ctx.fast_predict(paramset, np.ascontiguousarray(sub_sym), offsets[lo:hi + 1] - t0)
+                    dbn[t0:t1] = d
+                    scores[lo:hi] = sc
+                    nst[lo:hi] = ns
+                    return
+                idx = job
                 if not len(idx):
                     return
                 sub_sym, sub_off = take_csr(symbols, offsets, idx)
@@ -115,7 +153,7 @@ class MultiGPU:
             except Exception as e:                     # surfaced in the caller's thread
                 errors.append(e)
 
-        threads = [threading.Thread(target=work, args=(c, idx)) for c, idx in zip(self.ctx, plan)]
+        threads = [threading.Thread(target=work, args=(c, job)) for c, job in zip(self.ctx, jobs)]
         for t in threads:
             t.start()
         for t in threads:

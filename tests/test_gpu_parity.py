@@ -316,12 +316,7 @@ def test_long_reference_cases(gpu_ctx):
     with open(os.path.join(here, "golden", "seq_api_long.json")) as f:
         cases = json.load(f)
     confs, bad = {}, []
-    # The fixture was made after the round's GPU budget was spent.  The pl = 1 cases follow a path that was verified
-    # on the GPU against the oracle at these lengths (test_predict_batch_full *_pl1_long), and the oracle reproduces
-    # every case of the fixture on the CPU (tests/test_oracle_golden.py), so they run here; the six pool cases
-    # (pl = 3 / 5 above 320 nt) are left to the CPU tests until they have been seen on a GPU once.
-    cases = [c for c in cases if c["poollim"] == 1]
-    assert len(cases) >= 15
+    assert len(cases) >= 20 and sum(c["poollim"] > 1 for c in cases) >= 6          # pool rounds on CTA teams included
     for c in cases:
         if c["conf"] not in confs:
             psets = CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1]
@@ -359,6 +354,126 @@ def test_rrna_scale_reference_cases(gpu_ctx, cluster):
             assert tuple(float(x) for x in scores[0]) == tuple(float(x) for x in want_sc)
     finally:
         gpu_ctx.set_cluster(0)
+
+
+def _load_golden(name):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)) as f:
+        return json.load(f)
+
+
+def _gsets_of(conf, cache={}):
+    import os
+    from squarna_b200 import SQUARNA as CLI
+    if conf not in cache:
+        pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+        psets = CLI.ParseConfig(os.path.join(pkg, conf + ".conf"))[1]
+        cache[conf] = [p for p in psets if p["algorithms"] == {"G"} and not p["bpp"]]
+    return cache[conf]
+
+
+def test_config3_above_620nt_reference_cases(gpu_ctx):
+    """BASELINE config 3 where round 1 had no GPU parity: 550 .. 1500 nt inputs of workloads.config3 (reactivity
+    letters, restraints, planted stems), 500nobpp's two G sets (500-999 nt) and 1000nobpp (>= 1000 nt) at the CLI's
+    pl=100 -- pool rounds on CTA teams, up to 148 ranked structures -- against the real reference's own output
+    (tests/golden/seq_api_c3b.json), one batched call per config as Predict() makes it"""
+    cases = _load_golden("seq_api_c3b.json")
+    assert len(cases) == 8
+    bad = []
+    for conf in ("500nobpp", "1000nobpp"):
+        sub = [c for c in cases if c["conf"] == conf]
+        got = S.predict_many([(c["seq"], c["reacts"], c["restraints"], None) for c in sub], _gsets_of(conf), poollim=100,
+                             algos=frozenset({"G"}))
+        for c, g in zip(sub, got):
+            want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+            if not T.same_prediction((g[0], g[1]), want):
+                bad.append((conf, len(c["seq"])))
+    assert not bad, "%d of %d differ: %r" % (len(bad), len(cases), bad)
+
+
+@pytest.mark.parametrize("cluster", [1, 0, 8], ids=["one-cta-each", "automatic", "cluster8"])
+def test_config5_lengths_against_the_oracle(gpu_ctx, cluster):
+    """BASELINE config 5 at its stated lengths: 2900 .. 5000 nt (workloads.config5), 1000nobpp G set, pl=1, against the
+    oracle -- one 1024-thread CTA per sequence over its global candidate list, and thread-block clusters sharing one
+    list (8 sequences: fewer than half the SMs, so `automatic` picks clusters too).  The oracle needs minutes per
+    sequence at 5000 nt: its results are computed once per session."""
+    import workloads
+    if "c5" not in _ORACLE_CACHE:
+        parts = [workloads.config5(1, seed=700 + n, lo=n, hi=n) for n in (2900, 3200, 3500, 3800, 4100, 4400, 4700, 5000)]
+        sym = np.concatenate([p[0] for p in parts])
+        off = np.zeros(len(parts) + 1, np.int64)
+        np.cumsum([int(p[2][0]) for p in parts], out=off[1:])
+        import os
+        _ORACLE_CACHE["c5"] = (sym, off, O.predict_batch_simple(sym, off, [T.G1000], poollim=1, nthreads=min(8, os.cpu_count() or 1)))
+    sym, off, (odbn, oscores, onst) = _ORACLE_CACHE["c5"]
+    try:
+        gpu_ctx.set_cluster(cluster)
+        dbn, scores, nst = gpu_ctx.fast_predict(T.G1000, sym, off)
+        st = gpu_ctx.stats()
+    finally:
+        gpu_ctx.set_cluster(0)
+    glyph = np.zeros(256, np.int8)
+    for lv, (o, c) in enumerate(zip(_OPEN, _CLOSE), 1):
+        glyph[ord(o)], glyph[ord(c)] = lv, -lv
+    assert np.array_equal(nst, onst) and np.array_equal(scores, oscores)
+    assert np.array_equal(glyph[dbn], odbn)
+    assert int(np.abs(odbn).max()) >= 3                     # several pseudoknot levels, as config 5 asks
+    assert st["optimal_calls"] >= int(onst.sum())
+
+
+_ORACLE_CACHE = {}
+
+
+def test_rrna_3000nt_reference_case(gpu_ctx):
+    """one plain 3000-nt sequence (config 5 lengths) against the real reference's own output
+    (tests/golden/seq_api_xlong3k.json; about an hour in the reference)"""
+    (c,) = _load_golden("seq_api_xlong3k.json")
+    ps = _gsets_of(c["conf"])[0]
+    sym, off = pack_sequences([c["seq"]])
+    for cluster in (1, 0):
+        try:
+            gpu_ctx.set_cluster(cluster)
+            dbn, scores, _nst = gpu_ctx.fast_predict(ps, sym, off)
+        finally:
+            gpu_ctx.set_cluster(0)
+        want_dbn, want_sc, _ = c["structs"][0]
+        assert bytes(dbn).decode() == want_dbn == c["cons"]
+        assert tuple(float(x) for x in scores[0]) == tuple(float(x) for x in want_sc)
+
+
+def test_bpp_parameter_sets_match_the_reference(gpu_ctx):
+    """bpp != 0 parameter sets (the CLI's default configs): the N x N probability term goes to the device per sequence
+    and parameter set (sqrn_batch.bpp_term) and is added to / multiplied into every cell score -- against the REAL
+    reference driven by tests/fake_rna.py in place of ViennaRNA (tests/golden/seq_api_bpp.json, entropy_bpp.json)"""
+    import os
+    from squarna_b200 import SQUARNA as CLI
+    from tests import fake_rna
+    pkg = os.path.dirname(os.path.abspath(CLI.__file__))
+    S.set_rna_module(fake_rna)
+    try:
+        confs, bad = {}, []
+        cases = _load_golden("seq_api_bpp.json")
+        for c in cases:
+            if c["conf"] not in confs:
+                confs[c["conf"]] = CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1]
+            kw = dict(c["kw"])
+            if "priority" in kw:
+                kw["priority"] = set(kw["priority"])
+            kw["rankby"] = tuple(kw["rankby"])
+            got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, confs[c["conf"]], poollim=c["poollim"],
+                               M=c["M"], B=c["B"], **kw)
+            want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+            if not T.same_prediction((got[0], got[1]), want):
+                bad.append((c["conf"], c["seq"], c["kw"]))
+        assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+        for c in _load_golden("entropy_bpp.json"):
+            psets = CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1]
+            got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, psets, entropy=True,
+                               interchainonly=c["interchainonly"])
+            assert got == c["entropy"], (c["seq"], got, c["entropy"])
+    finally:
+        S.set_rna_module(None)
 
 
 def test_config3_shape_reference_cases(gpu_ctx):

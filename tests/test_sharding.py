@@ -46,6 +46,39 @@ def test_plan_covers_everything_once_and_balances():
     assert SH.plan_imbalance(heavy, SH.shard_plan(heavy, 8), 3.0) > 1.0   # one rRNA dominates: reported, not hidden
 
 
+def test_contiguous_plan_balances_cost():
+    rng = np.random.default_rng(4)
+    lens = rng.integers(60, 201, size=100000)
+    for world in (1, 2, 4, 8):
+        cuts = SH.contiguous_plan(lens, world)
+        assert cuts[0] == 0 and cuts[-1] == len(lens) and (np.diff(cuts) >= 0).all() and len(cuts) == world + 1
+        cost = np.array([(lens[a:b].astype(np.float64) ** 2).sum() for a, b in zip(cuts[:-1], cuts[1:])])
+        assert cost.max() / cost.mean() < 1.001
+    assert SH.contiguous_plan([], 4).tolist() == [0, 0, 0, 0, 0]
+    assert SH.contiguous_plan([10], 3).tolist()[-1] == 1
+
+
+def test_run_sharded_keeps_input_order():
+    """the one-host-thread-per-GPU dealer of predict_many / YieldStems: every item once, results in input order,
+    errors of a worker surface in the caller"""
+    from squarna_b200 import SQRNdbnseq as S
+    items = ["x" * n for n in np.random.default_rng(5).integers(1, 400, size=257).tolist()]
+    seen = []
+
+    def fn(sub, dev):
+        seen.append((dev, len(sub)))
+        return [(dev, len(x)) for x in sub]
+
+    out = S.run_sharded(fn, items, [len(x) for x in items], [0, 1, 2])
+    assert [o[1] for o in out] == [len(x) for x in items] and sorted(d for d, _ in seen) == [0, 1, 2]
+    assert sum(k for _, k in seen) == len(items)
+
+    def bad(sub, dev):
+        raise ValueError("boom")
+    with pytest.raises(ValueError, match="boom"):
+        S.run_sharded(bad, items, [len(x) for x in items], [0, 1])
+
+
 def test_csr_take_put_round_trip():
     sym, off = _batch(2, 300, 0, 90)                        # includes empty sequences
     idx = np.random.default_rng(3).permutation(300)[:170]
@@ -111,3 +144,31 @@ def test_multigpu_equals_single_context(gpu_ctx):
         m.close()
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+    # the dealt (non-contiguous) path: a few sequences above 320 nt send the batch through shard_plan
+    seqs2 = T.rand_seqs(42, 400, 1, 200) + T.rand_seqs(43, 6, 330, 700)
+    sym2, off2 = pack_sequences(seqs2)
+    want2 = gpu_ctx.fast_predict(T.FASTEST, sym2, off2)
+    m = SH.MultiGPU()
+    try:
+        got2 = m.fast_predict(T.FASTEST, sym2, off2)
+    finally:
+        m.close()
+    for a, b in zip(got2, want2):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_predict_many_over_all_gpus_equals_one(gpu_ctx):
+    """predict_many(devices=None) deals the entries to every visible GPU (one host thread each); same predictions,
+    same order as on one device -- pools, restraints, reactivities included"""
+    import random
+    from tests import common as T
+    from squarna_b200 import SQRNdbnseq as S
+    rng = random.Random(77)
+    cases = [T.rand_case(rng, 20, 160) for _ in range(96)]
+    entries = [(c[0], c[1], c[2], None) for c in cases]
+    one = S.predict_many(entries, [T.DEFG1, T.DEFG2], poollim=20, device=0)
+    every = S.predict_many(entries, [T.DEFG1, T.DEFG2], poollim=20, devices=None)
+    assert len(one) == len(every) == len(entries)
+    for a, b in zip(one, every):
+        assert T.same_prediction((a[0], a[1]), (b[0], b[1]))
