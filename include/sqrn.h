@@ -162,6 +162,7 @@ SQRN_API int  sqrn_ctx_set_stream(sqrn_ctx *ctx, void *cuda_stream);
                                         1 never, 2/4/8/16 always with this cluster size */
 #define SQRN_TUNE_NO_GLIST 4         /* 1: CTA teams (> 320 nt) rescan the anti-diagonals every greedy step instead of keeping
                                         the persistent candidate list in global memory (k_long) */
+#define SQRN_TUNE_GL_REBUILD 5       /* passes between two rebuilds (compaction + re-binning) of that list; 0: the default */
 SQRN_API int  sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value);
 
 /* The full "G" path for a batch: replaces SQRNdbnseq.py:1048-1246 (algos == {"G"},

@@ -183,7 +183,7 @@ struct CachedStems {
 
 enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS, B_BPP, B_BPPOFF,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -204,6 +204,7 @@ struct sqrn_ctx {
     int no_cluster = 0, force_cluster = 0;   // tuning knobs: never / always (with this size) use k_cluster for long sequences
     int64_t n_cluster_launches = 0, n_glist_launches = 0;
     int no_glist = 0;            // tuning knob: CTA teams rescan every step (no global persistent list)
+    int gl_rebuild = 0;          // tuning knob: rebuild period of the binned global list in passes (0: the default)
     CachedResult cres; CachedStems cstems;
 };
 
@@ -260,6 +261,7 @@ extern "C" int sqrn_ctx_create(int device, sqrn_ctx **out)
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char *e = getenv("SQRN_GL_REBUILD")) ctx->gl_rebuild = std::max(0, atoi(e));      // experiment knob (SQRN_TUNE_GL_REBUILD)
     *out = ctx;
     return SQRN_OK;
 }
@@ -297,6 +299,7 @@ extern "C" int sqrn_ctx_set_tuning(sqrn_ctx *ctx, int what, int value)
     if (what == SQRN_TUNE_REGION && value >= 0 && value <= 2) { ctx->region_mode = value; return SQRN_OK; }
     if (what == SQRN_TUNE_NO_FAST_KERNEL) { ctx->no_fast_kernel = value != 0; return SQRN_OK; }
     if (what == SQRN_TUNE_NO_GLIST) { ctx->no_glist = value != 0; return SQRN_OK; }
+    if (what == SQRN_TUNE_GL_REBUILD && value >= 0) { ctx->gl_rebuild = value; return SQRN_OK; }
     if (what == SQRN_TUNE_CLUSTER && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) {
         ctx->no_cluster = value == 1; ctx->force_cluster = value > 1 ? value : 0; return SQRN_OK;   // 0 automatic, 1 never, 2..16 always
     }
@@ -411,9 +414,10 @@ static void maybe_glist(sqrn_ctx *ctx, const PEntry &P, Plan &pl, int nmax, int 
     // entries per slot: runs whose positive part reaches minbpscore, ~0.02 N^2 for minlen 2 on random RNA
     const double dens = m >= 4 ? 0.003 : (m == 3 ? 0.008 : 0.02);
     pl.gcap = (long long)(1.5 * dens * nmax * (double)nmax) + 4096;
-    // at most ~6 GB of list space: fewer resident CTAs rather than smaller slots
-    const long long budget = 6ll << 30;
-    if (pl.gcap * 24 * pl.grid_g > budget) pl.grid_g = (int)std::max<long long>(1, budget / (pl.gcap * 24));
+    // a slot is two halves of gcap records (16-byte record + bp score + bin = 25 bytes); at most ~16 GB of list
+    // space: fewer resident CTAs rather than smaller slots
+    const long long budget = 16ll << 30;
+    if (pl.gcap * 50 * pl.grid_g > budget) pl.grid_g = (int)std::max<long long>(1, budget / (pl.gcap * 50));
     pl.glist = true;
 }
 
@@ -519,15 +523,16 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
     if (pl.cluster && use_glist && pl.tw == 32) {
         // a thread-block cluster per sequence over ONE shared candidate list; overflowed items go to k_work<32> behind it
         const int ncl = std::min(pl.grid, std::max(W.n_items, 1));
-        GEnt *ge; double *gb; int32_t *ovf; int *cnt, *gcnt;
-        TRY(dalloc(ctx, W_GENT, (size_t)ncl * pl.gcap, &ge));
-        TRY(dalloc(ctx, W_GBPS, (size_t)ncl * pl.gcap, &gb));
+        GEnt *ge; double *gb; uint8_t *gq; int32_t *ovf; int *cnt, *gcnt;
+        TRY(dalloc(ctx, W_GENT, (size_t)2 * ncl * pl.gcap, &ge));
+        TRY(dalloc(ctx, W_GBPS, (size_t)2 * ncl * pl.gcap, &gb));
+        TRY(dalloc(ctx, W_GQB, (size_t)2 * ncl * pl.gcap, &gq));
         TRY(dalloc(ctx, W_OVF2, (size_t)W.n_items, &ovf));      // not W_OVF: fast-lane chunks on the other stream use that one
         TRY(dalloc(ctx, W_GCNT, 4, &cnt));
-        TRY(dalloc(ctx, W_GCNT2, (size_t)4 * ncl, &gcnt));
+        TRY(dalloc(ctx, W_GCNT2, (size_t)GL_CNT_INTS * ncl, &gcnt));
         CK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
-        CK(cudaMemsetAsync(gcnt, 0, (size_t)4 * ncl * sizeof(int), st));
-        DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_cap = pl.gcap; W1.g_cnt = gcnt;
+        CK(cudaMemsetAsync(gcnt, 0, (size_t)GL_CNT_INTS * ncl * sizeof(int), st));
+        DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_qb = gq; W1.g_cap = pl.gcap; W1.g_cnt = gcnt; W1.g_rebuild = ctx->gl_rebuild;
         W1.ovf_count = cnt; W1.ovf_list = ovf;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(ncl * pl.cluster)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = pl.smem_g; cfg.stream = st;
@@ -561,13 +566,14 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
     if (grid > teams) grid = std::max(teams, 1);
     if (use_glist) {       // items with pre-selected stems (pool tails) have few steps left: they rescan
         const int gg = std::max(1, std::min(pl.grid_g, W.n_items));
-        GEnt *ge; double *gb; int32_t *ovf; int *cnt;
-        TRY(dalloc(ctx, W_GENT, (size_t)gg * pl.gcap, &ge));
-        TRY(dalloc(ctx, W_GBPS, (size_t)gg * pl.gcap, &gb));
+        GEnt *ge; double *gb; uint8_t *gq; int32_t *ovf; int *cnt;
+        TRY(dalloc(ctx, W_GENT, (size_t)2 * gg * pl.gcap, &ge));
+        TRY(dalloc(ctx, W_GBPS, (size_t)2 * gg * pl.gcap, &gb));
+        TRY(dalloc(ctx, W_GQB, (size_t)2 * gg * pl.gcap, &gq));
         TRY(dalloc(ctx, W_OVF2, (size_t)W.n_items, &ovf));      // not W_OVF: fast-lane chunks on the other stream use that one
         TRY(dalloc(ctx, W_GCNT, 4, &cnt));
         CK(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), st));
-        DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_cap = pl.gcap;
+        DevWork W1 = W; W1.g_ent = ge; W1.g_bps = gb; W1.g_qb = gq; W1.g_cap = pl.gcap; W1.g_rebuild = ctx->gl_rebuild;
         const bool trace = getenv("SQRN_TRACE") != nullptr;
         unsigned long long *d_stat = nullptr;
         if (trace) { TRY(dalloc(ctx, W_GSTAT, 16, &d_stat)); CK(cudaMemsetAsync(d_stat, 0, 16 * sizeof(unsigned long long), st)); W1.g_stat = d_stat; }
@@ -586,8 +592,8 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
             CK(cudaMemcpy(h, d_stat, sizeof h, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(hc, cnt, sizeof hc, cudaMemcpyDeviceToHost));
             fprintf(stderr, "[sqrn] k_long<%d>: %d items (%d overflowed), %d CTAs x %lld entries; steps %llu (level changes %llu), "
-                    "entries swept %llu, evaluations %llu, cache resets %llu, cuts %llu\n", pl.tw, W.n_items, hc[0], gg, pl.gcap,
-                    h[3], h[4], h[0], h[1], h[2], h[5]);
+                    "entries swept %llu, evaluations %llu, cache resets %llu, cuts %llu, rebuilds %llu\n", pl.tw, W.n_items, hc[0], gg, pl.gcap,
+                    h[3], h[4], h[0], h[1], h[2], h[5], h[12]);
             fprintf(stderr, "[sqrn]   cycles (thread 0, summed over CTAs, M): build %.1f, loop %.1f = levels %.1f + sweep1 %.1f + sweep2 %.1f + apply %.1f + rest\n",
                     h[9] / 1e6, h[8] / 1e6, h[10] / 1e6, h[6] / 1e6, h[7] / 1e6, h[11] / 1e6);
         }

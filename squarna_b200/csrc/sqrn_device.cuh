@@ -137,8 +137,10 @@ struct DevWork {
     const int     *n_items_dev;  // if set, the item count is read from here (a list an earlier kernel of the stream filled)
     void          *g_ent;        // Cfg::GLIST: persistent candidate lists (16-byte GEnt records), slot b = [b * g_cap, (b + 1) * g_cap)
     double        *g_bps;
-    long long      g_cap;
-    int           *g_cnt;        // cluster flavour: 4 ints per slot -- [0] records in the list, [1] chunk counter of the sweeps
+    uint8_t       *g_qb;         //   bin of every record (gl_bin of its static bound)
+    long long      g_cap;        //   records per HALF slot: a slot is two halves (the rebuild copies from one into the other)
+    int            g_rebuild;    //   rebuild period in passes (0: GL_REBUILD)
+    int           *g_cnt;        // cluster flavour: GL_CNT_INTS ints per slot -- [0] records in the list, [1] chunk counter of the sweeps, [16..] histograms
     unsigned long long *g_stat;      // optional counters: [0] entries swept, [1] ScoreStems evaluations, [2] cache resets,
                                      // [3] steps, [4] steps with a level change, [5] cuts
     int           *ovf_count;    // Cfg::PERSIST kernels: items whose run list overflowed are appended here and
@@ -162,7 +164,7 @@ struct Layout {
     int o_pbps, o_pkey;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
         o_sti, o_stj, o_stl, o_stlev, o_evpos, o_evid, o_cc, o_perm, o_grp, o_gsz,
-        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, o_stlev2, o_evjump, total;
+        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, o_stlev2, o_evjump, o_glx, total;
 };
 
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -241,6 +243,8 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     o = align_up(o, 2);
     L.o_evjump = tw != 1 ? o : -1;                    // CTA teams (and the host emulation, tw = 0): where the arm walk of
     o += tw != 1 ? 4 * L.Scap : 0;                    // ScoreStems may jump to (team_apply_stem)
+    o = align_up(o, 4);
+    L.o_glx = o;     o += pcap < 0 ? 4 * (3 * 256 + 4) : 0;   // global list: histogram, bin ends, scatter cursors (gl_make_bins)
     L.total = align_up(o, 16);
     return L;
 }
@@ -346,7 +350,7 @@ struct State {
     uint16_t *rcode;
     int16_t  *partner, *owner, *sepcnt, *sti, *stj, *stl, *evpos, *evid, *evjump, *perm, *grp, *rbv, *rbw;
     uint32_t *M, *PR, *rowok, *colokR, *Ub, *ckey, *rkey, *pkey;
-    int32_t  *cc, *gsz, *Ubase;
+    int32_t  *cc, *gsz, *Ubase, *ghist, *gbend, *gcur;
     uint16_t *clen, *rlen;
     double   *cbps, *cfin, *red, *pbps;
     unsigned char *xchg;
@@ -378,6 +382,7 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
     s.red = (double *)(base + L.o_red);
     s.xchg = base + L.o_xchg;
     s.misc = (int *)(base + L.o_misc);
+    s.ghist = (int32_t *)(base + L.o_glx);  s.gbend = s.ghist + 256;  s.gcur = s.gbend + 260;
     s.W = L.W; s.WR = L.WR;
     s.N = 0; s.nst = 0; s.nrb = 0; s.has_sep = 0; s.has_react = 0; s.has_smat = 0; s.default_reacts = 1;
     s.region_mode = REGION_AUTO;
@@ -778,7 +783,70 @@ __device__ int team_levels(State &S, int added = -1)
             S.perm[rank] = (int16_t)t;
         }
         Team<TW>::sync();
-        if (r == 0) {
+        bool serial = true;
+#ifndef SQRN_HOST_EMU
+        if (TW > 1) {
+            // CTA teams (hundreds of stems): perm[] is sorted by cross_count, so the stems that cross nothing come
+            // first and all join group 0; the others are placed one after the other (the order matters) by warp 0,
+            // a lane per earlier crossing stem: bit h of the clash mask = group h holds a stem that crosses this
+            // one, first-fit = its lowest clear bit.  More than 64 groups: the serial loop below.
+            if (r < 32) {
+                const int lane = r;
+                int n0 = 0, sz0 = 0;
+                #pragma unroll 1
+                for (int a0 = 0; a0 < n; a0 += 32) {
+                    const int a = a0 + lane;
+                    bool z = false; int l = 0;
+                    if (a < n) { const int t = S.perm[a]; z = S.cc[t] == 0; if (z) { S.grp[t] = 0; l = S.stl[t]; } }
+                    const int nz = __popc(__ballot_sync(0xffffffffu, z));
+                    n0 += nz;
+                    sz0 += __reduce_add_sync(0xffffffffu, l);
+                    if (nz < 32) break;
+                }
+                int ngw = 0, over = 0;
+                if (n0 > 0) { ngw = 1; if (lane == 0) S.gsz[0] = sz0; }
+                __syncwarp();
+                #pragma unroll 1
+                for (int a = n0; a < n; a++) {
+                    const int t = S.perm[a], i = S.sti[t], j = S.stj[t];
+                    uint32_t mlo = 0, mhi = 0;
+                    #pragma unroll 1
+                    for (int b = n0 + lane; b < a; b += 32) {
+                        const int u = S.perm[b];
+                        if (stems_cross(i, j, S.sti[u], S.stj[u])) { const int h = S.grp[u]; if (h < 32) mlo |= 1u << h; else mhi |= 1u << (h - 32); }
+                    }
+                    mlo = __reduce_or_sync(0xffffffffu, mlo); mhi = __reduce_or_sync(0xffffffffu, mhi);
+                    const int g = ~mlo ? __ffs(~mlo) - 1 : (~mhi ? 32 + __ffs(~mhi) - 1 : 64);
+                    if (g >= 64) { over = 1; break; }
+                    if (lane == 0) { S.grp[t] = (int16_t)g; S.gsz[g] = (g == ngw ? 0 : S.gsz[g]) + S.stl[t]; }
+                    if (g == ngw) ngw++;
+                    __syncwarp();
+                }
+                // does the first-created group (home of every stem that crosses nothing) rank first?
+                bool bigger = false;
+                #pragma unroll 1
+                for (int h = 1 + lane; h < ngw; h += 32) if (S.gsz[h] > S.gsz[0]) bigger = true;
+                bigger = __any_sync(0xffffffffu, bigger);
+                if (lane == 0) { S.misc[5] = ngw; S.misc[13] = bigger ? 0 : 1; S.misc[6] = over; }
+            }
+            __syncthreads();
+            serial = S.misc[6] != 0;
+            if (!serial) {
+                // groups.sort(key=len, reverse=True) is stable: level = 1 + #groups that come first
+                const int ngw = S.misc[5];
+                #pragma unroll 1
+                for (int t = r; t < n; t += T) {
+                    const int g = S.grp[t], sz = S.gsz[g];
+                    int lev = 1;
+                    #pragma unroll 1
+                    for (int h = 0; h < ngw; h++)
+                        if (S.gsz[h] > sz || (S.gsz[h] == sz && h < g)) lev++;
+                    S.stlev[t] = (uint8_t)(lev > 255 ? 255 : lev);
+                }
+            }
+        }
+#endif
+        if (serial && r == 0) {
             ng = 0;
             #pragma unroll 1
             for (int a = 0; a < n; a++) {
@@ -1815,20 +1883,32 @@ __device__ Best persist_step(State &S, const DevParams &P, const DevBatch &B, co
 // Long sequences have 10^5 .. 10^6 maximal runs and hundreds of greedy steps; rescanning them
 // costs O(N^2) cell visits plus a ScoreStems region walk per surviving candidate per step.  Here
 // the runs are enumerated ONCE into a per-CTA list in global memory (key, length, bp score) and
-// every entry CACHES what the last evaluation found:
+// every record CACHES what the last evaluation found:
 //   FRESH   nothing known;
-//   EVAL    g_fin = the adjusted score (ScoreStems) under the structure it was evaluated with;
-//   PRUNED  g_fin = an upper bound of the adjusted score (tight_bound) that was below the best score of
+//   EVAL    v = the adjusted score (ScoreStems) under the structure it was evaluated with;
+//   PRUNED  v = an upper bound of the adjusted score (tight_bound) that was below the best score of
 //           the step that looked at it;  PRUNED1: the same with score_bound, which does not depend on
 //           the structure and therefore never goes stale;
 //   BELOW   the run's bp score is under minbpscore: no candidate as it stands, kept because a piece of
 //           it may be one after a cut.
-// A step (gl_step) makes two coalesced sweeps over the list:
-//   1. cut the runs that touch the stem T just selected (as persist_step does), put the entries
-//      whose cached value may have changed back to FRESH, and take the arg-max of the cached
-//      scores that are still valid -> the floor;
-//   2. look at FRESH entries and at PRUNED entries whose bound reaches the floor: bounds first,
-//      ScoreStems only for what passes.
+//
+// The list is BINNED by a static upper bound.  gl_ub0 bounds the adjusted score of a run AND of every
+// piece a later cut can leave of it (sum of the positive cells x the largest value of every factor of
+// seq.py:732, the tetraloop factor exact); gl_bin maps it monotonically to one of 256 bins and the
+// records lie in descending bin order (two enumeration passes: histogram, then scatter).  A greedy
+// step only has to look at the records whose bound reaches its best score -- a PREFIX of the list:
+//   * the prefix [0, done) is found by rounds: the floor known so far (last step's runner-ups, then
+//     the best of the round) gives the bin the next round has to reach;
+//   * records behind the prefix are not touched at all -- not even cut.  When the floor drops and
+//     they enter the prefix they are CAUGHT UP from the unpaired mask (a cell is live iff both of
+//     its positions are still unpaired: the masked matrix only loses cells, seq.py:446-451) and
+//     start FRESH;
+//   * records that were in the prefix of the previous step are up to date but for the stem T just
+//     selected: they are revised incrementally (cut if T meets them; cached value dropped if T may
+//     have changed it -- see below);
+//   * pieces that cuts append live in an unsorted tail behind the bins and are always swept;
+//   * every GL_REBUILD steps the whole list is caught up, the dead records are dropped and the
+//     survivors are re-binned into the other half of the slot (their bounds only shrink).
 // When does the adjusted score of a candidate c = (oi, oj, len), innermost pair (ss, se), change?
 // ScoreStems reads (seq.py:607-751) the partners of the positions in (ss, se) and within five of
 // the outermost pair, and the levels of the selected stems with a wing inside (ss, se).  So T can
@@ -1836,20 +1916,44 @@ __device__ Best persist_step(State &S, const DevParams &P, const DevBatch &B, co
 // selected stem B that itself lies inside (ss, se): positions under B are behind `inblockend`
 // (seq.py:672-689) both before and after.  The host of T ("encloser": the selected stem with the
 // largest i that encloses T) is found once per step.  Levels: if the level of any OLD stem
-// changed when T was added, every EVAL entry goes back to FRESH.
+// changed when T was added, every EVAL record that counted a wing goes back to FRESH.
 #ifdef SQRN_HOST_EMU
 static inline long long gl_clock() { return 0; }
+static long g_emu_gl_rebuilds = 0, g_emu_gl_catchups = 0;      // tests assert that these paths really ran
+static int g_emu_gl_rebuild_every = 0;                          // tests: rebuild period (0: default)
 #else
 __device__ __forceinline__ long long gl_clock() { return clock64(); }
 #endif
 constexpr uint32_t GK_DEAD = 0xffffffffu;
 constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u, GS_PRUNED1 = 4u;
 constexpr uint32_t GS_MASK = 7u, GS_LEVELS = 8u;      // GS_LEVELS (with EVAL): the score involves pseudoknot levels
+constexpr int GL_NBIN = 256;
+constexpr int GL_REBUILD = 16;    // default rebuild period (DevWork::g_rebuild overrides)
 
-// one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16, v = the cached score / bound
+// one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16 | stamp << 20, v = the cached score / bound
 struct alignas(16) GEnt { uint32_t key, meta; double v; };
-struct GList { GEnt *ent; double *bps; int cap; unsigned long long *stat; int *cnt; };
+// a slot holds two halves of `cap` records (the rebuild copies from one into the other)
+struct GList { GEnt *ent; double *bps; uint8_t *qb; int cap; unsigned long long *stat; int *cnt; int rebuild; };
+// what the team remembers about its list between two passes (uniform over the team / cluster)
+struct GState { int n_sorted, n_inc, half, since; };
 constexpr int GL_BATCH = 8;       // records a thread loads back to back before it looks at any (memory-level parallelism)
+constexpr int GL_CNT_INTS = 16 + 16 * GL_NBIN;      // cluster flavour: ints per slot in DevWork::g_cnt ([0] records, [1] chunk counter, [16 + 256 rank + q] histograms)
+
+#ifdef SQRN_HOST_EMU
+constexpr int GL_WL = 1;
+static inline uint32_t gl_ballot(bool p) { return p ? 1u : 0u; }
+static inline int gl_bcast0(int v) { return v; }
+static inline void gl_wsync() {}
+static inline int gl_lane() { return 0; }
+static inline int gl_wid() { return 0; }
+#else
+constexpr int GL_WL = 32;
+__device__ __forceinline__ uint32_t gl_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+__device__ __forceinline__ int gl_bcast0(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ void gl_wsync() { __syncwarp(); }
+__device__ __forceinline__ int gl_lane() { return threadIdx.x & 31; }
+__device__ __forceinline__ int gl_wid() { return threadIdx.x >> 5; }
+#endif
 
 __device__ __forceinline__ GEnt gl_load(const GEnt *p)
 {
@@ -1893,6 +1997,44 @@ __device__ __forceinline__ double tight_bound(const State &S, const DevParams &P
     return __dmul_rn(u, tf);
 }
 
+// Static bound of the run (s, a, len) and of every piece of it: `pos` (the sum of its positive cells)
+// bounds the bp score of any piece, every factor of seq.py:732 takes its largest value in the same
+// order with the same rounding (score_bound), and the tetraloop factor is 1.25 only if the run holds
+// the one cell of its diagonal that closes a four-position hairpin with the GNRA pattern (a piece
+// can only have it as its innermost cell).
+__device__ __forceinline__ double gl_ub0(const State &S, const DevParams &P, int s, int a, int len, double pos)
+{
+    if (!(pos > 0.0)) return 1e300;
+    double tf = 1.0;
+    const int t = s - a, d = t - a - 5;
+    if (d >= 0 && !(d & 1) && (d >> 1) < len) {
+        const int ss = a + (d >> 1);
+        if (S.code[ss + 1] == CODE_G && (S.code[ss + 3] == CODE_G || S.code[ss + 3] == CODE_A) && S.code[ss + 4] == CODE_A) tf = 1.25;
+    }
+    double u = __dmul_rn(pos, P.sdf_max);
+    u = __dmul_rn(u, P.of_max);
+    u = __dmul_rn(u, P.lf_max);
+    return __dmul_rn(u, tf);
+}
+
+// monotone map of a score (bound or floor) to a bin: linear between minfinscore and five times that, clamped
+__device__ __forceinline__ int gl_bin(const DevParams &P, double u)
+{
+    const double lo = P.minfinscore > 0.0 ? P.minfinscore : 1.0;
+    if (!(u > lo)) return 0;
+    const double x = (u - lo) * ((GL_NBIN - 2) / (4.0 * lo));
+    return x >= (double)(GL_NBIN - 2) ? GL_NBIN - 1 : (int)x;
+}
+
+// 32 bits of the unpaired mask starting at position p0 (positions outside the sequence read as 0)
+__device__ __forceinline__ uint32_t unpaired_bits32(const State &S, int p0)
+{
+    const int w = p0 >> 5, sh = p0 & 31;
+    const uint32_t lo = (w >= 0 && w < S.W) ? S.Ub[w] : 0u, hi = (w + 1 >= 0 && w + 1 < S.W) ? S.Ub[w + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ bool unpaired_at(const State &S, int p) { return (S.Ub[p >> 5] >> (p & 31)) & 1u; }
+
 __device__ __forceinline__ bool gl_wanted(int N, const DevParams &P, long long cap)
 {
     if (cap <= 0 || N > 32767 || !P.ub_ok || !(P.loopbonus >= 0.0)) return false;
@@ -1908,31 +2050,23 @@ template <class C>
 __device__ __forceinline__ void gl_sync()
 {
 #ifndef SQRN_HOST_EMU
-    if (C::CLUSTER) { cooperative_groups::this_cluster().sync(); return; }
+    if (C::CLUSTER) { __threadfence(); cooperative_groups::this_cluster().sync(); return; }
 #endif
     Team<C::TW>::sync();
 }
 template <class C>
 __device__ __forceinline__ bool gl_leader(const State &S) { return Team<C::TW>::rank() == 0 && (!C::CLUSTER || S.doffset == 0); }
 
-// Enumerates the maximal runs of the current structure state into the global list (a warp per
-// anti-diagonal, a word per lane).  false: overflow.
-template <class C>
-__device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const GList &g)
+// Calls emit(s, a, len) for every maximal run of at least P.m cells of the current masked matrix: a warp
+// per anti-diagonal, a word per lane.  Diagonals are dealt statically (two calls visit the same runs in
+// the same threads).
+template <class C, class F>
+__device__ __forceinline__ void gl_enum(const State &S, const DevParams &P, const DevBatch &B, F &&emit)
 {
     constexpr int TW = C::TW;
-    const int r = Team<TW>::rank();
-#ifdef SQRN_HOST_EMU
-    constexpr int WL = 1;
-    const int lane = 0, wid = 0, nw = 1;
-#else
-    constexpr int WL = 32;
-    const int lane = threadIdx.x & 31, wid = r >> 5, nw = TW;
-#endif
+    const int lane = gl_lane(), wid = gl_wid();
+    const int nw = TW > 0 ? TW : 1;
     const int smax = 2 * S.N - 6;
-    int *np = C::CLUSTER ? &g.cnt[0] : &S.misc[8];        // records in the list
-    if (gl_leader<C>(S)) *np = 0;
-    gl_sync<C>();
     const int gw = C::CLUSTER ? S.doffset * nw + wid : wid, gnw = C::CLUSTER ? S.dstride * nw : nw;
     #pragma unroll 1
     for (int s = 4 + gw; s <= smax; s += gnw) {
@@ -1941,7 +2075,7 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
         const int k1 = hi >> 5;
         uint32_t carry_top = 0;
         #pragma unroll 1
-        for (int kb = lo >> 5; kb <= k1; kb += WL) {
+        for (int kb = lo >> 5; kb <= k1; kb += GL_WL) {
             const int k = kb + lane;
             const uint32_t x = k <= k1 ? diag_word<C>(S, P, s, k, lo, hi) : 0u;
 #ifdef SQRN_HOST_EMU
@@ -1974,35 +2108,106 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
                 }
                 const int len = e - a + 1;
                 if ((double)len < P.minlen) continue;
-                double pos;
-                const double sc = run_score_pos<C>(S, P, B, s, a, len, pos);
-                if (!(pos >= P.minbpscore)) continue;
-                const int slot = atomicAdd(np, 1);
-                if (slot < g.cap) {
-                    gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)a, (uint32_t)len | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
-                    g.bps[slot] = sc;
-                }
+                emit(s, a, len);
             }
         }
     }
-    ((int *)S.cbps)[r] = -1;                          // gl_step: no remembered best yet
-    gl_sync<C>();
-    return *(volatile int *)np <= g.cap;
 }
 
-// One OptimalStems pass over the global list: ONE coalesced sweep.  (ui, uj, ul): the stem T applied since
-// the last pass (ul = 0: none); (ei, ej): the selected stem enclosing T with the largest i (ei < 0: none);
-// relevel: the level of some older stem changed when T was added; step: number of this pass (stamps the
-// records it has brought up to date, so that nothing is revised twice).  ok = false: overflow.
+// From the team's histogram S.ghist[] (records per bin counted by THIS CTA): S.gbend[q] = records in the bins
+// >= q (bins lie in descending order: bin q occupies [gbend[q + 1], gbend[q])), S.gcur[q] = where this CTA's
+// records of bin q start.  Returns the number of records.  A cluster adds up the histograms of its CTAs
+// through global memory; each CTA's records of a bin follow those of the lower ranks.
+template <class C>
+__device__ int gl_make_bins(State &S, const GList &g)
+{
+    constexpr int TW = C::TW;
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    Team<TW>::sync();             // the histogram is complete
+#ifndef SQRN_HOST_EMU
+    if (C::CLUSTER) {
+        int *gh = g.cnt + 16;
+        #pragma unroll 1
+        for (int q = r; q < GL_NBIN; q += T) gh[GL_NBIN * S.doffset + q] = S.ghist[q];
+        gl_sync<C>();
+        #pragma unroll 1
+        for (int q = r; q < GL_NBIN; q += T) {
+            int tot = 0, before = 0;
+            #pragma unroll 1
+            for (int k = 0; k < S.dstride; k++) { const int h = *(volatile int *)&gh[GL_NBIN * k + q]; tot += h; if (k < S.doffset) before += h; }
+            S.ghist[q] = tot; S.gcur[q] = before;
+        }
+        Team<TW>::sync();
+    } else
+#endif
+    {
+        #pragma unroll 1
+        for (int q = r; q < GL_NBIN; q += T) S.gcur[q] = 0;
+        Team<TW>::sync();
+    }
+    if (r == 0) {
+        int acc = 0;
+        S.gbend[GL_NBIN] = 0;
+        #pragma unroll 1
+        for (int q = GL_NBIN - 1; q >= 0; q--) { S.gcur[q] += acc; acc += S.ghist[q]; S.gbend[q] = acc; }
+    }
+    gl_sync<C>();                 // (cluster: nobody overwrites its histogram in global memory before everyone has read it)
+    return S.gbend[0];
+}
+
+// Enumerates the maximal runs of the current structure state into the global list, binned by their static
+// bound (two enumeration passes: histogram, scatter).  false: overflow.
+template <class C>
+__device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const GList &g, GState &gs)
+{
+    constexpr int TW = C::TW;
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    int *np = C::CLUSTER ? &g.cnt[0] : &S.misc[8];        // records in the list
+    #pragma unroll 1
+    for (int q = r; q < GL_NBIN; q += T) S.ghist[q] = 0;
+    Team<TW>::sync();
+    gl_enum<C>(S, P, B, [&](int s, int a, int len) {
+        double pos;
+        run_score_pos<C>(S, P, B, s, a, len, pos);
+        if (!(pos >= P.minbpscore)) return;
+        atomicAdd(&S.ghist[gl_bin(P, gl_ub0(S, P, s, a, len, pos))], 1);
+    });
+    const int n = gl_make_bins<C>(S, g);
+    gs.n_sorted = n; gs.n_inc = n; gs.half = 0; gs.since = 0;
+    ((int *)S.cbps)[r] = -1;                          // gl_step: no remembered best yet
+    if (gl_leader<C>(S)) *np = n;
+    if (n > g.cap) { gl_sync<C>(); return false; }
+    gl_enum<C>(S, P, B, [&](int s, int a, int len) {
+        double pos;
+        const double sc = run_score_pos<C>(S, P, B, s, a, len, pos);
+        if (!(pos >= P.minbpscore)) return;
+        const int q = gl_bin(P, gl_ub0(S, P, s, a, len, pos));
+        const int slot = atomicAdd(&S.gcur[q], 1);
+        gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)a, (uint32_t)len | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
+        g.bps[slot] = sc;
+        g.qb[slot] = (uint8_t)q;
+    });
+    gl_sync<C>();
+    return true;
+}
+
+// One OptimalStems pass over the global list.  (ui, uj, ul): the stem T applied since the last pass (ul = 0:
+// none); (ei, ej): the selected stem enclosing T with the largest i (ei < 0: none); relevel: the level of some
+// older stem changed when T was added; step: number of this pass (stamps the records it has brought up to
+// date, so that nothing is revised twice).  ok = false: overflow.
 //
+//   rebuild   (every g.rebuild passes) the whole list is brought up to date, dead records are dropped and the
+//             rest is re-binned into the other half of the slot;
 //   prologue  every thread re-checks the record that was ITS best in the previous pass; what is still a valid
 //             cached score gives the floor before the sweep starts (usually last pass's runner-up);
-//   sweep     per record: cut / invalidate against T (`revise`), arg-max of the cached scores that hold, and
-//             FRESH records or PRUNED ones whose bound reaches the floor go to a per-warp list that is
-//             SCREENED 32 at a time (bounds); what passes goes to a second list EVALUATED 32 at a time;
+//   rounds    the prefix of the binned list whose bounds reach the floor (plus the tail of appended pieces) is
+//             swept -- per record: cut / invalidate against T (`revise`), arg-max of the cached scores that
+//             hold; FRESH records or PRUNED ones whose bound reaches the floor go to a per-warp list that is
+//             SCREENED 32 at a time (bounds); what passes goes to a second list EVALUATED 32 at a time.  The
+//             best of a round is the floor of the next one, until the prefix stops growing;
 //   epilogue  the pieces appended by the cuts of this pass (behind the old end of the list) are screened too.
 template <class C>
-__device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const GList &g, int ui, int uj, int ul,
+__device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const GList &g, GState &gs, int ui, int uj, int ul,
                         int ei, int ej, bool relevel, bool &ok, int &xc, int step)
 {
     constexpr int TW = C::TW;
@@ -2011,29 +2216,25 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     int *np = C::CLUSTER ? &g.cnt[0] : &S.misc[8];        // records in the list
     int *cc = C::CLUSTER ? &g.cnt[1] : &S.misc[12];       // next chunk of the sweep
     int *top = (int *)S.cbps;                             // per thread: the record that was its best in the last pass
-    const int n = *(volatile int *)np;
+    GEnt *ent = g.ent + (size_t)gs.half * g.cap;
+    double *bps = g.bps + (size_t)gs.half * g.cap;
+    uint8_t *qb = g.qb + (size_t)gs.half * g.cap;
+    int n = *(volatile int *)np;
     const uint32_t stamp = (uint32_t)(step % 4095 + 1) << 20;       // never 0 (= not stamped); the caller stops at 4094 passes
     Best best; best.fin = -1e300; best.key = 0xffffffffu; best.len = 0;
     int best_idx = -1;
     const int u1 = ui + ul - 1, v0 = uj - ul + 1;          // the arms of T: [ui, u1] and [v0, uj]
-    unsigned n_eval = 0, n_reset = 0, n_cut = 0;
+    unsigned n_eval = 0, n_reset = 0, n_cut = 0, n_swept = 0;
     GEnt buf[GL_BATCH];
-#ifdef SQRN_HOST_EMU
-    const int lane = 0;
-    constexpr int WL = 1;
-    int next_chunk = 0;
-    auto grab = [&]() { const int c0 = next_chunk; next_chunk += WL * GL_BATCH; return c0; };
-#else
-    const int lane = threadIdx.x & 31;
-    constexpr int WL = 32;
-    // warps take chunks of 32 * GL_BATCH consecutive records from a shared counter (cuts and evaluations are
-    // unevenly spread over the list; fixed strides would leave most warps waiting at the barriers)
+    const int lane = gl_lane();
+    constexpr int CH = GL_WL * GL_BATCH;                  // records per chunk
+    // warps take chunks of consecutive records from a shared counter (cuts and evaluations are unevenly spread
+    // over the list; fixed strides would leave most warps waiting at the barriers)
     auto grab = [&]() {
         int c0 = 0;
-        if (lane == 0) c0 = atomicAdd(cc, WL * GL_BATCH);
-        return __shfl_sync(0xffffffffu, c0, 0);
+        if (lane == 0) c0 = atomicAdd(cc, CH);
+        return gl_bcast0(c0);
     };
-#endif
     unsigned *fl_hi = (unsigned *)&S.misc[9];     // high word of the best score found so far (a lower bound of it)
     double floor = -1e300;
     auto refresh_floor = [&]() {
@@ -2047,195 +2248,321 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
             if (fin > floor) { floor = fin; if (fin > 0.0) atomicMax(fl_hi, (unsigned)__double2hiint(fin)); }
         }
     };
-    // Brings record c (loaded into e) up to date with T: cuts it, or puts its cached value back to FRESH when T
-    // may have changed it.  Returns the state it is in now (GK_DEAD records and cut ones report GS_BELOW: nothing
-    // more to do with them in this pass -- the pieces of a cut are FRESH records of their own).
-    auto revise = [&](int c, GEnt &e) -> uint32_t {
+    // Replaces record c = (s, a, len), some of whose cells died, by its surviving pieces (the first one stays in
+    // the slot, the others are appended).  Pieces are FRESH (or BELOW) and carry this pass's stamp.
+    auto cut = [&](int c, GEnt &e, int s, int a, int len) -> uint32_t {
+        const int t = s - a;
+        uint32_t live = 0u;
+        if (len <= 32) live = unpaired_bits32(S, a) & __brev(unpaired_bits32(S, t - 31)) & (0xffffffffu >> (32 - len));
+        auto dead = [&](int q) { return !(unpaired_at(S, a + q) && unpaired_at(S, t - q)); };
+        bool first = true;
+        int q = 0;
+        #pragma unroll 1
+        for (;;) {
+            int p0, pl;
+            if (len <= 32) {
+                if (!live) break;
+                p0 = __ffs(live) - 1;
+                const uint32_t inv = ~(live >> p0);
+                pl = inv ? __ffs(inv) - 1 : 32;
+                live = (p0 + pl >= 32) ? 0u : (live >> (p0 + pl)) << (p0 + pl);
+            } else {
+                #pragma unroll 1
+                while (q < len && dead(q)) q++;
+                if (q >= len) break;
+                p0 = q;
+                #pragma unroll 1
+                while (q < len && !dead(q)) q++;
+                pl = q - p0;
+            }
+            if ((double)pl < P.minlen) continue;
+            double pos;
+            const double sc = run_score_pos<C>(S, P, B, s, a + p0, pl, pos);
+            if (!(pos >= P.minbpscore)) continue;
+            const int slot = first ? c : atomicAdd(np, 1);
+            const uint32_t nm = (uint32_t)pl | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16) | stamp;
+            if (slot < g.cap) {
+                gl_store(&ent[slot], ((uint32_t)s << 16) | (uint32_t)(a + p0), nm, 0.0);
+                bps[slot] = sc;
+                qb[slot] = (uint8_t)gl_bin(P, gl_ub0(S, P, s, a + p0, pl, pos));
+            }
+            if (first) { e.key = ((uint32_t)s << 16) | (uint32_t)(a + p0); e.meta = nm; }
+            first = false;
+        }
+        n_cut++;
+        if (first) { ent[c].key = GK_DEAD; e.key = GK_DEAD; return GS_BELOW; }
+        return (e.meta >> 16) & GS_MASK;          // the piece that stayed in this slot
+    };
+    // Brings record c (loaded into e) up to date.  `stale` = false: it is up to date but for T -- it is cut if T
+    // meets it, and its cached value goes back to FRESH when T may have changed it.  `stale` = true: it has not
+    // been looked at for several passes -- it is cut by the unpaired mask and loses any cached value that depends
+    // on the structure.  Returns the state it is in now (GK_DEAD records report GS_BELOW: nothing more to do with
+    // them in this pass).
+    auto revise = [&](int c, GEnt &e, bool stale) -> uint32_t {
         if (e.key == GK_DEAD) return GS_BELOW;
         const uint32_t meta = e.meta;
         uint32_t st = (meta >> 16) & GS_MASK;
-        if (ul <= 0 || (meta & 0xfff00000u) == stamp) return st;          // no new stem, or already revised in this pass
+        if ((meta & 0xfff00000u) == stamp) return st;                     // already revised in this pass
         const int len = (int)(meta & 0xffffu), a = (int)(e.key & 0xffffu), s = (int)(e.key >> 16), t = s - a;
+        if (stale) {
+#ifdef SQRN_HOST_EMU
+            g_emu_gl_catchups++;
+#endif
+            bool hit;
+            if (len <= 32) {
+                const uint32_t full = 0xffffffffu >> (32 - len);
+                hit = (unpaired_bits32(S, a) & __brev(unpaired_bits32(S, t - 31)) & full) != full;
+            } else {
+                hit = false;
+                #pragma unroll 1
+                for (int q = 0; q < len && !hit; q++) hit = !(unpaired_at(S, a + q) && unpaired_at(S, t - q));
+            }
+            if (hit) return cut(c, e, s, a, len);
+            if (st == GS_EVAL || st == GS_PRUNED) { st = GS_FRESH; e.meta = (uint32_t)len | stamp; ent[c].meta = e.meta; n_reset++; }
+            return st;
+        }
+        if (ul <= 0) return st;
         // T can cut the run or change its cached score only if one of its arms meets [a - 5, t + 5]
         // (the run's rows and columns all lie in [a, t]); most records fail this test and are done
         if (!((u1 < a - 5 || ui > t + 5) && (uj < a - 5 || v0 > t + 5))) {
             const int A0 = ui - a, A1 = u1 - a, B0 = v0 - a, B1 = uj - a;
             const int C0 = t - u1, C1 = t - ui, D0 = t - uj, D1 = t - v0;
             const int topq = len - 1;
-            if ((A0 <= topq && A1 >= 0) || (B0 <= topq && B1 >= 0) || (C0 <= topq && C1 >= 0) || (D0 <= topq && D1 >= 0)) {
-                uint32_t live = len <= 32 ? (0xffffffffu >> (32 - len)) & ~(bits_between(A0, A1) | bits_between(B0, B1) |
-                                                                            bits_between(C0, C1) | bits_between(D0, D1)) : 0u;
-                auto dead = [&](int q) { return (q >= A0 && q <= A1) || (q >= B0 && q <= B1) || (q >= C0 && q <= C1) || (q >= D0 && q <= D1); };
-                bool first = true;
-                int q = 0;
-                #pragma unroll 1
-                for (;;) {
-                    int p0, pl;
-                    if (len <= 32) {
-                        if (!live) break;
-                        p0 = __ffs(live) - 1;
-                        const uint32_t inv = ~(live >> p0);
-                        pl = inv ? __ffs(inv) - 1 : 32;
-                        live = (p0 + pl >= 32) ? 0u : (live >> (p0 + pl)) << (p0 + pl);
-                    } else {
-                        #pragma unroll 1
-                        while (q < len && dead(q)) q++;
-                        if (q >= len) break;
-                        p0 = q;
-                        #pragma unroll 1
-                        while (q < len && !dead(q)) q++;
-                        pl = q - p0;
-                    }
-                    if ((double)pl < P.minlen) continue;
-                    double pos;
-                    const double sc = run_score_pos<C>(S, P, B, s, a + p0, pl, pos);
-                    if (!(pos >= P.minbpscore)) continue;
-                    const int slot = first ? c : atomicAdd(np, 1);
-                    const uint32_t nm = (uint32_t)pl | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16) | stamp;
-                    if (slot < g.cap) {
-                        gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)(a + p0), nm, 0.0);
-                        g.bps[slot] = sc;
-                    }
-                    if (first) { e.key = ((uint32_t)s << 16) | (uint32_t)(a + p0); e.meta = nm; }
-                    first = false;
-                }
-                n_cut++;
-                if (first) { g.ent[c].key = GK_DEAD; e.key = GK_DEAD; return GS_BELOW; }
-                return (e.meta >> 16) & GS_MASK;          // the piece that stayed in this slot
-            }
+            if ((A0 <= topq && A1 >= 0) || (B0 <= topq && B1 >= 0) || (C0 <= topq && C1 >= 0) || (D0 <= topq && D1 >= 0))
+                return cut(c, e, s, a, len);
             if (st == GS_EVAL || st == GS_PRUNED) {
                 // T meets the window the cached value was computed from: stale unless T is shielded
                 const int ss = a + len - 1, se = t - len + 1;
                 const bool shielded = ei >= 0 && ss < ei && ej < se;
-                if (!shielded) { st = GS_FRESH; e.meta = (uint32_t)len | stamp; g.ent[c].meta = e.meta; n_reset++; return st; }
+                if (!shielded) { st = GS_FRESH; e.meta = (uint32_t)len | stamp; ent[c].meta = e.meta; n_reset++; return st; }
             }
         }
         // a level change only matters to scores that counted the wing of a selected stem
-        if (relevel && st == GS_EVAL && (meta >> 16 & GS_LEVELS)) { st = GS_FRESH; e.meta = (uint32_t)len | stamp; g.ent[c].meta = e.meta; n_reset++; }
+        if (relevel && st == GS_EVAL && (meta >> 16 & GS_LEVELS)) { st = GS_FRESH; e.meta = (uint32_t)len | stamp; ent[c].meta = e.meta; n_reset++; }
         return st;
     };
     auto evaluate = [&](int c) {
-        const GEnt e = gl_load(&g.ent[c]);
+        const GEnt e = gl_load(&ent[c]);
         const int len = (int)(e.meta & 0xffffu);
-        const double bps = g.bps[c];
+        const double sc = bps[c];
         int order = 0;
-        const double fin = score_candidate<C>(S, P, (int)(e.key >> 16), (int)(e.key & 0xffffu), len, bps, &order);
-        gl_store(&g.ent[c], e.key, (uint32_t)len | ((GS_EVAL | (order ? GS_LEVELS : 0u)) << 16) | stamp, fin);
+        const double fin = score_candidate<C>(S, P, (int)(e.key >> 16), (int)(e.key & 0xffffu), len, sc, &order);
+        gl_store(&ent[c], e.key, (uint32_t)len | ((GS_EVAL | (order ? GS_LEVELS : 0u)) << 16) | stamp, fin);
         n_eval++;
 #ifdef SQRN_EMU_DEBUG
-        printf("  eval nst=%d (%d,%d,%d) bps=%g fin=%.17g\n", S.nst, (int)(e.key & 0xffff), (int)(e.key >> 16) - (int)(e.key & 0xffff), len, bps, fin);
+        printf("  eval nst=%d (%d,%d,%d) bps=%g fin=%.17g\n", S.nst, (int)(e.key & 0xffff), (int)(e.key >> 16) - (int)(e.key & 0xffff), len, sc, fin);
 #endif
         offer(fin, e.key, len, c);
     };
     // true: record c (already revised) has to be evaluated: its bounds reach the floor
     auto screen = [&](int c) -> bool {
-        const GEnt e = gl_load(&g.ent[c]);
+        const GEnt e = gl_load(&ent[c]);
         if (e.key == GK_DEAD) return false;
         const uint32_t st = (e.meta >> 16) & GS_MASK;
         if (st == GS_EVAL || st == GS_BELOW) return false;
         if ((st == GS_PRUNED || st == GS_PRUNED1) && e.v < floor) return false;
         const int len = (int)(e.meta & 0xffffu);
-        const double bps = g.bps[c];
-        double ub = score_bound(P, bps);
-        if (ub < floor || ub < P.minfinscore) { if (st != GS_PRUNED1) gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED1 << 16) | stamp, ub); return false; }
-        ub = tight_bound(S, P, e.key, len, bps);
-        if (ub < floor || ub < P.minfinscore) { gl_store(&g.ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16) | stamp, ub); return false; }
+        const double sc = bps[c];
+        double ub = score_bound(P, sc);
+        if (ub < floor || ub < P.minfinscore) { if (st != GS_PRUNED1) gl_store(&ent[c], e.key, (uint32_t)len | (GS_PRUNED1 << 16) | stamp, ub); return false; }
+        ub = tight_bound(S, P, e.key, len, sc);
+        if (ub < floor || ub < P.minfinscore) { gl_store(&ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16) | stamp, ub); return false; }
         return true;
     };
     auto wants_look = [&](uint32_t st, const GEnt &e) {
         return st == GS_FRESH || ((st == GS_PRUNED || st == GS_PRUNED1) && !(e.v < floor));
     };
-
-    // ---- prologue: the floor from the records that were the threads' bests in the last pass
-    if (r == 0) *fl_hi = 0u;
-    if (gl_leader<C>(S)) *cc = 0;
-    gl_sync<C>();
-    const long long t_a = g.stat ? gl_clock() : 0;
-    if (n >= 8 * T || C::CLUSTER) {                // (short lists: a sweep is a few records per thread, a floor buys nothing)
-        const int c = top[r];
-        if (c >= 0 && c < n) {
-            GEnt e = gl_load(&g.ent[c]);
-            if (revise(c, e) == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
-        }
-        Best f = team_argmax<C>(S, best);
-        if (C::CLUSTER) f = cluster_best<C>(S, f, xc++);
-        if (f.fin > floor) floor = f.fin;          // every thread starts from the team-wide (cluster-wide) floor
-    }
-    // ---- the sweep
-#ifdef SQRN_HOST_EMU
-    auto look = [&](int c) { refresh_floor(); if (screen(c)) evaluate(c); };
-    #pragma unroll 1
-    for (int c = 0; c < n; c++) {
-        GEnt e = gl_load(&g.ent[c]);
-        const uint32_t st = revise(c, e);
-        if (st == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
-        else if (wants_look(st, e)) look(c);
-    }
-    const int n2 = *(volatile int *)np;
-    if (n2 > g.cap) { ok = false; return best; }
-    #pragma unroll 1
-    for (int c = n; c < n2; c++) look(c);           // the pieces appended by this pass
-    const long long t_b = t_a;
-#else
-    const int wid = threadIdx.x >> 5;
-    int *wa = (int *)S.ckey + 128 * wid, *wb = wa + 64;      // Layout::Ccap = 128 per warp
+    // per-warp lists: `wa` records to screen, `wb` records to evaluate (Layout::Ccap >= 4 GL_WL per warp)
+    int *wa = (int *)S.ckey + 4 * GL_WL * gl_wid(), *wb = wa + 2 * GL_WL;
     int na = 0, nb = 0;
     auto push = [&](int *list, int &cnt, bool p, int c) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, p);
+        const uint32_t bal = gl_ballot(p);
         if (p) list[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
         cnt += __popc(bal);
-        __syncwarp();
+        gl_wsync();
     };
     auto drain = [&](bool all) {
         #pragma unroll 1
-        while (na >= 32 || (all && na > 0)) {
-            const int take = na >= 32 ? 32 : na;
+        while (na >= GL_WL || (all && na > 0)) {
+            const int take = na >= GL_WL ? GL_WL : na;
             na -= take;
             refresh_floor();
             const int c = lane < take ? wa[na + lane] : 0;
             const bool need = lane < take && screen(c);
-            __syncwarp();
+            gl_wsync();
             push(wb, nb, need, c);
-            if (nb >= 32) { nb -= 32; evaluate(wb[nb + lane]); __syncwarp(); }
+            if (nb >= GL_WL) { nb -= GL_WL; evaluate(wb[nb + lane]); gl_wsync(); }
         }
-        if (all && nb > 0) { if (lane < nb) evaluate(wb[lane]); nb = 0; __syncwarp(); }
+        if (all && nb > 0) { if (lane < nb) evaluate(wb[lane]); nb = 0; gl_wsync(); }
     };
-    #pragma unroll 1
-    for (int c0 = grab(); c0 < n; c0 = grab()) {
-        #pragma unroll
-        for (int u = 0; u < GL_BATCH; u++) {
-            const int c = c0 + u * 32 + lane;
-            if (c < n) buf[u] = gl_load(&g.ent[c]); else buf[u].key = GK_DEAD;
-        }
-        refresh_floor();
+    const long long t_a = g.stat ? gl_clock() : 0;
+
+    // ---- rebuild: everything up to date, dead records dropped, survivors re-binned into the other half
+    const int period = g.rebuild > 0 ? g.rebuild : GL_REBUILD;
+    if (ul > 0 && gs.since >= period) {
+#ifdef SQRN_HOST_EMU
+        g_emu_gl_rebuilds++;
+#endif
+        GEnt *ent2 = g.ent + (size_t)(gs.half ^ 1) * g.cap;
+        double *bps2 = g.bps + (size_t)(gs.half ^ 1) * g.cap;
+        uint8_t *qb2 = g.qb + (size_t)(gs.half ^ 1) * g.cap;
         #pragma unroll 1
-        for (int u = 0; u < GL_BATCH; u++) {
-            const int c = c0 + u * 32 + lane;
-            GEnt e = buf[u];
-            const uint32_t st = revise(c, e);
-            if (st == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
-            push(wa, na, wants_look(st, e), c);
-            if (na >= 32) drain(false);
+        for (int q = r; q < GL_NBIN; q += T) S.ghist[q] = 0;
+        Team<TW>::sync();
+        // chunks are dealt statically (a cluster's CTAs scatter what they counted)
+        const int nw = TW > 0 ? TW : 1;
+        const int gw = C::CLUSTER ? S.doffset * nw + gl_wid() : gl_wid(), gnw = C::CLUSTER ? S.dstride * nw : nw;
+        #pragma unroll 1
+        for (int c0 = gw * CH; c0 < n; c0 += gnw * CH) {
+            #pragma unroll
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int c = c0 + u * GL_WL + lane;
+                if (c < n) buf[u] = gl_load(&ent[c]); else buf[u].key = GK_DEAD;
+            }
+            #pragma unroll 1
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int c = c0 + u * GL_WL + lane;
+                GEnt e = buf[u];
+                revise(c, e, c >= gs.n_inc && c < gs.n_sorted);
+                if (e.key != GK_DEAD) atomicAdd(&S.ghist[qb[c]], 1);
+            }
         }
+        gl_sync<C>();
+        const int n2 = *(volatile int *)np;
+        if (n2 > g.cap) { ok = false; return best; }
+        #pragma unroll 1
+        for (int c0 = n + gw * GL_WL; c0 < n2; c0 += gnw * GL_WL) {          // the pieces these cuts appended
+            const int c = c0 + lane;
+            if (c < n2) atomicAdd(&S.ghist[qb[c]], 1);
+        }
+        const int nn = gl_make_bins<C>(S, g);
+        #pragma unroll 1
+        for (int c0 = gw * CH; c0 < n; c0 += gnw * CH) {
+            #pragma unroll
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int c = c0 + u * GL_WL + lane;
+                if (c < n) buf[u] = gl_load(&ent[c]); else buf[u].key = GK_DEAD;
+            }
+            #pragma unroll 1
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int c = c0 + u * GL_WL + lane;
+                if (buf[u].key == GK_DEAD) continue;
+                const int q = qb[c];
+                const int slot = atomicAdd(&S.gcur[q], 1);
+                gl_store(&ent2[slot], buf[u].key, buf[u].meta, buf[u].v);
+                bps2[slot] = bps[c]; qb2[slot] = (uint8_t)q;
+            }
+        }
+        #pragma unroll 1
+        for (int c0 = n + gw * GL_WL; c0 < n2; c0 += gnw * GL_WL) {
+            const int c = c0 + lane;
+            if (c < n2) {
+                const GEnt e = gl_load(&ent[c]);
+                const int q = qb[c];
+                const int slot = atomicAdd(&S.gcur[q], 1);
+                gl_store(&ent2[slot], e.key, e.meta, e.v);
+                bps2[slot] = bps[c]; qb2[slot] = (uint8_t)q;
+            }
+        }
+        top[r] = -1;
+        gl_sync<C>();
+        if (gl_leader<C>(S)) *np = nn;
+        gs.half ^= 1; gs.n_sorted = nn; gs.n_inc = nn; gs.since = 0;
+        ent = ent2; bps = bps2; qb = qb2;
+        n = nn;
+        ul = 0;                                    // every record has seen T
+        if (g.stat && gl_leader<C>(S)) atomicAdd(&g.stat[12], 1ull);
     }
-    drain(true);
+    gs.since++;
+
+    // ---- prologue: the floor from the records that were the threads' bests in the last pass
+    if (r == 0) *fl_hi = 0u;
+    gl_sync<C>();
+    Best fb; fb.fin = -1e300; fb.key = 0xffffffffu; fb.len = 0;
+    if (n >= 8 * T || C::CLUSTER) {                // (short lists: a sweep is a few records per thread, a floor buys nothing)
+        const int c = top[r];
+        if (c >= 0 && c < n) {
+            GEnt e = gl_load(&ent[c]);
+            if (revise(c, e, false) == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
+        }
+        fb = team_argmax<C>(S, best);
+        if (C::CLUSTER) fb = cluster_best<C>(S, fb, xc++);
+        if (fb.fin > floor) floor = fb.fin;        // every thread starts from the team-wide (cluster-wide) floor
+    }
+    // ---- rounds over the prefix of the binned list that the floor reaches (+ the tail, in the first one)
+    const int ns = gs.n_sorted, ntail = n - ns;
+    int done = 0;
+    bool first_round = true;
+    #pragma unroll 1
+    for (;;) {
+        // as far as the floor known so far asks for, but no further than four times what has been swept (a weak
+        // early floor must not drag the whole list in: the next round will know better); whole bins
+        int target = fb.fin > -1e300 ? S.gbend[gl_bin(P, fb.fin)] : ns;
+        {
+            const int want = done > 0 ? 4 * done : 16 * T;
+            if (target > want) {
+                int q = 0, qh = GL_NBIN - 1;               // the highest bin q with gbend[q] >= want (gbend falls with q)
+                #pragma unroll 1
+                while (q < qh) { const int mid = (q + qh + 1) >> 1; if (S.gbend[mid] >= want) q = mid; else qh = mid - 1; }
+                if (S.gbend[q] < target) target = S.gbend[q];
+            }
+        }
+        if (target > ns) target = ns;
+        if (target <= done && !first_round) break;
+        if (target < done) target = done;
+        // virtual index space of the round: [done, target) of the bins, then (first round) the tail [ns, n)
+        const int span = target - done, vtot = span + (first_round ? ntail : 0);
+        if (gl_leader<C>(S)) *cc = 0;
+        gl_sync<C>();
+        #pragma unroll 1
+        for (int v0_ = grab(); v0_ < vtot; v0_ = grab()) {
+            #pragma unroll
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int v = v0_ + u * GL_WL + lane;
+                const int c = v < span ? done + v : ns + (v - span);
+                if (v < vtot) buf[u] = gl_load(&ent[c]); else buf[u].key = GK_DEAD;
+            }
+            refresh_floor();
+            #pragma unroll 1
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int v = v0_ + u * GL_WL + lane;
+                const int c = v < span ? done + v : ns + (v - span);
+                GEnt e = buf[u];
+                const uint32_t st = revise(c, e, v < span && c >= gs.n_inc);
+                if (st == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
+                push(wa, na, wants_look(st, e), c);
+                if (na >= GL_WL) drain(false);
+            }
+            n_swept += GL_BATCH;
+        }
+        drain(true);
+        done = target; first_round = false;
+        fb = team_argmax<C>(S, best);
+        if (C::CLUSTER) fb = cluster_best<C>(S, fb, xc++);
+        if (fb.fin > floor) floor = fb.fin;
+        if (done >= ns) break;
+    }
+    // what is up to date with every selected stem now: the records this pass revised; the others still are
+    // if this pass had no new stem to show them
+    gs.n_inc = ul > 0 ? done : (done > gs.n_inc ? done : gs.n_inc);
     // ---- epilogue: the pieces this pass appended
     if (gl_leader<C>(S)) *cc = n;
     gl_sync<C>();
     const long long t_b = g.stat ? gl_clock() : 0;
     const int n2 = *(volatile int *)np;
     if (n2 > g.cap) { ok = false; return best; }
-    #pragma unroll 1
-    for (int c0 = grab(); c0 < n2; c0 = grab()) {
+    if (n2 > n) {
         #pragma unroll 1
-        for (int u = 0; u < GL_BATCH; u++) {
-            const int c = c0 + u * 32 + lane;
-            push(wa, na, c < n2, c);
-            if (na >= 32) drain(false);
+        for (int c0 = grab(); c0 < n2; c0 = grab()) {
+            #pragma unroll 1
+            for (int u = 0; u < GL_BATCH; u++) {
+                const int c = c0 + u * GL_WL + lane;
+                push(wa, na, c < n2, c);
+                if (na >= GL_WL) drain(false);
+            }
         }
+        drain(true);
     }
-    drain(true);
-#endif
     top[r] = best_idx;
     if (g.stat) {
         Team<TW>::sync();
@@ -2243,11 +2570,15 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         if (n_eval) atomicAdd(&g.stat[1], (unsigned long long)n_eval);
         if (n_reset) atomicAdd(&g.stat[2], (unsigned long long)n_reset);
         if (n_cut) atomicAdd(&g.stat[5], (unsigned long long)n_cut);
-        if (gl_leader<C>(S)) { atomicAdd(&g.stat[0], (unsigned long long)n); atomicAdd(&g.stat[3], 1ull); if (relevel) atomicAdd(&g.stat[4], 1ull); }
+        if (n_swept && lane == 0) atomicAdd(&g.stat[0], (unsigned long long)n_swept * GL_WL);
+        if (gl_leader<C>(S)) { atomicAdd(&g.stat[3], 1ull); if (relevel) atomicAdd(&g.stat[4], 1ull); }
     }
-    best = team_argmax<C>(S, best);
-    if (C::CLUSTER) best = cluster_best<C>(S, best, xc++);
-    return best;
+    if (n2 > n) {
+        best = team_argmax<C>(S, best);
+        if (C::CLUSTER) best = cluster_best<C>(S, best, xc++);
+        return best;
+    }
+    return fb;
 }
 
 // two stems are "in conflict" when they share a paired position (seq.py:783-786)
@@ -2515,15 +2846,16 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
     const int mode = C::MODE >= 0 ? C::MODE : Wk.mode;
     S.region_mode = Wk.region_mode;
     GList g{};
+    GState gs{};
     if (C::GLIST) {
 #ifdef SQRN_HOST_EMU
         const long long slot = 0;
 #else
         const long long slot = C::CLUSTER ? blockIdx.x / (unsigned)S.dstride : blockIdx.x;      // one list per cluster
 #endif
-        g.ent = (GEnt *)Wk.g_ent + slot * Wk.g_cap; g.bps = Wk.g_bps + slot * Wk.g_cap;
-        g.cap = (int)Wk.g_cap; g.stat = Wk.g_stat;
-        g.cnt = Wk.g_cnt ? Wk.g_cnt + 4 * slot : nullptr;
+        g.ent = (GEnt *)Wk.g_ent + 2 * slot * Wk.g_cap; g.bps = Wk.g_bps + 2 * slot * Wk.g_cap; g.qb = Wk.g_qb + 2 * slot * Wk.g_cap;
+        g.cap = (int)Wk.g_cap; g.stat = Wk.g_stat; g.rebuild = Wk.g_rebuild;
+        g.cnt = Wk.g_cnt ? Wk.g_cnt + GL_CNT_INTS * slot : nullptr;
     }
     if (C::PERSIST) {
         // hopeless for the list (too long for this parameter set): straight to the rescanning kernel
@@ -2551,7 +2883,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         if (C::PERSIST && mode == MODE_TAIL && (double)S.nst != P.maxstemnum)
         {
             const long long t0 = (C::GLIST && g.stat) ? gl_clock() : 0;
-            ok = C::GLIST ? gl_build<C>(S, P, B, g) : persist_build<C>(S, P, B, L);
+            ok = C::GLIST ? gl_build<C>(S, P, B, g, gs) : persist_build<C>(S, P, B, L);
             if (C::GLIST && g.stat && r == 0) atomicAdd(&g.stat[9], (unsigned long long)(gl_clock() - t0));
         }
         bool lev_ok = false;                        // stlev[] matches the current stem set
@@ -2587,7 +2919,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
                 for (int t = r; t < S.nst; t += T) S.stlev2[t] = S.stlev[t];
                 Team<TW>::sync();
                 if (calls >= 4094) { ok = false; break; }        // the pass stamp of the records has 12 bits: let the rescanning kernel do it
-                b = gl_step<C>(S, P, B, g, ui, uj, ul, ei, ej, relevel, ok, xc, (int)calls);
+                b = gl_step<C>(S, P, B, g, gs, ui, uj, ul, ei, ej, relevel, ok, xc, (int)calls);
                 if (!ok) break;
             } else if (C::PERSIST) {
                 b = persist_step<C>(S, P, B, L, ui, uj, ul, ok);

@@ -36,6 +36,9 @@ def lib():
             [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         _lib.emu_pyround3.restype = C.c_double
         _lib.emu_persist_steps.restype = C.c_long
+        _lib.emu_gl_rebuilds.restype = C.c_long
+        _lib.emu_gl_catchups.restype = C.c_long
+        _lib.emu_gl_set_rebuild.argtypes = [C.c_int]
         _lib.emu_pyround3.argtypes = [C.c_double]
     return _lib
 

@@ -47,10 +47,11 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     W.out_stemfin = out_stemfin; W.out_raw = out_raw; W.out_flags = out_flags; W.dbn_off = dbn_off;
     W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls; W.region_mode = region_mode;
     Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, (flavour == 3 || flavour == 4) ? pcap : (flavour == 5 ? -1 : 0));
-    std::vector<GEnt> ge; std::vector<double> gb;
-    if (flavour == 5) {            // global persistent list with cached scores (what CTA teams run), capacity pcap
-        ge.resize((size_t)pcap + 1); gb.resize((size_t)pcap + 1);
-        W.g_ent = ge.data(); W.g_bps = gb.data(); W.g_cap = pcap;
+    std::vector<GEnt> ge; std::vector<double> gb; std::vector<uint8_t> gq;
+    if (flavour == 5) {            // global persistent list with cached scores (what CTA teams run), capacity pcap (two halves)
+        ge.resize(2 * (size_t)pcap + 2); gb.resize(2 * (size_t)pcap + 2); gq.resize(2 * (size_t)pcap + 2);
+        W.g_ent = ge.data(); W.g_bps = gb.data(); W.g_qb = gq.data(); W.g_cap = pcap;
+        W.g_rebuild = sqrn::g_emu_gl_rebuild_every;
     }
     unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
     // PERSIST flavours park the items whose run list overflowed; they are redone by the rescanning flavour
@@ -80,5 +81,8 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
 }
 
 extern "C" long emu_persist_steps(void) { return sqrn::g_emu_persist_steps; }
+extern "C" long emu_gl_rebuilds(void) { return sqrn::g_emu_gl_rebuilds; }
+extern "C" long emu_gl_catchups(void) { return sqrn::g_emu_gl_catchups; }
+extern "C" void emu_gl_set_rebuild(int every) { sqrn::g_emu_gl_rebuild_every = every; }
 
 extern "C" double emu_pyround3(double x) { return pyround3(x); }

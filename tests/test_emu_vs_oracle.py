@@ -184,12 +184,24 @@ def test_step_on_random_pseudoknotted_structures(region):
             assert got == chosen, (seq, stems)
 
 
-def test_glist_cached_scores_under_pseudoknots():
+@pytest.fixture
+def rebuild_period(request):
+    """rebuild period of the binned global list (passes); restored to the default afterwards"""
+    emu.lib().emu_gl_set_rebuild(request.param)
+    yield request.param
+    emu.lib().emu_gl_set_rebuild(0)
+
+
+@pytest.mark.parametrize("rebuild_period", [0, 1, 3, 7], indirect=True, ids=["default", "every-pass", "every-3", "every-7"])
+def test_glist_cached_scores_under_pseudoknots(rebuild_period):
     """The global persistent list (CTA teams) keeps the adjusted score of a candidate between greedy steps
     unless the new stem meets the window ScoreStems read, or an older stem changed its pseudoknot level.
     Parameter sets that accept many pseudoknots (up to ~10 levels) against the rescanning flavour and,
-    for a sample, the oracle."""
+    for a sample, the oracle.  The list is binned by a static bound: records behind the prefix a pass looks at
+    are caught up from the unpaired mask when they enter it, and every `rebuild_period` passes the list is
+    compacted and re-binned -- both paths must have run."""
     pk = dict(T.ALI); pk["orderpenalty"] = 0.1; pk["minfinscorefactor"] = 0.8
+    before = emu.lib().emu_gl_rebuilds(), emu.lib().emu_gl_catchups()
     for ps in (T.ALI, T.DEFG2, T.G1000, pk):
         seqs = T.rand_seqs(101, 40, 150, 450) + T.rand_seqs(102, 10, 300, 500, "GC") + T.rand_seqs(103, 10, 200, 400, "GGCCAU")
         a = emu.run(ps, seqs, ccap=256, flavour=5, pcap=1 << 20)
@@ -203,9 +215,11 @@ def test_glist_cached_scores_under_pseudoknots():
             _, structs, _ = O.predict_short(seqs[k], [0.5] * len(seqs[k]), "." * len(seqs[k]), [ps], poollim=1)
             sa = [tuple(int(x) for x in a["stems"][a["off"][k] + q]) for q in range(a["n"][k])]
             assert sa == structs[0][4]
+    assert emu.lib().emu_gl_rebuilds() > before[0]
+    assert emu.lib().emu_gl_catchups() > before[1] or rebuild_period == 1      # (rebuilt every pass, nothing is ever behind)
 
 
-@pytest.mark.parametrize("flavour", [5, 2], ids=["global-list", "rescan"])
+@pytest.mark.parametrize("flavour", [5, 2, 55], ids=["global-list", "rescan", "global-list-rebuild-every-5"])
 def test_device_code_on_rrna_scale_reference_cases(flavour):
     """the device functions (host emulation) on the reference's OWN results for plain sequences of 2050 .. 2500 nt
     (tests/golden/seq_api_xlong.json): the global candidate list with cached scores, and the rescanning pass"""
@@ -213,11 +227,17 @@ def test_device_code_on_rrna_scale_reference_cases(flavour):
     pkg = os.path.dirname(os.path.abspath(CLI.__file__))
     with open(os.path.join(G, "seq_api_xlong.json")) as f:
         cases = json.load(f)
+    if flavour == 55:
+        emu.lib().emu_gl_set_rebuild(5)
+        flavour = 5
     for c in cases:
         if flavour == 2 and c["conf"] != "fastest":
             continue                                  # minlen 2 at 2050 nt: minutes in the single-thread rescanning build
         ps = [p for p in CLI.ParseConfig(os.path.join(pkg, c["conf"] + ".conf"))[1] if p["algorithms"] == {"G"} and not p["bpp"]][0]
-        r = emu.run(ps, [c["seq"]], ccap=4096, flavour=flavour, pcap=1 << 21)
+        try:
+            r = emu.run(ps, [c["seq"]], ccap=4096, flavour=flavour, pcap=1 << 21)
+        finally:
+            emu.lib().emu_gl_set_rebuild(0) if c is cases[-1] else None
         dbn, sc, _psl = c["structs"][0]
         assert bytes(r["dbn_ascii"][:len(c["seq"])]).decode() == dbn == c["cons"]
         got = tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][0])
