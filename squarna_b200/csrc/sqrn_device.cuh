@@ -1928,7 +1928,7 @@ constexpr uint32_t GK_DEAD = 0xffffffffu;
 constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u, GS_PRUNED1 = 4u;
 constexpr uint32_t GS_MASK = 7u, GS_LEVELS = 8u;      // GS_LEVELS (with EVAL): the score involves pseudoknot levels
 constexpr int GL_NBIN = 256;
-constexpr int GL_REBUILD = 16;    // default rebuild period (DevWork::g_rebuild overrides)
+constexpr int GL_REBUILD = 32;    // default rebuild period (DevWork::g_rebuild overrides)
 
 // one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16 | stamp << 20, v = the cached score / bound
 struct alignas(16) GEnt { uint32_t key, meta; double v; };
@@ -2499,7 +2499,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         // early floor must not drag the whole list in: the next round will know better); whole bins
         int target = fb.fin > -1e300 ? S.gbend[gl_bin(P, fb.fin)] : ns;
         {
-            const int want = done > 0 ? 4 * done : 16 * T;
+            const int want = done > 0 ? 4 * done : (gs.n_inc > 16 * T && gs.n_inc < ns ? gs.n_inc : 16 * T);     // (first round: what the last pass needed)
             if (target > want) {
                 int q = 0, qh = GL_NBIN - 1;               // the highest bin q with gbend[q] >= want (gbend falls with q)
                 #pragma unroll 1
