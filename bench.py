@@ -345,6 +345,16 @@ def bench_fast(args, rank, world, local):
     h_dbn = torch.empty(total, dtype=torch.uint8).pin_memory()
     h_sc = torch.empty(n * 3, dtype=torch.float64).pin_memory()
     h_ns = torch.empty(n, dtype=torch.int32).pin_memory()
+    # the packed boundary format of the same batch (include/sqrn.h): 2-bit base codes + uint32 offsets in,
+    # 4-bit bracket codes + scores in thousandths + uint16 stem counts + flags out
+    pk_np, n_other = _lib.pack_symbols(sym)
+    assert n_other == 0
+    p_sym = torch.from_numpy(pk_np).pin_memory()
+    p_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).pin_memory()      # (uint32 values)
+    p_nib = torch.empty(total // 2 + n + 1, dtype=torch.uint8).pin_memory()
+    p_milli = torch.empty(2 * n, dtype=torch.int32).pin_memory()
+    p_ns = torch.empty(n, dtype=torch.int16).pin_memory()                              # (uint16 values)
+    p_fl = torch.empty(n, dtype=torch.uint8).pin_memory()
     with torch.cuda.stream(stream):
         d_sym = h_sym.cuda(non_blocking=True)
         d_off = h_off.cuda(non_blocking=True)
@@ -360,6 +370,11 @@ def bench_fast(args, rank, world, local):
     def step_host():
         rc = ctx.L.sqrn_fast_predict_host(ctx.h, ps, n, h_off.data_ptr(), h_sym.data_ptr(), h_dbn.data_ptr(),
                                           h_sc.data_ptr(), h_ns.data_ptr())
+        ctx._check(rc)
+
+    def step_packed():
+        rc = ctx.L.sqrn_fast_predict_packed_host(ctx.h, ps, n, p_off.data_ptr(), p_sym.data_ptr(), p_nib.data_ptr(),
+                                                 p_milli.data_ptr(), p_ns.data_ptr(), p_fl.data_ptr())
         ctx._check(rc)
 
     def barrier():
@@ -396,7 +411,10 @@ def bench_fast(args, rank, world, local):
     kern_ms = dev_ms / args.steps
     for _ in range(2 if cfg == 2 else 1):
         step_host()
-    _, e2e_wall_ms = timed(step_host, args.steps)
+    _, bytes_wall_ms = timed(step_host, args.steps)
+    for _ in range(2 if cfg == 2 else 1):
+        step_packed()
+    _, e2e_wall_ms = timed(step_packed, args.steps)
     e2e_stats = ctx.stats()
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -408,6 +426,13 @@ def bench_fast(args, rank, world, local):
     near = np.round(dsc, 3)
     for k in np.flatnonzero(near != hsc).tolist():                       # rounding ties: Python's round() decides
         assert round(float(dsc[k]), 3) == float(hsc[k]), "device and host legs disagree (scores)"
+
+    # ... and the packed leg the same again: 4-bit codes -> ASCII, thousandths -> the rounded doubles
+    assert not (p_fl.numpy() & 2).any(), "a structure has more than 7 pseudoknot levels (packed format)"
+    assert np.array_equal(_lib.unpack_dbn(p_off.numpy().view(np.uint32), p_nib.numpy()), h_dbn.numpy()[:total]), "packed and byte legs disagree"
+    pm = p_milli.numpy().reshape(-1, 2)
+    assert np.array_equal(pm[:, 0] / 1000.0, hsc.reshape(-1, 3)[:, 0]) and np.array_equal(pm[:, 1] / 1000.0, hsc.reshape(-1, 3)[:, 1])
+    assert np.array_equal(p_ns.numpy().view(np.uint16).astype(np.int32), h_ns.numpy())
 
     # strong scaling: finished results gathered on rank 0 in input order (host-side, after the timed region)
     gathered = None
@@ -448,13 +473,15 @@ def bench_fast(args, rank, world, local):
             cpu = cpu_baseline_config2(sym, off, lens, threads)
         else:
             cpu = cpu_baseline_config5(threads, psd, dev_stats, n)
-        h2d = int(sym.nbytes + off.nbytes)
-        d2h = int(total + n * 3 * 8 + n * 4 + n)
+        h2d_bytes = int(sym.nbytes + off.nbytes)
+        d2h_bytes = int(total + n * 3 * 8 + n * 4 + n)
+        h2d = int((total + 3) // 4 + (n + 1) * 4)
+        d2h = int(total // 2 + n + n * 2 * 4 + n * 2 + n)
         line = {"metric": METRIC[cfg], "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "nt2_per_s": nt2,
                 "config": {"workload": workload, "seqs_per_gpu_per_step": n, "total_nt_per_gpu": total,
-                           "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no flush" % ((h2d + d2h) / 1e6)
+                           "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no flush" % ((h2d_bytes + d2h_bytes) / 1e6)
                            if cfg == 2 else "every step streams the sequences' candidate lists (GBs) through L2; no flush",
                            "sharding": ("one global batch dealt by length^3, imbalance %.4f, results gathered on rank 0: %s"
                                         % (imbalance, gathered)) if strong else "independent sequences per rank, no collective",
@@ -462,7 +489,14 @@ def bench_fast(args, rank, world, local):
                 "e2e": {"value": e2e, "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_wall_ms / args.steps,
                         "kernel_ms_in_step": e2e_stats["kernel_ms"], "launches_per_step": e2e_stats["launches"],
-                        "pipeline": "chunked: H2D, kernel and D2H of neighbouring chunks overlap on 4 streams"},
+                        "pipeline": "chunked: H2D, kernel and D2H of neighbouring chunks overlap on 4 streams",
+                        "call": "sqrn_fast_predict_packed_host: pinned host buffers in the packed boundary format (2-bit base codes + "
+                                "uint32 offsets in; 4-bit bracket codes + int32 thousandths + uint16 stem counts + flags out)",
+                        "byte_format": {"value": n_global / (bytes_wall_ms / args.steps / 1e3), "unit": "seq/s",
+                                        "ms_per_step": bytes_wall_ms / args.steps, "h2d_bytes_per_step": h2d_bytes,
+                                        "d2h_bytes_per_step": d2h_bytes,
+                                        "call": "sqrn_fast_predict_host: ASCII symbols + int64 offsets in, ASCII dot-bracket + "
+                                                "3 float64 scores + int32 stem counts out"}},
                 "gpu_launches": args.steps * (2 if cfg == 2 else max(int(dev_stats["launches"]), 1) * 2),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

@@ -43,7 +43,7 @@ extern "C" {
 #define SQRN_API
 #endif
 
-#define SQRN_ABI_VERSION 2
+#define SQRN_ABI_VERSION 3
 
 #define SQRN_OK             0
 #define SQRN_E_BADARG      -1
@@ -190,6 +190,28 @@ SQRN_API int  sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps,
                               int64_t n_seqs, int64_t total_len, int32_t max_len,
                               const int64_t *d_offsets, const uint8_t *d_symbols,
                               uint8_t *d_dbn_ascii, double *d_scores, int32_t *d_n_stems);
+
+/* The same lane over the PACKED boundary format (2-bit base codes in, 4-bit bracket codes out): 0.11 GB instead of
+ * 0.30 GB over PCIe per million 130-nt sequences.  Plain A/C/G/U(T) sequences only (sqrn_pack_symbols reports anything
+ * else; such batches use the byte lane).
+ *   offsets  [n_seqs+1] uint32, in bases (the batch holds < 2^32 bases);
+ *   packed   base k of the batch = bits 2 (k & 3) .. of byte k >> 2; A C G U = 0 1 2 3;
+ *   dbn_nib  [total/2 + n_seqs + 1] bytes: sequence b starts at byte (offsets[b] >> 1) + b, two positions per byte
+ *            (low nibble first): 0 '.', L = opening, 8 | L = closing bracket of level L (1..7);
+ *   score_milli [2 n_seqs]: round(total, 3) and round(structscore, 3) (ScoreStruct, SQRNdbnseq.py:899) in thousandths;
+ *            the reactscore of a plain sequence is 0.5;
+ *   n_stems  [n_seqs] uint16 or NULL;  flags [n_seqs] or NULL: bit 0 = structscore is the int 0, bit 1 = MORE THAN 7
+ *            pseudoknot levels -- that sequence's dbn_nib is not valid, redo it through the byte lane.
+ * sqrn_pack_symbols / sqrn_unpack_dbn are the host-side converters (threaded); *n_other = symbols outside ACGUT.     */
+SQRN_API int  sqrn_fast_predict_packed_host(sqrn_ctx *ctx, const sqrn_paramset *ps,
+                            int64_t n_seqs, const uint32_t *offsets, const uint8_t *packed,
+                            uint8_t *dbn_nib, int32_t *score_milli, uint16_t *n_stems, uint8_t *flags);
+SQRN_API int  sqrn_pack_symbols(int64_t n_total, const uint8_t *symbols, uint8_t *packed, int64_t *n_other);
+SQRN_API int  sqrn_unpack_dbn(int64_t n_seqs, const uint32_t *offsets, const uint8_t *dbn_nib, uint8_t *dbn_ascii);
+/* Per-sequence flags of the last sqrn_fast_predict_host call (bit 1: more than 30 pseudoknot levels, the ASCII
+ * glyphs ran out).  When that call returns SQRN_E_UNSUPPORTED for this reason every OTHER sequence's result is valid:
+ * the flagged ones go through sqrn_predict_batch, whose level codes have no such limit.                              */
+SQRN_API int  sqrn_fast_last_flags(const sqrn_ctx *ctx, int64_t n_seqs, uint8_t *flags);
 
 /* TEST SEAM (tests/ only): one launch of the work kernel in a given mode
  * (0 run to completion, 1 one OptimalStems + ChooseStems, 2 AnnotateStems,

@@ -475,7 +475,11 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
             and not paramsets[0].get("bpp", 0) and poollim == 1 and not interchainonly
             and min(toplim, outplim, conslim) >= 1 and (fmt == "fasta" or inputformat.startswith("q"))
             and not entropy and os.environ.get("SQRN_NO_BULK") is None):
-        if _bulk_lane(inputfile, fmt == "fasta", paramsetnames[0], paramsets[0], conslim, write_to):
+        def per_entry(entries):              # the few entries the bulk lane cannot print (> 30 pseudoknot levels)
+            RunSQRNdbnseqBatch(entries, paramsetnames, paramsets, rankbydiff, rankby, hardrest, interchainonly,
+                               toplim, outplim, conslim, reactformat, evalonly, poollim, sink=write_to,
+                               algos=algos, priority=priority, rfam=None, levellimit=levellimit, entropy=entropy, M=M, B=B)
+        if _bulk_lane(inputfile, fmt == "fasta", paramsetnames[0], paramsets[0], conslim, write_to, per_entry=per_entry):
             return
 
     def config_for(sequence):               # autoconfig by RAW (gapped) length, cli.py:870-878
@@ -505,7 +509,7 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
     flush()
 
 
-def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, slice_entries=131072):
+def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, slice_entries=131072, per_entry=None):
     """SQUARNA.py:845-935 for the plain shape of an input.  False: not that shape (nothing was written)."""
     import numpy as np
     from . import _lib
@@ -527,19 +531,36 @@ def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, sl
     else:
         ctx = get_context(devs[0])
     try:
-        dbn, scores, _nst = ctx.fast_predict(paramset, sym, sym_off)
+        dbn, scores, nst = ctx.fast_predict(paramset, sym, sym_off)
     except _lib.SqrnError:
-        return False                                                 # e.g. more than 30 pseudoknot levels: general path
+        return False
+    # sequences whose structure has more than 30 pseudoknot levels (n_stems = -1: the one-byte glyphs ran out) are
+    # printed by the per-entry path, in their place; everything around them stays on the bulk formatter
+    deep = np.flatnonzero(nst < 0).tolist()
+    if deep and per_entry is None:
+        return False
     binary = getattr(sink, "buffer", None)
     scratch = []                                                     # one text buffer, reused by every slice
-    for first in range(0, parsed.n, slice_entries):
-        count = min(slice_entries, parsed.n - first)
-        block = _lib.text_format(parsed, first, count, sym_off, dbn, scores, conslim, psname, scratch)
-        if binary is not None:
-            sink.flush()
-            binary.write(memoryview(block))
-        else:
-            sink.write(block.tobytes().decode("ascii"))
+
+    def emit(first, stop):
+        for lo in range(first, stop, slice_entries):
+            count = min(slice_entries, stop - lo)
+            block = _lib.text_format(parsed, lo, count, sym_off, dbn, scores, conslim, psname, scratch)
+            if binary is not None:
+                sink.flush()
+                binary.write(memoryview(block))
+            else:
+                sink.write(block.tobytes().decode("ascii"))
+
+    at = 0
+    for e in deep:
+        emit(at, e)
+        nb, nl = int(parsed.name_begin[e]), int(parsed.name_len[e])
+        name = bytes(parsed.text[nb:nb + nl]).decode("ascii")
+        seq = bytes(parsed.seq[int(parsed.seq_offsets[e]):int(parsed.seq_offsets[e + 1])]).decode("ascii")
+        per_entry([(name, seq, None, None, None)])
+        at = e + 1
+    emit(at, parsed.n)
     return True
 
 

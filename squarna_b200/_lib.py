@@ -10,6 +10,8 @@ import numpy as np
 
 from ._abi import (Batch, ParamSet, Result, Stems, E_CAPACITY, OK, pack_sequences, paramset_array, ptr)
 
+E_UNSUPPORTED = -4
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsqrn_b200.so")
 
@@ -18,7 +20,8 @@ MODE_TAIL, MODE_STEP, MODE_YIELD, MODE_FINAL = 0, 1, 2, 3
 EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx_destroy",
            "sqrn_last_error", "sqrn_ctx_set_stream", "sqrn_predict_batch", "sqrn_yield_stems_batch",
            "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
-           "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_ungap", "sqrn_text_format"]
+           "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_ungap", "sqrn_text_format",
+           "sqrn_fast_predict_packed_host", "sqrn_pack_symbols", "sqrn_unpack_dbn", "sqrn_fast_last_flags"]
 
 _lib = None
 
@@ -50,6 +53,10 @@ def load():
     L.sqrn_yield_stems_batch.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.POINTER(Stems)]
     L.sqrn_fast_predict_host.argtypes = [vp, C.POINTER(ParamSet), i64, vp, vp, vp, vp, vp]
     L.sqrn_fast_predict_device.argtypes = [vp, C.POINTER(ParamSet), i64, i64, i32, vp, vp, vp, vp, vp]
+    L.sqrn_fast_predict_packed_host.argtypes = [vp, C.POINTER(ParamSet), i64, vp, vp, vp, vp, vp, vp]
+    L.sqrn_pack_symbols.argtypes = [i64, vp, vp, C.POINTER(i64)]
+    L.sqrn_unpack_dbn.argtypes = [i64, vp, vp, vp]
+    L.sqrn_fast_last_flags.argtypes = [vp, i64, vp]
     L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
     L.sqrn_debug_run.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.c_int, C.c_int] + [vp] * 11 + [C.c_int]
     L.sqrn_text_parse.argtypes = [vp, i64, C.c_int, C.POINTER(i64), C.POINTER(i64), i64, i64, vp, vp, vp, vp]
@@ -123,6 +130,29 @@ def text_format(parsed, first, count, sym_offsets, dbn, scores, conslim, psname,
     if rc != OK:
         raise SqrnError("sqrn_text_format failed (%d)" % rc)
     return buf[:need.value] if scratch is not None else buf[:need.value].tobytes()
+
+
+def pack_symbols(symbols):
+    """ASCII symbols (uint8 array) -> (2-bit packed uint8 array, number of symbols outside ACGUT); host only"""
+    L = load()
+    symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+    packed = np.empty((len(symbols) + 3) // 4 + 1, np.uint8)
+    bad = C.c_int64(0)
+    rc = L.sqrn_pack_symbols(len(symbols), ptr(symbols), ptr(packed), C.byref(bad))
+    if rc != OK:
+        raise SqrnError("sqrn_pack_symbols failed (%d)" % rc)
+    return packed, bad.value
+
+
+def unpack_dbn(offsets32, dbn_nib):
+    """4-bit bracket codes of the packed lane -> ASCII dot-bracket bytes (uint8 [total]); host only"""
+    L = load()
+    n = len(offsets32) - 1
+    out = np.empty(max(int(offsets32[-1]), 1), np.uint8)
+    rc = L.sqrn_unpack_dbn(n, ptr(offsets32), ptr(dbn_nib), ptr(out))
+    if rc != OK:
+        raise SqrnError("sqrn_unpack_dbn failed (%d)" % rc)
+    return out[:int(offsets32[-1])]
 
 
 class PackedBatch:
@@ -247,9 +277,43 @@ class Context:
         dbn = np.empty(max(int(offsets[-1]), 1), dtype=np.uint8)
         scores = np.empty((max(n, 1), 3), dtype=np.float64)
         nst = np.empty(max(n, 1), dtype=np.int32)
-        self._check(self.L.sqrn_fast_predict_host(self.h, C.byref(ps), n, ptr(offsets), ptr(symbols),
-                                                  ptr(dbn), ptr(scores), ptr(nst)))
+        rc = self.L.sqrn_fast_predict_host(self.h, C.byref(ps), n, ptr(offsets), ptr(symbols),
+                                           ptr(dbn), ptr(scores), ptr(nst))
+        if rc == E_UNSUPPORTED and n:
+            # more than 30 pseudoknot levels somewhere: every other sequence is complete (include/sqrn.h); the
+            # flagged ones are marked n_stems = -1 and left to the caller (predict_batch has no such limit)
+            flags = self.fast_last_flags(n)
+            deep = (flags & 2) != 0
+            if deep.any():
+                nst[:n][deep] = -1
+                rc = OK
+        self._check(rc)
         return dbn[:int(offsets[-1])], scores[:n], nst[:n]
+
+    def fast_last_flags(self, n):
+        """per-sequence flags of the last fast_predict call (bit 1: pseudoknot levels beyond the output format)"""
+        fl = np.zeros(max(n, 1), np.uint8)
+        self._check(self.L.sqrn_fast_last_flags(self.h, n, ptr(fl)))
+        return fl[:n]
+
+    def fast_predict_packed(self, paramset, packed, offsets32, dbn_nib=None, milli=None, nst=None, flags=None):
+        """the fast lane over the packed boundary format (include/sqrn.h): 2-bit base codes + uint32 offsets in ->
+        (4-bit bracket codes, scores in thousandths (n,2) int32, n_stems uint16, flags uint8).  Output arrays may be
+        passed in (pinned memory of the caller)."""
+        n = len(offsets32) - 1
+        total = int(offsets32[-1])
+        ps = paramset if isinstance(paramset, ParamSet) else ParamSet.from_dict(paramset)
+        if dbn_nib is None:
+            dbn_nib = np.empty(total // 2 + n + 1, np.uint8)
+        if milli is None:
+            milli = np.empty((max(n, 1), 2), np.int32)
+        if nst is None:
+            nst = np.empty(max(n, 1), np.uint16)
+        if flags is None:
+            flags = np.empty(max(n, 1), np.uint8)
+        self._check(self.L.sqrn_fast_predict_packed_host(self.h, C.byref(ps), n, ptr(offsets32), ptr(packed),
+                                                         ptr(dbn_nib), ptr(milli), ptr(nst), ptr(flags)))
+        return dbn_nib, milli[:n], nst[:n], flags[:n]
 
     def fast_predict_device(self, paramset, n, total, max_len, d_off, d_sym, d_dbn, d_scores, d_nst):
         """device pointers (ints) in/out, asynchronous on the context's stream"""

@@ -126,13 +126,13 @@ template <int NCAP> __host__ __device__ constexpr Layout rescan_layout()
 {
     return make_layout(NCAP, 0, FAST_CCAP, 4, 1, FAST_RCAP, -1, 0, NCAP / 4 + 2, 0, 2);
 }
-template <int NCAP>
+template <int NCAP, int IO = 1>
 __global__ void __launch_bounds__(32 * FAST_TEAMS, 4)
 k_fast(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr Layout L = fast_layout<NCAP>();
-    work_loop<Cfg<1, true, true, MODE_TAIL, -1, false, true>>(Pg, B, Wk, L, smem);
+    work_loop<Cfg<1, true, true, MODE_TAIL, -1, false, true, -1, IO>>(Pg, B, Wk, L, smem);
 }
 // The same lane without the persistent run list: every greedy step re-enumerates the anti-diagonals.
 // Runs behind k_fast on the items whose list overflowed (DevWork::ovf_list), normally none.
@@ -142,7 +142,7 @@ k_fast_rescan(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr Layout L = rescan_layout<NCAP>();
-    work_loop<Cfg<1, true, true, MODE_TAIL>>(Pg, B, Wk, L, smem);
+    work_loop<Cfg<1, true, true, MODE_TAIL>>(Pg, B, Wk, L, smem);          // (either boundary format, decided at run time)
 }
 
 // ----------------------------------------------------------------- context
@@ -181,9 +181,9 @@ struct CachedStems {
     std::vector<int64_t> off; std::vector<int32_t> stems; std::vector<double> scores;
 };
 
-enum { B_OFF, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS, B_BPP, B_BPPOFF,
+enum { B_OFF, B_OFF32, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS, B_BPP, B_BPPOFF,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, W_RNDC, W_RNDL, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -429,6 +429,7 @@ static int plan_fast(sqrn_ctx *ctx, Plan &pl)
     pl.tw = 1; pl.tpc = FAST_TEAMS; pl.threads = 32 * FAST_TEAMS; pl.L = L; pl.smem = (size_t)FAST_TEAMS * L.total;
     pl.fast_ncap = NCAP;
     CK(cudaFuncSetAttribute(k_fast<NCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    CK(cudaFuncSetAttribute(k_fast<NCAP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fast<NCAP>, pl.threads, pl.smem));
     if (nb < 1) { ctx->err = "kernel does not fit on an SM"; return SQRN_E_UNSUPPORTED; }
@@ -602,7 +603,12 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
     if (pl.fast_ncap) {
         if (!W.ovf_list || !W.ovf_count || !W.n_items_dev) { ctx->err = "fast lane launched without an overflow list"; return SQRN_E_BADARG; }
         DevWork W1 = W; W1.n_items_dev = nullptr;
-        if (pl.fast_ncap == 128) k_fast<128><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
+        if (B.sym_packed) {
+            if (pl.fast_ncap == 128) k_fast<128, 2><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
+            else if (pl.fast_ncap == 224) k_fast<224, 2><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
+            else k_fast<320, 2><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
+        }
+        else if (pl.fast_ncap == 128) k_fast<128><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
         else if (pl.fast_ncap == 224) k_fast<224><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
         else k_fast<320><<<grid, pl.threads, pl.smem, st>>>(P.d_p, B, W1);
         CK(cudaGetLastError());
@@ -634,13 +640,16 @@ static int launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, const DevBatch
 
 // ------------------------------------------------ fast lane (byseq pl=1 shape)
 // one launch over items [item_base, item_base + n_items) of a resident CSR batch
+// compact device outputs of the packed lane (NULL members: the byte lane)
+struct PackedOut { uint8_t *nib = nullptr; int32_t *milli = nullptr; uint16_t *ns16 = nullptr; int *rnd_count = nullptr; double *rnd_list = nullptr; int rnd_cap = 0; };
+
 static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t st, int64_t item_base, int64_t n_items,
                        const int64_t *d_offsets, const uint8_t *d_symbols, uint8_t *d_dbn_ascii, double *d_scores,
                        int32_t *d_n_stems, uint8_t *d_flags, int *d_counter, int32_t *d_ovf, unsigned long long *d_ncalls, int round3,
-                       cudaEvent_t e0, cudaEvent_t e1, const int32_t *d_order = nullptr)
+                       cudaEvent_t e0, cudaEvent_t e1, const int32_t *d_order = nullptr, const PackedOut *pk = nullptr)
 {
     DevBatch B; memset(&B, 0, sizeof B);
-    B.n_seqs = item_base + n_items; B.off = d_offsets; B.sym = d_symbols;
+    B.n_seqs = item_base + n_items; B.off = d_offsets; B.sym = d_symbols; B.sym_packed = pk != nullptr;
     DevWork W; memset(&W, 0, sizeof W);
     W.n_items = (int)n_items; W.item_base = (int)item_base; W.mode = MODE_TAIL; W.region_mode = ctx->region_mode;
     W.round3 = round3; W.counter = d_counter; W.out_flags = d_flags; W.n_calls = d_ncalls;
@@ -648,6 +657,7 @@ static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStrea
         W.ovf_count = d_counter + 1; W.n_items_dev = d_counter + 1; W.ovf_list = d_ovf + item_base;
     }
     W.out_nstems = d_n_stems; W.out_raw = d_scores; W.dbn_off = d_offsets; W.out_dbn_ascii = d_dbn_ascii;
+    if (pk) { W.out_dbn_ascii = nullptr; W.out_raw = nullptr; W.out_nstems = nullptr; W.out_dbn_nib = pk->nib; W.out_milli = pk->milli; W.out_ns16 = pk->ns16; W.rnd_count = pk->rnd_count; W.rnd_list = pk->rnd_list; W.rnd_cap = pk->rnd_cap; }
     W.order = d_order;             // absolute item ids, or NULL: items item_base .. item_base + n_items - 1 in order
     if (e0) CK(cudaEventRecord(e0, st));
     TRY(dispatch(ctx, P, pl, st, B, W));
@@ -685,23 +695,55 @@ extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, 
 // Host buffers in, host buffers out.  The batch is cut into chunks that flow through three
 // stages on separate streams -- host->device copy, kernel, device->host copy -- so PCIe traffic
 // in both directions overlaps the kernels of the neighbouring chunks.
-extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, const int64_t *offsets,
-                                      const uint8_t *symbols, uint8_t *dbn_ascii, double *scores, int32_t *n_stems)
+//
+// Two boundary formats share the pipeline.  Bytes: ASCII symbols + int64 offsets in, ASCII dot-bracket + three rounded
+// float64 scores + int32 stem counts out.  Packed (`off32` set): 2-bit base codes + uint32 offsets in (offsets are
+// widened on the device), 4-bit bracket codes + two int32 scores in thousandths + uint16 stem counts + flags out --
+// 0.11 GB instead of 0.30 GB over PCIe per million 130-nt sequences.
+__global__ void k_widen_offsets(const uint32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n)
 {
-    if (!ctx || !ps || !offsets || n_seqs < 0 || n_seqs > 0x7fffffff) return SQRN_E_BADARG;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) out[k] = (int64_t)in[k];
+}
+
+struct FastIO {
+    const int64_t *off64 = nullptr; const uint32_t *off32 = nullptr; const uint8_t *symbols = nullptr;
+    uint8_t *dbn = nullptr;            // ASCII (bytes) or 4-bit codes (packed)
+    double *scores = nullptr; int32_t *n_stems = nullptr;                     // bytes
+    int32_t *milli = nullptr; uint16_t *ns16 = nullptr; uint8_t *flags = nullptr;   // packed
+};
+
+static int fast_predict_host_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, const FastIO &io)
+{
+    const bool packed = io.off32 != nullptr;
+    const int64_t *offsets = io.off64; const uint8_t *symbols = io.symbols; uint8_t *dbn_ascii = io.dbn;
+    double *scores = io.scores; int32_t *n_stems = io.n_stems;
+    auto OFF = [&](int64_t b) -> int64_t { return packed ? (int64_t)io.off32[b] : offsets[b]; };
     cudaSetDevice(ctx->device);
     ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
     if (n_seqs == 0) return SQRN_OK;
     const bool trace = getenv("SQRN_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_0 = now();
-    const int64_t total = offsets[n_seqs];
-    int64_t *d_off; uint8_t *d_sym, *d_dbn, *d_flags; double *d_sc; int32_t *d_ns; int *d_counter; unsigned long long *d_nc;
+    const int64_t total = OFF(n_seqs);
+    int64_t *d_off; uint8_t *d_sym, *d_dbn, *d_flags; double *d_sc = nullptr; int32_t *d_ns = nullptr; int *d_counter; unsigned long long *d_nc;
+    uint32_t *d_off32 = nullptr; PackedOut pk; int *d_rnd = nullptr;
+    constexpr int RND_CAP = 4096;
     TRY(dalloc(ctx, B_OFF, (size_t)n_seqs + 1, &d_off));
-    TRY(dalloc(ctx, B_SYM, (size_t)std::max<int64_t>(total, 1), &d_sym));
-    TRY(dalloc(ctx, W_DBNA, (size_t)std::max<int64_t>(total, 1), &d_dbn));
-    TRY(dalloc(ctx, W_ORAW, (size_t)n_seqs * 3, &d_sc));
-    TRY(dalloc(ctx, W_ON, (size_t)n_seqs, &d_ns));
+    if (packed) {
+        TRY(dalloc(ctx, B_OFF32, (size_t)n_seqs + 1, &d_off32));
+        TRY(dalloc(ctx, B_SYM, (size_t)(total + 3) / 4 + 1, &d_sym));
+        TRY(dalloc(ctx, W_DBNA, (size_t)(total / 2 + n_seqs + 1), &d_dbn));
+        TRY(dalloc(ctx, W_ORAW, (size_t)n_seqs, &d_sc));              // 2 int32 per sequence
+        TRY(dalloc(ctx, W_ON, (size_t)(n_seqs + 1) / 2, &d_ns));      // uint16 per sequence
+        TRY(dalloc(ctx, W_RNDC, 1, &d_rnd));
+        TRY(dalloc(ctx, W_RNDL, (size_t)4 * RND_CAP, &pk.rnd_list));
+        pk.nib = d_dbn; pk.milli = (int32_t *)d_sc; pk.ns16 = io.ns16 ? (uint16_t *)d_ns : nullptr; pk.rnd_count = d_rnd; pk.rnd_cap = RND_CAP;
+    } else {
+        TRY(dalloc(ctx, B_SYM, (size_t)std::max<int64_t>(total, 1), &d_sym));
+        TRY(dalloc(ctx, W_DBNA, (size_t)std::max<int64_t>(total, 1), &d_dbn));
+        TRY(dalloc(ctx, W_ORAW, (size_t)n_seqs * 3, &d_sc));
+        TRY(dalloc(ctx, W_ON, (size_t)n_seqs, &d_ns));
+    }
     TRY(dalloc(ctx, W_OFLAGS, (size_t)n_seqs, &d_flags));
     int32_t *d_ovf;
     TRY(dalloc(ctx, W_COUNTER, 4 * FAST_MAX_CHUNKS, &d_counter));
@@ -730,6 +772,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     cudaStream_t s_main = ctx->stream;
     CK(cudaMemsetAsync(d_counter, 0, 4 * FAST_MAX_CHUNKS * sizeof(int), s_main));
     CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), s_main));
+    if (packed) CK(cudaMemsetAsync(d_rnd, 0, sizeof(int), s_main));
     CK(cudaEventRecord(ctx->ev_start, s_main));
     CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
     Plan plans[4]; bool have_plan[4] = {false, false, false, false};
@@ -743,12 +786,12 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
     const bool no_order = getenv("SQRN_FAST_NO_ORDER") != nullptr;
     for (int c = 0; c < nchunks; c++) {
         const int64_t b0 = bounds[c], b1 = bounds[c + 1];
-        const int64_t t0 = offsets[b0], t1 = offsets[b1];
+        const int64_t t0 = OFF(b0), t1 = OFF(b1);
         cudaStream_t s_k = (c & 1) ? ctx->s_k2 : s_main;
         // the chunk's longest sequence picks its kernel (scanned while the earlier chunks are in flight)
         int max_len = 0;
         for (int64_t b = b0; b < b1; b++) {
-            int64_t n = offsets[b + 1] - offsets[b];
+            int64_t n = OFF(b + 1) - OFF(b);
             if (n < 0 || n > SQRN_MAX_LEN) { ctx->err = "sequence length out of range"; cudaDeviceSynchronize(); return SQRN_E_BADARG; }
             if (n > max_len) max_len = (int)n;
         }
@@ -767,29 +810,43 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
         if (b1 - b0 > 1 && (pl.tw > 1 || b1 - b0 >= 4096) && !no_order) {
             int32_t *ord = ctx->horder + b0;      // pinned, one region per chunk: the copy below is truly asynchronous
             len_count.assign((size_t)max_len + 2, 0);
-            for (int64_t b = b0; b < b1; b++) len_count[(size_t)(max_len - (offsets[b + 1] - offsets[b])) + 1]++;
+            for (int64_t b = b0; b < b1; b++) len_count[(size_t)(max_len - (OFF(b + 1) - OFF(b))) + 1]++;
             for (int l = 0; l <= max_len; l++) len_count[(size_t)l + 1] += len_count[(size_t)l];
-            for (int64_t b = b0; b < b1; b++) ord[len_count[(size_t)(max_len - (offsets[b + 1] - offsets[b]))]++] = (int32_t)b;
+            for (int64_t b = b0; b < b1; b++) ord[len_count[(size_t)(max_len - (OFF(b + 1) - OFF(b)))]++] = (int32_t)b;
             int32_t *d_o;
             TRY(dalloc(ctx, W_ORDER, (size_t)n_seqs, &d_o));
             CK(cudaMemcpyAsync(d_o + b0, ord, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
             d_order = d_o + b0;
         }
         // stage 1: inputs of the chunk
-        CK(cudaMemcpyAsync(d_off + b0 + (c ? 1 : 0), offsets + b0 + (c ? 1 : 0), (size_t)(b1 - b0 + (c ? 0 : 1)) * sizeof(int64_t),
-                           cudaMemcpyHostToDevice, ctx->s_in));
-        if (t1 > t0) CK(cudaMemcpyAsync(d_sym + t0, symbols + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, ctx->s_in));
+        const int64_t o_lo = b0 + (c ? 1 : 0), o_n = b1 - b0 + (c ? 0 : 1);      // offsets this chunk adds
+        if (packed) {
+            CK(cudaMemcpyAsync(d_off32 + o_lo, io.off32 + o_lo, (size_t)o_n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->s_in));
+            k_widen_offsets<<<(unsigned)std::min<int64_t>(256, (o_n + 255) / 256), 256, 0, ctx->s_in>>>(d_off32 + o_lo, d_off + o_lo, o_n);
+            CK(cudaGetLastError());
+            if (t1 > t0) CK(cudaMemcpyAsync(d_sym + t0 / 4, symbols + t0 / 4, (size_t)((t1 + 3) / 4 - t0 / 4), cudaMemcpyHostToDevice, ctx->s_in));
+        } else {
+            CK(cudaMemcpyAsync(d_off + o_lo, offsets + o_lo, (size_t)o_n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->s_in));
+            if (t1 > t0) CK(cudaMemcpyAsync(d_sym + t0, symbols + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, ctx->s_in));
+        }
         CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
         // stage 2: kernel
         CK(cudaStreamWaitEvent(s_k, ctx->ev_in[c], 0));
         if (c == 1) CK(cudaStreamWaitEvent(s_k, ctx->ev_start, 0));
         TRY(fast_launch(ctx, *P, pl, s_k, b0, b1 - b0, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + 4 * c, d_ovf, d_nc, 1,
-                        ctx->ev_k0[c], ctx->ev_k1[c], d_order));
+                        ctx->ev_k0[c], ctx->ev_k1[c], d_order, packed ? &pk : nullptr));
         // stage 3: outputs of the chunk
         CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k1[c], 0));
-        if (t1 > t0) CK(cudaMemcpyAsync(dbn_ascii + t0, d_dbn + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ctx->s_out));
-        CK(cudaMemcpyAsync(scores + 3 * b0, d_sc + 3 * b0, (size_t)(b1 - b0) * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
-        if (n_stems) CK(cudaMemcpyAsync(n_stems + b0, d_ns + b0, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (packed) {
+            const int64_t y0 = t0 / 2 + b0, y1 = t1 / 2 + b1;                     // bytes of the chunk's 4-bit codes
+            if (y1 > y0) CK(cudaMemcpyAsync(dbn_ascii + y0, d_dbn + y0, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, ctx->s_out));
+            CK(cudaMemcpyAsync(io.milli + 2 * b0, (int32_t *)d_sc + 2 * b0, (size_t)(b1 - b0) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+            if (io.ns16) CK(cudaMemcpyAsync(io.ns16 + b0, (uint16_t *)d_ns + b0, (size_t)(b1 - b0) * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        } else {
+            if (t1 > t0) CK(cudaMemcpyAsync(dbn_ascii + t0, d_dbn + t0, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, ctx->s_out));
+            CK(cudaMemcpyAsync(scores + 3 * b0, d_sc + 3 * b0, (size_t)(b1 - b0) * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_out));
+            if (n_stems) CK(cudaMemcpyAsync(n_stems + b0, d_ns + b0, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_out));
+        }
         CK(cudaMemcpyAsync(ctx->hflags + b0, d_flags + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, ctx->s_out));
         CK(cudaEventRecord(ctx->ev_o[c], ctx->s_out));
     }
@@ -809,12 +866,32 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
                 uint64_t w; memcpy(&w, fl + b, 8);
                 if (!(w & 0x0a0a0a0a0a0a0a0aull)) { b += 8; continue; }
             }
-            if (fl[b] & FLAG_ROUND) for (int t = 0; t < 3; t++) scores[3 * b + t] = pyround3(scores[3 * b + t]);
+            if ((fl[b] & FLAG_ROUND) && !packed) for (int t = 0; t < 3; t++) scores[3 * b + t] = pyround3(scores[3 * b + t]);
             if (fl[b] & FLAG_LEVELS) too_many_levels = true;
             b++;
         }
     }
     CK(cudaStreamSynchronize(s_main));
+    if (packed) {
+        // scores next to a rounding tie came back unrounded through the side list: CPython's round() on the host
+        int nr = 0;
+        CK(cudaMemcpy(&nr, d_rnd, sizeof nr, cudaMemcpyDeviceToHost));
+        if (nr > RND_CAP) { ctx->err = "too many scores next to a rounding tie"; return SQRN_E_UNSUPPORTED; }
+        if (nr > 0) {
+            std::vector<double> rl((size_t)4 * nr);
+            CK(cudaMemcpy(rl.data(), pk.rnd_list, rl.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int k = 0; k < nr; k++) {
+                const int64_t b = (int64_t)rl[4 * (size_t)k];
+                for (int t = 0; t < 2; t++) {
+                    const double q = pyround3(rl[4 * (size_t)k + 1 + t]) * 1000.0;
+                    if (!(fabs(q) < 2147483000.0)) { ctx->err = "score out of the range of the packed format"; return SQRN_E_UNSUPPORTED; }
+                    io.milli[2 * b + t] = (int32_t)llrint(q);
+                }
+            }
+        }
+        if (io.flags) memcpy(io.flags, ctx->hflags, (size_t)n_seqs);
+        too_many_levels = false;          // the caller reads the flags: bit 1 = the sequence needs the byte lane (more than 7 levels)
+    }
     const double t_3 = now();
     for (int c = 0; c < nchunks; c++) {
         float ms = 0;
@@ -842,6 +919,30 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
             fprintf(stderr, "[sqrn]   chunk %2d kernel %.3f .. %.3f ms\n", c, a, b);
         }
     }
+    return SQRN_OK;
+}
+
+extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, const int64_t *offsets,
+                                      const uint8_t *symbols, uint8_t *dbn_ascii, double *scores, int32_t *n_stems)
+{
+    if (!ctx || !ps || !offsets || n_seqs < 0 || n_seqs > 0x7fffffff) return SQRN_E_BADARG;
+    FastIO io; io.off64 = offsets; io.symbols = symbols; io.dbn = dbn_ascii; io.scores = scores; io.n_stems = n_stems;
+    return fast_predict_host_impl(ctx, ps, n_seqs, io);
+}
+
+extern "C" int sqrn_fast_predict_packed_host(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, const uint32_t *offsets,
+                                             const uint8_t *packed, uint8_t *dbn_nib, int32_t *score_milli, uint16_t *n_stems,
+                                             uint8_t *flags)
+{
+    if (!ctx || !ps || !offsets || !score_milli || n_seqs < 0 || n_seqs > 0x7fffffff) return SQRN_E_BADARG;
+    FastIO io; io.off32 = offsets; io.symbols = packed; io.dbn = dbn_nib; io.milli = score_milli; io.ns16 = n_stems; io.flags = flags;
+    return fast_predict_host_impl(ctx, ps, n_seqs, io);
+}
+
+extern "C" int sqrn_fast_last_flags(const sqrn_ctx *ctx, int64_t n_seqs, uint8_t *flags)
+{
+    if (!ctx || !flags || n_seqs < 0 || (size_t)n_seqs > ctx->hflags_cap) return SQRN_E_BADARG;
+    memcpy(flags, ctx->hflags, (size_t)n_seqs);
     return SQRN_OK;
 }
 

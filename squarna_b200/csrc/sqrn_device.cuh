@@ -114,6 +114,7 @@ struct DevBatch {
     int64_t        n_seqs;
     const int64_t *off;
     const uint8_t *sym;
+    int            sym_packed;    // sym is a 2-bit stream: base k of the batch at bits 2 (k & 3) of byte k >> 2, A C G U = 0 1 2 3
     const uint16_t *rcode; const double *rf_pos; const double *rf_neg; const double *rvals; int R;
     int            react_comp;
     const uint8_t *rclass; const int64_t *rbp_off; const int32_t *rbp;
@@ -155,6 +156,13 @@ struct DevWork {
     const int64_t *dbn_off;      // [n_items] offset of the item's dbn
     uint8_t       *out_dbn_ascii;
     int8_t        *out_dbn_code;
+    // compact outputs of the packed fast lane (sqrn_fast_predict_packed_host)
+    uint8_t       *out_dbn_nib;  // two positions per byte, item b from byte (dbn_off[b] >> 1) + b: 0 '.', L opening / 8 | L closing bracket of level L <= 7
+    int32_t       *out_milli;    // 2 per item: round(total, 3) and round(structscore, 3) in units of 0.001
+    uint16_t      *out_ns16;     // number of stems
+    int           *rnd_count;    // items whose rounding has to be redone by the host (FLAG_ROUND): count, and
+    double        *rnd_list;     //   (item, total, structscore, reactscore) unrounded, rnd_cap entries
+    int            rnd_cap;
     unsigned long long *n_calls; // OptimalStems-equivalent calls performed
 };
 
@@ -333,10 +341,13 @@ template <> struct Team<0> {
 //   GLIST: the persistent list lives in GLOBAL memory (DevWork::g_*; one slot per resident CTA) and
 //          caches the adjusted score of every candidate between steps (gl_build / gl_step): for CTA
 //          teams (long sequences, 10^5 .. 10^6 runs).  -1: on for CTA teams.
+//   IO:    boundary format of the fast lane: 1 bytes only (ASCII symbols in, ASCII dot-bracket + float64 scores out),
+//          2 packed only (2-bit codes in, 4-bit bracket codes + thousandths out), 0 decided at run time (DevBatch::
+//          sym_packed, DevWork::out_*).  The fast kernels carry one format each: their hot code has to stay small.
 template <int TW_, bool PLAIN_ = false, bool STDP_ = false, int MODE_ = -1, int RUNLIST_ = -1, bool CLUSTER_ = false,
-          bool PERSIST_ = false, int GLIST_ = -1>
+          bool PERSIST_ = false, int GLIST_ = -1, int IO_ = 0>
 struct Cfg {
-    static constexpr int TW = TW_, MODE = MODE_;
+    static constexpr int TW = TW_, MODE = MODE_, IO = IO_;
     static constexpr bool PLAIN = PLAIN_, STDP = STDP_, CLUSTER = CLUSTER_, PERSIST = PERSIST_;
     static constexpr bool GLIST = PERSIST_ && (GLIST_ < 0 ? (TW_ > 1) : (GLIST_ != 0));
     static constexpr bool RUNLIST = RUNLIST_ < 0 ? (TW_ == 1) : (RUNLIST_ != 0);
@@ -502,7 +513,8 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
         for (int k = 0; k < S.W; k++) {
             const int p = 32 * k + r;
             uint8_t c = CODE_OTHER;
-            if (p < N) c = P.code_table[B.sym[o + p]];
+            if (p < N) c = (C::IO == 2 || (C::IO == 0 && B.sym_packed)) ? (uint8_t)((B.sym[(o + p) >> 2] >> (2 * (int)((o + p) & 3))) & 3)
+                                                                         : P.code_table[B.sym[o + p]];
             S.code[p] = c;
             S.partner[p] = -1;
             sep |= c == CODE_SEP;
@@ -548,7 +560,8 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
     for (int p = r; p < Nw; p += T) {
         uint8_t c = CODE_OTHER, cl = 0;
         if (p < N) {
-            c = P.code_table[B.sym[o + p]];
+            c = (C::IO == 2 || (C::IO == 0 && B.sym_packed)) ? (uint8_t)((B.sym[(o + p) >> 2] >> (2 * (int)((o + p) & 3))) & 3)
+                                                             : P.code_table[B.sym[o + p]];
             if (!C::PLAIN) {
                 if (B.rcode) { uint16_t rc = B.rcode[o + p]; S.rcode[p] = rc; if (__ldg(&B.rvals[rc]) != 0.5) nondef = true; }
                 if (B.rclass) cl = B.rclass[o + p] & 7;
@@ -2701,6 +2714,15 @@ __device__ __forceinline__ double round3_fast(double x, bool &ok)
     return __ddiv_rn(k, 1000.0);
 }
 
+// the same as an integer number of thousandths (|k| < 2^31)
+__device__ __forceinline__ double round3_milli(double x, bool &ok)
+{
+    if (!(fabs(x) < 2e6)) { ok = false; return 0.0; }
+    double y = __dmul_rn(x, 1000.0), k = rint(y);
+    if (!(fabs(__dsub_rn(y, k)) < __dsub_rn(0.4999999, __dmul_rn(fabs(y), 1e-15)))) { ok = false; return 0.0; }
+    return k;
+}
+
 // ------------------------------------------------------------- finalisation
 // ScoreStruct (seq.py:861-899) + dbn of the finished structure.
 template <class C>
@@ -2712,7 +2734,7 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
     const int N = S.N;
     if (!levels_valid) team_levels<C>(S);         // stlev[] of the final structure
     int64_t doff = Wk.dbn_off ? Wk.dbn_off[item] : 0;
-    if (Wk.out_dbn_ascii || Wk.out_dbn_code) {
+    if (C::IO != 2 && (Wk.out_dbn_ascii || Wk.out_dbn_code)) {
         const int64_t so = B.off[Wk.item_seq ? Wk.item_seq[item] : item];
         #pragma unroll 1
         for (int p = r; p < N; p += T) {
@@ -2728,6 +2750,32 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
                 }
                 Wk.out_dbn_ascii[doff + p] = ch;
             }
+        }
+    }
+    const bool compact = C::IO == 2 || (C::IO == 0 && Wk.out_dbn_nib != nullptr);
+    if (compact) {
+        // two positions per byte; every item starts on a byte of its own ((doff >> 1) + item: at most one byte lost per item)
+        uint8_t *nb = Wk.out_dbn_nib + (doff >> 1) + item;
+        auto nib_of = [&](int p) -> uint32_t {
+            if (p >= N) return 0u;
+            const int pr = S.partner[p];
+            if (pr < 0) return 0u;
+            const int lv = S.stlev[S.owner[p]];
+            return (uint32_t)((p < pr ? 0 : 8) | (lv & 7));
+        };
+#ifndef SQRN_HOST_EMU
+        if (TW == 1) {
+            #pragma unroll 1
+            for (int p0 = 0; p0 < N; p0 += 32) {
+                const int p = p0 + r;
+                const uint32_t lo = nib_of(p), hi = __shfl_down_sync(0xffffffffu, lo, 1);
+                if (!(r & 1) && p < N) nb[p >> 1] = (uint8_t)(lo | (hi << 4));
+            }
+        } else
+#endif
+        {
+            #pragma unroll 1
+            for (int k = r; 2 * k < N; k += T) nb[k] = (uint8_t)(nib_of(2 * k) | (nib_of(2 * k + 1) << 4));
         }
     }
     // bpsum of every stem in units of 0.5 (GU -0.5, AU 1.5, GC 4.0), one stem per thread
@@ -2777,17 +2825,30 @@ __device__ void team_finalize(State &S, const DevParams &P, const DevBatch &B, c
             reactscore = __dsub_rn(1.0, __ddiv_rn(sum, (double)(N - nsep)));
         }
         if (!any) flags |= FLAG_INT0;
-        if (maxlev > 30) flags |= FLAG_LEVELS;
+        if (maxlev > (compact ? 7 : 30)) flags |= FLAG_LEVELS;
         double v0 = __dmul_rn(thescore, reactscore), v1 = thescore, v2 = reactscore;   // seq.py:899, before round()
-        if (Wk.round3) {
+        if (compact) {
+            // round(x, 3) as an integer number of thousandths; next to a rounding tie (or out of range) the host redoes it
             bool ok = true;
-            double q0 = round3_fast(v0, ok), q1 = round3_fast(v1, ok), q2 = round3_fast(v2, ok);
-            if (ok) { v0 = q0; v1 = q1; v2 = q2; } else flags |= FLAG_ROUND;    // raw values stay: host rounds them
+            const double k0 = round3_milli(v0, ok), k1 = round3_milli(v1, ok);
+            if (ok) { Wk.out_milli[2 * (int64_t)item] = (int32_t)k0; Wk.out_milli[2 * (int64_t)item + 1] = (int32_t)k1; }
+            else {
+                flags |= FLAG_ROUND;
+                const int slot = atomicAdd(Wk.rnd_count, 1);
+                if (slot < Wk.rnd_cap) { double *q = Wk.rnd_list + 4 * (int64_t)slot; q[0] = (double)item; q[1] = v0; q[2] = v1; q[3] = v2; }
+            }
+            if (Wk.out_ns16) Wk.out_ns16[item] = (uint16_t)(S.nst > 65535 ? 65535 : S.nst);
+        } else {
+            if (Wk.round3) {
+                bool ok = true;
+                double q0 = round3_fast(v0, ok), q1 = round3_fast(v1, ok), q2 = round3_fast(v2, ok);
+                if (ok) { v0 = q0; v1 = q1; v2 = q2; } else flags |= FLAG_ROUND;    // raw values stay: host rounds them
+            }
+            Wk.out_raw[3 * (int64_t)item] = v0;
+            Wk.out_raw[3 * (int64_t)item + 1] = v1;
+            Wk.out_raw[3 * (int64_t)item + 2] = v2;
+            Wk.out_nstems[item] = S.nst;
         }
-        Wk.out_raw[3 * (int64_t)item] = v0;
-        Wk.out_raw[3 * (int64_t)item + 1] = v1;
-        Wk.out_raw[3 * (int64_t)item + 2] = v2;
-        Wk.out_nstems[item] = S.nst;
         if (Wk.out_flags) Wk.out_flags[item] = flags;
     }
     // stems in selection order

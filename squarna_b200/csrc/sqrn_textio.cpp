@@ -302,3 +302,67 @@ extern "C" int sqrn_text_format(int64_t first, int64_t count, const char *text, 
     return SQRN_OK;
     } catch (...) { return SQRN_E_NOMEM; }
 }
+
+// ---------------------------------------------------------------- packed boundary format
+// Host helpers of sqrn_fast_predict_packed_host (include/sqrn.h): 2-bit base codes in, 4-bit bracket codes out.
+static int host_threads(int64_t work, int64_t per_thread)
+{
+    int nt = (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 16) nt = 16;
+    const int64_t want = work / per_thread + 1;
+    return (int)std::min<int64_t>(nt, want);
+}
+
+extern "C" int sqrn_pack_symbols(int64_t n_total, const uint8_t *symbols, uint8_t *packed, int64_t *n_other)
+{
+    if (n_total < 0 || (n_total && (!symbols || !packed))) return SQRN_E_BADARG;
+    uint8_t tab[256];
+    memset(tab, 4, sizeof tab);
+    tab['A'] = tab['a'] = 0; tab['C'] = tab['c'] = 1; tab['G'] = tab['g'] = 2;
+    tab['U'] = tab['u'] = tab['T'] = tab['t'] = 3;                 // T -> U as SQRNdbnseq does (seq.py:1004-1010)
+    const int64_t nbytes = (n_total + 3) / 4;
+    const int nt = host_threads(nbytes, 1 << 20);
+    std::vector<int64_t> bad((size_t)nt, 0);
+    auto fn = [&](int t) {
+        const int64_t b0 = nbytes * t / nt, b1 = nbytes * (t + 1) / nt;
+        int64_t nb = 0;
+        for (int64_t b = b0; b < b1; b++) {
+            unsigned v = 0;
+            for (int q = 0; q < 4; q++) {
+                const int64_t k = 4 * b + q;
+                unsigned c = k < n_total ? tab[symbols[k]] : 0u;
+                if (c > 3) { nb++; c = 0; }
+                v |= c << (2 * q);
+            }
+            packed[b] = (uint8_t)v;
+        }
+        bad[(size_t)t] = nb;
+    };
+    run_threads(nt, fn);
+    int64_t tot = 0;
+    for (int64_t x : bad) tot += x;
+    if (n_other) *n_other = tot;
+    return SQRN_OK;
+}
+
+extern "C" int sqrn_unpack_dbn(int64_t n_seqs, const uint32_t *offsets, const uint8_t *dbn_nib, uint8_t *dbn_ascii)
+{
+    if (n_seqs < 0 || (n_seqs && (!offsets || !dbn_nib || !dbn_ascii))) return SQRN_E_BADARG;
+    static const char op[] = ".([{<ABC", cl[] = ".)]}>abc";
+    const int nt = host_threads(n_seqs, 1 << 16);
+    auto fn = [&](int t) {
+        const int64_t s0 = n_seqs * t / nt, s1 = n_seqs * (t + 1) / nt;
+        for (int64_t b = s0; b < s1; b++) {
+            const int64_t o = offsets[b], n = (int64_t)offsets[b + 1] - o;
+            const uint8_t *src = dbn_nib + (o >> 1) + b;
+            uint8_t *dst = dbn_ascii + o;
+            for (int64_t p = 0; p < n; p++) {
+                const unsigned v = (src[p >> 1] >> (4 * (p & 1))) & 15u;
+                dst[p] = (uint8_t)((v & 8) ? cl[v & 7] : op[v & 7]);
+            }
+        }
+    };
+    run_threads(nt, fn);
+    return SQRN_OK;
+}

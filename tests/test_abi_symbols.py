@@ -23,7 +23,7 @@ def test_header_symbols_exported():
     for n in names:
         assert getattr(L, n) is not None, n
     assert set(_lib.EXPORTS) <= set(names)
-    assert L.sqrn_abi_version() == 2
+    assert L.sqrn_abi_version() == 3
 
 
 def test_struct_layouts_match_header():

@@ -39,6 +39,53 @@ def test_fast_lane_short(gpu_ctx):
     _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(11, 6000, 5, 200))
 
 
+def _check_packed(ctx, ps, seqs):
+    """the packed boundary format (2-bit codes in, 4-bit bracket codes + thousandths out) against the byte lane"""
+    from squarna_b200 import _lib
+    sym, off = pack_sequences(seqs)
+    dbn, scores, nst = ctx.fast_predict(ps, sym, off)
+    packed, bad = _lib.pack_symbols(sym)
+    assert bad == 0
+    off32 = off.astype(np.uint32)
+    nib, milli, nst16, flags = ctx.fast_predict_packed(ps, packed, off32)
+    assert not (flags & 2).any()
+    got = _lib.unpack_dbn(off32, nib)
+    assert bytes(got) == bytes(dbn[:len(got)])
+    assert (nst16.astype(np.int64) == nst).all()
+    # round(x, 3) in thousandths: the same decimal as the byte lane's rounded doubles
+    assert (milli[:, 0] / 1000.0 == scores[:, 0]).all() and (milli[:, 1] / 1000.0 == scores[:, 1]).all()
+    assert (scores[:, 2] == 0.5).all()
+    assert ((flags & 1) != 0).tolist() == (scores[:, 1] == 0.0).tolist()
+
+
+def test_packed_lane_equals_byte_lane(gpu_ctx):
+    """2-bit packed symbols / 4-bit dot-bracket codes: every chunk boundary parity (odd / even offsets), warp teams
+    and CTA teams, the empty batch and empty sequences"""
+    _check_packed(gpu_ctx, T.FASTEST, T.rand_seqs(31, 20000, 1, 200))
+    _check_packed(gpu_ctx, T.DEFG1, T.rand_seqs(32, 3000, 0, 230) + ["", "A", "", "GC"])
+    _check_packed(gpu_ctx, T.G1000, T.rand_seqs(33, 40, 300, 1500))
+    _check_packed(gpu_ctx, T.FASTEST, T.rand_seqs(34, 300000, 60, 200))       # several pipeline chunks
+
+
+def test_packed_lane_flags_deep_pseudoknots(gpu_ctx):
+    """more than 7 pseudoknot levels do not fit a 4-bit code: the sequence is flagged, the others are complete"""
+    from squarna_b200 import _lib
+    pk = dict(T.ALI); pk["orderpenalty"] = 0.0; pk["minfinscorefactor"] = 0.5; pk["minbpscore"] = 3.0
+    seqs = T.rand_seqs(35, 400, 150, 320, "GC") + T.rand_seqs(36, 200, 60, 200)
+    sym, off = pack_sequences(seqs)
+    packed, _ = _lib.pack_symbols(sym)
+    off32 = off.astype(np.uint32)
+    nib, milli, nst16, flags = gpu_ctx.fast_predict_packed(pk, packed, off32)
+    odbn, oscores, onst = O.predict_batch_simple(sym, off, [pk], poollim=1, nthreads=8)
+    deep = [b for b in range(len(seqs)) if abs(odbn[off[b]:off[b + 1]]).max(initial=0) > 7]
+    assert deep, "the generator should produce at least one structure with more than 7 levels"
+    assert sorted(np.nonzero(flags & 2)[0].tolist()) == deep
+    got = _lib.unpack_dbn(off32, nib)
+    for b in range(len(seqs)):
+        if b not in deep:
+            assert bytes(got[off[b]:off[b + 1]]).decode() == _ascii_from_codes(odbn[off[b]:off[b + 1]])
+
+
 def test_fast_lane_edge_lengths(gpu_ctx):
     seqs = ["A", "GC", "GGGG", "GGGAAACCC", "GGGGAAAACCCC", "GCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGCGC",
             "G" * 40 + "AAAA" + "C" * 40, "GGGGGGGGGGCCCCCCCCCC" * 10]

@@ -295,6 +295,38 @@ def test_bulk_lane_glue_without_a_gpu(tmp_path, monkeypatch):
     assert CLI._bulk_lane(str(tmp_path / "other.fa"), False, "fastestG", {"dummy": 1}, 1, io.StringIO()) is False
 
 
+def test_bulk_lane_hands_deep_pseudoknots_to_the_entry_path(tmp_path, monkeypatch):
+    """a sequence the fast lane marks n_stems = -1 (more than 30 pseudoknot levels: no one-byte glyph left) is
+    printed by the per-entry path IN ITS PLACE; the entries around it stay on the bulk formatter"""
+    import numpy as np
+
+    class Stub:
+        def fast_predict(self, ps, sym, off):
+            n = len(off) - 1
+            nst = np.ones(n, np.int32)
+            nst[1] = -1
+            nst[3] = -1
+            return np.full(len(sym), ord("."), np.uint8), np.tile([0.0, 0.0, 0.5], (n, 1)), nst
+
+    monkeypatch.setattr(S, "get_context", lambda device=0: Stub())
+    path = tmp_path / "in.fa"
+    path.write_text(">a\nACGU\n>b deep\nGG-GG\n>c\nACGUACGU\n>d\nCCCC\n")
+    seen = []
+
+    def per_entry(entries):
+        seen.extend(entries)
+        buf.write("<%s|%s>\n" % entries[0][:2])
+
+    buf = io.StringIO()
+    assert CLI._bulk_lane(str(path), False, "fastestG", {"dummy": 1}, 1, buf, per_entry=per_entry)
+    assert seen == [(">b deep", "GG-GG", None, None, None), (">d", "CCCC", None, None, None)]
+    parts = buf.getvalue().split("<>b deep|GG-GG>\n")
+    assert len(parts) == 2 and parts[0].startswith(">a\nACGU\n") and parts[1].startswith(">c\nACGUACGU\n")
+    assert parts[1].endswith("<>d|CCCC>\n")
+    # without a per-entry printer the lane declines (the caller then prints everything per entry)
+    assert CLI._bulk_lane(str(path), False, "fastestG", {"dummy": 1}, 1, io.StringIO()) is False
+
+
 class _OracleContext:
     """stands in for the GPU context in CPU tests of the host logic: AnnotateStems and the greedy structures come
     from the oracle (which the -m gpu tests prove bit-identical to the kernels)"""
@@ -541,3 +573,38 @@ def test_bulk_text_parse_of_a_long_text_in_segments(tmp_path, fasta):
         cut = text.rfind("\n>", 0, len(text) * 3 // 4)
         broken = text[:cut] + "\n>x\nACGU\n0.1 0.2 0.3 0.4" + text[cut:]          # an entry with a reactivity line, far from the start
         assert _lib.text_parse(broken.encode(), False) is None
+
+
+def test_packed_format_host_converters():
+    """sqrn_pack_symbols / sqrn_unpack_dbn (host only): 2-bit codes of A C G U/T in either case, count of everything
+    else; 4-bit bracket codes -> ASCII with every sequence starting on its own byte"""
+    import numpy as np
+    from squarna_b200 import _lib
+    rng = np.random.default_rng(5)
+    sym = np.frombuffer(b"ACGUacgutTNn-;&X", np.uint8)
+    packed, bad = _lib.pack_symbols(sym)
+    assert bad == 6
+    codes = [(int(packed[k >> 2]) >> (2 * (k & 3))) & 3 for k in range(len(sym))]
+    assert codes[:10] == [0, 1, 2, 3, 0, 1, 2, 3, 3, 3]
+    big = rng.integers(0, 4, 5_000_003).astype(np.uint8)
+    packed, bad = _lib.pack_symbols(np.frombuffer(b"ACGU", np.uint8)[big])
+    assert bad == 0
+    k = np.arange(len(big))
+    assert ((packed[k >> 2] >> (2 * (k & 3)).astype(np.uint8)) & 3 == big).all()
+    # unpack: lengths of both parities at offsets of both parities
+    lens = rng.integers(0, 40, 3000)
+    off = np.zeros(len(lens) + 1, np.uint32)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    nib = np.zeros(total // 2 + len(lens) + 1, np.uint8)
+    want = np.zeros(total, np.uint8)
+    glyph = ".([{<ABC" + ".)]}>abc"
+    for b in range(len(lens)):
+        base = (int(off[b]) >> 1) + b
+        for p in range(int(lens[b])):
+            v = int(rng.integers(0, 16))
+            if v == 8:
+                v = 0
+            nib[base + (p >> 1)] |= v << (4 * (p & 1))
+            want[int(off[b]) + p] = ord(glyph[v])
+    assert bytes(_lib.unpack_dbn(off, nib)) == bytes(want)
