@@ -16,6 +16,8 @@ import os
 import sys
 import threading
 
+import re
+
 import numpy as np
 
 from . import _lib
@@ -36,6 +38,8 @@ _OPEN = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ" + "БГДЁЖЙЛПФЦЧШЩЬЫЪЭЮ
 _CLOSE = ")]}>abcdefghijklmnopqrstuvwxyz" + "бгдёжйлпфцчшщьыъэюя"
 _OPEN_IDX = {c: k for k, c in enumerate(_OPEN)}
 _CLOSE_IDX = {c: k for k, c in enumerate(_CLOSE)}
+_BRACKET_RE = re.compile("[" + re.escape(_OPEN + _CLOSE) + "]")
+_RESTR_RE = re.compile(r"[_+/\\]")
 
 _ctx = {}
 _ctx_lock = threading.Lock()
@@ -195,13 +199,15 @@ def DBNToPairs(dbn):
     brackets without a partner are ignored (seq.py:172-207)."""
     stacks = {}
     pairs = set()
-    for pos, ch in enumerate(dbn):
+    # only bracket characters matter: a regular expression finds them (restraint lines are mostly dots)
+    for m in _BRACKET_RE.finditer(dbn):
+        ch, pos = m.group(), m.start()
         k = _OPEN_IDX.get(ch)
         if k is not None:
             stacks.setdefault(k, []).append(pos)
             continue
-        k = _CLOSE_IDX.get(ch)
-        if k is not None and stacks.get(k):
+        k = _CLOSE_IDX[ch]
+        if stacks.get(k):
             pairs.add((stacks[k].pop(), pos))
     return sorted(pairs)
 
@@ -261,6 +267,8 @@ def ReAlign(shortdbn, longseq, seqmode=False):
 
 def UnAlign(seq, dbn):
     """remove gap columns (and the pairs that touch them) (seq.py:236-255)"""
+    if not any(g in seq for g in GAPS):                    # nothing to remove (the usual single-sequence input)
+        return seq, dbn
     clean = list(dbn)
     for v, w in DBNToPairs(dbn):
         if seq[v] in GAPS or seq[w] in GAPS:
@@ -272,9 +280,10 @@ def UnAlign(seq, dbn):
 def ParseRestraints(restraints):
     """restraint string -> (rbps, rxs, rlefts, rrights) (seq.py:370-376)"""
     rbps = DBNToPairs(restraints)
-    rxs = {k for k, ch in enumerate(restraints) if ch in ('_', '+')}
-    rlefts = {k for k, ch in enumerate(restraints) if ch == '/'}
-    rrights = {k for k, ch in enumerate(restraints) if ch == '\\'}
+    rxs, rlefts, rrights = set(), set(), set()
+    for m in _RESTR_RE.finditer(restraints):
+        ch = m.group()
+        (rxs if ch in '_+' else rlefts if ch == '/' else rrights).add(m.start())
     return rbps, rxs, rlefts, rrights
 
 
@@ -614,7 +623,7 @@ def _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydif
             if "G" in use:
                 batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly, bpp=bpp, hardrest=False,
                                     rankbydiff=False, poollim=poollim, conslim=1, rankby=rankby, priority_mask=0)
-                for k, (_cons, structs, _nt) in zip(idx, ctx.predict_batch([ps], batch)):
+                for k, (_cons, structs, *_rest) in zip(idx, ctx.predict_batch([ps], batch)):
                     for codes, sc, isint, _mask, stems in structs:
                         stemset = [[[(i + q, j - q) for q in range(ln)], ln] for i, j, ln in np.asarray(stems).tolist()]
                         total, struct, react = sc
@@ -725,8 +734,8 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
                             poollim=poollim, conslim=conslim, rankby=rankby,
                             priority_mask=sum(1 << gsets.index(p) for p in priority if p in gsets))
         out = get_context(device).predict_batch([paramsets[g] for g in gsets], batch)
-        for k, (cons, structs, _ntot) in zip(idx, out):
-            results[k] = (cons, structs)
+        for k, o in zip(idx, out):
+            results[k] = (o[0], o[1], o[3] if len(o) > 3 else None)
 
     final = []
     for k, p in enumerate(preps):
@@ -748,16 +757,28 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
             return g.tobytes().decode("utf-32-le")
 
         if results[k] is None:
-            cons_codes, structs = np.zeros(len(p.shortseq), np.int8), []
+            cons_codes, structs, codes2d = np.zeros(len(p.shortseq), np.int8), [], None
         else:
-            cons_codes, structs = results[k]
+            cons_codes, structs, codes2d = results[k]
         cons = expand(cons_codes)
+        texts = None
+        if codes2d is not None and len(structs) > 1:
+            # every structure of the sequence in one pass: glyphs, gap columns, separators, one decode
+            g = _GLYPH32[codes2d.view(np.uint8)]
+            if keep is not None:
+                long_ = np.full((len(structs), len(raw)), ord('.'), dtype=np.uint32)
+                long_[:, keep] = g
+                g = long_
+            if len(seppos):
+                g[:, seppos] = raw[seppos]
+            whole, width = g.tobytes().decode("utf-32-le"), len(raw)
+            texts = [whole[q * width:(q + 1) * width] for q in range(len(structs))]
         preds = []
         bpsets = []
-        for codes, sc, isint, mask, stems in structs:
+        for q, (codes, sc, isint, mask, stems) in enumerate(structs):
             total, struct, react = sc
             inds = [gsets[b] for b in range(len(gsets)) if mask >> b & 1]
-            preds.append((expand(codes), (total, 0 if isint else struct, react), inds))
+            preds.append((texts[q] if texts is not None else expand(codes), (total, 0 if isint else struct, react), inds))
             bpsets.append(codes)
         if p.dbn:                                # seq.py:1249-1285
             known = set(DBNToPairs(p.shortdbn))

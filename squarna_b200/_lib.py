@@ -355,14 +355,20 @@ class Context:
                 continue
             self._check(rc)
             break
+        # per sequence: (consensus codes, [(codes, scores, is_int0, psmask, stems)], n_total, codes of all its structures as
+        # one (n_structs, N) array when they lie back to back).  Everything is a view of this call's arrays.
         out = []
+        so_l, sto_l, dbo_l, off_l = so.tolist(), sto.tolist(), dbo.tolist(), batch.offsets.tolist()
+        sc_l, isint_l, mask_l, ntot_l = scores.tolist(), isint.tolist(), mask.tolist(), ntot.tolist()
         for b in range(n):
-            N = int(batch.offsets[b + 1] - batch.offsets[b])
-            structs = []
-            for k in range(int(so[b]), int(so[b + 1])):
-                structs.append((dbn[dbo[k]:dbo[k] + N].copy(), tuple(float(x) for x in scores[k]), bool(isint[k]),
-                                int(mask[k]), stems[sto[k]:sto[k + 1]].copy()))
-            out.append((cons[batch.offsets[b]:batch.offsets[b] + N].copy(), structs, int(ntot[b])))
+            N = off_l[b + 1] - off_l[b]
+            k0, k1 = so_l[b], so_l[b + 1]
+            codes2d = None
+            if k1 > k0 and dbo_l[k1 - 1] - dbo_l[k0] == (k1 - k0 - 1) * N:
+                codes2d = dbn[dbo_l[k0]:dbo_l[k0] + (k1 - k0) * N].reshape(k1 - k0, N)
+            structs = [(codes2d[k - k0] if codes2d is not None else dbn[dbo_l[k]:dbo_l[k] + N], tuple(sc_l[k]), bool(isint_l[k]),
+                        mask_l[k], stems[sto_l[k]:sto_l[k + 1]]) for k in range(k0, k1)]
+            out.append((cons[off_l[b]:off_l[b] + N], structs, ntot_l[b], codes2d))
         return out
 
     def yield_stems(self, paramset, batch):

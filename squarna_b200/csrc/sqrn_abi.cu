@@ -7,7 +7,9 @@
 // hand back caller-owned buffers.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -183,7 +185,7 @@ struct CachedStems {
 
 enum { B_OFF, B_OFF32, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS, B_BPP, B_BPPOFF,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, W_RNDC, W_RNDL, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, W_RNDC, W_RNDL, W_BASE, W_BASEOFF, W_BASEN, W_BASEBEND, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -357,8 +359,9 @@ static int plan_for(sqrn_ctx *ctx, Plan &pl)
 // choose the team shape for sequences up to nmax symbols.  keep_all: the mode needs every
 // survivor of a scan in the list (MODE_STEP); otherwise the lists are flushed when they fill up
 // and their sizes only set the flush granularity.
+// small_lists: the items sweep a base list (only in-range survivors stay in the list between flushes).
 static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int min_ccap, bool keep_all, bool extras,
-                     int max_init, Plan &pl)
+                     int max_init, Plan &pl, bool small_lists = false)
 {
     const int m = P.hp.m, npc = P.hp.npc;
     // every stem the greedy adds has >= m pairs (AnnotateStems' minlen filter, seq.py:492); max_init < 0: unknown
@@ -379,6 +382,7 @@ static int make_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int rbmax, int mi
     pl.tw = nmax <= 2048 ? 8 : 32;
     // at least two rounds of survivors (one per thread and round) must fit between flushes
     int ccap = keep_all ? std::max(std::min(next_pow2(est), 4096), 1024 * (pl.tw / 8)) : (pl.tw == 8 ? 2048 : 8192);
+    if (small_lists) ccap = 1024 * (pl.tw / 8);             // (more CTAs per SM; an item whose window holds more is redone with min_ccap)
     if (ccap < min_ccap) ccap = next_pow2(min_ccap);
     for (;;) {
         pl.L = make_layout(nmax, rbmax, ccap, npc, pl.tw, 4096, extras, keep_all, scap);
@@ -1020,8 +1024,12 @@ static int upload_batch(sqrn_ctx *ctx, const sqrn_batch *in, DeviceBatch &D)
     return SQRN_OK;
 }
 
+// base lists of the batch for the current parameter set (device pointers; DevWork::base_*)
+struct BaseDev { BEnt *ent = nullptr; int64_t *off = nullptr; int32_t *n = nullptr; int32_t *bend = nullptr; bool valid = false; };
+
 struct HostWork {
     int mode = MODE_TAIL;
+    const BaseDev *base = nullptr;
     std::vector<int32_t> item_seq; std::vector<int64_t> init_off; std::vector<int32_t> init_stems;
     std::vector<double> subopt; std::vector<int64_t> out_cap;        // per item stem capacity
     bool want_dbn = false, want_fin = false;
@@ -1074,6 +1082,8 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
     TRY(dalloc(ctx, W_COUNTER, 1, &G.counter));
     TRY(dalloc(ctx, W_NCALLS, 1, &G.n_calls));
     CK(cudaMemsetAsync(G.n_calls, 0, sizeof(unsigned long long), ctx->stream));
+    const bool have_base = W.base && W.base->valid && (W.mode == MODE_STEP || W.mode == MODE_TAIL || W.mode == MODE_BASE);
+    if (have_base) { G.base_ent = W.base->ent; G.base_off = W.base->off; G.base_n = W.base->n; G.base_bend = W.base->bend; }
 
     // length classes: warp teams (<= 320), 256-thread CTAs (<= 2048), 1024-thread CTAs
     std::vector<int32_t> order((size_t)n);
@@ -1096,7 +1106,8 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
         int c = cls(order[pos]), end = pos;
         while (end < n && cls(order[end]) == c) end++;
         int nmax_c = D.len[W.item_seq[order[pos]]];
-        Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, W.mode == MODE_STEP, D.B.rcode != nullptr, max_init, pl));
+        Plan pl; TRY(make_plan(ctx, *P, std::max(nmax_c, 1), D.rbmax, min_ccap, W.mode == MODE_STEP, D.B.rcode != nullptr, max_init, pl,
+                               have_base && c > 0));
         {
             const bool plain = !D.B.rcode && !D.B.rclass && !D.B.rbp_off && !D.B.smat && !D.B.interchainonly && !D.B.bpp;
             maybe_glist(ctx, *P, pl, std::max(nmax_c, 1), D.rbmax, D.B.rcode != nullptr, max_init, W.mode == MODE_TAIL);
@@ -1122,6 +1133,41 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
     return SQRN_OK;
 }
 
+// Base lists for the pool rounds of one parameter set: every sequence served by CTA teams (> 320 nt) gets a slot sized
+// from the run density of random RNA (a slot that turns out too small just leaves its sequence to the enumerating path).
+static int build_base(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &D, BaseDev &bd)
+{
+    bd = BaseDev();
+    static const bool off_knob = getenv("SQRN_NO_BASE") != nullptr;
+    if (off_knob) return SQRN_OK;
+    const int64_t nseq = (int64_t)D.len.size();
+    const PEntry *P; TRY(get_params(ctx, ps, std::max(D.nmax, 1), &P));
+    if (!P->hp.ub_ok || !(P->hp.loopbonus >= 0.0)) return SQRN_OK;
+    const int m = P->hp.m;
+    const double dens = m >= 4 ? 0.003 : (m == 3 ? 0.008 : 0.02);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return SQRN_OK; }
+    const int64_t budget = (int64_t)std::min<size_t>(free_b / 2, (size_t)48 << 30) / (int64_t)sizeof(BEnt);
+    std::vector<int64_t> off((size_t)nseq + 1, 0);
+    HostWork W; W.mode = MODE_BASE;
+    for (int64_t b = 0; b < nseq; b++) {
+        int64_t cap = 0;
+        if (D.len[b] > 320) cap = (int64_t)(1.5 * dens * D.len[b] * (double)D.len[b]) + 1024;
+        if (off[b] + cap > budget) cap = 0;
+        off[b + 1] = off[b] + cap;
+        if (cap) { W.item_seq.push_back((int32_t)b); W.out_cap.push_back(0); }
+    }
+    if (W.item_seq.empty()) return SQRN_OK;
+    TRY(dalloc(ctx, W_BASE, (size_t)off[nseq], &bd.ent));
+    TRY(upload(ctx, W_BASEOFF, off.data(), (size_t)nseq + 1, &bd.off));
+    TRY(dalloc(ctx, W_BASEN, (size_t)nseq, &bd.n));
+    TRY(dalloc(ctx, W_BASEBEND, (size_t)nseq * (GL_NBIN + 1), &bd.bend));
+    CK(cudaMemsetAsync(bd.n, 0xff, (size_t)nseq * sizeof(int32_t), ctx->stream));
+    bd.valid = true;
+    W.base = &bd;
+    return run_items(ctx, ps, D, W);
+}
+
 // MODE_STEP with retries: grows the per-item output capacity / candidate list
 // until every item fits (no approximation is ever returned)
 static int run_step_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &D, HostWork &W)
@@ -1139,7 +1185,7 @@ static int run_step_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBa
     std::vector<int64_t> want((size_t)n, 0);
     for (int k : redo) want[k] = std::max<int64_t>(D.len[W.item_seq[k]] / 2 + 1, W.out_n[k]);
     for (int attempt = 0; attempt < 5 && !redo.empty(); attempt++) {
-        HostWork R; R.mode = MODE_STEP;
+        HostWork R; R.mode = MODE_STEP; R.base = W.base;
         bool list_overflow = false;
         for (int k : redo) {
             R.item_seq.push_back(W.item_seq[k]);
@@ -1227,6 +1273,28 @@ static void pairs_to_codes(std::vector<std::pair<int, int>> pairs, int N, int8_t
     }
 }
 
+// fn(b) for b in [0, n) on a few host threads (per-sequence bookkeeping of big batches: each b touches only its own
+// data).  Exceptions never leave a worker; a thread that cannot be started just leaves its share to the others.
+template <class F>
+static void parallel_for(int64_t n, F &&fn)
+{
+    int nt = (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 16));
+    if (n < 64 || nt == 1) { for (int64_t b = 0; b < n; b++) fn(b); return; }
+    std::atomic<int64_t> next(0);
+    auto work = [&] {
+        for (;;) {
+            const int64_t b0 = next.fetch_add(16);
+            if (b0 >= n) break;
+            for (int64_t b = b0; b < std::min(n, b0 + 16); b++) fn(b);
+        }
+    };
+    std::vector<std::thread> th;
+    try { for (int t = 1; t < nt; t++) th.emplace_back(work); } catch (...) {}
+    work();
+    for (auto &x : th) x.join();
+}
+
 // ------------------------------------------------------------ full G path
 struct Struct {
     std::vector<Stem3> stems; uint64_t psmask; double score[3]; uint8_t isint0;
@@ -1284,10 +1352,16 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
     if (in->bpp_mode && n_ps != 1) { ctx->err = "a bpp term belongs to one parameter set: call with n_ps == 1"; return SQRN_E_BADARG; }
     ctx->cres.valid = false;
     ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
+    const bool trace = getenv("SQRN_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now(), t_upload = 0, t_base = 0, t_gather = 0, t_step = 0, t_scatter = 0, t_tail = 0, t_dedupe = 0, t_final = 0;
+    auto lap = [&](double &acc) { const double t = now(); acc += t - t_mark; t_mark = t; };
+    int n_rounds = 0;
     DeviceBatch D;
     TRY(upload_batch(ctx, in, D));
     const int64_t nseq = in->n_seqs;
     const int poollim = in->poollim;
+    lap(t_upload);
     std::vector<std::vector<Struct>> uniq((size_t)nseq);
     std::vector<std::unordered_map<uint64_t, std::vector<int>>> index((size_t)nseq);
 
@@ -1296,10 +1370,13 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
         const double inc = (P.suboptmax - P.suboptmin) / P.suboptsteps;          // seq.py:1071
         std::vector<Pool> pools((size_t)nseq);
         for (auto &pl : pools) { pl.cur.assign(1, {}); pl.cursize = 1; pl.cursubopt = P.suboptmin; }
+        BaseDev base;
+        if (poollim > 1) TRY(build_base(ctx, P, D, base));      // (pl = 1: the structures run to completion on their own persistent lists)
+        lap(t_base);
         std::vector<std::pair<int, int>> tail_items;      // (seq, index in its pool) run to completion
         for (;;) {
             // round prologue per pool, seq.py:1161-1174
-            HostWork W; W.mode = MODE_STEP;
+            HostWork W; W.mode = MODE_STEP; W.base = &base;
             std::vector<std::pair<int, int>> owner;        // item -> (seq, pool index)
             bool any = false;
             for (int64_t b = 0; b < nseq; b++) {
@@ -1331,7 +1408,9 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                 for (auto &s : pools[o.first].cur[o.second]) { W.init_stems.push_back(s.i); W.init_stems.push_back(s.j); W.init_stems.push_back(s.len); }
                 W.init_off.push_back((int64_t)W.init_stems.size() / 3);
             }
+            lap(t_gather); n_rounds++;
             TRY(run_step_items(ctx, P, D, W));
+            lap(t_step);
             // seq.py:1179-1199: children in pool order, or finalise
             std::vector<std::vector<std::vector<Stem3>>> next((size_t)nseq);
             for (size_t k = 0; k < owner.size(); k++) {
@@ -1347,10 +1426,12 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                 }
             }
             for (int64_t b = 0; b < nseq; b++) if (!pools[b].done && !pools[b].tail) pools[b].cur.swap(next[b]);
+            lap(t_scatter);
         }
+        lap(t_gather);
         // tail phase: every remaining structure runs to completion on its own
         {
-            HostWork W; W.mode = MODE_TAIL;
+            HostWork W; W.mode = MODE_TAIL; W.base = &base;
             std::vector<std::pair<int, int>> owner;
             W.init_off.push_back(0);
             for (int64_t b = 0; b < nseq; b++) {
@@ -1393,8 +1474,9 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                 }
             }
         }
+        lap(t_tail);
         // dedupe by bp set across parameter sets, seq.py:1201-1212
-        for (int64_t b = 0; b < nseq; b++) {
+        parallel_for(nseq, [&](int64_t b) {
             for (auto &st : pools[b].fin) {
                 std::vector<std::pair<int, int>> bps;
                 stems_to_bps(st, bps);
@@ -1408,9 +1490,10 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                 index[b][h].push_back((int)uniq[b].size());
                 uniq[b].push_back(std::move(S));
             }
-        }
+        });
     }
 
+    lap(t_dedupe);
     // ScoreStruct + dbn of every unique structure on the device (MODE_FINAL)
     {
         HostWork W; W.mode = MODE_FINAL; W.want_dbn = true;
@@ -1423,25 +1506,25 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                 W.out_cap.push_back(0);
             }
         TRY(run_items(ctx, ps[0], D, W));
-        size_t k = 0;
-        for (int64_t b = 0; b < nseq; b++)
+        std::vector<size_t> first((size_t)nseq + 1, 0);
+        for (int64_t b = 0; b < nseq; b++) first[b + 1] = first[b] + uniq[b].size();
+        parallel_for(nseq, [&](int64_t b) {
+            size_t k = first[b];
             for (auto &S : uniq[b]) {
                 for (int t = 0; t < 3; t++) S.score[t] = pyround3(W.out_raw[3 * k + t]);     // seq.py:899
-                S.isint0 = W.flags[k] & 1;
-                if (W.flags[k] & 2) {
-                    // more than 127 levels cannot be coded in int8; 31..127 are fine for the code output
-                }
+                S.isint0 = W.flags[k] & 1;       // (flag 2, more than 30 levels: the int8 level codes of this output go up to 127)
                 S.dbn.assign(W.dbn.begin() + W.dbn_off[k], W.dbn.begin() + W.dbn_off[k + 1]);
                 k++;
             }
+        });
     }
 
+    lap(t_final);
     // rank (RankStructs, seq.py:902-955), forced pairs, consensus, truncate
     CachedResult &C = ctx->cres;
     C = CachedResult();
     C.n_seqs = nseq; C.total_len = in->offsets[nseq];
     C.struct_offsets.assign((size_t)nseq + 1, 0);
-    C.stem_offsets.assign(1, 0);
     C.n_total.assign((size_t)nseq, 0);
     C.cons.assign((size_t)C.total_len, 0);
     const int *rb = in->rankby;
@@ -1450,10 +1533,16 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
     }
     HostParams HP;           // symbol codes of the last paramset, for the hardrest key test
     if (in->hardrest) { std::string e; if (!build_host_params(ps[n_ps - 1], 16, HP, e)) { ctx->err = e; return SQRN_E_UNSUPPORTED; } }
-    for (int64_t b = 0; b < nseq; b++) {
+    // pass 1 (per sequence, in parallel): the final order; pass 2: where every sequence's output starts; pass 3 (in
+    // parallel): the output arrays
+    std::vector<std::vector<int>> order((size_t)nseq);
+    std::vector<int> keepn((size_t)nseq, 0);
+    std::vector<int64_t> stems_of((size_t)nseq + 1, 0);
+    parallel_for(nseq, [&](int64_t b) {
         auto &U = uniq[b];
         const int n = (int)U.size(), N = D.len[b];
-        std::vector<int> idx((size_t)n);
+        std::vector<int> &idx = order[b];
+        idx.resize((size_t)n);
         for (int k = 0; k < n; k++) idx[k] = k;
         auto keycmp = [&](int x, int y) {      // > 0 when x ranks before y
             for (int t = 0; t < 3; t++) {
@@ -1487,6 +1576,28 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
             }
             std::stable_sort(idx.begin() + cur, idx.end(), [&](int x, int y) { return keycmp(x, y) > 0; });
         }
+        C.n_total[b] = n;
+        keepn[b] = (in->max_structs > 0 && in->max_structs < n) ? in->max_structs : n;
+        int64_t ns = 0;
+        for (int r = 0; r < keepn[b]; r++) ns += (int64_t)U[idx[r]].stems.size();
+        stems_of[b + 1] = ns;
+    });
+    for (int64_t b = 0; b < nseq; b++) {
+        C.struct_offsets[b + 1] = C.struct_offsets[b] + keepn[b];
+        stems_of[b + 1] += stems_of[b];
+    }
+    const int64_t n_out = C.struct_offsets[nseq];
+    C.scores.resize((size_t)n_out * 3); C.isint0.resize((size_t)n_out); C.psmask.resize((size_t)n_out);
+    C.stem_offsets.resize((size_t)n_out + 1); C.dbn_offsets.resize((size_t)n_out);
+    C.stems.resize((size_t)stems_of[nseq] * 3);
+    std::vector<int64_t> dbn_of((size_t)nseq + 1, 0);
+    for (int64_t b = 0; b < nseq; b++) dbn_of[b + 1] = dbn_of[b] + (int64_t)keepn[b] * D.len[b];
+    C.dbn.resize((size_t)dbn_of[nseq]);
+    C.stem_offsets[(size_t)n_out] = stems_of[nseq];
+    parallel_for(nseq, [&](int64_t b) {
+        auto &U = uniq[b];
+        const int n = (int)U.size(), N = D.len[b];
+        const std::vector<int> &idx = order[b];
         // forced pairs, seq.py:1226-1228
         std::vector<std::pair<int, int>> forced;
         if (in->hardrest && in->rbp_offsets) {
@@ -1498,23 +1609,22 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                 if (HP.p.pairmask[cv] >> cw & 1) forced.emplace_back(v, w);
             }
         }
-        C.n_total[b] = n;
-        int keepn = (in->max_structs > 0 && in->max_structs < n) ? in->max_structs : n;
-        for (int r = 0; r < keepn; r++) {
+        int64_t so = stems_of[b];
+        for (int r = 0; r < keepn[b]; r++) {
             Struct &S = U[idx[r]];
-            for (int t = 0; t < 3; t++) C.scores.push_back(S.score[t]);
-            C.isint0.push_back(S.isint0); C.psmask.push_back(S.psmask);
-            for (auto &s : S.stems) { C.stems.push_back(s.i); C.stems.push_back(s.j); C.stems.push_back(s.len); }
-            C.stem_offsets.push_back((int64_t)C.stems.size() / 3);
-            C.dbn_offsets.push_back((int64_t)C.dbn.size());
-            if (forced.empty()) C.dbn.insert(C.dbn.end(), S.dbn.begin(), S.dbn.end());
+            const size_t k = (size_t)(C.struct_offsets[b] + r);
+            for (int t = 0; t < 3; t++) C.scores[3 * k + t] = S.score[t];
+            C.isint0[k] = S.isint0; C.psmask[k] = S.psmask;
+            C.stem_offsets[k] = so;
+            for (auto &st : S.stems) { C.stems[3 * (size_t)so] = st.i; C.stems[3 * (size_t)so + 1] = st.j; C.stems[3 * (size_t)so + 2] = st.len; so++; }
+            const int64_t o = dbn_of[b] + (int64_t)r * N;
+            C.dbn_offsets[k] = o;
+            if (forced.empty()) { if (N) memcpy(C.dbn.data() + o, S.dbn.data(), (size_t)N); }
             else {
                 std::vector<std::pair<int, int>> pp = S.bps; pp.insert(pp.end(), forced.begin(), forced.end());
-                size_t o = C.dbn.size(); C.dbn.resize(o + N);
                 pairs_to_codes(pp, N, C.dbn.data() + o);
             }
         }
-        C.struct_offsets[b + 1] = C.struct_offsets[b] + keepn;
         // consensus of the top conslim structures, seq.py:845-858, 1236
         {
             int top = std::min(std::max(in->conslim, 0), n);
@@ -1531,8 +1641,15 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
             if (top == 1 && forced.empty()) { if (N) memcpy(dst, U[idx[0]].dbn.data(), (size_t)N); }
             else { cb.insert(cb.end(), forced.begin(), forced.end()); pairs_to_codes(cb, N, dst); }
         }
-    }
+    });
     C.valid = true;
+    if (trace) {
+        double t_rank = 0; lap(t_rank);
+        fprintf(stderr, "[sqrn] predict_batch: %lld sequences x %d parameter sets, %d rounds, %lld launches, kernels %.1f ms; host ms: upload %.1f, "
+                "base lists %.1f, gather %.1f, step rounds %.1f, scatter %.1f, tails %.1f, dedupe %.1f, final %.1f, rank + output %.1f\n",
+                (long long)nseq, n_ps, n_rounds, (long long)ctx->n_launches, ctx->kernel_ms, t_upload, t_base, t_gather, t_step, t_scatter,
+                t_tail, t_dedupe, t_final, t_rank);
+    }
     return copy_result(ctx, out);
 }
 

@@ -82,6 +82,7 @@ constexpr int MODE_TAIL = 0;   // run the single-path greedy to completion
 constexpr int MODE_STEP = 1;   // one OptimalStems call, return the ChooseStems list
 constexpr int MODE_YIELD = 2;  // AnnotateStems only, stems in reference order
 constexpr int MODE_FINAL = 3;  // ScoreStruct + dbn of the given stems, no selection
+constexpr int MODE_BASE = 4;   // build the base list of the sequence (DevWork::base_*)
 
 constexpr int REGION_AUTO = 0, REGION_SCAN = 1, REGION_STEMS = 2;   // ScoreStems region evaluation
 
@@ -123,6 +124,8 @@ struct DevBatch {
     const double  *bpp; const int64_t *bpp_off; int bpp_mode;      // per-sequence N x N term, 1 additive / 2 multiplicative
 };
 
+struct BEnt;
+
 struct DevWork {
     int            n_items;
     int            mode;
@@ -144,6 +147,12 @@ struct DevWork {
     int           *g_cnt;        // cluster flavour: GL_CNT_INTS ints per slot -- [0] records in the list, [1] chunk counter of the sweeps, [16..] histograms
     unsigned long long *g_stat;      // optional counters: [0] entries swept, [1] ScoreStems evaluations, [2] cache resets,
                                      // [3] steps, [4] steps with a level change, [5] cuts
+    // base lists (pool rounds): records of sequence b at base_ent + base_off[b], capacity base_off[b + 1] - base_off[b];
+    // base_n[b] = records (-1: none / overflow), base_bend + 257 b = its bin ends
+    BEnt          *base_ent;
+    const int64_t *base_off;
+    int32_t       *base_n;
+    int32_t       *base_bend;
     int           *ovf_count;    // Cfg::PERSIST kernels: items whose run list overflowed are appended here and
     int32_t       *ovf_list;     //   left to a rescanning kernel launched behind them (order = ovf_list)
     // outputs
@@ -252,7 +261,7 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_evjump = tw != 1 ? o : -1;                    // CTA teams (and the host emulation, tw = 0): where the arm walk of
     o += tw != 1 ? 4 * L.Scap : 0;                    // ScoreStems may jump to (team_apply_stem)
     o = align_up(o, 4);
-    L.o_glx = o;     o += pcap < 0 ? 4 * (3 * 256 + 4) : 0;   // global list: histogram, bin ends, scatter cursors (gl_make_bins)
+    L.o_glx = o;     o += (pcap < 0 || tw != 1) ? 4 * (3 * 256 + 4) : 0;   // binned lists: histogram, bin ends, scatter cursors (gl_make_bins)
     L.total = align_up(o, 16);
     return L;
 }
@@ -652,8 +661,9 @@ __device__ void team_load(State &S, const DevBatch &B, const DevParams &P, int s
 // add a selected stem to the structure: partners, owner, row/column masks
 // (AnnotateStems zeroes the rows and columns of every selected position, seq.py:446-451),
 // the unpaired mask and the 5'-sorted copy of the stem list
+// light: the structure is only going to be scored and printed (MODE_FINAL): no arm events, nothing ScoreStems walks
 template <class C>
-__device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = true)
+__device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = true, bool light = false)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
@@ -670,6 +680,11 @@ __device__ void team_apply_stem(State &S, int i, int j, int len, bool refresh = 
         int rv = 32 + S.N - 1 - v, rw = 32 + S.N - 1 - w;
         atomicAnd(&S.colokR[rv >> 5], ~(1u << (rv & 31)));
         atomicAnd(&S.colokR[rw >> 5], ~(1u << (rw & 31)));
+    }
+    if (light) {
+        if (r == 0) { S.sti[idx] = (int16_t)i; S.stj[idx] = (int16_t)j; S.stl[idx] = (int16_t)len; }
+        S.nst = idx + 1;
+        return;                                  // (the caller synchronises once after the last stem)
     }
     // two arm events (first position of the 5' arm and of the 3' arm) go into the position-sorted
     // event list that ScoreStems walks: entries behind them move up by one or two
@@ -1375,6 +1390,38 @@ __device__ __forceinline__ double score_bound(const DevParams &P, double bps)
     return __dmul_rn(u, 1.25);
 }
 
+// ---- shared by the binned run lists (the persistent list of k_long and the per-sequence base list of the pool rounds)
+constexpr int GL_NBIN = 256;
+// monotone map of a score (bound or floor) to a bin: linear between minfinscore and five times that, clamped
+__device__ __forceinline__ int gl_bin(const DevParams &P, double u)
+{
+    const double lo = P.minfinscore > 0.0 ? P.minfinscore : 1.0;
+    if (!(u > lo)) return 0;
+    const double x = (u - lo) * ((GL_NBIN - 2) / (4.0 * lo));
+    return x >= (double)(GL_NBIN - 2) ? GL_NBIN - 1 : (int)x;
+}
+
+// 32 bits of the unpaired mask starting at position p0 (positions outside the sequence read as 0)
+__device__ __forceinline__ uint32_t unpaired_bits32(const State &S, int p0)
+{
+    const int w = p0 >> 5, sh = p0 & 31;
+    const uint32_t lo = (w >= 0 && w < S.W) ? S.Ub[w] : 0u, hi = (w + 1 >= 0 && w + 1 < S.W) ? S.Ub[w + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ bool unpaired_at(const State &S, int p) { return (S.Ub[p >> 5] >> (p & 31)) & 1u; }
+
+
+// Base list of a sequence: its maximal runs under the EMPTY structure (bp score cached), binned by the static bound
+// gl_ub0 like the persistent list of k_long, built once per (sequence, parameter set) by MODE_BASE and then shared,
+// read-only, by every work item of that sequence -- the partial structures of its pool (MODE_STEP) and their tails.
+// An item does not enumerate anti-diagonals: it sweeps the prefix of the list whose bounds reach its score window and
+// cuts each run on the fly by its own unpaired mask (team_scan).
+struct alignas(16) BEnt { uint32_t key, meta; double bps; };      // key = (i + j) << 16 | i, meta = len | candidate << 31
+struct BaseView { const BEnt *ent; int n; };                       // the bin ends are in State::gbend
+#ifdef SQRN_HOST_EMU
+static long g_emu_base_sweeps = 0;        // tests assert that the base-list path really ran
+#endif
+
 // Phase 2b for one survivor: ScoreStems' adjusted score; folds it into the lane's running best.
 // Candidates that cannot reach `floor` (the best score so far, or the lower end of the subopt
 // range) are skipped without evaluating their region.  Returns the adjusted score (-1e300 if it
@@ -1428,7 +1475,8 @@ __device__ __forceinline__ double consider(const State &S, const DevParams &P, u
 //     (misc[7] > Ccap: the in-range candidates alone overflow the list and the
 //     caller retries with a larger one).
 template <class C>
-__device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L, const double subopt)
+__device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const Layout &L, const double subopt,
+                          const BaseView *base = nullptr)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
@@ -1521,7 +1569,100 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
         nsurv += cnt;
     };
 
-    if (!C::RUNLIST) {
+    if (TW != 1 && base) {
+        // The sequence has a base list: no enumeration.  Rounds over the prefix of the binned list whose static bounds
+        // reach the score window known so far (the best of a round is the floor of the next; at most four times the
+        // records of the rounds before).  A thread per record: runs untouched by the structure keep their cached bp
+        // score, the others are cut by the unpaired mask into their live pieces, which are re-summed.  Candidates go
+        // through the same survivor list / flush as the enumerating paths.
+        const int nb = base->n;
+        int done = 0;
+#ifdef SQRN_HOST_EMU
+        g_emu_base_sweeps++;
+#endif
+        #pragma unroll 1
+        for (;;) {
+            int target = nb;
+            {
+                const double f = !keep ? best.fin : (best.fin > 0.0 ? __dmul_rn(subopt < 1.0 ? subopt : 1.0, best.fin) : -1e300);
+                if (f > -1e300) target = S.gbend[gl_bin(P, f)];
+                const int want = done > 0 ? 4 * done : 4 * T;
+                if (target > want) {
+                    int q = 0, qh = GL_NBIN - 1;               // the highest bin q with gbend[q] >= want (gbend falls with q)
+                    #pragma unroll 1
+                    while (q < qh) { const int mid = (q + qh + 1) >> 1; if (S.gbend[mid] >= want) q = mid; else qh = mid - 1; }
+                    if (S.gbend[q] < target) target = S.gbend[q];
+                }
+                if (target > nb) target = nb;
+            }
+            if (target <= done) break;
+            #pragma unroll 1
+            for (int c0 = done; c0 < target; c0 += T) {
+                const int c = c0 + r;
+                bool pending = c < target, whole = false;
+                uint32_t ekey = 0, live = 0; int len = 0, a = 0, s = 0, t = 0, q = 0; double ebps = 0.0; bool cand = false;
+                if (pending) {
+#ifdef SQRN_HOST_EMU
+                    const BEnt e = base->ent[c];
+                    ekey = e.key; len = (int)(e.meta & 0xffffu); cand = (e.meta >> 31) != 0; ebps = e.bps;
+#else
+                    const uint4 w = *reinterpret_cast<const uint4 *>(&base->ent[c]);
+                    ekey = w.x; len = (int)(w.y & 0xffffu); cand = (w.y >> 31) != 0; ebps = __hiloint2double((int)w.w, (int)w.z);
+#endif
+                    a = (int)(ekey & 0xffffu); s = (int)(ekey >> 16); t = s - a;
+                    if (len <= 32) {
+                        const uint32_t full = 0xffffffffu >> (32 - len);
+                        live = unpaired_bits32(S, a) & __brev(unpaired_bits32(S, t - 31)) & full;
+                        whole = live == full;
+                    } else {
+                        whole = true;
+                        #pragma unroll 1
+                        for (int k = 0; k < len && whole; k++) whole = unpaired_at(S, a + k) && unpaired_at(S, t - k);
+                    }
+                }
+                #pragma unroll 1
+                for (;;) {
+                    bool push = false; uint32_t key = 0; int plen = 0; double sc = 0.0;
+                    if (pending) {
+                        if (whole) { push = cand; key = ekey; plen = len; sc = ebps; pending = false; }
+                        else {
+                            int p0 = 0, pl = 0;
+                            if (len <= 32) {
+                                if (live) {
+                                    p0 = __ffs(live) - 1;
+                                    const uint32_t inv = ~(live >> p0);
+                                    pl = inv ? __ffs(inv) - 1 : 32;
+                                    live = (p0 + pl >= 32) ? 0u : (live >> (p0 + pl)) << (p0 + pl);
+                                }
+                            } else {
+                                #pragma unroll 1
+                                while (q < len && !(unpaired_at(S, a + q) && unpaired_at(S, t - q))) q++;
+                                p0 = q;
+                                #pragma unroll 1
+                                while (q < len && unpaired_at(S, a + q) && unpaired_at(S, t - q)) q++;
+                                pl = q - p0;
+                            }
+                            if (pl == 0) pending = false;
+                            else if ((double)pl >= P.minlen) {
+                                sc = run_score<C>(S, P, B, s, a + p0, pl);            // re-summed from the piece's own outermost cell (seq.py:416)
+                                push = sc >= P.minbpscore;
+                                key = ((uint32_t)s << 16) | (uint32_t)(a + p0); plen = pl;
+                            }
+                        }
+                    }
+                    if (nsurv + T > Ccap && !overflow) flush_survivors();
+                    add_survivors(push, key, plen, sc);
+#ifdef SQRN_HOST_EMU
+                    S.misc[7] = nsurv;                 // (the one-thread team's claim() does not use the shared counter)
+#endif
+                    if (!Team<TW>::any(pending)) break;
+                }
+            }
+            if (!overflow) flush_survivors();
+            done = target;
+            if (done >= nb) break;
+        }
+    } else if (!C::RUNLIST) {
         // CTA teams (long sequences: hundreds of runs per diagonal): a WARP walks one anti-diagonal,
         // 32 words (1024 cells) per step, one word per lane, so the lanes do the same work at the same
         // time: build the word, find the run starts in it, score those runs, append the ones that pass
@@ -1940,7 +2081,6 @@ __device__ __forceinline__ long long gl_clock() { return clock64(); }
 constexpr uint32_t GK_DEAD = 0xffffffffu;
 constexpr uint32_t GS_FRESH = 0u, GS_EVAL = 1u, GS_PRUNED = 2u, GS_BELOW = 3u, GS_PRUNED1 = 4u;
 constexpr uint32_t GS_MASK = 7u, GS_LEVELS = 8u;      // GS_LEVELS (with EVAL): the score involves pseudoknot levels
-constexpr int GL_NBIN = 256;
 constexpr int GL_REBUILD = 32;    // default rebuild period (DevWork::g_rebuild overrides)
 
 // one record = one 16-byte load: key = (i + j) << 16 | i, meta = len | state << 16 | stamp << 20, v = the cached score / bound
@@ -2029,24 +2169,6 @@ __device__ __forceinline__ double gl_ub0(const State &S, const DevParams &P, int
     u = __dmul_rn(u, P.lf_max);
     return __dmul_rn(u, tf);
 }
-
-// monotone map of a score (bound or floor) to a bin: linear between minfinscore and five times that, clamped
-__device__ __forceinline__ int gl_bin(const DevParams &P, double u)
-{
-    const double lo = P.minfinscore > 0.0 ? P.minfinscore : 1.0;
-    if (!(u > lo)) return 0;
-    const double x = (u - lo) * ((GL_NBIN - 2) / (4.0 * lo));
-    return x >= (double)(GL_NBIN - 2) ? GL_NBIN - 1 : (int)x;
-}
-
-// 32 bits of the unpaired mask starting at position p0 (positions outside the sequence read as 0)
-__device__ __forceinline__ uint32_t unpaired_bits32(const State &S, int p0)
-{
-    const int w = p0 >> 5, sh = p0 & 31;
-    const uint32_t lo = (w >= 0 && w < S.W) ? S.Ub[w] : 0u, hi = (w + 1 >= 0 && w + 1 < S.W) ? S.Ub[w + 1] : 0u;
-    return __funnelshift_r(lo, hi, sh);
-}
-__device__ __forceinline__ bool unpaired_at(const State &S, int p) { return (S.Ub[p >> 5] >> (p & 31)) & 1u; }
 
 __device__ __forceinline__ bool gl_wanted(int N, const DevParams &P, long long cap)
 {
@@ -2202,6 +2324,39 @@ __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const 
     });
     gl_sync<C>();
     return true;
+}
+
+// The base list of a sequence (BEnt, above): the same two enumeration passes, records and bin ends written to the
+// sequence's slot in global memory.  *n_out = records, or -1 when the slot is too small (its items then enumerate).
+template <class C>
+__device__ void base_build(State &S, const DevParams &P, const DevBatch &B, BEnt *ent, long long cap, int32_t *bend_out, int32_t *n_out)
+{
+    constexpr int TW = C::TW;
+    const int r = Team<TW>::rank(), T = Team<TW>::T;
+    #pragma unroll 1
+    for (int q = r; q < GL_NBIN; q += T) S.ghist[q] = 0;
+    Team<TW>::sync();
+    gl_enum<C>(S, P, B, [&](int s, int a, int len) {
+        double pos;
+        run_score_pos<C>(S, P, B, s, a, len, pos);
+        if (!(pos >= P.minbpscore)) return;
+        atomicAdd(&S.ghist[gl_bin(P, gl_ub0(S, P, s, a, len, pos))], 1);
+    });
+    GList none{};
+    const int n = gl_make_bins<C>(S, none);
+    if ((long long)n > cap || !P.ub_ok || !(P.loopbonus >= 0.0)) { if (r == 0) *n_out = -1; Team<TW>::sync(); return; }
+    gl_enum<C>(S, P, B, [&](int s, int a, int len) {
+        double pos;
+        const double sc = run_score_pos<C>(S, P, B, s, a, len, pos);
+        if (!(pos >= P.minbpscore)) return;
+        const int slot = atomicAdd(&S.gcur[gl_bin(P, gl_ub0(S, P, s, a, len, pos))], 1);
+        BEnt e; e.key = ((uint32_t)s << 16) | (uint32_t)a; e.meta = (uint32_t)len | (sc >= P.minbpscore ? 0x80000000u : 0u); e.bps = sc;
+        ent[slot] = e;
+    });
+    #pragma unroll 1
+    for (int q = r; q <= GL_NBIN; q += T) bend_out[q] = S.gbend[q];
+    if (r == 0) *n_out = n;
+    Team<TW>::sync();
 }
 
 // One OptimalStems pass over the global list.  (ui, uj, ul): the stem T applied since the last pass (ul = 0:
@@ -2930,11 +3085,31 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
     if (Wk.init_off) {
         const int64_t k0 = Wk.init_off[item], k1 = Wk.init_off[item + 1];
         #pragma unroll 1
+        const bool light = (C::MODE >= 0 ? C::MODE : Wk.mode) == MODE_FINAL;
         for (int64_t k = k0; k < k1; k++)
-            team_apply_stem<C>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2], false);
+            team_apply_stem<C>(S, Wk.init_stems[3 * k], Wk.init_stems[3 * k + 1], Wk.init_stems[3 * k + 2], false, light);
+        if (light) Team<TW>::sync();
         if (k1 > k0) team_unpaired_prefix<C>(S);
     }
     unsigned long long calls = 0;
+    // the sequence's base list, when the launch has one (pool rounds and their tails, CTA teams)
+    BaseView bview{}; const BaseView *basep = nullptr;
+    if (TW != 1 && Wk.base_n) {
+        if (mode == MODE_BASE) {
+            base_build<C>(S, P, B, Wk.base_ent + Wk.base_off[seq], Wk.base_off[seq + 1] - Wk.base_off[seq],
+                          Wk.base_bend + (GL_NBIN + 1) * (int64_t)seq, Wk.base_n + seq);
+            return;
+        }
+        const int nb = Wk.base_n[seq];
+        if (nb >= 0 && (mode == MODE_STEP || mode == MODE_TAIL) && !C::PERSIST) {
+            const int r_ = Team<TW>::rank();
+            #pragma unroll 1
+            for (int q = r_; q <= GL_NBIN; q += Team<TW>::T) S.gbend[q] = Wk.base_bend[(GL_NBIN + 1) * (int64_t)seq + q];
+            Team<TW>::sync();
+            bview.ent = Wk.base_ent + Wk.base_off[seq]; bview.n = nb; basep = &bview;
+        }
+    }
+    if (mode == MODE_BASE) return;
     if (mode == MODE_TAIL || mode == MODE_FINAL) {
         // the pool loop of seq.py:1159-1199 once it can no longer branch
         // (cursize >= poollim => stopper = 1): take the top stem until none is left
@@ -2985,7 +3160,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
             } else if (C::PERSIST) {
                 b = persist_step<C>(S, P, B, L, ui, uj, ul, ok);
                 if (!ok) break;
-            } else b = team_scan<C>(S, P, B, L, -1.0);
+            } else b = team_scan<C>(S, P, B, L, -1.0, basep);
             if (!C::GLIST) b = cluster_best<C>(S, b, (int)calls);
             calls++;
             if (b.fin <= -1e300) break;
@@ -3008,7 +3183,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
         int64_t so = Wk.out_off[item], cap = Wk.out_off[item + 1] - so;
         if ((double)S.nst != P.maxstemnum) {
             team_levels<C>(S);
-            Best b = team_scan<C>(S, P, B, L, Wk.item_subopt[item]);
+            Best b = team_scan<C>(S, P, B, L, Wk.item_subopt[item], basep);
             calls++;
             n = team_choose<C>(S, L, b, Wk.item_subopt[item], Wk.out_stems + 3 * so,
                                 Wk.out_stemfin ? Wk.out_stemfin + so : nullptr, (int)cap);

@@ -37,6 +37,7 @@ def lib():
         _lib.emu_pyround3.restype = C.c_double
         _lib.emu_persist_steps.restype = C.c_long
         _lib.emu_gl_rebuilds.restype = C.c_long
+        _lib.emu_base_sweeps.restype = C.c_long
         _lib.emu_gl_catchups.restype = C.c_long
         _lib.emu_gl_set_rebuild.argtypes = [C.c_int]
         _lib.emu_pyround3.argtypes = [C.c_double]

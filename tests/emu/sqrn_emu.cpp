@@ -54,6 +54,20 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
         W.g_rebuild = sqrn::g_emu_gl_rebuild_every;
     }
     unsigned char *smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16);
+    // flavour 6: the pool-round path of CTA teams -- a base list per sequence (MODE_BASE), then the items sweep it
+    std::vector<BEnt> be; std::vector<int64_t> boff; std::vector<int32_t> bn, bb;
+    if (flavour == 6) {
+        boff.resize((size_t)n_seqs + 1);
+        for (int64_t b = 0; b <= n_seqs; b++) boff[(size_t)b] = b * (int64_t)pcap;
+        be.resize((size_t)n_seqs * pcap + 1); bn.assign((size_t)n_seqs, -1); bb.assign((size_t)n_seqs * (GL_NBIN + 1), 0);
+        W.base_ent = be.data(); W.base_off = boff.data(); W.base_n = bn.data(); W.base_bend = bb.data();
+        DevWork Wb = W; Wb.mode = MODE_BASE; Wb.item_seq = nullptr; Wb.init_off = nullptr; Wb.n_items = (int)n_seqs;
+        for (int64_t b = 0; b < n_seqs; b++) {
+            State S = bind_state(smem, Lay);
+            team_run_item<Cfg<0>>(S, H.p, B, Wb, Lay, (int)b);
+        }
+        flavour = 0;
+    }
     // PERSIST flavours park the items whose run list overflowed; they are redone by the rescanning flavour
     std::vector<int32_t> ovf((size_t)n_items + 1); int n_ovf = 0;
     W.ovf_list = ovf.data(); W.ovf_count = &n_ovf;
@@ -81,6 +95,7 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
 }
 
 extern "C" long emu_persist_steps(void) { return sqrn::g_emu_persist_steps; }
+extern "C" long emu_base_sweeps(void) { return sqrn::g_emu_base_sweeps; }
 extern "C" long emu_gl_rebuilds(void) { return sqrn::g_emu_gl_rebuilds; }
 extern "C" long emu_gl_catchups(void) { return sqrn::g_emu_gl_catchups; }
 extern "C" void emu_gl_set_rebuild(int every) { sqrn::g_emu_gl_rebuild_every = every; }

@@ -37,9 +37,10 @@ def _prep_batch(cases):
     return preps, kw
 
 
-@pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist", "persist", "persist-small", "persist-general", "glist", "glist-small"],
+@pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist", "persist", "persist-small", "persist-general", "glist", "glist-small",
+                                    "base", "base-small"],
                          ids=["auto", "scan", "stems", "fastflavour", "runlist", "persist", "persist-smalllist", "persist-general",
-                              "glist", "glist-smalllist"])
+                              "glist", "glist-smalllist", "base-list", "base-list-overflow"])
 @pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
                          ids=["fastest", "defG1", "defG2-smalllist", "ali"])
 def test_tail_plain(ps, ccap, region):
@@ -62,6 +63,10 @@ def test_tail_plain(ps, ccap, region):
         r = emu.run(ps, seqs, ccap=ccap, flavour=5, pcap=1 << 16)
     elif region == "glist-small":
         r = emu.run(ps, seqs, ccap=ccap, flavour=5, pcap=600)
+    elif region == "base":     # what the tails of pools run: every step sweeps the sequence's base list
+        r = emu.run(ps, seqs, ccap=ccap, flavour=6, pcap=1 << 16)
+    elif region == "base-small":      # slots too small for the longer sequences: those enumerate as before
+        r = emu.run(ps, seqs, ccap=ccap, flavour=6, pcap=300)
     else:
         r = emu.run(ps, seqs, ccap=ccap, region_mode=region)
     for b, s in enumerate(seqs):
@@ -74,7 +79,7 @@ def test_tail_plain(ps, ccap, region):
         assert bool(r["flags"][b] & 1) == isint
 
 
-@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2), (0, 4), (0, 5)], ids=["scan", "stems", "runlist", "persist", "glist"])
+@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2), (0, 4), (0, 5), (0, 6)], ids=["scan", "stems", "runlist", "persist", "glist", "base-list"])
 @pytest.mark.parametrize("interchain", [False, True])
 def test_tail_with_restraints_and_reactivities(interchain, region, flavour):
     rng = random.Random(32)
@@ -155,7 +160,7 @@ def test_per_stem_levels_equal_per_pair_levels():
             assert codes[v] == lev and codes[w] == -lev, (stems, v, w)
 
 
-@pytest.mark.parametrize("region", [1, 2], ids=["scan", "stems"])
+@pytest.mark.parametrize("region", [1, 2, "base", "base-smalllist"], ids=["scan", "stems", "base-list", "base-list-smalllist"])
 def test_step_on_random_pseudoknotted_structures(region):
     """ScoreStems on top of arbitrary (pseudoknotted, multi-level) partial structures: the stem walk
     and the position scan must both reproduce the oracle's ChooseStems list and scores"""
@@ -177,8 +182,19 @@ def test_step_on_random_pseudoknotted_structures(region):
                 used |= pos
                 stems.append((i, j, ln))
             _, chosen = O.optimal(seq, ps, subopt, selected=stems)
-            r = emu.run(ps, [seq], mode=emu.MODE_STEP, init_stems=[stems], item_subopt=[subopt], ccap=4096,
-                        stem_cap=512, region_mode=region)
+            if isinstance(region, str):
+                # the pool-round path of CTA teams: the candidates come from the sequence's base list (runs of the empty
+                # structure, cut on the fly by this structure's unpaired mask) instead of an enumeration
+                before = emu.lib().emu_base_sweeps()
+                r = emu.run(ps, [seq], mode=emu.MODE_STEP, init_stems=[stems], item_subopt=[subopt],
+                            ccap=4096 if region == "base" else 48, stem_cap=512, flavour=6, pcap=1 << 15)
+                assert emu.lib().emu_base_sweeps() > before
+                if r["n"][0] < 0:                     # (the in-range candidates alone overflow the small list: the host retries)
+                    assert region == "base-smalllist"
+                    continue
+            else:
+                r = emu.run(ps, [seq], mode=emu.MODE_STEP, init_stems=[stems], item_subopt=[subopt], ccap=4096,
+                            stem_cap=512, region_mode=region)
             k = r["n"][0]
             got = [(int(r["stems"][q][0]), int(r["stems"][q][1]), int(r["stems"][q][2]), float(r["fin"][q])) for q in range(k)]
             assert got == chosen, (seq, stems)
