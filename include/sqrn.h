@@ -174,6 +174,18 @@ SQRN_API int  sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_p
 SQRN_API int  sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps,
                             const sqrn_batch *in, sqrn_stems *out);
 
+/* Alignment step 1 (SQRNdbnali.py:211-242, MatrixToDBNs 121-150) for a batch of ALIGNED sequences: the stems of every
+ * sequence (as sqrn_yield_stems_batch) summed into the smat_L x smat_L stem-score matrix, per cell in SEQUENCE ORDER
+ * (float64 addition order is observable), on the device; the stems never come back to the host.  in->cols maps every
+ * ungapped position to its alignment column, in->smat_L is the alignment length, in->smat must be NULL.
+ *   matrix     [smat_L * smat_L] row-major, symmetric (the reference adds every score to [v, w] and [w, v]);
+ *   threshold  minbpscore * depth: cells >= threshold with w - v >= 4 are what MatrixToDBNs walks;
+ *   cells      [cap_cells] their flat indices v * smat_L + w in MatrixToDBNs' order (value descending, index ascending);
+ *              *n_cells = how many, or -1 when there are more than cap_cells (or than 65536): the caller then sorts the
+ *              matrix itself.                                                                                          */
+SQRN_API int  sqrn_stem_matrix_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, double *matrix,
+                            double threshold, int64_t cap_cells, int64_t *n_cells, int32_t *cells);
+
 /* ---- single-path fast lane (poollim == 1: `byseq pl=1`, SQUARNA.py:887-935) --
  * One parameter set, default reactivities, no restraints: one structure per
  * sequence, written as ASCII dot-bracket.  `symbols`/`offsets`/outputs are HOST

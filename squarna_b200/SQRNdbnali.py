@@ -10,6 +10,7 @@ scores into the L x L matrix, MatrixToDBNs, Consensus and the text output.
 Lines cited as ali.py:N are /root/reference/src/SQUARNA/SQRNdbnali.py.
 """
 import io
+import os
 import sys
 
 import numpy as np
@@ -25,51 +26,74 @@ def ReAlignDict(shortseq, longseq):
     return {k: cols[k] for k in range(len(shortseq))}
 
 
-def _yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=None):
+def _yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=None, matrix=None):
     """entries: [(seq, reacts or None, restraints or None)] (aligned).  One GPU call per GPU: with several visible
     devices (device=None) the rows are dealt to one host thread per GPU (the reference's Pool.imap over sequences,
     ali.py:222-233) and come back in input order.
     Returns per entry (cols int32[n_ungapped], stems int32[k,3] ungapped, scores float64[k])."""
     if device is None:
         devs = _seq._resolve_devices(None)
-        if len(devs) > 1 and len(entries) >= 8 * len(devs):
+        if len(devs) > 1 and len(entries) >= 8 * len(devs) and matrix is None:
             return _seq.run_sharded(lambda sub, dev: _yield_many(sub, bpweights, interchainonly, minlen, minbpscore, dev),
                                     entries, [len(e[0]) for e in entries], devs, exponent=2.0)
         device = devs[0]
     preps = []
+    gap_bytes = np.frombuffer("".join(sorted(GAPS)).encode("latin-1"), dtype=np.uint8)
     for seq, reacts, rests in entries:
         seq = seq.upper().replace("T", "U")                           # ali.py:65
         if not rests:
             rests = '.' * len(seq)
         assert len(seq) == len(rests)
-        shortseq, shortrest = UnAlign(seq, rests)
-        keep = [k for k, ch in enumerate(seq) if ch not in GAPS]
-        shortreacts = [reacts[k] for k in keep] if reacts else None    # ali.py:77-82
-        rbps, rxs, rlefts, rrights = _seq.ParseRestraints(shortrest)
-        rc = np.zeros(max(len(shortseq), 1), dtype=np.uint8)
-        for k in rxs:
-            rc[k] |= 1
-        for k in rlefts:
-            rc[k] |= 2
-        for k in rrights:
-            rc[k] |= 4
-        preps.append((shortseq, shortreacts, rbps, rc[:len(shortseq)], np.array(keep, dtype=np.int32)))
-    any_react = any(p[1] is not None and any(x != 0.5 for x in p[1]) for p in preps)
+        raw = np.frombuffer(seq.encode("latin-1", "replace"), dtype=np.uint8)
+        if len(raw) != len(seq):                                       # (cannot happen: latin-1 is one byte per symbol)
+            raise ValueError("sequence encoding")
+        keep = np.flatnonzero(~np.isin(raw, gap_bytes)).astype(np.int32)
+        if rests.count('.') == len(rests):
+            # no restraints (the usual row of an alignment): nothing to parse, UnAlign is the column selection
+            shortseq, rbps = raw[keep].tobytes(), []
+            rc = np.zeros(len(keep), dtype=np.uint8)
+        else:
+            shortseq, shortrest = UnAlign(seq, rests)
+            rbps, rxs, rlefts, rrights = _seq.ParseRestraints(shortrest)
+            rc = np.zeros(max(len(shortseq), 1), dtype=np.uint8)
+            for k in rxs:
+                rc[k] |= 1
+            for k in rlefts:
+                rc[k] |= 2
+            for k in rrights:
+                rc[k] |= 4
+            rc = rc[:len(shortseq)]
+            shortseq = _seq._encode_symbols(shortseq)
+        shortreacts = np.asarray(reacts, dtype=np.float64)[keep] if reacts else None    # ali.py:77-82
+        preps.append((shortseq, shortreacts, rbps, rc, keep))
+    any_react = any(p[1] is not None and bool((p[1] != 0.5).any()) for p in preps)
     codes = values = None
     if any_react:
-        table, codes = {}, []
+        # distinct reactivity values of the batch -> value table + one code per position
+        flat = np.concatenate([p[1] if p[1] is not None else np.full(len(p[0]), 0.5) for p in preps])
+        values, inv = np.unique(flat, return_inverse=True)
+        if len(values) > 65535:
+            raise ValueError("more than 65535 distinct reactivity values in one alignment")
+        inv = inv.astype(np.uint16)
+        codes, at = [], 0
         for p in preps:
-            src = p[1] if p[1] is not None else [0.5] * len(p[0])
-            codes.append(np.array([table.setdefault(float(x), len(table)) for x in src], dtype=np.uint16))
-        values = np.array(list(table.keys()), dtype=np.float64)
+            codes.append(inv[at:at + len(p[0])])
+            at += len(p[0])
+        values = np.ascontiguousarray(values, dtype=np.float64)
     any_restr = any(p[2] or p[3].any() for p in preps)
-    batch = PackedBatch([_seq._encode_symbols(p[0]) for p in preps], react_codes=codes, react_values=values,
+    batch = PackedBatch([p[0] for p in preps], react_codes=codes, react_values=values,
                         restr_class=[p[3] for p in preps] if any_restr else None,
                         rbps=[np.array(p[2], dtype=np.int32).reshape(-1, 2) for p in preps] if any_restr else None,
-                        interchainonly=interchainonly)
+                        interchainonly=interchainonly,
+                        cols=[p[4] for p in preps] if matrix is not None else None,
+                        ali_len=matrix[0] if matrix is not None else 0)
     ps = dict(algorithms={"G"}, bpp=0.0, bpweights=bpweights, suboptmax=1.0, suboptmin=1.0, suboptsteps=1.0,
               minlen=minlen, minbpscore=minbpscore, minfinscorefactor=1.0, distcoef=0.0, bracketweight=-2.0,
               orderpenalty=0.0, loopbonus=0.0, maxstemnum=1e6)
+    if matrix is not None:
+        # the whole of step 1 on the device: stems, the sequence-ordered sum into the L x L matrix, the cells MatrixToDBNs
+        # walks (sqrn_stem_matrix_batch); matrix = (alignment length, score threshold)
+        return _seq.get_context(device).stem_matrix(ps, batch, matrix[1])
     out = _seq.get_context(device).yield_stems(ps, batch)
     return [(p[4], st, sc) for p, (st, sc) in zip(preps, out)]
 
@@ -87,14 +111,18 @@ def YieldStems(seq, reactivities=None, restraints=None,
     return out
 
 
-def MatrixToDBNs(mat, score, depth, verbose=False, sink=sys.stdout):
+def MatrixToDBNs(mat, score, depth, verbose=False, sink=sys.stdout, cells=None):
     """greedy assembly of structures from the stem-score matrix (ali.py:121-192):
     cells in stable descending order, stop below score*depth, accept w - v >= 4,
-    first-fit into position-disjoint structures."""
+    first-fit into position-disjoint structures.  cells: the flat indices of the cells that pass both tests, already
+    in that order (what sqrn_stem_matrix_batch returns); None: sorted here."""
     N = mat.shape[0]
     thr = score * depth
     flat = mat.ravel()
-    order = np.argsort(-flat, kind="stable")          # ties keep ascending flat index, like sorted(reverse=True)
+    if cells is None:
+        order = np.argsort(-flat, kind="stable")      # ties keep ascending flat index, like sorted(reverse=True)
+    else:
+        order = np.asarray(cells)
     res = [[[], set()]]
     if verbose:
         print(">Conserved base pairs (one by one)", file=sink)
@@ -136,12 +164,25 @@ def SQRNdbnali(objs, defrests=None, defreacts=None, defref=None,
                sink=sys.stdout, M=1.8, B=-0.6):
     """step 1 of the alignment mode: (predicted dbn, stem matrix) (ali.py:211-242)"""
     L = len(objs[0][1])
+    entries = [(obj[1], obj[2], defrests if defrests else obj[3]) for obj in objs]
+    if len(_seq._resolve_devices(None)) == 1 and not os.environ.get("SQRN_HOST_STEMMATRIX"):
+        # one GPU: stems, sequence-ordered accumulation and the ranking of the conserved cells all stay on the device
+        stemmatrix, cells = _yield_many(entries, bpweights, interchainonly, minlen, minbpscore,
+                                        matrix=(L, minbpscore * len(objs)))
+        pred_dbns = MatrixToDBNs(stemmatrix, minbpscore, len(objs), verbose, sink=sink, cells=cells)
+        return pred_dbns[0], stemmatrix
+    # several GPUs: every GPU enumerates the stems of its share of the rows; the only exchange of the alignment mode --
+    # the sum into the matrix -- is done here on the host, in sequence order (float64 addition order is observable)
+    stemmatrix = _accumulate_host(_yield_many(entries, bpweights, interchainonly, minlen, minbpscore), L)
+    pred_dbns = MatrixToDBNs(stemmatrix, minbpscore, len(objs), verbose, sink=sink)
+    return pred_dbns[0], stemmatrix
+
+
+def _accumulate_host(per_seq, L):
+    """the stem-score matrix from per-sequence stems (cols, stems, scores): sequence order, stem order, outer->inner
+    pairs -- the reference's accumulation order (ali.py:233-237).  Within one sequence every cell is touched by at most
+    one stem, so a fancy-indexed add per sequence performs exactly the same float64 additions per cell."""
     stemmatrix = np.zeros((L, L))
-    per_seq = _yield_many([(obj[1], obj[2], defrests if defrests else obj[3]) for obj in objs],
-                          bpweights, interchainonly, minlen, minbpscore)
-    # sequence order, stem order, outer->inner pairs: the reference's accumulation order.
-    # Within one sequence every cell is touched by at most one stem, so a fancy-indexed
-    # add per sequence performs exactly the same float64 additions per cell.
     for cols, stems, scores in per_seq:
         if not len(stems):
             continue
@@ -153,8 +194,7 @@ def SQRNdbnali(objs, defrests=None, defreacts=None, defref=None,
         s = scores[rep]
         stemmatrix[v, w] += s
         stemmatrix[w, v] += s
-    pred_dbns = MatrixToDBNs(stemmatrix, minbpscore, len(objs), verbose, sink=sink)
-    return pred_dbns[0], stemmatrix
+    return stemmatrix
 
 
 def Consensus(structs, freqlimit=0.0, verbose=False, sink=sys.stdout):

@@ -77,6 +77,7 @@ def ParseDefaultInput(inputname, inputformat, returndefaults=False, ignore=False
     t_ind, r_ind, f_ind = (inputformat.find(ch) for ch in "trf")
     defaults = {"t": None, "r": None, "f": None}
     warned = set()
+    resolved = {}
 
     def pick(data, ind, first_token):
         if ind <= 0 or ind >= len(data) or not data[ind]:       # find() > 0: position 0 is ignored (cli.py:102-104)
@@ -114,7 +115,12 @@ def ParseDefaultInput(inputname, inputformat, returndefaults=False, ignore=False
             reference = default_for("f", "reference", n)
         try:
             if reactivities:
-                reactivities = _resolve_reacts(reactivities, n, M, B)
+                key = (reactivities, n)                 # the default line is shared by every entry: processed once
+                if key not in resolved:
+                    if len(resolved) > 64:
+                        resolved.clear()
+                    resolved[key] = _resolve_reacts(reactivities, n, M, B)
+                reactivities = list(resolved[key])
             assert not reactivities or len(reactivities) == n
         except Exception:
             raise ValueError('Inappropriate reactivities line for entry "{}":\n {}'.format(name[1:], reactivities))

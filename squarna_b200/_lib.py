@@ -21,7 +21,8 @@ EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx
            "sqrn_last_error", "sqrn_ctx_set_stream", "sqrn_predict_batch", "sqrn_yield_stems_batch",
            "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
            "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_ungap", "sqrn_text_format",
-           "sqrn_fast_predict_packed_host", "sqrn_pack_symbols", "sqrn_unpack_dbn", "sqrn_fast_last_flags"]
+           "sqrn_fast_predict_packed_host", "sqrn_pack_symbols", "sqrn_unpack_dbn", "sqrn_fast_last_flags",
+           "sqrn_stem_matrix_batch"]
 
 _lib = None
 
@@ -57,6 +58,7 @@ def load():
     L.sqrn_pack_symbols.argtypes = [i64, vp, vp, C.POINTER(i64)]
     L.sqrn_unpack_dbn.argtypes = [i64, vp, vp, vp]
     L.sqrn_fast_last_flags.argtypes = [vp, i64, vp]
+    L.sqrn_stem_matrix_batch.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), vp, C.c_double, i64, C.POINTER(i64), vp]
     L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
     L.sqrn_debug_run.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), C.c_int, C.c_int] + [vp] * 11 + [C.c_int]
     L.sqrn_text_parse.argtypes = [vp, i64, C.c_int, C.POINTER(i64), C.POINTER(i64), i64, i64, vp, vp, vp, vp]
@@ -161,7 +163,7 @@ class PackedBatch:
     def __init__(self, seqs, react_codes=None, react_values=None, react_comp=False, restr_class=None,
                  rbps=None, smat=None, cols=None, interchainonly=False, hardrest=False, rankbydiff=False,
                  poollim=1000, conslim=1, max_structs=0, rankby=(0, 2, 1), priority_mask=0,
-                 bpp_terms=None, bpp_mode=0):
+                 bpp_terms=None, bpp_mode=0, ali_len=0):
         self.seqs = seqs
         self.symbols, self.offsets = pack_sequences(seqs)
         n = len(seqs)
@@ -183,6 +185,7 @@ class PackedBatch:
             self.rbps = cat(rbps, np.int32)
         self.smat = None if smat is None else np.ascontiguousarray(smat, np.float64)
         self.cols = cat(cols, np.int32)
+        self.ali_len = int(ali_len)
         b = Batch()
         b.n_seqs = n
         b.offsets = ptr(self.offsets)
@@ -195,7 +198,7 @@ class PackedBatch:
         b.rbp_offsets = ptr(self.rbp_offsets)
         b.rbps = ptr(self.rbps)
         b.smat = ptr(self.smat)
-        b.smat_L = 0 if self.smat is None else self.smat.shape[0]
+        b.smat_L = self.ali_len if self.smat is None else self.smat.shape[0]      # (without smat: the alignment length, for stem_matrix)
         b.cols = ptr(self.cols)
         b.interchainonly = int(bool(interchainonly))
         b.hardrest = int(bool(hardrest))
@@ -391,6 +394,19 @@ class Context:
             self._check(rc)
             break
         return [(st[off[b]:off[b + 1]].copy(), sc[off[b]:off[b + 1]].copy()) for b in range(n)]
+
+    def stem_matrix(self, paramset, batch, threshold, cap_cells=65536):
+        """alignment step 1 on the device (include/sqrn.h): batch carries cols and smat_L = alignment length (no smat).
+        Returns (matrix (L, L) float64, flat indices of the cells MatrixToDBNs walks in its order, or None when there are
+        too many for the device ranking)."""
+        ps = paramset if isinstance(paramset, ParamSet) else ParamSet.from_dict(paramset)
+        L_ = int(batch.c.smat_L)
+        mat = np.empty((L_, L_), np.float64)
+        cells = np.empty(max(cap_cells, 1), np.int32)
+        m = C.c_int64(0)
+        self._check(self.L.sqrn_stem_matrix_batch(self.h, C.byref(ps), C.byref(batch.c), ptr(mat), float(threshold),
+                                                  int(cap_cells), C.byref(m), ptr(cells)))
+        return mat, (cells[:m.value].copy() if m.value >= 0 else None)
 
     def debug_run(self, paramset, batch, mode, item_seq=None, init_stems=None, item_subopt=None,
                   out_cap=None, min_ccap=0, want_dbn=True):

@@ -185,7 +185,7 @@ struct CachedStems {
 
 enum { B_OFF, B_OFF32, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RBOFF, B_RB, B_SMAT, B_COLS, B_BPP, B_BPPOFF,
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
-       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, W_RNDC, W_RNDL, W_BASE, W_BASEOFF, W_BASEN, W_BASEBEND, NBUF };
+       W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, W_RNDC, W_RNDL, W_BASE, W_BASEOFF, W_BASEN, W_BASEBEND, W_MAT, W_CELLCNT, W_CELLS, W_CELLS2, NBUF };
 
 struct sqrn_ctx {
     int device = 0;
@@ -1033,6 +1033,9 @@ struct HostWork {
     std::vector<int32_t> item_seq; std::vector<int64_t> init_off; std::vector<int32_t> init_stems;
     std::vector<double> subopt; std::vector<int64_t> out_cap;        // per item stem capacity
     bool want_dbn = false, want_fin = false;
+    bool keep_on_device = false;     // leave stems / scores in the context's device buffers (only the counts come back)
+    // device copies of the outputs after run_items (valid until the context's scratch is reused)
+    const int32_t *d_out_stems = nullptr; const double *d_out_fin = nullptr; const int32_t *d_out_n = nullptr; const int64_t *d_out_off = nullptr;
     // outputs
     std::vector<int64_t> out_off, dbn_off;
     std::vector<int32_t> out_stems, out_n; std::vector<double> out_fin, out_raw;
@@ -1047,8 +1050,8 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
     W.out_off.assign((size_t)n + 1, 0);
     for (int k = 0; k < n; k++) W.out_off[k + 1] = W.out_off[k] + W.out_cap[k];
     const int64_t tot_stems = W.out_off[n];
-    W.out_stems.assign((size_t)tot_stems * 3, 0);
-    if (W.want_fin || W.mode == MODE_YIELD) W.out_fin.assign((size_t)tot_stems, 0.0);
+    W.out_stems.assign(W.keep_on_device ? 0 : (size_t)tot_stems * 3, 0);
+    if (W.want_fin || W.mode == MODE_YIELD) W.out_fin.assign(W.keep_on_device ? 1 : (size_t)tot_stems, 0.0);
     const bool fin = (W.mode == MODE_TAIL || W.mode == MODE_FINAL);
     if (fin) { W.out_raw.assign((size_t)n * 3, 0.0); W.flags.assign((size_t)n, 0); }
     int64_t tot_dbn = 0;
@@ -1118,8 +1121,9 @@ static int run_items(sqrn_ctx *ctx, const sqrn_paramset &ps, const DeviceBatch &
         pos = end;
     }
     CK(cudaMemcpyAsync(W.out_n.data(), G.out_nstems, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (tot_stems) CK(cudaMemcpyAsync(W.out_stems.data(), G.out_stems, (size_t)tot_stems * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (!W.out_fin.empty() && tot_stems) CK(cudaMemcpyAsync(W.out_fin.data(), G.out_stemfin, (size_t)tot_stems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    W.d_out_stems = G.out_stems; W.d_out_fin = G.out_stemfin; W.d_out_n = G.out_nstems; W.d_out_off = G.out_off;
+    if (tot_stems && !W.keep_on_device) CK(cudaMemcpyAsync(W.out_stems.data(), G.out_stems, (size_t)tot_stems * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!W.out_fin.empty() && tot_stems && !W.keep_on_device) CK(cudaMemcpyAsync(W.out_fin.data(), G.out_stemfin, (size_t)tot_stems * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (fin) {
         CK(cudaMemcpyAsync(W.out_raw.data(), G.out_raw, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(W.flags.data(), G.out_flags, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1651,6 +1655,124 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                 t_tail, t_dedupe, t_final, t_rank);
     }
     return copy_result(ctx, out);
+}
+
+// ------------------------------------------------- alignment step 1 on the device
+// SQRNdbnali (ali.py:211-242) sums the score of every stem of every sequence into the cells of its base pairs, sequence
+// after sequence -- and float64 addition order is observable.  Here every CTA owns a band of matrix ROWS and walks the
+// stems of ALL sequences in sequence order (they sit in device memory, written by the YieldStems kernel; the stream of
+// (i, j, len, score) records is read through L2 by every band); within one sequence a cell belongs to at most one stem,
+// so the threads of a CTA never meet on a cell, and a barrier per sequence keeps the order: the additions every cell sees
+// are exactly the reference's, without atomics or sorting.  Only the upper triangle is accumulated (the reference adds the
+// same value to [v, w] and [w, v]); k_mirror fills the rest.
+__global__ void __launch_bounds__(256)
+k_stem_matrix(int64_t n_seqs, const int64_t *__restrict__ seq_off, const int32_t *__restrict__ cols,
+              const int64_t *__restrict__ st_off, const int32_t *__restrict__ st_n, const int32_t *__restrict__ stems,
+              const double *__restrict__ score, int L, int rows_per_band, double *__restrict__ mat)
+{
+    const int r0 = blockIdx.x * rows_per_band, r1 = min(L, r0 + rows_per_band);
+    for (int64_t b = 0; b < n_seqs; b++) {
+        const int32_t *cb = cols + seq_off[b];
+        const int64_t o = st_off[b];
+        const int ns = st_n[b];
+        for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+            const int i = stems[3 * (o + k)], j = stems[3 * (o + k) + 1], len = stems[3 * (o + k) + 2];
+            // rows of the stem's cells: cols[i] .. cols[i + len - 1], increasing
+            if (cb[i] >= r1 || cb[i + len - 1] < r0) continue;
+            const double sc = score[o + k];
+            for (int q = 0; q < len; q++) {
+                const int v = cb[i + q], w = cb[j - q];
+                if (v >= r0 && v < r1) mat[(int64_t)v * L + w] += sc;          // (v < w: i + q < j - q and cols increase)
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_mirror(int L, double *__restrict__ mat)
+{
+    const int64_t n = (int64_t)L * L;
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(c / L), w = (int)(c % L);
+        if (v > w) mat[c] = mat[(int64_t)w * L + v];
+    }
+}
+
+// MatrixToDBNs (ali.py:133-150) looks at the cells in stable descending order of their value, stops below the threshold
+// and skips w - v < 4: the cells that pass both tests are collected, then ranked by counting (value descending, flat
+// index ascending) -- a few hundred conserved pairs on real alignments.
+__global__ void k_cells_collect(int L, const double *__restrict__ mat, double thr, int cap, int *__restrict__ count, int32_t *__restrict__ cells)
+{
+    const int64_t n = (int64_t)L * L;
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(c / L), w = (int)(c % L);
+        if (w - v >= 4 && !(mat[c] < thr)) { const int slot = atomicAdd(count, 1); if (slot < cap) cells[slot] = (int32_t)c; }
+    }
+}
+__global__ void k_cells_rank(int m, const double *__restrict__ mat, const int32_t *__restrict__ cells, int32_t *__restrict__ sorted)
+{
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < m; a += gridDim.x * blockDim.x) {
+        const int32_t ca = cells[a]; const double va = mat[ca];
+        int rank = 0;
+        for (int b = 0; b < m; b++) { const int32_t c = cells[b]; const double v = mat[c]; if (v > va || (v == va && c < ca)) rank++; }
+        sorted[rank] = ca;
+    }
+}
+
+extern "C" int sqrn_stem_matrix_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, double *matrix,
+                                      double threshold, int64_t cap_cells, int64_t *n_cells, int32_t *cells)
+{
+    if (!ctx || !ps || !in || !matrix || !n_cells) return SQRN_E_BADARG;
+    if (in->smat || !in->cols || in->smat_L <= 0) { ctx->err = "stem matrix: need the column map (cols, smat_L = alignment length) and no smat"; return SQRN_E_BADARG; }
+    cudaSetDevice(ctx->device);
+    ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
+    const int L = in->smat_L;
+    const int64_t nseq = in->n_seqs, total = in->offsets[nseq];
+    for (int64_t k = 0; k < total; k++) if (in->cols[k] < 0 || in->cols[k] >= L) { ctx->err = "column out of range"; return SQRN_E_BADARG; }
+    DeviceBatch D;
+    TRY(upload_batch(ctx, in, D));
+    HostWork W; W.mode = MODE_YIELD; W.keep_on_device = true;
+    for (int64_t b = 0; b < nseq; b++) {
+        W.item_seq.push_back((int32_t)b);
+        const double n = D.len[b];
+        W.out_cap.push_back((int64_t)(0.03 * n * n) + 64);
+    }
+    TRY(run_items(ctx, *ps, D, W));
+    bool redo = false;
+    for (int64_t b = 0; b < nseq; b++) if (W.out_n[b] > W.out_cap[b]) { W.out_cap[b] = W.out_n[b]; redo = true; }
+    if (redo) TRY(run_items(ctx, *ps, D, W));
+    int32_t *d_cols; double *d_mat; int *d_cnt; int32_t *d_cells, *d_sorted;
+    TRY(upload(ctx, B_COLS, in->cols, (size_t)total, &d_cols));
+    TRY(dalloc(ctx, W_MAT, (size_t)L * L, &d_mat));
+    const int cap = (int)std::min<int64_t>(std::max<int64_t>(cap_cells, 0), 1 << 16);
+    TRY(dalloc(ctx, W_CELLCNT, 1, &d_cnt));
+    TRY(dalloc(ctx, W_CELLS, (size_t)std::max(cap, 1), &d_cells));
+    TRY(dalloc(ctx, W_CELLS2, (size_t)std::max(cap, 1), &d_sorted));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(d_mat, 0, (size_t)L * L * sizeof(double), st));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+    const int bands = std::max(1, std::min(L, 2 * ctx->sm_count)), rpb = (L + bands - 1) / bands;
+    k_stem_matrix<<<(L + rpb - 1) / rpb, 256, 0, st>>>(nseq, D.B.off, d_cols, W.d_out_off, W.d_out_n, W.d_out_stems, W.d_out_fin, L, rpb, d_mat);
+    CK(cudaGetLastError());
+    k_mirror<<<2 * ctx->sm_count, 256, 0, st>>>(L, d_mat);
+    k_cells_collect<<<2 * ctx->sm_count, 256, 0, st>>>(L, d_mat, threshold, cap, d_cnt, d_cells);
+    CK(cudaGetLastError());
+    int m = 0;
+    CK(cudaMemcpyAsync(&m, d_cnt, sizeof m, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(matrix, d_mat, (size_t)L * L * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->n_launches += 3;
+    *n_cells = m;
+    if (m > cap) { *n_cells = -1; return SQRN_OK; }      // more cells than the caller (or the device ranking) takes: the caller sorts the matrix itself
+    if (m > 0) {
+        if (!cells) return SQRN_E_BADARG;
+        k_cells_rank<<<std::min(2 * ctx->sm_count, (m + 255) / 256), 256, 0, st>>>(m, d_mat, d_cells, d_sorted);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(cells, d_sorted, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->n_launches++;
+    }
+    return SQRN_OK;
 }
 
 // ------------------------------------------------------------- YieldStems

@@ -545,3 +545,50 @@ def test_config3_shape_reference_cases(gpu_ctx):
         if not T.same_prediction((got[0], got[1]), want):
             bad.append((c["conf"], len(c["seq"])))
     assert not bad, "%d of %d differ: %r" % (len(bad), len(cases), bad)
+
+
+def _stem_matrix_both_ways(entries, ps, L, thr):
+    """alignment step 1: the device-side sum (sqrn_stem_matrix_batch) and the host accumulation of the stems that
+    sqrn_yield_stems_batch returns -- the same float64 additions per cell in the same (sequence) order"""
+    from squarna_b200 import SQRNdbnali as A
+    mat_d, cells = A._yield_many(entries, ps["bpweights"], False, ps["minlen"], ps["minbpscore"], device=0, matrix=(L, thr))
+    mat_h = A._accumulate_host(A._yield_many(entries, ps["bpweights"], False, ps["minlen"], ps["minbpscore"], device=0), L)
+    assert mat_d.shape == mat_h.shape and (mat_d == mat_h).all()
+    # MatrixToDBNs' order: value descending, flat index ascending, stop below the threshold, w - v >= 4
+    flat = mat_h.ravel()
+    order = np.argsort(-flat, kind="stable")
+    want = [int(c) for c in order.tolist() if flat[c] >= thr and (c % L) - (c // L) >= 4]
+    assert cells is not None and cells.tolist() == want
+    return mat_d, cells
+
+
+def test_alignment_step1_matrix_on_device(gpu_ctx):
+    """(8f-3) the stem-score matrix of an alignment: gaps, reactivities (scores that are not dyadic rationals: the order
+    of the additions matters), restraints; two parameter sets; thresholds that keep few and many cells"""
+    import workloads
+    rows, _ref = workloads.config4(96, 150, 200, seed=3)
+    rng = random.Random(41)
+    L = len(rows[0])
+    plain = [(r, None, None) for r in rows]
+    _stem_matrix_both_ways(plain, T.ALI, L, T.ALI["minbpscore"] * len(rows))
+    _stem_matrix_both_ways(plain, T.DEFG1, L, 40.0)
+    reacts = [[round(rng.random(), 3) if rng.random() < 0.7 else 0.5 for _ in range(L)] for _ in rows]
+    rests = ["".join(rng.choice("....._/") for _ in range(L)) for _ in rows]
+    mixed = [(r, reacts[k] if k % 2 else None, rests[k] if k % 3 == 0 else None) for k, r in enumerate(rows)]
+    _stem_matrix_both_ways(mixed, T.ALI, L, 25.0)
+    _stem_matrix_both_ways(mixed[:1], T.ALI, L, 1.0)
+    _stem_matrix_both_ways([("A" * L, None, None)], T.ALI, L, 1.0)                  # no stems at all
+
+
+def test_config4_size_alignment_step1(gpu_ctx):
+    """BASELINE config 4 at its stated size: 2000 sequences x 400 columns (workloads.config4), step 1 on the device
+    against the host accumulation, and the structure MatrixToDBNs builds from either"""
+    import workloads
+    from squarna_b200 import SQRNdbnali as A
+    rows, ref = workloads.config4(2000, 300, 400)
+    L = len(rows[0])
+    entries = [(r, None, None) for r in rows]
+    mat, cells = _stem_matrix_both_ways(entries, T.ALI, L, T.ALI["minbpscore"] * len(rows))
+    a = A.MatrixToDBNs(mat, T.ALI["minbpscore"], len(rows), cells=cells)
+    b = A.MatrixToDBNs(mat, T.ALI["minbpscore"], len(rows))
+    assert a == b and a[0].count("(") >= 0.8 * ref.count("(")

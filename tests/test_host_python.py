@@ -483,10 +483,14 @@ def test_sqrndbnseq_host_python_on_the_reference_cases(monkeypatch):
     assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
 
 
-def _oracle_yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=0):
-    """SQRNdbnali._yield_many with the oracle's AnnotateStems in place of the GPU call"""
+def _oracle_yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=0, matrix=None):
+    """SQRNdbnali._yield_many with the oracle's AnnotateStems in place of the GPU call (matrix: the device-side sum of
+    sqrn_stem_matrix_batch is stood in for by the host accumulation; the cells come back unsorted = None)"""
     import numpy as np
     from oracle import oracle as O
+    if matrix is not None:
+        from squarna_b200 import SQRNdbnali as A
+        return A._accumulate_host(_oracle_yield_many(entries, bpweights, interchainonly, minlen, minbpscore), matrix[0]), None
     out = []
     ps = dict(bpweights=bpweights, minlen=minlen, minbpscore=minbpscore)
     for seq, reacts, rests in entries:
