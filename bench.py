@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the greedy hot path on BASELINE.json's configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|5] [--seqs S] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--seqs S] [--impl ours|reference]
 
 --config 2 (default, the configuration the metric is quoted on): 1 M synthetic random RNAs U{60..200} per GPU,
             `byseq pl=1 c=fastest.conf`; weak scaling (S per GPU, ranks take disjoint batches).
@@ -616,6 +616,9 @@ def bench_config3(args, rank, world, local):
     for _ in range(max(args.warmup, 3)):
         for c, es in groups.items():
             S.predict_many(es[:8], psets[c], poollim=100, device=local)
+    # ... and one full-size pass (the library sizes its device scratch -- base lists, candidate lists -- on first use)
+    for c, es in groups.items():
+        S.predict_many(es, psets[c], poollim=100, device=local)
     sampler = ClockSampler(local)
     sampler.start()
     # e2e leg: predict_many from Python strings (prepare, pack, C-ABI call with host buffers, result assembly)
@@ -673,7 +676,7 @@ def bench_config3(args, rank, world, local):
                 "config": {"workload": "config3: %d synthetic RNAs%s, len U{300..1500}, rf=26 reactivity letters (3%% '?'), restraints "
                                        "(5%% '_', 1%% '/', 1%% '\\', 0-2 planted stems), G sets by length (greedynobpp / 500nobpp / "
                                        "1000nobpp), pl=100" % (n_global, cap),
-                           "warmup_note": "warm-up passes run on an 8-sequence prefix of every length class",
+                           "warmup_note": "warm-up: three passes over an 8-sequence prefix of every length class, then one full-size pass",
                            "sharding": "one global batch dealt by length^3, imbalance %.4f" % plan_imbalance(glens, plan, 3.0),
                            "l2_policy": "inputs larger than L2 per pass; no flush"},
                 "e2e": {"value": n_global / e2e_s, "unit": "seq/s", "ms_per_step": e2e_s * 1e3,
@@ -725,12 +728,98 @@ def cpu_baseline_config3(entries, threads):
     return out
 
 
+# ------------------------------------------------------------------------------ config 4: alignment mode
+def bench_config4(args, rank, world, local):
+    """BASELINE config 4: alignment mode on a synthetic 2000-sequence x 400-column alignment (workloads.config4).
+    `value`: rows / second of step 1 through the C ABI (sqrn_stem_matrix_batch on a prepared batch, twice -- the second
+    iteration feeds the first structure back as restraints): stems, the sequence-ordered sum and the ranking of the
+    conserved cells on the device.  `e2e`: the whole alignment mode through the unchanged Predict() surface (input file in,
+    text out: step 1, step 2 = stem-matrix-weighted single-sequence predictions of every row, consensus on the host)."""
+    import io
+    import torch
+    from squarna_b200 import SQRNdbnali as A
+    from squarna_b200 import SQRNdbnseq as S
+    from squarna_b200 import SQUARNA as CLI
+    if rank != 0:
+        return                                                     # one alignment: the path does not shard at step 1
+    torch.cuda.set_device(local)
+    n_rows = args.seqs
+    rows, ref = workloads.config4(n_rows, 300, 400)
+    L = len(rows[0])
+    names, psets = CLI.ParseConfig(os.path.join(os.path.dirname(os.path.abspath(CLI.__file__)), "ali.conf"))
+    first = psets[0]
+    os.environ["SQRN_DEVICES"] = str(local)
+    ctx = S.get_context(local)
+    entries = [(r, None, None) for r in rows]
+    thr = first["minbpscore"] * n_rows
+
+    def step1():
+        mat, cells = A._yield_many(entries, first["bpweights"], False, first["minlen"], first["minbpscore"], device=local, matrix=(L, thr))
+        dbn = A.MatrixToDBNs(mat, first["minbpscore"], n_rows, cells=cells)[0]
+        ent2 = [(r, None, dbn) for r in rows]
+        A._yield_many(ent2, first["bpweights"], False, first["minlen"], first["minbpscore"], device=local, matrix=(L, thr))
+        return dbn
+
+    for _ in range(max(args.warmup, 3)):
+        dbn1 = step1()
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kms, launches = 0.0, 0
+    for _ in range(args.steps):
+        step1()
+        st = ctx.stats()
+        kms += st["kernel_ms"]; launches += st["launches"]
+    torch.cuda.synchronize()
+    step1_s = (time.perf_counter() - t0) / args.steps
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "c4.afa")
+        with open(path, "w") as f:
+            f.write(workloads.config4_text(rows, ref))
+        buf = io.StringIO()
+        CLI.Predict(inputfile=path, alignment=True, write_to=buf)                  # warm-up of the step-2 kernels
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            buf = io.StringIO()
+            CLI.Predict(inputfile=path, alignment=True, write_to=buf)
+        e2e_s = (time.perf_counter() - t0) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    text = buf.getvalue()
+    step3 = [ln for ln in text.split("\n") if "Step-3" in ln]
+    peaks = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    lens = np.array([len(r) - r.count("-") for r in rows])
+    abytes = workloads.algorithmic_bytes(lens) + 8 * L * L
+    achieved = abytes / max(step1_s, 1e-9) / 1e9
+    line = {"metric": "alignment rows/sec (SQRNdbnali step 1; e2e: the whole alignment mode)", "value": n_rows / step1_s, "unit": "seq/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step1_s * 1e3, "higher_is_better": True,
+            "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config4: alignment mode on a synthetic %d-sequence x %d-column alignment (ancestor with planted "
+                                   "hairpins, 10%% substitutions, 2%% deletions, shared gap columns), ali.conf" % (n_rows, L),
+                       "l2_policy": "the stems of all rows (tens of MB) are re-read per row band through L2; no flush"},
+            "e2e": {"value": n_rows / e2e_s, "unit": "seq/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(3 * (lens.sum() * 5 + 8 * n_rows)), "d2h_bytes_per_step": int(2 * 8 * L * L + n_rows * L * 2),
+                    "call": "squarna_b200.SQUARNA.Predict(inputfile=<alignment>, alignment=True): steps 1-3, text out",
+                    "step3_line": step3[0] if step3 else None},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "kernel": "k_work<8> (MODE_YIELD) + k_stem_matrix",
+                         "algorithmic_bytes_per_launch": abytes, "kernel_ms": kms / args.steps,
+                         "note": "host-bound: the Python preparation of the rows and the text dominate (DESIGN.md)"},
+            "cpu_baseline": {"value": 0.0, "unit": "seq/s", "cores": host_cores(), "kind": "reference", "sample": "not run (see BASELINE.md: "
+                             "the reference needs minutes per alignment of this size)"},
+            "clocks": sampler.summary()}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--seqs", type=int, default=None,
                     help="config 2: sequences per GPU per step (default 1 000 000); configs 3 / 5: sequences of the global batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -738,9 +827,9 @@ def main():
     ap.add_argument("--no-cli", action="store_true", help="skip the CLI-level end-to-end leg of config 2")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = {2: 20, 5: 3, 3: 1}[args.config]
+        args.steps = {2: 20, 5: 3, 3: 1, 4: 3}[args.config]
     if args.seqs is None:
-        args.seqs = {2: 1_000_000, 5: 10_000, 3: 100_000 if args.gpus >= 8 else 20_000}[args.config]
+        args.seqs = {2: 1_000_000, 5: 10_000, 3: 100_000 if args.gpus >= 8 else 20_000, 4: 2000}[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -752,6 +841,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     if args.config == 3:
         bench_config3(args, rank, world, local)
+    elif args.config == 4:
+        bench_config4(args, rank, world, local)
     else:
         bench_fast(args, rank, world, local)
 

@@ -35,6 +35,11 @@ __device__ __forceinline__ void work_loop(const DevParams *__restrict__ Pg, cons
     __syncthreads();
     const int team = (TW == 1) ? (threadIdx.x >> 5) : 0;
     State S = bind_state(smem + (size_t)team * L.total, L);
+    if (TW > 1 && !C::PERSIST) {
+        // the two staging barriers of the base-list sweep (team_scan): one arrival each, the elected producer's
+        if (threadIdx.x == 0) { mbar_init(S.stage, 1); mbar_init(S.stage + 8, 1); mbar_fence_init(); }
+        __syncthreads();
+    }
     const int n_items = Wk.n_items_dev ? *Wk.n_items_dev : Wk.n_items;
     for (;;) {
         int item = 0;

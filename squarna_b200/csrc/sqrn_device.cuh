@@ -181,7 +181,7 @@ struct Layout {
     int o_pbps, o_pkey;
     int o_code, o_rcode, o_rcl, o_partner, o_owner, o_sepcnt, o_M, o_PR, o_rowok, o_colokR, o_Ub, o_Ubase,
         o_sti, o_stj, o_stl, o_stlev, o_evpos, o_evid, o_cc, o_perm, o_grp, o_gsz,
-        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, o_stlev2, o_evjump, o_glx, total;
+        o_rbv, o_rbw, o_rkey, o_rlen, o_ckey, o_clen, o_cbps, o_cfin, o_red, o_xchg, o_misc, o_stlev2, o_evjump, o_glx, o_stage, total;
 };
 
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -262,6 +262,8 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     o += tw != 1 ? 4 * L.Scap : 0;                    // ScoreStems may jump to (team_apply_stem)
     o = align_up(o, 4);
     L.o_glx = o;     o += (pcap < 0 || tw != 1) ? 4 * (3 * 256 + 4) : 0;   // binned lists: histogram, bin ends, scatter cursors (gl_make_bins)
+    o = align_up(o, 16);
+    L.o_stage = o;   o += tw > 1 ? 16 + 2 * 16 * 32 * tw : 0;             // base-list sweep: two mbarriers + two tiles of T 16-byte records (cp.async.bulk)
     L.total = align_up(o, 16);
     return L;
 }
@@ -373,7 +375,8 @@ struct State {
     int32_t  *cc, *gsz, *Ubase, *ghist, *gbend, *gcur;
     uint16_t *clen, *rlen;
     double   *cbps, *cfin, *red, *pbps;
-    unsigned char *xchg;
+    unsigned char *xchg, *stage;
+    uint32_t bphase[2];  // phase parity of the two staging barriers (base-list sweep)
     int      *misc;      // [0] run count  [1] next item  [2..6] scratch  [7] survivor count  [8] persistent entries
     const int32_t *cols; // global, per sequence
 };
@@ -403,12 +406,14 @@ __device__ __forceinline__ State bind_state(unsigned char *base, const Layout &L
     s.xchg = base + L.o_xchg;
     s.misc = (int *)(base + L.o_misc);
     s.ghist = (int32_t *)(base + L.o_glx);  s.gbend = s.ghist + 256;  s.gcur = s.gbend + 260;
+    s.stage = base + L.o_stage;
     s.W = L.W; s.WR = L.WR;
     s.N = 0; s.nst = 0; s.nrb = 0; s.has_sep = 0; s.has_react = 0; s.has_smat = 0; s.default_reacts = 1;
     s.region_mode = REGION_AUTO;
     s.bpp_mode = 0; s.bpp = nullptr;
     s.dstride = 1; s.doffset = 0;
     s.cols = nullptr;
+    s.bphase[0] = s.bphase[1] = 0;
     return s;
 }
 
@@ -1411,6 +1416,30 @@ __device__ __forceinline__ uint32_t unpaired_bits32(const State &S, int p0)
 __device__ __forceinline__ bool unpaired_at(const State &S, int p) { return (S.Ub[p >> 5] >> (p & 31)) & 1u; }
 
 
+// ---- bulk asynchronous copies (TMA unit, cp.async.bulk) with mbarrier completion: tiles of the base list are staged in
+// shared memory one tile ahead of the threads that look at them.  One elected thread arms the barrier with the byte
+// count and issues the copy; every thread waits on the barrier's phase before it reads the tile.
+#ifndef SQRN_HOST_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// bytes: a multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, void *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
 // Base list of a sequence: its maximal runs under the EMPTY structure (bp score cached), binned by the static bound
 // gl_ub0 like the persistent list of k_long, built once per (sequence, parameter set) by MODE_BASE and then shared,
 // read-only, by every work item of that sequence -- the partial structures of its pool (MODE_STEP) and their tails.
@@ -1579,6 +1608,15 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
         int done = 0;
 #ifdef SQRN_HOST_EMU
         g_emu_base_sweeps++;
+#else
+        // tiles of T records go through a two-stage ring in shared memory, filled by cp.async.bulk one tile ahead
+        unsigned long long *bar = (unsigned long long *)S.stage;
+        uint4 *tile = (uint4 *)(S.stage + 16);
+        uint32_t phase0 = S.bphase[0], phase1 = S.bphase[1];        // (the barriers are initialised once per kernel: work_loop)
+        auto fetch = [&](int c0, int stage, int stop) {            // (thread 0) records [c0, min(c0 + T, stop)) -> tile[stage]
+            const int cnt = stop - c0 < T ? stop - c0 : T;
+            bulk_load(tile + stage * T, &base->ent[c0], (uint32_t)cnt * 16u, &bar[stage]);
+        };
 #endif
         #pragma unroll 1
         for (;;) {
@@ -1596,17 +1634,30 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
                 if (target > nb) target = nb;
             }
             if (target <= done) break;
+#ifndef SQRN_HOST_EMU
+            int kt = 0;                                  // tile number within the round (its stage: kt & 1)
+            if (r == 0) fetch(done, 0, target);         // (every thread is past the barriers of the last flush: the ring is free)
+#endif
             #pragma unroll 1
             for (int c0 = done; c0 < target; c0 += T) {
                 const int c = c0 + r;
                 bool pending = c < target, whole = false;
                 uint32_t ekey = 0, live = 0; int len = 0, a = 0, s = 0, t = 0, q = 0; double ebps = 0.0; bool cand = false;
+#ifndef SQRN_HOST_EMU
+                const int stage = kt & 1;
+                // the tile after this one: its stage was read during the tile before this one, and every thread has
+                // passed a team barrier since then (the claim of the survivor list)
+                if (r == 0 && c0 + T < target) fetch(c0 + T, stage ^ 1, target);
+                mbar_wait(&bar[stage], stage ? phase1 : phase0);
+                if (stage) phase1 ^= 1u; else phase0 ^= 1u;
+                kt++;
+#endif
                 if (pending) {
 #ifdef SQRN_HOST_EMU
                     const BEnt e = base->ent[c];
                     ekey = e.key; len = (int)(e.meta & 0xffffu); cand = (e.meta >> 31) != 0; ebps = e.bps;
 #else
-                    const uint4 w = *reinterpret_cast<const uint4 *>(&base->ent[c]);
+                    const uint4 w = tile[stage * T + r];
                     ekey = w.x; len = (int)(w.y & 0xffffu); cand = (w.y >> 31) != 0; ebps = __hiloint2double((int)w.w, (int)w.z);
 #endif
                     a = (int)(ekey & 0xffffu); s = (int)(ekey >> 16); t = s - a;
@@ -1662,6 +1713,9 @@ __device__ Best team_scan(State &S, const DevParams &P, const DevBatch &B, const
             done = target;
             if (done >= nb) break;
         }
+#ifndef SQRN_HOST_EMU
+        S.bphase[0] = phase0; S.bphase[1] = phase1;
+#endif
     } else if (!C::RUNLIST) {
         // CTA teams (long sequences: hundreds of runs per diagonal): a WARP walks one anti-diagonal,
         // 32 words (1024 cells) per step, one word per lane, so the lanes do the same work at the same
@@ -3101,7 +3155,7 @@ __device__ void team_run_item(State &S, const DevParams &P, const DevBatch &B, c
             return;
         }
         const int nb = Wk.base_n[seq];
-        if (nb >= 0 && (mode == MODE_STEP || mode == MODE_TAIL) && !C::PERSIST) {
+        if (nb >= 0 && (mode == MODE_STEP || mode == MODE_TAIL) && !C::PERSIST && !C::CLUSTER) {
             const int r_ = Team<TW>::rank();
             #pragma unroll 1
             for (int q = r_; q <= GL_NBIN; q += Team<TW>::T) S.gbend[q] = Wk.base_bend[(GL_NBIN + 1) * (int64_t)seq + q];
