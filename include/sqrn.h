@@ -218,6 +218,13 @@ SQRN_API int  sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps,
 SQRN_API int  sqrn_fast_predict_packed_host(sqrn_ctx *ctx, const sqrn_paramset *ps,
                             int64_t n_seqs, const uint32_t *offsets, const uint8_t *packed,
                             uint8_t *dbn_nib, int32_t *score_milli, uint16_t *n_stems, uint8_t *flags);
+/* ... and with everything resident in HBM (asynchronous on the context's stream; d_offsets int64 as in
+ * sqrn_fast_predict_device).  d_flags bit 3: the score sat next to a rounding tie and its thousandths are NOT set
+ * (the host variant redoes those with CPython's round()).                                                            */
+SQRN_API int  sqrn_fast_predict_packed_device(sqrn_ctx *ctx, const sqrn_paramset *ps,
+                            int64_t n_seqs, int64_t total_len, int32_t max_len,
+                            const int64_t *d_offsets, const uint8_t *d_packed,
+                            uint8_t *d_dbn_nib, int32_t *d_score_milli, uint16_t *d_n_stems, uint8_t *d_flags);
 SQRN_API int  sqrn_pack_symbols(int64_t n_total, const uint8_t *symbols, uint8_t *packed, int64_t *n_other);
 SQRN_API int  sqrn_unpack_dbn(int64_t n_seqs, const uint32_t *offsets, const uint8_t *dbn_nib, uint8_t *dbn_ascii);
 /* Per-sequence flags of the last sqrn_fast_predict_host call (bit 1: more than 30 pseudoknot levels, the ASCII

@@ -13,7 +13,7 @@ from ._abi import (Batch, ParamSet, Result, Stems, E_CAPACITY, OK, pack_sequence
 E_UNSUPPORTED = -4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsqrn_b200.so")
+LIB_PATH = os.environ.get("SQRN_LIB_PATH") or os.path.join(_HERE, "libsqrn_b200.so")      # (override: kernel experiments)
 
 MODE_TAIL, MODE_STEP, MODE_YIELD, MODE_FINAL = 0, 1, 2, 3
 
@@ -22,7 +22,7 @@ EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx
            "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
            "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_ungap", "sqrn_text_format",
            "sqrn_fast_predict_packed_host", "sqrn_pack_symbols", "sqrn_unpack_dbn", "sqrn_fast_last_flags",
-           "sqrn_stem_matrix_batch"]
+           "sqrn_stem_matrix_batch", "sqrn_fast_predict_packed_device"]
 
 _lib = None
 
@@ -55,6 +55,7 @@ def load():
     L.sqrn_fast_predict_host.argtypes = [vp, C.POINTER(ParamSet), i64, vp, vp, vp, vp, vp]
     L.sqrn_fast_predict_device.argtypes = [vp, C.POINTER(ParamSet), i64, i64, i32, vp, vp, vp, vp, vp]
     L.sqrn_fast_predict_packed_host.argtypes = [vp, C.POINTER(ParamSet), i64, vp, vp, vp, vp, vp, vp]
+    L.sqrn_fast_predict_packed_device.argtypes = [vp, C.POINTER(ParamSet), i64, i64, i32, vp, vp, vp, vp, vp, vp]
     L.sqrn_pack_symbols.argtypes = [i64, vp, vp, C.POINTER(i64)]
     L.sqrn_unpack_dbn.argtypes = [i64, vp, vp, vp]
     L.sqrn_fast_last_flags.argtypes = [vp, i64, vp]

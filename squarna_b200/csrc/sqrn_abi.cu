@@ -701,6 +701,36 @@ extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, 
     return rc;
 }
 
+extern "C" int sqrn_fast_predict_packed_device(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
+                                               int32_t max_len, const int64_t *d_offsets, const uint8_t *d_packed,
+                                               uint8_t *d_dbn_nib, int32_t *d_score_milli, uint16_t *d_n_stems, uint8_t *d_flags)
+{
+    if (!ctx || !ps || !d_score_milli || !d_flags || n_seqs < 0 || n_seqs > 0x7fffffff || max_len > SQRN_MAX_LEN) return SQRN_E_BADARG;
+    (void)total_len;
+    cudaSetDevice(ctx->device);
+    if (n_seqs == 0) return SQRN_OK;
+    const PEntry *P;
+    TRY(get_params(ctx, *ps, max_len, &P));
+    Plan pl;
+    TRY(make_fast_plan(ctx, *P, max_len, (int)n_seqs, pl));
+    int *d_counter; unsigned long long *d_nc; int32_t *d_ovf; int *d_rnd; PackedOut pk;
+    constexpr int RND_CAP = 4096;
+    TRY(dalloc(ctx, W_COUNTER, 4 * FAST_MAX_CHUNKS, &d_counter));
+    TRY(dalloc(ctx, W_OVF, (size_t)n_seqs, &d_ovf));
+    TRY(dalloc(ctx, W_NCALLS, 1, &d_nc));
+    TRY(dalloc(ctx, W_RNDC, 1, &d_rnd));
+    TRY(dalloc(ctx, W_RNDL, (size_t)4 * RND_CAP, &pk.rnd_list));
+    CK(cudaMemsetAsync(d_counter, 0, 4 * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d_nc, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(d_rnd, 0, sizeof(int), ctx->stream));
+    pk.nib = d_dbn_nib; pk.milli = d_score_milli; pk.ns16 = d_n_stems; pk.rnd_count = d_rnd; pk.rnd_cap = RND_CAP;
+    // (scores next to a rounding tie keep FLAG_ROUND in d_flags and their thousandths unset: the host variant redoes those)
+    int rc = fast_launch(ctx, *P, pl, ctx->stream, 0, n_seqs, d_offsets, d_packed, nullptr, nullptr, nullptr,
+                         d_flags, d_counter, d_ovf, d_nc, 0, ctx->ev0, ctx->ev1, nullptr, &pk);
+    if (rc == SQRN_OK) ctx->ev_valid = true;
+    return rc;
+}
+
 // Host buffers in, host buffers out.  The batch is cut into chunks that flow through three
 // stages on separate streams -- host->device copy, kernel, device->host copy -- so PCIe traffic
 // in both directions overlaps the kernels of the neighbouring chunks.
