@@ -517,15 +517,20 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
 
 def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, slice_entries=131072, per_entry=None):
     """SQUARNA.py:845-935 for the plain shape of an input.  False: not that shape (nothing was written)."""
+    import time
     import numpy as np
     from . import _lib
     from .SQRNdbnseq import get_context
+    trace = os.environ.get("SQRN_TRACE") is not None
+    t0 = time.perf_counter()
     with open(path, "rb") as fh:
         text = fh.read()
+    t1 = time.perf_counter()
     parsed = _lib.text_parse(text, multiline)
     if parsed is None:
         return False
     sym, sym_off = _lib.text_ungap(parsed)                           # UnAlign (seq.py:236-255) on the whole buffer
+    t2 = time.perf_counter()
     if int(np.diff(sym_off).max(initial=0)) > 16000:
         return False
     from .SQRNdbnseq import _resolve_devices
@@ -542,6 +547,7 @@ def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, sl
         return False
     # sequences whose structure has more than 30 pseudoknot levels (n_stems = -1: the one-byte glyphs ran out) are
     # printed by the per-entry path, in their place; everything around them stays on the bulk formatter
+    t3 = time.perf_counter()
     deep = np.flatnonzero(nst < 0).tolist()
     if deep and per_entry is None:
         return False
@@ -567,6 +573,9 @@ def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, sl
         per_entry([(name, seq, None, None, None)])
         at = e + 1
     emit(at, parsed.n)
+    if trace:
+        print("[sqrn] bulk lane: read %.3f s, parse + ungap %.3f s, predict %.3f s, format + write %.3f s (%d entries)"
+              % (t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3, parsed.n), file=sys.stderr)
     return True
 
 

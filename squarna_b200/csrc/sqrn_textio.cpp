@@ -143,7 +143,7 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
     int nt = 1;
     if (len >= (4ll << 20)) {
         nt = (int)std::thread::hardware_concurrency();
-        nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+        nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
     }
     std::vector<int64_t> cut((size_t)nt + 1, len);
     cut[0] = 0;
@@ -196,14 +196,39 @@ extern "C" int sqrn_text_parse(const char *text, int64_t len, int multiline, int
 extern "C" int sqrn_text_ungap(int64_t n, const int64_t *seq_offsets, const uint8_t *seq, int64_t *sym_offsets, uint8_t *sym)
 {
     if (n < 0 || !seq_offsets || !seq || !sym_offsets || !sym) return SQRN_E_BADARG;
-    int64_t w = 0;
-    sym_offsets[0] = 0;
-    for (int64_t k = 0; k < n; k++) {
-        for (int64_t c = seq_offsets[k]; c < seq_offsets[k + 1]; c++)
-            if (!is_gap(seq[c])) sym[w++] = seq[c];
-        sym_offsets[k + 1] = w;
+    try {
+    // ranges of entries, one host thread each: count the symbols that stay, then copy them to where the range starts
+    int nt = 1;
+    if (seq_offsets[n] >= (4ll << 20)) {
+        nt = (int)std::thread::hardware_concurrency();
+        nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
     }
+    std::vector<int64_t> kept((size_t)nt + 1, 0);
+    auto count = [&](int t) {
+        const int64_t k0 = n * t / nt, k1 = n * (t + 1) / nt;
+        int64_t c = 0;
+        for (int64_t q = seq_offsets[k0]; q < seq_offsets[k1]; q++) c += !is_gap(seq[q]);
+        kept[(size_t)t + 1] = c;
+    };
+    run_threads(nt, count);
+    for (int t = 0; t < nt; t++) kept[(size_t)t + 1] += kept[(size_t)t];
+    auto fill = [&](int t) {
+        const int64_t k0 = n * t / nt, k1 = n * (t + 1) / nt;
+        int64_t w = kept[(size_t)t];
+        const bool no_gaps = kept[(size_t)t + 1] - kept[(size_t)t] == seq_offsets[k1] - seq_offsets[k0];
+        if (no_gaps && k1 > k0) memcpy(sym + w, seq + seq_offsets[k0], (size_t)(seq_offsets[k1] - seq_offsets[k0]));
+        for (int64_t k = k0; k < k1; k++) {
+            if (no_gaps) w += seq_offsets[k + 1] - seq_offsets[k];
+            else
+                for (int64_t c = seq_offsets[k]; c < seq_offsets[k + 1]; c++)
+                    if (!is_gap(seq[c])) sym[w++] = seq[c];
+            sym_offsets[k + 1] = w;
+        }
+    };
+    sym_offsets[0] = 0;
+    run_threads(nt, fill);
     return SQRN_OK;
+    } catch (...) { return SQRN_E_NOMEM; }
 }
 
 namespace {
@@ -282,7 +307,7 @@ extern "C" int sqrn_text_format(int64_t first, int64_t count, const char *text, 
     int nthreads = 1;
     if (count >= 8192) {
         nthreads = (int)std::thread::hardware_concurrency();
-        nthreads = nthreads < 1 ? 1 : (nthreads > 8 ? 8 : nthreads);
+        nthreads = nthreads < 1 ? 1 : (nthreads > 16 ? 16 : nthreads);
     }
     auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = first + count * t / nthreads; hi = first + count * (t + 1) / nthreads; };
     std::vector<int64_t> start((size_t)count + 1);
