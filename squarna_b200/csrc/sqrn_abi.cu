@@ -192,6 +192,11 @@ enum { B_OFF, B_OFF32, B_SYM, B_RCODE, B_RVALS, B_RFPOS, B_RFNEG, B_RCLASS, B_RB
        W_ORDER, W_ISEQ, W_IOFF, W_ISTEMS, W_SUBOPT, W_COUNTER, W_OOFF, W_OSTEMS, W_ON, W_OFIN, W_ORAW,
        W_OFLAGS, W_DOFF, W_DBNA, W_DBNC, W_NCALLS, W_OVF, W_GENT, W_GBPS, W_GQB, W_GCNT, W_GCNT2, W_GSTAT, W_OVF2, W_RNDC, W_RNDL, W_BASE, W_BASEOFF, W_BASEN, W_BASEBEND, W_MAT, W_CELLCNT, W_CELLS, W_CELLS2, NBUF };
 
+// ------------------------------------------------------------- launch plan
+struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; int cluster = 0; bool cl_plain = false;
+              size_t smem_rescan = 0; int grid_rescan = 0;
+              bool glist = false; Layout Lg; size_t smem_g = 0; int grid_g = 0; long long gcap = 0; int grid_classic = 0; };
+
 struct sqrn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = false;
@@ -201,6 +206,7 @@ struct sqrn_ctx {
     cudaEvent_t ev_in[FAST_MAX_CHUNKS] = {}, ev_k0[FAST_MAX_CHUNKS] = {}, ev_k1[FAST_MAX_CHUNKS] = {}, ev_o[FAST_MAX_CHUNKS] = {};
     uint8_t *hflags = nullptr; size_t hflags_cap = 0;                    // pinned staging for the result flags
     int32_t *horder = nullptr; size_t horder_cap = 0;                   // pinned: processing order of the fast-lane chunks
+    Plan fast_plans[3]; bool fast_plan_ok[3] = {false, false, false};   // the three length classes of the fast kernels
     std::string err;
     int sm_count = 0; size_t smem_optin = 0;
     std::vector<PEntry> pcache;
@@ -344,10 +350,6 @@ static int get_params(sqrn_ctx *ctx, const sqrn_paramset &ps, int nmax, const PE
 }
 
 // ------------------------------------------------------------- launch plan
-struct Plan { int tw, threads, tpc, grid; size_t smem; Layout L; int fast_ncap = 0; int cluster = 0; bool cl_plain = false;
-              size_t smem_rescan = 0; int grid_rescan = 0;
-              bool glist = false; Layout Lg; size_t smem_g = 0; int grid_g = 0; long long gcap = 0; int grid_classic = 0; };
-
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 template <int TW>
@@ -459,9 +461,15 @@ static bool fast_eligible(const PEntry &P, int nmax) { return P.hp.std_pairs && 
 static int make_fast_plan(sqrn_ctx *ctx, const PEntry &P, int nmax, int n_items, Plan &pl)
 {
     if (fast_eligible(P, nmax) && !ctx->no_fast_kernel) {
-        if (nmax <= 128) return plan_fast<128>(ctx, pl);
-        if (nmax <= 224) return plan_fast<224>(ctx, pl);
-        return plan_fast<320>(ctx, pl);
+        // (the attributes and occupancy of the three length classes are looked up once per context)
+        const int cls = nmax <= 128 ? 0 : nmax <= 224 ? 1 : 2;
+        if (!ctx->fast_plan_ok[cls]) {
+            Plan q;
+            TRY(cls == 0 ? plan_fast<128>(ctx, q) : cls == 1 ? plan_fast<224>(ctx, q) : plan_fast<320>(ctx, q));
+            ctx->fast_plans[cls] = q; ctx->fast_plan_ok[cls] = true;
+        }
+        pl = ctx->fast_plans[cls];
+        return SQRN_OK;
     }
     TRY(make_plan(ctx, P, nmax, 0, 0, false, false, 0, pl));
     maybe_glist(ctx, P, pl, nmax, 0, false, 0, true);
