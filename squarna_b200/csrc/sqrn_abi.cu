@@ -854,7 +854,10 @@ static int fast_predict_host_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_
         // persistent CTAs of a chunk then finish on short items, so the SM slots the next chunk's kernel is
         // waiting for free up together instead of trailing behind one long sequence each.
         const int32_t *d_order = nullptr;
-        if (b1 - b0 > 1 && (pl.tw > 1 || b1 - b0 >= 4096) && !no_order) {
+        // (warp-team chunks are taken in input order: measured, the order list bought nothing there -- 11.3 ms either way per
+        //  1 M sequences -- and cost the host 5 ms of counting sort per step plus 4 MB of copies)
+        static const bool order_short = getenv("SQRN_FAST_ORDER_SHORT") != nullptr;
+        if (b1 - b0 > 1 && (pl.tw > 1 || (order_short && b1 - b0 >= 4096)) && !no_order) {
             int32_t *ord = ctx->horder + b0;      // pinned, one region per chunk: the copy below is truly asynchronous
             len_count.assign((size_t)max_len + 2, 0);
             for (int64_t b = b0; b < b1; b++) len_count[(size_t)(max_len - (OFF(b + 1) - OFF(b))) + 1]++;
@@ -1422,14 +1425,14 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
         lap(t_base);
         std::vector<std::pair<int, int>> tail_items;      // (seq, index in its pool) run to completion
         for (;;) {
-            // round prologue per pool, seq.py:1161-1174
+            // round prologue per pool, seq.py:1161-1174 (per sequence, on a few host threads); then where every pool's
+            // items and their pre-selected stems start in the flat arrays of the launch, and the fill (threads again)
             HostWork W; W.mode = MODE_STEP; W.base = &base;
-            std::vector<std::pair<int, int>> owner;        // item -> (seq, pool index)
-            bool any = false;
-            for (int64_t b = 0; b < nseq; b++) {
+            std::vector<int64_t> item0((size_t)nseq + 1, 0), stem0((size_t)nseq + 1, 0);
+            parallel_for(nseq, [&](int64_t b) {
                 Pool &pl = pools[b];
-                if (pl.done || pl.tail) continue;
-                if (pl.cur.empty()) { pl.done = true; continue; }
+                if (pl.done || pl.tail) return;
+                if (pl.cur.empty()) { pl.done = true; return; }
                 if ((int)pl.cur.size() > pl.cursize) {
                     pl.cursize = (int)pl.cur.size();
                     if (pl.cursubopt < P.suboptmax) pl.cursubopt += inc;
@@ -1440,39 +1443,52 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
                     else keep.push_back(std::move(st));
                 }
                 pl.cur.swap(keep);
-                if (pl.cur.empty()) { pl.done = true; continue; }
-                if (pl.cursize >= poollim) { pl.tail = true; continue; }    // stopper == 1 from now on
-                any = true;
-                for (size_t q = 0; q < pl.cur.size(); q++) {
-                    W.item_seq.push_back((int32_t)b);
-                    W.subopt.push_back(pl.cursubopt);
-                    owner.emplace_back((int)b, (int)q);
+                if (pl.cur.empty()) { pl.done = true; return; }
+                if (pl.cursize >= poollim) { pl.tail = true; return; }    // stopper == 1 from now on
+                int64_t ns = 0;
+                for (auto &st : pl.cur) ns += (int64_t)st.size();
+                item0[b + 1] = (int64_t)pl.cur.size(); stem0[b + 1] = ns;
+            });
+            for (int64_t b = 0; b < nseq; b++) { item0[b + 1] += item0[b]; stem0[b + 1] += stem0[b]; }
+            const int64_t n_it = item0[nseq];
+            if (n_it == 0) break;
+            std::vector<std::pair<int, int>> owner((size_t)n_it);        // item -> (seq, pool index)
+            W.item_seq.resize((size_t)n_it); W.subopt.resize((size_t)n_it);
+            W.init_off.resize((size_t)n_it + 1); W.init_stems.resize((size_t)stem0[nseq] * 3);
+            W.init_off[(size_t)n_it] = stem0[nseq];
+            parallel_for(nseq, [&](int64_t b) {
+                if (item0[b + 1] == item0[b]) return;
+                Pool &pl = pools[b];
+                int64_t k = item0[b], so = stem0[b];
+                for (size_t q = 0; q < pl.cur.size(); q++, k++) {
+                    W.item_seq[(size_t)k] = (int32_t)b; W.subopt[(size_t)k] = pl.cursubopt; owner[(size_t)k] = std::make_pair((int)b, (int)q);
+                    W.init_off[(size_t)k] = so;
+                    for (auto &st : pl.cur[q]) { W.init_stems[3 * (size_t)so] = st.i; W.init_stems[3 * (size_t)so + 1] = st.j; W.init_stems[3 * (size_t)so + 2] = st.len; so++; }
                 }
-            }
-            if (!any) break;
-            W.init_off.push_back(0);
-            for (auto &o : owner) {
-                for (auto &s : pools[o.first].cur[o.second]) { W.init_stems.push_back(s.i); W.init_stems.push_back(s.j); W.init_stems.push_back(s.len); }
-                W.init_off.push_back((int64_t)W.init_stems.size() / 3);
-            }
+            });
             lap(t_gather); n_rounds++;
             TRY(run_step_items(ctx, P, D, W));
             lap(t_step);
-            // seq.py:1179-1199: children in pool order, or finalise
-            std::vector<std::vector<std::vector<Stem3>>> next((size_t)nseq);
-            for (size_t k = 0; k < owner.size(); k++) {
-                Pool &pl = pools[owner[k].first];
-                auto &st = pl.cur[owner[k].second];
-                int nnew = W.out_n[k];
-                if (nnew == 0) { pl.fin.push_back(std::move(st)); continue; }
-                for (int q = 0; q < nnew; q++) {
-                    std::vector<Stem3> child = st;
-                    const int32_t *o = &W.out_stems[3 * (W.out_off[k] + q)];
-                    child.push_back(Stem3{ o[0], o[1], o[2] });
-                    next[owner[k].first].push_back(std::move(child));
+            // seq.py:1179-1199: children in pool order, or finalise (per sequence, on a few host threads)
+            parallel_for(nseq, [&](int64_t b) {
+                if (item0[b + 1] == item0[b]) return;
+                Pool &pl = pools[b];
+                std::vector<std::vector<Stem3>> next;
+                for (int64_t k = item0[b]; k < item0[b + 1]; k++) {
+                    auto &st = pl.cur[(size_t)(k - item0[b])];
+                    const int nnew = W.out_n[(size_t)k];
+                    if (nnew == 0) { pl.fin.push_back(std::move(st)); continue; }
+                    for (int q = 0; q < nnew; q++) {
+                        const int32_t *o = &W.out_stems[3 * (W.out_off[(size_t)k] + q)];
+                        if (q + 1 == nnew) { st.push_back(Stem3{ o[0], o[1], o[2] }); next.push_back(std::move(st)); break; }   // the last child takes the parent's storage
+                        std::vector<Stem3> child; child.reserve(st.size() + 1);
+                        child = st;
+                        child.push_back(Stem3{ o[0], o[1], o[2] });
+                        next.push_back(std::move(child));
+                    }
                 }
-            }
-            for (int64_t b = 0; b < nseq; b++) if (!pools[b].done && !pools[b].tail) pools[b].cur.swap(next[b]);
+                pl.cur.swap(next);
+            });
             lap(t_scatter);
         }
         lap(t_gather);

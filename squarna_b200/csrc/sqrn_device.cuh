@@ -2588,7 +2588,11 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
         double ub = score_bound(P, sc);
         if (ub < floor || ub < P.minfinscore) { if (st != GS_PRUNED1) gl_store(&ent[c], e.key, (uint32_t)len | (GS_PRUNED1 << 16) | stamp, ub); return false; }
         ub = tight_bound(S, P, e.key, len, sc);
-        if (ub < floor || ub < P.minfinscore) { gl_store(&ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16) | stamp, ub); return false; }
+        if (ub < floor || ub < P.minfinscore) {
+            // (a record that was PRUNED with this very bound stays as it is: no store, no dirty sector)
+            if (!(st == GS_PRUNED && ub == e.v)) gl_store(&ent[c], e.key, (uint32_t)len | (GS_PRUNED << 16) | stamp, ub);
+            return false;
+        }
         return true;
     };
     auto wants_look = [&](uint32_t st, const GEnt &e) {
