@@ -724,35 +724,34 @@ def bench_config3(args, rank, world, local):
 
 
 def cpu_baseline_config3(entries, threads):
-    """the Python reference on a stratified sample (one sequence near 300 / 500 / 800 / 1100 / 1500 nt per worker, at most
-    64 in all): Predict(byseq, algo=G, pl=100) with the reference's own autoconfig replaced by the bpp-free G sets"""
-    targets = [300, 500, 800, 1100, 1500]
-    per = max(1, min(threads, 64) // len(targets))
+    """the Python reference on a BOUNDED sample: the `threads` sequences nearest to 300 nt, one per worker -- the SHORT end
+    of the workload.  Measured: one 302-nt sequence of this workload with pl=100 takes the reference 83 s on one core; its
+    cost grows faster than N^3 (500-600 nt: more than 10 minutes for 8 sequences on 16 threads), so no bench run can afford
+    the stated length mix and the rate reported here flatters the reference by orders of magnitude.
+    Predict(byseq, algo=G, pl=100) with the reference's own autoconfig replaced by the bpp-free G set of that length."""
     lens = np.array([len(e[0]) for e in entries])
-    pick = []
-    for tlen in targets:
-        order = np.argsort(np.abs(lens - tlen), kind="stable")
-        pick += order[:per].tolist()
+    pick = np.argsort(np.abs(lens - 300), kind="stable")[:max(1, min(threads, 32))].tolist()
     out = {"unit": "seq/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model()}
-    total_s, per_len = 0.0, {}
     with tempfile.TemporaryDirectory() as tmp:
-        for conf in ("greedynobpp", "500nobpp", "1000nobpp"):
-            ks = [k for k in pick if workloads.config3_conf(int(lens[k])) == conf]
-            if not ks:
-                continue
-            inp = os.path.join(tmp, "ref_c3_%s.fa" % conf)
-            with open(inp, "w") as f:
-                for k in ks:
-                    f.write(">s%d\n%s\n%s\n%s\n" % (k, entries[k][0], entries[k][1], entries[k][2]))
-            secs, _ = run_python_reference(inp, dict(configfile=conf, byseq=True, poollim=100, threads=threads, algorithms="G",
-                                                     inputformat="qtr", reactformat=26), timeout=3000)
-            if secs is None:
-                out.update({"value": 0.0, "sample": "Python reference unavailable"})
-                return out
-            total_s += secs
-            per_len[conf] = {"sequences": len(ks), "seconds": secs}
-    out.update({"value": len(pick) / total_s, "sample": "stratified sample of %d sequences nearest to 300/500/800/1100/1500 nt, "
-                "the reference's own Predict(byseq, algo=G, pl=100) per length class: %s" % (len(pick), json.dumps(per_len))})
+        inp = os.path.join(tmp, "ref_c3_greedynobpp.fa")
+        with open(inp, "w") as f:
+            for k in pick:
+                f.write(">s%d\n%s\n%s\n%s\n" % (k, entries[k][0], entries[k][1], entries[k][2]))
+        budget = 420
+        try:
+            secs, _ = run_python_reference(inp, dict(configfile="greedynobpp", byseq=True, poollim=100, threads=threads, algorithms="G",
+                                                     inputformat="qtr", reactformat=26), timeout=budget)
+        except subprocess.TimeoutExpired:
+            out.update({"value": len(pick) / float(budget), "sample": "UPPER bound: the reference did not finish %d sequences of "
+                        "%d-%d nt (Predict(byseq, algo=G, pl=100, greedynobpp)) within %d s" % (len(pick), int(lens[pick].min()),
+                                                                                                 int(lens[pick].max()), budget)})
+            return out
+    if secs is None:
+        out.update({"value": 0.0, "sample": "Python reference unavailable"})
+        return out
+    out.update({"value": len(pick) / secs, "sample": "%d sequences of %d-%d nt (the short end of the 300-1500 nt workload; longer ones "
+                "are out of reach: see the docstring), the reference's own Predict(byseq, algo=G, pl=100, greedynobpp, threads=%d): %.1f s"
+                % (len(pick), int(lens[pick].min()), int(lens[pick].max()), threads, secs)})
     return out
 
 
