@@ -6,9 +6,13 @@
 // launches, de-duplicate / rank the finished structures (seq.py:1201-1224) and
 // hand back caller-owned buffers.
 #include <cuda_runtime.h>
+#include <pthread.h>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <unordered_map>
@@ -226,6 +230,16 @@ static std::string g_create_err;
 #define TRY(x) do { int r_ = (x); if (r_ != SQRN_OK) return r_; } while (0)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return SQRN_E_CUDA; } } while (0)
+
+// No exception crosses the C boundary: host allocation failures inside an entry point come back as SQRN_E_NOMEM.
+template <class F>
+static int guarded(sqrn_ctx *ctx, F &&body)
+{
+    try { return body(); }
+    catch (const std::bad_alloc &) { if (ctx) ctx->err = "out of host memory"; return SQRN_E_NOMEM; }
+    catch (const std::exception &e) { if (ctx) ctx->err = std::string("internal error: ") + e.what(); return SQRN_E_NOMEM; }
+    catch (...) { if (ctx) ctx->err = "internal error"; return SQRN_E_NOMEM; }
+}
 
 extern "C" int sqrn_abi_version(void) { return SQRN_ABI_VERSION; }
 
@@ -683,7 +697,7 @@ static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStrea
     return SQRN_OK;
 }
 
-extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
+static int sqrn_fast_predict_device_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
                                         int32_t max_len, const int64_t *d_offsets, const uint8_t *d_symbols,
                                         uint8_t *d_dbn_ascii, double *d_scores, int32_t *d_n_stems)
 {
@@ -709,7 +723,14 @@ extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, 
     return rc;
 }
 
-extern "C" int sqrn_fast_predict_packed_device(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
+extern "C" int sqrn_fast_predict_device(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
+                                        int32_t max_len, const int64_t *d_offsets, const uint8_t *d_symbols,
+                                        uint8_t *d_dbn_ascii, double *d_scores, int32_t *d_n_stems)
+{
+    return guarded(ctx, [&] { return sqrn_fast_predict_device_impl(ctx, ps, n_seqs, total_len, max_len, d_offsets, d_symbols, d_dbn_ascii, d_scores, d_n_stems); });
+}
+
+static int sqrn_fast_predict_packed_device_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
                                                int32_t max_len, const int64_t *d_offsets, const uint8_t *d_packed,
                                                uint8_t *d_dbn_nib, int32_t *d_score_milli, uint16_t *d_n_stems, uint8_t *d_flags)
 {
@@ -737,6 +758,13 @@ extern "C" int sqrn_fast_predict_packed_device(sqrn_ctx *ctx, const sqrn_paramse
                          d_flags, d_counter, d_ovf, d_nc, 0, ctx->ev0, ctx->ev1, nullptr, &pk);
     if (rc == SQRN_OK) ctx->ev_valid = true;
     return rc;
+}
+
+extern "C" int sqrn_fast_predict_packed_device(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, int64_t total_len,
+                                               int32_t max_len, const int64_t *d_offsets, const uint8_t *d_packed,
+                                               uint8_t *d_dbn_nib, int32_t *d_score_milli, uint16_t *d_n_stems, uint8_t *d_flags)
+{
+    return guarded(ctx, [&] { return sqrn_fast_predict_packed_device_impl(ctx, ps, n_seqs, total_len, max_len, d_offsets, d_packed, d_dbn_nib, d_score_milli, d_n_stems, d_flags); });
 }
 
 // Host buffers in, host buffers out.  The batch is cut into chunks that flow through three
@@ -977,7 +1005,7 @@ extern "C" int sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps, in
 {
     if (!ctx || !ps || !offsets || n_seqs < 0 || n_seqs > 0x7fffffff) return SQRN_E_BADARG;
     FastIO io; io.off64 = offsets; io.symbols = symbols; io.dbn = dbn_ascii; io.scores = scores; io.n_stems = n_stems;
-    return fast_predict_host_impl(ctx, ps, n_seqs, io);
+    return guarded(ctx, [&] { return fast_predict_host_impl(ctx, ps, n_seqs, io); });
 }
 
 extern "C" int sqrn_fast_predict_packed_host(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_t n_seqs, const uint32_t *offsets,
@@ -986,7 +1014,7 @@ extern "C" int sqrn_fast_predict_packed_host(sqrn_ctx *ctx, const sqrn_paramset 
 {
     if (!ctx || !ps || !offsets || !score_milli || n_seqs < 0 || n_seqs > 0x7fffffff) return SQRN_E_BADARG;
     FastIO io; io.off32 = offsets; io.symbols = packed; io.dbn = dbn_nib; io.milli = score_milli; io.ns16 = n_stems; io.flags = flags;
-    return fast_predict_host_impl(ctx, ps, n_seqs, io);
+    return guarded(ctx, [&] { return fast_predict_host_impl(ctx, ps, n_seqs, io); });
 }
 
 extern "C" int sqrn_fast_last_flags(const sqrn_ctx *ctx, int64_t n_seqs, uint8_t *flags)
@@ -1324,25 +1352,78 @@ static void pairs_to_codes(std::vector<std::pair<int, int>> pairs, int N, int8_t
 }
 
 // fn(b) for b in [0, n) on a few host threads (per-sequence bookkeeping of big batches: each b touches only its own
-// data).  Exceptions never leave a worker; a thread that cannot be started just leaves its share to the others.
+// data).  The workers are started once per process and sleep between jobs (a pool round posts three jobs; starting
+// fifteen threads for each cost as much as it saved).  Exceptions never leave a worker: they are reported by the caller.
+namespace {
+struct HostPool {
+    std::vector<std::thread> th;
+    std::mutex mu; std::condition_variable cv_job, cv_done;
+    std::function<void()> job; uint64_t generation = 0; int pending = 0; bool stop = false;
+    HostPool()
+    {
+        int nt = (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min(nt, 16));
+        try { for (int t = 1; t < nt; t++) th.emplace_back([this] { loop(); }); } catch (...) {}
+    }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> g(mu); stop = true; }
+        cv_job.notify_all();
+        for (auto &x : th) x.join();
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv_job.wait(g, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation; f = job;
+            }
+            f();
+            { std::lock_guard<std::mutex> g(mu); if (--pending == 0) cv_done.notify_all(); }
+        }
+    }
+    // every worker and the caller run f once (f pulls its share from a shared counter)
+    void run(const std::function<void()> &f)
+    {
+        { std::lock_guard<std::mutex> g(mu); job = f; pending = (int)th.size(); generation++; }
+        cv_job.notify_all();
+        f();
+        std::unique_lock<std::mutex> g(mu);
+        cv_done.wait(g, [&] { return pending == 0; });
+    }
+};
+std::mutex g_pool_guard;              // one job at a time (contexts of several GPUs may call from several host threads)
+std::atomic<bool> g_forked(false);    // a fork()ed child has no workers: it runs its jobs on the calling thread
+// (never destroyed: the workers end with the process; a destructor would have to join threads a forked child does not have)
+HostPool &host_pool()
+{
+    static HostPool *p = [] { pthread_atfork(nullptr, nullptr, [] { g_forked.store(true); }); return new HostPool; }();
+    return *p;
+}
+}  // namespace
+
 template <class F>
 static void parallel_for(int64_t n, F &&fn)
 {
-    int nt = (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(nt, 16));
-    if (n < 64 || nt == 1) { for (int64_t b = 0; b < n; b++) fn(b); return; }
+    if (n < 64 || g_forked.load()) { for (int64_t b = 0; b < n; b++) fn(b); return; }
+    std::unique_lock<std::mutex> only(g_pool_guard, std::try_to_lock);
+    if (!only.owns_lock()) { for (int64_t b = 0; b < n; b++) fn(b); return; }      // (another GPU's host thread has the workers)
     std::atomic<int64_t> next(0);
-    auto work = [&] {
-        for (;;) {
-            const int64_t b0 = next.fetch_add(16);
-            if (b0 >= n) break;
-            for (int64_t b = b0; b < std::min(n, b0 + 16); b++) fn(b);
-        }
-    };
-    std::vector<std::thread> th;
-    try { for (int t = 1; t < nt; t++) th.emplace_back(work); } catch (...) {}
-    work();
-    for (auto &x : th) x.join();
+    std::atomic<bool> failed(false);
+    host_pool().run([&] {
+        try {
+            for (;;) {
+                const int64_t b0 = next.fetch_add(16);
+                if (b0 >= n || failed.load()) break;
+                for (int64_t b = b0; b < std::min(n, b0 + 16); b++) fn(b);
+            }
+        } catch (...) { failed.store(true); }          // (out of host memory in a worker: reported by the calling thread)
+    });
+    if (failed.load()) throw std::bad_alloc();
 }
 
 // ------------------------------------------------------------ full G path
@@ -1390,7 +1471,7 @@ static int copy_result(sqrn_ctx *ctx, sqrn_result *out)
     return SQRN_OK;
 }
 
-extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps, const sqrn_batch *in, sqrn_result *out)
+static int sqrn_predict_batch_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps, const sqrn_batch *in, sqrn_result *out)
 {
     if (!ctx || !out) return SQRN_E_BADARG;
     cudaSetDevice(ctx->device);
@@ -1716,6 +1797,11 @@ extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_
     return copy_result(ctx, out);
 }
 
+extern "C" int sqrn_predict_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, int n_ps, const sqrn_batch *in, sqrn_result *out)
+{
+    return guarded(ctx, [&] { return sqrn_predict_batch_impl(ctx, ps, n_ps, in, out); });
+}
+
 // ------------------------------------------------- alignment step 1 on the device
 // SQRNdbnali (ali.py:211-242) sums the score of every stem of every sequence into the cells of its base pairs, sequence
 // after sequence -- and float64 addition order is observable.  Here every CTA owns a band of matrix ROWS and walks the
@@ -1778,7 +1864,7 @@ __global__ void k_cells_rank(int m, const double *__restrict__ mat, const int32_
     }
 }
 
-extern "C" int sqrn_stem_matrix_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, double *matrix,
+static int sqrn_stem_matrix_batch_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, double *matrix,
                                       double threshold, int64_t cap_cells, int64_t *n_cells, int32_t *cells)
 {
     if (!ctx || !ps || !in || !matrix || !n_cells) return SQRN_E_BADARG;
@@ -1834,8 +1920,14 @@ extern "C" int sqrn_stem_matrix_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, co
     return SQRN_OK;
 }
 
+extern "C" int sqrn_stem_matrix_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, double *matrix,
+                                      double threshold, int64_t cap_cells, int64_t *n_cells, int32_t *cells)
+{
+    return guarded(ctx, [&] { return sqrn_stem_matrix_batch_impl(ctx, ps, in, matrix, threshold, cap_cells, n_cells, cells); });
+}
+
 // ------------------------------------------------------------- YieldStems
-extern "C" int sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, sqrn_stems *out)
+static int sqrn_yield_stems_batch_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, sqrn_stems *out)
 {
     if (!ctx || !out) return SQRN_E_BADARG;
     cudaSetDevice(ctx->device);
@@ -1876,11 +1968,16 @@ extern "C" int sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, co
     return SQRN_OK;
 }
 
+extern "C" int sqrn_yield_stems_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, sqrn_stems *out)
+{
+    return guarded(ctx, [&] { return sqrn_yield_stems_batch_impl(ctx, ps, in, out); });
+}
+
 // ------------------------------------------------------------- test seam
 // One launch of the work kernel on host buffers, any mode: lets the GPU tests
 // check AnnotateStems / OptimalStems seams against the oracle with arbitrary
 // pre-selected stems.  Same argument meaning as the DevWork fields.
-extern "C" int sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, int mode, int n_items,
+static int sqrn_debug_run_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, int mode, int n_items,
                               const int32_t *item_seq, const int64_t *init_off, const int32_t *init_stems,
                               const double *item_subopt, const int64_t *out_cap, int32_t *out_stems, int32_t *out_n,
                               double *out_fin, double *out_raw, uint8_t *out_flags, int8_t *dbn_code, int min_ccap)
@@ -1909,4 +2006,12 @@ extern "C" int sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn
     if (out_flags && !W.flags.empty()) memcpy(out_flags, W.flags.data(), W.flags.size());
     if (dbn_code && !W.dbn.empty()) memcpy(dbn_code, W.dbn.data(), W.dbn.size());
     return SQRN_OK;
+}
+
+extern "C" int sqrn_debug_run(sqrn_ctx *ctx, const sqrn_paramset *ps, const sqrn_batch *in, int mode, int n_items,
+                              const int32_t *item_seq, const int64_t *init_off, const int32_t *init_stems,
+                              const double *item_subopt, const int64_t *out_cap, int32_t *out_stems, int32_t *out_n,
+                              double *out_fin, double *out_raw, uint8_t *out_flags, int8_t *dbn_code, int min_ccap)
+{
+    return guarded(ctx, [&] { return sqrn_debug_run_impl(ctx, ps, in, mode, n_items, item_seq, init_off, init_stems, item_subopt, out_cap, out_stems, out_n, out_fin, out_raw, out_flags, dbn_code, min_ccap); });
 }
