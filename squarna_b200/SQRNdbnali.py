@@ -37,8 +37,15 @@ def _yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=N
             return _seq.run_sharded(lambda sub, dev: _yield_many(sub, bpweights, interchainonly, minlen, minbpscore, dev),
                                     entries, [len(e[0]) for e in entries], devs, exponent=2.0)
         device = devs[0]
-    preps = []
     gap_bytes = np.frombuffer("".join(sorted(GAPS)).encode("latin-1"), dtype=np.uint8)
+    ps = dict(algorithms={"G"}, bpp=0.0, bpweights=bpweights, suboptmax=1.0, suboptmin=1.0, suboptsteps=1.0,
+              minlen=minlen, minbpscore=minbpscore, minfinscorefactor=1.0, distcoef=0.0, bracketweight=-2.0,
+              orderpenalty=0.0, loopbonus=0.0, maxstemnum=1e6)
+    if matrix is not None and len(entries) >= 16 and all(len(e[0]) == matrix[0] for e in entries):
+        batch = _rows_batch(entries, matrix[0], gap_bytes, interchainonly)
+        if batch is not None:
+            return _seq.get_context(device).stem_matrix(ps, batch, matrix[1])
+    preps = []
     for seq, reacts, rests in entries:
         seq = seq.upper().replace("T", "U")                           # ali.py:65
         if not rests:
@@ -87,15 +94,75 @@ def _yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=N
                         interchainonly=interchainonly,
                         cols=[p[4] for p in preps] if matrix is not None else None,
                         ali_len=matrix[0] if matrix is not None else 0)
-    ps = dict(algorithms={"G"}, bpp=0.0, bpweights=bpweights, suboptmax=1.0, suboptmin=1.0, suboptsteps=1.0,
-              minlen=minlen, minbpscore=minbpscore, minfinscorefactor=1.0, distcoef=0.0, bracketweight=-2.0,
-              orderpenalty=0.0, loopbonus=0.0, maxstemnum=1e6)
     if matrix is not None:
         # the whole of step 1 on the device: stems, the sequence-ordered sum into the L x L matrix, the cells MatrixToDBNs
         # walks (sqrn_stem_matrix_batch); matrix = (alignment length, score threshold)
         return _seq.get_context(device).stem_matrix(ps, batch, matrix[1])
     out = _seq.get_context(device).yield_stems(ps, batch)
     return [(p[4], st, sc) for p, (st, sc) in zip(preps, out)]
+
+
+def _rows_batch(entries, L, gap_bytes, interchainonly):
+    """The rows of an alignment as one CSR batch without a Python loop over the rows: UnAlign (ali.py:70-82) is a column
+    selection per row, a restraint line shared by the rows is parsed once in aligned coordinates (a pair survives in a row
+    when both of its columns hold a symbol there: seq.py:236-255), reactivity lists shared by the rows are indexed by column.
+    None: the rows differ in their restraint lines or reactivity lists in a way this path does not cover."""
+    n = len(entries)
+    rest_lines = {e[2] if e[2] else None for e in entries}
+    if len(rest_lines) > 1:
+        return None
+    rests = next(iter(rest_lines))
+    react_ids = {id(e[1]) if e[1] else 0 for e in entries}
+    if len(react_ids) > 1:
+        first = next(e[1] for e in entries if e[1])
+        if not all(e[1] == first for e in entries if e[1]) or any(not e[1] for e in entries):
+            return None
+    reacts = next((e[1] for e in entries if e[1]), None)
+    text = "".join(e[0].upper().replace("T", "U") for e in entries)
+    raw = np.frombuffer(text.encode("latin-1", "replace"), dtype=np.uint8)
+    if raw.size != n * L:
+        return None
+    raw = raw.reshape(n, L)
+    mask = ~np.isin(raw, gap_bytes)
+    lens = mask.sum(axis=1)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    rows_idx, cols_flat = np.nonzero(mask)                      # row-major: the CSR order
+    symbols = raw[mask]
+    kw = {}
+    if rests is not None and rests.count('.') != len(rests):
+        if len(rests) != L:
+            return None
+        idx = np.cumsum(mask, axis=1, dtype=np.int32) - 1       # ungapped index of every column, per row
+        pairs = np.array(DBNToPairs(rests), dtype=np.int64).reshape(-1, 2)
+        cls_line = np.zeros(L, np.uint8)
+        for k, ch in enumerate(rests):
+            if ch in '_+':
+                cls_line[k] = 1
+            elif ch == '/':
+                cls_line[k] = 2
+            elif ch == '\\':
+                cls_line[k] = 4
+        if len(pairs):
+            alive = mask[:, pairs[:, 0]] & mask[:, pairs[:, 1]]  # n x P
+            r_, p_ = np.nonzero(alive)
+            rbps = np.stack([idx[r_, pairs[p_, 0]], idx[r_, pairs[p_, 1]]], axis=1).astype(np.int32)
+            rb_off = np.zeros(n + 1, np.int64)
+            np.cumsum(alive.sum(axis=1), out=rb_off[1:])
+        else:
+            rbps, rb_off = np.zeros((0, 2), np.int32), np.zeros(n + 1, np.int64)
+        kw["restr_class"] = cls_line[cols_flat]
+        kw["rbps"] = (rb_off, rbps)
+    if reacts is not None:
+        arr = np.asarray(reacts, dtype=np.float64)
+        if arr.shape != (L,):
+            return None
+        if bool((arr != 0.5).any()):
+            values, inv = np.unique(arr, return_inverse=True)
+            kw["react_codes"] = inv.astype(np.uint16)[cols_flat]
+            kw["react_values"] = np.ascontiguousarray(values, np.float64)
+    return PackedBatch((symbols, offsets), interchainonly=interchainonly, cols=cols_flat.astype(np.int32), ali_len=L,
+                       flat=True, **kw)
 
 
 def YieldStems(seq, reactivities=None, restraints=None,

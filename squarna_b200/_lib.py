@@ -164,14 +164,25 @@ class PackedBatch:
     def __init__(self, seqs, react_codes=None, react_values=None, react_comp=False, restr_class=None,
                  rbps=None, smat=None, cols=None, interchainonly=False, hardrest=False, rankbydiff=False,
                  poollim=1000, conslim=1, max_structs=0, rankby=(0, 2, 1), priority_mask=0,
-                 bpp_terms=None, bpp_mode=0, ali_len=0):
+                 bpp_terms=None, bpp_mode=0, ali_len=0, flat=False):
+        """flat=True: the batch is already in CSR form -- seqs = (symbols uint8, offsets int64) and react_codes / restr_class /
+        cols are single arrays over all positions, rbps = (rbp_offsets int64, pairs int32 (k, 2))"""
         self.seqs = seqs
-        self.symbols, self.offsets = pack_sequences(seqs)
-        n = len(seqs)
+        if flat:
+            self.symbols, self.offsets = np.ascontiguousarray(seqs[0], np.uint8), np.ascontiguousarray(seqs[1], np.int64)
+            if self.symbols.size == 0:
+                self.symbols = np.zeros(1, np.uint8)
+            n = len(self.offsets) - 1
+        else:
+            self.symbols, self.offsets = pack_sequences(seqs)
+            n = len(seqs)
 
         def cat(lst, dt):
             if lst is None:
                 return None
+            if flat:
+                a = np.ascontiguousarray(lst, dtype=dt).ravel()
+                return a if a.size else np.zeros(1, dt)
             arrs = [np.asarray(x, dtype=dt).ravel() for x in lst]
             tot = sum(a.size for a in arrs)
             return np.concatenate(arrs) if tot else np.zeros(1, dt)
@@ -180,7 +191,10 @@ class PackedBatch:
         self.react_values = None if react_values is None else np.ascontiguousarray(react_values, np.float64)
         self.restr_class = cat(restr_class, np.uint8)
         self.rbp_offsets = self.rbps = None
-        if rbps is not None:
+        if rbps is not None and flat:
+            self.rbp_offsets = np.ascontiguousarray(rbps[0], np.int64)
+            self.rbps = cat(rbps[1], np.int32)
+        elif rbps is not None:
             self.rbp_offsets = np.zeros(n + 1, dtype=np.int64)
             np.cumsum([len(x) for x in rbps], out=self.rbp_offsets[1:])
             self.rbps = cat(rbps, np.int32)

@@ -612,3 +612,48 @@ def test_packed_format_host_converters():
             nib[base + (p >> 1)] |= v << (4 * (p & 1))
             want[int(off[b]) + p] = ord(glyph[v])
     assert bytes(_lib.unpack_dbn(off, nib)) == bytes(want)
+
+
+def test_alignment_rows_batch_equals_the_per_row_preparation(monkeypatch):
+    """SQRNdbnali._rows_batch (the rows of an alignment as one CSR batch, no Python loop over rows) hands the device the
+    same arrays as the per-row preparation: symbols, offsets, columns, restraint classes, surviving restraint pairs,
+    reactivity values -- with gaps, a shared restraint line with nested / crossing brackets and a shared reactivity list"""
+    import random
+    import numpy as np
+    import workloads
+    from squarna_b200 import SQRNdbnali as A
+    rows, _ = workloads.config4(40, 90, 120, seed=3)
+    L = len(rows[0])
+    rng = random.Random(1)
+    rest = [rng.choice("....._/\\+") for _ in range(L)]
+    for i, j, o, c in [(5, 100, '(', ')'), (6, 99, '(', ')'), (20, 60, '[', ']'), (30, 80, '(', ')'), (31, 79, '(', ')')]:
+        rest[i], rest[j] = o, c
+    rest = "".join(rest)
+    reacts = [round(rng.random(), 2) for _ in range(L)]
+    gap = np.frombuffer("".join(sorted(S.GAPS)).encode(), np.uint8)
+    captured = {}
+
+    class Ctx:
+        def stem_matrix(self, ps, batch, thr):
+            captured["b"] = batch
+
+    monkeypatch.setattr(S, "get_context", lambda device=0: Ctx())
+    weights = {"GC": 3.25, "AU": 2.0, "GU": -1.0}
+    for ents in ([(r, None, None) for r in rows], [(r, reacts, rest) for r in rows], [(r, None, rest) for r in rows],
+                 [(r, reacts, None) for r in rows]):
+        fast = A._rows_batch(ents, L, gap, False)
+        assert fast is not None
+        with monkeypatch.context() as m:
+            m.setattr(A, "_rows_batch", lambda *a: None)
+            A._yield_many(ents, weights, False, 2, 4.5, device=0, matrix=(L, 10.0))
+        slow = captured["b"]
+        for name in ("symbols", "offsets", "cols", "restr_class", "rbp_offsets", "rbps"):
+            a, b = getattr(fast, name), getattr(slow, name)
+            if a is None or b is None:
+                assert (a is None or not np.any(a)) and (b is None or not np.any(b)), name
+                continue
+            assert np.array_equal(np.asarray(a).ravel(), np.asarray(b).ravel()), name
+        if fast.react_code is not None or slow.react_code is not None:
+            assert np.array_equal(fast.react_values[fast.react_code], slow.react_values[slow.react_code])
+    # rows with different restraint lines are left to the per-row path
+    assert A._rows_batch([(rows[0], None, rest), (rows[1], None, "." * L)] * 8, L, gap, False) is None
