@@ -16,6 +16,7 @@ import os
 import sys
 import threading
 
+import functools
 import re
 
 import numpy as np
@@ -184,6 +185,14 @@ def ProcessReacts(reacts, missing_threshold=-10, middle=0.5, reverse=False, M=1.
 
 def EncodedReactivities(seq, reacts, reactformat):
     """list of floats -> reactivity line (seq.py:82-101)"""
+    line = _reactivity_line(tuple(reacts), reactformat)       # (the default line of an alignment is shared by its rows)
+    if len(line) == len(seq) and not any(ch in seq for ch in SEPS):
+        return line
+    return ''.join(seq[k] if seq[k] in SEPS else line[k] for k in range(len(seq)))
+
+
+@functools.lru_cache(maxsize=256)
+def _reactivity_line(reacts, reactformat):
     clipped = [min(max(x, 0), 1) if x == x else 1 for x in reacts]
     if reactformat == 3:
         line = ''.join("_+##"[int(x * 3)] for x in clipped)
@@ -191,12 +200,19 @@ def EncodedReactivities(seq, reacts, reactformat):
         line = ''.join("01234567899"[int(x * 10)] for x in clipped)
     else:
         line = ''.join("abcdefghijklmnopqrstuvwxyz"[int(x * 25 + 0.5)] for x in clipped)
-    return ''.join(seq[k] if seq[k] in SEPS else line[k] for k in range(len(seq)))
+    return line
 
 
 def DBNToPairs(dbn):
     """dbn string -> sorted list of (i, j); one stack per bracket type, closing
-    brackets without a partner are ignored (seq.py:172-207)."""
+    brackets without a partner are ignored (seq.py:172-207).  (The same line is parsed again and again -- the reference
+    structure and the restraint line of an alignment by every row: the pairs of the last few thousand distinct strings are
+    kept; callers get their own list.)"""
+    return list(_dbn_pairs(dbn))
+
+
+@functools.lru_cache(maxsize=4096)
+def _dbn_pairs(dbn):
     stacks = {}
     pairs = set()
     # only bracket characters matter: a regular expression finds them (restraint lines are mostly dots)
@@ -209,7 +225,7 @@ def DBNToPairs(dbn):
         k = _CLOSE_IDX[ch]
         if stacks.get(k):
             pairs.add((stacks[k].pop(), pos))
-    return sorted(pairs)
+    return tuple(sorted(pairs))
 
 
 def _pair_levels(pairs):
