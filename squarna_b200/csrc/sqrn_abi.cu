@@ -1573,49 +1573,59 @@ static int sqrn_predict_batch_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int n
             lap(t_scatter);
         }
         lap(t_gather);
-        // tail phase: every remaining structure runs to completion on its own
+        // tail phase: every remaining structure runs to completion on its own (items and results per sequence, on the
+        // host threads)
         {
             HostWork W; W.mode = MODE_TAIL; W.base = &base;
-            std::vector<std::pair<int, int>> owner;
-            W.init_off.push_back(0);
+            std::vector<int64_t> item0((size_t)nseq + 1, 0), stem0((size_t)nseq + 1, 0);
             for (int64_t b = 0; b < nseq; b++) {
-                Pool &pl = pools[b];
-                if (!pl.tail) continue;
-                for (size_t q = 0; q < pl.cur.size(); q++) {
-                    W.item_seq.push_back((int32_t)b);
-                    for (auto &s : pl.cur[q]) { W.init_stems.push_back(s.i); W.init_stems.push_back(s.j); W.init_stems.push_back(s.len); }
-                    W.init_off.push_back((int64_t)W.init_stems.size() / 3);
-                    W.out_cap.push_back(D.len[b] / 2 + 1);
-                    owner.emplace_back((int)b, (int)q);
-                }
+                const Pool &pl = pools[b];
+                int64_t ni = 0, ns = 0;
+                if (pl.tail) { ni = (int64_t)pl.cur.size(); for (auto &st : pl.cur) ns += (int64_t)st.size(); }
+                item0[b + 1] = item0[b] + ni; stem0[b + 1] = stem0[b] + ns;
             }
-            if (!owner.empty()) {
+            const int64_t n_it = item0[nseq];
+            if (n_it > 0) {
+                W.item_seq.resize((size_t)n_it); W.out_cap.resize((size_t)n_it);
+                W.init_off.resize((size_t)n_it + 1); W.init_stems.resize((size_t)stem0[nseq] * 3);
+                W.init_off[(size_t)n_it] = stem0[nseq];
+                parallel_for(nseq, [&](int64_t b) {
+                    if (item0[b + 1] == item0[b]) return;
+                    const Pool &pl = pools[b];
+                    int64_t k = item0[b], so = stem0[b];
+                    for (size_t q = 0; q < pl.cur.size(); q++, k++) {
+                        W.item_seq[(size_t)k] = (int32_t)b; W.out_cap[(size_t)k] = D.len[b] / 2 + 1;
+                        W.init_off[(size_t)k] = so;
+                        for (auto &st : pl.cur[q]) { W.init_stems[3 * (size_t)so] = st.i; W.init_stems[3 * (size_t)so + 1] = st.j; W.init_stems[3 * (size_t)so + 2] = st.len; so++; }
+                    }
+                });
                 TRY(run_items(ctx, P, D, W));
                 // finalisation order inside the tail: by round (= stems added), structures that hit
                 // maxstemnum before those that ran dry, then pool order (seq.py:1168-1196)
                 struct Key { int round, kind, idx; size_t item; };
-                std::vector<std::vector<Key>> keys((size_t)nseq);
-                for (size_t k = 0; k < owner.size(); k++) {
-                    int b = owner[k].first;
-                    int n0 = (int)pools[b].cur[owner[k].second].size(), n1 = W.out_n[k];
-                    int kind = ((double)n1 == P.maxstemnum) ? 0 : 1;
-                    keys[b].push_back(Key{ n1 - n0, kind, owner[k].second, k });
-                }
-                for (int64_t b = 0; b < nseq; b++) {
-                    auto &kv = keys[b];
+                parallel_for(nseq, [&](int64_t b) {
+                    if (item0[b + 1] == item0[b]) return;
+                    Pool &pl = pools[b];
+                    std::vector<Key> kv;
+                    kv.reserve((size_t)(item0[b + 1] - item0[b]));
+                    for (int64_t k = item0[b]; k < item0[b + 1]; k++) {
+                        const int q = (int)(k - item0[b]);
+                        const int n0 = (int)pl.cur[(size_t)q].size(), n1 = W.out_n[(size_t)k];
+                        kv.push_back(Key{ n1 - n0, ((double)n1 == P.maxstemnum) ? 0 : 1, q, (size_t)k });
+                    }
                     std::stable_sort(kv.begin(), kv.end(), [](const Key &x, const Key &y) {
                         if (x.round != y.round) return x.round < y.round;
                         if (x.kind != y.kind) return x.kind < y.kind;
                         return x.idx < y.idx; });
                     for (auto &key : kv) {
-                        std::vector<Stem3> st;
+                        std::vector<Stem3> st((size_t)W.out_n[key.item]);
                         for (int q = 0; q < W.out_n[key.item]; q++) {
                             const int32_t *o = &W.out_stems[3 * (W.out_off[key.item] + q)];
-                            st.push_back(Stem3{ o[0], o[1], o[2] });
+                            st[(size_t)q] = Stem3{ o[0], o[1], o[2] };
                         }
-                        pools[b].fin.push_back(std::move(st));
+                        pl.fin.push_back(std::move(st));
                     }
-                }
+                });
             }
         }
         lap(t_tail);
@@ -1641,17 +1651,27 @@ static int sqrn_predict_batch_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int n
     // ScoreStruct + dbn of every unique structure on the device (MODE_FINAL)
     {
         HostWork W; W.mode = MODE_FINAL; W.want_dbn = true;
-        W.init_off.push_back(0);
-        for (int64_t b = 0; b < nseq; b++)
-            for (auto &S : uniq[b]) {
-                W.item_seq.push_back((int32_t)b);
-                for (auto &s : S.stems) { W.init_stems.push_back(s.i); W.init_stems.push_back(s.j); W.init_stems.push_back(s.len); }
-                W.init_off.push_back((int64_t)W.init_stems.size() / 3);
-                W.out_cap.push_back(0);
-            }
-        TRY(run_items(ctx, ps[0], D, W));
         std::vector<size_t> first((size_t)nseq + 1, 0);
-        for (int64_t b = 0; b < nseq; b++) first[b + 1] = first[b] + uniq[b].size();
+        std::vector<int64_t> stem0((size_t)nseq + 1, 0);
+        for (int64_t b = 0; b < nseq; b++) {
+            first[b + 1] = first[b] + uniq[b].size();
+            int64_t ns = 0;
+            for (auto &S : uniq[b]) ns += (int64_t)S.stems.size();
+            stem0[b + 1] = stem0[b] + ns;
+        }
+        const size_t n_it = first[(size_t)nseq];
+        W.item_seq.resize(n_it); W.out_cap.assign(n_it, 0);
+        W.init_off.resize(n_it + 1); W.init_stems.resize((size_t)stem0[nseq] * 3);
+        W.init_off[n_it] = stem0[nseq];
+        parallel_for(nseq, [&](int64_t b) {
+            size_t k = first[b]; int64_t so = stem0[b];
+            for (auto &S : uniq[b]) {
+                W.item_seq[k] = (int32_t)b; W.init_off[k] = so;
+                for (auto &st : S.stems) { W.init_stems[3 * (size_t)so] = st.i; W.init_stems[3 * (size_t)so + 1] = st.j; W.init_stems[3 * (size_t)so + 2] = st.len; so++; }
+                k++;
+            }
+        });
+        TRY(run_items(ctx, ps[0], D, W));
         parallel_for(nseq, [&](int64_t b) {
             size_t k = first[b];
             for (auto &S : uniq[b]) {
