@@ -1893,7 +1893,11 @@ static int sqrn_stem_matrix_batch_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, c
     ctx->n_launches = 0; ctx->n_calls = 0; ctx->kernel_ms = 0; ctx->n_cluster_launches = 0;
     const int L = in->smat_L;
     const int64_t nseq = in->n_seqs, total = in->offsets[nseq];
-    for (int64_t k = 0; k < total; k++) if (in->cols[k] < 0 || in->cols[k] >= L) { ctx->err = "column out of range"; return SQRN_E_BADARG; }
+    for (int64_t b = 0; b < nseq; b++)                 // columns of a row: inside the alignment, strictly increasing
+        for (int64_t k = in->offsets[b]; k < in->offsets[b + 1]; k++)
+            if (in->cols[k] < 0 || in->cols[k] >= L || (k > in->offsets[b] && in->cols[k] <= in->cols[k - 1])) {
+                ctx->err = "stem matrix: the column map of a row must be strictly increasing and inside the alignment"; return SQRN_E_BADARG;
+            }
     DeviceBatch D;
     TRY(upload_batch(ctx, in, D));
     HostWork W; W.mode = MODE_YIELD; W.keep_on_device = true;
