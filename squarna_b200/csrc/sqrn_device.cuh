@@ -212,7 +212,10 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     if (planes <= 0) planes = npc;
     int o = 0;
     // ---- the lists (doubles first: 8-byte aligned)
-    L.o_cbps = o;    o += 8 * Ccap;
+    // (global-list kernels, pcap < 0: cbps only holds one int per thread -- the record that was its best -- and ckey the
+    //  per-warp screen / evaluate lists; clen and the staging ring of the base-list sweep are not used)
+    const bool gl = pcap < 0;
+    L.o_cbps = o;    o += gl ? align_up(4 * 32 * (tw > 0 ? tw : 1), 8) : 8 * Ccap;
     L.o_ckey = o;    o += 4 * Ccap;
     // run list; without a persistent list the level scratch (cc, gsz, perm, grp) is only live between
     // two scans and shares its space
@@ -223,7 +226,7 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     L.o_rkey = o;    L.o_rlen = o + 4 * L.Rcap;
     L.o_cc = o;      L.o_gsz = o + 4 * L.Scap;  L.o_perm = o + 8 * L.Scap;  L.o_grp = o + 10 * L.Scap;
     o += uni;
-    L.o_clen = o;    o += 2 * Ccap;
+    L.o_clen = o;    o += gl ? 0 : 2 * Ccap;
     L.o_pbps = 0;    L.o_pkey = pcap > 0 ? 8 * pcap : 0;
     if (pcap > 0) {
         if (o < 12 * pcap) o = 12 * pcap;
@@ -263,7 +266,7 @@ __host__ __device__ constexpr Layout make_layout(int Nmax, int RBmax, int Ccap, 
     o = align_up(o, 4);
     L.o_glx = o;     o += (pcap < 0 || tw != 1) ? 4 * (3 * 256 + 4) : 0;   // binned lists: histogram, bin ends, scatter cursors (gl_make_bins)
     o = align_up(o, 16);
-    L.o_stage = o;   o += tw > 1 ? 16 + 2 * 16 * 32 * tw : 0;             // base-list sweep: two mbarriers + two tiles of T 16-byte records (cp.async.bulk)
+    L.o_stage = o;   o += (tw > 1 && !gl) ? 16 + 2 * 16 * 32 * tw : 0;             // base-list sweep: two mbarriers + two tiles of T 16-byte records (cp.async.bulk)
     L.total = align_up(o, 16);
     return L;
 }

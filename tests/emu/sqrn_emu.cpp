@@ -73,7 +73,12 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     W.ovf_list = ovf.data(); W.ovf_count = &n_ovf;
     for (int pass = 0; pass < 2; pass++) {
     const int todo = pass == 0 ? n_items : n_ovf;
-    if (pass == 1) { if (flavour == 3) flavour = 1; else if (flavour == 4 || flavour == 5) flavour = 2; }
+    if (pass == 1) {
+        // (the product redoes overflowed items with another kernel and that kernel's own layout: the global-list layout
+        //  has no room for the lists of the rescanning pass)
+        if (flavour == 5) { Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, 0); free(smem); smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16); }
+        if (flavour == 3) flavour = 1; else if (flavour == 4 || flavour == 5) flavour = 2;
+    }
     for (int q = 0; q < todo; q++) {
         const int item = pass == 0 ? q : ovf[q];
         State S = bind_state(smem, Lay);
