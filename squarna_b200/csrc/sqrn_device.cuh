@@ -2348,37 +2348,56 @@ __device__ int gl_make_bins(State &S, const GList &g)
 }
 
 // Enumerates the maximal runs of the current structure state into the global list, binned by their static
-// bound (two enumeration passes: histogram, scatter).  false: overflow.
+// bound: ONE enumeration writes the records, unsorted, into the second half of the slot; a count pass and a scatter
+// pass over those records (chunks dealt statically, so that a cluster's CTAs scatter what they counted) put them in
+// bin order into the first half.  false: overflow.
 template <class C>
 __device__ bool gl_build(State &S, const DevParams &P, const DevBatch &B, const GList &g, GState &gs)
 {
     constexpr int TW = C::TW;
     const int r = Team<TW>::rank(), T = Team<TW>::T;
     int *np = C::CLUSTER ? &g.cnt[0] : &S.misc[8];        // records in the list
+    GEnt *ent2 = g.ent + g.cap; double *bps2 = g.bps + g.cap; uint8_t *qb2 = g.qb + g.cap;
+    if (gl_leader<C>(S)) *np = 0;
     #pragma unroll 1
     for (int q = r; q < GL_NBIN; q += T) S.ghist[q] = 0;
-    Team<TW>::sync();
-    gl_enum<C>(S, P, B, [&](int s, int a, int len) {
-        double pos;
-        run_score_pos<C>(S, P, B, s, a, len, pos);
-        if (!(pos >= P.minbpscore)) return;
-        atomicAdd(&S.ghist[gl_bin(P, gl_ub0(S, P, s, a, len, pos))], 1);
-    });
-    const int n = gl_make_bins<C>(S, g);
-    gs.n_sorted = n; gs.n_inc = n; gs.half = 0; gs.since = 0;
-    ((int *)S.cbps)[r] = -1;                          // gl_step: no remembered best yet
-    if (gl_leader<C>(S)) *np = n;
-    if (n > g.cap) { gl_sync<C>(); return false; }
+    gl_sync<C>();
     gl_enum<C>(S, P, B, [&](int s, int a, int len) {
         double pos;
         const double sc = run_score_pos<C>(S, P, B, s, a, len, pos);
         if (!(pos >= P.minbpscore)) return;
-        const int q = gl_bin(P, gl_ub0(S, P, s, a, len, pos));
-        const int slot = atomicAdd(&S.gcur[q], 1);
-        gl_store(&g.ent[slot], ((uint32_t)s << 16) | (uint32_t)a, (uint32_t)len | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
-        g.bps[slot] = sc;
-        g.qb[slot] = (uint8_t)q;
+        const int slot = atomicAdd(np, 1);
+        if (slot < g.cap) {
+            gl_store(&ent2[slot], ((uint32_t)s << 16) | (uint32_t)a, (uint32_t)len | ((sc >= P.minbpscore ? GS_FRESH : GS_BELOW) << 16), 0.0);
+            bps2[slot] = sc;
+            qb2[slot] = (uint8_t)gl_bin(P, gl_ub0(S, P, s, a, len, pos));
+        }
     });
+    gl_sync<C>();
+    const int n0 = *(volatile int *)np;
+    gs.n_sorted = n0; gs.n_inc = n0; gs.half = 0; gs.since = 0;
+    ((int *)S.cbps)[r] = -1;                          // gl_step: no remembered best yet
+    if (n0 > g.cap) { gl_sync<C>(); return false; }
+    const int lane = gl_lane();
+    const int nw = TW > 0 ? TW : 1;
+    const int gw = C::CLUSTER ? S.doffset * nw + gl_wid() : gl_wid(), gnw = C::CLUSTER ? S.dstride * nw : nw;
+    #pragma unroll 1
+    for (int c0 = gw * GL_WL; c0 < n0; c0 += gnw * GL_WL) {
+        const int c = c0 + lane;
+        if (c < n0) atomicAdd(&S.ghist[qb2[c]], 1);
+    }
+    gl_make_bins<C>(S, g);
+    #pragma unroll 1
+    for (int c0 = gw * GL_WL; c0 < n0; c0 += gnw * GL_WL) {
+        const int c = c0 + lane;
+        if (c < n0) {
+            const GEnt e = gl_load(&ent2[c]);
+            const int q = qb2[c];
+            const int slot = atomicAdd(&S.gcur[q], 1);
+            gl_store(&g.ent[slot], e.key, e.meta, e.v);
+            g.bps[slot] = bps2[c]; g.qb[slot] = (uint8_t)q;
+        }
+    }
     gl_sync<C>();
     return true;
 }
