@@ -114,12 +114,12 @@ k_work(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
 // Long sequences, run to completion (MODE_TAIL): CTA teams over the persistent candidate list in
 // global memory (gl_build / gl_step): one enumeration per sequence, cached adjusted scores.  Items
 // whose list overflows its slot go to DevWork::ovf_list and are redone by k_work<TW> behind it.
-template <int TW>
+template <int TW, bool SIMPLE = false>
 __global__ void __launch_bounds__(TW * 32, TW == 8 ? 4 : 1)
 k_long(const DevParams *__restrict__ Pg, DevBatch B, DevWork Wk, Layout L)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    work_loop<Cfg<TW, false, false, MODE_TAIL, -1, false, true>>(Pg, B, Wk, L, smem);
+    work_loop<Cfg<TW, false, false, MODE_TAIL, -1, false, true, SIMPLE ? 2 : -1>>(Pg, B, Wk, L, smem);
 }
 
 // Fast lane (`byseq pl=1` shape): one warp per sequence, plain sequences (no reactivities,
@@ -420,6 +420,7 @@ template <int TW>
 static int plan_glist_t(sqrn_ctx *ctx, Plan &pl)
 {
     CK(cudaFuncSetAttribute(k_long<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_g));
+    if (TW == 8) CK(cudaFuncSetAttribute(k_long<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_g));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_long<TW>, TW * 32, pl.smem_g));
     if (nb < 1) return SQRN_E_UNSUPPORTED;
@@ -610,7 +611,11 @@ static int dispatch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t
         unsigned long long *d_stat = nullptr;
         if (trace) { TRY(dalloc(ctx, W_GSTAT, 16, &d_stat)); CK(cudaMemsetAsync(d_stat, 0, 16 * sizeof(unsigned long long), st)); W1.g_stat = d_stat; }
         W1.ovf_count = cnt; W1.ovf_list = ovf;
-        if (pl.tw == 8) k_long<8><<<gg, 256, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
+        // (lists of a few thousand records -- 256-thread CTAs on parameter sets with minlen >= 3, or short sequences: the
+        //  flavour that sweeps the whole list every pass; its smaller code keeps four CTAs per SM inside the instruction cache)
+        static const bool no_simple = getenv("SQRN_NO_LONG_SIMPLE") != nullptr;
+        if (pl.tw == 8 && !no_simple && pl.gcap <= 24576) k_long<8, true><<<gg, 256, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
+        else if (pl.tw == 8) k_long<8><<<gg, 256, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
         else k_long<32><<<gg, 1024, pl.smem_g, st>>>(P.d_p, B, W1, pl.Lg);
         CK(cudaGetLastError());
         DevWork W2 = W; W2.order = ovf; W2.n_items_dev = cnt; W2.counter = cnt + 1;

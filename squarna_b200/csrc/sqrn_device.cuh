@@ -364,6 +364,9 @@ struct Cfg {
     static constexpr int TW = TW_, MODE = MODE_, IO = IO_;
     static constexpr bool PLAIN = PLAIN_, STDP = STDP_, CLUSTER = CLUSTER_, PERSIST = PERSIST_;
     static constexpr bool GLIST = PERSIST_ && (GLIST_ < 0 ? (TW_ > 1) : (GLIST_ != 0));
+    // GLIST_ == 2: every pass sweeps the whole list (no prefix rounds, no catch-up, no rebuild): for lists of a few thousand
+    // records, where that machinery buys nothing and its code costs instruction-cache hits (four CTAs per SM)
+    static constexpr bool GL_SIMPLE = GLIST_ == 2;
     static constexpr bool RUNLIST = RUNLIST_ < 0 ? (TW_ == 1) : (RUNLIST_ != 0);
 };
 
@@ -2647,7 +2650,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
 
     // ---- rebuild: everything up to date, dead records dropped, survivors re-binned into the other half
     const int period = g.rebuild > 0 ? g.rebuild : GL_REBUILD;
-    if (ul > 0 && gs.since >= period) {
+    if (!C::GL_SIMPLE && ul > 0 && gs.since >= period) {
 #ifdef SQRN_HOST_EMU
         g_emu_gl_rebuilds++;
 #endif
@@ -2745,8 +2748,8 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
     for (;;) {
         // as far as the floor known so far asks for, but no further than four times what has been swept (a weak
         // early floor must not drag the whole list in: the next round will know better); whole bins
-        int target = fb.fin > -1e300 ? S.gbend[gl_bin(P, fb.fin)] : ns;
-        {
+        int target = (fb.fin > -1e300 && !C::GL_SIMPLE) ? S.gbend[gl_bin(P, fb.fin)] : ns;
+        if (!C::GL_SIMPLE) {
             const int want = done > 0 ? 4 * done : (gs.n_inc > 16 * T && gs.n_inc < ns ? gs.n_inc : 16 * T);     // (first round: what the last pass needed)
             if (target > want) {
                 int q = 0, qh = GL_NBIN - 1;               // the highest bin q with gbend[q] >= want (gbend falls with q)
@@ -2776,7 +2779,7 @@ __device__ Best gl_step(State &S, const DevParams &P, const DevBatch &B, const G
                 const int v = v0_ + u * GL_WL + lane;
                 const int c = v < span ? done + v : ns + (v - span);
                 GEnt e = buf[u];
-                const uint32_t st = revise(c, e, v < span && c >= gs.n_inc);
+                const uint32_t st = revise(c, e, !C::GL_SIMPLE && v < span && c >= gs.n_inc);
                 if (st == GS_EVAL) offer(e.v, e.key, (int)(e.meta & 0xffffu), c);
                 push(wa, na, wants_look(st, e), c);
                 if (na >= GL_WL) drain(false);

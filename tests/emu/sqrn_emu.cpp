@@ -46,9 +46,9 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     W.item_subopt = item_subopt; W.out_off = out_off; W.out_stems = out_stems; W.out_nstems = out_nstems;
     W.out_stemfin = out_stemfin; W.out_raw = out_raw; W.out_flags = out_flags; W.dbn_off = dbn_off;
     W.out_dbn_ascii = dbn_ascii; W.out_dbn_code = dbn_code; W.n_calls = n_calls; W.region_mode = region_mode;
-    Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, (flavour == 3 || flavour == 4) ? pcap : (flavour == 5 ? -1 : 0));
+    Layout Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, (flavour == 3 || flavour == 4) ? pcap : ((flavour == 5 || flavour == 8) ? -1 : 0));
     std::vector<GEnt> ge; std::vector<double> gb; std::vector<uint8_t> gq;
-    if (flavour == 5) {            // global persistent list with cached scores (what CTA teams run), capacity pcap (two halves)
+    if (flavour == 5 || flavour == 8) {            // global persistent list with cached scores (what CTA teams run), capacity pcap (two halves)
         ge.resize(2 * (size_t)pcap + 2); gb.resize(2 * (size_t)pcap + 2); gq.resize(2 * (size_t)pcap + 2);
         W.g_ent = ge.data(); W.g_bps = gb.data(); W.g_qb = gq.data(); W.g_cap = pcap;
         W.g_rebuild = sqrn::g_emu_gl_rebuild_every;
@@ -76,8 +76,8 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
     if (pass == 1) {
         // (the product redoes overflowed items with another kernel and that kernel's own layout: the global-list layout
         //  has no room for the lists of the rescanning pass)
-        if (flavour == 5) { Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, 0); free(smem); smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16); }
-        if (flavour == 3) flavour = 1; else if (flavour == 4 || flavour == 5) flavour = 2;
+        if (flavour == 5 || flavour == 8) { Lay = make_layout(nmax, rbmax, ccap, H.p.npc, 0, 0, 1, 1, 0, 0); free(smem); smem = (unsigned char *)aligned_alloc(16, (size_t)Lay.total + 16); }
+        if (flavour == 3) flavour = 1; else if (flavour == 4 || flavour == 5 || flavour == 8) flavour = 2;
     }
     for (int q = 0; q < todo; q++) {
         const int item = pass == 0 ? q : ovf[q];
@@ -90,10 +90,11 @@ extern "C" int emu_run(const sqrn_paramset *ps, int64_t n_seqs, const int64_t *o
             team_run_item<Cfg<0, true, true, MODE_TAIL, 1, false, true>>(S, H.p, B, W, Lay, item);
         } else if (flavour == 4) team_run_item<Cfg<0, false, false, -1, 1, false, true>>(S, H.p, B, W, Lay, item);   // general flavour, persistent list
         else if (flavour == 5) team_run_item<Cfg<0, false, false, -1, 0, false, true, 1>>(S, H.p, B, W, Lay, item);   // global list
+        else if (flavour == 8) team_run_item<Cfg<0, false, false, -1, 0, false, true, 2>>(S, H.p, B, W, Lay, item);   // global list, whole-list sweeps
         else if (flavour == 2) team_run_item<Cfg<0, false, false, -1, 1>>(S, H.p, B, W, Lay, item);   // run-list scan
         else team_run_item<Cfg<0>>(S, H.p, B, W, Lay, item);                                              // per-thread rounds
     }
-    if (flavour != 3 && flavour != 4 && flavour != 5) break;
+    if (flavour != 3 && flavour != 4 && flavour != 5 && flavour != 8) break;
     }
     free(smem);
     return 0;

@@ -38,9 +38,9 @@ def _prep_batch(cases):
 
 
 @pytest.mark.parametrize("region", [0, 1, 2, "fast", "runlist", "persist", "persist-small", "persist-general", "glist", "glist-small",
-                                    "base", "base-small"],
+                                    "base", "base-small", "glist-simple"],
                          ids=["auto", "scan", "stems", "fastflavour", "runlist", "persist", "persist-smalllist", "persist-general",
-                              "glist", "glist-smalllist", "base-list", "base-list-overflow"])
+                              "glist", "glist-smalllist", "base-list", "base-list-overflow", "glist-whole-list-sweeps"])
 @pytest.mark.parametrize("ps,ccap", [(T.FASTEST, 128), (T.DEFG1, 128), (T.DEFG2, 16), (T.ALI, 64)],
                          ids=["fastest", "defG1", "defG2-smalllist", "ali"])
 def test_tail_plain(ps, ccap, region):
@@ -63,6 +63,8 @@ def test_tail_plain(ps, ccap, region):
         r = emu.run(ps, seqs, ccap=ccap, flavour=5, pcap=1 << 16)
     elif region == "glist-small":
         r = emu.run(ps, seqs, ccap=ccap, flavour=5, pcap=600)
+    elif region == "glist-simple":    # k_long<8, simple>: the list swept whole every pass (small lists)
+        r = emu.run(ps, seqs, ccap=ccap, flavour=8, pcap=1 << 16)
     elif region == "base":     # what the tails of pools run: every step sweeps the sequence's base list
         r = emu.run(ps, seqs, ccap=ccap, flavour=6, pcap=1 << 16)
     elif region == "base-small":      # slots too small for the longer sequences: those enumerate as before
@@ -79,7 +81,8 @@ def test_tail_plain(ps, ccap, region):
         assert bool(r["flags"][b] & 1) == isint
 
 
-@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2), (0, 4), (0, 5), (0, 6)], ids=["scan", "stems", "runlist", "persist", "glist", "base-list"])
+@pytest.mark.parametrize("region,flavour", [(1, 0), (2, 0), (0, 2), (0, 4), (0, 5), (0, 6), (0, 8)],
+                         ids=["scan", "stems", "runlist", "persist", "glist", "base-list", "glist-whole-list-sweeps"])
 @pytest.mark.parametrize("interchain", [False, True])
 def test_tail_with_restraints_and_reactivities(interchain, region, flavour):
     rng = random.Random(32)
