@@ -194,7 +194,11 @@ SQRN_API int  sqrn_stem_matrix_batch(sqrn_ctx *ctx, const sqrn_paramset *ps, con
  * context's stream).  scores: 3 doubles per sequence (total, structscore,
  * reactscore; ScoreStruct, SQRNdbnseq.py:899), rounded as round(x,3) by the host
  * variant and unrounded by the device variant.  The host variant pipelines the
- * batch in chunks: host->device copy, kernel and device->host copy overlap.    */
+ * batch in chunks: host->device copy, kernel and device->host copy overlap; a
+ * chunk that mixes sequences of <= 320 symbols with longer ones is dealt to two
+ * launches (warp teams / CTA teams), so any mix of lengths may be passed in any
+ * order.  The device variants run ONE kernel chosen from max_len: group
+ * resident batches by length class (<= 128, 224, 320, longer).                 */
 SQRN_API int  sqrn_fast_predict_host(sqrn_ctx *ctx, const sqrn_paramset *ps,
                             int64_t n_seqs, const int64_t *offsets, const uint8_t *symbols,
                             uint8_t *dbn_ascii, double *scores, int32_t *n_stems);

@@ -208,6 +208,7 @@ struct sqrn_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool ev_valid = false;
     cudaEvent_t ev_start = nullptr, ev_out = nullptr, ev_k2done = nullptr;
     cudaEvent_t ev_in[FAST_MAX_CHUNKS] = {}, ev_k0[FAST_MAX_CHUNKS] = {}, ev_k1[FAST_MAX_CHUNKS] = {}, ev_o[FAST_MAX_CHUNKS] = {};
+    cudaEvent_t ev_l0[FAST_MAX_CHUNKS] = {}, ev_l1[FAST_MAX_CHUNKS] = {};   // the CTA-team launch of a chunk of mixed lengths
     uint8_t *hflags = nullptr; size_t hflags_cap = 0;                    // pinned staging for the result flags
     int32_t *horder = nullptr; size_t horder_cap = 0;                   // pinned: processing order of the fast-lane chunks
     Plan fast_plans[3]; bool fast_plan_ok[3] = {false, false, false};   // the three length classes of the fast kernels
@@ -282,6 +283,7 @@ extern "C" int sqrn_ctx_create(int device, sqrn_ctx **out)
     for (int c = 0; c < FAST_MAX_CHUNKS && ok; c++)
         ok = cudaEventCreateWithFlags(&ctx->ev_in[c], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreate(&ctx->ev_k0[c]) == cudaSuccess && cudaEventCreate(&ctx->ev_k1[c]) == cudaSuccess &&
+             cudaEventCreate(&ctx->ev_l0[c]) == cudaSuccess && cudaEventCreate(&ctx->ev_l1[c]) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_o[c], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { g_create_err = std::string("context creation failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return SQRN_E_CUDA; }
     cudaDeviceProp prop;
@@ -304,7 +306,7 @@ extern "C" void sqrn_ctx_destroy(sqrn_ctx *ctx)
     cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_k2);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_out); cudaEventDestroy(ctx->ev_k2done);
-    for (int c = 0; c < FAST_MAX_CHUNKS; c++) { cudaEventDestroy(ctx->ev_in[c]); cudaEventDestroy(ctx->ev_k0[c]); cudaEventDestroy(ctx->ev_k1[c]); cudaEventDestroy(ctx->ev_o[c]); }
+    for (int c = 0; c < FAST_MAX_CHUNKS; c++) { cudaEventDestroy(ctx->ev_in[c]); cudaEventDestroy(ctx->ev_k0[c]); cudaEventDestroy(ctx->ev_k1[c]); cudaEventDestroy(ctx->ev_o[c]); cudaEventDestroy(ctx->ev_l0[c]); cudaEventDestroy(ctx->ev_l1[c]); }
     if (ctx->hflags) cudaFreeHost(ctx->hflags);
     if (ctx->horder) cudaFreeHost(ctx->horder);
     delete ctx;
@@ -682,10 +684,10 @@ struct PackedOut { uint8_t *nib = nullptr; int32_t *milli = nullptr; uint16_t *n
 static int fast_launch(sqrn_ctx *ctx, const PEntry &P, const Plan &pl, cudaStream_t st, int64_t item_base, int64_t n_items,
                        const int64_t *d_offsets, const uint8_t *d_symbols, uint8_t *d_dbn_ascii, double *d_scores,
                        int32_t *d_n_stems, uint8_t *d_flags, int *d_counter, int32_t *d_ovf, unsigned long long *d_ncalls, int round3,
-                       cudaEvent_t e0, cudaEvent_t e1, const int32_t *d_order = nullptr, const PackedOut *pk = nullptr)
+                       cudaEvent_t e0, cudaEvent_t e1, const int32_t *d_order = nullptr, const PackedOut *pk = nullptr, int64_t n_batch = -1)
 {
     DevBatch B; memset(&B, 0, sizeof B);
-    B.n_seqs = item_base + n_items; B.off = d_offsets; B.sym = d_symbols; B.sym_packed = pk != nullptr;
+    B.n_seqs = n_batch >= 0 ? n_batch : item_base + n_items; B.off = d_offsets; B.sym = d_symbols; B.sym_packed = pk != nullptr;
     DevWork W; memset(&W, 0, sizeof W);
     W.n_items = (int)n_items; W.item_base = (int)item_base; W.mode = MODE_TAIL; W.region_mode = ctx->region_mode;
     W.round3 = round3; W.counter = d_counter; W.out_flags = d_flags; W.n_calls = d_ncalls;
@@ -863,34 +865,63 @@ static int fast_predict_host_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_
         ctx->horder_cap = (size_t)n_seqs + 64;
     }
     std::vector<int64_t> len_count;
+    bool split_chunk[FAST_MAX_CHUNKS] = {};
     const bool no_order = getenv("SQRN_FAST_NO_ORDER") != nullptr;
     for (int c = 0; c < nchunks; c++) {
         const int64_t b0 = bounds[c], b1 = bounds[c + 1];
         const int64_t t0 = OFF(b0), t1 = OFF(b1);
         cudaStream_t s_k = (c & 1) ? ctx->s_k2 : s_main;
-        // the chunk's longest sequence picks its kernel (scanned while the earlier chunks are in flight)
-        int max_len = 0;
+        // the chunk's longest sequence picks its kernel (scanned while the earlier chunks are in flight); a chunk that
+        // mixes sequences of up to 320 symbols with longer ones is dealt to two launches (warp teams / CTA teams)
+        int max_len = 0, short_max = 0;
+        int64_t n_long = 0;
         for (int64_t b = b0; b < b1; b++) {
             int64_t n = OFF(b + 1) - OFF(b);
             if (n < 0 || n > SQRN_MAX_LEN) { ctx->err = "sequence length out of range"; cudaDeviceSynchronize(); return SQRN_E_BADARG; }
             if (n > max_len) max_len = (int)n;
+            if (n > 320) n_long++; else if (n > short_max) short_max = (int)n;
         }
+        static const bool no_split = getenv("SQRN_FAST_NO_SPLIT") != nullptr;
+        const bool split = n_long > 0 && n_long < b1 - b0 && !no_split;
+        const int64_t n_short = split ? (b1 - b0) - n_long : 0;
         const PEntry *P;
         TRY(get_params(ctx, *ps, max_len, &P));
         const int cls = max_len <= 128 ? 0 : max_len <= 224 ? 1 : max_len <= 320 ? 2 : 3;
-        if (cls == 3 || !have_plan[cls]) { TRY(make_fast_plan(ctx, *P, max_len, (int)(b1 - b0), plans[cls])); have_plan[cls] = true; }
+        // (plans of the three short classes are kept for the call: they are laid out for the class limit, not this chunk's maximum)
+        static const int cls_cap[3] = {128, 224, 320};
+        if (cls == 3 || !have_plan[cls]) { TRY(make_fast_plan(ctx, *P, cls == 3 ? max_len : cls_cap[cls], (int)(split ? n_long : b1 - b0), plans[cls])); have_plan[cls] = true; }
         const Plan &pl = plans[cls];
-        // CTA-team plans share per-context scratch (candidate lists, counters): their chunks all go to one stream
-        if (pl.tw > 1) s_k = s_main;
-        // long sequences: longest first, so that the last CTAs to finish are not the longest items
-        // Longest first within the chunk (a counting sort by length, done while the earlier chunks run): the
-        // persistent CTAs of a chunk then finish on short items, so the SM slots the next chunk's kernel is
-        // waiting for free up together instead of trailing behind one long sequence each.
+        const int scls = short_max <= 128 ? 0 : short_max <= 224 ? 1 : 2;
+        if (split && !have_plan[scls]) { TRY(make_fast_plan(ctx, *P, cls_cap[scls], (int)n_short, plans[scls])); have_plan[scls] = true; }
+        // CTA-team plans share per-context scratch (candidate lists, counters): their launches all go to one stream
+        if (pl.tw > 1 && !split) s_k = s_main;
+        // Long sequences: longest first (a counting sort by length, done while the earlier chunks run), so that the
+        // last CTAs to finish are not the longest items and the SM slots the next chunk's kernel is waiting for
+        // free up together instead of trailing behind one long sequence each.
         const int32_t *d_order = nullptr;
         // (warp-team chunks are taken in input order: measured, the order list bought nothing there -- 11.3 ms either way per
         //  1 M sequences -- and cost the host 5 ms of counting sort per step plus 4 MB of copies)
         static const bool order_short = getenv("SQRN_FAST_ORDER_SHORT") != nullptr;
-        if (b1 - b0 > 1 && (pl.tw > 1 || (order_short && b1 - b0 >= 4096)) && !no_order) {
+        if (split) {
+            // [short items in input order | long items, longest first]
+            int32_t *ord = ctx->horder + b0;
+            len_count.assign((size_t)max_len + 2, 0);
+            int64_t ks = 0;
+            for (int64_t b = b0; b < b1; b++) {
+                const int64_t n = OFF(b + 1) - OFF(b);
+                if (n > 320) len_count[(size_t)(max_len - n) + 1]++; else ord[ks++] = (int32_t)b;
+            }
+            for (int l = 0; l <= max_len; l++) len_count[(size_t)l + 1] += len_count[(size_t)l];
+            for (int64_t b = b0; b < b1; b++) {
+                const int64_t n = OFF(b + 1) - OFF(b);
+                if (n > 320) ord[n_short + len_count[(size_t)(max_len - n)]++] = (int32_t)b;
+            }
+            int32_t *d_o;
+            TRY(dalloc(ctx, W_ORDER, (size_t)n_seqs, &d_o));
+            CK(cudaMemcpyAsync(d_o + b0, ord, (size_t)(b1 - b0) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_in));
+            d_order = d_o + b0;
+        }
+        else if (b1 - b0 > 1 && (pl.tw > 1 || (order_short && b1 - b0 >= 4096)) && !no_order) {
             int32_t *ord = ctx->horder + b0;      // pinned, one region per chunk: the copy below is truly asynchronous
             len_count.assign((size_t)max_len + 2, 0);
             for (int64_t b = b0; b < b1; b++) len_count[(size_t)(max_len - (OFF(b + 1) - OFF(b))) + 1]++;
@@ -916,6 +947,18 @@ static int fast_predict_host_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_
         // stage 2: kernel
         CK(cudaStreamWaitEvent(s_k, ctx->ev_in[c], 0));
         if (c == 1) CK(cudaStreamWaitEvent(s_k, ctx->ev_start, 0));
+        if (split) {
+            // the short items through their warp-team kernel on the chunk's stream, the long ones through CTA teams on the
+            // main stream (counter: the spare word of the chunk's four); the chunk's outputs wait for both
+            TRY(fast_launch(ctx, *P, plans[scls], s_k, b0, n_short, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + 4 * c, d_ovf, d_nc, 1,
+                            ctx->ev_k0[c], ctx->ev_k1[c], d_order, packed ? &pk : nullptr, b1));
+            if (s_k != s_main) CK(cudaStreamWaitEvent(s_main, ctx->ev_in[c], 0));
+            TRY(fast_launch(ctx, *P, pl, s_main, b0, n_long, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + 4 * c + 3, d_ovf, d_nc, 1,
+                            ctx->ev_l0[c], ctx->ev_l1[c], d_order + n_short, packed ? &pk : nullptr, b1));
+            CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_l1[c], 0));
+            split_chunk[c] = true;
+        }
+        else
         TRY(fast_launch(ctx, *P, pl, s_k, b0, b1 - b0, d_off, d_sym, d_dbn, d_sc, d_ns, d_flags, d_counter + 4 * c, d_ovf, d_nc, 1,
                         ctx->ev_k0[c], ctx->ev_k1[c], d_order, packed ? &pk : nullptr));
         // stage 3: outputs of the chunk
@@ -979,6 +1022,7 @@ static int fast_predict_host_impl(sqrn_ctx *ctx, const sqrn_paramset *ps, int64_
     for (int c = 0; c < nchunks; c++) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev_k0[c], ctx->ev_k1[c]) == cudaSuccess) ctx->kernel_ms += ms;
+        if (split_chunk[c] && cudaEventElapsedTime(&ms, ctx->ev_l0[c], ctx->ev_l1[c]) == cudaSuccess) ctx->kernel_ms += ms;
     }
     {
         unsigned long long c = 0;

@@ -67,6 +67,31 @@ def test_packed_lane_equals_byte_lane(gpu_ctx):
     _check_packed(gpu_ctx, T.FASTEST, T.rand_seqs(34, 300000, 60, 200))       # several pipeline chunks
 
 
+def test_fast_lane_mixed_lengths(gpu_ctx):
+    """a chunk that mixes warp-team lengths (<= 320) with longer sequences is dealt to two launches: every sequence
+    against the oracle, both boundary formats, the 320 / 321 edge, and several pipeline chunks against the two
+    groups predicted separately"""
+    rng = random.Random(77)
+    seqs = T.rand_seqs(71, 3000, 5, 200) + T.rand_seqs(72, 40, 321, 900) + T.rand_seqs(73, 3, 320, 320) + T.rand_seqs(74, 3, 321, 321)
+    rng.shuffle(seqs)
+    _check_fast(gpu_ctx, T.FASTEST, seqs)
+    _check_fast(gpu_ctx, T.DEFG1, seqs[:800])
+    _check_packed(gpu_ctx, T.FASTEST, seqs)
+    _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(75, 50, 400, 700) + ["GGGGAAAACCCC"])        # one short among long
+    _check_fast(gpu_ctx, T.FASTEST, T.rand_seqs(76, 500, 10, 120) + T.rand_seqs(77, 1, 2100, 2100))   # one rRNA-sized among short
+    big = T.rand_seqs(78, 200000, 60, 200)
+    for k, s in zip(rng.sample(range(len(big)), 60), T.rand_seqs(79, 60, 330, 700)):
+        big[k] = s
+    sym, off = pack_sequences(big)
+    dbn, scores, nst = gpu_ctx.fast_predict(T.FASTEST, sym, off)
+    for keep in (lambda s: len(s) <= 320, lambda s: len(s) > 320):
+        idx = [b for b, s in enumerate(big) if keep(s)]
+        sym1, off1 = pack_sequences([big[b] for b in idx])
+        dbn1, scores1, nst1 = gpu_ctx.fast_predict(T.FASTEST, sym1, off1)
+        assert (nst1 == nst[idx]).all() and (scores1 == scores[idx]).all()
+        assert bytes(dbn1) == b"".join(bytes(dbn[off[b]:off[b + 1]]) for b in idx)
+
+
 def test_packed_lane_flags_deep_pseudoknots(gpu_ctx):
     """more than 7 pseudoknot levels do not fit a 4-bit code: the sequence is flagged, the others are complete"""
     from squarna_b200 import _lib
