@@ -426,6 +426,7 @@ static int plan_glist_t(sqrn_ctx *ctx, Plan &pl)
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_long<TW>, TW * 32, pl.smem_g));
     if (nb < 1) return SQRN_E_UNSUPPORTED;
+    if (const char *e = getenv("SQRN_LONG_PER_SM")) nb = std::max(1, std::min(nb, atoi(e)));      // experiment: fewer resident CTAs
     pl.grid_g = nb * ctx->sm_count;
     return SQRN_OK;
 }
