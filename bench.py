@@ -675,7 +675,7 @@ def bench_config3(args, rank, world, local):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for c, b in batches:
-            ctx.predict_batch(psets[c], b)
+            ctx.predict_batch_flat(psets[c], b)          # (the flat arrays the C call filled: no per-structure Python objects)
     barrier()
     abi_s = (time.perf_counter() - t0) / args.steps
     sampler.stop_flag = True

@@ -231,6 +231,10 @@ SQRN_API int  sqrn_fast_predict_packed_device(sqrn_ctx *ctx, const sqrn_paramset
                             uint8_t *d_dbn_nib, int32_t *d_score_milli, uint16_t *d_n_stems, uint8_t *d_flags);
 SQRN_API int  sqrn_pack_symbols(int64_t n_total, const uint8_t *symbols, uint8_t *packed, int64_t *n_other);
 SQRN_API int  sqrn_unpack_dbn(int64_t n_seqs, const uint32_t *offsets, const uint8_t *dbn_nib, uint8_t *dbn_ascii);
+/* Level codes of sqrn_result::dbn / cons (+L opening, -L closing bracket of level L, 0 unpaired) -> the glyphs of
+ * PairsToDBN (SQRNdbnseq.py:142-143), threaded.  Levels 31..49 (Cyrillic brackets) come out as byte 0: the caller
+ * prints those structures itself; levels beyond the alphabet are '.', as in the reference.                            */
+SQRN_API int  sqrn_codes_to_ascii(int64_t n, const int8_t *codes, uint8_t *ascii);
 /* Per-sequence flags of the last sqrn_fast_predict_host call (bit 1: more than 30 pseudoknot levels, the ASCII
  * glyphs ran out).  When that call returns SQRN_E_UNSUPPORTED for this reason every OTHER sequence's result is valid:
  * the flagged ones go through sqrn_predict_batch, whose level codes have no such limit.                              */

@@ -353,6 +353,10 @@ for _lev in range(1, 128):
         _GLYPH32[256 - _lev] = ord(_CLOSE[_lev - 1])
 
 
+_GLYPH8 = np.where(_GLYPH32 < 128, _GLYPH32, 0).astype(np.uint8)      # 0: the glyph needs the wide table
+_GLYPH_TABLE = _GLYPH8.tobytes()           # the same table for bytes.translate
+
+
 def _codes_to_dbn(codes):
     """int8 level codes (+L open, -L close) -> glyph string"""
     return _GLYPH32[np.asarray(codes, dtype=np.int8).view(np.uint8)].tobytes().decode("utf-32-le")
@@ -371,7 +375,7 @@ def _metrics(pred, known):
 # ------------------------------------------------------------ batch front-end
 class _Prepared:
     """one sequence digested the way seq.py:1004-1037 does it"""
-    __slots__ = ("seq", "shortseq", "shortrest", "_sr", "rbps", "rclass", "_keep", "shortdbn",
+    __slots__ = ("seq", "shortseq", "shortrest", "_sr", "_rl", "rbps", "rclass", "_keep", "shortdbn",
                  "dbn", "compensated", "bppm", "bppm_key")
 
     @property
@@ -417,7 +421,7 @@ def _prepare(seq, reacts, restraints, dbn):
     """seq.py:1004-1037 for one entry.  The common shapes (no gaps, no restraints, encoded or absent
     reactivities) take vectorised paths; everything else goes through the reference's own steps."""
     p = _Prepared()
-    p.bppm = p.bppm_key = None
+    p.bppm = p.bppm_key = p._rl = None
     seq = seq.upper().replace("T", "U")                               # seq.py:1004
     n = len(seq)
     if restraints:
@@ -441,26 +445,22 @@ def _prepare(seq, reacts, restraints, dbn):
             p.shortseq, p.shortrest, p.rbps = seq, restraints, []    # no brackets: nothing for DBNToPairs
             p.rclass = _RC_BYTES[rraw]
         else:
-            p.shortseq, p.shortrest = UnAlign(seq, restraints)
-            rbps, rxs, rlefts, rrights = ParseRestraints(p.shortrest)
-            p.rbps = rbps
-            rc = np.zeros(max(len(p.shortseq), 1), dtype=np.uint8)
-            for k in rxs:
-                rc[k] |= 1
-            for k in rlefts:
-                rc[k] |= 2
-            for k in rrights:
-                rc[k] |= 4
-            p.rclass = rc[:len(p.shortseq)]
+            # the restraint classes of ParseRestraints (seq.py:370-376) are one table look-up per symbol; only the
+            # brackets need its parser
+            p.shortseq, p.shortrest = UnAlign(seq, restraints) if has_gaps else (seq, restraints)
+            p.rbps = DBNToPairs(p.shortrest)
+            p.rclass = _RC_BYTES[rraw[p._keep] if has_gaps else rraw]
     # --- reactivities ---------------------------------------------------------
     if not reacts:
         p._sr = None                                                  # all 0.5: "default reacts"
         p.compensated = True
     elif type(reacts) == str:
-        vals = _react_lut()[np.frombuffer(reacts.encode("latin-1", "replace"), dtype=np.uint8)]
+        letters = np.frombuffer(reacts.encode("latin-1", "replace"), dtype=np.uint8)
+        vals = _react_lut()[letters]
         if np.isnan(vals).any():
             raise KeyError(next(ch for ch in reacts if ch not in ReactDict))
         p._sr = vals[p._keep] if has_gaps else vals                   # numpy floats, like ProcessReacts' output
+        p._rl = letters[p._keep] if has_gaps else letters             # (their letters: _make_batch codes them without a sort)
         p.compensated = False
     else:
         keep = p._keep if has_gaps else range(n)
@@ -484,7 +484,26 @@ def _make_batch(preps, idx, comp, stemmatrix, interchainonly, bpp=None, **opts):
     """PackedBatch of the prepared entries idx (all with the same reactivity-sum mode `comp`)"""
     # distinct processed reactivities of the batch -> codes + value table (host pow() table in the library)
     codes = values = None
-    arrs = [None if preps[k]._sr is None else np.asarray(preps[k]._sr, dtype=np.float64) for k in idx]
+    if idx and all(preps[k]._sr is None or preps[k]._rl is not None for k in idx):
+        # letter-encoded (or absent) reactivities: the distinct values are those of the letters that occur -- the same
+        # sorted table and codes as below, from a histogram of the letters instead of a sort of every value
+        lens_ = [len(preps[k].shortseq) for k in idx]
+        letters = np.concatenate([np.zeros(n_, np.uint8) if preps[k]._rl is None else preps[k]._rl for k, n_ in zip(idx, lens_)])
+        seen = np.flatnonzero(np.bincount(letters, minlength=256))
+        cand = np.where(seen == 0, 0.5, _react_lut()[seen])           # byte 0 stands for "no reactivities": 0.5
+        if bool((cand != 0.5).any()):
+            values_bits, inv = np.unique(cand.view(np.uint64), return_inverse=True)
+            values = values_bits.view(np.float64)
+            table = np.zeros(256, np.uint16)
+            table[seen] = inv
+            coded = table[letters]
+            codes, o = [], 0
+            for n_ in lens_:
+                codes.append(coded[o:o + n_])
+                o += n_
+        arrs = []
+    else:
+        arrs = [None if preps[k]._sr is None else np.asarray(preps[k]._sr, dtype=np.float64) for k in idx]
     if any(a is not None and bool((a != 0.5).any()) for a in arrs):
         lens_ = [len(preps[k].shortseq) for k in idx]
         flat = np.concatenate([np.full(n_, 0.5) if a is None else a for a, n_ in zip(arrs, lens_)]) if idx else np.zeros(0)
@@ -735,7 +754,11 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
             return out
         return _predict_many_mixed(entries, paramsets, conslim, toplim, hardrest, rankbydiff, rankby,
                                    interchainonly, stemmatrix, poollim, priority, algos, device, levellimit, M, B)
+    import time
+    t_0 = time.perf_counter()
     preps = [_prepare(*e) for e in entries]
+    t_1 = time.perf_counter()
+    t_call = 0.0
     results = [None] * len(entries)
     if not gsets:
         todo = []
@@ -749,67 +772,86 @@ def predict_many(entries, paramsets, conslim=1, toplim=5, hardrest=False, rankby
         batch = _make_batch(preps, idx, comp, stemmatrix, interchainonly, hardrest=hardrest, rankbydiff=rankbydiff,
                             poollim=poollim, conslim=conslim, rankby=rankby,
                             priority_mask=sum(1 << gsets.index(p) for p in priority if p in gsets))
-        out = get_context(device).predict_batch([paramsets[g] for g in gsets], batch)
-        for k, o in zip(idx, out):
-            results[k] = (o[0], o[1], o[3] if len(o) > 3 else None)
+        t_c = time.perf_counter()
+        flat = get_context(device).predict_batch_flat([paramsets[g] for g in gsets], batch)
+        t_call += time.perf_counter() - t_c
+        for q, k in enumerate(idx):
+            results[k] = (flat, q)
 
+    # The reference's 4-tuple per entry.  With pl=100 a sequence has tens of structures: their texts come from one glyph
+    # gather and one decode per sequence, their score tuples straight from the flat result's columns.
+    t_2 = time.perf_counter()
+    inds_of = {}
     final = []
-    for k, p in enumerate(preps):
-        seq = p.seq
+    # (tens of thousands of small tuples and strings, none of them cyclic: the collector's generation scans over the
+    #  growing result cost 40 % of this loop, so it rests while the loop runs)
+    import gc
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        for k, p in enumerate(preps):
+            seq = p.seq
+            keep = p._keep
+            seps = ';' in seq or '&' in seq
+            width = len(seq)
+            if seps or keep is not None:
+                raw8 = np.frombuffer(seq.encode("latin-1", "replace"), dtype=np.uint8)
+                seppos = np.flatnonzero((raw8 == 59) | (raw8 == 38)) if seps else ()        # ';' '&'
 
-        raw = np.frombuffer(seq.encode("utf-32-le"), dtype=np.uint32)
-        seppos = np.flatnonzero((raw == ord(';')) | (raw == ord('&')))
-        keep = p._keep
+            def expand(codes2d):                       # glyphs + ReAlign + separators (seq.py:1239-1246), one row per structure
+                if keep is None and not seps:
+                    text = codes2d.tobytes().translate(_GLYPH_TABLE).decode("latin-1")
+                    if "\x00" not in text:
+                        return text
+                for table, wide, encoding in ((_GLYPH8, np.uint8, "latin-1"), (_GLYPH32, np.uint32, "utf-32-le")):
+                    g = np.take(table, codes2d.view(np.uint8))
+                    if keep is not None:
+                        long_ = np.full((len(g), width), 46, dtype=wide)
+                        long_[:, keep] = g
+                        g = long_
+                    if seps:
+                        g[:, seppos] = raw8[seppos]
+                    if wide is np.uint32 or bool(g.all()):          # (0: a level of the Cyrillic part of the alphabet)
+                        return g.tobytes().decode(encoding)
 
-        def expand(codes, raw=raw, seppos=seppos, keep=keep):     # glyphs + ReAlign + separators, seq.py:1239-1246
-            g = _GLYPH32[np.asarray(codes, dtype=np.int8).view(np.uint8)]
-            if keep is not None:
-                long_ = np.full(len(raw), ord('.'), dtype=np.uint32)
-                long_[keep] = g
-                g = long_
-            if len(seppos):
-                g = g.copy() if keep is None else g
-                g[seppos] = raw[seppos]
-            return g.tobytes().decode("utf-32-le")
-
-        if results[k] is None:
-            cons_codes, structs, codes2d = np.zeros(len(p.shortseq), np.int8), [], None
-        else:
-            cons_codes, structs, codes2d = results[k]
-        cons = expand(cons_codes)
-        texts = None
-        if codes2d is not None and len(structs) > 1:
-            # every structure of the sequence in one pass: glyphs, gap columns, separators, one decode
-            g = _GLYPH32[codes2d.view(np.uint8)]
-            if keep is not None:
-                long_ = np.full((len(structs), len(raw)), ord('.'), dtype=np.uint32)
-                long_[:, keep] = g
-                g = long_
-            if len(seppos):
-                g[:, seppos] = raw[seppos]
-            whole, width = g.tobytes().decode("utf-32-le"), len(raw)
-            texts = [whole[q * width:(q + 1) * width] for q in range(len(structs))]
-        preds = []
-        bpsets = []
-        for q, (codes, sc, isint, mask, stems) in enumerate(structs):
-            total, struct, react = sc
-            inds = [gsets[b] for b in range(len(gsets)) if mask >> b & 1]
-            preds.append((texts[q] if texts is not None else expand(codes), (total, 0 if isint else struct, react), inds))
-            bpsets.append(codes)
-        if p.dbn:                                # seq.py:1249-1285
-            known = set(DBNToPairs(p.shortdbn))
-            consresult = list(_metrics(set(DBNToPairs(_codes_to_dbn(cons_codes))), known))
-            best, result = -1, []
-            for rank, codes in enumerate(bpsets):
-                tp, fp, fn, fsc, prc, rcl = _metrics(set(DBNToPairs(_codes_to_dbn(codes))), known)
-                if fsc > best:
-                    best = fsc
-                    result = [tp, fp, fn, fsc, prc, rcl, rank + 1]
-                if rank + 1 >= toplim:
-                    break
-            final.append((cons, preds, consresult, result))
-        else:
-            final.append((cons, preds, [np.nan] * 6, [np.nan] * 7))
+            if results[k] is None:
+                cons_codes, c2, k0, k1, flat = np.zeros(len(p.shortseq), np.int8), None, 0, 0, None
+            else:
+                flat, q = results[k]
+                cons_codes, k0, k1 = flat.cons_codes(q), flat.so[q], flat.so[q + 1]
+                c2 = flat.codes2d(q) if k1 > k0 else None
+            cons = expand(cons_codes.reshape(1, -1))
+            preds = []
+            if c2 is not None:
+                whole = flat.text(q) if keep is None and not seps else None      # (the library's threaded glyph pass)
+                if whole is None or "\x00" in whole:
+                    whole = expand(c2)
+                for j, sc, isint, mask in zip(range(0, (k1 - k0) * max(width, 1), max(width, 1)), flat.scores[k0:k1],
+                                              flat.isint[k0:k1], flat.mask[k0:k1]):
+                    inds = inds_of.get(mask)
+                    if inds is None:
+                        inds = inds_of[mask] = [gsets[b] for b in range(len(gsets)) if mask >> b & 1]
+                    preds.append((whole[j:j + width], (sc[0], 0 if isint else sc[1], sc[2]), inds[:]))
+            if p.dbn:                                # seq.py:1249-1285
+                known = set(DBNToPairs(p.shortdbn))
+                consresult = list(_metrics(set(DBNToPairs(_codes_to_dbn(cons_codes))), known))
+                best, result = -1, []
+                for rank in range(k1 - k0):
+                    tp, fp, fn, fsc, prc, rcl = _metrics(set(DBNToPairs(_codes_to_dbn(c2[rank]))), known)
+                    if fsc > best:
+                        best = fsc
+                        result = [tp, fp, fn, fsc, prc, rcl, rank + 1]
+                    if rank + 1 >= toplim:
+                        break
+                final.append((cons, preds, consresult, result))
+            else:
+                final.append((cons, preds, [np.nan] * 6, [np.nan] * 7))
+    finally:
+        if gc_was_on:
+            gc.enable()
+    if os.environ.get("SQRN_TRACE") is not None:
+        print("[sqrn] predict_many: prepare %.3f s, pack %.3f s, library call %.3f s, assemble %.3f s (%d entries)"
+              % (t_1 - t_0, t_2 - t_1 - t_call, t_call, time.perf_counter() - t_2, len(entries)), file=sys.stderr)
     return final
 
 

@@ -22,7 +22,7 @@ EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx
            "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
            "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_ungap", "sqrn_text_format",
            "sqrn_fast_predict_packed_host", "sqrn_pack_symbols", "sqrn_unpack_dbn", "sqrn_fast_last_flags",
-           "sqrn_stem_matrix_batch", "sqrn_fast_predict_packed_device"]
+           "sqrn_stem_matrix_batch", "sqrn_fast_predict_packed_device", "sqrn_codes_to_ascii"]
 
 _lib = None
 
@@ -58,6 +58,7 @@ def load():
     L.sqrn_fast_predict_packed_device.argtypes = [vp, C.POINTER(ParamSet), i64, i64, i32, vp, vp, vp, vp, vp, vp]
     L.sqrn_pack_symbols.argtypes = [i64, vp, vp, C.POINTER(i64)]
     L.sqrn_unpack_dbn.argtypes = [i64, vp, vp, vp]
+    L.sqrn_codes_to_ascii.argtypes = [i64, vp, vp]
     L.sqrn_fast_last_flags.argtypes = [vp, i64, vp]
     L.sqrn_stem_matrix_batch.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), vp, C.c_double, i64, C.POINTER(i64), vp]
     L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
@@ -147,6 +148,18 @@ def pack_symbols(symbols):
     return packed, bad.value
 
 
+def codes_to_ascii(codes):
+    """int8 level codes (+L opening, -L closing bracket) -> glyph bytes (uint8, same shape); levels 31..49 -- the
+    Cyrillic brackets -- come out as 0 (include/sqrn.h); host only, threaded"""
+    L = load()
+    codes = np.ascontiguousarray(codes, dtype=np.int8)
+    out = np.empty(codes.shape, np.uint8)
+    rc = L.sqrn_codes_to_ascii(codes.size, ptr(codes), ptr(out))
+    if rc != OK:
+        raise SqrnError("sqrn_codes_to_ascii failed (%d)" % rc)
+    return out
+
+
 def unpack_dbn(offsets32, dbn_nib):
     """4-bit bracket codes of the packed lane -> ASCII dot-bracket bytes (uint8 [total]); host only"""
     L = load()
@@ -234,6 +247,98 @@ class PackedBatch:
             b.bpp_offsets = ptr(self.bpp_offsets)
             b.bpp_mode = int(bpp_mode)
         self.c = b
+
+
+class FlatResult:
+    """What one sqrn_predict_batch call returned (include/sqrn.h, sqrn_result), as the flat arrays it filled.
+    Sequence b of the batch has N = offsets[b+1] - offsets[b] positions and the structures so[b] .. so[b+1]-1 in rank
+    order; structure k has scores[k] = (total, structscore, reactscore), isint[k] (structscore is the int 0),
+    mask[k] (bit q: parameter set q predicted it), stems[sto[k]:sto[k+1]] and N level codes at dbn[dbo[k]:].
+    The offset / score columns are Python lists (one tolist() per array)."""
+
+    def __init__(self, offsets, so, scores, isint, mask, ntot, sto, stems, dbo, dbn, cons):
+        self.n = len(offsets) - 1
+        self.off = np.asarray(offsets).tolist()
+        self.so, self.sto, self.dbo = so.tolist(), sto.tolist(), dbo.tolist()
+        nk = self.so[-1] if self.n else 0
+        self.scores, self.isint, self.mask = scores[:nk].tolist(), isint[:nk].tolist(), mask[:nk].tolist()
+        self.ntot = ntot.tolist()
+        self.stems, self.dbn, self.cons = stems, dbn, cons
+        self._glyphs = None
+
+    def cons_codes(self, b):
+        return self.cons[self.off[b]:self.off[b + 1]]
+
+    def codes2d(self, b):
+        """level codes of every structure of sequence b as one (n_structs, N) int8 array (a view when the rows lie
+        back to back, which is how the library writes them)"""
+        N = self.off[b + 1] - self.off[b]
+        k0, k1 = self.so[b], self.so[b + 1]
+        if k1 == k0:
+            return np.zeros((0, N), np.int8)
+        d0 = self.dbo[k0]
+        if self.dbo[k1 - 1] - d0 == (k1 - k0 - 1) * N:
+            return self.dbn[d0:d0 + (k1 - k0) * N].reshape(k1 - k0, N)
+        return np.stack([self.dbn[self.dbo[k]:self.dbo[k] + N] for k in range(k0, k1)])
+
+    def text(self, b):
+        """the glyphs of every structure of sequence b, row after row in one str (n_structs * N characters), or None
+        when its rows do not lie back to back.  Byte 0 in it: a bracket beyond the ASCII part of the alphabet."""
+        N = self.off[b + 1] - self.off[b]
+        k0, k1 = self.so[b], self.so[b + 1]
+        if k1 == k0:
+            return ""
+        d0 = self.dbo[k0]
+        if self.dbo[k1 - 1] - d0 != (k1 - k0 - 1) * N:
+            return None
+        if self._glyphs is None:                  # the whole call's codes in one threaded pass
+            used = 0
+            for q in range(self.n):
+                if self.so[q + 1] > self.so[q]:
+                    used = max(used, self.dbo[self.so[q + 1] - 1] + self.off[q + 1] - self.off[q])
+            self._glyphs = codes_to_ascii(self.dbn[:used])
+        return str(memoryview(self._glyphs[d0:d0 + (k1 - k0) * N]), "latin-1")
+
+    def sequence(self, b):
+        """(cons_codes, [(codes, (total, struct, react), struct_is_int0, psmask, stems (k,3))], n_total, codes2d)"""
+        k0, k1 = self.so[b], self.so[b + 1]
+        c2 = self.codes2d(b) if k1 > k0 else None
+        sto, stems = self.sto, self.stems
+        structs = [(c2[k - k0], tuple(self.scores[k]), bool(self.isint[k]), self.mask[k], stems[sto[k]:sto[k + 1]])
+                   for k in range(k0, k1)]
+        return (self.cons_codes(b), structs, self.ntot[b], c2)
+
+    def per_sequence(self):
+        return [self.sequence(b) for b in range(self.n)]
+
+    @classmethod
+    def from_sequences(cls, seqs):
+        """the flat form of a per-sequence result list (what `per_sequence` returns; the 4th element may be missing)"""
+        n = len(seqs)
+        off = np.zeros(n + 1, np.int64)
+        np.cumsum([len(q[0]) for q in seqs], out=off[1:])
+        so = np.zeros(n + 1, np.int64)
+        np.cumsum([len(q[1]) for q in seqs], out=so[1:])
+        nk = int(so[-1])
+        scores, isint, mask = np.zeros((max(nk, 1), 3)), np.zeros(max(nk, 1), np.uint8), np.zeros(max(nk, 1), np.uint64)
+        sto, dbo = np.zeros(nk + 1, np.int64), np.zeros(max(nk, 1), np.int64)
+        stems, dbn = [], []
+        cons = np.concatenate([np.asarray(q[0], np.int8) for q in seqs]) if n else np.zeros(0, np.int8)
+        k = at = 0
+        for q in seqs:
+            for codes, sc, ii, m, st in q[1]:
+                scores[k], isint[k], mask[k] = sc, int(bool(ii)), m
+                dbo[k] = at
+                dbn.append(np.asarray(codes, np.int8))
+                at += len(dbn[-1])
+                st = np.asarray(st, np.int32).reshape(-1, 3)
+                stems.append(st)
+                sto[k + 1] = sto[k] + len(st)
+                k += 1
+        ntot = np.array([q[2] for q in seqs] if n else [0], np.int32)
+        return cls(off, so, scores, isint, mask, ntot, sto,
+                   np.concatenate(stems) if stems else np.zeros((0, 3), np.int32), dbo,
+                   np.concatenate(dbn) if dbn else np.zeros(0, np.int8), cons)
 
 
 class Context:
@@ -343,7 +448,13 @@ class Context:
     # ---- general path ---------------------------------------------------
     def predict_batch(self, paramsets, batch):
         """paramsets: list of dicts; batch: PackedBatch.  Returns per sequence a tuple
-        (cons_codes int8[N], [ (dbn_codes, (total, struct, react), struct_is_int0, psmask, stems (k,3)) ], n_total)"""
+        (cons_codes int8[N], [ (dbn_codes, (total, struct, react), struct_is_int0, psmask, stems (k,3)) ], n_total,
+        codes of all its structures as one (n_structs, N) array)"""
+        return self.predict_batch_flat(paramsets, batch).per_sequence()
+
+    def predict_batch_flat(self, paramsets, batch):
+        """the same call, the result left in the flat arrays the C ABI filled (FlatResult): callers that format many
+        structures per sequence (predict_many with pl=100: ~40) read them without one Python object per structure"""
         arr = paramsets if not isinstance(paramsets, (list, tuple)) else paramset_array(list(paramsets))
         nps = len(paramsets)
         n = len(batch.offsets) - 1
@@ -373,21 +484,7 @@ class Context:
                 continue
             self._check(rc)
             break
-        # per sequence: (consensus codes, [(codes, scores, is_int0, psmask, stems)], n_total, codes of all its structures as
-        # one (n_structs, N) array when they lie back to back).  Everything is a view of this call's arrays.
-        out = []
-        so_l, sto_l, dbo_l, off_l = so.tolist(), sto.tolist(), dbo.tolist(), batch.offsets.tolist()
-        sc_l, isint_l, mask_l, ntot_l = scores.tolist(), isint.tolist(), mask.tolist(), ntot.tolist()
-        for b in range(n):
-            N = off_l[b + 1] - off_l[b]
-            k0, k1 = so_l[b], so_l[b + 1]
-            codes2d = None
-            if k1 > k0 and dbo_l[k1 - 1] - dbo_l[k0] == (k1 - k0 - 1) * N:
-                codes2d = dbn[dbo_l[k0]:dbo_l[k0] + (k1 - k0) * N].reshape(k1 - k0, N)
-            structs = [(codes2d[k - k0] if codes2d is not None else dbn[dbo_l[k]:dbo_l[k] + N], tuple(sc_l[k]), bool(isint_l[k]),
-                        mask_l[k], stems[sto_l[k]:sto_l[k + 1]]) for k in range(k0, k1)]
-            out.append((cons[off_l[b]:off_l[b] + N], structs, ntot_l[b], codes2d))
-        return out
+        return FlatResult(batch.offsets, so, scores, isint, mask, ntot, sto, stems, dbo, dbn, cons)
 
     def yield_stems(self, paramset, batch):
         """AnnotateStems per sequence: list of (stems (k,3) int32, scores (k,) float64)"""

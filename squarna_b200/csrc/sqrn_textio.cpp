@@ -371,6 +371,25 @@ extern "C" int sqrn_pack_symbols(int64_t n_total, const uint8_t *symbols, uint8_
     return SQRN_OK;
 }
 
+extern "C" int sqrn_codes_to_ascii(int64_t n, const int8_t *codes, uint8_t *ascii)
+{
+    if (n < 0 || (n && (!codes || !ascii))) return SQRN_E_BADARG;
+    // PairsToDBN's bracket alphabet (SQRNdbnseq.py:142-143): level L opens with op[L-1] and closes with cl[L-1].  Its
+    // levels 31..49 are Cyrillic letters: those come out as byte 0 and the caller redoes that text in a wider
+    // encoding; levels beyond the alphabet print as '.'
+    static const char op[] = "([{<ABCDEFGHIJKLMNOPQRSTUVWXYZ", cl[] = ")]}>abcdefghijklmnopqrstuvwxyz";
+    uint8_t tab[256];
+    memset(tab, '.', sizeof tab);
+    for (int l = 1; l <= 49; l++) { tab[l] = l <= 30 ? (uint8_t)op[l - 1] : 0; tab[256 - l] = l <= 30 ? (uint8_t)cl[l - 1] : 0; }
+    const int nt = host_threads(n, 1 << 20);
+    auto fn = [&](int t) {
+        const int64_t k0 = n * t / nt, k1 = n * (t + 1) / nt;
+        for (int64_t k = k0; k < k1; k++) ascii[k] = tab[(uint8_t)codes[k]];
+    };
+    run_threads(nt, fn);
+    return SQRN_OK;
+}
+
 extern "C" int sqrn_unpack_dbn(int64_t n_seqs, const uint32_t *offsets, const uint8_t *dbn_nib, uint8_t *dbn_ascii)
 {
     if (n_seqs < 0 || (n_seqs && (!offsets || !dbn_nib || !dbn_ascii))) return SQRN_E_BADARG;

@@ -371,6 +371,10 @@ class _OracleContext:
                                for codes, sc, isint, psl, stems, *_ in structs], len(structs)))
         return out
 
+    def predict_batch_flat(self, paramsets, b):
+        from squarna_b200._lib import FlatResult
+        return FlatResult.from_sequences(self.predict_batch(paramsets, b))
+
 
 def _stand_in(monkeypatch):
     monkeypatch.setattr(S, "get_context", lambda device=0: _OracleContext())
@@ -657,3 +661,116 @@ def test_alignment_rows_batch_equals_the_per_row_preparation(monkeypatch):
             assert np.array_equal(fast.react_values[fast.react_code], slow.react_values[slow.react_code])
     # rows with different restraint lines are left to the per-row path
     assert A._rows_batch([(rows[0], None, rest), (rows[1], None, "." * L)] * 8, L, gap, False) is None
+
+
+def test_reactivity_letter_coding_equals_the_sorted_coding(monkeypatch):
+    """_make_batch codes letter-encoded reactivities from a histogram of the letters: the same value table and codes as
+    the sort over every processed value it replaces (gaps, '?', entries without reactivities included)"""
+    import random
+    import numpy as np
+    captured = {}
+    monkeypatch.setattr(S, "PackedBatch", lambda seqs, **kw: captured.update(kw=kw))
+    rng = random.Random(3)
+    letters = "abcdefghijklmnopqrstuvwxyz?"
+    for trial in range(40):
+        ents = []
+        for _ in range(rng.randint(1, 6)):
+            n = rng.randint(1, 60)
+            seq = "".join(rng.choice("ACGU-") for _ in range(n))
+            reacts = None if rng.random() < 0.3 else "".join(rng.choice(letters[:rng.randint(1, 27)]) for _ in range(n))
+            ents.append((seq, reacts, None, None))
+        preps = [S._prepare(*e) for e in ents]
+        for comp in (False, True):
+            idx = [k for k in range(len(preps)) if preps[k].compensated == comp]
+            if not idx:
+                continue
+            S._make_batch(preps, idx, comp, None, False)
+            fast = captured["kw"]
+            saved = [p._rl for p in preps]
+            for p in preps:
+                p._rl = None                                   # the general path: a sort over the values
+            S._make_batch(preps, idx, comp, None, False)
+            slow = captured["kw"]
+            for p, v in zip(preps, saved):
+                p._rl = v
+            assert (fast["react_values"] is None) == (slow["react_values"] is None)
+            if fast["react_values"] is not None:
+                assert np.array_equal(fast["react_values"].view(np.uint64), slow["react_values"].view(np.uint64))
+                assert all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(fast["react_codes"], slow["react_codes"]))
+
+
+def test_flat_result_round_trip():
+    """FlatResult: per_sequence() of the flat arrays, from_sequences() back, rows that do not lie back to back"""
+    import numpy as np
+    from squarna_b200._lib import FlatResult
+    rng = np.random.default_rng(5)
+    seqs = []
+    for n, ns in ((7, 3), (0, 0), (12, 1), (5, 0), (9, 4)):
+        structs = [(rng.integers(-3, 4, n).astype(np.int8), tuple(np.round(rng.random(3), 3).tolist()), bool(k & 1), int(k + 1),
+                    rng.integers(0, 9, (k, 3)).astype(np.int32)) for k in range(ns)]
+        seqs.append((rng.integers(-2, 3, n).astype(np.int8), structs, ns + 2))
+    flat = FlatResult.from_sequences(seqs)
+    back = flat.per_sequence()
+    assert len(back) == len(seqs)
+    for (cons, structs, ntot), (cons2, structs2, ntot2, c2) in zip(seqs, back):
+        assert np.array_equal(cons, cons2) and ntot == ntot2 and len(structs) == len(structs2)
+        assert (c2 is None) == (len(structs) == 0)
+        for q, ((codes, sc, ii, m, st), (codes2, sc2, ii2, m2, st2)) in enumerate(zip(structs, structs2)):
+            assert np.array_equal(codes, codes2) and np.array_equal(codes, c2[q]) and sc == sc2 and ii == ii2 and m == m2
+            assert np.array_equal(st, st2)
+    # rows of one sequence apart from each other: codes2d gathers them
+    flat.dbo[flat.so[4] + 2], flat.dbo[flat.so[4] + 3] = flat.dbo[flat.so[4] + 3], flat.dbo[flat.so[4] + 2]
+    c2 = flat.codes2d(4)
+    assert np.array_equal(c2[2], seqs[4][1][3][0]) and np.array_equal(c2[3], seqs[4][1][2][0])
+
+
+def test_predict_many_result_assembly(monkeypatch):
+    """predict_many's texts come from one glyph pass per sequence (the library's threaded converter, bytes.translate,
+    or numpy tables): against the per-character definition (PairsToDBN glyphs, ReAlign, separators; seq.py:1239-1246)
+    on gapped sequences, separators, the Cyrillic levels 31..49, levels beyond the alphabet, empty sequences"""
+    import numpy as np
+    from squarna_b200 import _lib
+    rng = np.random.default_rng(11)
+    seqs = ["GGGAAACCC", "GG-GA.AA~CC-C", "GGGA&AACC;C", "G-GG&AA-ACCC", "", "ACGUACGUACGUACGUACGU", "AC-GU&ACGUA"]
+    deep = {5: 35, 6: 49, 1: 60}                   # entry -> highest level used
+
+    class Ctx:
+        def predict_batch_flat(self, paramsets, batch):
+            out = []
+            off = np.asarray(batch.offsets)
+            for b in range(len(off) - 1):
+                n = int(off[b + 1] - off[b])
+                top = deep.get(b, 6)
+                structs = []
+                for q in range(3):
+                    codes = rng.integers(-top, top + 1, n).astype(np.int8)
+                    if n:
+                        codes[rng.integers(0, n)] = top if q == 0 else -top
+                    structs.append((codes, (float(q), 0.0 if q == 1 else q + 0.5, 0.25), q == 1, 1 + q, np.zeros((0, 3), np.int32)))
+                out.append((rng.integers(-2, 3, n).astype(np.int8), structs, 3))
+            Ctx.last = out
+            return _lib.FlatResult.from_sequences(out)
+
+    monkeypatch.setattr(S, "get_context", lambda device=0: Ctx())
+    from tests import common as T
+    ps = [dict(T.FASTEST, algorithms={"G"}) for _ in range(3)]
+    got = S.predict_many([(s, None, None, None) for s in seqs], ps, poollim=5, device=0)
+
+    def text(codes, seq):
+        glyphs = ["." if c == 0 or abs(c) > len(S._OPEN) else (S._OPEN[c - 1] if c > 0 else S._CLOSE[-c - 1]) for c in codes.tolist()]
+        out, k = [], 0                              # (a separator has a position in the ungapped sequence: its own symbol is printed)
+        for ch in seq.upper():
+            if ch in S.GAPS:
+                out.append(".")
+            else:
+                out.append(ch if ch in ";&" else glyphs[k])
+                k += 1
+        return "".join(out)
+
+    for seq, (cons, preds, m1, m2), (cons_codes, structs, _) in zip(seqs, got, Ctx.last):
+        assert cons == text(cons_codes, seq)
+        assert len(preds) == len(structs)
+        for (dbn, sc, inds), (codes, osc, isint, mask, _) in zip(preds, structs):
+            assert dbn == text(codes, seq), (seq, dbn, text(codes, seq))
+            assert sc == (osc[0], 0 if isint else osc[1], osc[2]) and type(sc[1]) is (int if isint else float)
+            assert inds == [b for b in range(3) if mask >> b & 1]
