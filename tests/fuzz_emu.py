@@ -1,0 +1,177 @@
+"""Randomised parity campaign (not collected by pytest: run it by hand, `python tests/fuzz_emu.py [seed] [rounds]`):
+the device code in single-thread host emulation (tests/emu) against the oracle under RANDOM parameter sets --
+pair weights, minlen 2..5, thresholds, distance / order / loop terms in and beyond the range of the shipped .conf
+files -- on sequences of several compositions, for every list flavour of the kernels.  Prints the first difference
+with everything needed to replay it.  tests/test_emu_vs_oracle.py::test_random_parameter_sets runs a seeded slice."""
+import random
+import sys
+
+from oracle import oracle as O
+from tests import common as T
+from tests.emu import emu
+
+FLAVOURS = [(0, 1, 0), (0, 2, 0), (2, 0, 0), (3, 0, 4096), (3, 0, 96), (4, 0, 4096), (5, 0, 1 << 16), (5, 0, 600),
+            (8, 0, 1 << 16), (6, 0, 1 << 16), (6, 0, 300)]       # (flavour, region_mode, pcap)
+
+
+def rand_paramset(rng):
+    gc = rng.choice([1.5, 2.0, 3.0, 3.25, 3.75, 4.0, 4.5])
+    au = rng.choice([0.25, 0.5, 1.0, 1.25, 2.0, 2.5])
+    gu = rng.choice([-2.0, -1.5, -1.25, -1.0, -0.5, 0.5, 1.0, 1.5])
+    return T._ps(bpweights={"GC": gc, "AU": au, "GU": gu}, suboptmax=1.0, suboptmin=1.0,
+                 minlen=float(rng.choice([2, 2, 3, 4, 4, 5])), minbpscore=rng.choice([2.0, 2.25, 3.0, 3.75, 4.5, 6.0, 7.0, 8.0]),
+                 minfinscorefactor=rng.choice([0.5, 0.75, 0.99, 1.0, 1.25, 1.5]), distcoef=rng.choice([0.0, 0.05, 0.09, 0.1, 0.2]),
+                 bracketweight=rng.choice([-2.0, -2.0, -1.0, 0.0, 1.0]), orderpenalty=rng.choice([0.0, 0.5, 0.75, 1.0, 1.35, 2.0]),
+                 loopbonus=rng.choice([0.0, 0.125, 0.125, 0.5, -0.1]), maxstemnum=rng.choice([1e6, 1e6, 1e6, 3.0, 1.0]))
+
+
+def rand_batch(rng):
+    seqs = []
+    for alphabet, lo, hi, count in (("ACGU", 5, 220, 14), ("GC", 20, 160, 4), ("GGCCAU", 30, 200, 4), ("ACGUN", 5, 120, 3),
+                                    ("GU", 20, 120, 2), ("AU", 20, 150, 2)):
+        seqs += [T.rand_seq(rng, rng.randint(lo, hi), alphabet) for _ in range(count)]
+    unit = T.rand_seq(rng, rng.randint(2, 9), "ACGU")
+    seqs.append((unit * 60)[:rng.randint(40, 200)])           # a low-complexity repeat
+    return seqs
+
+
+def check(ps, seqs, flavour, region, pcap, ccap):
+    r = emu.run(ps, seqs, ccap=ccap, flavour=flavour, region_mode=region, pcap=pcap)
+    for b, s in enumerate(seqs):
+        _, structs, _ = O.predict_short(s, [0.5] * len(s), "." * len(s), [ps], poollim=1)
+        dbn, sc, isint, _, stems, _, _ = structs[0]
+        o = r["dbn_off"][b]
+        got_stems = [tuple(int(x) for x in r["stems"][r["off"][b] + k]) for k in range(r["n"][b])]
+        got_sc = tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][b])
+        got_dbn = bytes(r["dbn_ascii"][o:o + len(s)]).decode()
+        if got_stems != stems or got_sc != sc or bool(r["flags"][b] & 1) != isint or (got_dbn != dbn and not r["flags"][b] & 2):
+            return dict(seq=s, paramset=ps, flavour=flavour, region=region, pcap=pcap, ccap=ccap, got=(got_stems, got_sc, got_dbn),
+                        want=(stems, sc, dbn))
+    return None
+
+
+def campaign(seed, rounds, verbose=False):
+    rng = random.Random(seed)
+    for k in range(rounds):
+        ps = rand_paramset(rng)
+        seqs = rand_batch(rng)
+        ccap = rng.choice([16, 64, 128])
+        for flavour, region, pcap in FLAVOURS:
+            bad = check(ps, seqs, flavour, region, pcap, ccap)
+            if bad:
+                return bad
+        if verbose:
+            print("round %d ok (%d sequences x %d flavours)" % (k, len(seqs), len(FLAVOURS)), flush=True)
+    return None
+
+
+def stems_of(r, k):
+    return [tuple(int(x) for x in r["stems"][r["off"][k] + q]) for q in range(r["n"][k])]
+
+
+def campaign_long(seed, rounds, verbose=False):
+    """150..500 nt: the global candidate list (prefix rounds, catch-up, rebuilds with a random period), its whole-list
+    flavour and the base-list sweep against the rescanning flavour on every sequence and the oracle on a sample"""
+    rng = random.Random(seed)
+    try:
+        for k in range(rounds):
+            ps = rand_paramset(rng)
+            seqs = [T.rand_seq(rng, rng.randint(150, 500), a) for a in ("ACGU",) * 5 + ("GC", "GGCCAU", "ACGUN")]
+            period = rng.choice([0, 1, 2, 3, 5, 7, 16])
+            emu.lib().emu_gl_set_rebuild(period)
+            ref = emu.run(ps, seqs, ccap=256, flavour=2)
+            for flavour, pcap in ((5, 1 << 20), (5, 3000), (8, 1 << 20), (6, 1 << 20)):
+                r = emu.run(ps, seqs, ccap=256, flavour=flavour, pcap=pcap)
+                for b in range(len(seqs)):
+                    if stems_of(r, b) != stems_of(ref, b) or not (r["raw"][b] == ref["raw"][b]).all():
+                        return dict(seq=seqs[b], paramset=ps, flavour=flavour, pcap=pcap, rebuild=period,
+                                    got=stems_of(r, b), want=stems_of(ref, b))
+            b = rng.randrange(len(seqs))
+            _, structs, _ = O.predict_short(seqs[b], [0.5] * len(seqs[b]), "." * len(seqs[b]), [ps], poollim=1)
+            if stems_of(ref, b) != structs[0][4]:
+                return dict(seq=seqs[b], paramset=ps, flavour=2, got=stems_of(ref, b), want=structs[0][4])
+            if verbose:
+                print("long round %d ok (rebuild period %d)" % (k, period), flush=True)
+    finally:
+        emu.lib().emu_gl_set_rebuild(0)
+    return None
+
+
+def campaign_extras(seed, rounds, verbose=False):
+    """restraints, reactivities, separators, interchainonly (run to completion) and single OptimalStems passes on
+    top of random pseudoknotted partial structures (the pool rounds), under random parameter sets"""
+    import numpy as np
+    from squarna_b200 import SQRNdbnseq as S
+    rng = random.Random(seed)
+    for k in range(rounds):
+        ps = rand_paramset(rng)
+        ps["suboptmax"] = ps["suboptmin"] = 1.0
+        interchain = rng.random() < 0.3
+        cases = [T.rand_case(rng, 8, 150, p_gap=0.2) for _ in range(16)]
+        preps = [S._prepare(c[0], c[1], c[2], None) for c in cases]
+        for comp in (False, True):
+            idx = [q for q, p in enumerate(preps) if p.compensated == comp]
+            if not idx:
+                continue
+            table, codes = {}, []
+            for q in idx:
+                codes.append(np.array([table.setdefault(float(x), len(table)) for x in preps[q].shortreacts], np.uint16))
+            kw = dict(react_codes=codes, react_values=np.array(list(table.keys())), restr_class=[preps[q].rclass for q in idx],
+                      rbps=[np.array(preps[q].rbps, np.int32).reshape(-1, 2) for q in idx])
+            for flavour, region in ((0, 1), (0, 2), (2, 0), (4, 0), (5, 0), (6, 0), (8, 0)):
+                r = emu.run(ps, [preps[q].shortseq for q in idx], react_comp=comp, interchainonly=interchain,
+                            region_mode=region, flavour=flavour, pcap=4096, **kw)
+                for b, q in enumerate(idx):
+                    p = preps[q]
+                    _, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, [ps], interchainonly=interchain,
+                                                    poollim=1, compensated_sum=comp)
+                    dbn, sc, isint, _, stems, _, _ = structs[0]
+                    if stems_of(r, b) != stems or tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][b]) != sc:
+                        return dict(case=cases[q], paramset=ps, flavour=flavour, region=region, interchain=interchain, comp=comp,
+                                    got=stems_of(r, b), want=stems)
+        # one OptimalStems pass on top of a random partial structure (maxstemnum is the pool loop's business, seq.py:1130:
+        # a structure that has reached it is not extended, so the device returns no candidates for it)
+        ps = dict(ps, maxstemnum=1e6)
+        for _ in range(10):
+            n = rng.randint(40, 180)
+            seq = T.rand_seq(rng, n, "ACGU" if rng.random() < 0.8 else "ACGU;")
+            subopt = rng.choice([0.2, 0.3, 0.5, 0.65, 0.9, 1.0])
+            used, stems = set(), []
+            for _ in range(rng.randint(1, 12)):
+                i, j, ln = rng.randrange(n), rng.randrange(n), rng.randint(1, 6)
+                if i > j:
+                    i, j = j, i
+                if j - i < 2 * ln + 2:
+                    continue
+                pos = set(range(i, i + ln)) | set(range(j - ln + 1, j + 1))
+                if pos & used or any(seq[p] == ";" for p in pos):
+                    continue
+                used |= pos
+                stems.append((i, j, ln))
+            _, chosen = O.optimal(seq, ps, subopt, selected=stems)
+            for flavour, region, ccap in ((0, 1, 4096), (0, 2, 4096), (6, 0, 4096)):
+                r = emu.run(ps, [seq], mode=emu.MODE_STEP, init_stems=[stems], item_subopt=[subopt], ccap=ccap, stem_cap=512,
+                            region_mode=region, flavour=flavour, pcap=1 << 15 if flavour == 6 else 0)
+                got = [(int(r["stems"][q][0]), int(r["stems"][q][1]), int(r["stems"][q][2]), float(r["fin"][q])) for q in range(r["n"][0])]
+                if got != chosen:
+                    return dict(seq=seq, stems=stems, subopt=subopt, paramset=ps, flavour=flavour, region=region, got=got, want=chosen)
+        if verbose:
+            print("extras round %d ok" % k, flush=True)
+    return None
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 3 and sys.argv[3] == "extras":
+        bad = campaign_extras(int(sys.argv[1]), int(sys.argv[2]), verbose=True)
+        print("DIFFERENCE: %r" % (bad,) if bad else "no difference")
+        sys.exit(1 if bad else 0)
+    if len(sys.argv) > 3 and sys.argv[3] == "long":
+        bad = campaign_long(int(sys.argv[1]), int(sys.argv[2]), verbose=True)
+        print("DIFFERENCE: %r" % (bad,) if bad else "no difference")
+        sys.exit(1 if bad else 0)
+
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    bad = campaign(seed, rounds, verbose=True)
+    print("DIFFERENCE: %r" % (bad,) if bad else "no difference in %d rounds (seed %d)" % (rounds, seed))
+    sys.exit(1 if bad else 0)

@@ -283,3 +283,14 @@ def test_device_code_on_long_reference_cases(flavour):
         assert S.ReAlign(short, p.seq) == want_dbn == c["cons"], (c["conf"], len(c["seq"]))
         got = tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][0])
         assert got == tuple(float(x) for x in want_sc) and bool(r["flags"][0] & 1) == (type(want_sc[1]) is int)
+
+
+def test_random_parameter_sets():
+    """a seeded slice of tests/fuzz_emu.py: random parameter sets (pair weights, minlen 2..5, thresholds, distance / order /
+    loop terms in and beyond the range of the shipped .conf files, small maxstemnum) for every list flavour, run to
+    completion, with restraints / reactivities / interchainonly, single OptimalStems passes on partial structures, and
+    150-500 nt through the global candidate list with random rebuild periods"""
+    from tests import fuzz_emu
+    assert fuzz_emu.campaign(20261018, 4) is None
+    assert fuzz_emu.campaign_extras(20261018, 2) is None
+    assert fuzz_emu.campaign_long(20261018, 2) is None
