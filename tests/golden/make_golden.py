@@ -390,6 +390,58 @@ def bpp_golden():
     dump("entropy_bpp.json", ent)
 
 
+def fuzz_golden(n_cases, n_keep, seed=20261018):
+    """the reference under RANDOM parameter sets (tests/fuzz_emu.rand_paramset: pair weights, minlen 2..5, thresholds,
+    distance / order / loop terms in and beyond the range of the shipped .conf files, small maxstemnum; 1-3 sets per
+    call with random subopt ranges) on rand_case inputs (gaps, separators, restraints, reactivities), random poollim:
+    every case is compared with the oracle HERE, the first n_keep are written to seq_api_fuzz.json"""
+    import time
+    from oracle import oracle as O
+    from tests.fuzz_emu import rand_paramset
+    rng = random.Random(seed)
+    cases, bad, t0 = [], 0, time.time()
+    while len(cases) < n_cases:
+        psets = []
+        for _ in range(rng.choice([1, 1, 2, 3])):
+            ps = rand_paramset(rng)
+            ps["suboptmax"] = rng.choice([1.0, 0.99, 0.95, 0.9, 0.8])
+            ps["suboptmin"] = min(ps["suboptmax"], rng.choice([1.0, 0.99, 0.9, 0.65, 0.5]))
+            ps["suboptsteps"] = float(rng.choice([1, 1, 2, 3]))
+            psets.append(ps)
+        pl = rng.choice([1, 1, 3, 20, 100])
+        seq, reacts, rest, kw = rand_case(rng, 8, 110)
+        if rng.random() < 0.25 and len(psets) > 1:
+            kw["priority"] = [rng.randrange(len(psets))]
+        try:
+            out = R.SQRNdbnseq(seq, reacts, rest, None, psets, mp=False, poollim=pl, algos={"G"},
+                               **{k: (set(v) if k == "priority" else v) for k, v in kw.items()})
+        except ZeroDivisionError:
+            continue
+        case = {"paramsets": [jsonable_ps(p) for p in psets], "poollim": pl, "seq": seq, "reacts": reacts, "restraints": rest,
+                "kw": kw, "smat": None, "cons": out[0], "structs": [[d, list(sc), list(ps)] for d, sc, ps in out[1]]}
+        cases.append(case)
+        okw = dict(kw)
+        okw["rankby"] = tuple(okw["rankby"])
+        cons, structs = O.sqrn_dbnseq(seq, reacts, rest, paramsets=psets, poollim=pl, **okw)
+        same = cons == out[0] and len(structs) == len(out[1]) and all(
+            d == gd and list(sc) == list(gsc) and psl == list(gpsl) and type(sc[1]) is type(gsc[1])
+            for (d, sc, psl), (gd, gsc, gpsl) in zip(structs, out[1]))
+        if not same:
+            bad += 1
+            print("ORACLE DIFFERS:", json.dumps(case)[:2000], flush=True)
+        if len(cases) % 200 == 0:
+            print("%d cases, %d differences, %.0f s" % (len(cases), bad, time.time() - t0), flush=True)
+    print("oracle against the reference under random parameter sets: %d cases, %d differences" % (len(cases), bad))
+    if n_keep:
+        dump("seq_api_fuzz.json", cases[:n_keep])
+    return bad
+
+
+if __name__ == "__main__" and "fuzz" in sys.argv[1:]:
+    k = sys.argv.index("fuzz")
+    sys.exit(1 if fuzz_golden(int(sys.argv[k + 1]), int(sys.argv[k + 2]) if len(sys.argv) > k + 2 else 0,
+                              int(sys.argv[k + 3]) if len(sys.argv) > k + 3 else 20261018) else 0)
+
 if __name__ == "__main__" and "bpp" in sys.argv[1:]:
     bpp_golden()
     sys.exit(0)

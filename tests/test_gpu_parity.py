@@ -403,6 +403,31 @@ def test_long_reference_cases(gpu_ctx):
     assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
 
 
+def test_reference_cases_under_random_parameter_sets(gpu_ctx):
+    """SQRNdbnseq on the reference's own outputs under RANDOM parameter sets (tests/golden/seq_api_fuzz.json: pair weights,
+    minlen 2..5, thresholds, distance / order / loop terms in and beyond the shipped .conf files, small maxstemnum, 1-3 sets
+    with random subopt ranges, random poollim; gaps, separators, restraints, reactivities): the kernels' pruning bounds
+    and list flavours must hold for any parameter values, not only the shipped ones"""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "seq_api_fuzz.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 250
+    bad = []
+    for c in cases:
+        kw = dict(c["kw"])
+        if "priority" in kw:
+            kw["priority"] = set(kw["priority"])
+        kw["rankby"] = tuple(kw["rankby"])
+        psets = [dict(p, algorithms=set(p["algorithms"])) for p in c["paramsets"]]
+        got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, psets, poollim=c["poollim"], algos={"G"}, **kw)
+        want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+        if not T.same_prediction((got[0], got[1]), want):
+            bad.append((c["seq"], c["paramsets"], c["kw"]))
+    assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+
+
 @pytest.mark.parametrize("cluster", [0, 1], ids=["clusters", "one-cta-each"])
 def test_rrna_scale_reference_cases(gpu_ctx, cluster):
     """plain sequences of 2050 .. 2500 nt against the real reference's own output (tests/golden/seq_api_xlong.json,

@@ -487,6 +487,25 @@ def test_sqrndbnseq_host_python_on_the_reference_cases(monkeypatch):
     assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
 
 
+def test_sqrndbnseq_host_python_on_random_parameter_sets(monkeypatch):
+    """the same on the reference's outputs under random parameter sets (tests/golden/seq_api_fuzz.json)"""
+    from tests import common as T
+    _stand_in(monkeypatch)
+    bad = []
+    cases = load("seq_api_fuzz.json")
+    for c in cases:
+        kw = dict(c["kw"])
+        if "priority" in kw:
+            kw["priority"] = set(kw["priority"])
+        kw["rankby"] = tuple(kw["rankby"])
+        psets = [dict(p, algorithms=set(p["algorithms"])) for p in c["paramsets"]]
+        got = S.SQRNdbnseq(c["seq"], c["reacts"], c["restraints"], None, psets, poollim=c["poollim"], algos={"G"}, **kw)
+        want = (c["cons"], [(d, tuple(sc), ps) for d, sc, ps in c["structs"]])
+        if not T.same_prediction((got[0], got[1]), want):
+            bad.append((c["seq"], c["kw"]))
+    assert not bad, "%d of %d differ; first: %r" % (len(bad), len(cases), bad[0])
+
+
 def _oracle_yield_many(entries, bpweights, interchainonly, minlen, minbpscore, device=0, matrix=None):
     """SQRNdbnali._yield_many with the oracle's AnnotateStems in place of the GPU call (matrix: the device-side sum of
     sqrn_stem_matrix_batch is stood in for by the host accumulation; the cells come back unsorted = None)"""

@@ -56,6 +56,24 @@ def test_seq_api(configs, fname, least):
             assert type(sc[1]) is type(gsc[1])
 
 
+def test_seq_api_random_parameter_sets():
+    """the same end-to-end comparison under RANDOM parameter sets (make_golden.py fuzz: pair weights, minlen 2..5,
+    thresholds, distance / order / loop terms in and beyond the range of the shipped .conf files, small maxstemnum, 1-3
+    sets per call with random subopt ranges, random poollim) -- 250 committed cases; the generating run compared 20 000"""
+    cases = load("seq_api_fuzz.json")
+    assert len(cases) >= 250 and sum(len(c["paramsets"]) > 1 for c in cases) > 50 and sum(c["poollim"] > 1 for c in cases) > 100
+    for c in cases:
+        kw = dict(c["kw"])
+        kw["rankby"] = tuple(kw["rankby"])
+        cons, structs = O.sqrn_dbnseq(c["seq"], c["reacts"], c["restraints"], paramsets=[_ps(p) for p in c["paramsets"]],
+                                      poollim=c["poollim"], **kw)
+        assert cons == c["cons"], c["seq"]
+        assert len(structs) == len(c["structs"]), c["seq"]
+        for (d, sc, psl), (gd, gsc, gpsl) in zip(structs, c["structs"]):
+            assert d == gd and list(sc) == gsc and psl == gpsl, (c["seq"], d, gd, sc, gsc)
+            assert type(sc[1]) is type(gsc[1])
+
+
 def test_annotate_stems():
     """BPMatrix + AnnotateStems: same stems, same order, same float64 scores"""
     for c in load("annotate.json"):
