@@ -129,6 +129,25 @@ def campaign_extras(seed, rounds, verbose=False):
                     if stems_of(r, b) != stems or tuple(emu.lib().emu_pyround3(float(x)) for x in r["raw"][b]) != sc:
                         return dict(case=cases[q], paramset=ps, flavour=flavour, region=region, interchain=interchain, comp=comp,
                                     got=stems_of(r, b), want=stems)
+        # AnnotateStems alone (alignment step 1, the non-greedy builders): every stem, in order, with its score
+        for comp in (False, True):
+            idx = [q for q, p in enumerate(preps) if p.compensated == comp]
+            if not idx:
+                continue
+            table, codes = {}, []
+            for q in idx:
+                codes.append(np.array([table.setdefault(float(x), len(table)) for x in preps[q].shortreacts], np.uint16))
+            r = emu.run(ps, [preps[q].shortseq for q in idx], mode=emu.MODE_YIELD, react_comp=comp, interchainonly=interchain,
+                        react_codes=codes, react_values=np.array(list(table.keys())), restr_class=[preps[q].rclass for q in idx],
+                        rbps=[np.array(preps[q].rbps, np.int32).reshape(-1, 2) for q in idx])
+            for b, q in enumerate(idx):
+                p = preps[q]
+                want = O.annotate(p.shortseq, ps, p.shortreacts, p.shortrest, interchainonly=interchain)
+                lo = r["off"][b]
+                got = [(int(r["stems"][lo + t][0]), int(r["stems"][lo + t][1]), int(r["stems"][lo + t][2]), float(r["fin"][lo + t]))
+                       for t in range(r["n"][b])]
+                if got != [tuple(x) for x in want]:
+                    return dict(case=cases[q], paramset=ps, mode="yield", interchain=interchain, got=got[:5], want=want[:5])
         # one OptimalStems pass on top of a random partial structure (maxstemnum is the pool loop's business, seq.py:1130:
         # a structure that has reached it is not extended, so the device returns no candidates for it)
         ps = dict(ps, maxstemnum=1e6)
