@@ -1003,19 +1003,35 @@ def RunSQRNdbnseq(name, sequence, reactivities, restraints,
 def RunSQRNdbnseqBatch(entries, paramsetnames, paramsets, rankbydiff, rankby, hardrest, interchainonly,
                        toplim, outplim, conslim, reactformat, evalonly, poollim=1000, sink=sys.stdout,
                        stemmatrix=None, algos={'G', }, priority=None, rfam=None, levellimit=None,
-                       entropy=False, M=1.8, B=-0.6, devices=None):
+                       entropy=False, M=1.8, B=-0.6, devices=None, header_on_error=True):
     """RunSQRNdbnseq for many entries [(name, seq, reacts, restraints, reference)]
     with ONE batched GPU call; text is written in input order (what the
     reference's ordered imap gives, SQUARNA.py:929-935)."""
+    priority_in = priority
     priority = _resolve_priority(priority, paramsetnames, rfam)
     preds = [None] * len(entries)
     ents = [None] * len(entries)
-    if entropy:                                                  # seq.py:1313-1318, before evalonly returns
-        ents = entropy_many([(e[1], e[2], e[3]) for e in entries], paramsets[0], interchainonly, stemmatrix, M=M, B=B)
-    if not evalonly:
-        preds = predict_many([(e[1], e[2], e[3], e[4]) for e in entries], paramsets, conslim, toplim,
-                             hardrest, rankbydiff, rankby, interchainonly, stemmatrix, poollim,
-                             frozenset(priority), frozenset(algos), levellimit=levellimit, M=M, B=B, devices=devices)
+    try:
+        if entropy:                                              # seq.py:1313-1318, before evalonly returns
+            ents = entropy_many([(e[1], e[2], e[3]) for e in entries], paramsets[0], interchainonly, stemmatrix, M=M, B=B)
+        if not evalonly:
+            preds = predict_many([(e[1], e[2], e[3], e[4]) for e in entries], paramsets, conslim, toplim,
+                                 hardrest, rankbydiff, rankby, interchainonly, stemmatrix, poollim,
+                                 frozenset(priority), frozenset(algos), levellimit=levellimit, M=M, B=B, devices=devices)
+    except Exception:
+        # An entry the prediction rejects.  The reference handles one entry at a time (SQUARNA.py:887-935), so it has
+        # printed every entry before the bad one, and that entry's own header (seq.py:1300-1345), when it raises:
+        # redo the batch entry by entry to fail at the same place.
+        if len(entries) == 1:
+            if not entropy and header_on_error:          # (byseq workers print into a buffer of their own, which is dropped)
+                _print_entry(*entries[0], reactformat, sink, rfam, None)
+            raise
+        out = []
+        for e in entries:
+            out += RunSQRNdbnseqBatch([e], paramsetnames, paramsets, rankbydiff, rankby, hardrest, interchainonly, toplim,
+                                      outplim, conslim, reactformat, evalonly, poollim, sink, stemmatrix, algos, priority_in,
+                                      rfam, levellimit, entropy, M, B, devices, header_on_error)
+        return out
     out = []
     for (name, seq, reacts, rests, ref), pred, ent in zip(entries, preds, ents):
         _print_entry(name, seq, reacts, rests, ref, reactformat, sink, rfam, ent)

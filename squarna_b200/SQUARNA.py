@@ -495,6 +495,7 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
 
     tables = [(paramsetnames, paramsets)] + (list(auto) if auto else [])
     pending = []
+    n_seen = n_printed = 0
 
     def flush():
         # entries of one flush share a config table; input order is preserved because a
@@ -502,12 +503,29 @@ def Predict(inputfile=None, fileformat="unknown", inputseq=None,
         if not pending:
             return
         names_, sets_ = tables[pending[0][0]]
+        nonlocal n_printed
+        n_printed += len(pending)
         RunSQRNdbnseqBatch([e[1] for e in pending], names_, sets_, rankbydiff, rankby, hardrest, interchainonly,
                            toplim, outplim, conslim, reactformat, evalonly, poollim, sink=write_to,
-                           algos=algos, priority=priority, rfam=None, levellimit=levellimit, entropy=entropy, M=M, B=B)
+                           algos=algos, priority=priority, rfam=None, levellimit=levellimit, entropy=entropy, M=M, B=B,
+                           header_on_error=not byseq)
         del pending[:]
 
-    for entry in inputs:
+    entries = iter(inputs)
+    while True:
+        try:
+            entry = next(entries)
+        except StopIteration:
+            break
+        except Exception:
+            # a line the parser rejects: the reference streams its input (SQUARNA.py:866-885) and has printed every
+            # entry before it; with byseq it prints in groups of threads * 10 entries (887-935): the full groups
+            if byseq:
+                group = max(int(threads), 1) * 10
+                del pending[max(n_seen // group * group - n_printed, 0):]
+            flush()
+            raise
+        n_seen += 1
         which = config_for(entry[1])
         if pending and (pending[0][0] != which or len(pending) >= BATCH_ENTRIES):
             flush()
