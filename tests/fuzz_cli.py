@@ -140,17 +140,23 @@ def rand_args(rng, alignment):
             args.append("c=" + rng.choice(["ali", "fastest", "greedynobpp"]))
         if rng.random() < 0.3:
             args.append("pl=%d" % rng.choice([1, 5, 50]))
+        if rng.random() < 0.15:
+            args.append("ent")
+        if rng.random() < 0.15:
+            args.append("ico")
         return args, None
     fmt = rng.choice([None, 3, 10, 26])
     args = ["c=" + rng.choice(["fastest", "greedynobpp", "alt", "500nobpp", "1000nobpp", "nobpp", "edmondsnobpp", "hungariannobpp",
                                "nussinovnobpp"])]
     if fmt:
         args.append("rf=%d" % fmt)
-    for flag, p in (("byseq", 0.3), ("hr", 0.2), ("ico", 0.15), ("eo", 0.08), ("iw", 0.2)):
+    for flag, p in (("byseq", 0.3), ("hr", 0.2), ("ico", 0.15), ("eo", 0.08), ("iw", 0.2), ("ent", 0.12)):
         if rng.random() < p:
             args.append(flag)
     for key, choices, p in (("pl", [1, 3, 20, 100], 0.6), ("tl", [1, 3, 5], 0.3), ("ol", [1, 2, 4], 0.3), ("cl", [1, 2, 3], 0.3),
-                            ("rb", ["r", "s", "d", "rs", "dsr", "sd"], 0.4), ("msn", [1, 3], 0.15), ("ll", [1, 2], 0.15)):
+                            ("rb", ["r", "s", "d", "rs", "dsr", "sd"], 0.4), ("msn", [1, 3], 0.15), ("ll", [1, 2], 0.15),
+                            ("algo", ["G", "N", "GE", "H"], 0.12), ("pr", ["defG1", "defG2,defG1", "fastestG", "nosuchset"], 0.1),
+                            ("if", ["qtrf", "qrtf", "qtr", "qr", "qf", "qt"], 0.15)):
         if rng.random() < p:
             args.append("%s=%s" % (key, rng.choice(choices)))
     return args, fmt
@@ -185,7 +191,7 @@ def campaign(seed, cases, verbose=True):
     H._stand_in(mp)
     mp.setattr(A, "_yield_many", H._oracle_yield_many)
     rng = random.Random(seed)
-    bad = 0
+    bad, outcomes, n_chars = 0, {}, 0
     try:
         with tempfile.TemporaryDirectory() as tmp:
             for k in range(cases):
@@ -204,6 +210,8 @@ def campaign(seed, cases, verbose=True):
                         sys.argv = saved
                 want = run_main(ref_main, args + ["t=1"], tmp)
                 got = run_main(CLI.Main, args + ["t=1"], tmp)
+                outcomes[want[0].split()[0]] = outcomes.get(want[0].split()[0], 0) + 1
+                n_chars += len(want[1])
                 if got != want:
                     bad += 1
                     print("DIFFERENCE #%d: args %r\n--- input\n%s--- reference (%s)\n%s--- ours (%s)\n%s" %
@@ -214,7 +222,7 @@ def campaign(seed, cases, verbose=True):
                     print("%d cases, %d differences" % (k + 1, bad), flush=True)
     finally:
         mp.undo()
-    print("CLI against the reference: %d differences" % bad)
+    print("CLI against the reference: %d differences; reference outcomes %r, %d characters of output compared" % (bad, outcomes, n_chars))
     return bad
 
 
