@@ -125,6 +125,9 @@ def rand_alignment(rng):
     return "\n".join(lines) + "\n"
 
 
+BPP_CONFIGS = False          # campaign(..., bpp=True): also the configs whose sets ask ViennaRNA for pair probabilities
+
+
 def rand_args(rng, alignment):
     if alignment:
         args = ["a"]
@@ -146,8 +149,10 @@ def rand_args(rng, alignment):
             args.append("ico")
         return args, None
     fmt = rng.choice([None, 3, 10, 26])
-    args = ["c=" + rng.choice(["fastest", "greedynobpp", "alt", "500nobpp", "1000nobpp", "nobpp", "edmondsnobpp", "hungariannobpp",
-                               "nussinovnobpp"])]
+    confs = ["fastest", "greedynobpp", "alt", "500nobpp", "1000nobpp", "nobpp", "edmondsnobpp", "hungariannobpp", "nussinovnobpp"]
+    if BPP_CONFIGS:
+        confs = ["def", "greedy", "500", "1000", "edmonds", "hungarian", "nussinov", "greedynobpp"]
+    args = ["c=" + rng.choice(confs)]
     if fmt:
         args.append("rf=%d" % fmt)
     for flag, p in (("byseq", 0.3), ("hr", 0.2), ("ico", 0.15), ("eo", 0.08), ("iw", 0.2), ("ent", 0.12)):
@@ -179,7 +184,9 @@ def run_main(main, args, cwd):
     return outcome, buf.getvalue()
 
 
-def campaign(seed, cases, verbose=True):
+def campaign(seed, cases, verbose=True, bpp=False):
+    global BPP_CONFIGS
+    BPP_CONFIGS = bpp
     from _pytest.monkeypatch import MonkeyPatch
     from squarna_b200 import SQRNdbnali as A
     from squarna_b200 import SQRNdbnseq as S
@@ -190,6 +197,10 @@ def campaign(seed, cases, verbose=True):
     H._OracleContext.fast_predict = H._oracle_fast_predict
     H._stand_in(mp)
     mp.setattr(A, "_yield_many", H._oracle_yield_many)
+    if bpp:                                   # tests/fake_rna.py stands in for ViennaRNA on both sides
+        from tests import fake_rna
+        sys.modules["RNA"] = fake_rna
+        S.set_rna_module(fake_rna)
     rng = random.Random(seed)
     bad, outcomes, n_chars = 0, {}, 0
     try:
@@ -222,9 +233,11 @@ def campaign(seed, cases, verbose=True):
                     print("%d cases, %d differences" % (k + 1, bad), flush=True)
     finally:
         mp.undo()
+        S.set_rna_module(None)
     print("CLI against the reference: %d differences; reference outcomes %r, %d characters of output compared" % (bad, outcomes, n_chars))
     return bad
 
 
 if __name__ == "__main__":
-    sys.exit(1 if campaign(int(sys.argv[1]) if len(sys.argv) > 1 else 1, int(sys.argv[2]) if len(sys.argv) > 2 else 100) else 0)
+    sys.exit(1 if campaign(int(sys.argv[1]) if len(sys.argv) > 1 else 1, int(sys.argv[2]) if len(sys.argv) > 2 else 100,
+                           bpp="bpp" in sys.argv[3:]) else 0)
