@@ -285,6 +285,24 @@ def UnAlign(seq, dbn):
     """remove gap columns (and the pairs that touch them) (seq.py:236-255)"""
     if not any(g in seq for g in GAPS):                    # nothing to remove (the usual single-sequence input)
         return seq, dbn
+    if len(seq) == len(dbn):
+        # byte arrays instead of per-character joins (alignment rows: hundreds of columns, thousands of rows)
+        try:
+            sraw = np.frombuffer(seq.encode("latin-1"), dtype=np.uint8)
+            draw = np.frombuffer(dbn.encode("latin-1"), dtype=np.uint8)
+        except UnicodeEncodeError:
+            sraw = None                                    # (Cyrillic brackets of deep pseudoknots, ...: the general path)
+        if sraw is not None:
+            gap = _GAP_BYTES[sraw]
+            pairs = _dbn_pairs(dbn)
+            if pairs:
+                pr = np.array(pairs, dtype=np.int64)
+                hit = gap[pr[:, 0]] | gap[pr[:, 1]]
+                if hit.any():
+                    draw = draw.copy()
+                    draw[pr[hit].ravel()] = 46             # '.'
+            keep = ~gap
+            return sraw[keep].tobytes().decode("latin-1"), draw[keep].tobytes().decode("latin-1")
     clean = list(dbn)
     for v, w in DBNToPairs(dbn):
         if seq[v] in GAPS or seq[w] in GAPS:
@@ -408,6 +426,7 @@ def _react_lut(M=1.8, B=1.6):
 _GAP_BYTES = np.zeros(256, dtype=bool)
 for _ch in GAPS:
     _GAP_BYTES[ord(_ch)] = True
+_GAP_DELETE = {ord(_ch): None for _ch in GAPS}      # str.translate: drop the gap symbols
 _RC_BYTES = np.zeros(256, dtype=np.uint8)
 _RC_BYTES[ord('_')] = _RC_BYTES[ord('+')] = 1
 _RC_BYTES[ord('/')] = 2
@@ -435,7 +454,7 @@ def _prepare(seq, reacts, restraints, dbn):
     p._keep = np.flatnonzero(~gapmask) if has_gaps else None         # None: identity
     # --- restraints -----------------------------------------------------------
     if not restraints:
-        p.shortseq = ''.join(seq[k] for k in p._keep) if has_gaps else seq
+        p.shortseq = seq.translate(_GAP_DELETE) if has_gaps else seq
         p.shortrest = '.' * len(p.shortseq)
         p.rbps = []
         p.rclass = np.zeros(len(p.shortseq), dtype=np.uint8)
@@ -463,10 +482,12 @@ def _prepare(seq, reacts, restraints, dbn):
         p._rl = letters[p._keep] if has_gaps else letters             # (their letters: _make_batch codes them without a sort)
         p.compensated = False
     else:
-        keep = p._keep if has_gaps else range(n)
-        p._sr = [reacts[k] for k in keep]
+        if has_gaps:
+            p._sr = [reacts[k] for k in p._keep.tolist()]
+        else:
+            p._sr = list(reacts) if n else []
         # builtin sum() in ScoreStruct compensates exact Python floats only (CPython >= 3.12)
-        p.compensated = all(type(x) is float for x in p._sr)
+        p.compensated = set(map(type, p._sr)) <= {float}
     p.dbn = dbn
     p.shortdbn = None
     if dbn:

@@ -802,3 +802,27 @@ def test_predict_many_result_assembly(monkeypatch):
             assert dbn == text(codes, seq), (seq, dbn, text(codes, seq))
             assert sc == (osc[0], 0 if isint else osc[1], osc[2]) and type(sc[1]) is (int if isint else float)
             assert inds == [b for b in range(3) if mask >> b & 1]
+
+
+def test_unalign_on_byte_arrays_equals_the_per_character_definition():
+    """UnAlign (seq.py:236-255) takes a byte-array path for latin-1 strings: against the per-character definition on
+    random gapped sequences with brackets of several kinds, pairs that touch gap columns, unmatched brackets; Cyrillic
+    brackets take the general path"""
+    import random
+    rng = random.Random(8)
+
+    def slow(seq, dbn):
+        clean = list(dbn)
+        for v, w in S.DBNToPairs(dbn):
+            if seq[v] in S.GAPS or seq[w] in S.GAPS:
+                clean[v] = clean[w] = '.'
+        keep = [k for k, ch in enumerate(seq) if ch not in S.GAPS]
+        return ''.join(seq[k] for k in keep), ''.join(clean[k] for k in keep)
+
+    for trial in range(400):
+        n = rng.randint(1, 80)
+        seq = "".join(rng.choice("ACGU-.~;") for _ in range(n))
+        alphabet = ".....([{<)]}>Aa_/+" + ("Бб" if trial % 10 == 0 else "")
+        dbn = "".join(rng.choice(alphabet) for _ in range(n))
+        assert S.UnAlign(seq, dbn) == slow(seq, dbn), (seq, dbn)
+    assert S.UnAlign("ACGU", "(..)") == ("ACGU", "(..)")
