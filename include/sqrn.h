@@ -235,6 +235,11 @@ SQRN_API int  sqrn_unpack_dbn(int64_t n_seqs, const uint32_t *offsets, const uin
  * PairsToDBN (SQRNdbnseq.py:142-143), threaded.  Levels 31..49 (Cyrillic brackets) come out as byte 0: the caller
  * prints those structures itself; levels beyond the alphabet are '.', as in the reference.                            */
 SQRN_API int  sqrn_codes_to_ascii(int64_t n, const int8_t *codes, uint8_t *ascii);
+/* DBNToPairs (SQRNdbnseq.py:172-207) on one dot-bracket line given as n code points: one stack per bracket kind, closing
+ * brackets without a partner ignored, pairs sorted by (i, j).  open_cp / close_cp: the n_kinds bracket glyphs (the
+ * alphabet of PairsToDBN, passed by the Python mirror); pairs [2 * (n / 2)] int32; host only.                         */
+SQRN_API int  sqrn_dbn_pairs(int64_t n, const uint32_t *text, int32_t n_kinds, const uint32_t *open_cp, const uint32_t *close_cp,
+                             int32_t *pairs, int64_t *n_pairs);
 /* Per-sequence flags of the last sqrn_fast_predict_host call (bit 1: more than 30 pseudoknot levels, the ASCII
  * glyphs ran out).  When that call returns SQRN_E_UNSUPPORTED for this reason every OTHER sequence's result is valid:
  * the flagged ones go through sqrn_predict_batch, whose level codes have no such limit.                              */

@@ -211,8 +211,18 @@ def DBNToPairs(dbn):
     return list(_dbn_pairs(dbn))
 
 
+_OPEN_CP = np.array([ord(c) for c in _OPEN], dtype=np.uint32)
+_CLOSE_CP = np.array([ord(c) for c in _CLOSE], dtype=np.uint32)
+
+
 @functools.lru_cache(maxsize=4096)
 def _dbn_pairs(dbn):
+    if len(dbn) >= 48:                  # long lines (alignment rows, rRNA restraints): the library's host-side parser
+        return _lib.dbn_pairs(dbn, _OPEN_CP, _CLOSE_CP)
+    return _dbn_pairs_py(dbn)
+
+
+def _dbn_pairs_py(dbn):
     stacks = {}
     pairs = set()
     # only bracket characters matter: a regular expression finds them (restraint lines are mostly dots)

@@ -22,7 +22,7 @@ EXPORTS = ["sqrn_abi_version", "sqrn_device_count", "sqrn_ctx_create", "sqrn_ctx
            "sqrn_fast_predict_host", "sqrn_fast_predict_device", "sqrn_ctx_last_stats", "sqrn_debug_run",
            "sqrn_ctx_set_tuning", "sqrn_text_parse", "sqrn_text_ungap", "sqrn_text_format",
            "sqrn_fast_predict_packed_host", "sqrn_pack_symbols", "sqrn_unpack_dbn", "sqrn_fast_last_flags",
-           "sqrn_stem_matrix_batch", "sqrn_fast_predict_packed_device", "sqrn_codes_to_ascii"]
+           "sqrn_stem_matrix_batch", "sqrn_fast_predict_packed_device", "sqrn_codes_to_ascii", "sqrn_dbn_pairs"]
 
 _lib = None
 
@@ -59,6 +59,7 @@ def load():
     L.sqrn_pack_symbols.argtypes = [i64, vp, vp, C.POINTER(i64)]
     L.sqrn_unpack_dbn.argtypes = [i64, vp, vp, vp]
     L.sqrn_codes_to_ascii.argtypes = [i64, vp, vp]
+    L.sqrn_dbn_pairs.argtypes = [i64, vp, C.c_int32, vp, vp, vp, C.POINTER(C.c_int64)]
     L.sqrn_fast_last_flags.argtypes = [vp, i64, vp]
     L.sqrn_stem_matrix_batch.argtypes = [vp, C.POINTER(ParamSet), C.POINTER(Batch), vp, C.c_double, i64, C.POINTER(i64), vp]
     L.sqrn_ctx_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
@@ -146,6 +147,19 @@ def pack_symbols(symbols):
     if rc != OK:
         raise SqrnError("sqrn_pack_symbols failed (%d)" % rc)
     return packed, bad.value
+
+
+def dbn_pairs(text, open_glyphs, close_glyphs):
+    """DBNToPairs (include/sqrn.h: sqrn_dbn_pairs) of one dot-bracket line -> tuple of (i, j), sorted; host only"""
+    L = load()
+    cp = np.frombuffer(text.encode("utf-32-le", "surrogatepass"), dtype=np.uint32)
+    pairs = np.empty(max(len(cp) // 2, 1) * 2, np.int32)
+    m = C.c_int64(0)
+    rc = L.sqrn_dbn_pairs(len(cp), ptr(cp), len(open_glyphs), ptr(open_glyphs), ptr(close_glyphs), ptr(pairs), C.byref(m))
+    if rc != OK:
+        raise SqrnError("sqrn_dbn_pairs failed (%d)" % rc)
+    flat = pairs[:2 * m.value].tolist()
+    return tuple(zip(flat[0::2], flat[1::2]))
 
 
 def codes_to_ascii(codes):

@@ -371,6 +371,44 @@ extern "C" int sqrn_pack_symbols(int64_t n_total, const uint8_t *symbols, uint8_
     return SQRN_OK;
 }
 
+// DBNToPairs (SQRNdbnseq.py:172-207): one stack per bracket kind, closing brackets without a partner are ignored,
+// pairs sorted.  text = n code points; open_cp / close_cp = the n_kinds bracket glyphs of PairsToDBN's alphabet (passed in:
+// the alphabet lives in the Python mirror).  pairs must hold n / 2 pairs.
+extern "C" int sqrn_dbn_pairs(int64_t n, const uint32_t *text, int32_t n_kinds, const uint32_t *open_cp, const uint32_t *close_cp,
+                              int32_t *pairs, int64_t *n_pairs)
+{
+    if (n < 0 || n > 0x7fffffff || n_kinds < 0 || n_kinds > 127 || !n_pairs || (n && (!text || !pairs)) || (n_kinds && (!open_cp || !close_cp)))
+        return SQRN_E_BADARG;
+    try {
+        int8_t ascii[128];                          // +k+1: opening bracket of kind k, -(k+1): closing
+        memset(ascii, 0, sizeof ascii);
+        for (int k = 0; k < n_kinds; k++) {
+            if (open_cp[k] < 128) ascii[open_cp[k]] = (int8_t)(k + 1);
+            if (close_cp[k] < 128) ascii[close_cp[k]] = (int8_t)-(k + 1);
+        }
+        std::vector<std::vector<int32_t>> stack((size_t)n_kinds);
+        std::vector<std::pair<int32_t, int32_t>> found;
+        for (int64_t p = 0; p < n; p++) {
+            const uint32_t c = text[p];
+            int kind = 0;
+            if (c < 128) kind = ascii[c];
+            else for (int k = 0; k < n_kinds; k++) {
+                if (c == open_cp[k]) { kind = k + 1; break; }
+                if (c == close_cp[k]) { kind = -(k + 1); break; }
+            }
+            if (kind > 0) stack[(size_t)kind - 1].push_back((int32_t)p);
+            else if (kind < 0 && !stack[(size_t)(-kind) - 1].empty()) {
+                found.emplace_back(stack[(size_t)(-kind) - 1].back(), (int32_t)p);
+                stack[(size_t)(-kind) - 1].pop_back();
+            }
+        }
+        std::sort(found.begin(), found.end());
+        for (size_t k = 0; k < found.size(); k++) { pairs[2 * k] = found[k].first; pairs[2 * k + 1] = found[k].second; }
+        *n_pairs = (int64_t)found.size();
+    } catch (...) { return SQRN_E_NOMEM; }
+    return SQRN_OK;
+}
+
 extern "C" int sqrn_codes_to_ascii(int64_t n, const int8_t *codes, uint8_t *ascii)
 {
     if (n < 0 || (n && (!codes || !ascii))) return SQRN_E_BADARG;

@@ -826,3 +826,21 @@ def test_unalign_on_byte_arrays_equals_the_per_character_definition():
         dbn = "".join(rng.choice(alphabet) for _ in range(n))
         assert S.UnAlign(seq, dbn) == slow(seq, dbn), (seq, dbn)
     assert S.UnAlign("ACGU", "(..)") == ("ACGU", "(..)")
+
+
+def test_dbn_pairs_in_the_library_equals_the_python_parser():
+    """long dot-bracket lines are parsed by sqrn_dbn_pairs (host only): the same pairs as the Python restatement of
+    DBNToPairs (seq.py:172-207) -- every bracket kind incl. the Cyrillic ones, unmatched brackets of both directions"""
+    import random
+    rng = random.Random(4)
+    alphabet = "....." + S._OPEN + S._CLOSE + "_/+-;&?"
+    f = S._dbn_pairs.__wrapped__
+    for trial in range(1500):
+        n = rng.randint(48, 300)
+        kinds = rng.randint(1, 12)
+        sub = "....." + "".join(rng.sample(S._OPEN, kinds)) + "_/+"
+        sub += "".join(S._CLOSE[S._OPEN.index(c)] for c in sub if c in S._OPEN) + rng.choice(alphabet)
+        line = "".join(rng.choice(sub) for _ in range(n))
+        assert f(line) == S._dbn_pairs_py(line), line
+    assert f("." * 60) == () and f("(" * 30 + ")" * 30) == tuple((k, 59 - k) for k in range(30))
+    assert S.DBNToPairs(")" * 50 + "(" * 50) == []
