@@ -961,12 +961,15 @@ def _print_entry(name, sequence, reactivities, restraints, reference, reactforma
         print(sequence, file=sink)
     if reactivities:
         print(EncodedReactivities(sequence, reactivities, reactformat), "reactivities", sep='\t', file=sink)
+    def with_separators(line):                   # the chain separators of the sequence shine through (seq.py:1326-1341)
+        if len(line) == len(sequence) and ';' not in sequence and '&' not in sequence:
+            return line
+        return ''.join(sequence[k] if sequence[k] in SEPS else line[k] for k in range(len(sequence)))
+
     if restraints:
-        print(''.join(sequence[k] if sequence[k] in SEPS else restraints[k] for k in range(len(sequence))),
-              "restraints" + ("(" + rfam + ")" if rfam else ""), sep='\t', file=sink)
+        print(with_separators(restraints), "restraints" + ("(" + rfam + ")" if rfam else ""), sep='\t', file=sink)
     if reference:
-        print(''.join(sequence[k] if sequence[k] in SEPS else reference[k] for k in range(len(sequence))),
-              "reference", *ReferenceScores(sequence, reference, reactivities), sep='\t', file=sink)
+        print(with_separators(reference), "reference", *ReferenceScores(sequence, reference, reactivities), sep='\t', file=sink)
     print('_' * len(sequence), file=sink)
 
 
