@@ -570,17 +570,34 @@ def _bulk_lane(path, multiline, psname, paramset, conslim, sink, device=None, sl
     if deep and per_entry is None:
         return False
     binary = getattr(sink, "buffer", None)
-    scratch = []                                                     # one text buffer, reused by every slice
+    scratch = [[], []]                                               # two text buffers, reused by every other slice
 
     def emit(first, stop):
-        for lo in range(first, stop, slice_entries):
-            count = min(slice_entries, stop - lo)
-            block = _lib.text_format(parsed, lo, count, sym_off, dbn, scores, conslim, psname, scratch)
-            if binary is not None:
-                sink.flush()
-                binary.write(memoryview(block))
-            else:
-                sink.write(block.tobytes().decode("ascii"))
+        # slice k + 1 is formatted (library threads) while a writer thread hands slice k to the file: both release the GIL
+        writer = pending = None
+        try:
+            for k, lo in enumerate(range(first, stop, slice_entries)):
+                count = min(slice_entries, stop - lo)
+                block = _lib.text_format(parsed, lo, count, sym_off, dbn, scores, conslim, psname, scratch[k & 1])
+                if binary is None:
+                    sink.write(block.tobytes().decode("ascii"))
+                    continue
+                if pending is not None:
+                    pending.result()                                 # (its buffer is the one the next slice will reuse)
+                elif stop - lo > slice_entries:
+                    from concurrent.futures import ThreadPoolExecutor
+                    writer = ThreadPoolExecutor(1)
+                    sink.flush()
+                if writer is None:
+                    sink.flush()
+                    binary.write(memoryview(block))
+                else:
+                    pending = writer.submit(binary.write, memoryview(block))
+            if pending is not None:
+                pending.result()
+        finally:
+            if writer is not None:
+                writer.shutdown(wait=True)
 
     at = 0
     for e in deep:

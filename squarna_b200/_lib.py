@@ -82,13 +82,20 @@ def text_parse(text, multiline):
     (the caller then takes the per-entry path)."""
     L = load()
     n, tot = C.c_int64(0), C.c_int64(0)
-    cap_e, cap_s = text.count(b">") + 1, len(text) + 1
-    name_begin = np.empty(cap_e, np.int64)
-    name_len = np.empty(cap_e, np.int32)
-    seq_off = np.empty(cap_e + 1, np.int64)
+    # entry capacity: a guess (counting the '>' of a 140 MB file in Python took longer than parsing it); the library
+    # counts first and reports SQRN_E_CAPACITY with the exact number when the guess was too small
+    cap_e, cap_s = len(text) // 24 + 16, len(text) + 1
     seq = np.empty(cap_s, np.uint8)
-    rc = L.sqrn_text_parse(text, len(text), int(bool(multiline)), C.byref(n), C.byref(tot), cap_e, cap_s,
-                           ptr(name_begin), ptr(name_len), ptr(seq_off), ptr(seq))
+    while True:
+        name_begin = np.empty(cap_e, np.int64)
+        name_len = np.empty(cap_e, np.int32)
+        seq_off = np.empty(cap_e + 1, np.int64)
+        rc = L.sqrn_text_parse(text, len(text), int(bool(multiline)), C.byref(n), C.byref(tot), cap_e, cap_s,
+                               ptr(name_begin), ptr(name_len), ptr(seq_off), ptr(seq))
+        if rc == E_CAPACITY and n.value > cap_e and tot.value <= cap_s:
+            cap_e = n.value
+            continue
+        break
     if rc != OK:
         return None
     out = ParsedText()

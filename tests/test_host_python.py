@@ -844,3 +844,47 @@ def test_dbn_pairs_in_the_library_equals_the_python_parser():
         assert f(line) == S._dbn_pairs_py(line), line
     assert f("." * 60) == () and f("(" * 30 + ")" * 30) == tuple((k, 59 - k) for k in range(30))
     assert S.DBNToPairs(")" * 50 + "(" * 50) == []
+
+
+def test_bulk_text_parse_with_more_entries_than_guessed():
+    """text_parse guesses the entry capacity from the text length; very short entries take the retry with the exact count"""
+    from squarna_b200 import _lib
+    for fasta in (False, True):
+        text = b"".join(b">e%d\n%s\n" % (k, b"ACGU"[k % 4:k % 4 + 1]) for k in range(3000))
+        parsed = _lib.text_parse(text, fasta)
+        assert parsed is not None and parsed.n == 3000
+        assert bytes(parsed.seq) == b"".join(b"ACGU"[k % 4:k % 4 + 1] for k in range(3000))
+        assert parsed.seq_offsets.tolist() == list(range(3001))
+        assert [int(parsed.name_len[k]) for k in (0, 10, 2999)] == [3, 4, 6]      # ">e0", ">e10", ">e2999"
+
+
+def test_bulk_lane_writes_slices_through_the_writer_thread(tmp_path, monkeypatch):
+    """a binary sink and more entries than one slice: slices are formatted while the previous one is being written
+    (two alternating buffers, one writer thread) -- the file must equal the one-slice text, also around an entry that is
+    handed to the per-entry path in the middle"""
+    import numpy as np
+    import random
+
+    class Stub:
+        def fast_predict(self, ps, sym, off):
+            n = len(off) - 1
+            nst = np.ones(n, np.int32)
+            nst[37] = -1                                     # "more than 30 pseudoknot levels": the per-entry path prints it
+            return np.full(len(sym), ord("."), np.uint8), np.tile([1.5, 3.0, 0.5], (n, 1)), nst
+
+    monkeypatch.setattr(S, "get_context", lambda device=0: Stub())
+    rng = random.Random(12)
+    path = tmp_path / "in.fa"
+    path.write_text("".join(">s%d\n%s\n" % (k, "".join(rng.choice("ACGU") for _ in range(rng.randint(5, 60)))) for k in range(101)))
+    texts = []
+    for slice_entries in (1000, 7, 1):
+        out = tmp_path / ("out%d.txt" % slice_entries)
+        with open(out, "w") as sink:
+            sink.write("header\n")                           # text written before the lane starts must stay in front
+            assert CLI._bulk_lane(str(path), True, "fastestG", {"dummy": 1}, 1, sink, slice_entries=slice_entries,
+                                  per_entry=lambda entries: print("<entry %s>" % entries[0][0], file=sink))
+            sink.write("trailer\n")
+        texts.append(out.read_text())
+    assert texts[0] == texts[1] == texts[2]
+    assert texts[0].startswith("header\n>s0\n") and texts[0].endswith("trailer\n") and "<entry >s37>" in texts[0]
+    assert texts[0].index(">s36\n") < texts[0].index("<entry >s37>") < texts[0].index(">s38\n")
