@@ -413,7 +413,7 @@ def test_reference_cases_under_random_parameter_sets(gpu_ctx):
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, "golden", "seq_api_fuzz.json")) as f:
         cases = json.load(f)
-    assert len(cases) >= 250
+    assert len(cases) >= 1000
     bad = []
     for c in cases:
         kw = dict(c["kw"])
