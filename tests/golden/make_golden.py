@@ -390,7 +390,7 @@ def bpp_golden():
     dump("entropy_bpp.json", ent)
 
 
-def fuzz_golden(n_cases, n_keep, seed=20261018):
+def fuzz_golden(n_cases, n_keep, seed=20261018, lo=8, hi=110):
     """the reference under RANDOM parameter sets (tests/fuzz_emu.rand_paramset: pair weights, minlen 2..5, thresholds,
     distance / order / loop terms in and beyond the range of the shipped .conf files, small maxstemnum; 1-3 sets per
     call with random subopt ranges) on rand_case inputs (gaps, separators, restraints, reactivities), random poollim:
@@ -409,7 +409,9 @@ def fuzz_golden(n_cases, n_keep, seed=20261018):
             ps["suboptsteps"] = float(rng.choice([1, 1, 2, 3]))
             psets.append(ps)
         pl = rng.choice([1, 1, 3, 20, 100])
-        seq, reacts, rest, kw = rand_case(rng, 8, 110)
+        seq, reacts, rest, kw = rand_case(rng, lo, hi)
+        if hi > 200:
+            pl = min(pl, 3)                          # (the reference needs minutes per pool at these lengths)
         if rng.random() < 0.25 and len(psets) > 1:
             kw["priority"] = [rng.randrange(len(psets))]
         try:
@@ -429,7 +431,7 @@ def fuzz_golden(n_cases, n_keep, seed=20261018):
         if not same:
             bad += 1
             print("ORACLE DIFFERS:", json.dumps(case)[:2000], flush=True)
-        if len(cases) % 200 == 0:
+        if len(cases) % (200 if hi <= 200 else 10) == 0:
             print("%d cases, %d differences, %.0f s" % (len(cases), bad, time.time() - t0), flush=True)
     print("oracle against the reference under random parameter sets: %d cases, %d differences" % (len(cases), bad))
     if n_keep:
@@ -440,7 +442,9 @@ def fuzz_golden(n_cases, n_keep, seed=20261018):
 if __name__ == "__main__" and "fuzz" in sys.argv[1:]:
     k = sys.argv.index("fuzz")
     sys.exit(1 if fuzz_golden(int(sys.argv[k + 1]), int(sys.argv[k + 2]) if len(sys.argv) > k + 2 else 0,
-                              int(sys.argv[k + 3]) if len(sys.argv) > k + 3 else 20261018) else 0)
+                              int(sys.argv[k + 3]) if len(sys.argv) > k + 3 else 20261018,
+                              int(sys.argv[k + 4]) if len(sys.argv) > k + 4 else 8,
+                              int(sys.argv[k + 5]) if len(sys.argv) > k + 5 else 110) else 0)
 
 if __name__ == "__main__" and "bpp" in sys.argv[1:]:
     bpp_golden()
