@@ -97,7 +97,7 @@ def campaign_long(seed, rounds, verbose=False):
     return None
 
 
-def campaign_extras(seed, rounds, verbose=False):
+def campaign_extras(seed, rounds, verbose=False, len_lo=8, len_hi=150):
     """restraints, reactivities, separators, interchainonly (run to completion) and single OptimalStems passes on
     top of random pseudoknotted partial structures (the pool rounds), under random parameter sets"""
     import numpy as np
@@ -107,7 +107,7 @@ def campaign_extras(seed, rounds, verbose=False):
         ps = rand_paramset(rng)
         ps["suboptmax"] = ps["suboptmin"] = 1.0
         interchain = rng.random() < 0.3
-        cases = [T.rand_case(rng, 8, 150, p_gap=0.2) for _ in range(16)]
+        cases = [T.rand_case(rng, len_lo, len_hi, p_gap=0.2) for _ in range(16 if len_hi <= 150 else 6)]
         preps = [S._prepare(c[0], c[1], c[2], None) for c in cases]
         for comp in (False, True):
             idx = [q for q, p in enumerate(preps) if p.compensated == comp]
@@ -120,7 +120,7 @@ def campaign_extras(seed, rounds, verbose=False):
                       rbps=[np.array(preps[q].rbps, np.int32).reshape(-1, 2) for q in idx])
             for flavour, region in ((0, 1), (0, 2), (2, 0), (4, 0), (5, 0), (6, 0), (8, 0)):
                 r = emu.run(ps, [preps[q].shortseq for q in idx], react_comp=comp, interchainonly=interchain,
-                            region_mode=region, flavour=flavour, pcap=4096, **kw)
+                            region_mode=region, flavour=flavour, pcap=4096 if len_hi <= 150 else 1 << 16, **kw)
                 for b, q in enumerate(idx):
                     p = preps[q]
                     _, structs, _ = O.predict_short(p.shortseq, p.shortreacts, p.shortrest, [ps], interchainonly=interchain,
@@ -181,7 +181,8 @@ def campaign_extras(seed, rounds, verbose=False):
 
 if __name__ == "__main__":
     if len(sys.argv) > 3 and sys.argv[3] == "extras":
-        bad = campaign_extras(int(sys.argv[1]), int(sys.argv[2]), verbose=True)
+        bad = campaign_extras(int(sys.argv[1]), int(sys.argv[2]), verbose=True, len_lo=int(sys.argv[4]) if len(sys.argv) > 4 else 8,
+                              len_hi=int(sys.argv[5]) if len(sys.argv) > 5 else 150)
         print("DIFFERENCE: %r" % (bad,) if bad else "no difference")
         sys.exit(1 if bad else 0)
     if len(sys.argv) > 3 and sys.argv[3] == "long":
